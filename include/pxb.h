@@ -1,0 +1,303 @@
+/*
+ * pxb.h -- C ABI of libpxb, the sm_100a photon-generation / photon-projection hot path.
+ *
+ * This is the drop-in boundary for pyXSIM's native + NumPy hot path.  Every entry point
+ * names the reference interface it replaces (paths relative to the pyXSIM tree):
+ *
+ *   pxb_model_create ............ SpectralInterpolator1D/2D construction,
+ *                                 pyxsim/spectral_models.py:22-62 (tables come from
+ *                                 TableCIEModel.prepare_spectrum :253-263 /
+ *                                 PionSpectralModel.prepare_spectrum :413-427)
+ *   pxb_interp_spec ............. interp1d_spec / interp2d_spec,
+ *                                 pyxsim/lib/interpolate.pyx:10-58 / :64-143 (bit-exact)
+ *   pxb_thermal_spectra ......... get_spectrum + abundance combine + clip,
+ *                                 pyxsim/source_models/thermal_sources/base.py:453-460
+ *   pxb_thermal_counts .......... cut mask, cell_nrm, spec_sum, Poisson counts,
+ *                                 base.py:335-354,423-425,463-468
+ *   pxb_scan_counts ............. the implicit running cursor `ei`/`end_e`, base.py:474-491,
+ *                                 and active-cell selection, base.py:517-520
+ *   pxb_compact_cells ........... gather/unwrap/recentre of active cells,
+ *                                 pyxsim/photon_list.py:423-451
+ *   pxb_thermal_sample .......... per-cell CDF + inverse-CDF sampling, base.py:471-491,522-523
+ *   pxb_powerlaw_counts/sample .. pyxsim/source_models/power_law_sources.py:186-250
+ *   pxb_line_counts/sample ...... pyxsim/source_models/line_sources.py:193-234
+ *   pxb_radius2 ................. SourceModel.compute_radius, source_models/sources.py:77-87
+ *   pxb_doppler_shift ........... doppler_shift, pyxsim/lib/sky_functions.pyx:20-34
+ *   pxb_pixel_to_cel ............ pixel_to_cel, sky_functions.pyx:153-179
+ *   pxb_absorb_transmission ..... AbsorptionModel.get_absorb, spectral_models.py:556-561
+ *                                 (+ soxs get_wabs_absorb used by WabsModel :633-635)
+ *   pxb_project ................. the projection tile loop, photon_list.py:686-799:
+ *                                 doppler_shift + absorb_photons (spectral_models.py:563-583)
+ *                                 + scatter_events (sky_functions.pyx:40-147) or
+ *                                 scatter_events_allsky (:185-250) + sigma_pos + /D_A +
+ *                                 flat-sky | pixel_to_cel + eobs[det] + flux/emin/emax
+ *
+ * Conventions
+ *   - All array pointers are DEVICE pointers unless a field says "host".
+ *   - Sizes are explicit int64 element counts.  `stream` is a cudaStream_t passed as void*.
+ *   - Every function returns 0 on success and a negative pxb_status on failure;
+ *     pxb_last_error() returns a thread-local message.  No exceptions cross the ABI.
+ *   - The caller owns every buffer (two-phase count -> scan -> fill for variable-length
+ *     outputs); the only library-owned memory is the table model behind pxb_model.
+ *   - Deterministic: outputs are a pure function of (inputs, seed, cell_id0).
+ */
+#ifndef PXB_H
+#define PXB_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PXB_MAX_VAR 64
+
+enum pxb_status {
+  PXB_OK = 0,
+  PXB_ERR_INVALID = -1,   /* bad argument */
+  PXB_ERR_CUDA = -2,      /* CUDA runtime error (message has the cudaError string) */
+  PXB_ERR_UNSUPPORTED = -3,
+  PXB_ERR_NO_DEVICE = -4
+};
+
+const char* pxb_last_error(void);
+int pxb_version(void);
+/* sm count / compute capability of the current device */
+int pxb_device_info(int* sm_count, int* cc_major, int* cc_minor);
+/* sizeof() of pxb_table_desc, pxb_model_desc, pxb_thermal_cells, pxb_geometry,
+ * pxb_powerlaw_cells, pxb_line_cells, pxb_photon_list, pxb_project_params (in that order);
+ * returns the number of entries written.  Lets a binding verify its struct layout. */
+int pxb_struct_sizes(int64_t* out, int n);
+
+/* ------------------------------------------------------------------------------------
+ * Thermal spectral tables
+ * ---------------------------------------------------------------------------------- */
+typedef struct {
+  int32_t nx;            /* number of temperature nodes (0 => table absent) */
+  int32_t ny;            /* number of density nodes, 0 => 1-D table */
+  int32_t nbins;
+  int32_t nvar;
+  const double* xnodes;  /* host [nx] */
+  const double* ynodes;  /* host [ny] or NULL */
+  const double* cosmic;  /* host [max(ny,1)*nx, nbins], row = nx*y_i + x_i */
+  const double* metal;   /* host, same shape */
+  const double* var;     /* host [nvar, rows, nbins] or NULL */
+} pxb_table_desc;
+
+typedef struct {
+  pxb_table_desc primary;
+  pxb_table_desc fallback;    /* 1-D table used outside the primary's (kT,nH) bounds */
+  int32_t log_t;              /* primary coordinate is log10(kT*K_per_keV) (y: log10 nH) */
+  int32_t fallback_log_t;
+  int32_t density_dependent;  /* 2-D lookup, result divided by nH */
+  int32_t binscale_log;       /* bin_edges are log10(ebins); sampled energies are 10**E */
+  int32_t method;             /* 0 invert_cdf, 1 accept_reject (bin centres) */
+  int32_t reserved;
+  double K_per_keV;
+  double kT_lo, kT_hi, nH_lo, nH_hi; /* bounds of the primary 2-D table (use_igm mask) */
+  const double* bin_edges;    /* host [nbins+1] */
+  const double* emid;         /* host [nbins] */
+} pxb_model_desc;
+
+typedef struct pxb_model pxb_model;
+
+int pxb_model_create(const pxb_model_desc* desc, pxb_model** out);
+int pxb_model_destroy(pxb_model* model);
+/* 1 when every table entry is >= 0 (the O(1) row-sum / mixture fast paths are legal) */
+int pxb_model_nonnegative(const pxb_model* model);
+
+/* Per-chunk inputs of the thermal source (all per-cell arrays are device, length ncell). */
+typedef struct {
+  int64_t ncell;
+  int64_t cell_id0;            /* global id of cell 0: RNG counters use cell_id0 + i */
+  const double* kT;            /* keV */
+  const double* em;            /* emission measure, cm^-3 */
+  const double* nH;            /* H nuclei density cm^-3, or NULL */
+  const double* zmet;          /* metallicity field or NULL -> zmet_const */
+  const double* xh;            /* hydrogen mass fraction field or NULL -> xh_const */
+  const double* density;       /* NULL -> no max_density cut */
+  const double* entropy;       /* NULL -> no min_entropy cut */
+  const double* r2;            /* cm^2, internal observer (cell_nrm /= r2) or NULL */
+  const double* elem[PXB_MAX_VAR];   /* per-element abundance field or NULL -> elem_const[k] */
+  double elem_const[PXB_MAX_VAR];
+  double elem_scale[PXB_MAX_VAR];    /* mconvert factor (1 when already Zsun) */
+  int32_t elem_by_xh[PXB_MAX_VAR];   /* divide the factor by X_H */
+  double zmet_const;
+  double zmet_scale;           /* Zconvert (1 when already Zsun) */
+  int32_t zmet_by_xh;
+  int32_t nvar;
+  double xh_const;
+  double spectral_norm;
+  double kT_min, kT_max;
+  double max_density, min_entropy;
+  uint64_t seed;
+} pxb_thermal_cells;
+
+/* lambda_out (nullable) receives spec_sum*cell_nrm, counts_out the Poisson draws.
+ * Cells failing the cut get lambda = 0, count = 0. */
+int pxb_thermal_counts(const pxb_model* model, const pxb_thermal_cells* cells,
+                       double* lambda_out, int64_t* counts_out, void* stream);
+
+/* Test/diagnostic: clipped total spectrum of every cell, spec_out[ncell, nbins]. */
+int pxb_thermal_spectra(const pxb_model* model, const pxb_thermal_cells* cells,
+                        double* spec_out, void* stream);
+
+/* Bit-exact replacement of interp1d_spec / interp2d_spec on the model's PRIMARY table.
+ * x_vals/y_vals are table coordinates (already log10 when the model is log_t), x_is/y_is
+ * the clamped node indices; outputs c,m [n, nbins], v [nvar, n, nbins] (nullable). */
+int pxb_interp_spec(const pxb_model* model, int64_t n, const double* x_vals,
+                    const int32_t* x_is, const double* y_vals, const int32_t* y_is,
+                    double* c_out, double* m_out, double* v_out, void* stream);
+
+/* Inverse-CDF energy sampling for the active cells.  idx[k] is the chunk-local cell index,
+ * nph[k] its photon count, poff[k] its first slot in `energies`. */
+int pxb_thermal_sample(const pxb_model* model, const pxb_thermal_cells* cells,
+                       int64_t n_active, const int64_t* idx, const int64_t* nph,
+                       const int64_t* poff, int64_t n_photons, double* energies,
+                       void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * Counts -> offsets, active-cell compaction
+ * ---------------------------------------------------------------------------------- */
+int pxb_scan_workspace_bytes(int64_t n, int64_t* bytes);
+/* offsets[n+1]: exclusive prefix of counts; arank[n+1]: exclusive prefix of (counts>0);
+ * totals[2] (device) = {sum(counts), number of active cells}. */
+int pxb_scan_counts(const int64_t* counts, int64_t n, int64_t* offsets, int64_t* arank,
+                    int64_t* totals, void* workspace, int64_t workspace_bytes, void* stream);
+
+typedef struct {
+  double c[3];        /* centre, kpc */
+  double le[3], re[3], dw[3]; /* object bounds and domain width, kpc */
+  double bulk_v[3];   /* km/s */
+  int32_t periodic[3];
+  int32_t reserved;
+} pxb_geometry;
+
+/* Gather the active cells: idx/nph/poff plus recentred, periodically unwrapped positions
+ * (photon_list.py:423-451) and bulk-subtracted velocities.  dx may be NULL (point sources). */
+int pxb_compact_cells(int64_t n, const int64_t* counts, const int64_t* offsets,
+                      const int64_t* arank, const double* x, const double* y, const double* z,
+                      const double* vx, const double* vy, const double* vz, const double* dx,
+                      const pxb_geometry* geom, int64_t* idx_out, int64_t* nph_out,
+                      int64_t* poff_out, double* xo, double* yo, double* zo, double* vxo,
+                      double* vyo, double* vzo, double* dxo, void* stream);
+
+/* r2[i] = |pos - c|^2 * cm2_per_kpc2 with periodic unwrap (sources.py:77-87). */
+int pxb_radius2(int64_t n, const double* x, const double* y, const double* z,
+                const pxb_geometry* geom, double* r2_out, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * Power-law and line sources
+ * ---------------------------------------------------------------------------------- */
+typedef struct {
+  int64_t ncell;
+  int64_t cell_id0;
+  const double* lum;      /* luminosity in keV/s */
+  const double* alpha;    /* photon index field or NULL -> alpha_const */
+  const double* r2;       /* cm^2 or NULL */
+  double alpha_const;
+  double e0, emin, emax;  /* keV */
+  double spectral_norm;
+  double scale_factor;    /* 1/(1+z) */
+  uint64_t seed;
+} pxb_powerlaw_cells;
+
+int pxb_powerlaw_counts(const pxb_powerlaw_cells* cells, double* lambda_out,
+                        int64_t* counts_out, void* stream);
+int pxb_powerlaw_sample(const pxb_powerlaw_cells* cells, int64_t n_active, const int64_t* idx,
+                        const int64_t* nph, const int64_t* poff, int64_t n_photons,
+                        double* energies, void* stream);
+
+typedef struct {
+  int64_t ncell;
+  int64_t cell_id0;
+  const double* rate;     /* photons/s (cgs value of the emission field) */
+  const double* sigma;    /* line width in keV per cell, or NULL -> sigma_const */
+  const double* r2;
+  double sigma_const;
+  double e0;              /* keV */
+  double spectral_norm;
+  double scale_factor;
+  uint64_t seed;
+} pxb_line_cells;
+
+int pxb_line_counts(const pxb_line_cells* cells, double* lambda_out, int64_t* counts_out,
+                    void* stream);
+int pxb_line_sample(const pxb_line_cells* cells, int64_t n_active, const int64_t* idx,
+                    const int64_t* nph, const int64_t* poff, int64_t n_photons,
+                    double* energies, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * Projection
+ * ---------------------------------------------------------------------------------- */
+typedef struct {
+  int64_t n_cells;
+  int64_t n_photons;
+  const int64_t* nph;    /* [n_cells] */
+  const int64_t* poff;   /* [n_cells+1] exclusive offsets into energy */
+  const double* x;       /* kpc, centred */
+  const double* y;
+  const double* z;
+  const double* vx;      /* km/s, bulk-subtracted */
+  const double* vy;
+  const double* vz;
+  const double* dx;      /* kpc (cell width or smoothing length) */
+  const double* energy;  /* [n_photons] keV */
+} pxb_photon_list;
+
+enum { PXB_ABS_NONE = 0, PXB_ABS_TABLE = 1, PXB_ABS_WABS = 2 };
+enum { PXB_SKY_TAN = 0, PXB_SKY_FLAT = 1, PXB_SKY_PHYS = 2 };
+
+typedef struct {
+  int32_t observer;      /* 0 external, 1 internal (all-sky) */
+  int32_t data_type;     /* 0 cells, 1 particles */
+  int32_t kernel;        /* 0 top_hat, 1 gaussian */
+  int32_t no_shifting;
+  int32_t vn_axis;       /* 0/1/2: that velocity component; -1: v . z_hat */
+  int32_t sky_mode;      /* PXB_SKY_* */
+  int32_t save_los;
+  int32_t absorb_kind;   /* PXB_ABS_* */
+  int32_t has_sigma_pos;
+  int32_t reserved;
+  double sigma_pos;
+  double x_hat[3], y_hat[3], z_hat[3];
+  double D_A_kpc;
+  double sky_center[2];  /* degrees */
+  double nH;             /* foreground column, 1e22 cm^-2 */
+  const double* abs_energy;  /* device [abs_n], ascending, keV */
+  const double* abs_sigma;   /* device [abs_n], cm^2 * 1e22 (so that tau = sigma*nH) */
+  int64_t abs_n;
+  int32_t abs_grid;          /* 0 arbitrary ascending grid (binary search), 1 uniform in E,
+                                2 uniform in log10(E): index = (x - abs_x0) * abs_inv_dx */
+  int32_t reserved2;
+  double abs_x0, abs_inv_dx;
+  const double* nH_cell;     /* device per-cell internal column (1e22 cm^-2) or NULL */
+  double oneplusz;
+  uint64_t seed;
+  int64_t cell_id0;
+} pxb_project_params;
+
+int pxb_project_workspace_bytes(int64_t n_cells, int64_t n_photons, int64_t* bytes);
+/* Outputs xsky/ysky/eobs (and los when save_los) must hold n_photons entries; the first
+ * n_events are valid and keep the photon-list order (stable compaction).
+ * n_events_out: device int64[1].  stats_out: device double[3] = {sum(eobs), min, max}. */
+int pxb_project(const pxb_photon_list* photons, const pxb_project_params* params,
+                double* xsky, double* ysky, double* eobs, double* los,
+                int64_t* n_events_out, double* stats_out, void* workspace,
+                int64_t workspace_bytes, void* stream);
+
+/* In-place Doppler shift with per-cell factors (sky_functions.pyx:20-34). */
+int pxb_doppler_shift(int64_t n_cells, const double* beta_n, const double* beta2,
+                      const int64_t* poff, int64_t n_photons, double* eobs, void* stream);
+/* In-place inverse gnomonic projection (sky_functions.pyx:153-179); radians in, degrees out. */
+int pxb_pixel_to_cel(int64_t n, double* xsky, double* ysky, double ra0_deg, double dec0_deg,
+                     void* stream);
+/* transmission exp(-sigma(E)*nH) for n energies with the absorption described by params
+ * (absorb_kind, nH, abs_*). */
+int pxb_absorb_transmission(const pxb_project_params* params, int64_t n, const double* energy,
+                            double* trans_out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PXB_H */

@@ -1,0 +1,35 @@
+"""pyxsim_b200 -- B200-native (sm_100a) photon generation and projection behind pyXSIM's
+``make_photons`` / ``project_photons`` / ``SourceModel`` API.
+
+Public names follow ``pyxsim/__init__.py:11-31`` for the parts that belong to the hot path.
+"""
+from .data import ArrayDataSource, Cosmology
+from .photon_list import (
+    DeviceList,
+    drop_list,
+    load_list,
+    make_photons,
+    project_photons,
+    project_photons_allsky,
+)
+from .source_models import (
+    CIESourceModel,
+    IGMSourceModel,
+    LineSourceModel,
+    NEISourceModel,
+    PionSourceModel,
+    PowerLawSourceModel,
+    SourceModel,
+    ThermalSourceModel,
+)
+from .spectral_models import (
+    AbsorptionModel,
+    PionSpectralModel,
+    TableCIEModel,
+    TBabsModel,
+    ThermalSpectralModel,
+    WabsModel,
+    absorb_models,
+)
+
+__version__ = "0.1.0"

@@ -1,0 +1,231 @@
+// common.cuh -- shared device/host helpers for libpxb (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <math.h>
+#include "../../include/pxb.h"
+
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
+#error "libpxb is written for sm_100a (B200) only"
+#endif
+
+// ---------------------------------------------------------------------------------------
+// error plumbing (host)
+// ---------------------------------------------------------------------------------------
+void pxb_set_error(const char* fmt, ...);
+
+#define PXB_CUDA(call)                                                                 \
+  do {                                                                                 \
+    cudaError_t _e = (call);                                                           \
+    if (_e != cudaSuccess) {                                                           \
+      pxb_set_error("%s failed at %s:%d: %s", #call, __FILE__, __LINE__,               \
+                    cudaGetErrorString(_e));                                           \
+      return PXB_ERR_CUDA;                                                             \
+    }                                                                                  \
+  } while (0)
+
+#define PXB_REQUIRE(cond, ...)                                                         \
+  do {                                                                                 \
+    if (!(cond)) {                                                                     \
+      pxb_set_error(__VA_ARGS__);                                                      \
+      return PXB_ERR_INVALID;                                                          \
+    }                                                                                  \
+  } while (0)
+
+#define PXB_LAUNCH_CHECK()                                                             \
+  do {                                                                                 \
+    cudaError_t _e = cudaGetLastError();                                               \
+    if (_e != cudaSuccess) {                                                           \
+      pxb_set_error("kernel launch failed at %s:%d: %s", __FILE__, __LINE__,           \
+                    cudaGetErrorString(_e));                                           \
+      return PXB_ERR_CUDA;                                                             \
+    }                                                                                  \
+  } while (0)
+
+int pxb_sm_count();  // cached SM count of the current device (148 on B200)
+
+// ---------------------------------------------------------------------------------------
+// RNG: Philox4x32-10 (Salmon et al. 2011), counter-based.
+//   key     = 64-bit user seed
+//   counter = (draw_lo, draw_hi, cell_lo, cell_hi16<<16 | stream)
+// so every (cell, draw, stream) triple owns an independent 128-bit block: results do not
+// depend on launch geometry, chunking or GPU count.
+// ---------------------------------------------------------------------------------------
+enum PxbStream : uint32_t {
+  STREAM_POISSON = 1,
+  STREAM_ENERGY = 2,
+  STREAM_PROJ_A = 3,   // absorption + first scatter draws
+  STREAM_PROJ_B = 4,   // remaining scatter draws
+  STREAM_PROJ_C = 5,   // sigma_pos smoothing
+  STREAM_PROJ_D = 6,   // internal absorption
+  STREAM_POWERLAW = 7,
+  STREAM_LINE = 8,
+};
+
+struct Philox4 {
+  uint32_t x, y, z, w;
+};
+
+__device__ __forceinline__ Philox4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2,
+                                                 uint32_t c3, uint32_t k0, uint32_t k1) {
+  const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u;
+  const uint32_t W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    uint32_t hi0 = __umulhi(M0, c0), lo0 = M0 * c0;
+    uint32_t hi1 = __umulhi(M1, c2), lo1 = M1 * c2;
+    uint32_t n0 = hi1 ^ c1 ^ k0;
+    uint32_t n2 = hi0 ^ c3 ^ k1;
+    c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+    k0 += W0; k1 += W1;
+  }
+  return Philox4{c0, c1, c2, c3};
+}
+
+__device__ __forceinline__ Philox4 pxb_rand4(uint64_t seed, uint32_t stream, uint64_t cell,
+                                             uint64_t draw) {
+  return philox4x32_10((uint32_t)draw, (uint32_t)(draw >> 32), (uint32_t)cell,
+                       (((uint32_t)(cell >> 32)) << 16) | (stream & 0xFFFFu),
+                       (uint32_t)seed, (uint32_t)(seed >> 32));
+}
+
+// 53-bit uniform in [0,1)
+__device__ __forceinline__ double u53(uint32_t hi, uint32_t lo) {
+  uint64_t v = (((uint64_t)hi << 32) | lo) >> 11;
+  return (double)v * (1.0 / 9007199254740992.0);
+}
+// 53-bit uniform in (0,1]  (safe for log)
+__device__ __forceinline__ double u53_open0(uint32_t hi, uint32_t lo) {
+  uint64_t v = (((uint64_t)hi << 32) | lo) >> 11;
+  return (double)(v + 1) * (1.0 / 9007199254740992.0);
+}
+
+// two standard normals from one Philox block (Box-Muller)
+__device__ __forceinline__ void normal2(const Philox4& r, double& n0, double& n1) {
+  double u1 = u53_open0(r.x, r.y);
+  double u2 = u53(r.z, r.w);
+  double rad = sqrt(-2.0 * log(u1));
+  double s, c;
+  sincospi(2.0 * u2, &s, &c);
+  n0 = rad * c;
+  n1 = rad * s;
+}
+
+// Sequential uniform stream for one cell (Poisson sampler): draw d -> two doubles per block.
+struct CellStream {
+  uint64_t seed, cell;
+  uint32_t stream;
+  uint64_t block;
+  int have;
+  double spare;
+  __device__ CellStream(uint64_t s, uint32_t st, uint64_t c)
+      : seed(s), cell(c), stream(st), block(0), have(0), spare(0.0) {}
+  __device__ double next() {
+    if (have) {
+      have = 0;
+      return spare;
+    }
+    Philox4 r = pxb_rand4(seed, stream, cell, block++);
+    spare = u53(r.z, r.w);
+    have = 1;
+    return u53(r.x, r.y);
+  }
+};
+
+// Poisson(lam): multiplication method below 10 (Knuth), transformed rejection PTRS above
+// (Hoermann 1993, "The transformed rejection method for generating Poisson random variables").
+__device__ inline int64_t poisson_draw(double lam, CellStream& rs) {
+  if (!(lam > 0.0) || !isfinite(lam)) return 0;
+  if (lam < 10.0) {
+    double enlam = exp(-lam);
+    int64_t k = 0;
+    double prod = rs.next();
+    while (prod > enlam) {
+      ++k;
+      prod *= rs.next();
+    }
+    return k;
+  }
+  double slam = sqrt(lam);
+  double loglam = log(lam);
+  double b = 0.931 + 2.53 * slam;
+  double a = -0.059 + 0.02483 * b;
+  double invalpha = 1.1239 + 1.1328 / (b - 3.4);
+  double vr = 0.9277 - 3.6224 / (b - 2.0);
+  for (int it = 0; it < 1000; ++it) {
+    double U = rs.next() - 0.5;
+    double V = rs.next();
+    double us = 0.5 - fabs(U);
+    double kf = floor((2.0 * a / us + b) * U + lam + 0.43);
+    if (us >= 0.07 && V <= vr) return (int64_t)kf;
+    if (kf < 0.0 || (us < 0.013 && V > us)) continue;
+    if (log(V) + log(invalpha) - log(a / (us * us) + b) <=
+        -lam + kf * loglam - lgamma(kf + 1.0))
+      return (int64_t)kf;
+  }
+  return (int64_t)floor(lam + 0.5);  // unreachable in practice
+}
+
+// ---------------------------------------------------------------------------------------
+// small utilities
+// ---------------------------------------------------------------------------------------
+// np.digitize(x, nodes) - 1 clamped to [0, n-2]  (spectral_models.py:35-37): largest i with
+// nodes[i] <= x, clamped.
+__device__ __forceinline__ int node_index(const double* __restrict__ nodes, int n, double x) {
+  int lo = 0, hi = n;  // count of nodes <= x
+  while (lo < hi) {
+    int mid = (lo + hi) >> 1;
+    if (__ldg(nodes + mid) <= x) lo = mid + 1; else hi = mid;
+  }
+  int i = lo - 1;
+  i = max(0, min(i, n - 2));
+  return i;
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_min(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ double warp_incl_scan(double v, int lane) {
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    double t = __shfl_up_sync(0xffffffffu, v, o);
+    if (lane >= o) v += t;
+  }
+  return v;
+}
+__device__ __forceinline__ int64_t warp_incl_scan_i64(int64_t v, int lane) {
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    int64_t t = __shfl_up_sync(0xffffffffu, v, o);
+    if (lane >= o) v += t;
+  }
+  return v;
+}
+
+// streaming (read-once / write-once) global accesses: keep L1 for the tables
+__device__ __forceinline__ double ld_stream(const double* p) {
+  double v;
+  asm volatile("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ int64_t ld_stream_i64(const int64_t* p) {
+  int64_t v;
+  asm volatile("ld.global.nc.L1::no_allocate.s64 %0, [%1];" : "=l"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ void st_stream(double* p, double v) {
+  asm volatile("st.global.L1::no_allocate.f64 [%0], %1;" ::"l"(p), "d"(v));
+}

@@ -1,0 +1,589 @@
+// project.cu -- photon projection: Doppler shift, foreground/internal absorption rejection,
+// position scatter, sky transform and stable stream compaction in ONE pass over the photons.
+//
+// Reference path: _project_photons tile loop, pyxsim/photon_list.py:661-808, calling
+//   doppler_shift            pyxsim/lib/sky_functions.pyx:20-34
+//   absorb_photons           pyxsim/spectral_models.py:556-583
+//   scatter_events           sky_functions.pyx:40-147
+//   scatter_events_allsky    sky_functions.pyx:185-250
+//   pixel_to_cel             sky_functions.pyx:153-179
+//
+// Layout: a small per-cell pre-pass (k_project_cells) turns the 7 per-cell arrays into the 5
+// derived values every photon of that cell needs (Doppler factor, rotated centre, scatter
+// width).  The photon pass (k_project_photons) owns tiles of TILE photons; tiles take a
+// ticket, compact their survivors with ballots + a decoupled look-back over per-tile counts,
+// so the event list keeps the photon-list order like the reference's cursor `k`
+// (sky_functions.pyx:87-105) and is bit-reproducible.
+#include "tiles.cuh"
+
+constexpr double PXB_C_KMS = 299792.458;          // clight in km/s (utils.py:10-11)
+constexpr double PXB_PI = 3.14159265358979323846;
+constexpr double PXB_RAD2DEG = 180.0 / PXB_PI;
+
+// ---------------------------------------------------------------------------------------
+// absorption: transmission(E) = exp(-sigma(E) * nH)
+// ---------------------------------------------------------------------------------------
+// Morrison & McCammon (1983) piecewise polynomial, as used by soxs.get_wabs_absorb (the
+// third-party routine behind WabsModel, spectral_models.py:633-635): sigma(E) =
+// (c0 + c1 E + c2 E^2) / E^3 * 1e-24 cm^2.
+__constant__ double c_wabs_edge[15] = {0.03, 0.1, 0.284, 0.4, 0.532, 0.707, 0.867, 1.303,
+                                       1.84, 2.471, 3.21, 4.038, 7.111, 8.331, 10.0};
+__constant__ double c_wabs_c0[14] = {17.3, 34.6, 78.1, 71.4, 95.5, 308.9, 120.6,
+                                     141.3, 202.7, 342.7, 352.2, 433.9, 629.0, 701.2};
+__constant__ double c_wabs_c1[14] = {608.1, 267.9, 18.8, 66.8, 145.8, -380.6, 169.3,
+                                     146.8, 104.7, 18.7, 18.7, -2.4, 30.9, 25.2};
+__constant__ double c_wabs_c2[14] = {-2150.0, -476.1, 4.3, -51.4, -61.1, 294.0, -47.7,
+                                     -31.5, -17.0, 0.0, 0.0, 0.75, 0.0, 0.0};
+
+__device__ __forceinline__ double wabs_tau_per_nh(double e) {
+  int k = 0;
+#pragma unroll
+  for (int q = 1; q < 14; ++q) k += (e >= c_wabs_edge[q]);
+  const double s = (c_wabs_c0[k] + e * (c_wabs_c1[k] + e * c_wabs_c2[k])) / (e * e * e);
+  return s * 1.0e-2;  // 1e-24 cm^2 * 1e22 cm^-2
+}
+
+// np.interp(e, emid, sigma, left=0, right=0): spectral_models.py:560
+__device__ __forceinline__ double table_tau_per_nh(const pxb_project_params& P, double e) {
+  const int64_t n = P.abs_n;
+  const double* __restrict__ xs = P.abs_energy;
+  const double* __restrict__ ys = P.abs_sigma;
+  if (n < 1 || !(e >= __ldg(xs)) || !(e <= __ldg(xs + n - 1))) return 0.0;
+  int64_t lo;
+  if (P.abs_grid == 0) {
+    lo = 0;
+    int64_t hi = n - 1;  // xs[lo] <= e <= xs[hi]
+    while (hi - lo > 1) {
+      const int64_t mid = (lo + hi) >> 1;
+      if (__ldg(xs + mid) <= e) lo = mid; else hi = mid;
+    }
+  } else {
+    const double xx = (P.abs_grid == 2) ? log10(e) : e;
+    lo = (int64_t)((xx - P.abs_x0) * P.abs_inv_dx);
+    lo = lo < 0 ? 0 : (lo > n - 2 ? n - 2 : lo);
+    // the analytic index may be off by one ulp-wise: fix up against the stored nodes
+    if (lo > 0 && __ldg(xs + lo) > e) --lo;
+    else if (lo < n - 2 && __ldg(xs + lo + 1) <= e) ++lo;
+  }
+  if (n == 1) return __ldg(ys);
+  const double x0 = __ldg(xs + lo), x1 = __ldg(xs + lo + 1);
+  const double y0 = __ldg(ys + lo), y1 = __ldg(ys + lo + 1);
+  return y0 + (y1 - y0) / (x1 - x0) * (e - x0);
+}
+
+__device__ __forceinline__ double tau_per_nh(const pxb_project_params& P, double e) {
+  return P.absorb_kind == PXB_ABS_WABS ? wabs_tau_per_nh(e) : table_tau_per_nh(P, e);
+}
+
+__global__ void __launch_bounds__(256)
+k_absorb_transmission(const __grid_constant__ pxb_project_params P, int64_t n,
+                      const double* __restrict__ e, double* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  out[i] = (P.absorb_kind == PXB_ABS_NONE) ? 1.0 : exp(-tau_per_nh(P, e[i]) * P.nH);
+}
+
+// ---------------------------------------------------------------------------------------
+// stand-alone natives (deterministic parity against the reference Cython)
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ double doppler_factor(double beta_n, double beta2) {
+  return (1.0 - beta_n) / sqrt(1.0 - beta2);  // sky_functions.pyx:31
+}
+
+__global__ void __launch_bounds__(256)
+k_doppler_shift(int64_t n_cells, const double* __restrict__ beta_n,
+                const double* __restrict__ beta2, const int64_t* __restrict__ poff,
+                int64_t n_photons, double* __restrict__ eobs) {
+  constexpr int TILE = 1024;
+  __shared__ int64_t s_off[TILE + 1];
+  __shared__ int64_t s_c[2];
+  const int64_t p0 = (int64_t)blockIdx.x * TILE;
+  const int64_t p1 = min(p0 + (int64_t)TILE, n_photons);
+  TileMap<TILE> tm;
+  tm.build(poff, n_cells, p0, p1, s_off, s_c);
+  for (int64_t p = p0 + threadIdx.x; p < p1; p += blockDim.x) {
+    const int64_t c = tm.cell_of(p, s_off);
+    eobs[p] = eobs[p] * doppler_factor(__ldg(beta_n + c), __ldg(beta2 + c));
+  }
+}
+
+// inverse gnomonic projection; closed form of sky_functions.pyx:167-179
+// (xi = -x, eta = y: RA = RA0 + atan2(xi, cos d0 - eta sin d0),
+//  Dec = atan2(sin d0 + eta cos d0, hypot(xi, cos d0 - eta sin d0)))
+__device__ __forceinline__ void tan_to_cel(double x, double y, double ra0_rad, double sin_d0,
+                                           double cos_d0, double& ra_deg, double& dec_deg) {
+  const double den = cos_d0 - y * sin_d0;
+  const double num = sin_d0 + y * cos_d0;
+  ra_deg = (ra0_rad + atan2(-x, den)) * PXB_RAD2DEG;
+  dec_deg = atan2(num, sqrt(x * x + den * den)) * PXB_RAD2DEG;
+}
+
+__global__ void __launch_bounds__(256)
+k_pixel_to_cel(int64_t n, double* __restrict__ xs, double* __restrict__ ys, double ra0_rad,
+               double sin_d0, double cos_d0) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double ra, dec;
+  tan_to_cel(xs[i], ys[i], ra0_rad, sin_d0, cos_d0, ra, dec);
+  xs[i] = ra;
+  ys[i] = dec;
+}
+
+// ---------------------------------------------------------------------------------------
+// per-cell pre-pass
+// ---------------------------------------------------------------------------------------
+struct CellDerived {
+  double* shift;  // Doppler factor (1 when no_shifting)
+  double* cx;     // centre . x_hat
+  double* cy;     // centre . y_hat
+  double* cz;     // centre . z_hat (the reference's `los`; also the 3rd all-sky coordinate)
+  double* w;      // scatter width: dx (cells), dx/2 (particles, external observer)
+};
+
+__global__ void __launch_bounds__(256)
+k_project_cells(const __grid_constant__ pxb_photon_list L,
+                const __grid_constant__ pxb_project_params P, CellDerived D) {
+  const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= L.n_cells) return;
+  const double x = L.x[c], y = L.y[c], z = L.z[c];
+  double shift = 1.0;
+  if (!P.no_shifting) {
+    const double vx = L.vx[c], vy = L.vy[c], vz = L.vz[c];
+    double vn;
+    if (P.observer == 1) {
+      vn = -(vx * x + vy * y + vz * z) / sqrt(x * x + y * y + z * z);  // photon_list.py:688-697
+    } else if (P.vn_axis >= 0) {
+      vn = P.vn_axis == 0 ? vx : (P.vn_axis == 1 ? vy : vz);
+    } else {
+      vn = vx * P.z_hat[0] + vy * P.z_hat[1] + vz * P.z_hat[2];
+    }
+    const double v2 = vx * vx + vy * vy + vz * vz;
+    const double ss = -1.0 / PXB_C_KMS;  // scale_shift
+    shift = doppler_factor(vn * ss, v2 * (ss * ss));
+  }
+  D.shift[c] = shift;
+  D.cx[c] = x * P.x_hat[0] + y * P.x_hat[1] + z * P.x_hat[2];
+  D.cy[c] = x * P.y_hat[0] + y * P.y_hat[1] + z * P.y_hat[2];
+  D.cz[c] = x * P.z_hat[0] + y * P.z_hat[1] + z * P.z_hat[2];
+  double w = L.dx ? L.dx[c] : 0.0;
+  if (P.observer == 0 && P.data_type == 1) w *= 0.5;  // photon_list.py:733-734
+  D.w[c] = w;
+}
+
+// ---------------------------------------------------------------------------------------
+// photon pass
+// ---------------------------------------------------------------------------------------
+constexpr int PROJ_THREADS = 256;
+constexpr int PROJ_ITEMS = 4;
+constexpr int PROJ_TILE = PROJ_THREADS * PROJ_ITEMS;
+constexpr int PROJ_WARPS = PROJ_THREADS / 32;
+static_assert(PROJ_ITEMS * PROJ_WARPS == 32, "group counts are scanned by one warp");
+
+constexpr unsigned long long ST_AGG = 1ull << 62;   // tile aggregate available
+constexpr unsigned long long ST_INC = 2ull << 62;   // inclusive prefix available
+constexpr unsigned long long ST_MASK = 3ull << 62;
+
+struct ProjWork {
+  unsigned long long* status;  // [ntiles]
+  unsigned int* ticket;        // [1]
+  double* part_sum;            // [ntiles]
+  double* part_min;
+  double* part_max;
+};
+
+struct Event { double xs, ys, e, los; };
+
+// scatter + sky transform for one detected photon
+__device__ __forceinline__ void scatter_one(const pxb_project_params& P, const CellDerived& D,
+                                            int64_t c, uint64_t cell_key, uint64_t draw,
+                                            const Philox4& ra, double sin_d0, double cos_d0,
+                                            double ra0_rad, Event& ev) {
+  const double w = __ldg(D.w + c);
+  const double cx = __ldg(D.cx + c), cy = __ldg(D.cy + c), cz = __ldg(D.cz + c);
+  if (P.observer == 0) {
+    double ox, oy;  // offsets in the sky plane in units of w
+    if (P.data_type == 0) {
+      // cells: uniform inside the cube, rotated into the sky plane (sky_functions.pyx:74-76,
+      // 110-121; on-axis x_hat/y_hat are axis vectors so only two of the draws contribute)
+      const Philox4 rb = pxb_rand4(P.seed, STREAM_PROJ_B, cell_key, draw);
+      const double u0 = u53(ra.z, ra.w) - 0.5, u1 = u53(rb.x, rb.y) - 0.5,
+                   u2 = u53(rb.z, rb.w) - 0.5;
+      ox = u0 * P.x_hat[0] + u1 * P.x_hat[1] + u2 * P.x_hat[2];
+      oy = u0 * P.y_hat[0] + u1 * P.y_hat[1] + u2 * P.y_hat[2];
+    } else {
+      const Philox4 rb = pxb_rand4(P.seed, STREAM_PROJ_B, cell_key, draw);
+      if (P.kernel == 1) {
+        normal2(rb, ox, oy);  // sky_functions.pyx:78-80
+      } else {
+        // top_hat: r ~ U(0,1) (NOT sqrt(U)), theta = 2 pi U  (sky_functions.pyx:81-85)
+        const double r = u53(rb.x, rb.y);
+        double s, co;
+        sincospi(2.0 * u53(rb.z, rb.w), &s, &co);
+        ox = r * co;
+        oy = r * s;
+      }
+    }
+    double xs = cx + ox * w, ys = cy + oy * w;
+    if (P.has_sigma_pos && P.data_type == 0) {
+      // photon_list.py:753-756: sigma = sigma_pos * dx
+      const Philox4 rc = pxb_rand4(P.seed, STREAM_PROJ_C, cell_key, draw);
+      double n0, n1;
+      normal2(rc, n0, n1);
+      const double sg = P.sigma_pos * w;
+      xs += sg * n0;
+      ys += sg * n1;
+    }
+    ev.los = cz;  // from the unscattered centre (sky_functions.pyx:124,143)
+    if (P.sky_mode != PXB_SKY_PHYS) {
+      xs /= P.D_A_kpc;
+      ys /= P.D_A_kpc;
+      if (P.sky_mode == PXB_SKY_FLAT) {
+        xs = P.sky_center[0] - xs * PXB_RAD2DEG;   // photon_list.py:762-764
+        ys = P.sky_center[1] + ys * PXB_RAD2DEG;
+      } else {
+        double ra, dec;
+        tan_to_cel(xs, ys, ra0_rad, sin_d0, cos_d0, ra, dec);
+        xs = ra;
+        ys = dec;
+      }
+    }
+    ev.xs = xs;
+    ev.ys = ys;
+  } else {
+    // internal observer: sky_functions.pyx:205-248
+    double o0, o1, o2;
+    const Philox4 rb = pxb_rand4(P.seed, STREAM_PROJ_B, cell_key, draw);
+    if (P.data_type == 0) {
+      o0 = u53(ra.z, ra.w) - 0.5;
+      o1 = u53(rb.x, rb.y) - 0.5;
+      o2 = u53(rb.z, rb.w) - 0.5;
+    } else if (P.kernel == 1) {
+      const Philox4 rc = pxb_rand4(P.seed, STREAM_PROJ_C, cell_key, draw);
+      double dump;
+      normal2(rb, o0, o1);
+      normal2(rc, o2, dump);
+    } else {
+      const double r = u53(ra.z, ra.w);
+      double sp, cp;
+      sincospi(2.0 * u53(rb.x, rb.y), &sp, &cp);
+      const double ct = 2.0 * u53(rb.z, rb.w) - 1.0;  // cos(theta), theta = arccos(U(-1,1))
+      const double stheta = sqrt(fmax(0.0, 1.0 - ct * ct));
+      o0 = r * cp * stheta;
+      o1 = r * sp * stheta;
+      o2 = r * ct;
+    }
+    const double xx = cx + w * (o0 * P.x_hat[0] + o1 * P.x_hat[1] + o2 * P.x_hat[2]);
+    const double yy = cy + w * (o0 * P.y_hat[0] + o1 * P.y_hat[1] + o2 * P.y_hat[2]);
+    const double zz = cz + w * (o0 * P.z_hat[0] + o1 * P.z_hat[1] + o2 * P.z_hat[2]);
+    const double rr = sqrt(xx * xx + yy * yy + zz * zz);
+    double lon = atan2(yy, xx) - 0.5 * PXB_PI;
+    if (lon < 0.0) lon += 2.0 * PXB_PI;
+    if (lon > 2.0 * PXB_PI) lon -= 2.0 * PXB_PI;
+    const double lat = 0.5 * PXB_PI - acos(zz / rr);
+    ev.xs = lon * PXB_RAD2DEG;
+    ev.ys = lat * PXB_RAD2DEG;
+    ev.los = rr;
+  }
+}
+
+__global__ void __launch_bounds__(PROJ_THREADS)
+k_project_photons(const __grid_constant__ pxb_photon_list L,
+                  const __grid_constant__ pxb_project_params P, const CellDerived D,
+                  const ProjWork W, double* __restrict__ xsky, double* __restrict__ ysky,
+                  double* __restrict__ eobs_out, double* __restrict__ los_out,
+                  int64_t* __restrict__ n_events_out, int64_t ntiles) {
+  __shared__ int64_t s_off[PROJ_TILE + 1];
+  __shared__ int64_t s_c[2];
+  __shared__ int s_cnt[PROJ_ITEMS * PROJ_WARPS + 1];
+  __shared__ unsigned int s_tile;
+  __shared__ int64_t s_base;
+  __shared__ double s_red[3][PROJ_WARPS];
+
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  double sin_d0, cos_d0;
+  sincos(P.sky_center[1] * (PXB_PI / 180.0), &sin_d0, &cos_d0);
+  const double ra0_rad = P.sky_center[0] * (PXB_PI / 180.0);
+
+  for (;;) {
+    __syncthreads();
+    if (threadIdx.x == 0) s_tile = atomicAdd(W.ticket, 1u);
+    __syncthreads();
+    const int64_t tile = s_tile;
+    if (tile >= ntiles) return;
+    const int64_t p0 = tile * PROJ_TILE;
+    const int64_t p1 = min(p0 + (int64_t)PROJ_TILE, L.n_photons);
+    TileMap<PROJ_TILE> tm;
+    tm.build(L.poff, L.n_cells, p0, p1, s_off, s_c);
+
+    Event ev[PROJ_ITEMS];
+    unsigned detbits = 0;
+    double tsum = 0.0, tmin = 1.0e99, tmax = -1.0e99;
+#pragma unroll
+    for (int r = 0; r < PROJ_ITEMS; ++r) {
+      const int64_t p = p0 + r * PROJ_THREADS + threadIdx.x;
+      bool det = false;
+      if (p < p1) {
+        const int64_t c = tm.cell_of(p, s_off);
+        const uint64_t cell_key = (uint64_t)(P.cell_id0 + c);
+        const uint64_t draw = (uint64_t)(p - __ldg(L.poff + c));  // index inside its cell
+        double e = ld_stream(L.energy + p) * __ldg(D.shift + c);
+        const Philox4 ra = pxb_rand4(P.seed, STREAM_PROJ_A, cell_key, draw);
+        det = true;
+        if (P.absorb_kind != PXB_ABS_NONE) {
+          if (P.nH_cell) {
+            // internal absorption on the source-frame energy, photon_list.py:715-723
+            const Philox4 rd = pxb_rand4(P.seed, STREAM_PROJ_D, cell_key, draw);
+            const double tr = exp(-tau_per_nh(P, e * P.oneplusz) * __ldg(P.nH_cell + c));
+            det = u53(rd.x, rd.y) < tr;
+          }
+          if (det && P.nH > 0.0) {
+            const double tr = exp(-tau_per_nh(P, e) * P.nH);
+            det = u53(ra.x, ra.y) < tr;
+          }
+        }
+        if (det) {
+          ev[r].e = e;
+          scatter_one(P, D, c, cell_key, draw, ra, sin_d0, cos_d0, ra0_rad, ev[r]);
+          tsum += e;
+          tmin = fmin(tmin, e);
+          tmax = fmax(tmax, e);
+        }
+      }
+      const unsigned bal = __ballot_sync(0xffffffffu, det);
+      if (det) detbits |= 1u << r;
+      if (lane == 0) s_cnt[r * PROJ_WARPS + wid] = __popc(bal);
+      // rank of this thread inside its (round, warp) group
+      const int rank = __popc(bal & ((1u << lane) - 1u));
+      // stash the in-group rank in the low bits of detbits' upper half
+      detbits |= (unsigned)rank << (8 + 5 * r);
+    }
+    // block reduce of the flux statistics
+    tsum = warp_sum(tsum); tmin = warp_min(tmin); tmax = warp_max(tmax);
+    if (lane == 0) { s_red[0][wid] = tsum; s_red[1][wid] = tmin; s_red[2][wid] = tmax; }
+    __syncthreads();
+    // exclusive scan of the PROJ_ITEMS*PROJ_WARPS group counts (photon order = round-major)
+    if (wid == 0) {
+      constexpr int NG = PROJ_ITEMS * PROJ_WARPS;  // 32
+      int v = (lane < NG) ? s_cnt[lane] : 0;
+      int inc = v;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        int t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+      }
+      if (lane < NG) s_cnt[lane] = inc - v;
+      const int total = __shfl_sync(0xffffffffu, inc, 31);
+      if (lane == 0) {
+        s_cnt[NG] = total;
+        double a = 0.0, b = 1.0e99, cmax = -1.0e99;
+        for (int w = 0; w < PROJ_WARPS; ++w) {
+          a += s_red[0][w]; b = fmin(b, s_red[1][w]); cmax = fmax(cmax, s_red[2][w]);
+        }
+        W.part_sum[tile] = a; W.part_min[tile] = b; W.part_max[tile] = cmax;
+        // decoupled look-back over the tile counts
+        int64_t prefix = 0;
+        if (tile == 0) {
+          atomicExch(W.status, ST_INC | (unsigned long long)total);
+        } else {
+          atomicExch(W.status + tile, ST_AGG | (unsigned long long)total);
+          int64_t j = tile - 1;
+          for (;;) {
+            unsigned long long s;
+            do {
+              s = *((volatile unsigned long long*)(W.status + j));
+            } while ((s & ST_MASK) == 0);
+            prefix += (int64_t)(s & ~ST_MASK);
+            if ((s & ST_MASK) == ST_INC) break;
+            --j;
+          }
+          atomicExch(W.status + tile, ST_INC | (unsigned long long)(prefix + total));
+        }
+        s_base = prefix;
+        if (tile == ntiles - 1) *n_events_out = prefix + total;
+      }
+    }
+    __syncthreads();
+    const int64_t base = s_base;
+#pragma unroll
+    for (int r = 0; r < PROJ_ITEMS; ++r) {
+      if (detbits & (1u << r)) {
+        const int rank = (detbits >> (8 + 5 * r)) & 31;
+        const int64_t o = base + s_cnt[r * PROJ_WARPS + wid] + rank;
+        st_stream(xsky + o, ev[r].xs);
+        st_stream(ysky + o, ev[r].ys);
+        st_stream(eobs_out + o, ev[r].e);
+        if (los_out) st_stream(los_out + o, ev[r].los);
+      }
+    }
+  }
+}
+
+// deterministic two-level reduction of the per-tile statistics
+__global__ void __launch_bounds__(256)
+k_reduce_stats(const double* __restrict__ ps, const double* __restrict__ pmin,
+               const double* __restrict__ pmax, int64_t n, double* __restrict__ out,
+               int64_t per_block) {
+  __shared__ double s[3][8];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int64_t b0 = (int64_t)blockIdx.x * per_block;
+  const int64_t b1 = min(b0 + per_block, n);
+  double a = 0.0, mn = 1.0e99, mx = -1.0e99;
+  for (int64_t i = b0 + threadIdx.x; i < b1; i += blockDim.x) {
+    a += ps[i]; mn = fmin(mn, pmin[i]); mx = fmax(mx, pmax[i]);
+  }
+  a = warp_sum(a); mn = warp_min(mn); mx = warp_max(mx);
+  if (lane == 0) { s[0][wid] = a; s[1][wid] = mn; s[2][wid] = mx; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < 8; ++w) { a += s[0][w]; mn = fmin(mn, s[1][w]); mx = fmax(mx, s[2][w]); }
+    out[3 * blockIdx.x + 0] = a; out[3 * blockIdx.x + 1] = mn; out[3 * blockIdx.x + 2] = mx;
+  }
+}
+__global__ void k_reduce_stats_final(const double* __restrict__ part, int nb,
+                                     double* __restrict__ out) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  double a = 0.0, mn = 1.0e99, mx = -1.0e99;
+  for (int i = 0; i < nb; ++i) {
+    a += part[3 * i]; mn = fmin(mn, part[3 * i + 1]); mx = fmax(mx, part[3 * i + 2]);
+  }
+  out[0] = a; out[1] = mn; out[2] = mx;
+}
+
+// ---------------------------------------------------------------------------------------
+// host
+// ---------------------------------------------------------------------------------------
+constexpr int STATS_BLOCKS = 256;
+
+static inline int64_t align256(int64_t v) { return (v + 255) & ~(int64_t)255; }
+
+struct ProjLayout {
+  int64_t ntiles;
+  int64_t off_cells, off_status, off_ticket, off_part, off_red, total;
+};
+
+static ProjLayout proj_layout(int64_t n_cells, int64_t n_photons) {
+  ProjLayout l;
+  l.ntiles = (n_photons + PROJ_TILE - 1) / PROJ_TILE;
+  int64_t o = 0;
+  l.off_cells = o;  o += align256(5 * n_cells * (int64_t)sizeof(double));
+  l.off_status = o; o += align256(l.ntiles * 8);
+  l.off_ticket = o; o += 256;
+  l.off_part = o;   o += align256(3 * l.ntiles * 8);
+  l.off_red = o;    o += align256(3 * STATS_BLOCKS * 8);
+  l.total = o;
+  return l;
+}
+
+extern "C" int pxb_project_workspace_bytes(int64_t n_cells, int64_t n_photons, int64_t* bytes) {
+  PXB_REQUIRE(bytes && n_photons >= 0 && n_cells >= 0, "bad argument");
+  *bytes = proj_layout(n_cells, n_photons).total;
+  return PXB_OK;
+}
+
+static int check_params(const pxb_project_params* P) {
+  PXB_REQUIRE(P, "NULL params");
+  PXB_REQUIRE(P->absorb_kind >= 0 && P->absorb_kind <= 2, "bad absorb_kind");
+  if (P->absorb_kind == PXB_ABS_TABLE)
+    PXB_REQUIRE(P->abs_energy && P->abs_sigma && P->abs_n >= 1, "absorption table missing");
+  return PXB_OK;
+}
+
+extern "C" int pxb_project(const pxb_photon_list* L, const pxb_project_params* P, double* xsky,
+                           double* ysky, double* eobs, double* los, int64_t* n_events_out,
+                           double* stats_out, void* workspace, int64_t workspace_bytes,
+                           void* stream) {
+  PXB_REQUIRE(L && n_events_out && stats_out, "NULL argument");
+  int rc = check_params(P);
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (L->n_photons == 0 || L->n_cells == 0) {
+    PXB_CUDA(cudaMemsetAsync(n_events_out, 0, sizeof(int64_t), st));
+    const double init[3] = {0.0, 1.0e99, -1.0e99};
+    PXB_CUDA(cudaMemcpyAsync(stats_out, init, sizeof(init), cudaMemcpyHostToDevice, st));
+    PXB_CUDA(cudaStreamSynchronize(st));
+    return PXB_OK;
+  }
+  PXB_REQUIRE(xsky && ysky && eobs, "output arrays missing");
+  PXB_REQUIRE(!P->save_los || los, "save_los needs the los array");
+  PXB_REQUIRE(L->nph && L->poff && L->x && L->y && L->z && L->energy, "photon list incomplete");
+  PXB_REQUIRE(P->no_shifting || (L->vx && L->vy && L->vz), "velocities missing");
+  PXB_REQUIRE(P->observer == 1 || P->sky_mode == PXB_SKY_PHYS || P->D_A_kpc > 0.0,
+              "D_A must be positive for sky coordinates");
+  const ProjLayout lay = proj_layout(L->n_cells, L->n_photons);
+  PXB_REQUIRE(workspace && workspace_bytes >= lay.total,
+              "projection workspace too small (%lld < %lld)", (long long)workspace_bytes,
+              (long long)lay.total);
+  PXB_REQUIRE(lay.ntiles < (1LL << 32) - 4096, "too many photons for one projection call");
+  char* ws = (char*)workspace;
+  CellDerived D;
+  D.shift = (double*)(ws + lay.off_cells);
+  D.cx = D.shift + L->n_cells;
+  D.cy = D.cx + L->n_cells;
+  D.cz = D.cy + L->n_cells;
+  D.w = D.cz + L->n_cells;
+  ProjWork W;
+  W.status = (unsigned long long*)(ws + lay.off_status);
+  W.ticket = (unsigned int*)(ws + lay.off_ticket);
+  W.part_sum = (double*)(ws + lay.off_part);
+  W.part_min = W.part_sum + lay.ntiles;
+  W.part_max = W.part_min + lay.ntiles;
+  double* red = (double*)(ws + lay.off_red);
+  // status + ticket are adjacent: one memset
+  PXB_CUDA(cudaMemsetAsync(ws + lay.off_status, 0, (size_t)(lay.off_part - lay.off_status), st));
+  k_project_cells<<<(unsigned)((L->n_cells + 255) / 256), 256, 0, st>>>(*L, *P, D);
+  PXB_LAUNCH_CHECK();
+  int per_sm = 0;
+  PXB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_project_photons, PROJ_THREADS, 0));
+  if (per_sm < 1) per_sm = 1;
+  int64_t grid = (int64_t)pxb_sm_count() * per_sm;
+  if (grid > lay.ntiles) grid = lay.ntiles;
+  k_project_photons<<<(unsigned)grid, PROJ_THREADS, 0, st>>>(
+      *L, *P, D, W, xsky, ysky, eobs, P->save_los ? los : nullptr, n_events_out, lay.ntiles);
+  PXB_LAUNCH_CHECK();
+  const int64_t per_block = (lay.ntiles + STATS_BLOCKS - 1) / STATS_BLOCKS;
+  const int nb = (int)((lay.ntiles + per_block - 1) / per_block);
+  k_reduce_stats<<<nb, 256, 0, st>>>(W.part_sum, W.part_min, W.part_max, lay.ntiles, red, per_block);
+  PXB_LAUNCH_CHECK();
+  k_reduce_stats_final<<<1, 32, 0, st>>>(red, nb, stats_out);
+  PXB_LAUNCH_CHECK();
+  return PXB_OK;
+}
+
+extern "C" int pxb_doppler_shift(int64_t n_cells, const double* beta_n, const double* beta2,
+                                 const int64_t* poff, int64_t n_photons, double* eobs,
+                                 void* stream) {
+  PXB_REQUIRE(n_cells >= 0 && n_photons >= 0, "bad sizes");
+  if (n_cells == 0 || n_photons == 0) return PXB_OK;
+  PXB_REQUIRE(beta_n && beta2 && poff && eobs, "NULL argument");
+  const int64_t ntiles = (n_photons + 1023) / 1024;
+  PXB_REQUIRE(ntiles < (1LL << 31), "too many photons");
+  k_doppler_shift<<<(unsigned)ntiles, 256, 0, (cudaStream_t)stream>>>(n_cells, beta_n, beta2, poff,
+                                                                     n_photons, eobs);
+  PXB_LAUNCH_CHECK();
+  return PXB_OK;
+}
+
+extern "C" int pxb_pixel_to_cel(int64_t n, double* xsky, double* ysky, double ra0_deg,
+                                double dec0_deg, void* stream) {
+  PXB_REQUIRE(n >= 0, "bad n");
+  if (n == 0) return PXB_OK;
+  PXB_REQUIRE(xsky && ysky, "NULL argument");
+  const double d0 = dec0_deg * PXB_PI / 180.0;
+  k_pixel_to_cel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      n, xsky, ysky, ra0_deg * PXB_PI / 180.0, sin(d0), cos(d0));
+  PXB_LAUNCH_CHECK();
+  return PXB_OK;
+}
+
+extern "C" int pxb_absorb_transmission(const pxb_project_params* params, int64_t n,
+                                       const double* energy, double* trans_out, void* stream) {
+  int rc = check_params(params);
+  if (rc) return rc;
+  PXB_REQUIRE(n >= 0, "bad n");
+  if (n == 0) return PXB_OK;
+  PXB_REQUIRE(energy && trans_out, "NULL argument");
+  k_absorb_transmission<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      *params, n, energy, trans_out);
+  PXB_LAUNCH_CHECK();
+  return PXB_OK;
+}

@@ -1,0 +1,185 @@
+"""Minimal host front end for array-backed datasets.
+
+In the reference the front end is yt (dataset I/O, chunk iteration, units; e.g.
+pyxsim/photon_list.py:401,426-451).  yt is not part of the hot path and is not required
+here: :class:`ArrayDataSource` exposes the handful of things ``make_photons`` and the source
+models ask of a yt data object -- chunk iteration, ``chunk[field]`` access in known units,
+domain geometry -- for plain NumPy / torch arrays (host or device).  When yt *is* installed,
+yt data objects are accepted as well (see :func:`wrap_data_source`).
+
+Unit conventions of an ArrayDataSource (override per field with ``units={field: unit}``):
+  temperature  K            (or "keV")
+  emission measure  cm**-3
+  density  g/cm**3, entropy keV*cm**2, H nuclei density cm**-3
+  metallicity / element fields  Zsun  (or "dimensionless" mass fraction)
+  positions, widths  kpc;  velocities  km/s
+  luminosity (power law)  keV/s  (or "erg/s");  line emission  photons/s
+"""
+import numpy as np
+import torch
+
+from . import constants as K
+
+
+class Cosmology:
+    """Flat/non-flat LCDM angular diameter distance; defaults follow yt's Cosmology()
+    (h=0.71, Om=0.27, OL=0.73), which make_photons falls back to (photon_list.py:225-231)."""
+
+    def __init__(self, hubble_constant=0.71, omega_matter=0.27, omega_lambda=0.73,
+                 omega_curvature=0.0, omega_radiation=0.0):
+        self.hubble_constant = hubble_constant
+        self.omega_matter = omega_matter
+        self.omega_lambda = omega_lambda
+        self.omega_curvature = omega_curvature
+        self.omega_radiation = omega_radiation
+
+    def _e(self, z):
+        zp1 = 1.0 + z
+        return np.sqrt(self.omega_matter * zp1**3 + self.omega_curvature * zp1**2
+                       + self.omega_radiation * zp1**4 + self.omega_lambda)
+
+    def comoving_radial_distance_mpc(self, z1, z2):
+        from scipy.integrate import quad
+
+        c_over_h0 = K.clight_kms / (100.0 * self.hubble_constant)  # Mpc
+        val, _ = quad(lambda z: 1.0 / self._e(z), z1, z2, epsabs=0.0, epsrel=1e-12)
+        return c_over_h0 * val
+
+    def angular_diameter_distance_mpc(self, z1, z2):
+        dc = self.comoving_radial_distance_mpc(z1, z2)
+        c_over_h0 = K.clight_kms / (100.0 * self.hubble_constant)
+        ok = self.omega_curvature
+        if ok > 0:
+            dm = c_over_h0 / np.sqrt(ok) * np.sinh(np.sqrt(ok) * dc / c_over_h0)
+        elif ok < 0:
+            dm = c_over_h0 / np.sqrt(-ok) * np.sin(np.sqrt(-ok) * dc / c_over_h0)
+        else:
+            dm = dc
+        return dm / (1.0 + z2)
+
+
+_UNIT_FACTORS = {
+    ("K", "keV"): 1.0 / K.K_per_keV, ("keV", "K"): K.K_per_keV,
+    ("erg/s", "keV/s"): 1.0 / K.erg_per_keV, ("keV/s", "erg/s"): K.erg_per_keV,
+    ("cm", "kpc"): 1.0 / K.cm_per_kpc, ("kpc", "cm"): K.cm_per_kpc,
+    ("Mpc", "kpc"): 1.0e3, ("kpc", "Mpc"): 1.0e-3,
+    ("cm/s", "km/s"): 1.0e-5, ("km/s", "cm/s"): 1.0e5,
+}
+
+_DEFAULT_UNITS = {
+    "temperature": "K", "kT": "keV", "emission_measure": "cm**-3", "density": "g/cm**3",
+    "entropy": "keV*cm**2", "H_nuclei_density": "cm**-3", "metallicity": "Zsun",
+}
+
+
+def convert(values, unit_from, unit_to):
+    if unit_from == unit_to or unit_to is None or unit_from is None:
+        return values
+    try:
+        f = _UNIT_FACTORS[(unit_from, unit_to)]
+    except KeyError:
+        raise ValueError(f"pyxsim_b200 cannot convert '{unit_from}' to '{unit_to}'") from None
+    return values * f
+
+
+class ArrayChunk:
+    """One contiguous slab of an ArrayDataSource (the analogue of a yt io chunk)."""
+
+    def __init__(self, src, start, stop):
+        self.src = src
+        self.start = start
+        self.stop = stop
+        self.ds = src
+
+    @property
+    def size(self):
+        return self.stop - self.start
+
+    def __contains__(self, field):
+        return field in self.src.fields
+
+    def __getitem__(self, field):
+        return self.src.fields[field][self.start:self.stop]
+
+    def units(self, field):
+        u = self.src.units.get(field)
+        if u is None:
+            name = field[1] if isinstance(field, tuple) else field
+            u = _DEFAULT_UNITS.get(name)
+        return u
+
+    def to_value(self, field, unit=None):
+        return convert(self[field], self.units(field), unit)
+
+
+class ArrayDataSource:
+    """Array-backed data object (cells or particles).
+
+    fields : dict mapping a field key (any hashable; yt-style tuples recommended) to a 1-D
+        array (NumPy, or torch on host/device).  The geometry fields are looked up by
+        ``position_fields`` / ``velocity_fields`` / ``width_field``.
+    """
+
+    def __init__(self, fields, *, data_type="cells", domain_left_edge=None,
+                 domain_right_edge=None, periodicity=(False, False, False), left_edge=None,
+                 right_edge=None, center=None, position_fields=None, velocity_fields=None,
+                 width_field="default", units=None, chunk_size=None, cosmology=None,
+                 name="ArrayDataSource", ftype="gas"):
+        self.fields = dict(fields)
+        self.units = dict(units or {})
+        self.data_type = data_type
+        self.name = name
+        self.ftype = ftype
+        any_field = next(iter(self.fields.values()))
+        self.size = int(any_field.shape[0])
+        for k, v in self.fields.items():
+            if v.ndim != 1 or v.shape[0] != self.size:
+                raise ValueError(f"field {k} must be 1-D with {self.size} entries")
+        if data_type == "cells":
+            pf = [("index", ax) for ax in "xyz"]
+            vf = [(ftype, f"velocity_{ax}") for ax in "xyz"]
+            wf = ("index", "dx")
+        elif data_type == "particles":
+            pf = [(ftype, f"particle_position_{ax}") for ax in "xyz"]
+            vf = [(ftype, f"particle_velocity_{ax}") for ax in "xyz"]
+            wf = (ftype, "smoothing_length")
+        else:
+            raise ValueError("data_type must be 'cells' or 'particles'")
+        self.position_fields = list(position_fields or pf)
+        self.velocity_fields = list(velocity_fields or vf)
+        self.width_field = wf if width_field == "default" else width_field
+        if self.width_field is not None and self.width_field not in self.fields:
+            self.width_field = None
+        self.periodicity = tuple(bool(p) for p in periodicity)
+        self.domain_left_edge = None if domain_left_edge is None else np.asarray(domain_left_edge, "float64")
+        self.domain_right_edge = None if domain_right_edge is None else np.asarray(domain_right_edge, "float64")
+        if self.domain_left_edge is None:
+            lo, hi = [], []
+            for f in self.position_fields:
+                v = self.fields[f]
+                lo.append(float(v.min()))
+                hi.append(float(v.max()))
+            self.domain_left_edge = np.array(lo)
+            self.domain_right_edge = np.array(hi)
+        self.left_edge = self.domain_left_edge if left_edge is None else np.asarray(left_edge, "float64")
+        self.right_edge = self.domain_right_edge if right_edge is None else np.asarray(right_edge, "float64")
+        self.domain_width = self.domain_right_edge - self.domain_left_edge
+        self.center = 0.5 * (self.left_edge + self.right_edge) if center is None else np.asarray(center, "float64")
+        self.chunk_size = chunk_size
+        self.cosmology = cosmology
+
+    def chunks(self, rank=0, size=1):
+        """Yield chunks; with ``size`` > 1 chunks are dealt round-robin over ranks like yt's
+        ``parallel_objects`` (photon_list.py:401)."""
+        cs = self.chunk_size or self.size
+        starts = list(range(0, self.size, cs)) or [0]
+        for j, s in enumerate(starts):
+            if j % size == rank:
+                yield ArrayChunk(self, s, min(s + cs, self.size))
+
+    def __repr__(self):
+        return f"{self.name}({self.data_type}, n={self.size})"
+
+
+def is_yt_object(obj):
+    return hasattr(obj, "ds") and hasattr(obj, "chunks") and not isinstance(obj, ArrayDataSource)

@@ -1,0 +1,77 @@
+"""Multi-GPU plumbing: one process per GPU, ``torch.distributed`` for the only collectives
+the path has -- the scalar count reductions of pyxsim/photon_list.py:471-472,826.
+
+Cells/particles shard over ranks with no data-path exchange (the reference deals yt chunks
+round-robin over MPI ranks, photon_list.py:401, and writes one file per rank, :214-216);
+each rank keeps its own photon/event shard ``{prefix}.{rank:04d}``.
+"""
+import os
+
+import torch
+import torch.distributed as dist
+
+
+def is_initialized():
+    return dist.is_available() and dist.is_initialized()
+
+
+def rank():
+    return dist.get_rank() if is_initialized() else 0
+
+
+def size():
+    return dist.get_world_size() if is_initialized() else 1
+
+
+def init_from_env(backend=None):
+    """Initialise the default process group from torchrun's environment (no-op when
+    WORLD_SIZE is unset or 1).  Binds this process to ``cuda:LOCAL_RANK`` when CUDA exists."""
+    ws = int(os.environ.get("WORLD_SIZE", "1"))
+    if torch.cuda.is_available():
+        torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
+    if ws <= 1 or is_initialized():
+        return
+    if backend is None:
+        backend = "nccl" if torch.cuda.is_available() else "gloo"
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    dist.init_process_group(backend=backend)
+
+
+def _device():
+    if is_initialized() and dist.get_backend() == "nccl":
+        return torch.device("cuda", torch.cuda.current_device())
+    return torch.device("cpu")
+
+
+def allreduce_sum(value):
+    """Sum of an integer over ranks (comm.mpi_allreduce in the reference)."""
+    if size() == 1:
+        return int(value)
+    t = torch.tensor([int(value)], dtype=torch.int64, device=_device())
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return int(t.item())
+
+
+def allgather_counts(values):
+    """All-gather a short list of int64 counters: returns a [size, len(values)] tensor on the
+    host.  Used to derive global offsets (exclusive prefix over ranks) for concatenated output."""
+    t = torch.tensor([int(v) for v in values], dtype=torch.int64, device=_device())
+    if size() == 1:
+        return t.cpu().reshape(1, -1)
+    out = [torch.empty_like(t) for _ in range(size())]
+    dist.all_gather(out, t)
+    return torch.stack(out).cpu()
+
+
+def barrier():
+    if size() > 1:
+        dist.barrier()
+
+
+def shard_bounds(n, block=4096, r=None, s=None):
+    """Block-cyclic ownership of ``n`` cells: rank r owns blocks r, r+s, r+2s ...  Returns the
+    list of (start, stop) ranges; photon-rich core cells are spread over all ranks."""
+    r = rank() if r is None else r
+    s = size() if s is None else s
+    nblocks = (n + block - 1) // block
+    return [(b * block, min((b + 1) * block, n)) for b in range(r, nblocks, s)]

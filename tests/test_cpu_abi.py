@@ -1,0 +1,76 @@
+"""CPU: the C-ABI library loads, exports every symbol include/pxb.h declares, and its struct
+layout matches the ctypes binding.  No compute calls (no GPU here)."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from pyxsim_b200 import build, _lib
+
+    build.build()
+    return _lib.load()
+
+
+def header_symbols():
+    src = open(os.path.join(ROOT, "include", "pxb.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(pxb_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_every_declared_symbol_is_exported(lib):
+    syms = header_symbols()
+    assert len(syms) >= 24
+    for s in syms:
+        assert hasattr(lib, s), f"{s} declared in include/pxb.h but not exported by libpxb.so"
+
+
+def test_binding_covers_header(lib):
+    from pyxsim_b200 import _lib
+
+    assert sorted(_lib.SIGNATURES) == header_symbols()
+
+
+def test_struct_layout_matches(lib):
+    from pyxsim_b200 import _lib
+
+    sizes = (C.c_int64 * 8)()
+    n = lib.pxb_struct_sizes(sizes, 8)
+    assert n == 8
+    assert [int(v) for v in sizes] == [C.sizeof(t) for t in _lib.ABI_STRUCTS]
+    assert lib.pxb_struct_sizes(sizes, 2) < 0
+    assert b"room" in lib.pxb_last_error()
+
+
+def test_no_device_is_a_loud_error(lib):
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is visible")
+    assert lib.pxb_device_info(None, None, None) == -4
+    assert b"no CPU fallback" in lib.pxb_last_error()
+    import pyxsim_b200 as px
+    import numpy as np
+
+    src = px.ArrayDataSource({("gas", "kT"): np.ones(4), ("gas", "emission_measure"): np.ones(4),
+                              ("index", "x"): np.zeros(4), ("index", "y"): np.zeros(4),
+                              ("index", "z"): np.zeros(4)})
+    sm = px.ThermalSpectralModel(np.linspace(0.1, 1, 11), np.array([0.5, 2.0]),
+                                 np.ones((2, 10)), np.ones((2, 10)))
+    model = px.ThermalSourceModel(sm, 0.1, 1.0, 10, 0.3, temperature_field=("gas", "kT"))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        px.make_photons("mem:x", src, 0.05, 100.0, 100.0, model)
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "pyxsim_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh")):
+                txt = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in txt and "from oracle" not in txt, f

@@ -1,0 +1,338 @@
+"""GPU parity: projection (Doppler, absorption, scatter, sky transform, compaction) and the
+power-law / line generators against the oracle (reference Cython + restated glue)."""
+import numpy as np
+import pytest
+import torch
+from scipy import stats
+
+import pyxsim_b200 as px
+from pyxsim_b200 import _lib, synthetic
+from pyxsim_b200.device import empty, ptr, stream_ptr, to_device
+from pyxsim_b200.photon_list import DeviceList, save_list, load_list
+
+import helpers as H
+
+pytestmark = pytest.mark.gpu
+
+
+def make_plist(n_cells=3000, mean_ph=40.0, data_type="cells", seed=13, observer="external",
+               zero_cells=False, redshift=0.05):
+    rng = np.random.RandomState(seed)
+    nph = rng.poisson(mean_ph * rng.lognormal(0, 1.0, n_cells)).astype(np.int64)
+    if not zero_cells:
+        nph = np.maximum(nph, 1)
+    d = dict(x=rng.uniform(-300, 300, n_cells), y=rng.uniform(-300, 300, n_cells),
+             z=rng.uniform(-300, 300, n_cells), vx=rng.normal(0, 500, n_cells),
+             vy=rng.normal(0, 500, n_cells), vz=rng.normal(100, 500, n_cells),
+             dx=rng.uniform(2.0, 30.0, n_cells), num_photons=nph,
+             energy=np.exp(rng.uniform(np.log(0.1), np.log(10.0), int(nph.sum()))))
+    params = dict(fid_exp_time=1.0e5, fid_area=1000.0, fid_redshift=redshift, fid_d_a=200.0,
+                  data_type=data_type, observer=observer)
+    return d, params
+
+
+def put(name, d, params):
+    save_list("mem:" + name, DeviceList({}, params, {k: torch.from_numpy(v).cuda() for k, v in d.items()}))
+    return "mem:" + name
+
+
+def events(name):
+    lst = load_list("mem:" + name)
+    return {k: lst.numpy(k) for k in lst.data}, lst.parameters
+
+
+# ---------------------------------------------------------------------------------------
+# deterministic natives
+# ---------------------------------------------------------------------------------------
+def test_doppler_shift_matches_reference(cuda, oracle):
+    d, _ = make_plist(zero_cells=True)
+    sf = oracle.ref()["sky_functions"]
+    bn = d["vz"] * oracle.scale_shift
+    b2 = (d["vx"] ** 2 + d["vy"] ** 2 + d["vz"] ** 2) * oracle.scale_shift2
+    e_ref = d["energy"].copy()
+    sf.doppler_shift(bn, b2, d["num_photons"], e_ref)
+    poff = np.concatenate([[0], np.cumsum(d["num_photons"])]).astype(np.int64)
+    e = to_device(d["energy"].copy())
+    _lib.call("pxb_doppler_shift", d["num_photons"].size, ptr(to_device(bn)), ptr(to_device(b2)),
+              ptr(to_device(poff, torch.int64)), e.numel(), ptr(e), stream_ptr())
+    np.testing.assert_allclose(e.cpu().numpy(), e_ref, rtol=2e-16, atol=0)
+
+
+def test_pixel_to_cel_known_answer(cuda, oracle):
+    """pyxsim/tests/test_pixel_to_cel.py with the analytic TAN inverse as the known answer
+    (astropy is not installed) and the reference Cython beside it."""
+    prng = np.random.RandomState(24)
+    n_evt = 100000
+    rr = 100.0 * prng.uniform(size=n_evt)
+    theta = 2.0 * np.pi * prng.uniform(size=n_evt)
+    xx = rr * np.cos(theta) / 1.0e5
+    yy = rr * np.sin(theta) / 1.0e5
+    xs, ys = to_device(xx.copy()), to_device(yy.copy())
+    _lib.call("pxb_pixel_to_cel", n_evt, ptr(xs), ptr(ys), 30.0, 45.0, stream_ptr())
+    ra, dec = oracle.tan_known_answer(xx, yy, 30.0, 45.0)
+    np.testing.assert_allclose(xs.cpu().numpy(), ra, rtol=1e-7)       # the reference test's bar
+    np.testing.assert_allclose(ys.cpu().numpy(), dec, rtol=1e-7)
+    x1, y1 = xx.copy(), yy.copy()
+    oracle.ref()["sky_functions"].pixel_to_cel(x1, y1, np.array([30.0, 45.0]))
+    np.testing.assert_allclose(xs.cpu().numpy(), x1, rtol=1e-12)
+    np.testing.assert_allclose(ys.cpu().numpy(), y1, rtol=1e-12)
+
+
+@pytest.mark.parametrize("kind", ["table_log", "table_lin", "table_irregular", "wabs"])
+def test_absorb_transmission(cuda, oracle, kind):
+    rng = np.random.RandomState(2)
+    e = np.exp(rng.uniform(np.log(0.02), np.log(20.0), 50000))
+    if kind == "wabs":
+        prod, orc = px.WabsModel(0.07), oracle.WabsAbsorb(0.07)
+    else:
+        en, sg = synthetic.tbabs_like_sigma(n=3000)
+        if kind == "table_lin":
+            en2 = np.linspace(en[0], en[-1], 5000)
+            sg = np.interp(en2, en, sg)
+            en = en2
+        elif kind == "table_irregular":
+            keep = np.sort(rng.choice(en.size, 1500, replace=False))
+            en, sg = en[keep], sg[keep]
+        prod, orc = px.TBabsModel(0.07, energy=en, cross_section=sg), oracle.TableAbsorb(0.07, en, sg)
+    np.testing.assert_allclose(prod.get_absorb(e), orc.get_absorb(e), rtol=1e-12, atol=1e-300)
+
+
+# ---------------------------------------------------------------------------------------
+# projection invariants and distributions
+# ---------------------------------------------------------------------------------------
+def test_no_shift_no_absorb_identity(cuda):
+    """pyxsim/tests/test_sloshing.py:96-117: without shifting and absorption every photon
+    becomes an event and the event energies ARE the photon energies (same order)."""
+    d, p = make_plist(zero_cells=True)
+    put("id_ph", d, p)
+    n = px.project_photons("mem:id_ph", "mem:id_ev", "z", [30.0, 45.0], no_shifting=True, prng=3)
+    ev, par = events("id_ev")
+    assert n == d["energy"].size == ev["eobs"].size
+    assert np.array_equal(ev["eobs"], d["energy"])
+    assert par["emin"] == d["energy"].min() and par["emax"] == d["energy"].max()
+    flux = d["energy"].sum() * 1.602176634e-9 / p["fid_exp_time"] / p["fid_area"]
+    np.testing.assert_allclose(par["flux"], flux, rtol=1e-12)
+
+
+@pytest.mark.parametrize("normal", ["x", "y", "z", [0.3, -0.5, 0.8]])
+def test_doppler_in_projection(cuda, oracle, normal):
+    d, p = make_plist()
+    put("dop_ph", d, p)
+    n = px.project_photons("mem:dop_ph", "mem:dop_ev", normal, [30.0, 45.0], prng=3)
+    ev, _ = events("dop_ev")
+    ref = oracle.project_photons(d, p, normal, [30.0, 45.0], np.random.RandomState(1))
+    assert n == ref["n_events"] == d["energy"].size
+    np.testing.assert_allclose(ev["eobs"], ref["eobs"], rtol=4e-16, atol=0)
+
+
+def _ks_ok(a, b, pmin=0.01):
+    return stats.ks_2samp(a, b).pvalue > pmin
+
+
+@pytest.mark.parametrize("case", [
+    dict(normal="z", data_type="cells"),
+    dict(normal="x", data_type="cells", flat_sky=True),
+    dict(normal=[1.0, -2.0, 5.0], data_type="cells"),
+    dict(normal=[1.0, -2.0, 5.0], data_type="cells", north_vector=[0.0, 0.0, 1.0], sigma_pos=0.5),
+    dict(normal="y", data_type="particles", kernel="top_hat"),
+    dict(normal=[0.2, 0.9, -0.4], data_type="particles", kernel="gaussian"),
+    dict(normal="z", data_type="cells", phys_coord=True),
+])
+def test_scatter_and_absorb_distributions(cuda, oracle, case):
+    """Sky positions, line-of-sight and energies of the events against the oracle's: KS on
+    every coordinate (both are random draws of the same distributions), absorbed fraction
+    within binomial error, LOS coordinates exactly equal as multisets."""
+    case = dict(case)
+    normal = case.pop("normal")
+    data_type = case.pop("data_type")
+    d, p = make_plist(n_cells=2000, mean_ph=60.0, data_type=data_type)
+    en, sg = synthetic.tbabs_like_sigma()
+    put("sc_ph", d, p)
+    n = px.project_photons("mem:sc_ph", "mem:sc_ev", normal, [30.0, 45.0],
+                           absorb_model=px.TBabsModel(0.15, energy=en, cross_section=sg), nH=0.15,
+                           save_los=True, prng=17, **case)
+    ev, par = events("sc_ev")
+    ref = oracle.project_photons(d, p, normal, [30.0, 45.0], np.random.RandomState(5),
+                                 absorb_model=oracle.TableAbsorb(0.15, en, sg), nH=0.15,
+                                 save_los=True, **case)
+    ntot = d["energy"].size
+    assert 0.2 * ntot < n < 0.98 * ntot
+    pbar = 0.5 * (n + ref["n_events"]) / ntot
+    assert abs(n - ref["n_events"]) < 5 * np.sqrt(2 * ntot * pbar * (1 - pbar))
+    for k in ("xsky", "ysky", "eobs", "los"):
+        assert _ks_ok(ev[k], ref[k]), k
+    # per-cell residuals: offsets relative to the cell centre isolate the scatter kernel
+    assert ev["eobs"].min() == par["emin"] and ev["eobs"].max() == par["emax"]
+    np.testing.assert_allclose(par["flux"], ev["eobs"].sum() * 1.602176634e-9 / 1e5 / 1e3, rtol=1e-12)
+
+
+@pytest.mark.parametrize("data_type,kernel", [("cells", "top_hat"), ("particles", "top_hat"),
+                                               ("particles", "gaussian")])
+def test_scatter_kernel_shape(cuda, oracle, data_type, kernel):
+    """One cell, many photons, no absorption: the scatter offsets themselves (physical
+    coordinates) must follow the reference kernel -- including r ~ U(0,1) for the top-hat."""
+    n = 200000
+    d = dict(x=np.array([10.0]), y=np.array([-20.0]), z=np.array([5.0]), vx=np.zeros(1),
+             vy=np.zeros(1), vz=np.zeros(1), dx=np.array([8.0]),
+             num_photons=np.array([n], dtype=np.int64), energy=np.full(n, 1.0))
+    p = dict(fid_exp_time=1.0, fid_area=1.0, fid_redshift=0.0, fid_d_a=100.0, data_type=data_type,
+             observer="external")
+    put("k_ph", d, p)
+    for normal in ("z", [0.6, 0.0, 0.8]):
+        px.project_photons("mem:k_ph", "mem:k_ev", normal, [0.0, 0.0], kernel=kernel,
+                           phys_coord=True, no_shifting=True, prng=8)
+        ev, _ = events("k_ev")
+        ref = oracle.project_photons(d, p, normal, [0.0, 0.0], np.random.RandomState(6),
+                                     kernel=kernel, phys_coord=True, no_shifting=True)
+        for k in ("xsky", "ysky"):
+            assert _ks_ok(ev[k], ref[k]), (normal, k)
+        r_mine = np.hypot(ev["xsky"] - np.median(ref["xsky"]), ev["ysky"] - np.median(ref["ysky"]))
+        r_ref = np.hypot(ref["xsky"] - np.median(ref["xsky"]), ref["ysky"] - np.median(ref["ysky"]))
+        assert _ks_ok(r_mine, r_ref), normal
+
+
+@pytest.mark.parametrize("data_type,kernel", [("cells", "top_hat"), ("particles", "top_hat"),
+                                               ("particles", "gaussian")])
+def test_allsky_internal_observer(cuda, oracle, data_type, kernel):
+    d, p = make_plist(n_cells=1500, mean_ph=50.0, data_type=data_type, observer="internal",
+                      redshift=0.0)
+    p["fid_d_a"] = 0.0
+    put("as_ph", d, p)
+    normal = [0.1, 0.3, 0.9]
+    n = px.project_photons_allsky("mem:as_ph", "mem:as_ev", normal, absorb_model="wabs", nH=0.05,
+                                  kernel=kernel, save_los=True, center_vector=[1.0, 0.0, 0.0],
+                                  prng=4)
+    ev, _ = events("as_ev")
+    ref = oracle.project_photons(d, p, normal, [0.0, 0.0], np.random.RandomState(9),
+                                 absorb_model=oracle.WabsAbsorb(0.05), nH=0.05, kernel=kernel,
+                                 save_los=True, north_vector=[1.0, 0.0, 0.0])
+    assert abs(n - ref["n_events"]) < 6 * np.sqrt(ref["n_events"])
+    for k in ("xsky", "ysky", "eobs", "los"):
+        assert _ks_ok(ev[k], ref[k]), k
+    assert ev["xsky"].min() >= 0 and ev["xsky"].max() <= 360 and np.abs(ev["ysky"]).max() <= 90
+
+
+def test_internal_absorption_per_cell(cuda, oracle):
+    d, p = make_plist(n_cells=800, mean_ph=80.0)
+    rng = np.random.RandomState(3)
+    nhc = rng.uniform(0.0, 0.5, 800)
+    en, sg = synthetic.tbabs_like_sigma()
+    put("ia_ph", d, p)
+    n = px.project_photons("mem:ia_ph", "mem:ia_ev", "z", [30.0, 45.0],
+                           absorb_model=px.TBabsModel(0.02, energy=en, cross_section=sg), nH=0.02,
+                           nH_cell=nhc, prng=12)
+    ev, _ = events("ia_ev")
+    ref = oracle.project_photons(d, p, "z", [30.0, 45.0], np.random.RandomState(2),
+                                 absorb_model=oracle.TableAbsorb(0.02, en, sg), nH=0.02, nH_int=nhc)
+    assert abs(n - ref["n_events"]) < 6 * np.sqrt(ref["n_events"])
+    assert _ks_ok(ev["eobs"], ref["eobs"])
+
+
+def test_projection_bit_reproducible_and_stable_order(cuda):
+    d, p = make_plist(n_cells=5000, mean_ph=30.0)
+    put("rp_ph", d, p)
+    runs = []
+    for _ in range(3):
+        px.project_photons("mem:rp_ph", "mem:rp_ev", [0.2, 0.3, 0.9], [10.0, -30.0],
+                           absorb_model="wabs", nH=0.1, save_los=True, prng=99)
+        ev, par = events("rp_ev")
+        runs.append((ev, par))
+    for ev, par in runs[1:]:
+        for k in ev:
+            assert np.array_equal(ev[k], runs[0][0][k]), k
+        assert par["flux"] == runs[0][1]["flux"]
+    # stable compaction: events are a subsequence of the Doppler-shifted photon list
+    px.project_photons("mem:rp_ph", "mem:rp_all", [0.2, 0.3, 0.9], [10.0, -30.0], prng=99)
+    allev, _ = events("rp_all")
+    e_all, e_det = allev["eobs"], runs[0][0]["eobs"]
+    ok = True
+    idx = 0
+    for v in e_det[:20000]:
+        while idx < e_all.size and e_all[idx] != v:
+            idx += 1
+        if idx == e_all.size:
+            ok = False
+            break
+        idx += 1
+    assert ok
+
+
+def test_photon_list_with_empty_cells_and_errors(cuda):
+    d, p = make_plist(n_cells=4000, mean_ph=0.3, zero_cells=True)
+    assert (d["num_photons"] == 0).sum() > 1000
+    put("z_ph", d, p)
+    n = px.project_photons("mem:z_ph", "mem:z_ev", "z", [0.0, 0.0], no_shifting=True, prng=1)
+    assert n == d["energy"].size
+    with pytest.raises(KeyError):
+        px.project_photons("mem:z_ph", "mem:z_ev", "z", [0.0, 0.0], absorb_model="nope", nH=0.1)
+    with pytest.raises(RuntimeError):
+        px.project_photons_allsky("mem:z_ph", "mem:z_ev", [0, 0, 1.0])
+    p2 = dict(p, data_type="particles")
+    put("z2_ph", d, p2)
+    with pytest.raises(RuntimeError):
+        px.project_photons("mem:z2_ph", "mem:z_ev", "z", [0.0, 0.0], sigma_pos=1.0)
+
+
+# ---------------------------------------------------------------------------------------
+# power law / line
+# ---------------------------------------------------------------------------------------
+def test_powerlaw_counts_and_energies(cuda, oracle):
+    n = 4000
+    rng = np.random.RandomState(33)
+    alpha = rng.uniform(0.5, 2.5, n)
+    alpha[:200] = 1.0
+    alpha[200:400] = 2.0
+    lum = 1.0e45 * rng.lognormal(0, 1, n)
+    src = px.ArrayDataSource({("gas", "lum"): lum, ("gas", "alpha"): alpha,
+                              ("index", "x"): np.zeros(n), ("index", "y"): np.zeros(n),
+                              ("index", "z"): np.zeros(n)}, units={("gas", "lum"): "keV/s"})
+    model = px.PowerLawSourceModel(1.0, 0.5, 40.0, ("gas", "lum"), ("gas", "alpha"), prng=33)
+    z = 0.5
+    model.setup_model("photons", src, z)
+    norm = 3.0e-44
+    lam, counts = model.expected_counts(next(src.chunks()), norm)
+    cfg = dict(e0=1.0, emin=0.5, emax=40.0, spectral_norm=norm, scale_factor=1 / (1 + z))
+    rlam, _, _ = oracle.powerlaw_lambda(cfg, lum, alpha)
+    np.testing.assert_allclose(lam.cpu().numpy(), rlam, rtol=1e-12)
+    out = model.generate_chunk(next(src.chunks()), norm)
+    nc, onph, oact, oe = oracle.powerlaw_process_data(cfg, lum, alpha, np.random.RandomState(1))
+    e = out.energy.cpu().numpy()
+    assert abs(e.size - rlam.sum()) < 6 * np.sqrt(rlam.sum())
+    assert e.min() >= 0.5 / 1.5 * (1 - 1e-12) and e.max() <= 40.0 / 1.5 * (1 + 1e-12)
+    assert _ks_ok(e, oe)
+    # alpha == 1 and alpha == 2 cells separately
+    idx, nph = out.idx.cpu().numpy(), out.nph.cpu().numpy()
+    off = np.concatenate([[0], np.cumsum(nph)])
+    ooff = np.concatenate([[0], np.cumsum(onph)])
+    oidx = np.where(oact)[0]
+    for lo, hi in ((0, 200), (200, 400)):
+        mine = np.concatenate([e[off[k]:off[k + 1]] for k in np.where((idx >= lo) & (idx < hi))[0]])
+        theirs = np.concatenate([oe[ooff[k]:ooff[k + 1]] for k in np.where((oidx >= lo) & (oidx < hi))[0]])
+        assert _ks_ok(mine, theirs)
+    # the reference returns a bool mask
+    res = model.process_data("photons", next(src.chunks()), norm)
+    assert res[2].dtype == bool and res[2].sum() == res[0]
+
+
+def test_line_counts_and_energies(cuda, oracle):
+    n = 3000
+    rng = np.random.RandomState(3)
+    rate = 1.0e42 * rng.lognormal(0, 1, n)
+    sig_kms = rng.uniform(100.0, 2000.0, n)
+    src = px.ArrayDataSource({("gas", "line"): rate, ("gas", "sig"): sig_kms,
+                              ("index", "x"): np.zeros(n), ("index", "y"): np.zeros(n),
+                              ("index", "z"): np.zeros(n)})
+    z = 0.2
+    norm = 5.0e-41
+    cfg = dict(e0=3.5, spectral_norm=norm, scale_factor=1 / (1 + z))
+    for sigma, sig_keV in ((("gas", "sig")), sig_kms * 3.5 / 299792.458), ((1000.0, "km/s"), 1000.0 * 3.5 / 299792.458), (0.02, 0.02):
+        model = px.LineSourceModel(3.5, ("gas", "line"), sigma, prng=5)
+        model.setup_model("photons", src, z)
+        lam, _ = model.expected_counts(next(src.chunks()), norm)
+        nc, onph, oact, oe, F = oracle.line_process_data(cfg, rate, sig_keV, np.random.RandomState(4))
+        np.testing.assert_allclose(lam.cpu().numpy(), F, rtol=1e-14)
+        out = model.generate_chunk(next(src.chunks()), norm)
+        e = out.energy.cpu().numpy()
+        assert abs(e.size - F.sum()) < 1.645 * 4 * np.sqrt(F.sum())
+        assert _ks_ok(e, oe)
+        assert abs(e.mean() - 3.5 / 1.2) < 5 * e.std() / np.sqrt(e.size)
