@@ -185,7 +185,7 @@ def thermal_select(cfg, a):
     cell_nrm = np.ravel(a["em"] * cfg["spectral_norm"])
     nH = np.ravel(a["nH"]) if a.get("nH") is not None else None
     hf = cfg.get("h_fraction", 0.7)
-    X_H = hf if np.isscalar(hf) else np.ravel(a[hf])
+    X_H = np.ravel(a[hf]) if isinstance(hf, str) else hf
     num_cells = int(cut.sum())
     kT = kT[cut]
     cell_nrm = cell_nrm[cut]
@@ -194,7 +194,7 @@ def thermal_select(cfg, a):
     X_Hc = X_H if np.isscalar(X_H) else X_H[cut]
     if cfg.get("nei"):
         metalZ = np.zeros(num_cells)
-    elif np.isscalar(cfg["Zmet"]):
+    elif not isinstance(cfg["Zmet"], str):
         metalZ = cfg["Zmet"] * np.ones(num_cells)
     else:
         mZ = np.ravel(a[cfg["Zmet"]])
@@ -207,7 +207,7 @@ def thermal_select(cfg, a):
     if len(var) > 0:
         elemZ = np.zeros((len(var), num_cells))
         for j, (value, mconv, by_xh) in enumerate(var):
-            if np.isscalar(value):
+            if not isinstance(value, str):
                 elemZ[j, :] = value
             else:
                 eZ = np.ravel(a[value])

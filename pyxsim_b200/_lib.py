@@ -191,4 +191,7 @@ def check(status):
 
 
 def call(name, *args):
+    from . import profiling
+
+    profiling.count_call(name)
     check(getattr(load(), name)(*args))

@@ -19,6 +19,7 @@ import torch
 from . import _lib, constants as K, parallel
 from .data import ArrayDataSource, Cosmology
 from .device import empty, ptr, stream_ptr, to_device, require_cuda
+from .profiling import stage
 from .spectral_models import absorb_models
 from .utils import get_normal_and_north, mylog, parse_value, prng_seed
 
@@ -526,8 +527,9 @@ def _project_photons(obs, photon_prefix, event_prefix, normal, sky_center, absor
         los = empty(n_photons) if save_los else None
         nev = empty(1, torch.int64)
         stats = empty(3)
-        _lib.call("pxb_project", C.byref(PL), C.byref(P), ptr(xsky), ptr(ysky), ptr(eobs), ptr(los),
-                  ptr(nev), ptr(stats), ptr(ws), need.value, stream_ptr())
+        with stage("project"):
+            _lib.call("pxb_project", C.byref(PL), C.byref(P), ptr(xsky), ptr(ysky), ptr(eobs),
+                      ptr(los), ptr(nev), ptr(stats), ptr(ws), need.value, stream_ptr())
         n_events = int(nev.cpu()[0])
         st = stats.cpu().numpy()
         del keep, ws

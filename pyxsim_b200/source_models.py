@@ -16,6 +16,7 @@ import torch
 from . import _lib, constants as K
 from .data import ArrayChunk, ArrayDataSource
 from .device import empty, ptr, stream_ptr, to_device, require_cuda
+from .profiling import stage
 from .utils import mylog, parse_prng, parse_value, prng_seed
 
 
@@ -136,8 +137,9 @@ class SourceModel:
         offsets = empty(n + 1, torch.int64)
         arank = empty(n + 1, torch.int64)
         totals = empty(2, torch.int64)
-        _lib.call("pxb_scan_counts", ptr(counts), n, ptr(offsets), ptr(arank), ptr(totals),
-                  ptr(self._scan_ws), self._scan_ws.numel(), stream_ptr())
+        with stage("scan_counts"):
+            _lib.call("pxb_scan_counts", ptr(counts), n, ptr(offsets), ptr(arank), ptr(totals),
+                      ptr(self._scan_ws), self._scan_ws.numel(), stream_ptr())
         n_photons, n_active = (int(v) for v in totals.cpu())  # the one sync of the chunk
         out = ChunkPhotons()
         out.n_cells, out.n_photons = n_active, n_photons
@@ -158,10 +160,11 @@ class SourceModel:
                 dx = to_device(field_value(chunk, wf, "kpc"))
             for name in ("x", "y", "z", "vx", "vy", "vz", "dx"):
                 setattr(out, name, empty(n_active))
-        _lib.call("pxb_compact_cells", n, ptr(counts), ptr(offsets), ptr(arank), ptr(x), ptr(y),
-                  ptr(z), ptr(vx), ptr(vy), ptr(vz), ptr(dx), C.byref(G), ptr(out.idx),
-                  ptr(out.nph), ptr(out.poff), ptr(out.x), ptr(out.y), ptr(out.z), ptr(out.vx),
-                  ptr(out.vy), ptr(out.vz), ptr(out.dx), stream_ptr())
+        with stage("compact_cells"):
+            _lib.call("pxb_compact_cells", n, ptr(counts), ptr(offsets), ptr(arank), ptr(x), ptr(y),
+                      ptr(z), ptr(vx), ptr(vy), ptr(vz), ptr(dx), C.byref(G), ptr(out.idx),
+                      ptr(out.nph), ptr(out.poff), ptr(out.x), ptr(out.y), ptr(out.z), ptr(out.vx),
+                      ptr(out.vy), ptr(out.vz), ptr(out.dx), stream_ptr())
         return out
 
     def generate_chunk(self, chunk, spectral_norm, gather=None):
@@ -383,13 +386,15 @@ class ThermalSourceModel(SourceModel):
         Cs = self._cells_struct(chunk, spectral_norm, keep)
         dm = self.spectral_model.device_model(self.method)
         counts = empty(Cs.ncell, torch.int64)
-        _lib.call("pxb_thermal_counts", dm.handle, C.byref(Cs), None, ptr(counts), stream_ptr())
+        with stage("thermal_counts"):
+            _lib.call("pxb_thermal_counts", dm.handle, C.byref(Cs), None, ptr(counts), stream_ptr())
         out = self._scan_and_compact(counts, chunk, gather)
         if out.n_photons == 0:
             return None
         out.energy = empty(out.n_photons)
-        _lib.call("pxb_thermal_sample", dm.handle, C.byref(Cs), out.n_cells, ptr(out.idx),
-                  ptr(out.nph), ptr(out.poff), out.n_photons, ptr(out.energy), stream_ptr())
+        with stage("thermal_sample"):
+            _lib.call("pxb_thermal_sample", dm.handle, C.byref(Cs), out.n_cells, ptr(out.idx),
+                      ptr(out.nph), ptr(out.poff), out.n_photons, ptr(out.energy), stream_ptr())
         return out
 
 

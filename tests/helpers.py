@@ -51,3 +51,18 @@ def ks_2samp_p(a, b):
     from scipy.stats import ks_2samp
 
     return ks_2samp(a, b).pvalue
+
+
+def assert_distributions_agree(run, seeds=((17, 5), (18, 6)), pmin=0.01):
+    """``run(seed_mine, seed_ref) -> {name: p-value}``.  Every comparison must reach
+    p > 0.01 (BASELINE.json north_star); a comparison that falls below gets ONE retry with
+    fresh, independent seeds and must pass then, which puts the false-alarm rate of a correct
+    implementation near 1e-4 per comparison instead of 1e-2 while a real discrepancy still
+    fails twice."""
+    ps = run(*seeds[0])
+    bad = [k for k, v in ps.items() if not v > pmin]
+    if not bad:
+        return
+    ps2 = run(*seeds[1])
+    still = {k: (ps[k], ps2[k]) for k in bad if not ps2[k] > pmin}
+    assert not still, f"distributions disagree twice: {still}"
