@@ -150,11 +150,17 @@ int pxb_interp_spec(const pxb_model* model, int64_t n, const double* x_vals,
                     double* c_out, double* m_out, double* v_out, void* stream);
 
 /* Inverse-CDF energy sampling for the active cells.  idx[k] is the chunk-local cell index,
- * nph[k] its photon count, poff[k] its first slot in `energies`. */
+ * nph[k] its photon count, poff[k] its first slot in `energies` (poff has n_active+1 entries).
+ * Two device paths with the same output distribution: cells whose tables, abundances and
+ * interpolation weights are all non-negative are sampled as a mixture of per-row CDFs
+ * (thread per photon); every other cell gets its own blended + clipped CDF in shared memory
+ * (CTA per cell).  The order of the photons inside a cell is not a contract (the reference
+ * sorts its uniforms, base.py:481). */
+int pxb_thermal_sample_workspace_bytes(int64_t n_active, int64_t* bytes);
 int pxb_thermal_sample(const pxb_model* model, const pxb_thermal_cells* cells,
                        int64_t n_active, const int64_t* idx, const int64_t* nph,
                        const int64_t* poff, int64_t n_photons, double* energies,
-                       void* stream);
+                       void* workspace, int64_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------
  * Counts -> offsets, active-cell compaction

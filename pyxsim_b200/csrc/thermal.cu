@@ -67,6 +67,43 @@ static int build_table(pxb_model* m, const pxb_table_desc& d, DevTable& t) {
     row_sums(d.var, (int64_t)t.nrows * d.nvar, d.nbins, rs, &t.nonneg);
     if ((rc = upload(m, rs.data(), rs.size() * sizeof(double), (const void**)&t.rs_v))) return rc;
   }
+  if (t.nonneg && d.nbins < 65536) {
+    // per-row normalised CDFs + guide tables for the mixture sampler
+    const int ntab = 2 + d.nvar;
+    const size_t nb = (size_t)d.nbins;
+    std::vector<double> cdf((size_t)ntab * t.nrows * (nb + 1));
+    std::vector<uint16_t> guide((size_t)ntab * t.nrows * nb);
+    for (int tb = 0; tb < ntab; ++tb) {
+      const double* tab = tb == 0 ? d.cosmic : (tb == 1 ? d.metal : d.var + (size_t)(tb - 2) * t.nrows * nb);
+      for (int r = 0; r < t.nrows; ++r) {
+        const double* p = tab + (size_t)r * nb;
+        double* c = cdf.data() + ((size_t)tb * t.nrows + r) * (nb + 1);
+        uint16_t* g = guide.data() + ((size_t)tb * t.nrows + r) * nb;
+        long double tot = 0.0L;
+        for (size_t j = 0; j < nb; ++j) tot += p[j];
+        long double run = 0.0L;
+        c[0] = 0.0;
+        for (size_t j = 0; j < nb; ++j) {
+          run += p[j];
+          c[j + 1] = tot > 0.0L ? (double)(run / tot) : 0.0;
+        }
+        if (tot > 0.0L) {
+          // everything from the last non-empty bin on is exactly 1
+          size_t last = nb;
+          while (last > 0 && p[last - 1] == 0.0) --last;
+          for (size_t j = last; j <= nb; ++j) c[j] = 1.0;
+        }
+        size_t j = 0;
+        for (size_t k = 0; k < nb; ++k) {
+          const double q = (double)k / (double)nb;
+          while (j + 1 < nb && c[j + 1] <= q) ++j;
+          g[k] = (uint16_t)j;
+        }
+      }
+    }
+    if ((rc = upload(m, cdf.data(), cdf.size() * sizeof(double), (const void**)&t.rowcdf))) return rc;
+    if ((rc = upload(m, guide.data(), guide.size() * sizeof(uint16_t), (const void**)&t.guide))) return rc;
+  }
   return PXB_OK;
 }
 
@@ -114,6 +151,7 @@ extern "C" int pxb_model_create(const pxb_model_desc* desc, pxb_model** out) {
     D.kT_lo = desc->kT_lo; D.kT_hi = desc->kT_hi; D.nH_lo = desc->nH_lo; D.nH_hi = desc->nH_hi;
     rc = upload(m, desc->bin_edges, (D.nbins + 1) * sizeof(double), (const void**)&D.edges);
     if (!rc) rc = upload(m, desc->emid, D.nbins * sizeof(double), (const void**)&D.emid);
+    D.fast_ok = D.prim.rowcdf != nullptr && (!D.has_fb || D.fb.rowcdf != nullptr);
   }
   if (rc) { pxb_model_destroy(m); return rc; }
   *out = m;
@@ -334,7 +372,8 @@ __global__ void __launch_bounds__(SAMPLE_THREADS)
 k_thermal_sample_cta(const DevModel M, const __grid_constant__ pxb_thermal_cells C,
                      int64_t n_active, const int64_t* __restrict__ idx,
                      const int64_t* __restrict__ nph, const int64_t* __restrict__ poff,
-                     double* __restrict__ energies) {
+                     double* __restrict__ energies, const int64_t* __restrict__ list,
+                     const int64_t* __restrict__ list_count) {
   extern __shared__ double smem[];
   double* cdf = smem;                       // nbins + 1
   double* s_eZ = smem + (M.nbins + 1);      // PXB_MAX_VAR
@@ -344,7 +383,10 @@ k_thermal_sample_cta(const DevModel M, const __grid_constant__ pxb_thermal_cells
   const int nbins = M.nbins;
   const int seg = ((nbins + NW - 1) / NW + 31) & ~31;  // bins per warp, multiple of 32
 
-  for (int64_t k = blockIdx.x; k < n_active; k += gridDim.x) {
+  // with a list only the listed active cells (those the mixture kernel declined) are done
+  const int64_t n_work = list ? *list_count : n_active;
+  for (int64_t kk = blockIdx.x; kk < n_work; kk += gridDim.x) {
+    const int64_t k = list ? list[kk] : kk;
     const int64_t i = idx[k];
     const int64_t N = nph[k];
     const int64_t off = poff[k];
@@ -355,7 +397,7 @@ k_thermal_sample_cta(const DevModel M, const __grid_constant__ pxb_thermal_cells
     const double xh = cell_xh(C, i);
     const double Z = cell_metal(C, i, xh);
     __syncthreads();  // previous cell's sampling is done with cdf/s_eZ
-    for (int kk = threadIdx.x; kk < C.nvar; kk += blockDim.x) s_eZ[kk] = cell_elem(C, kk, i, xh);
+    for (int ke = threadIdx.x; ke < C.nvar; ke += blockDim.x) s_eZ[ke] = cell_elem(C, ke, i, xh);
     if (threadIdx.x == 0) cdf[0] = 0.0;
     __syncthreads();
     // pass 1: per-warp inclusive scan of its contiguous segment
@@ -391,6 +433,176 @@ k_thermal_sample_cta(const DevModel M, const __grid_constant__ pxb_thermal_cells
         st_stream(energies + off + 2 * p + 1, e1);
       }
     }
+  }
+}
+
+
+// ---- energy sampling, mixture fast path ------------------------------------------------
+// When every table entry, abundance and interpolation weight is non-negative the clip of
+// base.py:460 is a no-op and the cell's normalised spectrum is a MIXTURE of the normalised
+// table rows it blends: p_j = sum_c q_c * row_c[j]/rowsum_c with q_c = coef_c*rowsum_c/S.
+// Sampling "pick component c with probability q_c, then invert row c's own CDF" has exactly
+// the distribution of inverting the blended CDF (base.py:471-482), needs no per-cell CDF
+// build, and only touches per-row CDFs + guide tables that are shared by all cells.
+// One thread per photon over tiles; per-tile per-cell setup lives in shared memory.
+#include "tiles.cuh"
+
+constexpr int FAST_THREADS = 256;
+constexpr int FAST_ITEMS = 4;
+constexpr int FAST_TILE = FAST_THREADS * FAST_ITEMS;
+
+struct FastCell {
+  int z1;        // first row
+  int meta;      // bits 0-2: number of rows, bit 3: fallback table, bit 4: eligible
+  double cum[3]; // cumulative row probabilities (last is implicitly 1)
+};
+
+__device__ __forceinline__ int fast_row(const DevTable* t, int z1, int nr, int r) {
+  if (nr == 2) return z1 + r;
+  return z1 + ((r & 1) ? t->nx : 0) + ((r >> 1) ? 1 : 0);   // order of cell_mix: z1, z2, z3, z4
+}
+
+__device__ __forceinline__ FastCell fast_setup(const DevModel& M, const pxb_thermal_cells& C,
+                                               int64_t i) {
+  FastCell fc;
+  const double kT = C.kT[i];
+  const double nH = C.nH ? C.nH[i] : 0.0;
+  CellMix mx;
+  cell_mix(M, kT, nH, mx);
+  const double xh = cell_xh(C, i);
+  const double Z = cell_metal(C, i, xh);
+  const DevTable* t = mx.t;
+  bool ok = mx.interior && (Z >= 0.0);
+  double s[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+  for (int r = 0; r < 4; ++r)
+    if (r < mx.nr) s[r] = __ldg(t->rs_c + mx.row[r]) + Z * __ldg(t->rs_m + mx.row[r]);
+  for (int k = 0; k < C.nvar; ++k) {
+    const double e = cell_elem(C, k, i, xh);
+    ok = ok && (e >= 0.0);
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+      if (r < mx.nr) s[r] += e * __ldg(t->rs_v + (size_t)k * t->nrows + mx.row[r]);
+  }
+  double tot = 0.0;
+  int last = 0;
+#pragma unroll
+  for (int r = 0; r < 4; ++r)
+    if (r < mx.nr) {
+      s[r] *= mx.w[r];
+      tot += s[r];
+      if (s[r] > 0.0) last = r;
+    }
+  ok = ok && (tot > 0.0);
+  double run = 0.0;
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+    run += s[r];
+    fc.cum[r] = (r >= last) ? 1.0 : run / tot;
+  }
+  fc.z1 = mx.row[0];
+  fc.meta = mx.nr | ((t == &M.fb) ? 8 : 0) | (ok ? 16 : 0);
+  return fc;
+}
+
+__device__ __forceinline__ double fast_draw(const DevModel& M, const pxb_thermal_cells& C,
+                                            const FastCell& fc, int64_t i, double u1, double u2) {
+  const DevTable* t = (fc.meta & 8) ? &M.fb : &M.prim;
+  const int nr = fc.meta & 7;
+  // row
+  int r = (u1 >= fc.cum[0]) + (u1 >= fc.cum[1]) + (u1 >= fc.cum[2]);
+  r = min(r, nr - 1);
+  const double lo = r > 0 ? fc.cum[r - 1] : 0.0;
+  const double hi = r < 3 ? fc.cum[r] : 1.0;
+  const double v = (u1 - lo) / (hi - lo);
+  const int row = fast_row(t, fc.z1, nr, r);
+  // table within the row: cosmic, metal, var_k with weights rs_c, Z rs_m, eZ_k rs_v
+  const double xh = cell_xh(C, i);
+  const double a0 = __ldg(t->rs_c + row), a1 = cell_metal(C, i, xh) * __ldg(t->rs_m + row);
+  int tab = 0;
+  if (C.nvar == 0) {
+    tab = (a1 > 0.0 && (v * (a0 + a1) >= a0 || !(a0 > 0.0))) ? 1 : 0;
+  } else {
+    double A = a0 + a1;
+    for (int k = 0; k < C.nvar; ++k)
+      A += cell_elem(C, k, i, xh) * __ldg(t->rs_v + (size_t)k * t->nrows + row);
+    double tgt = v * A;
+    int chosen = -1;
+    bool done = false;
+    if (a0 > 0.0) { chosen = 0; if (tgt < a0) done = true; else tgt -= a0; }
+    if (!done && a1 > 0.0) { chosen = 1; if (tgt < a1) done = true; else tgt -= a1; }
+    for (int k = 0; k < C.nvar && !done; ++k) {
+      const double a = cell_elem(C, k, i, xh) * __ldg(t->rs_v + (size_t)k * t->nrows + row);
+      if (a > 0.0) { chosen = 2 + k; if (tgt < a) done = true; else tgt -= a; }
+    }
+    tab = max(chosen, 0);
+  }
+  // invert the row CDF: guide table then a short forward walk
+  const int nb = t->nbins;
+  const size_t ro = (size_t)tab * t->nrows + row;
+  const double* __restrict__ cdf = t->rowcdf + ro * (size_t)(nb + 1);
+  const uint16_t* __restrict__ g = t->guide + ro * (size_t)nb;
+  int k = min((int)(u2 * nb), nb - 1);
+  int j = __ldg(g + k);
+  double c1 = __ldg(cdf + j + 1);
+  while (c1 <= u2 && j + 1 < nb) {
+    ++j;
+    c1 = __ldg(cdf + j + 1);
+  }
+  if (M.method == 1) return __ldg(M.emid + j);
+  const double c0 = __ldg(cdf + j);
+  const double e0 = __ldg(M.edges + j), e1 = __ldg(M.edges + j + 1);
+  return e0 + (u2 - c0) / (c1 - c0) * (e1 - e0);
+}
+
+__global__ void __launch_bounds__(FAST_THREADS)
+k_thermal_sample_fast(const DevModel M, const __grid_constant__ pxb_thermal_cells C,
+                      int64_t n_active, const int64_t* __restrict__ idx,
+                      const int64_t* __restrict__ poff, int64_t n_photons,
+                      double* __restrict__ energies, int64_t* __restrict__ list,
+                      unsigned long long* __restrict__ list_count) {
+  __shared__ int64_t s_off[FAST_TILE + 1];
+  __shared__ int64_t s_c[2];
+  __shared__ FastCell s_cell[FAST_TILE];
+  const int64_t p0 = (int64_t)blockIdx.x * FAST_TILE;
+  const int64_t p1 = min(p0 + (int64_t)FAST_TILE, n_photons);
+  TileMap<FAST_TILE> tm;
+  tm.build(poff, n_active, p0, p1, s_off, s_c);
+  for (int q = threadIdx.x; q < tm.nc; q += blockDim.x) {
+    const int64_t k = tm.c0 + q;
+    const FastCell fc = fast_setup(M, C, idx[k]);
+    s_cell[q] = fc;
+    // a declined cell is handed to the general kernel by the tile holding its first photon
+    if (!(fc.meta & 16) && s_off[q] >= p0 && s_off[q + 1] > s_off[q]) {
+      const unsigned long long slot = atomicAdd(list_count, 1ull);
+      list[slot] = k;
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int r = 0; r < FAST_ITEMS; ++r) {
+    const int64_t p = p0 + r * FAST_THREADS + threadIdx.x;
+    if (p >= p1) continue;
+    const int64_t k = tm.cell_of(p, s_off);
+    FastCell fc;
+    int64_t first;
+    if (tm.nc > 0) {
+      fc = s_cell[k - tm.c0];
+      first = s_off[k - tm.c0];
+    } else {  // tile spans more cells than photons: set up per photon (rare, never for active lists)
+      fc = fast_setup(M, C, idx[k]);
+      first = __ldg(poff + k);
+      if (!(fc.meta & 16) && p == first) {
+        const unsigned long long slot = atomicAdd(list_count, 1ull);
+        list[slot] = k;
+      }
+    }
+    if (!(fc.meta & 16)) continue;
+    const int64_t i = idx[k];
+    const Philox4 rn = pxb_rand4(C.seed, STREAM_ENERGY, (uint64_t)(C.cell_id0 + i), (uint64_t)(p - first));
+    double e = fast_draw(M, C, fc, i, u53(rn.x, rn.y), u53(rn.z, rn.w));
+    if (M.binscale_log) e = exp10(e);
+    st_stream(energies + p, e);
   }
 }
 
@@ -456,17 +668,25 @@ extern "C" int pxb_interp_spec(const pxb_model* model, int64_t n, const double* 
   return PXB_OK;
 }
 
+extern "C" int pxb_thermal_sample_workspace_bytes(int64_t n_active, int64_t* bytes) {
+  PXB_REQUIRE(bytes && n_active >= 0, "bad argument");
+  *bytes = (n_active + 2) * (int64_t)sizeof(int64_t);
+  return PXB_OK;
+}
+
 extern "C" int pxb_thermal_sample(const pxb_model* model, const pxb_thermal_cells* cells,
                                   int64_t n_active, const int64_t* idx, const int64_t* nph,
                                   const int64_t* poff, int64_t n_photons, double* energies,
-                                  void* stream) {
+                                  void* workspace, int64_t workspace_bytes, void* stream) {
   int rc = check_cells(model, cells);
   if (rc) return rc;
   if (n_active == 0 || n_photons == 0) return PXB_OK;
   PXB_REQUIRE(idx && nph && poff && energies, "NULL argument");
-  const size_t smem = ((size_t)model->dev.nbins + 1 + PXB_MAX_VAR + SAMPLE_THREADS / 32) * sizeof(double);
+  cudaStream_t st = (cudaStream_t)stream;
+  const DevModel& D = model->dev;
+  const size_t smem = ((size_t)D.nbins + 1 + PXB_MAX_VAR + SAMPLE_THREADS / 32) * sizeof(double);
   PXB_REQUIRE(smem <= 227 * 1024, "nbins=%d needs %zu B of shared memory for the per-cell CDF (max 227 KB)",
-              model->dev.nbins, smem);
+              D.nbins, smem);
   PXB_CUDA(cudaFuncSetAttribute(k_thermal_sample_cta, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)smem));
   int per_sm = 0;
@@ -475,8 +695,24 @@ extern "C" int pxb_thermal_sample(const pxb_model* model, const pxb_thermal_cell
   if (per_sm < 1) per_sm = 1;
   int64_t grid = (int64_t)pxb_sm_count() * per_sm;
   if (grid > n_active) grid = n_active;
-  k_thermal_sample_cta<<<(unsigned)grid, SAMPLE_THREADS, smem, (cudaStream_t)stream>>>(
-      model->dev, *cells, n_active, idx, nph, poff, energies);
+  int64_t* list = nullptr;
+  unsigned long long* count = nullptr;
+  if (D.fast_ok) {
+    int64_t need = 0;
+    pxb_thermal_sample_workspace_bytes(n_active, &need);
+    PXB_REQUIRE(workspace && workspace_bytes >= need, "sample workspace too small (%lld < %lld)",
+                (long long)workspace_bytes, (long long)need);
+    count = (unsigned long long*)workspace;
+    list = (int64_t*)workspace + 2;
+    PXB_CUDA(cudaMemsetAsync(count, 0, sizeof(unsigned long long), st));
+    const int64_t ntiles = (n_photons + FAST_TILE - 1) / FAST_TILE;
+    PXB_REQUIRE(ntiles < (1LL << 31), "too many photons for one call");
+    k_thermal_sample_fast<<<(unsigned)ntiles, FAST_THREADS, 0, st>>>(D, *cells, n_active, idx, poff,
+                                                                    n_photons, energies, list, count);
+    PXB_LAUNCH_CHECK();
+  }
+  k_thermal_sample_cta<<<(unsigned)grid, SAMPLE_THREADS, smem, st>>>(
+      D, *cells, n_active, idx, nph, poff, energies, list, (const int64_t*)count);
   PXB_LAUNCH_CHECK();
   return PXB_OK;
 }

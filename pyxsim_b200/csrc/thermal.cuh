@@ -22,6 +22,11 @@ struct DevTable {
   const double* rs_c;     // row sums [nrows]
   const double* rs_m;
   const double* rs_v;     // [nvar, nrows]
+  // mixture fast path (only when nonneg): per-row normalised CDFs [(2+nvar), nrows, nbins+1]
+  // (table order cosmic, metal, var_0..) and guide tables [(2+nvar), nrows, nbins]:
+  // guide[k] = bin holding the quantile k/nbins.
+  const double* rowcdf;
+  const uint16_t* guide;
 };
 
 struct DevModel {
@@ -33,6 +38,7 @@ struct DevModel {
   double kT_lo, kT_hi, nH_lo, nH_hi;
   const double* edges;    // [nbins+1]
   const double* emid;     // [nbins]
+  int fast_ok;            // mixture sampler usable (nonneg tables, nbins < 65536)
 };
 
 struct pxb_model {

@@ -124,7 +124,7 @@ class ArrayDataSource:
                  domain_right_edge=None, periodicity=(False, False, False), left_edge=None,
                  right_edge=None, center=None, position_fields=None, velocity_fields=None,
                  width_field="default", units=None, chunk_size=None, cosmology=None,
-                 name="ArrayDataSource", ftype="gas"):
+                 name="ArrayDataSource", ftype="gas", rank_local=False, global_offset=0):
         self.fields = dict(fields)
         self.units = dict(units or {})
         self.data_type = data_type
@@ -167,12 +167,18 @@ class ArrayDataSource:
         self.center = 0.5 * (self.left_edge + self.right_edge) if center is None else np.asarray(center, "float64")
         self.chunk_size = chunk_size
         self.cosmology = cosmology
+        # rank_local: this object already holds only this rank's shard (chunks are not dealt
+        # over ranks again); global_offset: global id of its first cell (RNG counters)
+        self.rank_local = rank_local
+        self.global_offset = int(global_offset)
 
     def chunks(self, rank=0, size=1):
         """Yield chunks; with ``size`` > 1 chunks are dealt round-robin over ranks like yt's
         ``parallel_objects`` (photon_list.py:401)."""
         cs = self.chunk_size or self.size
         starts = list(range(0, self.size, cs)) or [0]
+        if self.rank_local:
+            rank, size = 0, 1
         for j, s in enumerate(starts):
             if j % size == rank:
                 yield ArrayChunk(self, s, min(s + cs, self.size))

@@ -112,7 +112,7 @@ class SourceModel:
 
     def _cell_id0(self, chunk, n):
         if isinstance(chunk, ArrayChunk):
-            return chunk.start
+            return chunk.start + chunk.src.global_offset
         base = self._cell_cursor
         self._cell_cursor += n
         return base
@@ -392,9 +392,13 @@ class ThermalSourceModel(SourceModel):
         if out.n_photons == 0:
             return None
         out.energy = empty(out.n_photons)
+        need = C.c_int64()
+        _lib.call("pxb_thermal_sample_workspace_bytes", out.n_cells, C.byref(need))
+        ws = torch.empty(need.value, dtype=torch.uint8, device=out.energy.device)
         with stage("thermal_sample"):
             _lib.call("pxb_thermal_sample", dm.handle, C.byref(Cs), out.n_cells, ptr(out.idx),
-                      ptr(out.nph), ptr(out.poff), out.n_photons, ptr(out.energy), stream_ptr())
+                      ptr(out.nph), ptr(out.poff), out.n_photons, ptr(out.energy), ptr(ws),
+                      need.value, stream_ptr())
         return out
 
 
