@@ -173,247 +173,342 @@ k_project_cells(const __grid_constant__ pxb_photon_list L,
 // ---------------------------------------------------------------------------------------
 // photon pass
 // ---------------------------------------------------------------------------------------
+// Each WARP owns a tile of 256 consecutive photons (8 per lane, striped so loads/stores
+// coalesce).  A CTA draws one ticket for its 8 warp tiles; after that the warps never meet
+// at a CTA barrier again:
+//   phase 1  find the photon's cell (32-ary warp search of the offsets, then a shared-memory
+//            search), Doppler-shift, decide absorption -> survivors, ballot ranks, tile count
+//   phase 2  publish the tile count and resolve the exclusive prefix with a warp-wide
+//            decoupled look-back over the per-tile status words (flag | count in 64 bits)
+//   phase 3  scatter + sky transform of the survivors, written straight to their final,
+//            order-preserving slots.
 constexpr int PROJ_THREADS = 256;
-constexpr int PROJ_ITEMS = 4;
-constexpr int PROJ_TILE = PROJ_THREADS * PROJ_ITEMS;
 constexpr int PROJ_WARPS = PROJ_THREADS / 32;
-static_assert(PROJ_ITEMS * PROJ_WARPS == 32, "group counts are scanned by one warp");
+constexpr int PROJ_ITEMS = 8;
+constexpr int PROJ_WTILE = 32 * PROJ_ITEMS;            // photons per warp tile
+constexpr int PROJ_CTILE = PROJ_WARPS * PROJ_WTILE;    // photons per ticket
 
 constexpr unsigned long long ST_AGG = 1ull << 62;   // tile aggregate available
 constexpr unsigned long long ST_INC = 2ull << 62;   // inclusive prefix available
 constexpr unsigned long long ST_MASK = 3ull << 62;
 
 struct ProjWork {
-  unsigned long long* status;  // [ntiles]
+  unsigned long long* status;  // [n_wtiles]
   unsigned int* ticket;        // [1]
-  double* part_sum;            // [ntiles]
+  double* part_sum;            // [n_wtiles]
   double* part_min;
   double* part_max;
 };
 
-struct Event { double xs, ys, e, los; };
+__device__ __forceinline__ unsigned long long ld_status(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ void st_status(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v));
+}
 
-// scatter + sky transform for one detected photon
-__device__ __forceinline__ void scatter_one(const pxb_project_params& P, const CellDerived& D,
-                                            int64_t c, uint64_t cell_key, uint64_t draw,
-                                            const Philox4& ra, double sin_d0, double cos_d0,
-                                            double ra0_rad, Event& ev) {
-  const double w = __ldg(D.w + c);
-  const double cx = __ldg(D.cx + c), cy = __ldg(D.cy + c), cz = __ldg(D.cz + c);
-  if (P.observer == 0) {
-    double ox, oy;  // offsets in the sky plane in units of w
-    if (P.data_type == 0) {
-      // cells: uniform inside the cube, rotated into the sky plane (sky_functions.pyx:74-76,
-      // 110-121; on-axis x_hat/y_hat are axis vectors so only two of the draws contribute)
-      const Philox4 rb = pxb_rand4(P.seed, STREAM_PROJ_B, cell_key, draw);
-      const double u0 = u53(ra.z, ra.w) - 0.5, u1 = u53(rb.x, rb.y) - 0.5,
-                   u2 = u53(rb.z, rb.w) - 0.5;
-      ox = u0 * P.x_hat[0] + u1 * P.x_hat[1] + u2 * P.x_hat[2];
-      oy = u0 * P.y_hat[0] + u1 * P.y_hat[1] + u2 * P.y_hat[2];
-    } else {
-      const Philox4 rb = pxb_rand4(P.seed, STREAM_PROJ_B, cell_key, draw);
-      if (P.kernel == 1) {
-        normal2(rb, ox, oy);  // sky_functions.pyx:78-80
-      } else {
-        // top_hat: r ~ U(0,1) (NOT sqrt(U)), theta = 2 pi U  (sky_functions.pyx:81-85)
-        const double r = u53(rb.x, rb.y);
-        double s, co;
-        sincospi(2.0 * u53(rb.z, rb.w), &s, &co);
-        ox = r * co;
-        oy = r * s;
-      }
-    }
-    double xs = cx + ox * w, ys = cy + oy * w;
-    if (P.has_sigma_pos && P.data_type == 0) {
-      // photon_list.py:753-756: sigma = sigma_pos * dx
-      const Philox4 rc = pxb_rand4(P.seed, STREAM_PROJ_C, cell_key, draw);
-      double n0, n1;
-      normal2(rc, n0, n1);
-      const double sg = P.sigma_pos * w;
-      xs += sg * n0;
-      ys += sg * n1;
-    }
-    ev.los = cz;  // from the unscattered centre (sky_functions.pyx:124,143)
-    if (P.sky_mode != PXB_SKY_PHYS) {
-      xs /= P.D_A_kpc;
-      ys /= P.D_A_kpc;
-      if (P.sky_mode == PXB_SKY_FLAT) {
-        xs = P.sky_center[0] - xs * PXB_RAD2DEG;   // photon_list.py:762-764
-        ys = P.sky_center[1] + ys * PXB_RAD2DEG;
-      } else {
-        double ra, dec;
-        tan_to_cel(xs, ys, ra0_rad, sin_d0, cos_d0, ra, dec);
-        xs = ra;
-        ys = dec;
-      }
-    }
-    ev.xs = xs;
-    ev.ys = ys;
+// exclusive prefix of the counts of all earlier tiles; whole warp participates
+__device__ __forceinline__ int64_t warp_lookback(unsigned long long* status, int64_t tile,
+                                                 int64_t total, int lane) {
+  if (tile == 0) {
+    if (lane == 0) st_status(status, ST_INC | (unsigned long long)total);
+    return 0;
+  }
+  if (lane == 0) st_status(status + tile, ST_AGG | (unsigned long long)total);
+  int64_t prefix = 0;
+  int64_t j = tile - 1;
+  for (;;) {
+    const int64_t idx = j - lane;
+    unsigned long long sv = (idx >= 0) ? ld_status(status + idx) : ST_INC;
+    const unsigned inc = __ballot_sync(0xffffffffu, (sv & ST_MASK) == ST_INC);
+    const unsigned emp = __ballot_sync(0xffffffffu, (sv & ST_MASK) == 0ull);
+    const int first = inc ? (__ffs(inc) - 1) : 32;           // nearest tile with an inclusive prefix
+    const unsigned need = first >= 31 ? 0xffffffffu : ((2u << first) - 1u);
+    if (emp & need) continue;                                // a needed predecessor is not ready
+    int64_t v = (lane <= first) ? (int64_t)(sv & ~ST_MASK) : 0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    prefix += v;
+    if (first < 32) break;
+    j -= 32;
+  }
+  if (lane == 0) st_status(status + tile, ST_INC | (unsigned long long)(prefix + total));
+  return prefix;
+}
+
+// atan(t) for small |t| by its Maclaurin series (terms to t^15: < 1 ulp for |t| <= 1/16)
+__device__ __forceinline__ double atan_small(double t) {
+  const double z = t * t;
+  double p = -1.0 / 15.0;
+  p = p * z + 1.0 / 13.0;
+  p = p * z - 1.0 / 11.0;
+  p = p * z + 1.0 / 9.0;
+  p = p * z - 1.0 / 7.0;
+  p = p * z + 1.0 / 5.0;
+  p = p * z - 1.0 / 3.0;
+  return t + t * z * p;
+}
+
+// inverse gnomonic projection for the fused kernel.  Same map as tan_to_cel, arranged so that
+// both angles are small-argument arctangents (no atan2, no cancellation):
+//   RA  - RA0  = atan(-x / den),                      den = cos d0 - y sin d0
+//   Dec - Dec0 = atan((y - s sin d0) / (1 + s cos d0)), s = x^2 / (hypot(x, den) + den)
+// Wide fields (|arg| > 1/16 or den <= 0) take the general formula.
+__device__ __forceinline__ void tan_to_cel_fast(double x, double y, double ra0_rad, double d0_rad,
+                                                double sin_d0, double cos_d0, double& ra_deg,
+                                                double& dec_deg) {
+  const double den = cos_d0 - y * sin_d0;
+  const double h = sqrt(x * x + den * den);
+  const double s = x * x / (h + den);
+  const double t1 = -x / den;
+  const double t2 = (y - s * sin_d0) / (1.0 + s * cos_d0);
+  if (den > 0.0 && fabs(t1) <= 0.0625 && fabs(t2) <= 0.0625) {
+    ra_deg = (ra0_rad + atan_small(t1)) * PXB_RAD2DEG;
+    dec_deg = (d0_rad + atan_small(t2)) * PXB_RAD2DEG;
   } else {
-    // internal observer: sky_functions.pyx:205-248
-    double o0, o1, o2;
-    const Philox4 rb = pxb_rand4(P.seed, STREAM_PROJ_B, cell_key, draw);
-    if (P.data_type == 0) {
-      o0 = u53(ra.z, ra.w) - 0.5;
-      o1 = u53(rb.x, rb.y) - 0.5;
-      o2 = u53(rb.z, rb.w) - 0.5;
-    } else if (P.kernel == 1) {
-      const Philox4 rc = pxb_rand4(P.seed, STREAM_PROJ_C, cell_key, draw);
-      double dump;
-      normal2(rb, o0, o1);
-      normal2(rc, o2, dump);
-    } else {
-      const double r = u53(ra.z, ra.w);
-      double sp, cp;
-      sincospi(2.0 * u53(rb.x, rb.y), &sp, &cp);
-      const double ct = 2.0 * u53(rb.z, rb.w) - 1.0;  // cos(theta), theta = arccos(U(-1,1))
-      const double stheta = sqrt(fmax(0.0, 1.0 - ct * ct));
-      o0 = r * cp * stheta;
-      o1 = r * sp * stheta;
-      o2 = r * ct;
-    }
-    const double xx = cx + w * (o0 * P.x_hat[0] + o1 * P.x_hat[1] + o2 * P.x_hat[2]);
-    const double yy = cy + w * (o0 * P.y_hat[0] + o1 * P.y_hat[1] + o2 * P.y_hat[2]);
-    const double zz = cz + w * (o0 * P.z_hat[0] + o1 * P.z_hat[1] + o2 * P.z_hat[2]);
-    const double rr = sqrt(xx * xx + yy * yy + zz * zz);
-    double lon = atan2(yy, xx) - 0.5 * PXB_PI;
-    if (lon < 0.0) lon += 2.0 * PXB_PI;
-    if (lon > 2.0 * PXB_PI) lon -= 2.0 * PXB_PI;
-    const double lat = 0.5 * PXB_PI - acos(zz / rr);
-    ev.xs = lon * PXB_RAD2DEG;
-    ev.ys = lat * PXB_RAD2DEG;
-    ev.los = rr;
+    tan_to_cel(x, y, ra0_rad, sin_d0, cos_d0, ra_deg, dec_deg);
   }
 }
 
-__global__ void __launch_bounds__(PROJ_THREADS)
+// u < exp(-tau) without evaluating exp when the bounds 1 - tau <= exp(-tau) <= 1 - tau + tau^2/2
+// already decide (tau >= 0)
+__device__ __forceinline__ bool survives(double u, double tau) {
+  const double lo = 1.0 - tau;
+  if (u < lo) return true;
+  if (u >= lo + 0.5 * tau * tau) return false;
+  return u < exp(-tau);
+}
+
+struct SkyConst {
+  double sin_d0, cos_d0, ra0_rad, d0_rad, inv_DA;
+};
+
+__device__ __forceinline__ double u32_centered(uint32_t w) {
+  return ((double)w + 0.5) * (1.0 / 4294967296.0) - 0.5;   // uniform in (-1/2, 1/2), 32-bit
+}
+
+// scatter + sky transform of one surviving photon (external observer)
+__device__ __forceinline__ void scatter_external(const pxb_project_params& P, const CellDerived& D,
+                                                 const SkyConst& K, int64_t c, uint64_t cell_key,
+                                                 uint64_t draw, double& xs_out, double& ys_out,
+                                                 double& los_out) {
+  const double w = __ldg(D.w + c);
+  const double cx = __ldg(D.cx + c), cy = __ldg(D.cy + c);
+  los_out = __ldg(D.cz + c);  // from the unscattered centre (sky_functions.pyx:124,143)
+  const Philox4 rb = pxb_rand4(P.seed, STREAM_PROJ_B, cell_key, draw);
+  double ox, oy;  // offsets in the sky plane in units of w
+  if (P.data_type == 0) {
+    // cells: uniform inside the cube, rotated into the sky plane (sky_functions.pyx:74-76,
+    // 110-121; on-axis x_hat/y_hat are axis vectors so only two of the draws contribute)
+    const double u0 = u32_centered(rb.x), u1 = u32_centered(rb.y), u2 = u32_centered(rb.z);
+    ox = u0 * P.x_hat[0] + u1 * P.x_hat[1] + u2 * P.x_hat[2];
+    oy = u0 * P.y_hat[0] + u1 * P.y_hat[1] + u2 * P.y_hat[2];
+  } else if (P.kernel == 1) {
+    normal2(rb, ox, oy);  // sky_functions.pyx:78-80
+  } else {
+    // top_hat: r ~ U(0,1) (NOT sqrt(U)), theta = 2 pi U  (sky_functions.pyx:81-85)
+    const double r = u53(rb.x, rb.y);
+    double sn, co;
+    sincospi(2.0 * u53(rb.z, rb.w), &sn, &co);
+    ox = r * co;
+    oy = r * sn;
+  }
+  double xs = cx + ox * w, ys = cy + oy * w;
+  if (P.has_sigma_pos && P.data_type == 0) {
+    // photon_list.py:753-756: sigma = sigma_pos * dx
+    const Philox4 rc = pxb_rand4(P.seed, STREAM_PROJ_C, cell_key, draw);
+    double n0, n1;
+    normal2(rc, n0, n1);
+    const double sg = P.sigma_pos * w;
+    xs += sg * n0;
+    ys += sg * n1;
+  }
+  if (P.sky_mode != PXB_SKY_PHYS) {
+    xs *= K.inv_DA;
+    ys *= K.inv_DA;
+    if (P.sky_mode == PXB_SKY_FLAT) {
+      xs = P.sky_center[0] - xs * PXB_RAD2DEG;   // photon_list.py:762-764
+      ys = P.sky_center[1] + ys * PXB_RAD2DEG;
+    } else {
+      double ra, dec;
+      tan_to_cel_fast(xs, ys, K.ra0_rad, K.d0_rad, K.sin_d0, K.cos_d0, ra, dec);
+      xs = ra;
+      ys = dec;
+    }
+  }
+  xs_out = xs;
+  ys_out = ys;
+}
+
+// internal observer: sky_functions.pyx:205-248
+__device__ __forceinline__ void scatter_allsky(const pxb_project_params& P, const CellDerived& D,
+                                               int64_t c, uint64_t cell_key, uint64_t draw,
+                                               double& lon_out, double& lat_out, double& los_out) {
+  const double w = __ldg(D.w + c);
+  const double cx = __ldg(D.cx + c), cy = __ldg(D.cy + c), cz = __ldg(D.cz + c);
+  double o0, o1, o2;
+  const Philox4 rb = pxb_rand4(P.seed, STREAM_PROJ_B, cell_key, draw);
+  if (P.data_type == 0) {
+    o0 = u32_centered(rb.x);
+    o1 = u32_centered(rb.y);
+    o2 = u32_centered(rb.z);
+  } else if (P.kernel == 1) {
+    const Philox4 rc = pxb_rand4(P.seed, STREAM_PROJ_C, cell_key, draw);
+    double dump;
+    normal2(rb, o0, o1);
+    normal2(rc, o2, dump);
+  } else {
+    const Philox4 rc = pxb_rand4(P.seed, STREAM_PROJ_C, cell_key, draw);
+    const double r = u53(rc.x, rc.y);
+    double sp, cp;
+    sincospi(2.0 * u53(rb.x, rb.y), &sp, &cp);
+    const double ct = 2.0 * u53(rb.z, rb.w) - 1.0;  // cos(theta), theta = arccos(U(-1,1))
+    const double stheta = sqrt(fmax(0.0, 1.0 - ct * ct));
+    o0 = r * cp * stheta;
+    o1 = r * sp * stheta;
+    o2 = r * ct;
+  }
+  // the reference scatters in the dataset frame and then rotates; rotation is linear
+  const double px = w * o0, py = w * o1, pz = w * o2;
+  const double xx = cx + px * P.x_hat[0] + py * P.x_hat[1] + pz * P.x_hat[2];
+  const double yy = cy + px * P.y_hat[0] + py * P.y_hat[1] + pz * P.y_hat[2];
+  const double zz = cz + px * P.z_hat[0] + py * P.z_hat[1] + pz * P.z_hat[2];
+  const double rr = sqrt(xx * xx + yy * yy + zz * zz);
+  double lon = atan2(yy, xx) - 0.5 * PXB_PI;
+  if (lon < 0.0) lon += 2.0 * PXB_PI;
+  if (lon > 2.0 * PXB_PI) lon -= 2.0 * PXB_PI;
+  const double lat = 0.5 * PXB_PI - acos(zz / rr);
+  lon_out = lon * PXB_RAD2DEG;
+  lat_out = lat * PXB_RAD2DEG;
+  los_out = rr;
+}
+
+template <int OBS>
+__global__ void __launch_bounds__(PROJ_THREADS, 3)
 k_project_photons(const __grid_constant__ pxb_photon_list L,
                   const __grid_constant__ pxb_project_params P, const CellDerived D,
                   const ProjWork W, double* __restrict__ xsky, double* __restrict__ ysky,
                   double* __restrict__ eobs_out, double* __restrict__ los_out,
-                  int64_t* __restrict__ n_events_out, int64_t ntiles) {
-  __shared__ int64_t s_off[PROJ_TILE + 1];
-  __shared__ int64_t s_c[2];
-  __shared__ int s_cnt[PROJ_ITEMS * PROJ_WARPS + 1];
-  __shared__ unsigned int s_tile;
-  __shared__ int64_t s_base;
-  __shared__ double s_red[3][PROJ_WARPS];
-
+                  int64_t* __restrict__ n_events_out, int64_t n_wtiles, int64_t n_ctiles) {
+  __shared__ int64_t s_off_all[PROJ_WARPS][PROJ_WTILE + 1];
+  __shared__ unsigned int s_ticket;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  double sin_d0, cos_d0;
-  sincos(P.sky_center[1] * (PXB_PI / 180.0), &sin_d0, &cos_d0);
-  const double ra0_rad = P.sky_center[0] * (PXB_PI / 180.0);
+  int64_t* s_off = s_off_all[wid];
+  SkyConst K;
+  K.d0_rad = P.sky_center[1] * (PXB_PI / 180.0);
+  sincos(K.d0_rad, &K.sin_d0, &K.cos_d0);
+  K.ra0_rad = P.sky_center[0] * (PXB_PI / 180.0);
+  K.inv_DA = 1.0 / P.D_A_kpc;
+  const bool absorb = P.absorb_kind != PXB_ABS_NONE;
 
   for (;;) {
     __syncthreads();
-    if (threadIdx.x == 0) s_tile = atomicAdd(W.ticket, 1u);
+    if (threadIdx.x == 0) s_ticket = atomicAdd(W.ticket, 1u);
     __syncthreads();
-    const int64_t tile = s_tile;
-    if (tile >= ntiles) return;
-    const int64_t p0 = tile * PROJ_TILE;
-    const int64_t p1 = min(p0 + (int64_t)PROJ_TILE, L.n_photons);
-    TileMap<PROJ_TILE> tm;
-    tm.build(L.poff, L.n_cells, p0, p1, s_off, s_c);
+    const int64_t ctile = s_ticket;
+    if (ctile >= n_ctiles) return;
+    const int64_t wtile = ctile * PROJ_WARPS + wid;
+    if (wtile >= n_wtiles) continue;   // past the end: nobody waits on this warp
+    const int64_t p0 = wtile * PROJ_WTILE;
+    const int64_t p1 = min(p0 + (int64_t)PROJ_WTILE, L.n_photons);
 
-    Event ev[PROJ_ITEMS];
-    unsigned detbits = 0;
+    // ---- cells intersecting this warp tile -------------------------------------------
+    const int64_t c0 = warp_search_le(L.poff, L.n_cells, p0, lane);
+    const int64_t c1 = warp_search_le(L.poff, L.n_cells, p1 - 1, lane);
+    const int nc = (c1 - c0 + 1 <= PROJ_WTILE) ? (int)(c1 - c0 + 1) : 0;
+    __syncwarp();
+    for (int q = lane; q <= nc && nc > 0; q += 32) s_off[q] = __ldg(L.poff + c0 + q);
+    __syncwarp();
+
+    // ---- phase 1: Doppler + absorption, survivors ----------------------------------------
+    double e[PROJ_ITEMS];
+    int rel[PROJ_ITEMS];        // cell index relative to c0
+    int slot[PROJ_ITEMS];       // tile-local output slot, -1 when absorbed
+    int run = 0;
     double tsum = 0.0, tmin = 1.0e99, tmax = -1.0e99;
 #pragma unroll
     for (int r = 0; r < PROJ_ITEMS; ++r) {
-      const int64_t p = p0 + r * PROJ_THREADS + threadIdx.x;
+      const int64_t p = p0 + r * 32 + lane;
       bool det = false;
+      e[r] = 0.0;
+      rel[r] = 0;
       if (p < p1) {
-        const int64_t c = tm.cell_of(p, s_off);
-        const uint64_t cell_key = (uint64_t)(P.cell_id0 + c);
-        const uint64_t draw = (uint64_t)(p - __ldg(L.poff + c));  // index inside its cell
-        double e = ld_stream(L.energy + p) * __ldg(D.shift + c);
-        const Philox4 ra = pxb_rand4(P.seed, STREAM_PROJ_A, cell_key, draw);
+        int64_t c;
+        if (nc == 1) {
+          c = c0;
+        } else if (nc > 0) {
+          int lo = 0, hi = nc;
+          while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (s_off[mid] <= p) lo = mid; else hi = mid;
+          }
+          c = c0 + lo;
+        } else {  // more cells than photons in the tile (many empty cells): global search
+          int64_t lo = c0, hi = c1 + 1;
+          while (hi - lo > 1) {
+            const int64_t mid = (lo + hi) >> 1;
+            if (__ldg(L.poff + mid) <= p) lo = mid; else hi = mid;
+          }
+          c = lo;
+        }
+        rel[r] = (int)(c - c0);
+        const double en = ld_stream(L.energy + p) * __ldg(D.shift + c);
+        e[r] = en;
         det = true;
-        if (P.absorb_kind != PXB_ABS_NONE) {
+        if (absorb) {
+          const uint64_t cell_key = (uint64_t)(P.cell_id0 + c);
+          const uint64_t draw = (uint64_t)(p - __ldg(L.poff + c));
           if (P.nH_cell) {
             // internal absorption on the source-frame energy, photon_list.py:715-723
             const Philox4 rd = pxb_rand4(P.seed, STREAM_PROJ_D, cell_key, draw);
-            const double tr = exp(-tau_per_nh(P, e * P.oneplusz) * __ldg(P.nH_cell + c));
-            det = u53(rd.x, rd.y) < tr;
+            det = survives(u53(rd.x, rd.y), tau_per_nh(P, en * P.oneplusz) * __ldg(P.nH_cell + c));
           }
           if (det && P.nH > 0.0) {
-            const double tr = exp(-tau_per_nh(P, e) * P.nH);
-            det = u53(ra.x, ra.y) < tr;
+            const Philox4 ra = pxb_rand4(P.seed, STREAM_PROJ_A, cell_key, draw);
+            det = survives(u53(ra.x, ra.y), tau_per_nh(P, en) * P.nH);
           }
         }
         if (det) {
-          ev[r].e = e;
-          scatter_one(P, D, c, cell_key, draw, ra, sin_d0, cos_d0, ra0_rad, ev[r]);
-          tsum += e;
-          tmin = fmin(tmin, e);
-          tmax = fmax(tmax, e);
+          tsum += en;
+          tmin = fmin(tmin, en);
+          tmax = fmax(tmax, en);
         }
       }
       const unsigned bal = __ballot_sync(0xffffffffu, det);
-      if (det) detbits |= 1u << r;
-      if (lane == 0) s_cnt[r * PROJ_WARPS + wid] = __popc(bal);
-      // rank of this thread inside its (round, warp) group
-      const int rank = __popc(bal & ((1u << lane) - 1u));
-      // stash the in-group rank in the low bits of detbits' upper half
-      detbits |= (unsigned)rank << (8 + 5 * r);
+      slot[r] = det ? run + __popc(bal & ((1u << lane) - 1u)) : -1;
+      run += __popc(bal);
     }
-    // block reduce of the flux statistics
-    tsum = warp_sum(tsum); tmin = warp_min(tmin); tmax = warp_max(tmax);
-    if (lane == 0) { s_red[0][wid] = tsum; s_red[1][wid] = tmin; s_red[2][wid] = tmax; }
-    __syncthreads();
-    // exclusive scan of the PROJ_ITEMS*PROJ_WARPS group counts (photon order = round-major)
-    if (wid == 0) {
-      constexpr int NG = PROJ_ITEMS * PROJ_WARPS;  // 32
-      int v = (lane < NG) ? s_cnt[lane] : 0;
-      int inc = v;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        int t = __shfl_up_sync(0xffffffffu, inc, o);
-        if (lane >= o) inc += t;
-      }
-      if (lane < NG) s_cnt[lane] = inc - v;
-      const int total = __shfl_sync(0xffffffffu, inc, 31);
-      if (lane == 0) {
-        s_cnt[NG] = total;
-        double a = 0.0, b = 1.0e99, cmax = -1.0e99;
-        for (int w = 0; w < PROJ_WARPS; ++w) {
-          a += s_red[0][w]; b = fmin(b, s_red[1][w]); cmax = fmax(cmax, s_red[2][w]);
-        }
-        W.part_sum[tile] = a; W.part_min[tile] = b; W.part_max[tile] = cmax;
-        // decoupled look-back over the tile counts
-        int64_t prefix = 0;
-        if (tile == 0) {
-          atomicExch(W.status, ST_INC | (unsigned long long)total);
-        } else {
-          atomicExch(W.status + tile, ST_AGG | (unsigned long long)total);
-          int64_t j = tile - 1;
-          for (;;) {
-            unsigned long long s;
-            do {
-              s = *((volatile unsigned long long*)(W.status + j));
-            } while ((s & ST_MASK) == 0);
-            prefix += (int64_t)(s & ~ST_MASK);
-            if ((s & ST_MASK) == ST_INC) break;
-            --j;
-          }
-          atomicExch(W.status + tile, ST_INC | (unsigned long long)(prefix + total));
-        }
-        s_base = prefix;
-        if (tile == ntiles - 1) *n_events_out = prefix + total;
-      }
+    tsum = warp_sum(tsum);
+    tmin = warp_min(tmin);
+    tmax = warp_max(tmax);
+    if (lane == 0) {
+      W.part_sum[wtile] = tsum;
+      W.part_min[wtile] = tmin;
+      W.part_max[wtile] = tmax;
     }
-    __syncthreads();
-    const int64_t base = s_base;
+
+    // ---- phase 2: exclusive prefix over tiles ----------------------------------------------
+    const int64_t base = warp_lookback(W.status, wtile, (int64_t)run, lane);
+    if (wtile == n_wtiles - 1 && lane == 0) *n_events_out = base + run;
+
+    // ---- phase 3: scatter survivors into their final slots ---------------------------------
 #pragma unroll
     for (int r = 0; r < PROJ_ITEMS; ++r) {
-      if (detbits & (1u << r)) {
-        const int rank = (detbits >> (8 + 5 * r)) & 31;
-        const int64_t o = base + s_cnt[r * PROJ_WARPS + wid] + rank;
-        st_stream(xsky + o, ev[r].xs);
-        st_stream(ysky + o, ev[r].ys);
-        st_stream(eobs_out + o, ev[r].e);
-        if (los_out) st_stream(los_out + o, ev[r].los);
-      }
+      if (slot[r] < 0) continue;
+      const int64_t p = p0 + r * 32 + lane;
+      const int64_t c = c0 + rel[r];
+      const uint64_t cell_key = (uint64_t)(P.cell_id0 + c);
+      const uint64_t draw = (uint64_t)(p - __ldg(L.poff + c));
+      double xs, ys, los;
+      if (OBS == 0) scatter_external(P, D, K, c, cell_key, draw, xs, ys, los);
+      else scatter_allsky(P, D, c, cell_key, draw, xs, ys, los);
+      const int64_t o = base + slot[r];
+      st_stream(xsky + o, xs);
+      st_stream(ysky + o, ys);
+      st_stream(eobs_out + o, e[r]);
+      if (los_out) st_stream(los_out + o, los);
     }
   }
 }
@@ -463,7 +558,7 @@ struct ProjLayout {
 
 static ProjLayout proj_layout(int64_t n_cells, int64_t n_photons) {
   ProjLayout l;
-  l.ntiles = (n_photons + PROJ_TILE - 1) / PROJ_TILE;
+  l.ntiles = (n_photons + PROJ_WTILE - 1) / PROJ_WTILE;   // warp tiles
   int64_t o = 0;
   l.off_cells = o;  o += align256(5 * n_cells * (int64_t)sizeof(double));
   l.off_status = o; o += align256(l.ntiles * 8);
@@ -513,7 +608,8 @@ extern "C" int pxb_project(const pxb_photon_list* L, const pxb_project_params* P
   PXB_REQUIRE(workspace && workspace_bytes >= lay.total,
               "projection workspace too small (%lld < %lld)", (long long)workspace_bytes,
               (long long)lay.total);
-  PXB_REQUIRE(lay.ntiles < (1LL << 32) - 4096, "too many photons for one projection call");
+  const int64_t n_ctiles = (lay.ntiles + PROJ_WARPS - 1) / PROJ_WARPS;
+  PXB_REQUIRE(n_ctiles < (1LL << 32) - 65536, "too many photons for one projection call");
   char* ws = (char*)workspace;
   CellDerived D;
   D.shift = (double*)(ws + lay.off_cells);
@@ -533,12 +629,21 @@ extern "C" int pxb_project(const pxb_photon_list* L, const pxb_project_params* P
   k_project_cells<<<(unsigned)((L->n_cells + 255) / 256), 256, 0, st>>>(*L, *P, D);
   PXB_LAUNCH_CHECK();
   int per_sm = 0;
-  PXB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_project_photons, PROJ_THREADS, 0));
+  if (P->observer == 0) {
+    PXB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_project_photons<0>, PROJ_THREADS, 0));
+  } else {
+    PXB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_project_photons<1>, PROJ_THREADS, 0));
+  }
   if (per_sm < 1) per_sm = 1;
   int64_t grid = (int64_t)pxb_sm_count() * per_sm;
-  if (grid > lay.ntiles) grid = lay.ntiles;
-  k_project_photons<<<(unsigned)grid, PROJ_THREADS, 0, st>>>(
-      *L, *P, D, W, xsky, ysky, eobs, P->save_los ? los : nullptr, n_events_out, lay.ntiles);
+  if (grid > n_ctiles) grid = n_ctiles;
+  if (P->observer == 0) {
+    k_project_photons<0><<<(unsigned)grid, PROJ_THREADS, 0, st>>>(
+        *L, *P, D, W, xsky, ysky, eobs, P->save_los ? los : nullptr, n_events_out, lay.ntiles, n_ctiles);
+  } else {
+    k_project_photons<1><<<(unsigned)grid, PROJ_THREADS, 0, st>>>(
+        *L, *P, D, W, xsky, ysky, eobs, P->save_los ? los : nullptr, n_events_out, lay.ntiles, n_ctiles);
+  }
   PXB_LAUNCH_CHECK();
   const int64_t per_block = (lay.ntiles + STATS_BLOCKS - 1) / STATS_BLOCKS;
   const int nb = (int)((lay.ntiles + per_block - 1) / per_block);

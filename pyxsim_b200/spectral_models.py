@@ -107,9 +107,9 @@ class ThermalSpectralModel:
             c, m, v = self._table_fn(zobs)
             self.cosmic_spec, self.metal_spec = _f64(c), _f64(m)
             self.var_spec = None if v is None else _f64(v)
+            self._dev = {}      # tables changed: the device copy is rebuilt on next use
         if self.cosmic_spec is None:
             raise RuntimeError("spectral model has no tables")
-        self._dev = {}
 
     def _Tconv(self, kT):
         return np.log10(kT * K.K_per_keV) if self._logT else kT
