@@ -90,15 +90,14 @@ __device__ __forceinline__ Philox4 pxb_rand4(uint64_t seed, uint32_t stream, uin
                        (uint32_t)seed, (uint32_t)(seed >> 32));
 }
 
-// 53-bit uniform in [0,1)
+// uniform in [0,1) from 52 random bits placed in the mantissa of a double in [1,2)
+// (cheaper than an int64 -> double conversion; granularity 2^-52)
 __device__ __forceinline__ double u53(uint32_t hi, uint32_t lo) {
-  uint64_t v = (((uint64_t)hi << 32) | lo) >> 11;
-  return (double)v * (1.0 / 9007199254740992.0);
+  return __hiloint2double(0x3FF00000 | (hi >> 12), (hi << 20) | (lo >> 12)) - 1.0;
 }
-// 53-bit uniform in (0,1]  (safe for log)
+// uniform in (0,1]  (safe for log)
 __device__ __forceinline__ double u53_open0(uint32_t hi, uint32_t lo) {
-  uint64_t v = (((uint64_t)hi << 32) | lo) >> 11;
-  return (double)(v + 1) * (1.0 / 9007199254740992.0);
+  return 2.0 - __hiloint2double(0x3FF00000 | (hi >> 12), (hi << 20) | (lo >> 12));
 }
 
 // two standard normals from one Philox block (Box-Muller)

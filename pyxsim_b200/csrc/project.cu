@@ -36,9 +36,11 @@ __constant__ double c_wabs_c2[14] = {-2150.0, -476.1, 4.3, -51.4, -61.1, 294.0, 
                                      -31.5, -17.0, 0.0, 0.0, 0.75, 0.0, 0.0};
 
 __device__ __forceinline__ double wabs_tau_per_nh(double e) {
-  int k = 0;
-#pragma unroll
-  for (int q = 1; q < 14; ++q) k += (e >= c_wabs_edge[q]);
+  // piece index = number of inner edges <= e, by bisection (edges 1..13)
+  int k = (e >= c_wabs_edge[7]) ? 7 : 0;
+  k += (e >= c_wabs_edge[k + 4]) ? 4 : 0;
+  k += (k + 2 <= 13 && e >= c_wabs_edge[k + 2]) ? 2 : 0;
+  k += (k + 1 <= 13 && e >= c_wabs_edge[k + 1]) ? 1 : 0;
   const double s = (c_wabs_c0[k] + e * (c_wabs_c1[k] + e * c_wabs_c2[k])) / (e * e * e);
   return s * 1.0e-2;  // 1e-24 cm^2 * 1e22 cm^-2
 }
@@ -286,7 +288,10 @@ struct SkyConst {
 };
 
 __device__ __forceinline__ double u32_centered(uint32_t w) {
-  return ((double)w + 0.5) * (1.0 / 4294967296.0) - 0.5;   // uniform in (-1/2, 1/2), 32-bit
+  // (w + 0.5) / 2^32 - 0.5: uniform in (-1/2, 1/2) with 32-bit resolution; the conversion is
+  // the exact 2^52 + w mantissa trick
+  const double d = __hiloint2double(0x43300000, w) - 4503599627370496.0;
+  return (d + 0.5) * (1.0 / 4294967296.0) - 0.5;
 }
 
 // scatter + sky transform of one surviving photon (external observer)
@@ -385,17 +390,44 @@ __device__ __forceinline__ void scatter_allsky(const pxb_project_params& P, cons
   los_out = rr;
 }
 
+// absorption decision of one photon (phase 1); kept out of line so the rolled item loop stays
+// small
+__device__ __noinline__ bool absorb_decision(const pxb_project_params& P, int64_t c, int64_t draw,
+                                             double en) {
+  const uint64_t cell_key = (uint64_t)(P.cell_id0 + c);
+  bool det = true;
+  if (P.nH_cell) {
+    // internal absorption on the source-frame energy, photon_list.py:715-723
+    const Philox4 rd = pxb_rand4(P.seed, STREAM_PROJ_D, cell_key, (uint64_t)draw);
+    det = survives(u53(rd.x, rd.y), tau_per_nh(P, en * P.oneplusz) * __ldg(P.nH_cell + c));
+  }
+  if (det && P.nH > 0.0) {
+    const Philox4 ra = pxb_rand4(P.seed, STREAM_PROJ_A, cell_key, (uint64_t)draw);
+    det = survives(u53(ra.x, ra.y), tau_per_nh(P, en) * P.nH);
+  }
+  return det;
+}
+
 template <int OBS>
-__global__ void __launch_bounds__(PROJ_THREADS, 3)
+__global__ void __launch_bounds__(PROJ_THREADS, 4)
 k_project_photons(const __grid_constant__ pxb_photon_list L,
                   const __grid_constant__ pxb_project_params P, const CellDerived D,
                   const ProjWork W, double* __restrict__ xsky, double* __restrict__ ysky,
                   double* __restrict__ eobs_out, double* __restrict__ los_out,
                   int64_t* __restrict__ n_events_out, int64_t n_wtiles, int64_t n_ctiles) {
+  // per-warp scratch: cell offsets of the tile and the per-photon state carried from phase 1
+  // to phase 3 (energy, cell, output slot) -- kept in shared memory so the item loops stay
+  // rolled (small code, few registers, more resident warps)
   __shared__ int64_t s_off_all[PROJ_WARPS][PROJ_WTILE + 1];
+  __shared__ double s_e_all[PROJ_WARPS][PROJ_WTILE];
+  __shared__ int s_rel_all[PROJ_WARPS][PROJ_WTILE];
+  __shared__ short s_slot_all[PROJ_WARPS][PROJ_WTILE];
   __shared__ unsigned int s_ticket;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   int64_t* s_off = s_off_all[wid];
+  double* s_e = s_e_all[wid];
+  int* s_rel = s_rel_all[wid];
+  short* s_slot = s_slot_all[wid];
   SkyConst K;
   K.d0_rad = P.sky_center[1] * (PXB_PI / 180.0);
   sincos(K.d0_rad, &K.sin_d0, &K.cos_d0);
@@ -423,53 +455,40 @@ k_project_photons(const __grid_constant__ pxb_photon_list L,
     __syncwarp();
 
     // ---- phase 1: Doppler + absorption, survivors ----------------------------------------
-    double e[PROJ_ITEMS];
-    int rel[PROJ_ITEMS];        // cell index relative to c0
-    int slot[PROJ_ITEMS];       // tile-local output slot, -1 when absorbed
     int run = 0;
     double tsum = 0.0, tmin = 1.0e99, tmax = -1.0e99;
-#pragma unroll
+#pragma unroll 1
     for (int r = 0; r < PROJ_ITEMS; ++r) {
-      const int64_t p = p0 + r * 32 + lane;
+      const int it = r * 32 + lane;
+      const int64_t p = p0 + it;
       bool det = false;
-      e[r] = 0.0;
-      rel[r] = 0;
       if (p < p1) {
-        int64_t c;
+        int rel = 0;
+        int64_t first;
         if (nc == 1) {
-          c = c0;
+          first = s_off[0];
         } else if (nc > 0) {
-          int lo = 0, hi = nc;
-          while (hi - lo > 1) {
-            const int mid = (lo + hi) >> 1;
-            if (s_off[mid] <= p) lo = mid; else hi = mid;
+          // branch-free bisection: largest q in [0, nc) with s_off[q] <= p
+#pragma unroll
+          for (int step = PROJ_WTILE / 2; step > 0; step >>= 1) {
+            const int q = rel + step;
+            if (q < nc && s_off[q] <= p) rel = q;
           }
-          c = c0 + lo;
+          first = s_off[rel];
         } else {  // more cells than photons in the tile (many empty cells): global search
           int64_t lo = c0, hi = c1 + 1;
           while (hi - lo > 1) {
             const int64_t mid = (lo + hi) >> 1;
             if (__ldg(L.poff + mid) <= p) lo = mid; else hi = mid;
           }
-          c = lo;
+          rel = (int)(lo - c0);
+          first = __ldg(L.poff + lo);
         }
-        rel[r] = (int)(c - c0);
+        const int64_t c = c0 + rel;
         const double en = ld_stream(L.energy + p) * __ldg(D.shift + c);
-        e[r] = en;
-        det = true;
-        if (absorb) {
-          const uint64_t cell_key = (uint64_t)(P.cell_id0 + c);
-          const uint64_t draw = (uint64_t)(p - __ldg(L.poff + c));
-          if (P.nH_cell) {
-            // internal absorption on the source-frame energy, photon_list.py:715-723
-            const Philox4 rd = pxb_rand4(P.seed, STREAM_PROJ_D, cell_key, draw);
-            det = survives(u53(rd.x, rd.y), tau_per_nh(P, en * P.oneplusz) * __ldg(P.nH_cell + c));
-          }
-          if (det && P.nH > 0.0) {
-            const Philox4 ra = pxb_rand4(P.seed, STREAM_PROJ_A, cell_key, draw);
-            det = survives(u53(ra.x, ra.y), tau_per_nh(P, en) * P.nH);
-          }
-        }
+        det = absorb ? absorb_decision(P, c, p - first, en) : true;
+        s_e[it] = en;
+        s_rel[it] = rel;
         if (det) {
           tsum += en;
           tmin = fmin(tmin, en);
@@ -477,7 +496,7 @@ k_project_photons(const __grid_constant__ pxb_photon_list L,
         }
       }
       const unsigned bal = __ballot_sync(0xffffffffu, det);
-      slot[r] = det ? run + __popc(bal & ((1u << lane) - 1u)) : -1;
+      s_slot[it] = det ? (short)(run + __popc(bal & ((1u << lane) - 1u))) : (short)-1;
       run += __popc(bal);
     }
     tsum = warp_sum(tsum);
@@ -494,20 +513,23 @@ k_project_photons(const __grid_constant__ pxb_photon_list L,
     if (wtile == n_wtiles - 1 && lane == 0) *n_events_out = base + run;
 
     // ---- phase 3: scatter survivors into their final slots ---------------------------------
-#pragma unroll
+#pragma unroll 1
     for (int r = 0; r < PROJ_ITEMS; ++r) {
-      if (slot[r] < 0) continue;
-      const int64_t p = p0 + r * 32 + lane;
-      const int64_t c = c0 + rel[r];
+      const int it = r * 32 + lane;
+      const int sl = s_slot[it];       // own entry: written by this lane in phase 1
+      if (sl < 0 || p0 + it >= p1) continue;
+      const int rel = s_rel[it];
+      const int64_t c = c0 + rel;
+      const int64_t first = (nc > 0) ? s_off[rel] : __ldg(L.poff + c);
       const uint64_t cell_key = (uint64_t)(P.cell_id0 + c);
-      const uint64_t draw = (uint64_t)(p - __ldg(L.poff + c));
+      const uint64_t draw = (uint64_t)(p0 + it - first);
       double xs, ys, los;
       if (OBS == 0) scatter_external(P, D, K, c, cell_key, draw, xs, ys, los);
       else scatter_allsky(P, D, c, cell_key, draw, xs, ys, los);
-      const int64_t o = base + slot[r];
+      const int64_t o = base + sl;
       st_stream(xsky + o, xs);
       st_stream(ysky + o, ys);
-      st_stream(eobs_out + o, e[r]);
+      st_stream(eobs_out + o, s_e[it]);
       if (los_out) st_stream(los_out + o, los);
     }
   }

@@ -103,6 +103,13 @@ static int build_table(pxb_model* m, const pxb_table_desc& d, DevTable& t) {
     }
     if ((rc = upload(m, cdf.data(), cdf.size() * sizeof(double), (const void**)&t.rowcdf))) return rc;
     if ((rc = upload(m, guide.data(), guide.size() * sizeof(uint16_t), (const void**)&t.guide))) return rc;
+    std::vector<double> pairs((size_t)ntab * t.nrows * nb * 2);
+    for (size_t ro = 0; ro < (size_t)ntab * t.nrows; ++ro)
+      for (size_t j = 0; j < nb; ++j) {
+        pairs[(ro * nb + j) * 2 + 0] = cdf[ro * (nb + 1) + j];
+        pairs[(ro * nb + j) * 2 + 1] = cdf[ro * (nb + 1) + j + 1];
+      }
+    if ((rc = upload(m, pairs.data(), pairs.size() * sizeof(double), (const void**)&t.cdfpair))) return rc;
   }
   return PXB_OK;
 }
@@ -152,6 +159,17 @@ extern "C" int pxb_model_create(const pxb_model_desc* desc, pxb_model** out) {
     rc = upload(m, desc->bin_edges, (D.nbins + 1) * sizeof(double), (const void**)&D.edges);
     if (!rc) rc = upload(m, desc->emid, D.nbins * sizeof(double), (const void**)&D.emid);
     D.fast_ok = D.prim.rowcdf != nullptr && (!D.has_fb || D.fb.rowcdf != nullptr);
+    {
+      const double* eb = desc->bin_edges;
+      const int nb = D.nbins;
+      const double de = (eb[nb] - eb[0]) / nb;
+      bool uni = de > 0.0;
+      for (int j = 0; j <= nb && uni; ++j)
+        if (fabs(eb[j] - (eb[0] + j * de)) > 4e-16 * fmax(fabs(eb[j]), fabs(eb[nb]))) uni = false;
+      D.edges_uniform = uni ? 1 : 0;
+      D.edge0 = eb[0];
+      D.dedge = de;
+    }
   }
   if (rc) { pxb_model_destroy(m); return rc; }
   *out = m;
@@ -448,8 +466,10 @@ k_thermal_sample_cta(const DevModel M, const __grid_constant__ pxb_thermal_cells
 #include "tiles.cuh"
 
 constexpr int FAST_THREADS = 256;
+constexpr int FAST_WARPS = FAST_THREADS / 32;
 constexpr int FAST_ITEMS = 4;
-constexpr int FAST_TILE = FAST_THREADS * FAST_ITEMS;
+constexpr int FAST_WTILE = 32 * FAST_ITEMS;             // photons per warp tile
+constexpr int FAST_CTILE = FAST_WARPS * FAST_WTILE;
 
 struct FastCell {
   int z1;        // first row
@@ -463,7 +483,7 @@ __device__ __forceinline__ int fast_row(const DevTable* t, int z1, int nr, int r
 }
 
 __device__ __forceinline__ FastCell fast_setup(const DevModel& M, const pxb_thermal_cells& C,
-                                               int64_t i) {
+                                            int64_t i) {
   FastCell fc;
   const double kT = C.kT[i];
   const double nH = C.nH ? C.nH[i] : 0.0;
@@ -537,25 +557,38 @@ __device__ __forceinline__ double fast_draw(const DevModel& M, const pxb_thermal
     }
     tab = max(chosen, 0);
   }
-  // invert the row CDF: guide table then a short forward walk
+  // invert the row CDF: guide table then a short forward walk over (cdf[j], cdf[j+1]) pairs
   const int nb = t->nbins;
   const size_t ro = (size_t)tab * t->nrows + row;
   const double* __restrict__ cdf = t->rowcdf + ro * (size_t)(nb + 1);
   const uint16_t* __restrict__ g = t->guide + ro * (size_t)nb;
-  int k = min((int)(u2 * nb), nb - 1);
+  const int k = min((int)(u2 * nb), nb - 1);
   int j = __ldg(g + k);
-  double c1 = __ldg(cdf + j + 1);
-  while (c1 <= u2 && j + 1 < nb) {
+  double2 c;
+  c.y = __ldg(cdf + j + 1);
+  while (c.y <= u2 && j + 1 < nb) {
     ++j;
-    c1 = __ldg(cdf + j + 1);
+    c.y = __ldg(cdf + j + 1);
   }
+  c.x = __ldg(cdf + j);
   if (M.method == 1) return __ldg(M.emid + j);
-  const double c0 = __ldg(cdf + j);
-  const double e0 = __ldg(M.edges + j), e1 = __ldg(M.edges + j + 1);
-  return e0 + (u2 - c0) / (c1 - c0) * (e1 - e0);
+  double e0, e1;
+  if (M.edges_uniform) {
+    e0 = M.edge0 + j * M.dedge;
+    e1 = M.edge0 + (j + 1) * M.dedge;
+  } else {
+    e0 = __ldg(M.edges + j);
+    e1 = __ldg(M.edges + j + 1);
+  }
+  return e0 + (u2 - c.x) / (c.y - c.x) * (e1 - e0);
 }
 
-__global__ void __launch_bounds__(FAST_THREADS)
+// One CTA per tile of 1024 photons (4 per thread, striped).  Shared memory per CTA is kept at
+// 40 KB and residency at 3 CTAs/SM on purpose: the per-row CDFs and guide tables the photons
+// gather from live in L1, and L1 is whatever the 228 KB array has left after shared memory.
+constexpr int FAST_TILE = FAST_THREADS * FAST_ITEMS;
+
+__global__ void __launch_bounds__(FAST_THREADS, 3)
 k_thermal_sample_fast(const DevModel M, const __grid_constant__ pxb_thermal_cells C,
                       int64_t n_active, const int64_t* __restrict__ idx,
                       const int64_t* __restrict__ poff, int64_t n_photons,
@@ -579,7 +612,7 @@ k_thermal_sample_fast(const DevModel M, const __grid_constant__ pxb_thermal_cell
     }
   }
   __syncthreads();
-#pragma unroll
+#pragma unroll 1
   for (int r = 0; r < FAST_ITEMS; ++r) {
     const int64_t p = p0 + r * FAST_THREADS + threadIdx.x;
     if (p >= p1) continue;
@@ -589,7 +622,7 @@ k_thermal_sample_fast(const DevModel M, const __grid_constant__ pxb_thermal_cell
     if (tm.nc > 0) {
       fc = s_cell[k - tm.c0];
       first = s_off[k - tm.c0];
-    } else {  // tile spans more cells than photons: set up per photon (rare, never for active lists)
+    } else {  // tile spans more cells than photons: set up per photon (never for active lists)
       fc = fast_setup(M, C, idx[k]);
       first = __ldg(poff + k);
       if (!(fc.meta & 16) && p == first) {

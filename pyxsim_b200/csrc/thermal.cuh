@@ -27,6 +27,7 @@ struct DevTable {
   // guide[k] = bin holding the quantile k/nbins.
   const double* rowcdf;
   const uint16_t* guide;
+  const double2* cdfpair; // [(2+nvar), nrows, nbins]: (cdf[j], cdf[j+1]) in one 16-byte load
 };
 
 struct DevModel {
@@ -39,6 +40,8 @@ struct DevModel {
   const double* edges;    // [nbins+1]
   const double* emid;     // [nbins]
   int fast_ok;            // mixture sampler usable (nonneg tables, nbins < 65536)
+  int edges_uniform;      // edges[j] == edge0 + j*dedge (to rounding): computed, not loaded
+  double edge0, dedge;
 };
 
 struct pxb_model {
