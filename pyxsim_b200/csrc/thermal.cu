@@ -71,14 +71,18 @@ static int build_table(pxb_model* m, const pxb_table_desc& d, DevTable& t) {
     // per-row normalised CDFs + guide tables for the mixture sampler
     const int ntab = 2 + d.nvar;
     const size_t nb = (size_t)d.nbins;
-    std::vector<double> cdf((size_t)ntab * t.nrows * (nb + 1));
-    std::vector<uint16_t> guide((size_t)ntab * t.nrows * nb);
+    const size_t cs = (nb + 2) & ~(size_t)1;     // doubles per CDF row (nb+1 used)
+    const size_t gs = (nb + 7) & ~(size_t)7;     // entries per guide row
+    t.cdf_stride = (int)cs;
+    t.guide_stride = (int)gs;
+    std::vector<double> cdf((size_t)ntab * t.nrows * cs, 1.0);
+    std::vector<uint16_t> guide((size_t)ntab * t.nrows * gs, 0);
     for (int tb = 0; tb < ntab; ++tb) {
       const double* tab = tb == 0 ? d.cosmic : (tb == 1 ? d.metal : d.var + (size_t)(tb - 2) * t.nrows * nb);
       for (int r = 0; r < t.nrows; ++r) {
         const double* p = tab + (size_t)r * nb;
-        double* c = cdf.data() + ((size_t)tb * t.nrows + r) * (nb + 1);
-        uint16_t* g = guide.data() + ((size_t)tb * t.nrows + r) * nb;
+        double* c = cdf.data() + ((size_t)tb * t.nrows + r) * cs;
+        uint16_t* g = guide.data() + ((size_t)tb * t.nrows + r) * gs;
         long double tot = 0.0L;
         for (size_t j = 0; j < nb; ++j) tot += p[j];
         long double run = 0.0L;
@@ -103,13 +107,6 @@ static int build_table(pxb_model* m, const pxb_table_desc& d, DevTable& t) {
     }
     if ((rc = upload(m, cdf.data(), cdf.size() * sizeof(double), (const void**)&t.rowcdf))) return rc;
     if ((rc = upload(m, guide.data(), guide.size() * sizeof(uint16_t), (const void**)&t.guide))) return rc;
-    std::vector<double> pairs((size_t)ntab * t.nrows * nb * 2);
-    for (size_t ro = 0; ro < (size_t)ntab * t.nrows; ++ro)
-      for (size_t j = 0; j < nb; ++j) {
-        pairs[(ro * nb + j) * 2 + 0] = cdf[ro * (nb + 1) + j];
-        pairs[(ro * nb + j) * 2 + 1] = cdf[ro * (nb + 1) + j + 1];
-      }
-    if ((rc = upload(m, pairs.data(), pairs.size() * sizeof(double), (const void**)&t.cdfpair))) return rc;
   }
   return PXB_OK;
 }
@@ -525,8 +522,17 @@ __device__ __forceinline__ FastCell fast_setup(const DevModel& M, const pxb_ther
   return fc;
 }
 
+// Rows staged in shared memory by the persistent sampler: CDFs and guides of rows (tag, tag+1)
+// of the cosmic and metal tables of the primary table (slot = 2*table + (row - tag)).
+struct StagedRows {
+  int tag;                 // first staged row, -1: nothing staged
+  const double* cdf;       // [4][cdf_stride]
+  const uint16_t* guide;   // [4][guide_stride]
+};
+
 __device__ __forceinline__ double fast_draw(const DevModel& M, const pxb_thermal_cells& C,
-                                            const FastCell& fc, int64_t i, double u1, double u2) {
+                                            const FastCell& fc, int64_t i, double u1, double u2,
+                                            const StagedRows& S) {
   const DevTable* t = (fc.meta & 8) ? &M.fb : &M.prim;
   const int nr = fc.meta & 7;
   // row
@@ -560,17 +566,23 @@ __device__ __forceinline__ double fast_draw(const DevModel& M, const pxb_thermal
   // invert the row CDF: guide table then a short forward walk over (cdf[j], cdf[j+1]) pairs
   const int nb = t->nbins;
   const size_t ro = (size_t)tab * t->nrows + row;
-  const double* __restrict__ cdf = t->rowcdf + ro * (size_t)(nb + 1);
-  const uint16_t* __restrict__ g = t->guide + ro * (size_t)nb;
+  const double* cdf = t->rowcdf + ro * (size_t)t->cdf_stride;
+  const uint16_t* g = t->guide + ro * (size_t)t->guide_stride;
+  const unsigned dr = (unsigned)(row - S.tag);
+  if (S.tag >= 0 && tab < 2 && dr < 2u && !(fc.meta & 8)) {   // staged: shared-memory gathers
+    const int slot = tab * 2 + (int)dr;
+    cdf = S.cdf + (size_t)slot * t->cdf_stride;
+    g = S.guide + (size_t)slot * t->guide_stride;
+  }
   const int k = min((int)(u2 * nb), nb - 1);
-  int j = __ldg(g + k);
+  int j = g[k];
   double2 c;
-  c.y = __ldg(cdf + j + 1);
+  c.y = cdf[j + 1];
   while (c.y <= u2 && j + 1 < nb) {
     ++j;
-    c.y = __ldg(cdf + j + 1);
+    c.y = cdf[j + 1];
   }
-  c.x = __ldg(cdf + j);
+  c.x = cdf[j];
   if (M.method == 1) return __ldg(M.emid + j);
   double e0, e1;
   if (M.edges_uniform) {
@@ -633,9 +645,181 @@ k_thermal_sample_fast(const DevModel M, const __grid_constant__ pxb_thermal_cell
     if (!(fc.meta & 16)) continue;
     const int64_t i = idx[k];
     const Philox4 rn = pxb_rand4(C.seed, STREAM_ENERGY, (uint64_t)(C.cell_id0 + i), (uint64_t)(p - first));
-    double e = fast_draw(M, C, fc, i, u53(rn.x, rn.y), u53(rn.z, rn.w));
+    const StagedRows none{-1, nullptr, nullptr};
+    double e = fast_draw(M, C, fc, i, u53(rn.x, rn.y), u53(rn.z, rn.w), none);
     if (M.binscale_log) e = exp10(e);
     st_stream(energies + p, e);
+  }
+}
+
+// ---- mixture sampler with TMA-staged table rows -----------------------------------------
+// Persistent CTAs (one per SM).  A CTA takes chunks of 32768 consecutive photons; the rows the
+// chunk's first cell blends (t, t+1 of the cosmic and metal tables: 4 x (32 KB CDF + 8 KB
+// guide) at nbins = 4000) are brought into shared memory with four+four cp.async.bulk copies
+// completing on one mbarrier, and stay there across chunks while the temperature bin does not
+// change.  Inside a chunk every warp owns 64-photon tiles (no CTA barriers); photons whose
+// component lives in a staged row gather from shared memory, all others from L1/L2.
+constexpr int STG_THREADS = 768;
+constexpr int STG_WARPS = STG_THREADS / 32;
+constexpr int STG_WTILE = 128;
+constexpr int STG_CHUNK = 32768;
+constexpr int STG_TILES_PER_CHUNK = STG_CHUNK / STG_WTILE;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, uint32_t bytes,
+                                             uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+      ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok = 0;
+  while (!ok) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+  }
+}
+
+// Per-cell preparation for the mixture sampler: one thread per ACTIVE cell computes the cell's
+// mixture weights once (FastCell, 32 B) and records, for every 128-photon tile that starts
+// inside the cell's photon range, that the tile starts in this cell -- so the sampler neither
+// repeats the table-node search per tile nor searches the offsets.  Cells the mixture path
+// cannot take (extrapolating, negative abundance) are appended to the general kernel's list.
+__global__ void __launch_bounds__(256)
+k_thermal_cellprep(const DevModel M, const __grid_constant__ pxb_thermal_cells C,
+                   int64_t n_active, const int64_t* __restrict__ idx,
+                   const int64_t* __restrict__ poff, FastCell* __restrict__ fcs,
+                   int64_t* __restrict__ tile_cell, int64_t* __restrict__ list,
+                   unsigned long long* __restrict__ list_count) {
+  const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n_active) return;
+  const FastCell fc = fast_setup(M, C, idx[k]);
+  fcs[k] = fc;
+  const int64_t a = poff[k], b = poff[k + 1];
+  if (!(fc.meta & 16) && b > a) {
+    const unsigned long long slot = atomicAdd(list_count, 1ull);
+    list[slot] = k;
+  }
+  for (int64_t t = (a + STG_WTILE - 1) / STG_WTILE; t * STG_WTILE < b; ++t) tile_cell[t] = k;
+}
+
+__global__ void __launch_bounds__(STG_THREADS, 1)
+k_thermal_sample_staged(const DevModel M, const __grid_constant__ pxb_thermal_cells C,
+                        int64_t n_active, const int64_t* __restrict__ idx,
+                        const int64_t* __restrict__ poff, int64_t n_photons,
+                        double* __restrict__ energies, const FastCell* __restrict__ fcs,
+                        const int64_t* __restrict__ tile_cell,
+                        unsigned int* __restrict__ chunk_counter, int use_staging) {
+  extern __shared__ __align__(128) unsigned char dyn[];
+  const DevTable& T = M.prim;
+  const size_t cdf_bytes = use_staging ? (size_t)T.cdf_stride * sizeof(double) : 0;
+  const size_t gd_bytes = use_staging ? (size_t)T.guide_stride * sizeof(uint16_t) : 0;
+  double* s_cdf = reinterpret_cast<double*>(dyn);
+  uint16_t* s_guide = reinterpret_cast<uint16_t*>(dyn + 4 * cdf_bytes);
+  int64_t* s_off_all = reinterpret_cast<int64_t*>(dyn + 4 * cdf_bytes + 4 * gd_bytes);
+  __shared__ uint64_t s_bar;
+  __shared__ unsigned int s_chunk;
+
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  int64_t* s_off = s_off_all + (size_t)wid * (STG_WTILE + 2);
+  if (threadIdx.x == 0) mbar_init(&s_bar, 1);
+  __syncthreads();
+  int tag = -1;
+  uint32_t parity = 0;
+  const int64_t nchunks = (n_photons + STG_CHUNK - 1) / STG_CHUNK;
+  const int64_t ntiles_all = (n_photons + STG_WTILE - 1) / STG_WTILE;
+
+  for (;;) {
+    if (threadIdx.x == 0) s_chunk = atomicAdd(chunk_counter, 1u);
+    __syncthreads();     // also: every warp is done with the previous chunk's staged rows
+    const int64_t chunk = s_chunk;
+    if (chunk >= nchunks) break;
+    const int64_t tile0 = chunk * STG_TILES_PER_CHUNK;
+    const int ntile = (int)min((int64_t)STG_TILES_PER_CHUNK, ntiles_all - tile0);
+    if (use_staging) {
+      // temperature bin of the chunk's first cell decides what is staged
+      const FastCell f0 = fcs[__ldg(tile_cell + tile0)];
+      const int want = ((f0.meta & 7) == 2 && !(f0.meta & 8)) ? f0.z1 : -1;
+      if (want >= 0 && want != tag) {
+        if (threadIdx.x == 0) {
+          mbar_expect_tx(&s_bar, (uint32_t)(4 * (cdf_bytes + gd_bytes)));
+#pragma unroll
+          for (int slot = 0; slot < 4; ++slot) {
+            const size_t ro = (size_t)(slot >> 1) * T.nrows + want + (slot & 1);
+            tma_bulk_g2s(s_cdf + (size_t)slot * T.cdf_stride, T.rowcdf + ro * T.cdf_stride,
+                         (uint32_t)cdf_bytes, &s_bar);
+            tma_bulk_g2s(s_guide + (size_t)slot * T.guide_stride, T.guide + ro * T.guide_stride,
+                         (uint32_t)gd_bytes, &s_bar);
+          }
+        }
+        mbar_wait(&s_bar, parity);
+        parity ^= 1u;
+        tag = want;
+      }
+    }
+    const StagedRows S{tag, s_cdf, s_guide};
+
+    for (int tl = wid; tl < ntile; tl += STG_WARPS) {
+      const int64_t tile = tile0 + tl;
+      const int64_t p0 = tile * STG_WTILE;
+      const int64_t p1 = min(p0 + (int64_t)STG_WTILE, n_photons);
+      const int64_t c0 = __ldg(tile_cell + tile);
+      const int64_t c1 = (tile + 1 < ntiles_all) ? __ldg(tile_cell + tile + 1) : n_active - 1;
+      const int nc = (c1 - c0 + 1 <= STG_WTILE + 1) ? (int)(c1 - c0 + 1) : 0;
+      __syncwarp();
+      for (int q = lane; q <= nc && nc > 0; q += 32) s_off[q] = __ldg(poff + c0 + q);
+      __syncwarp();
+#pragma unroll 2
+      for (int r = 0; r < STG_WTILE / 32; ++r) {
+        const int64_t p = p0 + r * 32 + lane;
+        if (p >= p1) continue;
+        int64_t first, k;
+        if (nc > 0) {
+          int rel = 0;
+          if (nc > 1) {
+#pragma unroll
+            for (int step = STG_WTILE; step > 0; step >>= 1) {
+              const int q = rel + step;
+              if (q < nc && s_off[q] <= p) rel = q;
+            }
+          }
+          k = c0 + rel;
+          first = s_off[rel];
+        } else {  // more cells than photons in the tile (never for active lists)
+          int64_t lo = c0, hi = c1 + 1;
+          while (hi - lo > 1) {
+            const int64_t mid = (lo + hi) >> 1;
+            if (__ldg(poff + mid) <= p) lo = mid; else hi = mid;
+          }
+          k = lo;
+          first = __ldg(poff + k);
+        }
+        const FastCell fc = fcs[k];
+        if (!(fc.meta & 16)) continue;
+        const int64_t i = __ldg(idx + k);
+        const Philox4 rn = pxb_rand4(C.seed, STREAM_ENERGY, (uint64_t)(C.cell_id0 + i), (uint64_t)(p - first));
+        double e = fast_draw(M, C, fc, i, u53(rn.x, rn.y), u53(rn.z, rn.w), S);
+        if (M.binscale_log) e = exp10(e);
+        st_stream(energies + p, e);
+      }
+    }
   }
 }
 
@@ -701,9 +885,11 @@ extern "C" int pxb_interp_spec(const pxb_model* model, int64_t n, const double* 
   return PXB_OK;
 }
 
-extern "C" int pxb_thermal_sample_workspace_bytes(int64_t n_active, int64_t* bytes) {
-  PXB_REQUIRE(bytes && n_active >= 0, "bad argument");
-  *bytes = (n_active + 2) * (int64_t)sizeof(int64_t);
+extern "C" int pxb_thermal_sample_workspace_bytes(int64_t n_active, int64_t n_photons,
+                                                  int64_t* bytes) {
+  PXB_REQUIRE(bytes && n_active >= 0 && n_photons >= 0, "bad argument");
+  const int64_t ntiles = (n_photons + STG_WTILE - 1) / STG_WTILE;
+  *bytes = (4 + n_active + ntiles + 1) * (int64_t)sizeof(int64_t) + n_active * (int64_t)sizeof(FastCell);
   return PXB_OK;
 }
 
@@ -732,16 +918,34 @@ extern "C" int pxb_thermal_sample(const pxb_model* model, const pxb_thermal_cell
   unsigned long long* count = nullptr;
   if (D.fast_ok) {
     int64_t need = 0;
-    pxb_thermal_sample_workspace_bytes(n_active, &need);
+    pxb_thermal_sample_workspace_bytes(n_active, n_photons, &need);
     PXB_REQUIRE(workspace && workspace_bytes >= need, "sample workspace too small (%lld < %lld)",
                 (long long)workspace_bytes, (long long)need);
+    // workspace: [count, chunk counter, pad, pad | list[n_active] | tile_cell[ntiles+1] | FastCell[n_active]]
+    const int64_t ntiles = (n_photons + STG_WTILE - 1) / STG_WTILE;
     count = (unsigned long long*)workspace;
-    list = (int64_t*)workspace + 2;
-    PXB_CUDA(cudaMemsetAsync(count, 0, sizeof(unsigned long long), st));
-    const int64_t ntiles = (n_photons + FAST_TILE - 1) / FAST_TILE;
-    PXB_REQUIRE(ntiles < (1LL << 31), "too many photons for one call");
-    k_thermal_sample_fast<<<(unsigned)ntiles, FAST_THREADS, 0, st>>>(D, *cells, n_active, idx, poff,
-                                                                    n_photons, energies, list, count);
+    unsigned int* chunk_counter = (unsigned int*)((int64_t*)workspace + 2);
+    list = (int64_t*)workspace + 4;
+    int64_t* tile_cell = list + n_active;
+    FastCell* fcs = (FastCell*)(tile_cell + ntiles + 1);
+    PXB_CUDA(cudaMemsetAsync(workspace, 0, 4 * sizeof(int64_t), st));
+    k_thermal_cellprep<<<(unsigned)((n_active + 255) / 256), 256, 0, st>>>(
+        D, *cells, n_active, idx, poff, fcs, tile_cell, list, count);
+    PXB_LAUNCH_CHECK();
+    // rows are staged in shared memory when the model is a plain 1-D table whose four blended
+    // rows fit beside the per-warp offsets; otherwise the same kernel gathers from L1/L2
+    const size_t off_bytes = (size_t)STG_WARPS * (STG_WTILE + 2) * sizeof(int64_t);
+    const size_t row_bytes = 4 * ((size_t)D.prim.cdf_stride * 8 + (size_t)D.prim.guide_stride * 2);
+    const int use_staging = (!D.density_dependent && !D.has_fb && row_bytes + off_bytes <= 220 * 1024) ? 1 : 0;
+    const size_t stg_smem = off_bytes + (use_staging ? row_bytes : 0);
+    PXB_REQUIRE(n_photons < (int64_t)STG_CHUNK * ((1LL << 32) - 4096), "too many photons for one call");
+    PXB_CUDA(cudaFuncSetAttribute(k_thermal_sample_staged,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stg_smem));
+    const int64_t nchunks = (n_photons + STG_CHUNK - 1) / STG_CHUNK;
+    int64_t g2 = pxb_sm_count();
+    if (g2 > nchunks) g2 = nchunks;
+    k_thermal_sample_staged<<<(unsigned)g2, STG_THREADS, stg_smem, st>>>(
+        D, *cells, n_active, idx, poff, n_photons, energies, fcs, tile_cell, chunk_counter, use_staging);
     PXB_LAUNCH_CHECK();
   }
   k_thermal_sample_cta<<<(unsigned)grid, SAMPLE_THREADS, smem, st>>>(

@@ -25,9 +25,9 @@ struct DevTable {
   // mixture fast path (only when nonneg): per-row normalised CDFs [(2+nvar), nrows, nbins+1]
   // (table order cosmic, metal, var_0..) and guide tables [(2+nvar), nrows, nbins]:
   // guide[k] = bin holding the quantile k/nbins.
-  const double* rowcdf;
-  const uint16_t* guide;
-  const double2* cdfpair; // [(2+nvar), nrows, nbins]: (cdf[j], cdf[j+1]) in one 16-byte load
+  const double* rowcdf;    // row stride cdf_stride doubles (even: rows are 16-byte aligned for TMA)
+  const uint16_t* guide;   // row stride guide_stride entries (multiple of 8)
+  int cdf_stride, guide_stride;
 };
 
 struct DevModel {

@@ -1,0 +1,168 @@
+"""GPU: whole-path tests through the public API (make_photons -> project_photons), including
+size-independent properties at larger sizes and file round trips."""
+import numpy as np
+import pytest
+import torch
+from scipy import stats
+
+import pyxsim_b200 as px
+from pyxsim_b200 import synthetic
+
+import helpers as H
+
+pytestmark = pytest.mark.gpu
+TF = ("gas", "kT")
+
+
+def _cluster(n=32, nbins=1000, **kw):
+    kT_nodes, ebins, cosmic, metal, _ = synthetic.apec_like_tables(nT=36, nbins=nbins)
+    src = synthetic.beta_model_source(n, v3d_sigma_kms=300.0, **kw)
+    sm = px.ThermalSpectralModel(ebins, kT_nodes, cosmic, metal)
+    return src, sm, (kT_nodes, ebins, cosmic, metal)
+
+
+def test_beta_model_end_to_end_vs_oracle(cuda, oracle):
+    """configs[0]-shaped run (beta-model cluster, thermal source, tabulated absorption, project
+    along z): photon and event counts within Poisson/binomial error of the oracle's, energy and
+    sky distributions KS-compatible -- the reference's acceptance style (tests/test_beta_model.py)."""
+    src, sm, (kT_nodes, ebins, cosmic, metal) = _cluster(32, kT_range=(2.0, 9.0))
+    en, sg = synthetic.tbabs_like_sigma()
+    area, texp, z = 3000.0, 1.0e5, 0.05
+
+    def run(seed_mine, seed_ref):
+        model = px.ThermalSourceModel(sm, 0.1, 10.0, 1000, 0.3, temperature_field=TF, prng=seed_mine)
+        n_ph, n_c = px.make_photons("mem:e2e_ph", src, z, area, texp, model)
+        n_ev = px.project_photons("mem:e2e_ph", "mem:e2e_ev", "z", [30.0, 45.0],
+                                  absorb_model=px.TBabsModel(0.02, energy=en, cross_section=sg),
+                                  nH=0.02, prng=seed_mine + 1)
+        ph, ev = px.load_list("mem:e2e_ph"), px.load_list("mem:e2e_ev")
+        # oracle on identical inputs
+        f = {k: v.cpu().numpy() for k, v in src.fields.items()}
+        D_A = px.Cosmology().angular_diameter_distance_mpc(0.0, z)
+        norm = area * texp / (4 * np.pi * (D_A * 3.0856775809623245e24) ** 2 * (1 + z) ** 2)
+        om = oracle.TableModel(ebins, kT_nodes, cosmic, metal)
+        cfg = dict(kT_min=0.025, kT_max=64.0, Zmet=0.3, spectral_norm=norm)
+        a = dict(kT=f[TF], em=f[("gas", "emission_measure")])
+        nc, nph, idx, e = oracle.thermal_process_data(om, cfg, a, np.random.RandomState(seed_ref))
+        cut, tot, lam = oracle.thermal_spectra(om, cfg, a)
+        assert abs(n_ph - lam.sum()) < 5 * np.sqrt(lam.sum())
+        assert abs(n_ph - nph.sum()) < 5 * np.sqrt(2 * lam.sum())
+        g = oracle.gather_active([f[("index", ax)] for ax in "xyz"],
+                                 [f[("gas", f"velocity_{ax}")] for ax in "xyz"], f[("index", "dx")],
+                                 idx, [-1000.0] * 3, [1000.0] * 3, [2000.0] * 3, [0.0] * 3, [0.0] * 3,
+                                 (False,) * 3)
+        d = dict(g, num_photons=nph, energy=e)
+        params = dict(data_type="cells", observer="external", fid_d_a=D_A, fid_redshift=z)
+        ref = oracle.project_photons(d, params, "z", [30.0, 45.0], np.random.RandomState(seed_ref + 1),
+                                     absorb_model=oracle.TableAbsorb(0.02, en, sg), nH=0.02)
+        frac_m, frac_r = n_ev / n_ph, ref["n_events"] / nph.sum()
+        assert abs(frac_m - frac_r) < 5 * np.sqrt(2 * frac_r * (1 - frac_r) / nph.sum())
+        return {"energy": stats.ks_2samp(ph.numpy("energy"), e).pvalue,
+                "eobs": stats.ks_2samp(ev.numpy("eobs"), ref["eobs"]).pvalue,
+                "xsky": stats.ks_2samp(ev.numpy("xsky"), ref["xsky"]).pvalue,
+                "ysky": stats.ks_2samp(ev.numpy("ysky"), ref["ysky"]).pvalue}
+
+    H.assert_distributions_agree(run, seeds=((50, 7), (60, 9)))
+
+
+def test_plugin_contract_and_file_roundtrip(cuda, tmp_path):
+    """process_data returns the reference tuple; lists written to disk (npz fallback of the HDF5
+    schema) project to the same events as the in-memory list."""
+    src, sm, _ = _cluster(16, nbins=500)
+    model = px.ThermalSourceModel(sm, 0.1, 10.0, 500, 0.3, temperature_field=TF, prng=3)
+    model.setup_model("photons", src, 0.05)
+    ncells, nph, idxs, energies = model.process_data("photons", next(src.chunks()), 1.0e-45)
+    assert isinstance(nph, np.ndarray) and nph.dtype == np.int64 and energies.dtype == np.float64
+    assert ncells == nph.size == idxs.size and energies.size == nph.sum() and np.all(nph > 0)
+    assert np.all(np.diff(idxs) > 0)
+    with pytest.raises(NotImplementedError):
+        model.process_data("spectrum", next(src.chunks()), 1.0)
+    prefix = str(tmp_path / "photons")
+    model2 = px.ThermalSourceModel(sm, 0.1, 10.0, 500, 0.3, temperature_field=TF, prng=3)
+    n1 = px.make_photons(prefix + ".h5", src, 0.05, 5.0e4, 1.0e5, model2)
+    model3 = px.ThermalSourceModel(sm, 0.1, 10.0, 500, 0.3, temperature_field=TF, prng=3)
+    n2 = px.make_photons("mem:rt", src, 0.05, 5.0e4, 1.0e5, model3)
+    assert n1 == n2
+    e1 = px.project_photons(prefix, str(tmp_path / "events"), [0.1, 0.2, 0.9], [12.0, -3.0],
+                            absorb_model="wabs", nH=0.03, prng=8)
+    e2 = px.project_photons("mem:rt", "mem:rt_ev", [0.1, 0.2, 0.9], [12.0, -3.0],
+                            absorb_model="wabs", nH=0.03, prng=8)
+    assert e1 == e2
+    a, b = px.load_list(str(tmp_path / "events")), px.load_list("mem:rt_ev")
+    for k in ("xsky", "ysky", "eobs"):
+        assert np.array_equal(a.numpy(k), b.numpy(k))
+    assert a.parameters["absoption_model"] == "wabs" and float(a.parameters["flux"]) == b.parameters["flux"]
+    with pytest.raises(ValueError):
+        px.make_photons("mem:bad", src, 0.0, 1.0, 1.0, model3)     # redshift <= 0 without dist
+    n3 = px.make_photons("mem:near", src, 0.0, 5.0e4, 1.0e5, model3, dist=(200.0, "Mpc"))
+    assert n3[0] > 0
+
+
+def test_reference_style_host_model_drives_make_photons(cuda):
+    """A third-party (host) source model that only honours the reference plugin contract can be
+    driven by pyxsim_b200.make_photons."""
+    src, sm, _ = _cluster(8, nbins=100)
+
+    class HostModel:
+        ftype = "gas"
+
+        def setup_model(self, mode, data_source, redshift):
+            pass
+
+        def set_pv(self, p_fields, v_fields, **kw):
+            self.p_fields, self.v_fields = p_fields, v_fields
+            for k, v in kw.items():
+                setattr(self, k, v)
+
+        def process_data(self, mode, chunk, spectral_norm):
+            n = chunk.size
+            nph = np.zeros(n, dtype=np.int64)
+            nph[::7] = 3
+            act = nph > 0
+            return int(act.sum()), nph[act], act, np.full(int(nph.sum()), 1.5)
+
+        def cleanup_model(self, mode):
+            pass
+
+    n_ph, n_c = px.make_photons("mem:host", src, 0.05, 1.0, 1.0, HostModel())
+    lst = px.load_list("mem:host")
+    assert n_ph == 3 * n_c and np.all(lst.numpy("energy") == 1.5)
+    assert np.array_equal(lst.numpy("x"), src.fields[("index", "x")].cpu().numpy()[::7])
+
+
+@pytest.mark.parametrize("n,photons", [(128, 2.0e8)])
+def test_large_properties(cuda, n, photons):
+    """Size-independent properties at a size the oracle cannot reach: counts add up, offsets are
+    consistent, energies stay inside the table range, no-shift/no-absorb projection is the
+    identity on energies, reruns are bit-identical, Doppler-only events are a permutation-free
+    rescaling of the photons."""
+    src, sm, (kT_nodes, ebins, cosmic, metal) = _cluster(n, nbins=4000, device="cuda")
+    em_sum = float(src.fields[("gas", "emission_measure")].sum())
+    ss = float(np.interp(6.0, kT_nodes, cosmic.sum(1) + 0.3 * metal.sum(1)))
+    D_A = px.Cosmology().angular_diameter_distance_mpc(0.0, 0.05)
+    at = photons / (em_sum * ss / (4 * np.pi * (D_A * 3.0856775809623245e24) ** 2 * 1.05 ** 2))
+    model = px.ThermalSourceModel(sm, 0.1, 10.0, 4000, 0.3, temperature_field=TF, prng=77)
+    n_ph, n_c = px.make_photons("mem:big", src, 0.05, at / 1e5, 1e5, model)
+    assert abs(n_ph - photons) < 6 * np.sqrt(photons)
+    lst = px.load_list("mem:big")
+    nph, e = lst.data["num_photons"], lst.data["energy"]
+    assert int(nph.sum()) == n_ph == e.numel() and int(nph.min()) >= 1 and nph.numel() == n_c
+    assert float(e.min()) >= ebins[0] and float(e.max()) <= ebins[-1]
+    checksum = float(e.sum())
+    n_all = px.project_photons("mem:big", "mem:big_id", "x", [1.0, 2.0], no_shifting=True, prng=5)
+    ev = px.load_list("mem:big_id")
+    assert n_all == n_ph and torch.equal(ev.data["eobs"], e)
+    n1 = px.project_photons("mem:big", "mem:big_a", "z", [30.0, 45.0], absorb_model="wabs", nH=0.02, prng=9)
+    a = {k: v.clone() for k, v in px.load_list("mem:big_a").data.items()}
+    n2 = px.project_photons("mem:big", "mem:big_a", "z", [30.0, 45.0], absorb_model="wabs", nH=0.02, prng=9)
+    b = px.load_list("mem:big_a").data
+    assert n1 == n2 and all(torch.equal(a[k], b[k]) for k in a)
+    assert 0.5 * n_ph < n1 < n_ph
+    # sky positions stay inside the projected box (+ half a cell), flux bookkeeping is exact
+    half = (1000.0 + 2000.0 / n) / (D_A * 1e3) * 180 / np.pi
+    assert float((a["ysky"] - 45.0).abs().max()) <= half * 1.001
+    model_b = px.ThermalSourceModel(sm, 0.1, 10.0, 4000, 0.3, temperature_field=TF, prng=77)
+    px.make_photons("mem:big2", src, 0.05, at / 1e5, 1e5, model_b)
+    assert float(px.load_list("mem:big2").data["energy"].sum()) == checksum
+    for k in ("mem:big", "mem:big2", "mem:big_id", "mem:big_a"):
+        px.drop_list(k)
