@@ -134,12 +134,15 @@ k_pixel_to_cel(int64_t n, double* __restrict__ xs, double* __restrict__ ys, doub
 // ---------------------------------------------------------------------------------------
 // per-cell pre-pass
 // ---------------------------------------------------------------------------------------
+constexpr int PROJ_WTILE_C = 256;   // photons per warp tile (== PROJ_WTILE below)
+
 struct CellDerived {
   double* shift;  // Doppler factor (1 when no_shifting)
   double* cx;     // centre . x_hat
   double* cy;     // centre . y_hat
   double* cz;     // centre . z_hat (the reference's `los`; also the 3rd all-sky coordinate)
   double* w;      // scatter width: dx (cells), dx/2 (particles, external observer)
+  int64_t* tile_cell;  // [n_wtiles + 1]: cell holding the first photon of every warp tile
 };
 
 __global__ void __launch_bounds__(256)
@@ -170,6 +173,9 @@ k_project_cells(const __grid_constant__ pxb_photon_list L,
   double w = L.dx ? L.dx[c] : 0.0;
   if (P.observer == 0 && P.data_type == 1) w *= 0.5;  // photon_list.py:733-734
   D.w[c] = w;
+  // every warp tile that starts inside this cell's photon range starts in this cell
+  const int64_t a = L.poff[c], b = L.poff[c + 1];
+  for (int64_t t = (a + PROJ_WTILE_C - 1) / PROJ_WTILE_C; t * PROJ_WTILE_C < b; ++t) D.tile_cell[t] = c;
 }
 
 // ---------------------------------------------------------------------------------------
@@ -188,6 +194,7 @@ constexpr int PROJ_THREADS = 256;
 constexpr int PROJ_WARPS = PROJ_THREADS / 32;
 constexpr int PROJ_ITEMS = 8;
 constexpr int PROJ_WTILE = 32 * PROJ_ITEMS;            // photons per warp tile
+static_assert(PROJ_WTILE == PROJ_WTILE_C, "tile size used by the cell pre-pass");
 constexpr int PROJ_CTILE = PROJ_WARPS * PROJ_WTILE;    // photons per ticket
 
 constexpr unsigned long long ST_AGG = 1ull << 62;   // tile aggregate available
@@ -228,7 +235,10 @@ __device__ __forceinline__ int64_t warp_lookback(unsigned long long* status, int
     const unsigned emp = __ballot_sync(0xffffffffu, (sv & ST_MASK) == 0ull);
     const int first = inc ? (__ffs(inc) - 1) : 32;           // nearest tile with an inclusive prefix
     const unsigned need = first >= 31 ? 0xffffffffu : ((2u << first) - 1u);
-    if (emp & need) continue;                                // a needed predecessor is not ready
+    if (emp & need) {                                        // a needed predecessor is not ready
+      __nanosleep(200);
+      continue;
+    }
     int64_t v = (lane <= first) ? (int64_t)(sv & ~ST_MASK) : 0;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -263,9 +273,13 @@ __device__ __forceinline__ void tan_to_cel_fast(double x, double y, double ra0_r
                                                 double& dec_deg) {
   const double den = cos_d0 - y * sin_d0;
   const double h = sqrt(x * x + den * den);
-  const double s = x * x / (h + den);
-  const double t1 = -x / den;
-  const double t2 = (y - s * sin_d0) / (1.0 + s * cos_d0);
+  // three quotients x^2/(h+den), -x/den, num2/den2 share one reciprocal
+  const double hd = h + den;
+  const double den2 = hd + x * x * cos_d0;          // (1 + s cos d0) * (h + den)
+  const double num2 = y * hd - x * x * sin_d0;      // (y - s sin d0) * (h + den)
+  const double inv = 1.0 / (den * den2);
+  const double t1 = -x * den2 * inv;
+  const double t2 = num2 * den * inv;
   if (den > 0.0 && fabs(t1) <= 0.0625 && fabs(t2) <= 0.0625) {
     ra_deg = (ra0_rad + atan_small(t1)) * PXB_RAD2DEG;
     dec_deg = (d0_rad + atan_small(t2)) * PXB_RAD2DEG;
@@ -277,9 +291,14 @@ __device__ __forceinline__ void tan_to_cel_fast(double x, double y, double ra0_r
 // u < exp(-tau) without evaluating exp when the bounds 1 - tau <= exp(-tau) <= 1 - tau + tau^2/2
 // already decide (tau >= 0)
 __device__ __forceinline__ bool survives(double u, double tau) {
-  const double lo = 1.0 - tau;
-  if (u < lo) return true;
-  if (u >= lo + 0.5 * tau * tau) return false;
+  // partial sums of the alternating series bracket exp(-tau) for tau >= 0:
+  //   S3 = 1 - t + t^2/2 - t^3/6 <= exp(-t) <= S3 + t^4/24
+  if (tau < 1.0) {
+    const double s3 = 1.0 - tau * (1.0 - tau * (0.5 - tau * (1.0 / 6.0)));
+    if (u < s3) return true;
+    const double t2 = tau * tau;
+    if (u >= s3 + t2 * t2 * (1.0 / 24.0)) return false;
+  }
   return u < exp(-tau);
 }
 
@@ -418,7 +437,7 @@ k_project_photons(const __grid_constant__ pxb_photon_list L,
   // per-warp scratch: cell offsets of the tile and the per-photon state carried from phase 1
   // to phase 3 (energy, cell, output slot) -- kept in shared memory so the item loops stay
   // rolled (small code, few registers, more resident warps)
-  __shared__ int64_t s_off_all[PROJ_WARPS][PROJ_WTILE + 1];
+  __shared__ int64_t s_off_all[PROJ_WARPS][PROJ_WTILE + 2];
   __shared__ double s_e_all[PROJ_WARPS][PROJ_WTILE];
   __shared__ int s_rel_all[PROJ_WARPS][PROJ_WTILE];
   __shared__ short s_slot_all[PROJ_WARPS][PROJ_WTILE];
@@ -447,12 +466,21 @@ k_project_photons(const __grid_constant__ pxb_photon_list L,
     const int64_t p1 = min(p0 + (int64_t)PROJ_WTILE, L.n_photons);
 
     // ---- cells intersecting this warp tile -------------------------------------------
-    const int64_t c0 = warp_search_le(L.poff, L.n_cells, p0, lane);
-    const int64_t c1 = warp_search_le(L.poff, L.n_cells, p1 - 1, lane);
-    const int nc = (c1 - c0 + 1 <= PROJ_WTILE) ? (int)(c1 - c0 + 1) : 0;
+    // (the per-cell pre-pass recorded the cell every tile starts in; the tile ends in the cell
+    // the next tile starts in, or one before it)
+    const int64_t c0 = __ldg(D.tile_cell + wtile);
+    const int64_t c1 = (wtile + 1 < n_wtiles) ? __ldg(D.tile_cell + wtile + 1) : L.n_cells - 1;
+    const int nc = (c1 - c0 + 1 <= PROJ_WTILE + 1) ? (int)(c1 - c0 + 1) : 0;
     __syncwarp();
     for (int q = lane; q <= nc && nc > 0; q += 32) s_off[q] = __ldg(L.poff + c0 + q);
     __syncwarp();
+
+    // all eight energy loads of the lane go out together (the item loop below is rolled)
+#pragma unroll
+    for (int r = 0; r < PROJ_ITEMS; ++r) {
+      const int it = r * 32 + lane;
+      if (p0 + it < p1) s_e[it] = ld_stream(L.energy + p0 + it);
+    }
 
     // ---- phase 1: Doppler + absorption, survivors ----------------------------------------
     int run = 0;
@@ -470,7 +498,7 @@ k_project_photons(const __grid_constant__ pxb_photon_list L,
         } else if (nc > 0) {
           // branch-free bisection: largest q in [0, nc) with s_off[q] <= p
 #pragma unroll
-          for (int step = PROJ_WTILE / 2; step > 0; step >>= 1) {
+          for (int step = PROJ_WTILE; step > 0; step >>= 1) {
             const int q = rel + step;
             if (q < nc && s_off[q] <= p) rel = q;
           }
@@ -485,7 +513,7 @@ k_project_photons(const __grid_constant__ pxb_photon_list L,
           first = __ldg(L.poff + lo);
         }
         const int64_t c = c0 + rel;
-        const double en = ld_stream(L.energy + p) * __ldg(D.shift + c);
+        const double en = s_e[it] * __ldg(D.shift + c);
         det = absorb ? absorb_decision(P, c, p - first, en) : true;
         s_e[it] = en;
         s_rel[it] = rel;
@@ -575,7 +603,7 @@ static inline int64_t align256(int64_t v) { return (v + 255) & ~(int64_t)255; }
 
 struct ProjLayout {
   int64_t ntiles;
-  int64_t off_cells, off_status, off_ticket, off_part, off_red, total;
+  int64_t off_cells, off_tilecell, off_status, off_ticket, off_part, off_red, total;
 };
 
 static ProjLayout proj_layout(int64_t n_cells, int64_t n_photons) {
@@ -583,6 +611,7 @@ static ProjLayout proj_layout(int64_t n_cells, int64_t n_photons) {
   l.ntiles = (n_photons + PROJ_WTILE - 1) / PROJ_WTILE;   // warp tiles
   int64_t o = 0;
   l.off_cells = o;  o += align256(5 * n_cells * (int64_t)sizeof(double));
+  l.off_tilecell = o; o += align256((l.ntiles + 1) * 8);
   l.off_status = o; o += align256(l.ntiles * 8);
   l.off_ticket = o; o += 256;
   l.off_part = o;   o += align256(3 * l.ntiles * 8);
@@ -639,6 +668,7 @@ extern "C" int pxb_project(const pxb_photon_list* L, const pxb_project_params* P
   D.cy = D.cx + L->n_cells;
   D.cz = D.cy + L->n_cells;
   D.w = D.cz + L->n_cells;
+  D.tile_cell = (int64_t*)(ws + lay.off_tilecell);
   ProjWork W;
   W.status = (unsigned long long*)(ws + lay.off_status);
   W.ticket = (unsigned int*)(ws + lay.off_ticket);

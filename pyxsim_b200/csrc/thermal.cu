@@ -72,7 +72,7 @@ static int build_table(pxb_model* m, const pxb_table_desc& d, DevTable& t) {
     const int ntab = 2 + d.nvar;
     const size_t nb = (size_t)d.nbins;
     const size_t cs = (nb + 2) & ~(size_t)1;     // doubles per CDF row (nb+1 used)
-    const size_t gs = (nb + 7) & ~(size_t)7;     // entries per guide row
+    const size_t gs = (nb + 8) & ~(size_t)7;     // entries per guide row (>= nb + 1)
     t.cdf_stride = (int)cs;
     t.guide_stride = (int)gs;
     std::vector<double> cdf((size_t)ntab * t.nrows * cs, 1.0);
@@ -103,6 +103,7 @@ static int build_table(pxb_model* m, const pxb_table_desc& d, DevTable& t) {
           while (j + 1 < nb && c[j + 1] <= q) ++j;
           g[k] = (uint16_t)j;
         }
+        for (size_t k = nb; k < gs; ++k) g[k] = (uint16_t)(nb - 1);   // sentinel: g[k+1] is always valid
       }
     }
     if ((rc = upload(m, cdf.data(), cdf.size() * sizeof(double), (const void**)&t.rowcdf))) return rc;
@@ -540,15 +541,16 @@ __device__ __forceinline__ double fast_draw(const DevModel& M, const pxb_thermal
   r = min(r, nr - 1);
   const double lo = r > 0 ? fc.cum[r - 1] : 0.0;
   const double hi = r < 3 ? fc.cum[r] : 1.0;
-  const double v = (u1 - lo) / (hi - lo);
   const int row = fast_row(t, fc.z1, nr, r);
   // table within the row: cosmic, metal, var_k with weights rs_c, Z rs_m, eZ_k rs_v
   const double xh = cell_xh(C, i);
   const double a0 = __ldg(t->rs_c + row), a1 = cell_metal(C, i, xh) * __ldg(t->rs_m + row);
   int tab = 0;
   if (C.nvar == 0) {
-    tab = (a1 > 0.0 && (v * (a0 + a1) >= a0 || !(a0 > 0.0))) ? 1 : 0;
+    // v = (u1 - lo)/(hi - lo) is the within-row uniform; metal iff v*(a0+a1) >= a0
+    tab = (a1 > 0.0 && ((u1 - lo) * (a0 + a1) >= a0 * (hi - lo) || !(a0 > 0.0))) ? 1 : 0;
   } else {
+    const double v = (u1 - lo) / (hi - lo);
     double A = a0 + a1;
     for (int k = 0; k < C.nvar; ++k)
       A += cell_elem(C, k, i, xh) * __ldg(t->rs_v + (size_t)k * t->nrows + row);
@@ -574,15 +576,18 @@ __device__ __forceinline__ double fast_draw(const DevModel& M, const pxb_thermal
     cdf = S.cdf + (size_t)slot * t->cdf_stride;
     g = S.guide + (size_t)slot * t->guide_stride;
   }
+  // the bin lies between the guide entries of quantiles k/nb and (k+1)/nb: bisect that range
+  // (a linear walk would make the whole warp wait for its unluckiest lane)
   const int k = min((int)(u2 * nb), nb - 1);
   int j = g[k];
-  double2 c;
-  c.y = cdf[j + 1];
-  while (c.y <= u2 && j + 1 < nb) {
-    ++j;
-    c.y = cdf[j + 1];
+  int jhi = g[k + 1];
+  while (jhi > j) {                      // largest j in [j, jhi] with cdf[j] <= u2
+    const int mid = (j + jhi + 1) >> 1;
+    if (cdf[mid] <= u2) j = mid; else jhi = mid - 1;
   }
+  double2 c;
   c.x = cdf[j];
+  c.y = cdf[j + 1];
   if (M.method == 1) return __ldg(M.emid + j);
   double e0, e1;
   if (M.edges_uniform) {
