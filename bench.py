@@ -301,7 +301,7 @@ def run_ours(args):
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks,
             "gpu_launches": launches,
         }
-        print(json.dumps(out))
+        emit(out)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -471,11 +471,29 @@ def run_reference(args):
            "ms_per_step": 1e3 * float(np.mean(walls)), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
            "data": "synthetic", "config": workload_config(args, world), "cpu_baseline": last,
            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(out))
+    emit(out)
+
+
+def _protect_stdout():
+    """Libraries (NCCL's version banner, for one) print to stdout; the driver wants exactly one
+    JSON line there.  Point fd 1 at stderr for the run and keep the real stdout for the result."""
+    real = os.fdopen(os.dup(1), "w")
+    sys.stdout.flush()
+    os.dup2(2, 1)
+    return real
+
+
+_REAL_STDOUT = None
+
+
+def emit(obj):
+    _REAL_STDOUT.write(json.dumps(obj) + "\n")
+    _REAL_STDOUT.flush()
 
 
 if __name__ == "__main__":
     a = parse_args()
+    _REAL_STDOUT = _protect_stdout()
     if a.impl == "reference":
         run_reference(a)
     else:

@@ -460,14 +460,9 @@ k_thermal_sample_cta(const DevModel M, const __grid_constant__ pxb_thermal_cells
 // Sampling "pick component c with probability q_c, then invert row c's own CDF" has exactly
 // the distribution of inverting the blended CDF (base.py:471-482), needs no per-cell CDF
 // build, and only touches per-row CDFs + guide tables that are shared by all cells.
-// One thread per photon over tiles; per-tile per-cell setup lives in shared memory.
+// A per-cell prep kernel computes the mixture weights once; the sampler is thread-per-photon.
 #include "tiles.cuh"
 
-constexpr int FAST_THREADS = 256;
-constexpr int FAST_WARPS = FAST_THREADS / 32;
-constexpr int FAST_ITEMS = 4;
-constexpr int FAST_WTILE = 32 * FAST_ITEMS;             // photons per warp tile
-constexpr int FAST_CTILE = FAST_WARPS * FAST_WTILE;
 
 struct FastCell {
   int z1;        // first row
@@ -598,63 +593,6 @@ __device__ __forceinline__ double fast_draw(const DevModel& M, const pxb_thermal
     e1 = __ldg(M.edges + j + 1);
   }
   return e0 + (u2 - c.x) / (c.y - c.x) * (e1 - e0);
-}
-
-// One CTA per tile of 1024 photons (4 per thread, striped).  Shared memory per CTA is kept at
-// 40 KB and residency at 3 CTAs/SM on purpose: the per-row CDFs and guide tables the photons
-// gather from live in L1, and L1 is whatever the 228 KB array has left after shared memory.
-constexpr int FAST_TILE = FAST_THREADS * FAST_ITEMS;
-
-__global__ void __launch_bounds__(FAST_THREADS, 3)
-k_thermal_sample_fast(const DevModel M, const __grid_constant__ pxb_thermal_cells C,
-                      int64_t n_active, const int64_t* __restrict__ idx,
-                      const int64_t* __restrict__ poff, int64_t n_photons,
-                      double* __restrict__ energies, int64_t* __restrict__ list,
-                      unsigned long long* __restrict__ list_count) {
-  __shared__ int64_t s_off[FAST_TILE + 1];
-  __shared__ int64_t s_c[2];
-  __shared__ FastCell s_cell[FAST_TILE];
-  const int64_t p0 = (int64_t)blockIdx.x * FAST_TILE;
-  const int64_t p1 = min(p0 + (int64_t)FAST_TILE, n_photons);
-  TileMap<FAST_TILE> tm;
-  tm.build(poff, n_active, p0, p1, s_off, s_c);
-  for (int q = threadIdx.x; q < tm.nc; q += blockDim.x) {
-    const int64_t k = tm.c0 + q;
-    const FastCell fc = fast_setup(M, C, idx[k]);
-    s_cell[q] = fc;
-    // a declined cell is handed to the general kernel by the tile holding its first photon
-    if (!(fc.meta & 16) && s_off[q] >= p0 && s_off[q + 1] > s_off[q]) {
-      const unsigned long long slot = atomicAdd(list_count, 1ull);
-      list[slot] = k;
-    }
-  }
-  __syncthreads();
-#pragma unroll 1
-  for (int r = 0; r < FAST_ITEMS; ++r) {
-    const int64_t p = p0 + r * FAST_THREADS + threadIdx.x;
-    if (p >= p1) continue;
-    const int64_t k = tm.cell_of(p, s_off);
-    FastCell fc;
-    int64_t first;
-    if (tm.nc > 0) {
-      fc = s_cell[k - tm.c0];
-      first = s_off[k - tm.c0];
-    } else {  // tile spans more cells than photons: set up per photon (never for active lists)
-      fc = fast_setup(M, C, idx[k]);
-      first = __ldg(poff + k);
-      if (!(fc.meta & 16) && p == first) {
-        const unsigned long long slot = atomicAdd(list_count, 1ull);
-        list[slot] = k;
-      }
-    }
-    if (!(fc.meta & 16)) continue;
-    const int64_t i = idx[k];
-    const Philox4 rn = pxb_rand4(C.seed, STREAM_ENERGY, (uint64_t)(C.cell_id0 + i), (uint64_t)(p - first));
-    const StagedRows none{-1, nullptr, nullptr};
-    double e = fast_draw(M, C, fc, i, u53(rn.x, rn.y), u53(rn.z, rn.w), none);
-    if (M.binscale_log) e = exp10(e);
-    st_stream(energies + p, e);
-  }
 }
 
 // ---- mixture sampler with TMA-staged table rows -----------------------------------------
