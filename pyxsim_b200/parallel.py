@@ -75,3 +75,35 @@ def shard_bounds(n, block=4096, r=None, s=None):
     s = size() if s is None else s
     nblocks = (n + block - 1) // block
     return [(b * block, min((b + 1) * block, n)) for b in range(r, nblocks, s)]
+
+
+def gather_arrays(arrays, dst=0):
+    """Variable-length gather of same-length 1-D tensors from every rank to rank ``dst`` in rank
+    order (the optional "final event-list concatenation"; by default lists stay sharded per rank
+    like the reference's per-rank files).  Counts travel with one all-gather, payloads with
+    point-to-point send/recv (NCCL over NVLink on GPUs, gloo in the CPU test).  Returns the
+    concatenated dict on ``dst`` and None elsewhere."""
+    keys = sorted(arrays)
+    n_local = int(arrays[keys[0]].shape[0]) if keys else 0
+    if size() == 1:
+        return dict(arrays)
+    counts = allgather_counts([n_local])[:, 0].tolist()
+    offs = [0]
+    for c in counts:
+        offs.append(offs[-1] + int(c))
+    me = rank()
+    if me == dst:
+        out = {}
+        for k in keys:
+            t = arrays[k]
+            buf = torch.empty(offs[-1], dtype=t.dtype, device=t.device)
+            buf[offs[me]:offs[me + 1]] = t
+            for r in range(size()):
+                if r != dst and counts[r] > 0:
+                    dist.recv(buf[offs[r]:offs[r + 1]], src=r)
+            out[k] = buf
+        return out
+    for k in keys:
+        if n_local > 0:
+            dist.send(arrays[k].contiguous(), dst=dst)
+    return None

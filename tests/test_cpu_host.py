@@ -132,8 +132,16 @@ save_list({tmp!r} + "/ev", DeviceList({{}}, {{"n": r}}, {{"e": np.full(3, float(
 parallel.barrier()
 other = np.load({tmp!r} + f"/ev.{{1 - r:04d}}.npz")
 assert other["data/e"][0] == 1 - r
+# optional concatenation of per-rank shards (variable length) onto rank 0
+mine = {{"e": torch.arange(3 + 2 * r, dtype=torch.float64) + 100 * r, "x": torch.full((3 + 2 * r,), float(r), dtype=torch.float64)}}
+cat = parallel.gather_arrays(mine, dst=0)
+if r == 0:
+    assert cat["e"].tolist() == [0.0, 1.0, 2.0, 100.0, 101.0, 102.0, 103.0, 104.0], cat["e"]
+    assert cat["x"].tolist() == [0.0] * 3 + [1.0] * 5
+else:
+    assert cat is None
 parallel.barrier()
-print("rank", r, "ok")
+sys.stdout.write(f"rank{{r}}ok\n"); sys.stdout.flush()
 """
 
 
@@ -145,4 +153,4 @@ def test_gloo_world_size_2(tmp_path):
            "--master-addr", "127.0.0.1", "--master-port", "29731", str(script)]
     p = subprocess.run(cmd, capture_output=True, text=True, env=env, timeout=240)
     assert p.returncode == 0, p.stdout + p.stderr
-    assert "rank 0 ok" in p.stdout and "rank 1 ok" in p.stdout
+    assert "rank0ok" in p.stdout and "rank1ok" in p.stdout

@@ -166,3 +166,98 @@ def test_large_properties(cuda, n, photons):
     assert float(px.load_list("mem:big2").data["energy"].sum()) == checksum
     for k in ("mem:big", "mem:big2", "mem:big_id", "mem:big_a"):
         px.drop_list(k)
+
+
+def test_sph_particles_igm_model_end_to_end(cuda, oracle):
+    """configs[3]-shaped run at test size: SPH-like particles, density-dependent (kT, nH) table
+    with the CIE fallback, log energy binning, SPH-kernel position smoothing."""
+    n = 40000
+    f = synthetic.particle_beta_model_fields(n, device="cuda", seed=35)
+    Tv, Dv, ebins, c2, m2, v2, cie = synthetic.pion_like_tables(nT=12, nD=7, nbins=600)
+    cie_T, cc, cm, cv = cie
+    cie_prod = px.ThermalSpectralModel(ebins, cie_T, cc, cm, cv, logT=True, binscale="log")
+    prod = px.PionSpectralModel(ebins, Tv, Dv, c2, m2, v2, cie_model=cie_prod, binscale="log")
+    src = px.ArrayDataSource(f, data_type="particles", domain_left_edge=[-1000.0] * 3,
+                             domain_right_edge=[1000.0] * 3)
+    hf = {k: v.cpu().numpy() for k, v in f.items()}
+    ocie = oracle.TableModel(ebins, cie_T, cc, cm, cv, logT=True, binscale="log")
+    orc = oracle.PionModel(ebins, Tv, Dv, c2, m2, v2, ocie, binscale="log")
+    area, texp, z = 2.0e3, 5.0e5, 0.03
+    D_A = px.Cosmology().angular_diameter_distance_mpc(0.0, z)
+    norm = area * texp / (4 * np.pi * (D_A * 3.0856775809623245e24) ** 2 * (1 + z) ** 2)
+    cfg = dict(kT_min=0.00431, kT_max=64.0, Zmet=0.3, spectral_norm=norm)
+    a = dict(kT=hf[TF], em=hf[("gas", "emission_measure")], nH=hf[("gas", "H_nuclei_density")])
+    cut, tot, lam = oracle.thermal_spectra(orc, cfg, a)
+
+    def run(seed_mine, seed_ref):
+        model = px.IGMSourceModel(0.3, 1.4, 600, 0.3, binscale="log", temperature_field=TF,
+                                  spectral_model=prod, prng=seed_mine)
+        n_ph, n_c = px.make_photons("mem:sph_ph", src, z, area, texp, model)
+        lst = px.load_list("mem:sph_ph")
+        assert str(lst.parameters["data_type"]) == "particles"
+        assert abs(n_ph - lam.sum()) < 5 * np.sqrt(lam.sum()) and n_ph > 20000
+        nc, nph, idx, e = oracle.thermal_process_data(orc, cfg, a, np.random.RandomState(seed_ref))
+        out = {"energy": stats.ks_2samp(lst.numpy("energy"), e).pvalue}
+        for kern in ("gaussian", "top_hat"):
+            n_ev = px.project_photons("mem:sph_ph", "mem:sph_ev", [0.3, 0.1, 0.9], [45.0, 30.0],
+                                      absorb_model="wabs", nH=0.01, kernel=kern, prng=seed_mine + 3)
+            ev = px.load_list("mem:sph_ev")
+            g = oracle.gather_active([hf[("gas", f"particle_position_{ax}")] for ax in "xyz"],
+                                     [hf[("gas", f"particle_velocity_{ax}")] for ax in "xyz"],
+                                     hf[("gas", "smoothing_length")], idx, [-1000.0] * 3, [1000.0] * 3,
+                                     [2000.0] * 3, [0.0] * 3, [0.0] * 3, (False,) * 3)
+            d = dict(g, num_photons=nph, energy=e)
+            params = dict(data_type="particles", observer="external", fid_d_a=D_A, fid_redshift=z)
+            ref = oracle.project_photons(d, params, [0.3, 0.1, 0.9], [45.0, 30.0],
+                                         np.random.RandomState(seed_ref + 3),
+                                         absorb_model=oracle.WabsAbsorb(0.01), nH=0.01, kernel=kern)
+            for k in ("xsky", "ysky", "eobs"):
+                out[f"{kern}:{k}"] = stats.ks_2samp(ev.numpy(k), ref[k]).pvalue
+        return out
+
+    H.assert_distributions_agree(run, seeds=((5, 6), (15, 16)))
+
+
+def test_powerlaw_plus_line_with_redshift_end_to_end(cuda, oracle):
+    """configs[4]-shaped run at test size: power-law (alpha field incl. exactly 1 and 2) and a
+    line source on a grid at z = 0.5 through make_photons/project_photons."""
+    n = 24
+    f = synthetic.beta_model_fields(n, v3d_sigma_kms=300.0, device="cuda")
+    N = n ** 3
+    rng = np.random.RandomState(4)
+    alpha = rng.uniform(1.0, 2.5, N)
+    alpha[::5] = 1.0
+    alpha[1::5] = 2.0
+    em = f[("gas", "emission_measure")].cpu().numpy()
+    f[("gas", "alpha")] = torch.from_numpy(alpha).cuda()
+    f[("gas", "xray_lum")] = torch.from_numpy(em * 3.0e-20).cuda()         # keV/s
+    f[("gas", "line_emission")] = torch.from_numpy(em * 4.0e-24).cuda()     # photons/s
+    src = px.ArrayDataSource(f, domain_left_edge=[-1000.0] * 3, domain_right_edge=[1000.0] * 3,
+                             units={("gas", "xray_lum"): "keV/s"})
+    z, area, texp = 0.5, 2.0e3, 1.0e5
+    D_A = px.Cosmology().angular_diameter_distance_mpc(0.0, z)
+    norm = area * texp / (4 * np.pi * (D_A * 3.0856775809623245e24) ** 2 * (1 + z) ** 2)
+    pcfg = dict(e0=1.0, emin=0.5, emax=40.0, spectral_norm=norm, scale_factor=1 / (1 + z))
+    lcfg = dict(e0=3.5, spectral_norm=norm, scale_factor=1 / (1 + z))
+
+    def run(seed_mine, seed_ref):
+        out = {}
+        pl = px.PowerLawSourceModel(1.0, 0.5, 40.0, ("gas", "xray_lum"), ("gas", "alpha"), prng=seed_mine)
+        n_ph, _ = px.make_photons("mem:pl", src, z, area, texp, pl)
+        rlam, _, _ = oracle.powerlaw_lambda(pcfg, em * 3.0e-20, alpha)
+        assert abs(n_ph - rlam.sum()) < 5 * np.sqrt(rlam.sum()) and n_ph > 10000
+        _, _, _, oe = oracle.powerlaw_process_data(pcfg, em * 3.0e-20, alpha, np.random.RandomState(seed_ref))
+        out["pl"] = stats.ks_2samp(px.load_list("mem:pl").numpy("energy"), oe).pvalue
+        ln = px.LineSourceModel(3.5, ("gas", "line_emission"), (1000.0, "km/s"), prng=seed_mine + 1)
+        n_l, _ = px.make_photons("mem:ln", src, z, area, texp, ln)
+        _, _, _, le, F = oracle.line_process_data(lcfg, em * 4.0e-24, 1000.0 * 3.5 / 299792.458,
+                                                  np.random.RandomState(seed_ref + 1))
+        assert abs(n_l - F.sum()) < 5 * np.sqrt(F.sum()) and n_l > 10000
+        out["line"] = stats.ks_2samp(px.load_list("mem:ln").numpy("energy"), le).pvalue
+        n_ev = px.project_photons("mem:pl", "mem:pl_ev", "y", [10.0, 10.0], absorb_model="wabs",
+                                  nH=0.05, prng=seed_mine + 2)
+        assert 0 < n_ev <= n_ph
+        assert float(px.load_list("mem:pl_ev").parameters["redshift"]) == z
+        return out
+
+    H.assert_distributions_agree(run, seeds=((21, 22), (31, 32)))
