@@ -188,6 +188,11 @@ def test_sph_particles_igm_model_end_to_end(cuda, oracle):
     cfg = dict(kT_min=0.00431, kT_max=64.0, Zmet=0.3, spectral_norm=norm)
     a = dict(kT=hf[TF], em=hf[("gas", "emission_measure")], nH=hf[("gas", "H_nuclei_density")])
     cut, tot, lam = oracle.thermal_spectra(orc, cfg, a)
+    boost = 6.0e4 / lam.sum()                     # scale the emission measure to ~6e4 photons
+    f[("gas", "emission_measure")] = f[("gas", "emission_measure")] * boost
+    src.fields[("gas", "emission_measure")] = f[("gas", "emission_measure")]
+    a["em"] = a["em"] * boost
+    lam = lam * boost
 
     def run(seed_mine, seed_ref):
         model = px.IGMSourceModel(0.3, 1.4, 600, 0.3, binscale="log", temperature_field=TF,
@@ -230,27 +235,30 @@ def test_powerlaw_plus_line_with_redshift_end_to_end(cuda, oracle):
     alpha[1::5] = 2.0
     em = f[("gas", "emission_measure")].cpu().numpy()
     f[("gas", "alpha")] = torch.from_numpy(alpha).cuda()
-    f[("gas", "xray_lum")] = torch.from_numpy(em * 3.0e-20).cuda()         # keV/s
-    f[("gas", "line_emission")] = torch.from_numpy(em * 4.0e-24).cuda()     # photons/s
-    src = px.ArrayDataSource(f, domain_left_edge=[-1000.0] * 3, domain_right_edge=[1000.0] * 3,
-                             units={("gas", "xray_lum"): "keV/s"})
     z, area, texp = 0.5, 2.0e3, 1.0e5
     D_A = px.Cosmology().angular_diameter_distance_mpc(0.0, z)
     norm = area * texp / (4 * np.pi * (D_A * 3.0856775809623245e24) ** 2 * (1 + z) ** 2)
     pcfg = dict(e0=1.0, emin=0.5, emax=40.0, spectral_norm=norm, scale_factor=1 / (1 + z))
     lcfg = dict(e0=3.5, spectral_norm=norm, scale_factor=1 / (1 + z))
+    lum0, _, _ = oracle.powerlaw_lambda(pcfg, em, alpha)
+    lum = em * (5.0e4 / lum0.sum())                                # keV/s, ~5e4 photons
+    rate = em * (5.0e4 / (em.sum() * norm / (1 + z)))              # photons/s, ~5e4 photons
+    f[("gas", "xray_lum")] = torch.from_numpy(lum).cuda()
+    f[("gas", "line_emission")] = torch.from_numpy(rate).cuda()
+    src = px.ArrayDataSource(f, domain_left_edge=[-1000.0] * 3, domain_right_edge=[1000.0] * 3,
+                             units={("gas", "xray_lum"): "keV/s"})
 
     def run(seed_mine, seed_ref):
         out = {}
         pl = px.PowerLawSourceModel(1.0, 0.5, 40.0, ("gas", "xray_lum"), ("gas", "alpha"), prng=seed_mine)
         n_ph, _ = px.make_photons("mem:pl", src, z, area, texp, pl)
-        rlam, _, _ = oracle.powerlaw_lambda(pcfg, em * 3.0e-20, alpha)
+        rlam, _, _ = oracle.powerlaw_lambda(pcfg, lum, alpha)
         assert abs(n_ph - rlam.sum()) < 5 * np.sqrt(rlam.sum()) and n_ph > 10000
-        _, _, _, oe = oracle.powerlaw_process_data(pcfg, em * 3.0e-20, alpha, np.random.RandomState(seed_ref))
+        _, _, _, oe = oracle.powerlaw_process_data(pcfg, lum, alpha, np.random.RandomState(seed_ref))
         out["pl"] = stats.ks_2samp(px.load_list("mem:pl").numpy("energy"), oe).pvalue
         ln = px.LineSourceModel(3.5, ("gas", "line_emission"), (1000.0, "km/s"), prng=seed_mine + 1)
         n_l, _ = px.make_photons("mem:ln", src, z, area, texp, ln)
-        _, _, _, le, F = oracle.line_process_data(lcfg, em * 4.0e-24, 1000.0 * 3.5 / 299792.458,
+        _, _, _, le, F = oracle.line_process_data(lcfg, rate, 1000.0 * 3.5 / 299792.458,
                                                   np.random.RandomState(seed_ref + 1))
         assert abs(n_l - F.sum()) < 5 * np.sqrt(F.sum()) and n_l > 10000
         out["line"] = stats.ks_2samp(px.load_list("mem:ln").numpy("energy"), le).pvalue
