@@ -383,3 +383,96 @@ def test_scan_and_compact(cuda):
                                    src.periodicity)
         for k in ("x", "y", "z", "vx", "vy", "vz", "dx"):
             assert np.array_equal(getattr(out, k).cpu().numpy(), g[k]), k
+
+
+def test_energy_distribution_with_variable_elements(cuda, oracle):
+    """Mixture sampler with per-cell abundance fields (metallicity + 2 elements): the component
+    pick has to weight the var tables per cell."""
+    from scipy import stats
+
+    t = H.make_tables(nbins=300, nvar=2)
+    n = 400
+    rng = np.random.RandomState(14)
+    kT = np.exp(rng.uniform(np.log(0.5), np.log(10.0), n))
+    em = 3.0e61 * rng.lognormal(0, 0.5, n)
+    extra = {("gas", "Z"): rng.uniform(0.0, 1.0, n), ("gas", "O"): rng.uniform(0.0, 3.0, n),
+             ("gas", "Fe"): rng.uniform(0.0, 3.0, n)}
+    src = H.cells_source(kT, em, extra=extra)
+    cfg = dict(kT_min=0.025, kT_max=64.0, Zmet="Z", Zconvert=1.0, z_by_xh=False, spectral_norm=1e-43,
+               var_elem=[("O", 1.0, False), ("Fe", 1.0, False)])
+    a = dict(kT=kT, em=em, Z=extra[("gas", "Z")], O=extra[("gas", "O")], Fe=extra[("gas", "Fe")])
+    om = H.oracle_model(oracle, t)
+
+    def run(seed_mine, seed_ref):
+        model = px.ThermalSourceModel(H.product_model(t), 0.1, 10.0, 300, ("gas", "Z"),
+                                      var_elem={"O": ("gas", "O"), "Fe": ("gas", "Fe")},
+                                      temperature_field=TF, prng=seed_mine)
+        model.setup_model("photons", src, 0.0)
+        out = model.generate_chunk(_chunk(src), 1e-43)
+        e = out.energy.cpu().numpy()
+        nc, nph, idx, oe = oracle.thermal_process_data(om, cfg, a, np.random.RandomState(seed_ref))
+        assert abs(e.size - oe.size) < 6 * np.sqrt(oe.size) and e.size > 100000
+        # hard and soft halves of the cell list separately (different mixture weights)
+        off = np.concatenate([[0], np.cumsum(out.nph.cpu().numpy())])
+        ooff = np.concatenate([[0], np.cumsum(nph)])
+        mi, oi = out.idx.cpu().numpy(), idx
+        hot_m = np.concatenate([e[off[k]:off[k + 1]] for k in np.where(kT[mi] > 3.0)[0]])
+        hot_o = np.concatenate([oe[ooff[k]:ooff[k + 1]] for k in np.where(kT[oi] > 3.0)[0]])
+        return {"all": stats.ks_2samp(e, oe).pvalue, "hot": stats.ks_2samp(hot_m, hot_o).pvalue}
+
+    H.assert_distributions_agree(run, seeds=((3, 4), (13, 14)))
+
+
+def test_large_nbins_and_single_bright_cell(cuda, oracle):
+    """nbins = 20000 (the reference's own test binning, tests/test_beta_model.py) does not fit
+    the staged rows: the sampler gathers from L2 instead, and the general kernel holds a 160 KB
+    CDF.  One very bright cell exercises a tile map with thousands of tiles per cell."""
+    from scipy import stats
+
+    t = H.make_tables(nbins=20000)
+    kT = np.array([4.0, 0.02, 7.5])           # the middle cell extrapolates -> general kernel
+    em = np.array([6.0e64, 2.0e67, 1.0e62])
+    src = H.cells_source(kT, em)
+    model = px.ThermalSourceModel(H.product_model(t), 0.1, 10.0, 20000, 0.3, temperature_field=TF,
+                                  prng=9, kT_min=0.001)
+    model.setup_model("photons", src, 0.0)
+    out = model.generate_chunk(_chunk(src), 1e-43)
+    nph = out.nph.cpu().numpy()
+    assert nph[0] > 2_000_000
+    cfg = dict(kT_min=0.001, kT_max=64.0, Zmet=0.3, spectral_norm=1e-43)
+    cut, tot, lam = oracle.thermal_spectra(H.oracle_model(oracle, t), cfg, dict(kT=kT, em=em))
+    assert np.all(np.abs(nph - lam[out.idx.cpu().numpy()]) < 6 * np.sqrt(lam[out.idx.cpu().numpy()]) + 5)
+    e = out.energy.cpu().numpy()
+    off = np.concatenate([[0], np.cumsum(nph)])
+    for k, i in enumerate(out.idx.cpu().numpy()):
+        mine = e[off[k]:off[k + 1]]
+        if mine.size < 2000:
+            continue
+        h, _ = np.histogram(mine, bins=t["ebins"])
+        p = tot[i] / tot[i].sum()
+        grp = np.minimum((np.cumsum(p) * 40).astype(int), 39)
+        ho = np.bincount(grp, weights=h, minlength=40)
+        he = np.bincount(grp, weights=p * mine.size, minlength=40)
+        ok = he > 10
+        chi2 = ((ho[ok] - he[ok]) ** 2 / he[ok]).sum()
+        assert stats.chi2.sf(chi2, ok.sum() - 1) > 1e-3, (i, chi2)
+
+
+def test_empty_and_tiny_inputs(cuda):
+    t = H.make_tables(nbins=128)
+    sm = H.product_model(t)
+    # no emission at all -> (0, 0) and an empty list that projects to zero events
+    src = H.cells_source(np.full(50, 5.0), np.zeros(50))
+    model = px.ThermalSourceModel(sm, 0.1, 10.0, 128, 0.3, temperature_field=TF, prng=1)
+    assert px.make_photons("mem:empty", src, 0.05, 1.0, 1.0, model) == (0, 0)
+    assert px.load_list("mem:empty").data["energy"].numel() == 0
+    assert px.project_photons("mem:empty", "mem:empty_ev", "z", [0.0, 0.0]) == 0
+    # every cell cut by kT_min/kT_max
+    src2 = H.cells_source(np.full(10, 1000.0), np.full(10, 1e65))
+    assert px.make_photons("mem:cut", src2, 0.05, 1e3, 1e5, model) == (0, 0)
+    # one cell, a handful of photons
+    src3 = H.cells_source(np.array([3.0]), np.array([2.0e62]))
+    model3 = px.ThermalSourceModel(sm, 0.1, 10.0, 128, 0.3, temperature_field=TF, prng=4)
+    n_ph, n_c = px.make_photons("mem:one", src3, 0.05, 1.0e3, 1.0e5, model3)
+    assert n_c == 1 and n_ph == px.load_list("mem:one").data["energy"].numel() > 0
+    assert px.project_photons("mem:one", "mem:one_ev", [0, 1.0, 1.0], [0.0, 0.0], no_shifting=True) == n_ph
