@@ -233,6 +233,13 @@ int pxb_line_sample(const pxb_line_cells* cells, int64_t n_active, const int64_t
                     const int64_t* nph, const int64_t* poff, int64_t n_photons,
                     double* energies, void* stream);
 
+/* Diagnostics: `count` independent draws of the device's Poisson / binomial samplers (the
+ * counter-based replacements of prng.poisson, base.py:466, and of the per-photon component
+ * choice); element i uses the Philox stream of "cell" i. */
+int pxb_rng_poisson(double lam, uint64_t seed, int64_t count, int64_t* out, void* stream);
+int pxb_rng_binomial(int64_t n, double p, uint64_t seed, int64_t count, int64_t* out,
+                     void* stream);
+
 /* ------------------------------------------------------------------------------------
  * Projection
  * ---------------------------------------------------------------------------------- */

@@ -143,6 +143,8 @@ SIGNATURES = {
     "pxb_line_counts": (C.c_int, [_P(LineCells), c_void_p, c_void_p, c_void_p]),
     "pxb_line_sample": (C.c_int, [_P(LineCells), C.c_int64, c_void_p, c_void_p, c_void_p,
                                   C.c_int64, c_void_p, c_void_p]),
+    "pxb_rng_poisson": (C.c_int, [C.c_double, C.c_uint64, C.c_int64, c_void_p, c_void_p]),
+    "pxb_rng_binomial": (C.c_int, [C.c_int64, C.c_double, C.c_uint64, C.c_int64, c_void_p, c_void_p]),
     "pxb_project_workspace_bytes": (C.c_int, [C.c_int64, C.c_int64, _P(C.c_int64)]),
     "pxb_project": (C.c_int, [_P(PhotonList), _P(ProjectParams), c_void_p, c_void_p, c_void_p,
                               c_void_p, c_void_p, c_void_p, c_void_p, C.c_int64, c_void_p]),

@@ -61,6 +61,7 @@ enum PxbStream : uint32_t {
   STREAM_PROJ_D = 6,   // internal absorption
   STREAM_POWERLAW = 7,
   STREAM_LINE = 8,
+  STREAM_SPLIT = 9,    // multinomial split of a cell's photons over its table rows
 };
 
 struct Philox4 {
@@ -164,6 +165,54 @@ __device__ inline int64_t poisson_draw(double lam, CellStream& rs) {
       return (int64_t)kf;
   }
   return (int64_t)floor(lam + 0.5);  // unreachable in practice
+}
+
+// Binomial(n, p): inversion (BINV, Kachitvichyanukul & Schmeiser 1988) for n*min(p,1-p) < 10,
+// transformed rejection BTRS (Hoermann 1993, "The generation of binomial random variates")
+// above.  Exact up to floating point; validated against scipy.stats.binom in the tests.
+__device__ inline int64_t binomial_draw(int64_t n, double p, CellStream& rs) {
+  if (n <= 0 || !(p > 0.0)) return 0;
+  if (p >= 1.0) return n;
+  const bool flip = p > 0.5;
+  const double pp = flip ? 1.0 - p : p;
+  const double nd = (double)n;
+  int64_t k = 0;
+  if (nd * pp < 10.0) {
+    const double q = 1.0 - pp, sr = pp / q, a = (nd + 1.0) * sr;
+    const double r0 = exp(nd * log1p(-pp));
+    for (int attempt = 0; attempt < 64; ++attempt) {
+      double u = rs.next(), r = r0;
+      int64_t x = 0;
+      while (u > r && x <= n) {
+        u -= r;
+        ++x;
+        r *= (a / (double)x - sr);
+      }
+      if (x <= n) { k = x; break; }
+    }
+  } else {
+    const double spq = sqrt(nd * pp * (1.0 - pp));
+    const double b = 1.15 + 2.53 * spq;
+    const double a = -0.0873 + 0.0248 * b + 0.01 * pp;
+    const double c = nd * pp + 0.5;
+    const double vr = 0.92 - 4.2 / b;
+    const double alpha = (2.83 + 5.1 / b) * spq;
+    const double lpq = log(pp / (1.0 - pp));
+    const double m = floor((nd + 1.0) * pp);
+    const double h = lgamma(m + 1.0) + lgamma(nd - m + 1.0);
+    k = (int64_t)floor(nd * pp + 0.5);
+    for (int it = 0; it < 1000; ++it) {
+      const double u = rs.next() - 0.5;
+      double v = rs.next();
+      const double us = 0.5 - fabs(u);
+      const double kf = floor((2.0 * a / us + b) * u + c);
+      if (us >= 0.07 && v <= vr) { k = (int64_t)kf; break; }
+      if (kf < 0.0 || kf > nd) continue;
+      v = log(v * alpha / (a / (us * us) + b));
+      if (v <= h - lgamma(kf + 1.0) - lgamma(nd - kf + 1.0) + (kf - m) * lpq) { k = (int64_t)kf; break; }
+    }
+  }
+  return flip ? n - k : k;
 }
 
 // ---------------------------------------------------------------------------------------

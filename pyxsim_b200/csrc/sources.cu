@@ -181,3 +181,41 @@ extern "C" int pxb_line_sample(const pxb_line_cells* cells, int64_t n_active, co
   PXB_LAUNCH_CHECK();
   return PXB_OK;
 }
+
+// ---------------------------------------------------------------------------------------
+// diagnostics: the discrete samplers on their own (statistical tests against scipy)
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_rng_poisson(double lam, uint64_t seed, int64_t count, int64_t* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  CellStream rs(seed, STREAM_POISSON, (uint64_t)i);
+  out[i] = poisson_draw(lam, rs);
+}
+
+__global__ void __launch_bounds__(256)
+k_rng_binomial(int64_t n, double p, uint64_t seed, int64_t count, int64_t* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  CellStream rs(seed, STREAM_SPLIT, (uint64_t)i);
+  out[i] = binomial_draw(n, p, rs);
+}
+
+extern "C" int pxb_rng_poisson(double lam, uint64_t seed, int64_t count, int64_t* out, void* stream) {
+  PXB_REQUIRE(count >= 0, "bad count");
+  if (count == 0) return PXB_OK;
+  PXB_REQUIRE(out, "NULL argument");
+  k_rng_poisson<<<(unsigned)((count + 255) / 256), 256, 0, (cudaStream_t)stream>>>(lam, seed, count, out);
+  PXB_LAUNCH_CHECK();
+  return PXB_OK;
+}
+
+extern "C" int pxb_rng_binomial(int64_t n, double p, uint64_t seed, int64_t count, int64_t* out,
+                                void* stream) {
+  PXB_REQUIRE(count >= 0 && n >= 0, "bad count");
+  if (count == 0) return PXB_OK;
+  PXB_REQUIRE(out, "NULL argument");
+  k_rng_binomial<<<(unsigned)((count + 255) / 256), 256, 0, (cudaStream_t)stream>>>(n, p, seed, count, out);
+  PXB_LAUNCH_CHECK();
+  return PXB_OK;
+}

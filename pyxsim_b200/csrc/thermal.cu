@@ -466,8 +466,13 @@ k_thermal_sample_cta(const DevModel M, const __grid_constant__ pxb_thermal_cells
 
 struct FastCell {
   int z1;        // first row
-  int meta;      // bits 0-2: number of rows, bit 3: fallback table, bit 4: eligible
-  double cum[3]; // cumulative row probabilities (last is implicitly 1)
+  int meta;      // bits 0-2: number of rows, bit 3: fallback table, bit 4: eligible,
+                 // bit 5: split mode (cnt valid) instead of probability mode (cum valid)
+  union {
+    double cum[3];     // cumulative row probabilities (last is implicitly 1)
+    long long cnt[3];  // split mode: cumulative photon counts of the components
+                       // (row0,cosmic), (row0,metal), (row1,cosmic) [, (row1,metal) = rest]
+  };
 };
 
 __device__ __forceinline__ int fast_row(const DevTable* t, int z1, int nr, int r) {
@@ -475,8 +480,13 @@ __device__ __forceinline__ int fast_row(const DevTable* t, int z1, int nr, int r
   return z1 + ((r & 1) ? t->nx : 0) + ((r >> 1) ? 1 : 0);   // order of cell_mix: z1, z2, z3, z4
 }
 
+// N = photons of the cell.  Plain 1-D tables without variable elements have only four mixture
+// components; for those the cell's N photons are split over the components ONCE here by
+// sequential binomial draws (a multinomial draw -- the same joint distribution as letting every
+// photon pick its component independently), so the per-photon work is just the CDF inversion
+// and one Philox block serves two photons.
 __device__ __forceinline__ FastCell fast_setup(const DevModel& M, const pxb_thermal_cells& C,
-                                            int64_t i) {
+                                            int64_t i, int64_t N) {
   FastCell fc;
   const double kT = C.kT[i];
   const double nH = C.nH ? C.nH[i] : 0.0;
@@ -515,8 +525,35 @@ __device__ __forceinline__ FastCell fast_setup(const DevModel& M, const pxb_ther
   }
   fc.z1 = mx.row[0];
   fc.meta = mx.nr | ((t == &M.fb) ? 8 : 0) | (ok ? 16 : 0);
+  if (ok && C.nvar == 0 && mx.nr == 2 && N > 0) {
+    double q[4];
+    q[0] = mx.w[0] * __ldg(t->rs_c + mx.row[0]);
+    q[1] = mx.w[0] * Z * __ldg(t->rs_m + mx.row[0]);
+    q[2] = mx.w[1] * __ldg(t->rs_c + mx.row[1]);
+    q[3] = mx.w[1] * Z * __ldg(t->rs_m + mx.row[1]);
+    CellStream rs(C.seed, STREAM_SPLIT, (uint64_t)(C.cell_id0 + i));
+    double rest = q[0] + q[1] + q[2] + q[3];
+    int64_t left = N, acc = 0;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const double pc = rest > 0.0 ? fmin(fmax(q[c] / rest, 0.0), 1.0) : 0.0;
+      const int64_t nk = binomial_draw(left, pc, rs);
+      left -= nk;
+      acc += nk;
+      rest -= q[c];
+      fc.cnt[c] = acc;
+    }
+    if (!(q[3] > 0.0) && left > 0) {
+      // rounding left photons for an empty last component: give them to the last non-empty one
+      int last_ne = q[2] > 0.0 ? 2 : (q[1] > 0.0 ? 1 : 0);
+      for (int c = last_ne; c < 3; ++c) fc.cnt[c] += left;
+    }
+    fc.meta |= 32;
+  }
   return fc;
 }
+
+// invert one table row's CDF at u2 (staged rows gather from shared memory)
 
 // Rows staged in shared memory by the persistent sampler: CDFs and guides of rows (tag, tag+1)
 // of the cosmic and metal tables of the primary table (slot = 2*table + (row - tag)).
@@ -525,6 +562,9 @@ struct StagedRows {
   const double* cdf;       // [4][cdf_stride]
   const uint16_t* guide;   // [4][guide_stride]
 };
+
+__device__ __forceinline__ double invert_row(const DevModel& M, const DevTable* t, int tab, int row,
+                                             double u2, const StagedRows& S, bool prim);
 
 __device__ __forceinline__ double fast_draw(const DevModel& M, const pxb_thermal_cells& C,
                                             const FastCell& fc, int64_t i, double u1, double u2,
@@ -560,13 +600,17 @@ __device__ __forceinline__ double fast_draw(const DevModel& M, const pxb_thermal
     }
     tab = max(chosen, 0);
   }
-  // invert the row CDF: guide table then a short forward walk over (cdf[j], cdf[j+1]) pairs
+  return invert_row(M, t, tab, row, u2, S, !(fc.meta & 8));
+}
+
+__device__ __forceinline__ double invert_row(const DevModel& M, const DevTable* t, int tab, int row,
+                                             double u2, const StagedRows& S, bool prim) {
   const int nb = t->nbins;
   const size_t ro = (size_t)tab * t->nrows + row;
   const double* cdf = t->rowcdf + ro * (size_t)t->cdf_stride;
   const uint16_t* g = t->guide + ro * (size_t)t->guide_stride;
   const unsigned dr = (unsigned)(row - S.tag);
-  if (S.tag >= 0 && tab < 2 && dr < 2u && !(fc.meta & 8)) {   // staged: shared-memory gathers
+  if (S.tag >= 0 && tab < 2 && dr < 2u && prim) {   // staged: shared-memory gathers
     const int slot = tab * 2 + (int)dr;
     cdf = S.cdf + (size_t)slot * t->cdf_stride;
     g = S.guide + (size_t)slot * t->guide_stride;
@@ -653,9 +697,9 @@ k_thermal_cellprep(const DevModel M, const __grid_constant__ pxb_thermal_cells C
                    unsigned long long* __restrict__ list_count) {
   const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= n_active) return;
-  const FastCell fc = fast_setup(M, C, idx[k]);
-  fcs[k] = fc;
   const int64_t a = poff[k], b = poff[k + 1];
+  const FastCell fc = fast_setup(M, C, idx[k], b - a);
+  fcs[k] = fc;
   if (!(fc.meta & 16) && b > a) {
     const unsigned long long slot = atomicAdd(list_count, 1ull);
     list[slot] = k;
@@ -729,38 +773,73 @@ k_thermal_sample_staged(const DevModel M, const __grid_constant__ pxb_thermal_ce
       __syncwarp();
       for (int q = lane; q <= nc && nc > 0; q += 32) s_off[q] = __ldg(poff + c0 + q);
       __syncwarp();
-#pragma unroll 2
-      for (int r = 0; r < STG_WTILE / 32; ++r) {
-        const int64_t p = p0 + r * 32 + lane;
-        if (p >= p1) continue;
-        int64_t first, k;
-        if (nc > 0) {
-          int rel = 0;
-          if (nc > 1) {
+      // every lane handles PAIRS of adjacent photons: in split mode photons 2m and 2m+1 of a
+      // cell share one Philox block, and the pair leaves as one 16-byte store
+#pragma unroll 1
+      for (int r = 0; r < STG_WTILE / 64; ++r) {
+        const int64_t pa = p0 + r * 64 + 2 * lane;
+        if (pa >= p1) continue;
+        Philox4 blk{0u, 0u, 0u, 0u};
+        uint64_t blk_cell = ~0ull, blk_idx = ~0ull;
+        double e2[2];
+        bool have[2] = {false, false};
 #pragma unroll
-            for (int step = STG_WTILE; step > 0; step >>= 1) {
-              const int q = rel + step;
-              if (q < nc && s_off[q] <= p) rel = q;
+        for (int h = 0; h < 2; ++h) {
+          const int64_t p = pa + h;
+          if (p >= p1) continue;
+          int64_t first, k;
+          if (nc > 0) {
+            int rel = 0;
+            if (nc > 1) {
+#pragma unroll
+              for (int step = STG_WTILE; step > 0; step >>= 1) {
+                const int q = rel + step;
+                if (q < nc && s_off[q] <= p) rel = q;
+              }
             }
+            k = c0 + rel;
+            first = s_off[rel];
+          } else {  // more cells than photons in the tile (never for active lists)
+            int64_t lo = c0, hi = c1 + 1;
+            while (hi - lo > 1) {
+              const int64_t mid = (lo + hi) >> 1;
+              if (__ldg(poff + mid) <= p) lo = mid; else hi = mid;
+            }
+            k = lo;
+            first = __ldg(poff + k);
           }
-          k = c0 + rel;
-          first = s_off[rel];
-        } else {  // more cells than photons in the tile (never for active lists)
-          int64_t lo = c0, hi = c1 + 1;
-          while (hi - lo > 1) {
-            const int64_t mid = (lo + hi) >> 1;
-            if (__ldg(poff + mid) <= p) lo = mid; else hi = mid;
+          const FastCell fc = fcs[k];
+          if (!(fc.meta & 16)) continue;
+          const int64_t i = __ldg(idx + k);
+          const uint64_t gid = (uint64_t)(C.cell_id0 + i);
+          const uint64_t d = (uint64_t)(p - first);
+          double e;
+          if (fc.meta & 32) {
+            if (!(blk_cell == gid && blk_idx == (d >> 1))) {
+              blk = pxb_rand4(C.seed, STREAM_ENERGY, gid, d >> 1);
+              blk_cell = gid;
+              blk_idx = d >> 1;
+            }
+            const double u2 = (d & 1) ? u53(blk.z, blk.w) : u53(blk.x, blk.y);
+            const long long dd = (long long)d;
+            const int comp = (dd >= fc.cnt[0]) + (dd >= fc.cnt[1]) + (dd >= fc.cnt[2]);
+            const bool prim = !(fc.meta & 8);
+            e = invert_row(M, prim ? &M.prim : &M.fb, comp & 1, fc.z1 + (comp >> 1), u2, S, prim);
+          } else {
+            const Philox4 rn = pxb_rand4(C.seed, STREAM_ENERGY, gid, d);
+            e = fast_draw(M, C, fc, i, u53(rn.x, rn.y), u53(rn.z, rn.w), S);
           }
-          k = lo;
-          first = __ldg(poff + k);
+          if (M.binscale_log) e = exp10(e);
+          e2[h] = e;
+          have[h] = true;
         }
-        const FastCell fc = fcs[k];
-        if (!(fc.meta & 16)) continue;
-        const int64_t i = __ldg(idx + k);
-        const Philox4 rn = pxb_rand4(C.seed, STREAM_ENERGY, (uint64_t)(C.cell_id0 + i), (uint64_t)(p - first));
-        double e = fast_draw(M, C, fc, i, u53(rn.x, rn.y), u53(rn.z, rn.w), S);
-        if (M.binscale_log) e = exp10(e);
-        st_stream(energies + p, e);
+        if (have[0] && have[1]) {
+          asm volatile("st.global.L1::no_allocate.v2.f64 [%0], {%1, %2};" ::"l"(energies + pa),
+                       "d"(e2[0]), "d"(e2[1]));
+        } else {
+          if (have[0]) st_stream(energies + pa, e2[0]);
+          if (have[1]) st_stream(energies + pa + 1, e2[1]);
+        }
       }
     }
   }
@@ -844,6 +923,7 @@ extern "C" int pxb_thermal_sample(const pxb_model* model, const pxb_thermal_cell
   if (rc) return rc;
   if (n_active == 0 || n_photons == 0) return PXB_OK;
   PXB_REQUIRE(idx && nph && poff && energies, "NULL argument");
+  PXB_REQUIRE(((uintptr_t)energies & 15) == 0, "energies must be 16-byte aligned");
   cudaStream_t st = (cudaStream_t)stream;
   const DevModel& D = model->dev;
   const size_t smem = ((size_t)D.nbins + 1 + PXB_MAX_VAR + SAMPLE_THREADS / 32) * sizeof(double);

@@ -476,3 +476,40 @@ def test_empty_and_tiny_inputs(cuda):
     n_ph, n_c = px.make_photons("mem:one", src3, 0.05, 1.0e3, 1.0e5, model3)
     assert n_c == 1 and n_ph == px.load_list("mem:one").data["energy"].numel() > 0
     assert px.project_photons("mem:one", "mem:one_ev", [0, 1.0, 1.0], [0.0, 0.0], no_shifting=True) == n_ph
+
+
+@pytest.mark.parametrize("n,p", [(1, 0.3), (7, 0.5), (40, 0.01), (1000, 0.004), (1000, 0.02), (50, 0.37),
+                                 (100000, 0.3), (100000, 0.9993), (3000000, 0.5), (12, 0.97),
+                                 (10**9, 1e-9), (10**9, 0.25)])
+def test_binomial_sampler(cuda, n, p):
+    """The device binomial sampler behind the multinomial split of a cell's photons over its
+    table rows: mean/variance and a chi^2 on the pmf against scipy.stats.binom."""
+    import ctypes as C
+
+    from scipy import stats
+
+    from pyxsim_b200 import _lib
+    from pyxsim_b200.device import empty, ptr, stream_ptr
+
+    count = 400000
+    out = empty(count, torch.int64)
+    _lib.call("pxb_rng_binomial", n, C.c_double(p), C.c_uint64(99), count, ptr(out), stream_ptr())
+    k = out.cpu().numpy()
+    assert k.min() >= 0 and k.max() <= n
+    mu, var = n * p, n * p * (1 - p)
+    assert abs(k.mean() - mu) < 5 * np.sqrt(var / count) + 1e-12
+    assert abs(k.var() - var) < 8 * var * np.sqrt(2.0 / count) + 6 * np.sqrt(var / count) + 1e-12
+    lo = int(stats.binom.ppf(1e-5, n, p))
+    hi = int(stats.binom.ppf(1 - 1e-5, n, p)) + 1
+    if hi - lo < 5000:
+        vals = np.arange(lo, hi + 1)
+        obs = np.array([(k == v).sum() for v in vals], dtype=float)
+        exp = count * stats.binom.pmf(vals, n, p)
+        keep = exp > 20
+        o, e = obs[keep], exp[keep]
+        ro, re = count - o.sum(), count - e.sum()
+        if re > 20:
+            o, e = np.append(o, ro), np.append(e, re)
+        if o.size > 1:
+            chi2 = ((o - e) ** 2 / e).sum()
+            assert stats.chi2.sf(chi2, o.size - 1) > 1e-3, (chi2, o.size)
