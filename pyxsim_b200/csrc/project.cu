@@ -136,14 +136,25 @@ k_pixel_to_cel(int64_t n, double* __restrict__ xs, double* __restrict__ ys, doub
 // ---------------------------------------------------------------------------------------
 constexpr int PROJ_WTILE_C = 256;   // photons per warp tile (== PROJ_WTILE below)
 
+// what the scatter step needs of a cell, one 32-byte sector per cell
+struct __align__(32) CellGeom {
+  double cx;  // centre . x_hat
+  double cy;  // centre . y_hat
+  double cz;  // centre . z_hat (the reference's `los`; also the 3rd all-sky coordinate)
+  double w;   // scatter width: dx (cells), dx/2 (particles, external observer)
+};
+
 struct CellDerived {
-  double* shift;  // Doppler factor (1 when no_shifting)
-  double* cx;     // centre . x_hat
-  double* cy;     // centre . y_hat
-  double* cz;     // centre . z_hat (the reference's `los`; also the 3rd all-sky coordinate)
-  double* w;      // scatter width: dx (cells), dx/2 (particles, external observer)
+  double* shift;       // Doppler factor (1 when no_shifting)
+  CellGeom* geom;
   int64_t* tile_cell;  // [n_wtiles + 1]: cell holding the first photon of every warp tile
 };
+
+__device__ __forceinline__ CellGeom ld_geom(const CellGeom* p) {
+  const double2* q = reinterpret_cast<const double2*>(p);
+  const double2 a = __ldg(q), b = __ldg(q + 1);
+  return CellGeom{a.x, a.y, b.x, b.y};
+}
 
 __global__ void __launch_bounds__(256)
 k_project_cells(const __grid_constant__ pxb_photon_list L,
@@ -167,12 +178,14 @@ k_project_cells(const __grid_constant__ pxb_photon_list L,
     shift = doppler_factor(vn * ss, v2 * (ss * ss));
   }
   D.shift[c] = shift;
-  D.cx[c] = x * P.x_hat[0] + y * P.x_hat[1] + z * P.x_hat[2];
-  D.cy[c] = x * P.y_hat[0] + y * P.y_hat[1] + z * P.y_hat[2];
-  D.cz[c] = x * P.z_hat[0] + y * P.z_hat[1] + z * P.z_hat[2];
   double w = L.dx ? L.dx[c] : 0.0;
   if (P.observer == 0 && P.data_type == 1) w *= 0.5;  // photon_list.py:733-734
-  D.w[c] = w;
+  CellGeom g;
+  g.cx = x * P.x_hat[0] + y * P.x_hat[1] + z * P.x_hat[2];
+  g.cy = x * P.y_hat[0] + y * P.y_hat[1] + z * P.y_hat[2];
+  g.cz = x * P.z_hat[0] + y * P.z_hat[1] + z * P.z_hat[2];
+  g.w = w;
+  D.geom[c] = g;
   // every warp tile that starts inside this cell's photon range starts in this cell
   const int64_t a = L.poff[c], b = L.poff[c + 1];
   for (int64_t t = (a + PROJ_WTILE_C - 1) / PROJ_WTILE_C; t * PROJ_WTILE_C < b; ++t) D.tile_cell[t] = c;
@@ -236,7 +249,7 @@ __device__ __forceinline__ int64_t warp_lookback(unsigned long long* status, int
     const int first = inc ? (__ffs(inc) - 1) : 32;           // nearest tile with an inclusive prefix
     const unsigned need = first >= 31 ? 0xffffffffu : ((2u << first) - 1u);
     if (emp & need) {                                        // a needed predecessor is not ready
-      __nanosleep(200);
+      __nanosleep(1000);
       continue;
     }
     int64_t v = (lane <= first) ? (int64_t)(sv & ~ST_MASK) : 0;
@@ -298,6 +311,11 @@ __device__ __forceinline__ bool survives(double u, double tau) {
     if (u < s3) return true;
     const double t2 = tau * tau;
     if (u >= s3 + t2 * t2 * (1.0 / 24.0)) return false;
+  } else if (tau < 80.0) {
+    // single-precision estimate with a safety margin decides all but ~1e-5 of the cases
+    const double p32 = (double)__expf(-(float)tau);
+    if (u < p32 * (1.0 - 1.0e-5)) return true;
+    if (u > p32 * (1.0 + 1.0e-5)) return false;
   }
   return u < exp(-tau);
 }
@@ -318,9 +336,9 @@ __device__ __forceinline__ void scatter_external(const pxb_project_params& P, co
                                                  const SkyConst& K, int64_t c, uint64_t cell_key,
                                                  uint64_t draw, double& xs_out, double& ys_out,
                                                  double& los_out) {
-  const double w = __ldg(D.w + c);
-  const double cx = __ldg(D.cx + c), cy = __ldg(D.cy + c);
-  los_out = __ldg(D.cz + c);  // from the unscattered centre (sky_functions.pyx:124,143)
+  const CellGeom g = ld_geom(D.geom + c);
+  const double w = g.w, cx = g.cx, cy = g.cy;
+  los_out = g.cz;  // from the unscattered centre (sky_functions.pyx:124,143)
   const Philox4 rb = pxb_rand4(P.seed, STREAM_PROJ_B, cell_key, draw);
   double ox, oy;  // offsets in the sky plane in units of w
   if (P.data_type == 0) {
@@ -370,8 +388,8 @@ __device__ __forceinline__ void scatter_external(const pxb_project_params& P, co
 __device__ __forceinline__ void scatter_allsky(const pxb_project_params& P, const CellDerived& D,
                                                int64_t c, uint64_t cell_key, uint64_t draw,
                                                double& lon_out, double& lat_out, double& los_out) {
-  const double w = __ldg(D.w + c);
-  const double cx = __ldg(D.cx + c), cy = __ldg(D.cy + c), cz = __ldg(D.cz + c);
+  const CellGeom g = ld_geom(D.geom + c);
+  const double w = g.w, cx = g.cx, cy = g.cy, cz = g.cz;
   double o0, o1, o2;
   const Philox4 rb = pxb_rand4(P.seed, STREAM_PROJ_B, cell_key, draw);
   if (P.data_type == 0) {
@@ -411,7 +429,7 @@ __device__ __forceinline__ void scatter_allsky(const pxb_project_params& P, cons
 
 // absorption decision of one photon (phase 1); kept out of line so the rolled item loop stays
 // small
-__device__ __noinline__ bool absorb_decision(const pxb_project_params& P, int64_t c, int64_t draw,
+__device__ __forceinline__ bool absorb_decision(const pxb_project_params& P, int64_t c, int64_t draw,
                                              double en) {
   const uint64_t cell_key = (uint64_t)(P.cell_id0 + c);
   bool det = true;
@@ -460,7 +478,9 @@ k_project_photons(const __grid_constant__ pxb_photon_list L,
     __syncthreads();
     const int64_t ctile = s_ticket;
     if (ctile >= n_ctiles) return;
-    const int64_t wtile = ctile * PROJ_WARPS + wid;
+    // the scheduler favours high warp ids, so those take the EARLIER tiles of the ticket: the
+    // warps that finish phase 1 last then own the tiles whose predecessors are already done
+    const int64_t wtile = ctile * PROJ_WARPS + (PROJ_WARPS - 1 - wid);
     if (wtile >= n_wtiles) continue;   // past the end: nobody waits on this warp
     const int64_t p0 = wtile * PROJ_WTILE;
     const int64_t p1 = min(p0 + (int64_t)PROJ_WTILE, L.n_photons);
@@ -663,11 +683,8 @@ extern "C" int pxb_project(const pxb_photon_list* L, const pxb_project_params* P
   PXB_REQUIRE(n_ctiles < (1LL << 32) - 65536, "too many photons for one projection call");
   char* ws = (char*)workspace;
   CellDerived D;
-  D.shift = (double*)(ws + lay.off_cells);
-  D.cx = D.shift + L->n_cells;
-  D.cy = D.cx + L->n_cells;
-  D.cz = D.cy + L->n_cells;
-  D.w = D.cz + L->n_cells;
+  D.geom = (CellGeom*)(ws + lay.off_cells);                 // 32-byte records first (alignment)
+  D.shift = (double*)(ws + lay.off_cells + 4 * L->n_cells * (int64_t)sizeof(double));
   D.tile_cell = (int64_t*)(ws + lay.off_tilecell);
   ProjWork W;
   W.status = (unsigned long long*)(ws + lay.off_status);
