@@ -15,6 +15,8 @@
 // so the event list keeps the photon-list order like the reference's cursor `k`
 // (sky_functions.pyx:87-105) and is bit-reproducible.
 #include "tiles.cuh"
+#include <stdlib.h>
+#include <string.h>
 
 constexpr double PXB_C_KMS = 299792.458;          // clight in km/s (utils.py:10-11)
 constexpr double PXB_PI = 3.14159265358979323846;
@@ -583,6 +585,164 @@ k_project_photons(const __grid_constant__ pxb_photon_list L,
   }
 }
 
+// ---------------------------------------------------------------------------------------
+// two-pass variant: detect (mask + per-tile counts) -> scan -> emit
+// ---------------------------------------------------------------------------------------
+// Same arithmetic and the same event list as the fused kernel, organised without any
+// inter-tile dependency: pass 1 decides absorption for every photon and leaves one 32-bit
+// survivor mask per (tile, round) plus the tile's count; an exclusive scan of the counts gives
+// every tile its base; pass 2 scatters the survivors.  Costs one more read of the energies
+// (+8 B/photon) and buys: no tickets, no look-back spinning, no per-photon state in shared
+// memory.
+__global__ void __launch_bounds__(PROJ_THREADS, 4)
+k_project_detect(const __grid_constant__ pxb_photon_list L,
+                 const __grid_constant__ pxb_project_params P, const CellDerived D,
+                 const ProjWork W, uint32_t* __restrict__ masks, int64_t* __restrict__ counts,
+                 int64_t n_wtiles) {
+  __shared__ int64_t s_off_all[PROJ_WARPS][PROJ_WTILE + 2];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  int64_t* s_off = s_off_all[wid];
+  const int64_t wtile = (int64_t)blockIdx.x * PROJ_WARPS + wid;
+  if (wtile >= n_wtiles) return;
+  const int64_t p0 = wtile * PROJ_WTILE;
+  const int64_t p1 = min(p0 + (int64_t)PROJ_WTILE, L.n_photons);
+  const int64_t c0 = __ldg(D.tile_cell + wtile);
+  const int64_t c1 = (wtile + 1 < n_wtiles) ? __ldg(D.tile_cell + wtile + 1) : L.n_cells - 1;
+  const int nc = (c1 - c0 + 1 <= PROJ_WTILE + 1) ? (int)(c1 - c0 + 1) : 0;
+  for (int q = lane; q <= nc && nc > 0; q += 32) s_off[q] = __ldg(L.poff + c0 + q);
+  // all eight energy loads of the lane go out together (the item loop below is rolled)
+  double en8[PROJ_ITEMS];
+#pragma unroll
+  for (int r = 0; r < PROJ_ITEMS; ++r) {
+    const int64_t p = p0 + r * 32 + lane;
+    en8[r] = (p < p1) ? ld_stream(L.energy + p) : 0.0;
+  }
+  __syncwarp();
+  const bool absorb = P.absorb_kind != PXB_ABS_NONE;
+  int run = 0;
+  double tsum = 0.0, tmin = 1.0e99, tmax = -1.0e99;
+#pragma unroll
+  for (int r = 0; r < PROJ_ITEMS; ++r) {
+    const int64_t p = p0 + r * 32 + lane;
+    bool det = false;
+    if (p < p1) {
+      int rel = 0;
+      int64_t first;
+      if (nc == 1) {
+        first = s_off[0];
+      } else if (nc > 0) {
+#pragma unroll
+        for (int step = PROJ_WTILE; step > 0; step >>= 1) {
+          const int q = rel + step;
+          if (q < nc && s_off[q] <= p) rel = q;
+        }
+        first = s_off[rel];
+      } else {
+        int64_t lo = c0, hi = c1 + 1;
+        while (hi - lo > 1) {
+          const int64_t mid = (lo + hi) >> 1;
+          if (__ldg(L.poff + mid) <= p) lo = mid; else hi = mid;
+        }
+        rel = (int)(lo - c0);
+        first = __ldg(L.poff + lo);
+      }
+      const int64_t c = c0 + rel;
+      const double en = en8[r] * __ldg(D.shift + c);
+      det = absorb ? absorb_decision(P, c, p - first, en) : true;
+      if (det) {
+        tsum += en;
+        tmin = fmin(tmin, en);
+        tmax = fmax(tmax, en);
+      }
+    }
+    const unsigned bal = __ballot_sync(0xffffffffu, det);
+    if (lane == 0) masks[wtile * PROJ_ITEMS + r] = bal;
+    run += __popc(bal);
+  }
+  tsum = warp_sum(tsum);
+  tmin = warp_min(tmin);
+  tmax = warp_max(tmax);
+  if (lane == 0) {
+    counts[wtile] = run;
+    W.part_sum[wtile] = tsum;
+    W.part_min[wtile] = tmin;
+    W.part_max[wtile] = tmax;
+  }
+}
+
+template <int OBS>
+__global__ void __launch_bounds__(PROJ_THREADS, 4)
+k_project_emit(const __grid_constant__ pxb_photon_list L,
+               const __grid_constant__ pxb_project_params P, const CellDerived D,
+               const uint32_t* __restrict__ masks, const int64_t* __restrict__ offsets,
+               double* __restrict__ xsky, double* __restrict__ ysky,
+               double* __restrict__ eobs_out, double* __restrict__ los_out,
+               int64_t* __restrict__ n_events_out, int64_t n_wtiles) {
+  __shared__ int64_t s_off_all[PROJ_WARPS][PROJ_WTILE + 2];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  int64_t* s_off = s_off_all[wid];
+  const int64_t wtile = (int64_t)blockIdx.x * PROJ_WARPS + wid;
+  if (wtile >= n_wtiles) return;
+  if (wtile == 0 && lane == 0) *n_events_out = __ldg(offsets + n_wtiles);
+  SkyConst K;
+  K.d0_rad = P.sky_center[1] * (PXB_PI / 180.0);
+  sincos(K.d0_rad, &K.sin_d0, &K.cos_d0);
+  K.ra0_rad = P.sky_center[0] * (PXB_PI / 180.0);
+  K.inv_DA = 1.0 / P.D_A_kpc;
+  const int64_t p0 = wtile * PROJ_WTILE;
+  const int64_t base = __ldg(offsets + wtile);
+  // the lane's eight mask words (warp-uniform values) and its survivors' energies
+  const uint32_t my_mask = (lane < PROJ_ITEMS) ? __ldg(masks + wtile * PROJ_ITEMS + lane) : 0u;
+  if (__ballot_sync(0xffffffffu, my_mask != 0u) == 0u) return;   // everything absorbed
+  const int64_t c0 = __ldg(D.tile_cell + wtile);
+  const int64_t c1 = (wtile + 1 < n_wtiles) ? __ldg(D.tile_cell + wtile + 1) : L.n_cells - 1;
+  const int nc = (c1 - c0 + 1 <= PROJ_WTILE + 1) ? (int)(c1 - c0 + 1) : 0;
+  for (int q = lane; q <= nc && nc > 0; q += 32) s_off[q] = __ldg(L.poff + c0 + q);
+  __syncwarp();
+  int run = 0;
+#pragma unroll 1
+  for (int r = 0; r < PROJ_ITEMS; ++r) {
+    const uint32_t bal = __shfl_sync(0xffffffffu, my_mask, r);
+    const bool det = (bal >> lane) & 1u;
+    if (det) {
+      const int64_t p = p0 + r * 32 + lane;
+      int rel = 0;
+      int64_t first;
+      if (nc == 1) {
+        first = s_off[0];
+      } else if (nc > 0) {
+#pragma unroll
+        for (int step = PROJ_WTILE; step > 0; step >>= 1) {
+          const int q = rel + step;
+          if (q < nc && s_off[q] <= p) rel = q;
+        }
+        first = s_off[rel];
+      } else {
+        int64_t lo = c0, hi = c1 + 1;
+        while (hi - lo > 1) {
+          const int64_t mid = (lo + hi) >> 1;
+          if (__ldg(L.poff + mid) <= p) lo = mid; else hi = mid;
+        }
+        rel = (int)(lo - c0);
+        first = __ldg(L.poff + lo);
+      }
+      const int64_t c = c0 + rel;
+      const double en = ld_stream(L.energy + p) * __ldg(D.shift + c);
+      const uint64_t cell_key = (uint64_t)(P.cell_id0 + c);
+      const uint64_t draw = (uint64_t)(p - first);
+      double xs, ys, los;
+      if (OBS == 0) scatter_external(P, D, K, c, cell_key, draw, xs, ys, los);
+      else scatter_allsky(P, D, c, cell_key, draw, xs, ys, los);
+      const int64_t o = base + run + __popc(bal & ((1u << lane) - 1u));
+      st_stream(xsky + o, xs);
+      st_stream(ysky + o, ys);
+      st_stream(eobs_out + o, en);
+      if (los_out) st_stream(los_out + o, los);
+    }
+    run += __popc(bal);
+  }
+}
+
 // deterministic two-level reduction of the per-tile statistics
 __global__ void __launch_bounds__(256)
 k_reduce_stats(const double* __restrict__ ps, const double* __restrict__ pmin,
@@ -624,6 +784,7 @@ static inline int64_t align256(int64_t v) { return (v + 255) & ~(int64_t)255; }
 struct ProjLayout {
   int64_t ntiles;
   int64_t off_cells, off_tilecell, off_status, off_ticket, off_part, off_red, total;
+  int64_t off_masks, off_counts, off_offsets, off_arank, off_totals, off_scanws, scanws_bytes;
 };
 
 static ProjLayout proj_layout(int64_t n_cells, int64_t n_photons) {
@@ -636,6 +797,15 @@ static ProjLayout proj_layout(int64_t n_cells, int64_t n_photons) {
   l.off_ticket = o; o += 256;
   l.off_part = o;   o += align256(3 * l.ntiles * 8);
   l.off_red = o;    o += align256(3 * STATS_BLOCKS * 8);
+  // two-pass variant
+  l.off_masks = o;   o += align256(l.ntiles * PROJ_ITEMS * 4);
+  l.off_counts = o;  o += align256(l.ntiles * 8);
+  l.off_offsets = o; o += align256((l.ntiles + 1) * 8);
+  l.off_arank = o;   o += align256((l.ntiles + 1) * 8);
+  l.off_totals = o;  o += 256;
+  l.scanws_bytes = 0;
+  pxb_scan_workspace_bytes(l.ntiles, &l.scanws_bytes);
+  l.off_scanws = o;  o += align256(l.scanws_bytes);
   l.total = o;
   return l;
 }
@@ -697,6 +867,33 @@ extern "C" int pxb_project(const pxb_photon_list* L, const pxb_project_params* P
   PXB_CUDA(cudaMemsetAsync(ws + lay.off_status, 0, (size_t)(lay.off_part - lay.off_status), st));
   k_project_cells<<<(unsigned)((L->n_cells + 255) / 256), 256, 0, st>>>(*L, *P, D);
   PXB_LAUNCH_CHECK();
+  // default: the fused single-pass kernel (DRAM traffic == algorithmic bytes).  The two-pass
+  // variant (PXB_PROJECT_MODE=twopass) produces the identical event list without any
+  // inter-tile waiting at the price of reading the energies twice; measured within 2 % of
+  // each other on B200 while the path is ALU-bound.
+  const char* mode = getenv("PXB_PROJECT_MODE");
+  const bool fused = !(mode && strcmp(mode, "twopass") == 0);
+  if (!fused) {
+    uint32_t* masks = (uint32_t*)(ws + lay.off_masks);
+    int64_t* counts = (int64_t*)(ws + lay.off_counts);
+    int64_t* offsets = (int64_t*)(ws + lay.off_offsets);
+    int64_t* arank = (int64_t*)(ws + lay.off_arank);
+    int64_t* totals = (int64_t*)(ws + lay.off_totals);
+    const unsigned g = (unsigned)n_ctiles;
+    k_project_detect<<<g, PROJ_THREADS, 0, st>>>(*L, *P, D, W, masks, counts, lay.ntiles);
+    PXB_LAUNCH_CHECK();
+    rc = pxb_scan_counts(counts, lay.ntiles, offsets, arank, totals, ws + lay.off_scanws,
+                         lay.scanws_bytes, stream);
+    if (rc) return rc;
+    if (P->observer == 0) {
+      k_project_emit<0><<<g, PROJ_THREADS, 0, st>>>(*L, *P, D, masks, offsets, xsky, ysky, eobs,
+                                                   P->save_los ? los : nullptr, n_events_out, lay.ntiles);
+    } else {
+      k_project_emit<1><<<g, PROJ_THREADS, 0, st>>>(*L, *P, D, masks, offsets, xsky, ysky, eobs,
+                                                   P->save_los ? los : nullptr, n_events_out, lay.ntiles);
+    }
+    PXB_LAUNCH_CHECK();
+  } else {
   int per_sm = 0;
   if (P->observer == 0) {
     PXB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_project_photons<0>, PROJ_THREADS, 0));
@@ -714,6 +911,7 @@ extern "C" int pxb_project(const pxb_photon_list* L, const pxb_project_params* P
         *L, *P, D, W, xsky, ysky, eobs, P->save_los ? los : nullptr, n_events_out, lay.ntiles, n_ctiles);
   }
   PXB_LAUNCH_CHECK();
+  }
   const int64_t per_block = (lay.ntiles + STATS_BLOCKS - 1) / STATS_BLOCKS;
   const int nb = (int)((lay.ntiles + per_block - 1) / per_block);
   k_reduce_stats<<<nb, 256, 0, st>>>(W.part_sum, W.part_min, W.part_max, lay.ntiles, red, per_block);

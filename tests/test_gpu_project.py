@@ -340,3 +340,27 @@ def test_line_counts_and_energies(cuda, oracle):
         assert abs(e.size - F.sum()) < 1.645 * 4 * np.sqrt(F.sum())
         assert _ks_ok(e, oe)
         assert abs(e.mean() - 3.5 / 1.2) < 5 * e.std() / np.sqrt(e.size)
+
+
+def test_two_pass_variant_is_bit_identical(cuda):
+    """PXB_PROJECT_MODE=twopass (detect -> scan -> emit) must give exactly the event list of the
+    default fused kernel: same decisions, same order, same flux."""
+    import os
+
+    d, p = make_plist(n_cells=6000, mean_ph=25.0, zero_cells=True)
+    put("tp_ph", d, p)
+    res = {}
+    for mode in ("fused", "twopass"):
+        os.environ["PXB_PROJECT_MODE"] = mode
+        try:
+            n = px.project_photons("mem:tp_ph", "mem:tp_ev", [0.3, 0.2, 0.9], [30.0, 45.0],
+                                   absorb_model="wabs", nH=0.08, save_los=True, sigma_pos=0.3, prng=5)
+        finally:
+            os.environ.pop("PXB_PROJECT_MODE", None)
+        ev, par = events("tp_ev")
+        res[mode] = (n, ev, par)
+    assert res["fused"][0] == res["twopass"][0] > 0
+    for k in res["fused"][1]:
+        assert np.array_equal(res["fused"][1][k], res["twopass"][1][k]), k
+    for k in ("flux", "emin", "emax"):
+        assert res["fused"][2][k] == res["twopass"][2][k]
