@@ -493,6 +493,7 @@ k_project_photons(const __grid_constant__ pxb_photon_list L,
     const int64_t c0 = __ldg(D.tile_cell + wtile);
     const int64_t c1 = (wtile + 1 < n_wtiles) ? __ldg(D.tile_cell + wtile + 1) : L.n_cells - 1;
     const int nc = (c1 - c0 + 1 <= PROJ_WTILE + 1) ? (int)(c1 - c0 + 1) : 0;
+    const int step0 = nc > 1 ? (1 << (31 - __clz(nc - 1))) : 0;
     __syncwarp();
     for (int q = lane; q <= nc && nc > 0; q += 32) s_off[q] = __ldg(L.poff + c0 + q);
     __syncwarp();
@@ -519,8 +520,7 @@ k_project_photons(const __grid_constant__ pxb_photon_list L,
           first = s_off[0];
         } else if (nc > 0) {
           // branch-free bisection: largest q in [0, nc) with s_off[q] <= p
-#pragma unroll
-          for (int step = PROJ_WTILE; step > 0; step >>= 1) {
+          for (int step = step0; step > 0; step >>= 1) {   // step0: largest power of two < nc
             const int q = rel + step;
             if (q < nc && s_off[q] <= p) rel = q;
           }
@@ -609,19 +609,21 @@ k_project_detect(const __grid_constant__ pxb_photon_list L,
   const int64_t c0 = __ldg(D.tile_cell + wtile);
   const int64_t c1 = (wtile + 1 < n_wtiles) ? __ldg(D.tile_cell + wtile + 1) : L.n_cells - 1;
   const int nc = (c1 - c0 + 1 <= PROJ_WTILE + 1) ? (int)(c1 - c0 + 1) : 0;
+  const int step0 = nc > 1 ? (1 << (31 - __clz(nc - 1))) : 0;
   for (int q = lane; q <= nc && nc > 0; q += 32) s_off[q] = __ldg(L.poff + c0 + q);
   // all eight energy loads of the lane go out together (the item loop below is rolled)
-  double en8[PROJ_ITEMS];
+  __shared__ double s_e_all[PROJ_WARPS][PROJ_WTILE];
+  double* s_e = s_e_all[wid];
 #pragma unroll
   for (int r = 0; r < PROJ_ITEMS; ++r) {
     const int64_t p = p0 + r * 32 + lane;
-    en8[r] = (p < p1) ? ld_stream(L.energy + p) : 0.0;
+    if (p < p1) s_e[r * 32 + lane] = ld_stream(L.energy + p);
   }
   __syncwarp();
   const bool absorb = P.absorb_kind != PXB_ABS_NONE;
   int run = 0;
   double tsum = 0.0, tmin = 1.0e99, tmax = -1.0e99;
-#pragma unroll
+#pragma unroll 1
   for (int r = 0; r < PROJ_ITEMS; ++r) {
     const int64_t p = p0 + r * 32 + lane;
     bool det = false;
@@ -631,8 +633,7 @@ k_project_detect(const __grid_constant__ pxb_photon_list L,
       if (nc == 1) {
         first = s_off[0];
       } else if (nc > 0) {
-#pragma unroll
-        for (int step = PROJ_WTILE; step > 0; step >>= 1) {
+        for (int step = step0; step > 0; step >>= 1) {   // step0: largest power of two < nc
           const int q = rel + step;
           if (q < nc && s_off[q] <= p) rel = q;
         }
@@ -647,7 +648,7 @@ k_project_detect(const __grid_constant__ pxb_photon_list L,
         first = __ldg(L.poff + lo);
       }
       const int64_t c = c0 + rel;
-      const double en = en8[r] * __ldg(D.shift + c);
+      const double en = s_e[r * 32 + lane] * __ldg(D.shift + c);
       det = absorb ? absorb_decision(P, c, p - first, en) : true;
       if (det) {
         tsum += en;
@@ -697,7 +698,15 @@ k_project_emit(const __grid_constant__ pxb_photon_list L,
   const int64_t c0 = __ldg(D.tile_cell + wtile);
   const int64_t c1 = (wtile + 1 < n_wtiles) ? __ldg(D.tile_cell + wtile + 1) : L.n_cells - 1;
   const int nc = (c1 - c0 + 1 <= PROJ_WTILE + 1) ? (int)(c1 - c0 + 1) : 0;
+  const int step0 = nc > 1 ? (1 << (31 - __clz(nc - 1))) : 0;
   for (int q = lane; q <= nc && nc > 0; q += 32) s_off[q] = __ldg(L.poff + c0 + q);
+  __shared__ double s_e_all[PROJ_WARPS][PROJ_WTILE];
+  double* s_e = s_e_all[wid];
+#pragma unroll
+  for (int r = 0; r < PROJ_ITEMS; ++r) {
+    const uint32_t bal = __shfl_sync(0xffffffffu, my_mask, r);
+    if ((bal >> lane) & 1u) s_e[r * 32 + lane] = ld_stream(L.energy + p0 + r * 32 + lane);
+  }
   __syncwarp();
   int run = 0;
 #pragma unroll 1
@@ -711,8 +720,7 @@ k_project_emit(const __grid_constant__ pxb_photon_list L,
       if (nc == 1) {
         first = s_off[0];
       } else if (nc > 0) {
-#pragma unroll
-        for (int step = PROJ_WTILE; step > 0; step >>= 1) {
+        for (int step = step0; step > 0; step >>= 1) {   // step0: largest power of two < nc
           const int q = rel + step;
           if (q < nc && s_off[q] <= p) rel = q;
         }
@@ -727,7 +735,7 @@ k_project_emit(const __grid_constant__ pxb_photon_list L,
         first = __ldg(L.poff + lo);
       }
       const int64_t c = c0 + rel;
-      const double en = ld_stream(L.energy + p) * __ldg(D.shift + c);
+      const double en = s_e[r * 32 + lane] * __ldg(D.shift + c);
       const uint64_t cell_key = (uint64_t)(P.cell_id0 + c);
       const uint64_t draw = (uint64_t)(p - first);
       double xs, ys, los;
@@ -867,12 +875,12 @@ extern "C" int pxb_project(const pxb_photon_list* L, const pxb_project_params* P
   PXB_CUDA(cudaMemsetAsync(ws + lay.off_status, 0, (size_t)(lay.off_part - lay.off_status), st));
   k_project_cells<<<(unsigned)((L->n_cells + 255) / 256), 256, 0, st>>>(*L, *P, D);
   PXB_LAUNCH_CHECK();
-  // default: the fused single-pass kernel (DRAM traffic == algorithmic bytes).  The two-pass
-  // variant (PXB_PROJECT_MODE=twopass) produces the identical event list without any
-  // inter-tile waiting at the price of reading the energies twice; measured within 2 % of
-  // each other on B200 while the path is ALU-bound.
+  // default: two passes (detect -> scan -> emit): no inter-tile waiting, small rolled kernels,
+  // at the price of reading the energies twice (+8 B/photon).  PXB_PROJECT_MODE=fused selects
+  // the single-pass kernel (DRAM traffic == algorithmic bytes, decoupled look-back), which
+  // produces the identical event list; on B200 it is ~10 % slower while the path is ALU-bound.
   const char* mode = getenv("PXB_PROJECT_MODE");
-  const bool fused = !(mode && strcmp(mode, "twopass") == 0);
+  const bool fused = mode && strcmp(mode, "fused") == 0;
   if (!fused) {
     uint32_t* masks = (uint32_t*)(ws + lay.off_masks);
     int64_t* counts = (int64_t*)(ws + lay.off_counts);

@@ -770,6 +770,7 @@ k_thermal_sample_staged(const DevModel M, const __grid_constant__ pxb_thermal_ce
       const int64_t c0 = __ldg(tile_cell + tile);
       const int64_t c1 = (tile + 1 < ntiles_all) ? __ldg(tile_cell + tile + 1) : n_active - 1;
       const int nc = (c1 - c0 + 1 <= STG_WTILE + 1) ? (int)(c1 - c0 + 1) : 0;
+      const int step0 = nc > 1 ? (1 << (31 - __clz(nc - 1))) : 0;
       __syncwarp();
       for (int q = lane; q <= nc && nc > 0; q += 32) s_off[q] = __ldg(poff + c0 + q);
       __syncwarp();
@@ -791,8 +792,7 @@ k_thermal_sample_staged(const DevModel M, const __grid_constant__ pxb_thermal_ce
           if (nc > 0) {
             int rel = 0;
             if (nc > 1) {
-#pragma unroll
-              for (int step = STG_WTILE; step > 0; step >>= 1) {
+              for (int step = step0; step > 0; step >>= 1) {   // largest power of two < nc
                 const int q = rel + step;
                 if (q < nc && s_off[q] <= p) rel = q;
               }

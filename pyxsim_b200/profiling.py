@@ -15,7 +15,7 @@ KERNELS_PER_CALL = {
     "pxb_thermal_counts": 2, "pxb_thermal_sample": 3, "pxb_thermal_spectra": 1,
     "pxb_interp_spec": 1, "pxb_scan_counts": 3, "pxb_compact_cells": 1, "pxb_radius2": 1,
     "pxb_powerlaw_counts": 1, "pxb_powerlaw_sample": 1, "pxb_line_counts": 1,
-    "pxb_line_sample": 1, "pxb_project": 4, "pxb_doppler_shift": 1, "pxb_pixel_to_cel": 1,
+    "pxb_line_sample": 1, "pxb_project": 8, "pxb_doppler_shift": 1, "pxb_pixel_to_cel": 1,
     "pxb_absorb_transmission": 1,
 }
 

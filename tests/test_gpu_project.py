@@ -343,8 +343,8 @@ def test_line_counts_and_energies(cuda, oracle):
 
 
 def test_two_pass_variant_is_bit_identical(cuda):
-    """PXB_PROJECT_MODE=twopass (detect -> scan -> emit) must give exactly the event list of the
-    default fused kernel: same decisions, same order, same flux."""
+    """The default two-pass projection (detect -> scan -> emit) and the fused single-pass kernel
+    (PXB_PROJECT_MODE=fused) must give exactly the same event list: decisions, order, flux."""
     import os
 
     d, p = make_plist(n_cells=6000, mean_ph=25.0, zero_cells=True)
