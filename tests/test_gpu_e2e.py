@@ -269,3 +269,65 @@ def test_powerlaw_plus_line_with_redshift_end_to_end(cuda, oracle):
         return out
 
     H.assert_distributions_agree(run, seeds=((21, 22), (31, 32)))
+
+
+def test_internal_observer_end_to_end(cuda, oracle):
+    """observer="internal": photons weighted by 1/r^2 from the chosen centre, redshift forced to
+    zero, all-sky projection (project_photons_allsky)."""
+    src, sm, (kT_nodes, ebins, cosmic, metal) = _cluster(24, nbins=500)
+    c = np.array([700.0, -650.0, 800.0])          # observer well off-centre, inside the box
+    f = {k: v.cpu().numpy() for k, v in src.fields.items()}
+    pos = [f[("index", ax)] for ax in "xyz"]
+    r2 = oracle.compute_radius(pos, [-1000.0] * 3, [1000.0] * 3, [2000.0] * 3, c, (False,) * 3)
+    texp = 1.0e5
+    a = dict(kT=f[TF], em=f[("gas", "emission_measure")], r2=r2)
+    om = oracle.TableModel(ebins, kT_nodes, cosmic, metal)
+    cfg1 = dict(kT_min=0.025, kT_max=64.0, Zmet=0.3, spectral_norm=texp / (4 * np.pi))
+    area = 3.0e4 / oracle.thermal_spectra(om, cfg1, a)[2].sum()        # ~3e4 photons
+    norm = area * texp / (4 * np.pi)
+    cfg = dict(kT_min=0.025, kT_max=64.0, Zmet=0.3, spectral_norm=norm)
+    cut, tot, lam = oracle.thermal_spectra(om, cfg, a)
+    model = px.ThermalSourceModel(sm, 0.1, 10.0, 500, 0.3, temperature_field=TF, prng=8)
+    n_ph, n_c = px.make_photons("mem:int_ph", src, 0.3, area, texp, model, observer="internal", center=c)
+    assert lam.sum() > 2.0e4 and abs(n_ph - lam.sum()) < 5 * np.sqrt(lam.sum())
+    lst = px.load_list("mem:int_ph")
+    assert float(lst.parameters["fid_redshift"]) == 0.0 and str(lst.parameters["observer"]) == "internal"
+    idx_x = lst.numpy("x")
+    assert np.allclose(idx_x.min(), pos[0].min() - c[0]) or idx_x.min() > pos[0].min() - c[0]
+    with pytest.raises(RuntimeError):
+        px.project_photons("mem:int_ph", "mem:int_ev", "z", [0.0, 0.0])
+    n_ev = px.project_photons_allsky("mem:int_ph", "mem:int_ev", [0.0, 0.0, 1.0], save_los=True, prng=2)
+    ev = px.load_list("mem:int_ev")
+    assert n_ev == n_ph
+    d = {k: lst.numpy(k) for k in ("x", "y", "z", "vx", "vy", "vz", "dx", "num_photons", "energy")}
+    params = dict(data_type="cells", observer="internal", fid_d_a=0.0, fid_redshift=0.0)
+    ref = oracle.project_photons(d, params, [0.0, 0.0, 1.0], [0.0, 0.0], np.random.RandomState(3), save_los=True)
+    for k in ("xsky", "ysky", "los"):
+        assert stats.ks_2samp(ev.numpy(k), ref[k]).pvalue > 0.01, k
+    np.testing.assert_allclose(np.sort(ev.numpy("eobs")), np.sort(ref["eobs"]), rtol=1e-14)
+
+
+def test_make_photons_options(cuda):
+    """point_sources, fields_to_keep, bulk_velocity, explicit velocity_fields, center."""
+    src, sm, _ = _cluster(12, nbins=200)
+    src.fields[("gas", "tracer")] = torch.arange(12 ** 3, dtype=torch.float64)
+    src.fields[("gas", "wind_x")] = torch.full((12 ** 3,), 7.0, dtype=torch.float64)
+    model = px.ThermalSourceModel(sm, 0.1, 10.0, 200, 0.3, temperature_field=TF, prng=3)
+    vf = [("gas", "wind_x"), ("gas", "velocity_y"), ("gas", "velocity_z")]
+    n_ph, n_c = px.make_photons("mem:opt", src, 0.05, 3.0e4, 1.0e5, model, point_sources=True,
+                                fields_to_keep=[("gas", "tracer")], bulk_velocity=[1.0, 2.0, 3.0],
+                                velocity_fields=vf, center=[10.0, 20.0, 30.0])
+    lst = px.load_list("mem:opt")
+    idx = lst.numpy("tracer").astype(int)
+    assert n_c == idx.size and np.all(np.diff(idx) > 0)
+    assert np.all(lst.numpy("dx") == 0.0)                                   # point sources
+    assert np.all(lst.numpy("vx") == 6.0)                                   # wind_x - bulk
+    x = src.fields[("index", "x")].cpu().numpy()
+    assert np.array_equal(lst.numpy("x"), x[idx] - 10.0)
+    vy = src.fields[("gas", "velocity_y")].cpu().numpy()
+    assert np.array_equal(lst.numpy("vy"), vy[idx] - 2.0)
+    # point sources project onto their cell centres exactly (no scatter width)
+    n_ev = px.project_photons("mem:opt", "mem:opt_ev", "z", [0.0, 0.0], phys_coord=True, no_shifting=True)
+    ev = px.load_list("mem:opt_ev")
+    nph = lst.numpy("num_photons")
+    assert n_ev == n_ph and np.array_equal(ev.numpy("xsky"), np.repeat(lst.numpy("x"), nph))
