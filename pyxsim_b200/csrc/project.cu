@@ -28,22 +28,26 @@ constexpr double PXB_RAD2DEG = 180.0 / PXB_PI;
 // Morrison & McCammon (1983) piecewise polynomial, as used by soxs.get_wabs_absorb (the
 // third-party routine behind WabsModel, spectral_models.py:633-635): sigma(E) =
 // (c0 + c1 E + c2 E^2) / E^3 * 1e-24 cm^2.
-__constant__ double c_wabs_edge[15] = {0.03, 0.1, 0.284, 0.4, 0.532, 0.707, 0.867, 1.303,
-                                       1.84, 2.471, 3.21, 4.038, 7.111, 8.331, 10.0};
-__constant__ double c_wabs_c0[14] = {17.3, 34.6, 78.1, 71.4, 95.5, 308.9, 120.6,
-                                     141.3, 202.7, 342.7, 352.2, 433.9, 629.0, 701.2};
-__constant__ double c_wabs_c1[14] = {608.1, 267.9, 18.8, 66.8, 145.8, -380.6, 169.3,
-                                     146.8, 104.7, 18.7, 18.7, -2.4, 30.9, 25.2};
-__constant__ double c_wabs_c2[14] = {-2150.0, -476.1, 4.3, -51.4, -61.1, 294.0, -47.7,
-                                     -31.5, -17.0, 0.0, 0.0, 0.75, 0.0, 0.0};
+// Coefficients live in global memory (L1-resident, 16-byte records) rather than __constant__:
+// the piece index differs per lane, and divergent constant-bank reads serialise.
+struct __align__(16) WabsPiece { double c0, c1, c2, pad; };
+__device__ const WabsPiece g_wabs[14] = {
+    {17.3, 608.1, -2150.0, 0.0},  {34.6, 267.9, -476.1, 0.0}, {78.1, 18.8, 4.3, 0.0},
+    {71.4, 66.8, -51.4, 0.0},     {95.5, 145.8, -61.1, 0.0},  {308.9, -380.6, 294.0, 0.0},
+    {120.6, 169.3, -47.7, 0.0},   {141.3, 146.8, -31.5, 0.0}, {202.7, 104.7, -17.0, 0.0},
+    {342.7, 18.7, 0.0, 0.0},      {352.2, 18.7, 0.0, 0.0},    {433.9, -2.4, 0.75, 0.0},
+    {629.0, 30.9, 0.0, 0.0},      {701.2, 25.2, 0.0, 0.0}};
 
 __device__ __forceinline__ double wabs_tau_per_nh(double e) {
-  // piece index = number of inner edges <= e, by bisection (edges 1..13)
-  int k = (e >= c_wabs_edge[7]) ? 7 : 0;
-  k += (e >= c_wabs_edge[k + 4]) ? 4 : 0;
-  k += (k + 2 <= 13 && e >= c_wabs_edge[k + 2]) ? 2 : 0;
-  k += (k + 1 <= 13 && e >= c_wabs_edge[k + 1]) ? 1 : 0;
-  const double s = (c_wabs_c0[k] + e * (c_wabs_c1[k] + e * c_wabs_c2[k])) / (e * e * e);
+  // piece index = number of inner edges <= e (edges 0.1 ... 8.331 keV; below 0.1 the first
+  // piece, above 10 the last): thirteen independent compares against immediates
+  const int k = (e >= 0.1) + (e >= 0.284) + (e >= 0.4) + (e >= 0.532) + (e >= 0.707) +
+                (e >= 0.867) + (e >= 1.303) + (e >= 1.84) + (e >= 2.471) + (e >= 3.21) +
+                (e >= 4.038) + (e >= 7.111) + (e >= 8.331);
+  const double2* q = reinterpret_cast<const double2*>(&g_wabs[k]);
+  const double2 a = __ldg(q), b = __ldg(q + 1);
+  const double inv = 1.0 / e;
+  const double s = (a.x + e * (a.y + e * b.x)) * (inv * inv * inv);
   return s * 1.0e-2;  // 1e-24 cm^2 * 1e22 cm^-2
 }
 
@@ -326,6 +330,16 @@ struct SkyConst {
   double sin_d0, cos_d0, ra0_rad, d0_rad, inv_DA;
 };
 
+static SkyConst make_sky_const(const pxb_project_params* P) {
+  SkyConst K;
+  K.d0_rad = P->sky_center[1] * (PXB_PI / 180.0);
+  K.sin_d0 = sin(K.d0_rad);
+  K.cos_d0 = cos(K.d0_rad);
+  K.ra0_rad = P->sky_center[0] * (PXB_PI / 180.0);
+  K.inv_DA = P->D_A_kpc != 0.0 ? 1.0 / P->D_A_kpc : 0.0;
+  return K;
+}
+
 __device__ __forceinline__ double u32_centered(uint32_t w) {
   // (w + 0.5) / 2^32 - 0.5: uniform in (-1/2, 1/2) with 32-bit resolution; the conversion is
   // the exact 2^52 + w mantissa trick
@@ -346,9 +360,15 @@ __device__ __forceinline__ void scatter_external(const pxb_project_params& P, co
   if (P.data_type == 0) {
     // cells: uniform inside the cube, rotated into the sky plane (sky_functions.pyx:74-76,
     // 110-121; on-axis x_hat/y_hat are axis vectors so only two of the draws contribute)
-    const double u0 = u32_centered(rb.x), u1 = u32_centered(rb.y), u2 = u32_centered(rb.z);
-    ox = u0 * P.x_hat[0] + u1 * P.x_hat[1] + u2 * P.x_hat[2];
-    oy = u0 * P.y_hat[0] + u1 * P.y_hat[1] + u2 * P.y_hat[2];
+    const double u0 = u32_centered(rb.x), u1 = u32_centered(rb.y);
+    if (P.vn_axis >= 0) {   // on-axis: x_hat, y_hat are coordinate axes, two draws suffice
+      ox = u0;
+      oy = u1;
+    } else {
+      const double u2 = u32_centered(rb.z);
+      ox = u0 * P.x_hat[0] + u1 * P.x_hat[1] + u2 * P.x_hat[2];
+      oy = u0 * P.y_hat[0] + u1 * P.y_hat[1] + u2 * P.y_hat[2];
+    }
   } else if (P.kernel == 1) {
     normal2(rb, ox, oy);  // sky_functions.pyx:78-80
   } else {
@@ -453,7 +473,8 @@ k_project_photons(const __grid_constant__ pxb_photon_list L,
                   const __grid_constant__ pxb_project_params P, const CellDerived D,
                   const ProjWork W, double* __restrict__ xsky, double* __restrict__ ysky,
                   double* __restrict__ eobs_out, double* __restrict__ los_out,
-                  int64_t* __restrict__ n_events_out, int64_t n_wtiles, int64_t n_ctiles) {
+                  int64_t* __restrict__ n_events_out, int64_t n_wtiles, int64_t n_ctiles,
+                  const SkyConst K) {
   // per-warp scratch: cell offsets of the tile and the per-photon state carried from phase 1
   // to phase 3 (energy, cell, output slot) -- kept in shared memory so the item loops stay
   // rolled (small code, few registers, more resident warps)
@@ -467,11 +488,6 @@ k_project_photons(const __grid_constant__ pxb_photon_list L,
   double* s_e = s_e_all[wid];
   int* s_rel = s_rel_all[wid];
   short* s_slot = s_slot_all[wid];
-  SkyConst K;
-  K.d0_rad = P.sky_center[1] * (PXB_PI / 180.0);
-  sincos(K.d0_rad, &K.sin_d0, &K.cos_d0);
-  K.ra0_rad = P.sky_center[0] * (PXB_PI / 180.0);
-  K.inv_DA = 1.0 / P.D_A_kpc;
   const bool absorb = P.absorb_kind != PXB_ABS_NONE;
 
   for (;;) {
@@ -678,18 +694,13 @@ k_project_emit(const __grid_constant__ pxb_photon_list L,
                const uint32_t* __restrict__ masks, const int64_t* __restrict__ offsets,
                double* __restrict__ xsky, double* __restrict__ ysky,
                double* __restrict__ eobs_out, double* __restrict__ los_out,
-               int64_t* __restrict__ n_events_out, int64_t n_wtiles) {
+               int64_t* __restrict__ n_events_out, int64_t n_wtiles, const SkyConst K) {
   __shared__ int64_t s_off_all[PROJ_WARPS][PROJ_WTILE + 2];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   int64_t* s_off = s_off_all[wid];
   const int64_t wtile = (int64_t)blockIdx.x * PROJ_WARPS + wid;
   if (wtile >= n_wtiles) return;
   if (wtile == 0 && lane == 0) *n_events_out = __ldg(offsets + n_wtiles);
-  SkyConst K;
-  K.d0_rad = P.sky_center[1] * (PXB_PI / 180.0);
-  sincos(K.d0_rad, &K.sin_d0, &K.cos_d0);
-  K.ra0_rad = P.sky_center[0] * (PXB_PI / 180.0);
-  K.inv_DA = 1.0 / P.D_A_kpc;
   const int64_t p0 = wtile * PROJ_WTILE;
   const int64_t base = __ldg(offsets + wtile);
   // the lane's eight mask words (warp-uniform values) and its survivors' energies
@@ -879,6 +890,7 @@ extern "C" int pxb_project(const pxb_photon_list* L, const pxb_project_params* P
   // at the price of reading the energies twice (+8 B/photon).  PXB_PROJECT_MODE=fused selects
   // the single-pass kernel (DRAM traffic == algorithmic bytes, decoupled look-back), which
   // produces the identical event list; on B200 it is ~10 % slower while the path is ALU-bound.
+  const SkyConst K = make_sky_const(P);
   const char* mode = getenv("PXB_PROJECT_MODE");
   const bool fused = mode && strcmp(mode, "fused") == 0;
   if (!fused) {
@@ -895,10 +907,10 @@ extern "C" int pxb_project(const pxb_photon_list* L, const pxb_project_params* P
     if (rc) return rc;
     if (P->observer == 0) {
       k_project_emit<0><<<g, PROJ_THREADS, 0, st>>>(*L, *P, D, masks, offsets, xsky, ysky, eobs,
-                                                   P->save_los ? los : nullptr, n_events_out, lay.ntiles);
+                                                   P->save_los ? los : nullptr, n_events_out, lay.ntiles, K);
     } else {
       k_project_emit<1><<<g, PROJ_THREADS, 0, st>>>(*L, *P, D, masks, offsets, xsky, ysky, eobs,
-                                                   P->save_los ? los : nullptr, n_events_out, lay.ntiles);
+                                                   P->save_los ? los : nullptr, n_events_out, lay.ntiles, K);
     }
     PXB_LAUNCH_CHECK();
   } else {
@@ -913,10 +925,10 @@ extern "C" int pxb_project(const pxb_photon_list* L, const pxb_project_params* P
   if (grid > n_ctiles) grid = n_ctiles;
   if (P->observer == 0) {
     k_project_photons<0><<<(unsigned)grid, PROJ_THREADS, 0, st>>>(
-        *L, *P, D, W, xsky, ysky, eobs, P->save_los ? los : nullptr, n_events_out, lay.ntiles, n_ctiles);
+        *L, *P, D, W, xsky, ysky, eobs, P->save_los ? los : nullptr, n_events_out, lay.ntiles, n_ctiles, K);
   } else {
     k_project_photons<1><<<(unsigned)grid, PROJ_THREADS, 0, st>>>(
-        *L, *P, D, W, xsky, ysky, eobs, P->save_los ? los : nullptr, n_events_out, lay.ntiles, n_ctiles);
+        *L, *P, D, W, xsky, ysky, eobs, P->save_los ? los : nullptr, n_events_out, lay.ntiles, n_ctiles, K);
   }
   PXB_LAUNCH_CHECK();
   }
