@@ -278,7 +278,7 @@ typedef struct {
   double sky_center[2];  /* degrees */
   double nH;             /* foreground column, 1e22 cm^-2 */
   const double* abs_energy;  /* device [abs_n], ascending, keV */
-  const double* abs_sigma;   /* device [abs_n], cm^2 * 1e22 (so that tau = sigma*nH) */
+  const double* abs_sigma;   /* device [abs_n], in 1e-22 cm^2 so that tau = sigma * nH */
   int64_t abs_n;
   int32_t abs_grid;          /* 0 arbitrary ascending grid (binary search), 1 uniform in E,
                                 2 uniform in log10(E): index = (x - abs_x0) * abs_inv_dx */

@@ -8,14 +8,22 @@ them cannot be imported (it needs yt / soxs / unyt / h5py, none installed), so i
 below in NumPy, statement by statement, each function citing the reference lines it follows
 (paths relative to /root/reference).
 
-Parity status: PINNED for the native routines (they are the reference) and for
-pixel_to_cel additionally against the analytic inverse-gnomonic known answer of
-pyxsim/tests/test_pixel_to_cel.py; the NumPy glue is pinned by construction against the
-reference natives it feeds and by the committed golden vectors in tests/golden (generated
-by tests/golden/make_golden.py from this file + oracle/_ref).  The reference's own golden
-HDF5 answers (pyxsim/tests/test_sloshing.py) are not in its tree and need network data.
-Third-party arithmetic (soxs tables, tbabs/wabs cross-sections, yt Orientation) is
-parameterised: tables and sigma(E) are inputs; wabs/orientation restate the published rules.
+Parity status: PINNED.
+  * The native routines are the reference itself (compiled from its Cython, oracle/_ref);
+    pixel_to_cel is additionally checked against the analytic inverse-gnomonic known answer of
+    pyxsim/tests/test_pixel_to_cel.py.
+  * The NumPy glue in this file is pinned bit for bit against outputs of the reference's OWN
+    Python code (ThermalSourceModel.process_data, PionSpectralModel.get_spectrum,
+    PowerLaw/LineSourceModel.process_data, AbsorptionModel.absorb_photons, _project_photons
+    for eight projection configurations) executed in the build container through
+    oracle/ref_import.py (stand-ins for the absent yt/soxs/unyt/h5py that carry no physics);
+    fixtures: tests/golden/reference_golden.npz, generator: tests/golden/make_reference_golden.py,
+    check: tests/test_cpu_oracle.py::test_restatement_matches_reference_python_bit_for_bit.
+  * NOT pinned (third-party arithmetic absent from the reference tree and from this image):
+    soxs' APEC/Cloudy table builders and tbabs/wabs cross-sections, yt's Orientation.  Tables
+    and sigma(E) are inputs; the wabs polynomial and the Orientation rule restate the published
+    algorithms.  The reference's golden HDF5 answers (pyxsim/tests/test_sloshing.py) need
+    network data.
 """
 import numpy as np
 
@@ -241,7 +249,7 @@ def thermal_spectra(model, cfg, a):
     return cut, tot, lam
 
 
-def thermal_process_data(model, cfg, a, prng, method="invert_cdf"):
+def thermal_process_data(model, cfg, a, prng, method="invert_cdf", literal_q3=False):
     """The photons branch, base.py:427-524: returns (ncells, number_of_photons[active],
     idxs[active], energies) exactly like the reference (RandomState draw order included)."""
     cut, kT, cell_nrm, nH, metalZ, elemZ = thermal_select(cfg, a)
@@ -285,7 +293,11 @@ def thermal_process_data(model, cfg, a, prng, method="invert_cdf"):
             energies.append(cell_e)
     active = number_of_photons > 0
     ee = np.concatenate(energies) if energies else np.zeros(0)
-    if model.binscale == "log" and method == "invert_cdf":
+    # base.py:522-523 applies 10** for log binning whatever the method; with accept_reject the
+    # energies are bin centres (not logarithms), so that is a latent bug.
+    # literal_q3=True reproduces it (used to pin this restatement against the reference's
+    # output); the default returns the bin centres unchanged, like the GPU path.
+    if model.binscale == "log" and (method == "invert_cdf" or literal_q3):
         ee = 10 ** ee
     return int(active.sum()), number_of_photons[active], idxs[active], ee
 
@@ -296,7 +308,9 @@ def thermal_process_data(model, cfg, a, prng, method="invert_cdf"):
 def powerlaw_lambda(cfg, lum_keV_s, alpha):
     """Expected counts Nph (power_law_sources.py:196-222) and norm_fac (:214)."""
     alpha = np.asarray(alpha, "float64") * np.ones_like(lum_keV_s)
-    e0, emin, emax = cfg["e0"], cfg["emin"], cfg["emax"]
+    # 0-d arrays like the reference's ``self.emin.v``: NumPy's array power loop (SIMD) and the
+    # scalar libm pow can differ in the last bit
+    e0, emin, emax = (np.asarray(cfg[k], dtype="float64") for k in ("e0", "emin", "emax"))
     ei, ef = emin, emax
     etoalpha = e0 ** alpha
     K_fac = emax ** (2.0 - alpha) - emin ** (2.0 - alpha)
@@ -320,7 +334,7 @@ def powerlaw_lambda(cfg, lum_keV_s, alpha):
 
 def powerlaw_process_data(cfg, lum_keV_s, alpha, prng):
     Nph, norm_fac, alpha = powerlaw_lambda(cfg, lum_keV_s, alpha)
-    ei, ef = cfg["emin"], cfg["emax"]
+    ei, ef = np.asarray(cfg["emin"], dtype="float64"), np.asarray(cfg["emax"], dtype="float64")
     number_of_photons = prng.poisson(lam=Nph)
     energies = np.zeros(number_of_photons.sum())
     start_e = 0
@@ -417,7 +431,9 @@ def orientation(normal, north_vector=None):
 # absorption: spectral_models.py:540-635
 # ---------------------------------------------------------------------------------------
 class TableAbsorb:
-    """AbsorptionModel with a tabulated cross-section (spectral_models.py:556-583)."""
+    """AbsorptionModel with a tabulated cross-section (spectral_models.py:540-583).  As in the
+    reference the optical depth is literally ``sigma * nH``: with nH in 1e22 cm^-2 the table
+    must be given in units of 1e-22 cm^2."""
 
     def __init__(self, nH, energy, cross_section):
         self._nH = nH
@@ -426,7 +442,7 @@ class TableAbsorb:
 
     def get_absorb(self, e):
         sigma = np.interp(e, self.emid, self.sigma, left=0.0, right=0.0)
-        return np.exp(-sigma * self._nH * 1.0e22)
+        return np.exp(-sigma * self._nH)
 
     def absorb_photons(self, eobs, prng):
         n_events = eobs.size

@@ -312,7 +312,9 @@ def _grid_kind(e):
 
 class AbsorptionModel:
     """``AbsorptionModel(nH, energy, cross_section)`` (spectral_models.py:540-583): tabulated
-    cross-section [cm^2] on an ascending energy grid [keV], nH in 1e22 cm^-2."""
+    cross-section on an ascending energy grid [keV].  As in the reference the optical depth is
+    literally ``cross_section * nH`` (spectral_models.py:560-561): with nH in 1e22 cm^-2 the
+    table is in units of 1e-22 cm^2."""
 
     _name = ""
     _kind = _lib.ABS_TABLE
@@ -338,7 +340,7 @@ class AbsorptionModel:
         if self._kind != _lib.ABS_TABLE:
             return []
         if self._dev is None:
-            self._dev = (to_device(self.emid), to_device(self.sigma * 1.0e22))
+            self._dev = (to_device(self.emid), to_device(self.sigma))
         P.abs_energy = self._dev[0].data_ptr()
         P.abs_sigma = self._dev[1].data_ptr()
         P.abs_n = self.emid.size
@@ -387,7 +389,8 @@ class TBabsModel(AbsorptionModel):
             nh_probe = 1.0e-3
             cross_section = -np.log(get_tbabs_absorb(energy, nh_probe, abund_table=abund_table))
             cross_section /= nh_probe * 1.0e22
-        super().__init__(nH, energy, cross_section)
+        # cross_section is per H atom in cm^2; nH is in 1e22 cm^-2
+        super().__init__(nH, energy, np.asarray(cross_section, dtype="float64") * 1.0e22)
         self.abund_table = abund_table
 
 

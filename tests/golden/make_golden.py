@@ -48,7 +48,7 @@ def compute(oracle):
 
     en, sg = synthetic.tbabs_like_sigma(n=500)
     ee = np.exp(rng.uniform(np.log(0.02), np.log(20), 300))
-    out.update(ab_e=ee, ab_tab=oracle.TableAbsorb(0.1, en, sg).get_absorb(ee),
+    out.update(ab_e=ee, ab_tab=oracle.TableAbsorb(0.1, en, sg * 1.0e22).get_absorb(ee),
                ab_wabs=oracle.WabsAbsorb(0.1).get_absorb(ee))
     # --- power law / line expected counts ------------------------------------------------------
     alpha = np.concatenate([[1.0, 2.0], rng.uniform(0.5, 2.5, 30)])

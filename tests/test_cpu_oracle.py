@@ -92,3 +92,114 @@ def test_golden_vectors(oracle):
     assert sorted(fresh) == sorted(stored.files)
     for k in stored.files:
         assert np.array_equal(fresh[k], stored[k]), k
+
+
+def _replay_reference_cases(O, I, cases):
+    """Recompute everything tests/golden/make_reference_golden.py stored, with the NumPy
+    restatement (oracle/ref_glue.py) instead of the reference's own Python."""
+    out = {}
+    a = I["t1"]
+    t = a["tables"]
+    om = O.TableModel(t["ebins"], t["Tvals"], t["cosmic"], t["metal"], t["var"], binscale=t["binscale"])
+    cfg = dict(kT_min=0.025, kT_max=64.0, Zmet="Z", Zconvert=a["Zconvert"], z_by_xh=True,
+               h_fraction=a["h_fraction"], spectral_norm=a["norm"], max_density=3e-26,
+               var_elem=[(0.5, 1.0, False), ("Fe", 1.0, False)])
+    nc, nph, idx, e = O.thermal_process_data(
+        om, cfg, dict(kT=a["kT"], em=a["em"], Z=a["Z"], Fe=a["Fe"], density=a["dens"]), np.random.RandomState(11))
+    out.update(t1_nc=nc, t1_nph=nph, t1_idx=idx, t1_e=e)
+
+    a = I["t2"]
+    t = a["tables"]
+    om = O.TableModel(t["ebins"], t["Tvals"], t["cosmic"], t["metal"], t["var"], binscale=t["binscale"])
+    cfg = dict(kT_min=0.025, kT_max=64.0, Zmet=0.3, spectral_norm=a["norm"])
+    for meth, seed in (("invert_cdf", 12), ("accept_reject", 13)):
+        nc, nph, idx, e = O.thermal_process_data(om, cfg, dict(kT=a["kT"], em=a["em"]),
+                                                 np.random.RandomState(seed), method=meth, literal_q3=True)
+        out.update({f"t2_{meth}_nph": nph, f"t2_{meth}_idx": idx, f"t2_{meth}_e": e})
+
+    a = I["pion"]
+    cie_T, cc, cm, cv = a["cie"]
+    ocie = O.TableModel(a["ebins"], cie_T, cc, cm, cv, logT=True, binscale="log")
+    pm = O.PionModel(a["ebins"], a["Tv"], a["Dv"], a["c2"], a["m2"], a["v2"], ocie, binscale="log")
+    c, m, v = pm.get_spectrum(a["kT"][:40], a["nH"][:40])
+    out.update(pion_c=c, pion_m=m, pion_v=v)
+    cfg = dict(kT_min=1e-3, kT_max=64.0, Zmet=0.3, spectral_norm=a["norm"],
+               var_elem=[(0.4, 1.0, False), (1.1, 1.0, False)])
+    nc, nph, idx, e = O.thermal_process_data(pm, cfg, dict(kT=a["kT"], em=a["em"], nH=a["nH"]),
+                                             np.random.RandomState(14))
+    out.update(pion_nph=nph, pion_idx=idx, pion_e=e)
+
+    a = I["pl"]
+    cfg = dict(e0=1.0, emin=0.5, emax=40.0, spectral_norm=a["norm"], scale_factor=1.0 / (1.0 + a["z"]))
+    nc, nph, act, e = O.powerlaw_process_data(cfg, a["lum"], a["alpha"], np.random.RandomState(15))
+    out.update(pl_nph=nph, pl_act=act, pl_e=e)
+    nc, nph, act, e = O.powerlaw_process_data(cfg, a["lum"], 1.7, np.random.RandomState(16))
+    out.update(plc_nph=nph, plc_act=act, plc_e=e)
+
+    a = I["ln"]
+    cfg = dict(e0=3.5, spectral_norm=a["norm"], scale_factor=1.0 / (1.0 + a["z"]))
+    nc, nph, act, e, F = O.line_process_data(cfg, a["rate"], a["sig_kms"] * 3.5 / 299792.458,
+                                             np.random.RandomState(17))
+    out.update(ln_nph=nph, ln_act=act, ln_e=e)
+
+    ab = I["abs"]
+    am = O.TableAbsorb(0.15, ab["energy"], ab["sigma"])
+    ee = I["plist"]["energy"][:500]
+    out.update(abs_trans=am.get_absorb(ee), abs_det=am.absorb_photons(ee, np.random.RandomState(18)))
+    d = I["plist"]
+    for name, case in cases.items():
+        ext = case["obs"] == "external"
+        params = dict(data_type=case["data_type"], observer=case["obs"], fid_d_a=200.0 if ext else 0.0,
+                      fid_redshift=0.05 if ext else 0.0)
+        akw = dict(absorb_model=O.TableAbsorb(0.15, ab["energy"], ab["sigma"]), nH=0.15) \
+            if case.get("absorb", True) else {}
+        ref = O.project_photons({k: v.copy() for k, v in d.items()}, params, case["normal"], [30.0, 45.0],
+                                np.random.RandomState(case["seed"]), **akw, **case["kw"])
+        out[f"pj_{name}_n"] = ref["n_events"]
+        for k in ("xsky", "ysky", "eobs"):
+            out[f"pj_{name}_{k}"] = ref[k]
+        if case["kw"].get("save_los"):
+            out[f"pj_{name}_los"] = ref["los"]
+        flux = ref["flux_sum"]
+        flux *= O.erg_per_keV / 1.0e5 / 1000.0
+        out[f"pj_{name}_flux"], out[f"pj_{name}_emin"], out[f"pj_{name}_emax"] = flux, ref["emin"], ref["emax"]
+    return out
+
+
+def _load_make_reference_golden():
+    import importlib.util
+
+    spec = importlib.util.spec_from_file_location(
+        "make_reference_golden", os.path.join(HERE, "golden", "make_reference_golden.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def test_restatement_matches_reference_python_bit_for_bit(oracle):
+    """tests/golden/reference_golden.npz holds outputs of the reference's OWN Python
+    (ThermalSourceModel.process_data, PionSpectralModel.get_spectrum, PowerLaw/Line
+    process_data, AbsorptionModel.absorb_photons, _project_photons) run with the same
+    RandomState seeds.  The NumPy restatement must reproduce every array exactly: photon
+    counts, cell indices, energies, absorption masks, sky positions, fluxes."""
+    mrg = _load_make_reference_golden()
+    stored = np.load(os.path.join(HERE, "golden", "reference_golden.npz"))
+    got = _replay_reference_cases(oracle, mrg.inputs(), mrg.PROJ_CASES)
+    assert sorted(got) == sorted(stored.files)
+    for k in stored.files:
+        a, b = np.asarray(got[k]), stored[k]
+        assert a.shape == b.shape, k
+        assert np.array_equal(a, b), (k, float(np.max(np.abs(a.astype(float) - b.astype(float)))))
+
+
+def test_reference_golden_is_reproducible_from_the_reference_tree():
+    """When the reference tree is present (build container) re-run its code and compare with
+    the committed fixtures; skipped on the GPU box where /root/reference does not exist."""
+    if not os.path.isdir("/root/reference/pyxsim"):
+        pytest.skip("reference tree not available")
+    mrg = _load_make_reference_golden()
+    fresh = mrg.run_reference(mrg.inputs())
+    stored = np.load(os.path.join(HERE, "golden", "reference_golden.npz"))
+    assert sorted(fresh) == sorted(stored.files)
+    for k in stored.files:
+        assert np.array_equal(np.asarray(fresh[k]), stored[k]), k

@@ -54,7 +54,7 @@ def test_beta_model_end_to_end_vs_oracle(cuda, oracle):
         d = dict(g, num_photons=nph, energy=e)
         params = dict(data_type="cells", observer="external", fid_d_a=D_A, fid_redshift=z)
         ref = oracle.project_photons(d, params, "z", [30.0, 45.0], np.random.RandomState(seed_ref + 1),
-                                     absorb_model=oracle.TableAbsorb(0.02, en, sg), nH=0.02)
+                                     absorb_model=oracle.TableAbsorb(0.02, en, sg * 1.0e22), nH=0.02)
         frac_m, frac_r = n_ev / n_ph, ref["n_events"] / nph.sum()
         assert abs(frac_m - frac_r) < 5 * np.sqrt(2 * frac_r * (1 - frac_r) / nph.sum())
         return {"energy": stats.ks_2samp(ph.numpy("energy"), e).pvalue,

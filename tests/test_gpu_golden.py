@@ -58,3 +58,67 @@ def test_golden_doppler_tan_absorb_powerlaw(cuda):
     model.setup_model("photons", src, 0.5)
     lam, _ = model.expected_counts(next(src.chunks()), 3e-44)
     np.testing.assert_allclose(lam.cpu().numpy(), G["pl_lam"], rtol=1e-12)
+
+
+def _reference_inputs():
+    import importlib.util
+
+    here = os.path.dirname(os.path.abspath(__file__))
+    spec = importlib.util.spec_from_file_location("mrg", os.path.join(here, "golden", "make_reference_golden.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod.inputs(), np.load(os.path.join(here, "golden", "reference_golden.npz"))
+
+
+def test_gpu_against_reference_python_outputs(cuda):
+    """Deterministic quantities against tests/golden/reference_golden.npz, i.e. against outputs
+    of the reference's own Python code: Pion (kT, nH) spectra bit for bit, table transmission
+    1e-12, Doppler-shifted energies and LOS of an unabsorbed projection, photon statistics of
+    the reference's Poisson draws against the GPU's expected counts."""
+    from pyxsim_b200.photon_list import DeviceList, save_list, load_list
+
+    I, R = _reference_inputs()
+    # --- Pion spectra ------------------------------------------------------------------
+    a = I["pion"]
+    cie_T, cc, cm, cv = a["cie"]
+    cie = px.ThermalSpectralModel(a["ebins"], cie_T, cc, cm, cv, logT=True, binscale="log")
+    pm = px.PionSpectralModel(a["ebins"], a["Tv"], a["Dv"], a["c2"], a["m2"], a["v2"], cie_model=cie,
+                              binscale="log")
+    pm.prepare_spectrum(0.0)
+    c, m, v = pm.get_spectrum(a["kT"][:40], a["nH"][:40])
+    assert np.array_equal(c, R["pion_c"]) and np.array_equal(m, R["pion_m"]) and np.array_equal(v, R["pion_v"])
+    # --- expected counts vs the reference's Poisson draws ------------------------------------
+    src = H.cells_source(a["kT"], a["em"], extra={("gas", "H_nuclei_density"): a["nH"]})
+    model = px.PionSourceModel(0.3, 1.4, pm.nbins, 0.3, binscale="log", temperature_field=("gas", "kT"),
+                               var_elem={"O": 0.4, "Ne": 1.1}, spectral_model=pm, prng=3, kT_min=1e-3)
+    model.setup_model("photons", src, 0.0)
+    lam, _ = model.expected_counts(next(src.chunks()), a["norm"])
+    lam = lam.cpu().numpy()
+    ref_counts = np.zeros(lam.size)
+    ref_counts[R["pion_idx"]] = R["pion_nph"]
+    chi2 = ((ref_counts - lam) ** 2 / np.maximum(lam, 1e-300))[lam > 5].sum()
+    ndf = (lam > 5).sum()
+    assert ndf > 30 and abs(chi2 - ndf) < 5 * np.sqrt(2 * ndf)
+    assert abs(ref_counts.sum() - lam.sum()) < 5 * np.sqrt(lam.sum())
+    # --- transmission -----------------------------------------------------------------------------
+    ab = I["abs"]
+    am = px.AbsorptionModel(0.15, ab["energy"], ab["sigma"])
+    np.testing.assert_allclose(am.get_absorb(I["plist"]["energy"][:500]), R["abs_trans"], rtol=1e-12)
+    # --- unabsorbed projections: Doppler energies (and LOS) are deterministic --------------------
+    d = I["plist"]
+    for name, obs, da, z in (("doppler_only", "external", 200.0, 0.05), ("doppler_internal", "internal", 0.0, 0.0)):
+        params = dict(fid_exp_time=1.0e5, fid_area=1000.0, fid_redshift=z, fid_d_a=da, data_type="cells",
+                      observer=obs)
+        save_list("mem:refgold", DeviceList({}, params, {k: torch.from_numpy(v).cuda() for k, v in d.items()}))
+        if obs == "external":
+            n = px.project_photons("mem:refgold", "mem:refgold_ev", [0.3, -0.5, 0.8], [30.0, 45.0],
+                                   save_los=True, prng=1)
+        else:
+            n = px.project_photons_allsky("mem:refgold", "mem:refgold_ev", [0.3, -0.5, 0.8], prng=1)
+        ev = load_list("mem:refgold_ev")
+        assert n == int(R[f"pj_{name}_n"]) == d["energy"].size
+        np.testing.assert_allclose(ev.numpy("eobs"), R[f"pj_{name}_eobs"], rtol=4e-16, atol=0)
+        np.testing.assert_allclose(ev.parameters["flux"], float(R[f"pj_{name}_flux"]), rtol=1e-13)
+        assert ev.parameters["emin"] == float(R[f"pj_{name}_emin"])
+        if obs == "external":
+            np.testing.assert_allclose(ev.numpy("los"), R[f"pj_{name}_los"], rtol=1e-12, atol=1e-11)  # FMA vs mul+add

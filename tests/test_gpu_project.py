@@ -94,7 +94,7 @@ def test_absorb_transmission(cuda, oracle, kind):
         elif kind == "table_irregular":
             keep = np.sort(rng.choice(en.size, 1500, replace=False))
             en, sg = en[keep], sg[keep]
-        prod, orc = px.TBabsModel(0.07, energy=en, cross_section=sg), oracle.TableAbsorb(0.07, en, sg)
+        prod, orc = px.TBabsModel(0.07, energy=en, cross_section=sg), oracle.TableAbsorb(0.07, en, sg * 1.0e22)
     np.testing.assert_allclose(prod.get_absorb(e), orc.get_absorb(e), rtol=1e-12, atol=1e-300)
 
 
@@ -157,7 +157,7 @@ def test_scatter_and_absorb_distributions(cuda, oracle, case):
                                nH=0.15, save_los=True, prng=seed_mine, **case)
         ev, par = events("sc_ev")
         ref = oracle.project_photons(d, p, normal, [30.0, 45.0], np.random.RandomState(seed_ref),
-                                     absorb_model=oracle.TableAbsorb(0.15, en, sg), nH=0.15,
+                                     absorb_model=oracle.TableAbsorb(0.15, en, sg * 1.0e22), nH=0.15,
                                      save_los=True, **case)
         assert 0.2 * ntot < n < 0.98 * ntot
         pbar = 0.5 * (n + ref["n_events"]) / ntot
@@ -227,7 +227,7 @@ def test_internal_absorption_per_cell(cuda, oracle):
                            nH_cell=nhc, prng=12)
     ev, _ = events("ia_ev")
     ref = oracle.project_photons(d, p, "z", [30.0, 45.0], np.random.RandomState(2),
-                                 absorb_model=oracle.TableAbsorb(0.02, en, sg), nH=0.02, nH_int=nhc)
+                                 absorb_model=oracle.TableAbsorb(0.02, en, sg * 1.0e22), nH=0.02, nH_int=nhc)
     assert abs(n - ref["n_events"]) < 6 * np.sqrt(ref["n_events"])
     assert _ks_ok(ev["eobs"], ref["eobs"])
 
