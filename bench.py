@@ -269,7 +269,7 @@ def run_ours(args):
     if dominant:
         achieved = alg[dominant] / (stage_ms[dominant] * 1e-3) / 1e9
         roofline = {"bound": "hbm", "kernel": {"thermal_sample": "k_thermal_sample_cta",
-                                               "project": "k_project_photons"}.get(dominant, dominant),
+                                               "project": "pxb_project: k_project_detect + scan + k_project_emit"}.get(dominant, dominant),
                     "achieved": round(achieved, 2), "peak": peak_gbs, "unit": "GB/s",
                     "frac": round(achieved / peak_gbs, 4), "traffic": None,
                     "peak_source": peak_src, "ms_per_launch": round(stage_ms[dominant], 3),
