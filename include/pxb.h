@@ -97,6 +97,8 @@ typedef struct {
   double kT_lo, kT_hi, nH_lo, nH_hi; /* bounds of the primary 2-D table (use_igm mask) */
   const double* bin_edges;    /* host [nbins+1] */
   const double* emid;         /* host [nbins] */
+  const double* ebins;        /* host [nbins+1] linear bin edges in keV (== bin_edges unless
+                                 binscale_log); used by the spectrum / band entry points */
 } pxb_model_desc;
 
 typedef struct pxb_model pxb_model;
@@ -163,6 +165,36 @@ int pxb_thermal_sample(const pxb_model* model, const pxb_thermal_cells* cells,
                        void* workspace, int64_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------
+ * Spectrum / band modes ("next" row f1 of the scope table)
+ * ---------------------------------------------------------------------------------- */
+/* mode="spectrum" of ThermalSourceModel.process_data (base.py:453-460,494-495) fused with
+ * shift_spectrum (pyxsim/lib/spectra.pyx:67-93): spec_out[j] += sum over cells passing the
+ * cut of shift^3 * cell_nrm * (C(ebnew[j+1]/shift) - C(ebnew[j]/shift)), C = np.interp of the
+ * cell's cumulative clipped spectrum on the model's linear bin edges.  shift is per cell
+ * (device) or NULL (= 1).  ebnew: device [nnew+1]; spec_out: device [nnew], ACCUMULATED. */
+int pxb_thermal_spectrum(const pxb_model* model, const pxb_thermal_cells* cells,
+                         const double* shift, int64_t nnew, const double* ebnew,
+                         double* spec_out, void* stream);
+/* make_band (spectra.pyx:96-126) on the cell's clipped spectrum, times cell_nrm
+ * (base.py:497-500): out[i] = cell_nrm * shift^(3 + use_energy) * sum_j ener_j * spec_ij over
+ * the bins with ebins[j] >= emin/shift and ebins[j+1] <= emax/shift; 0 for cut cells. */
+int pxb_thermal_band(const pxb_model* model, const pxb_thermal_cells* cells, int use_energy,
+                     double emin, double emax, const double* shift, double* out, void* stream);
+/* power_law_spectrum (spectra.pyx:11-32): spec_out[j] += sum_i shift_i^2 K_i (emid_j/shift_i)^-alpha_i */
+int pxb_powerlaw_spectrum(int64_t ncell, const double* alpha, const double* K, const double* shift,
+                          int64_t nbins, const double* emid, double* spec_out, void* stream);
+/* line_spectrum (spectra.pyx:35-64): spec_out[j] += sum_i shift_i^2 N_i g((ee_j/shift_i - e0)/sigma_i)/sigma_i,
+ * g = np.interp on the tabulated unit Gaussian (gx ascending, device [ng]). */
+int pxb_line_spectrum(int64_t ncell, double e0, const double* sigma, const double* N,
+                      const double* shift, int64_t nbins, const double* ee, int64_t ng,
+                      const double* gx, const double* gpdf, double* spec_out, void* stream);
+
+/* Doppler factor per cell for the spectrum modes, SourceModel.compute_shift (sources.py:89-95):
+ * sqrt(1 - beta^2) / (1 - beta . n_hat); velocities in km/s, normal = host double[3]. */
+int pxb_shift_factor(int64_t n, const double* vx, const double* vy, const double* vz,
+                     const double* normal, double* out, void* stream);
+
+/* ------------------------------------------------------------------------------------
  * Counts -> offsets, active-cell compaction
  * ---------------------------------------------------------------------------------- */
 int pxb_scan_workspace_bytes(int64_t n, int64_t* bytes);
@@ -226,6 +258,9 @@ typedef struct {
   double scale_factor;
   uint64_t seed;
 } pxb_line_cells;
+
+/* K = L / K_fac and the per-cell alpha (power_law_sources.py:196-206), inputs of the spectrum mode */
+int pxb_powerlaw_norm(const pxb_powerlaw_cells* cells, double* K_out, double* alpha_out, void* stream);
 
 int pxb_line_counts(const pxb_line_cells* cells, double* lambda_out, int64_t* counts_out,
                     void* stream);

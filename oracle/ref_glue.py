@@ -249,6 +249,29 @@ def thermal_spectra(model, cfg, a):
     return cut, tot, lam
 
 
+def thermal_spectrum_mode(model, cfg, a, ebins_new, shift=None):
+    """mode="spectrum" of ThermalSourceModel.process_data (base.py:436-460,494-495): per 100-cell
+    tile ``spec += shift_spectrum(self.ebins, ebins, tot_spec, shift, cnm)`` with the compiled
+    reference routine (spectra.pyx:67-93).  ``shift``: per selected cell, default ones."""
+    cut, kT, cell_nrm, nH, metalZ, elemZ = thermal_select(cfg, a)
+    n = kT.size
+    spec = np.zeros(ebins_new.size - 1)
+    sh = np.ones(n) if shift is None else np.ascontiguousarray(shift, dtype="float64")
+    fn = ref()["spectra"].shift_spectrum
+    for b, e in _chunked(n):
+        if model._density_dependence:
+            cspec, mspec, vspec = model.get_spectrum(kT[b:e], nH[b:e])
+        else:
+            cspec, mspec, vspec = model.get_spectrum(kT[b:e])
+        t = cspec
+        t += metalZ[b:e, np.newaxis] * mspec
+        if elemZ is not None:
+            t += np.sum(elemZ[:, b:e, np.newaxis] * vspec, axis=0)
+        np.clip(t, 0.0, None, out=t)
+        spec += fn(model.ebins, ebins_new, t, np.ascontiguousarray(sh[b:e]), np.ascontiguousarray(cell_nrm[b:e]))
+    return spec
+
+
 def thermal_process_data(model, cfg, a, prng, method="invert_cdf", literal_q3=False):
     """The photons branch, base.py:427-524: returns (ncells, number_of_photons[active],
     idxs[active], energies) exactly like the reference (RandomState draw order included)."""

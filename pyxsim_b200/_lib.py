@@ -36,7 +36,7 @@ class ModelDesc(C.Structure):
         ("method", C.c_int32), ("reserved", C.c_int32),
         ("K_per_keV", C.c_double),
         ("kT_lo", C.c_double), ("kT_hi", C.c_double), ("nH_lo", C.c_double), ("nH_hi", C.c_double),
-        ("bin_edges", c_void_p), ("emid", c_void_p),
+        ("bin_edges", c_void_p), ("emid", c_void_p), ("ebins", c_void_p),
     ]
 
 
@@ -131,6 +131,17 @@ SIGNATURES = {
     "pxb_thermal_sample_workspace_bytes": (C.c_int, [C.c_int64, C.c_int64, _P(C.c_int64)]),
     "pxb_thermal_sample": (C.c_int, [c_void_p, _P(ThermalCells), C.c_int64, c_void_p, c_void_p,
                                      c_void_p, C.c_int64, c_void_p, c_void_p, C.c_int64, c_void_p]),
+    "pxb_thermal_spectrum": (C.c_int, [c_void_p, _P(ThermalCells), c_void_p, C.c_int64, c_void_p,
+                                       c_void_p, c_void_p]),
+    "pxb_thermal_band": (C.c_int, [c_void_p, _P(ThermalCells), C.c_int, C.c_double, C.c_double,
+                                   c_void_p, c_void_p, c_void_p]),
+    "pxb_powerlaw_spectrum": (C.c_int, [C.c_int64, c_void_p, c_void_p, c_void_p, C.c_int64, c_void_p,
+                                        c_void_p, c_void_p]),
+    "pxb_line_spectrum": (C.c_int, [C.c_int64, C.c_double, c_void_p, c_void_p, c_void_p, C.c_int64,
+                                    c_void_p, C.c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "pxb_shift_factor": (C.c_int, [C.c_int64, c_void_p, c_void_p, c_void_p, _P(C.c_double), c_void_p,
+                                   c_void_p]),
+    "pxb_powerlaw_norm": (C.c_int, [_P(PowerlawCells), c_void_p, c_void_p, c_void_p]),
     "pxb_scan_workspace_bytes": (C.c_int, [C.c_int64, _P(C.c_int64)]),
     "pxb_scan_counts": (C.c_int, [c_void_p, C.c_int64, c_void_p, c_void_p, c_void_p, c_void_p,
                                   C.c_int64, c_void_p]),

@@ -1,0 +1,322 @@
+// spectra.cu -- spectrum / band modes ("next" row f1): the reference's remaining native
+// routines (pyxsim/lib/spectra.pyx: shift_spectrum :67-93, make_band :96-126,
+// power_law_spectrum :11-32, line_spectrum :35-64), the thermal ones fused with the table
+// lookup + abundance combine + clip of ThermalSourceModel.process_data (base.py:453-460).
+#include "thermal.cuh"
+
+// total spectrum value of bin j for a cell (clipped at 0): base.py:456-460
+__device__ __forceinline__ double spec_bin(const CellMix& mx, double Z, const double* eZ, int nvar,
+                                           int j) {
+  const DevTable* t = mx.t;
+  const int nb = t->nbins;
+  double c = 0.0, m = 0.0;
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    if (r < mx.nr) {
+      const size_t o = (size_t)mx.row[r] * nb + j;
+      c += __ldg(t->cosmic + o) * mx.w[r];
+      m += __ldg(t->metal + o) * mx.w[r];
+    }
+  }
+  double tot = c + Z * m;
+  for (int k = 0; k < nvar; ++k) {
+    double v = 0.0;
+    const double* vt = t->var + (size_t)k * t->nrows * nb;
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+      if (r < mx.nr) v += __ldg(vt + (size_t)mx.row[r] * nb + j) * mx.w[r];
+    tot += eZ[k] * v;
+  }
+  return fmax(tot, 0.0);
+}
+
+// np.interp(x, xp, fp) with xp ascending in global memory and fp in shared memory
+__device__ __forceinline__ double interp_cum(double x, const double* __restrict__ xp,
+                                             const double* fp, int n) {
+  if (x <= __ldg(xp)) return fp[0];
+  if (x >= __ldg(xp + n - 1)) return fp[n - 1];
+  int lo = 0, hi = n - 1;  // xp[lo] <= x < xp[hi]
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (__ldg(xp + mid) <= x) lo = mid; else hi = mid;
+  }
+  const double x0 = __ldg(xp + lo), x1 = __ldg(xp + lo + 1);
+  const double slope = (fp[lo + 1] - fp[lo]) / (x1 - x0);
+  return slope * (x - x0) + fp[lo];
+}
+
+constexpr int SPEC_THREADS = 256;
+
+// persistent CTAs; each keeps a private accumulator of the regridded spectrum in shared memory
+__global__ void __launch_bounds__(SPEC_THREADS)
+k_thermal_spectrum(const DevModel M, const __grid_constant__ pxb_thermal_cells C,
+                   const double* __restrict__ shift, int nnew, const double* __restrict__ ebnew,
+                   double* __restrict__ spec_out) {
+  extern __shared__ double smem[];
+  const int nbins = M.nbins;
+  double* cum = smem;                      // nbins + 1
+  double* acc = cum + (nbins + 1);         // nnew
+  double* s_eZ = acc + nnew;               // PXB_MAX_VAR
+  double* s_wtot = s_eZ + PXB_MAX_VAR;     // warps
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  constexpr int NW = SPEC_THREADS / 32;
+  const int seg = ((nbins + NW - 1) / NW + 31) & ~31;
+  for (int j = threadIdx.x; j < nnew; j += blockDim.x) acc[j] = 0.0;
+  for (int64_t i = blockIdx.x; i < C.ncell; i += gridDim.x) {
+    const double kT = C.kT[i];
+    if (!cell_cut(C, i, kT)) continue;                  // uniform across the CTA
+    const double nH = C.nH ? C.nH[i] : 0.0;
+    CellMix mx;
+    cell_mix(M, kT, nH, mx);
+    const double xh = cell_xh(C, i);
+    const double Z = cell_metal(C, i, xh);
+    __syncthreads();
+    for (int k = threadIdx.x; k < C.nvar; k += blockDim.x) s_eZ[k] = cell_elem(C, k, i, xh);
+    if (threadIdx.x == 0) cum[0] = 0.0;
+    __syncthreads();
+    const int j0 = wid * seg, j1 = min(j0 + seg, nbins);
+    double carry = 0.0;
+    for (int jb = j0; jb < j1; jb += 32) {
+      const int j = jb + lane;
+      double v = (j < j1) ? spec_bin(mx, Z, s_eZ, C.nvar, j) : 0.0;
+      v = warp_incl_scan(v, lane) + carry;
+      if (j < j1) cum[j + 1] = v;
+      carry = __shfl_sync(0xffffffffu, v, 31);
+    }
+    if (lane == 0) s_wtot[wid] = carry;
+    __syncthreads();
+    double basev = 0.0;
+    for (int w = 0; w < wid; ++w) basev += s_wtot[w];
+    if (wid > 0)
+      for (int j = j0 + lane; j < j1; j += 32) cum[j + 1] += basev;
+    __syncthreads();
+    const double s = shift ? shift[i] : 1.0;
+    const double wgt = s * s * s * cell_norm(C, i);
+    const double inv_s = 1.0 / s;
+    for (int j = threadIdx.x; j < nnew; j += blockDim.x) {
+      // ebnew / shift as in the reference (a division, not a multiplication by 1/shift)
+      const double a = interp_cum(__ldg(ebnew + j) / s, M.ebins, cum, nbins + 1);
+      const double b = interp_cum(__ldg(ebnew + j + 1) / s, M.ebins, cum, nbins + 1);
+      acc[j] += wgt * (b - a);
+    }
+    (void)inv_s;
+  }
+  __syncthreads();
+  for (int j = threadIdx.x; j < nnew; j += blockDim.x)
+    if (acc[j] != 0.0) atomicAdd(spec_out + j, acc[j]);
+}
+
+// make_band: one warp per cell
+__global__ void __launch_bounds__(256)
+k_thermal_band(const DevModel M, const __grid_constant__ pxb_thermal_cells C, int use_energy,
+               double emin, double emax, const double* __restrict__ shift,
+               double* __restrict__ out) {
+  __shared__ double s_eZ[8][PXB_MAX_VAR];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (i >= C.ncell) return;
+  const double kT = C.kT[i];
+  if (!cell_cut(C, i, kT)) {
+    if (lane == 0) out[i] = 0.0;
+    return;
+  }
+  const double nH = C.nH ? C.nH[i] : 0.0;
+  CellMix mx;
+  cell_mix(M, kT, nH, mx);
+  const double xh = cell_xh(C, i);
+  const double Z = cell_metal(C, i, xh);
+  for (int k = lane; k < C.nvar; k += 32) s_eZ[wib][k] = cell_elem(C, k, i, xh);
+  __syncwarp();
+  const double s = shift ? shift[i] : 1.0;
+  const double lo = emin / s, hi = emax / s;
+  double sum = 0.0;
+  for (int j = lane; j < M.nbins; j += 32) {
+    if (__ldg(M.ebins + j) >= lo && __ldg(M.ebins + j + 1) <= hi) {
+      const double ener = use_energy ? __ldg(M.emid + j) : 1.0;
+      sum += ener * spec_bin(mx, Z, s_eZ[wib], C.nvar, j);
+    }
+  }
+  sum = warp_sum(sum);
+  if (lane == 0) {
+    double sh = s * s * s;
+    if (use_energy) sh *= s;
+    out[i] = sh * sum * cell_norm(C, i);
+  }
+}
+
+// power_law_spectrum / line_spectrum: CTA = 256 bins x a slab of cells, register accumulators
+constexpr int SLAB = 4096;
+
+__global__ void __launch_bounds__(256)
+k_powerlaw_spectrum(int64_t ncell, const double* __restrict__ alpha, const double* __restrict__ K,
+                    const double* __restrict__ shift, int64_t nbins,
+                    const double* __restrict__ emid, double* __restrict__ spec_out) {
+  const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t i0 = (int64_t)blockIdx.y * SLAB, i1 = min(i0 + (int64_t)SLAB, ncell);
+  const double em = j < nbins ? emid[j] : 1.0;
+  double acc = 0.0;
+  for (int64_t i = i0; i < i1; ++i) {
+    const double s = shift ? __ldg(shift + i) : 1.0;
+    acc += s * s * __ldg(K + i) * pow(em / s, -__ldg(alpha + i));   // spectra.pyx:30
+  }
+  if (j < nbins && acc != 0.0) atomicAdd(spec_out + j, acc);
+}
+
+__global__ void __launch_bounds__(256)
+k_line_spectrum(int64_t ncell, double e0, const double* __restrict__ sigma,
+                const double* __restrict__ N, const double* __restrict__ shift, int64_t nbins,
+                const double* __restrict__ ee, int64_t ng, const double* __restrict__ gx,
+                const double* __restrict__ gpdf, double* __restrict__ spec_out) {
+  const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t i0 = (int64_t)blockIdx.y * SLAB, i1 = min(i0 + (int64_t)SLAB, ncell);
+  const double e = j < nbins ? ee[j] : 0.0;
+  const double g0 = __ldg(gx), g1 = __ldg(gx + ng - 1);
+  const double inv_dg = (double)(ng - 1) / (g1 - g0);
+  double acc = 0.0;
+  for (int64_t i = i0; i < i1; ++i) {
+    const double s = shift ? __ldg(shift + i) : 1.0;
+    const double sg = __ldg(sigma + i);
+    const double x = (e / s - e0) / sg;                            // spectra.pyx:59
+    double r;                                                       // np.interp(x, gx, gpdf)
+    if (x <= g0) r = __ldg(gpdf);
+    else if (x >= g1) r = __ldg(gpdf + ng - 1);
+    else {
+      int64_t k = (int64_t)((x - g0) * inv_dg);                    // gx is np.linspace: direct index
+      k = k < 0 ? 0 : (k > ng - 2 ? ng - 2 : k);
+      if (k > 0 && __ldg(gx + k) > x) --k;
+      else if (k < ng - 2 && __ldg(gx + k + 1) <= x) ++k;
+      const double x0 = __ldg(gx + k), x1 = __ldg(gx + k + 1);
+      const double slope = (__ldg(gpdf + k + 1) - __ldg(gpdf + k)) / (x1 - x0);
+      r = slope * (x - x0) + __ldg(gpdf + k);
+    }
+    acc += s * s * __ldg(N + i) * r / sg;                           // spectra.pyx:62
+  }
+  if (j < nbins && acc != 0.0) atomicAdd(spec_out + j, acc);
+}
+
+// compute_shift (sources.py:89-95): sqrt(1 - beta^2) / (1 - beta_n), beta_n = v . n / c
+__global__ void __launch_bounds__(256)
+k_shift_factor(int64_t n, const double* __restrict__ vx, const double* __restrict__ vy,
+               const double* __restrict__ vz, double nx, double ny, double nz,
+               double* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double c = 299792.458;
+  const double bx = vx[i] / c, by = vy[i] / c, bz = vz[i] / c;
+  const double bn = bx * nx + by * ny + bz * nz;
+  const double b2 = bx * bx + by * by + bz * bz;
+  out[i] = sqrt(1.0 - b2) / (1.0 - bn);
+}
+
+extern "C" int pxb_shift_factor(int64_t n, const double* vx, const double* vy, const double* vz,
+                                const double* normal, double* out, void* stream) {
+  PXB_REQUIRE(n >= 0 && normal, "bad argument");
+  if (n == 0) return PXB_OK;
+  PXB_REQUIRE(vx && vy && vz && out, "NULL argument");
+  const double nn = sqrt(normal[0] * normal[0] + normal[1] * normal[1] + normal[2] * normal[2]);
+  PXB_REQUIRE(nn > 0.0, "zero normal vector");
+  k_shift_factor<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      n, vx, vy, vz, normal[0] / nn, normal[1] / nn, normal[2] / nn, out);
+  PXB_LAUNCH_CHECK();
+  return PXB_OK;
+}
+
+// K = L / K_fac of the power-law model (power_law_sources.py:196-206)
+__global__ void __launch_bounds__(256)
+k_powerlaw_K(const __grid_constant__ pxb_powerlaw_cells C, double* __restrict__ K_out,
+             double* __restrict__ alpha_out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= C.ncell) return;
+  const double alpha = C.alpha ? C.alpha[i] : C.alpha_const;
+  const double etoalpha = pow(C.e0, alpha);
+  double kfac;
+  if (alpha == 2.0) kfac = log(C.emax / C.emin) * etoalpha;
+  else kfac = (pow(C.emax, 2.0 - alpha) - pow(C.emin, 2.0 - alpha)) * etoalpha / (2.0 - alpha);
+  K_out[i] = C.lum[i] / kfac;
+  alpha_out[i] = alpha;
+}
+
+extern "C" int pxb_powerlaw_norm(const pxb_powerlaw_cells* cells, double* K_out, double* alpha_out,
+                              void* stream) {
+  PXB_REQUIRE(cells && cells->ncell >= 0, "bad argument");
+  if (cells->ncell == 0) return PXB_OK;
+  PXB_REQUIRE(cells->lum && K_out && alpha_out, "NULL argument");
+  k_powerlaw_K<<<(unsigned)((cells->ncell + 255) / 256), 256, 0, (cudaStream_t)stream>>>(*cells, K_out, alpha_out);
+  PXB_LAUNCH_CHECK();
+  return PXB_OK;
+}
+
+static int check_model_cells(const pxb_model* model, const pxb_thermal_cells* c) {
+  PXB_REQUIRE(model && c, "NULL model/cells");
+  PXB_REQUIRE(c->nvar == model->dev.nvar, "cells.nvar=%d does not match the table's nvar=%d",
+              c->nvar, model->dev.nvar);
+  PXB_REQUIRE(c->ncell == 0 || (c->kT && c->em), "kT/em arrays are required");
+  PXB_REQUIRE(!model->dev.density_dependent || c->ncell == 0 || c->nH, "density dependent model needs nH");
+  return PXB_OK;
+}
+
+extern "C" int pxb_thermal_spectrum(const pxb_model* model, const pxb_thermal_cells* cells,
+                                    const double* shift, int64_t nnew, const double* ebnew,
+                                    double* spec_out, void* stream) {
+  int rc = check_model_cells(model, cells);
+  if (rc) return rc;
+  PXB_REQUIRE(nnew >= 1 && ebnew && spec_out, "bad output grid");
+  if (cells->ncell == 0) return PXB_OK;
+  const size_t smem = ((size_t)model->dev.nbins + 1 + nnew + PXB_MAX_VAR + SPEC_THREADS / 32) * sizeof(double);
+  PXB_REQUIRE(smem <= 227 * 1024, "nbins + output bins = %lld needs %zu B of shared memory (max 227 KB)",
+              (long long)(model->dev.nbins + nnew), smem);
+  PXB_CUDA(cudaFuncSetAttribute(k_thermal_spectrum, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int per_sm = 0;
+  PXB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_thermal_spectrum, SPEC_THREADS, smem));
+  if (per_sm < 1) per_sm = 1;
+  int64_t grid = (int64_t)pxb_sm_count() * per_sm;
+  if (grid > cells->ncell) grid = cells->ncell;
+  k_thermal_spectrum<<<(unsigned)grid, SPEC_THREADS, smem, (cudaStream_t)stream>>>(
+      model->dev, *cells, shift, (int)nnew, ebnew, spec_out);
+  PXB_LAUNCH_CHECK();
+  return PXB_OK;
+}
+
+extern "C" int pxb_thermal_band(const pxb_model* model, const pxb_thermal_cells* cells, int use_energy,
+                                double emin, double emax, const double* shift, double* out,
+                                void* stream) {
+  int rc = check_model_cells(model, cells);
+  if (rc) return rc;
+  if (cells->ncell == 0) return PXB_OK;
+  PXB_REQUIRE(out, "out is NULL");
+  const int64_t nwarp = cells->ncell;
+  const int64_t blocks = (nwarp + 7) / 8;
+  PXB_REQUIRE(blocks < (1LL << 31), "too many cells for one call");
+  k_thermal_band<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(model->dev, *cells, use_energy,
+                                                                    emin, emax, shift, out);
+  PXB_LAUNCH_CHECK();
+  return PXB_OK;
+}
+
+extern "C" int pxb_powerlaw_spectrum(int64_t ncell, const double* alpha, const double* K,
+                                     const double* shift, int64_t nbins, const double* emid,
+                                     double* spec_out, void* stream) {
+  PXB_REQUIRE(ncell >= 0 && nbins >= 1, "bad sizes");
+  if (ncell == 0) return PXB_OK;
+  PXB_REQUIRE(alpha && K && emid && spec_out, "NULL argument");
+  const dim3 grid((unsigned)((nbins + 255) / 256), (unsigned)((ncell + SLAB - 1) / SLAB));
+  PXB_REQUIRE(grid.y <= 65535, "too many cells for one call (max %d)", 65535 * SLAB);
+  k_powerlaw_spectrum<<<grid, 256, 0, (cudaStream_t)stream>>>(ncell, alpha, K, shift, nbins, emid, spec_out);
+  PXB_LAUNCH_CHECK();
+  return PXB_OK;
+}
+
+extern "C" int pxb_line_spectrum(int64_t ncell, double e0, const double* sigma, const double* N,
+                                 const double* shift, int64_t nbins, const double* ee, int64_t ng,
+                                 const double* gx, const double* gpdf, double* spec_out,
+                                 void* stream) {
+  PXB_REQUIRE(ncell >= 0 && nbins >= 1 && ng >= 2, "bad sizes");
+  if (ncell == 0) return PXB_OK;
+  PXB_REQUIRE(sigma && N && ee && gx && gpdf && spec_out, "NULL argument");
+  const dim3 grid((unsigned)((nbins + 255) / 256), (unsigned)((ncell + SLAB - 1) / SLAB));
+  PXB_REQUIRE(grid.y <= 65535, "too many cells for one call (max %d)", 65535 * SLAB);
+  k_line_spectrum<<<grid, 256, 0, (cudaStream_t)stream>>>(ncell, e0, sigma, N, shift, nbins, ee, ng, gx,
+                                                         gpdf, spec_out);
+  PXB_LAUNCH_CHECK();
+  return PXB_OK;
+}

@@ -156,6 +156,8 @@ extern "C" int pxb_model_create(const pxb_model_desc* desc, pxb_model** out) {
     D.kT_lo = desc->kT_lo; D.kT_hi = desc->kT_hi; D.nH_lo = desc->nH_lo; D.nH_hi = desc->nH_hi;
     rc = upload(m, desc->bin_edges, (D.nbins + 1) * sizeof(double), (const void**)&D.edges);
     if (!rc) rc = upload(m, desc->emid, D.nbins * sizeof(double), (const void**)&D.emid);
+    if (!rc) rc = upload(m, desc->ebins ? desc->ebins : desc->bin_edges, (D.nbins + 1) * sizeof(double),
+                         (const void**)&D.ebins);
     D.fast_ok = D.prim.rowcdf != nullptr && (!D.has_fb || D.fb.rowcdf != nullptr);
     {
       const double* eb = desc->bin_edges;

@@ -37,7 +37,8 @@ struct DevModel {
   int nbins, nvar;
   double K_per_keV;
   double kT_lo, kT_hi, nH_lo, nH_hi;
-  const double* edges;    // [nbins+1]
+  const double* edges;    // [nbins+1] (log10 when binscale_log)
+  const double* ebins;    // [nbins+1] linear keV
   const double* emid;     // [nbins]
   int fast_ok;            // mixture sampler usable (nonneg tables, nbins < 65536)
   int edges_uniform;      // edges[j] == edge0 + j*dedge (to rounding): computed, not loaded

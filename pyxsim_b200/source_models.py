@@ -81,13 +81,17 @@ class SourceModel:
     def cleanup_model(self, mode):
         self._scan_ws = None
 
-    def process_data(self, mode, chunk, spectral_norm, **kwargs):
+    def process_data(self, mode, chunk, spectral_norm, ebins=None, emin=None, emax=None, fluxf=None,
+                     shifting=False):
         """Reference contract (photon_list.py:402-405): ``None`` or ``(ncells_active,
-        number_of_photons[int64], idxs, energies[float64 keV])`` as NumPy arrays."""
+        number_of_photons[int64], idxs, energies[float64 keV])`` as NumPy arrays for
+        ``mode="photons"``; ``mode="spectrum"`` returns the chunk's spectrum on ``ebins``."""
+        if mode == "spectrum":
+            return self._spectrum_chunk(chunk, spectral_norm, np.asarray(ebins, "float64"), shifting)
         if mode != "photons":
             raise NotImplementedError(
-                f"pyxsim_b200 accelerates mode='photons' only (got {mode!r}); spectrum/intensity "
-                "modes are not part of the photon hot path")
+                f"pyxsim_b200 implements mode='photons' and mode='spectrum' (got {mode!r}); the "
+                "per-cell field modes are not part of the photon hot path")
         out = self.generate_chunk(chunk, spectral_norm)
         if out is None:
             return None
@@ -169,6 +173,68 @@ class SourceModel:
 
     def generate_chunk(self, chunk, spectral_norm, gather=None):
         raise NotImplementedError
+
+    # -- spectrum mode ("next" row f1) --------------------------------------------------------
+    def _spectrum_chunk(self, chunk, spectral_norm, ebins, shifting):
+        raise NotImplementedError
+
+    def compute_shift(self, chunk):
+        """Per-cell Doppler factor sqrt(1-beta^2)/(1-beta_n) along ``self._spec_normal``
+        (sources.py:89-95), device tensor."""
+        vf = self.v_fields or [(self.ftype, f"velocity_{ax}") for ax in "xyz"]
+        v = [to_device(field_value(chunk, f, "km/s")) for f in vf]
+        out = empty(v[0].numel())
+        nrm = (C.c_double * 3)(*[float(x) for x in self._spec_normal])
+        _lib.call("pxb_shift_factor", v[0].numel(), ptr(v[0]), ptr(v[1]), ptr(v[2]), nrm, ptr(out),
+                  stream_ptr())
+        return out
+
+    def make_spectrum(self, data_source, emin, emax, nbins, redshift=0.0, dist=None, cosmology=None,
+                      normal=None):
+        """Spectrum of all the data in ``data_source`` (thermal base.py:231-299, power law
+        :93-158, line sources alike): returns ``(ebins, spec)`` -- a count-rate spectrum
+        [photons/s/keV] in the source frame, or, with ``redshift``/``dist``, the observer-frame
+        flux spectrum [photons/s/cm^2/keV].  ``normal`` Doppler-shifts along that direction."""
+        from .data import Cosmology
+        from .photon_list import _chunks
+
+        require_cuda()
+        if isinstance(normal, str):
+            normal = "xyz".index(normal)
+        if isinstance(normal, (int, np.integer)):
+            nv = np.zeros(3)
+            nv[int(normal)] = 1.0
+            normal = nv
+        if normal is not None:
+            if redshift == 0.0 and dist is None:
+                raise RuntimeError("Cannot use a normal vector for the line-of-sight when a redshift "
+                                   "or the distance is not specified!")
+            self._spec_normal = np.asarray(normal, "float64")
+        shifting = normal is not None
+        emin, emax = parse_value(emin, "keV"), parse_value(emax, "keV")
+        self.setup_model("spectrum", data_source, redshift)
+        if isinstance(data_source, ArrayDataSource):
+            self.v_fields = data_source.velocity_fields
+        ebins = np.linspace(emin, emax, nbins + 1)
+        spec = np.zeros(nbins)
+        for chunk in _chunks(data_source):
+            out = self.process_data("spectrum", chunk, 1.0, ebins=ebins, shifting=shifting)
+            if out is not None:
+                spec += out
+        spec = self._finish_spectrum(ebins, spec)
+        self.cleanup_model("spectrum")
+        if redshift > 0.0 or dist is not None:
+            if dist is None:
+                cosmo = cosmology or getattr(data_source, "cosmology", None) or Cosmology()
+                d_l = cosmo.angular_diameter_distance_mpc(0.0, redshift) * (1.0 + redshift) ** 2 * K.cm_per_mpc
+            else:
+                redshift = 0.0
+                d_l = parse_value(dist, "kpc") * K.cm_per_kpc
+            spec = spec * (1.0 + redshift) ** 2 / (4.0 * np.pi * d_l * d_l)   # sources.py:132-135
+        return ebins, spec
+
+    def _finish_spectrum(self, ebins, spec):
+        return spec
 
 
 # =======================================================================================
@@ -378,6 +444,37 @@ class ThermalSourceModel(SourceModel):
         _lib.call("pxb_thermal_spectra", dm.handle, C.byref(Cs), ptr(spec), stream_ptr())
         return spec.reshape(Cs.ncell, self.nbins)
 
+    def _spectrum_chunk(self, chunk, spectral_norm, ebins, shifting):
+        """base.py:453-460,494-495 + shift_spectrum (spectra.pyx:67-93) in one kernel."""
+        require_cuda()
+        if self._chunk_size(chunk, self.temperature_field) == 0:
+            return None
+        keep = []
+        Cs = self._cells_struct(chunk, spectral_norm, keep)
+        dm = self.spectral_model.device_model(self.method)
+        shift = self.compute_shift(chunk) if shifting else None
+        eb = to_device(ebins)
+        spec = torch.zeros(ebins.size - 1, dtype=torch.float64, device=eb.device)
+        with stage("thermal_spectrum"):
+            _lib.call("pxb_thermal_spectrum", dm.handle, C.byref(Cs), ptr(shift), ebins.size - 1,
+                      ptr(eb), ptr(spec), stream_ptr())
+        return spec.cpu().numpy()
+
+    def _finish_spectrum(self, ebins, spec):
+        return spec / np.diff(ebins)      # base.py:297
+
+    def band_per_cell(self, chunk, spectral_norm, emin, emax, energy=False, shifting=False):
+        """make_band (spectra.pyx:96-126) times cell_nrm (base.py:497-500): per-cell band photon
+        rate (or energy rate) of the clipped spectrum, device tensor."""
+        keep = []
+        Cs = self._cells_struct(chunk, spectral_norm, keep)
+        dm = self.spectral_model.device_model(self.method)
+        shift = self.compute_shift(chunk) if shifting else None
+        out = empty(Cs.ncell)
+        _lib.call("pxb_thermal_band", dm.handle, C.byref(Cs), int(bool(energy)), C.c_double(emin),
+                  C.c_double(emax), ptr(shift), ptr(out), stream_ptr())
+        return out
+
     def generate_chunk(self, chunk, spectral_norm, gather=None):
         require_cuda()
         if self._chunk_size(chunk, self.temperature_field) == 0:
@@ -559,10 +656,27 @@ class PowerLawSourceModel(SourceModel):
                   ptr(out.poff), out.n_photons, ptr(out.energy), stream_ptr())
         return out
 
+    def _spectrum_chunk(self, chunk, spectral_norm, ebins, shifting):
+        """power_law_sources.py:264-270 + power_law_spectrum (spectra.pyx:11-32)."""
+        require_cuda()
+        if self._chunk_size(chunk, self.luminosity_field) == 0:
+            return None
+        keep = []
+        Cs = self._cells_struct(chunk, spectral_norm, keep)
+        Kc, alpha = empty(Cs.ncell), empty(Cs.ncell)
+        _lib.call("pxb_powerlaw_norm", C.byref(Cs), ptr(Kc), ptr(alpha), stream_ptr())
+        shift = self.compute_shift(chunk) if shifting else None
+        emid = 0.5 * (ebins[1:] + ebins[:-1]) * (1.0 / self.scale_factor) / self.e0
+        em = to_device(emid)
+        spec = torch.zeros(emid.size, dtype=torch.float64, device=em.device)
+        _lib.call("pxb_powerlaw_spectrum", Cs.ncell, ptr(alpha), ptr(Kc), ptr(shift), emid.size, ptr(em),
+                  ptr(spec), stream_ptr())
+        return spec.cpu().numpy()
+
     def process_data(self, mode, chunk, spectral_norm, **kwargs):
         res = super().process_data(mode, chunk, spectral_norm, **kwargs)
-        if res is None:
-            return None
+        if res is None or mode != "photons":
+            return res
         # the reference returns a boolean mask here (power_law_sources.py:242-250)
         ncells, nph, idx, energies = res
         mask = np.zeros(self._chunk_size(chunk, self.luminosity_field), dtype=bool)
@@ -647,10 +761,40 @@ class LineSourceModel(SourceModel):
                   ptr(out.poff), out.n_photons, ptr(out.energy), stream_ptr())
         return out
 
+    _gauss = None
+
+    def _spectrum_chunk(self, chunk, spectral_norm, ebins, shifting):
+        """line_sources.py:236-252 + line_spectrum (spectra.pyx:35-64); the unit Gaussian is the
+        reference's module-level table gx = linspace(-7, 7, 10000), gpdf = norm.pdf(gx)."""
+        require_cuda()
+        if self._chunk_size(chunk, self.emission_field) == 0:
+            return None
+        from scipy.stats import norm
+
+        if LineSourceModel._gauss is None:
+            gx = np.linspace(-7, 7, 10000)
+            LineSourceModel._gauss = (gx, norm.pdf(gx))
+        gx, gpdf = LineSourceModel._gauss
+        keep = []
+        Cs = self._cells_struct(chunk, spectral_norm, keep)
+        n = Cs.ncell
+        rate = keep[0]
+        if self.sigma_field is None:
+            sigma = torch.full((n,), float(self.sigma), dtype=torch.float64, device=rate.device)
+        else:
+            sigma = keep[1]
+        shift = self.compute_shift(chunk) if shifting else None
+        ee = 0.5 * (ebins[1:] + ebins[:-1]) / self.scale_factor
+        dee, dgx, dgp = to_device(ee), to_device(gx), to_device(gpdf)
+        spec = torch.zeros(ee.size, dtype=torch.float64, device=rate.device)
+        _lib.call("pxb_line_spectrum", n, C.c_double(self.e0), ptr(sigma), ptr(rate), ptr(shift), ee.size,
+                  ptr(dee), gx.size, ptr(dgx), ptr(dgp), ptr(spec), stream_ptr())
+        return spec.cpu().numpy()
+
     def process_data(self, mode, chunk, spectral_norm, **kwargs):
         res = super().process_data(mode, chunk, spectral_norm, **kwargs)
-        if res is None:
-            return None
+        if res is None or mode != "photons":
+            return res
         ncells, nph, idx, energies = res
         mask = np.zeros(self._chunk_size(chunk, self.emission_field), dtype=bool)
         mask[idx] = True

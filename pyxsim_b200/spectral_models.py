@@ -164,9 +164,11 @@ class ThermalSpectralModel:
             self._fill_desc(desc, keep)
             edges = _f64(self._bin_edges())
             emid = _f64(self.emid)
-            keep += [edges, emid]
+            lin = _f64(self.ebins)
+            keep += [edges, emid, lin]
             desc.bin_edges = edges.ctypes.data
             desc.emid = emid.ctypes.data
+            desc.ebins = lin.ctypes.data
             desc.binscale_log = int(self.binscale == "log")
             desc.method = {"invert_cdf": 0, "accept_reject": 1}[method]
             desc.K_per_keV = K.K_per_keV

@@ -133,6 +133,11 @@ def run_reference(I):
     nc, nph, idx, e = m.process_data("photons", chunk, a["norm"])
     out.update(t1_nc=nc, t1_nph=nph, t1_idx=idx, t1_e=np.asarray(e))
 
+    # spectrum mode of the same model (no Doppler shifting): base.py:494-495 + shift_spectrum
+    m.pbar = R.NoBar()
+    ebnew = np.linspace(0.3, 7.0, 41)
+    out.update(t1_spec=m.process_data("spectrum", chunk, a["norm"], ebins=ebnew, shifting=False))
+
     # ---- t2: log bins, both sampling methods -----------------------------------------------
     a = I["t2"]
     n = a["kT"].size

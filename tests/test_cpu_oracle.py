@@ -107,6 +107,8 @@ def _replay_reference_cases(O, I, cases):
     nc, nph, idx, e = O.thermal_process_data(
         om, cfg, dict(kT=a["kT"], em=a["em"], Z=a["Z"], Fe=a["Fe"], density=a["dens"]), np.random.RandomState(11))
     out.update(t1_nc=nc, t1_nph=nph, t1_idx=idx, t1_e=e)
+    out.update(t1_spec=O.thermal_spectrum_mode(
+        om, cfg, dict(kT=a["kT"], em=a["em"], Z=a["Z"], Fe=a["Fe"], density=a["dens"]), np.linspace(0.3, 7.0, 41)))
 
     a = I["t2"]
     t = a["tables"]

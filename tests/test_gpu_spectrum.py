@@ -1,0 +1,152 @@
+"""GPU parity for the spectrum / band modes ("next" row f1): libpxb against the reference's
+compiled native routines (pyxsim/lib/spectra.pyx: shift_spectrum, make_band,
+power_law_spectrum, line_spectrum) and against the reference's own Python output
+(tests/golden/reference_golden.npz, key t1_spec)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import pyxsim_b200 as px
+from pyxsim_b200 import synthetic
+
+import helpers as H
+
+pytestmark = pytest.mark.gpu
+TF = ("gas", "kT")
+
+
+def _setup(oracle, nbins=300, nvar=2, n=700, negative=False):
+    t = H.make_tables(nbins=nbins, nvar=nvar, negative=negative)
+    kT, em = H.random_cells(n, seed=4, kT_range=(0.02, 70.0))
+    src = H.cells_source(kT, em)
+    model = px.ThermalSourceModel(H.product_model(t), 0.1, 10.0, nbins, 0.3, temperature_field=TF,
+                                  var_elem={"O": 0.5, "Fe": 1.5} if nvar else None, prng=1)
+    model.setup_model("spectrum", src, 0.0)
+    model.v_fields = src.velocity_fields
+    cfg = dict(kT_min=0.025, kT_max=64.0, Zmet=0.3, spectral_norm=2e-44,
+               var_elem=[(0.5, 1.0, False), (1.5, 1.0, False)] if nvar else None)
+    return t, kT, em, src, model, cfg
+
+
+@pytest.mark.parametrize("negative", [False, True])
+def test_thermal_spectrum_and_band_vs_reference_cython(cuda, oracle, negative):
+    t, kT, em, src, model, cfg = _setup(oracle, negative=negative)
+    chunk = next(src.chunks())
+    om = H.oracle_model(oracle, t)
+    ebnew = np.linspace(0.25, 8.0, 201)
+    # no shifting
+    spec = model.process_data("spectrum", chunk, 2e-44, ebins=ebnew, shifting=False)
+    ref = oracle.thermal_spectrum_mode(om, cfg, dict(kT=kT, em=em), ebnew)
+    np.testing.assert_allclose(spec, ref, rtol=1e-11, atol=ref.max() * 1e-14)
+    # Doppler shifting along an off-axis direction
+    normal = np.array([0.3, -0.5, 0.8])
+    model._spec_normal = normal
+    spec_s = model.process_data("spectrum", chunk, 2e-44, ebins=ebnew, shifting=True)
+    v = np.stack([src.fields[f] for f in src.velocity_fields]) / 299792.458
+    nh = normal / np.linalg.norm(normal)
+    shift = np.sqrt(1.0 - (v ** 2).sum(0)) / (1.0 - nh @ v)
+    cut, tot, lam = oracle.thermal_spectra(om, cfg, dict(kT=kT, em=em))
+    ref_s = oracle.thermal_spectrum_mode(om, cfg, dict(kT=kT, em=em), ebnew, shift=shift[cut])
+    np.testing.assert_allclose(spec_s, ref_s, rtol=1e-11, atol=ref_s.max() * 1e-14)
+    assert not np.allclose(spec_s, spec, rtol=1e-6)
+    # make_band, both flavours, with and without shifting
+    emid = 0.5 * (t["ebins"][1:] + t["ebins"][:-1])
+    cnm = em[cut] * 2e-44
+    mb = oracle.ref()["spectra"].make_band
+    for use_energy in (0, 1):
+        for shifting in (False, True):
+            out = model.band_per_cell(chunk, 2e-44, 0.5, 7.0, energy=bool(use_energy), shifting=shifting)
+            sh = shift[cut] if shifting else np.ones(cut.sum())
+            refb = mb(use_energy, 0.5, 7.0, t["ebins"], emid, np.ascontiguousarray(tot), np.ascontiguousarray(sh)) * cnm
+            got = out.cpu().numpy()
+            np.testing.assert_allclose(got[cut], refb, rtol=1e-12, atol=refb.max() * 1e-15)
+            assert np.all(got[~cut] == 0)
+
+
+def test_thermal_spectrum_vs_reference_python(cuda):
+    """process_data(mode="spectrum") against the reference's own Python run (fixture t1_spec)."""
+    import importlib.util
+
+    here = os.path.dirname(os.path.abspath(__file__))
+    spec_ = importlib.util.spec_from_file_location("mrg", os.path.join(here, "golden", "make_reference_golden.py"))
+    mrg = importlib.util.module_from_spec(spec_)
+    spec_.loader.exec_module(mrg)
+    a = mrg.inputs()["t1"]
+    R = np.load(os.path.join(here, "golden", "reference_golden.npz"))
+    t = a["tables"]
+    src = H.cells_source(a["kT"], a["em"], extra={("gas", "Zf"): a["Z"], ("gas", "Fef"): a["Fe"],
+                                                  ("gas", "density"): a["dens"]})
+    src.units[("gas", "Zf")] = "dimensionless"
+    model = px.ThermalSourceModel(H.product_model(t), 0.1, 10.0, 64, ("gas", "Zf"), temperature_field=TF,
+                                  var_elem={"O": 0.5, "Fe": ("gas", "Fef")}, h_fraction=a["h_fraction"],
+                                  max_density=3e-26, prng=1)
+    model.setup_model("spectrum", src, 0.0)
+    model.Zconvert = a["Zconvert"]            # the fixture was generated with this conversion factor
+    spec = model.process_data("spectrum", next(src.chunks()), a["norm"], ebins=np.linspace(0.3, 7.0, 41))
+    np.testing.assert_allclose(spec, R["t1_spec"], rtol=1e-11, atol=R["t1_spec"].max() * 1e-14)
+
+
+def test_powerlaw_and_line_spectrum_vs_reference_cython(cuda, oracle):
+    sp = oracle.ref()["spectra"]
+    rng = np.random.RandomState(6)
+    n = 3000
+    alpha = rng.uniform(0.5, 2.5, n)
+    alpha[:50] = 1.0
+    alpha[50:100] = 2.0
+    lum = 1e40 * rng.lognormal(0, 1, n)
+    f = {("gas", "lum"): lum, ("gas", "alpha"): alpha, ("gas", "line"): 1e38 * rng.lognormal(0, 1, n),
+         ("gas", "sig"): rng.uniform(100.0, 2000.0, n), ("index", "x"): np.zeros(n), ("index", "y"): np.zeros(n),
+         ("index", "z"): np.zeros(n), ("gas", "velocity_x"): rng.normal(0, 800, n),
+         ("gas", "velocity_y"): rng.normal(0, 800, n), ("gas", "velocity_z"): rng.normal(0, 800, n)}
+    src = px.ArrayDataSource(f, units={("gas", "lum"): "keV/s"})
+    z = 0.3
+    sf = 1.0 / (1.0 + z)
+    normal = np.array([0.0, 0.6, 0.8])
+    v = np.stack([f[("gas", f"velocity_{ax}")] for ax in "xyz"]) / 299792.458
+    shift = np.sqrt(1.0 - (v ** 2).sum(0)) / (1.0 - normal @ v)
+
+    class Bar:
+        def update(self, *a):
+            pass
+
+    # power law
+    pl = px.PowerLawSourceModel(1.0, 0.5, 40.0, ("gas", "lum"), ("gas", "alpha"), prng=1)
+    eb, spec = pl.make_spectrum(src, 0.4, 30.0, 120, redshift=z, normal=normal)
+    K_fac = 40.0 ** (2.0 - alpha) - 0.5 ** (2.0 - alpha)
+    K_fac[alpha == 2] = np.log(40.0 / 0.5)
+    K_fac[alpha != 2] /= 2.0 - alpha[alpha != 2]
+    Kc = lum / K_fac
+    emid = 0.5 * (eb[1:] + eb[:-1]) * (1.0 / sf) / 1.0
+    ref = sp.power_law_spectrum(n, emid, alpha, Kc, shift, Bar())
+    d_l = px.Cosmology().angular_diameter_distance_mpc(0.0, z) * (1 + z) ** 2 * 3.0856775809623245e24
+    ref = ref * (1 + z) ** 2 / (4 * np.pi * d_l ** 2)
+    np.testing.assert_allclose(spec, ref, rtol=1e-11)
+    # line
+    ln = px.LineSourceModel(3.5, ("gas", "line"), ("gas", "sig"), prng=1)
+    eb, spec = ln.make_spectrum(src, 3.0, 4.0, 150, redshift=z, normal=normal)
+    from scipy.stats import norm
+
+    gx = np.linspace(-7, 7, 10000)
+    ee = 0.5 * (eb[1:] + eb[:-1]) / sf
+    sig_keV = f[("gas", "sig")] * 3.5 / 299792.458
+    ref = sp.line_spectrum(n, 3.5, ee, sig_keV, gx, norm.pdf(gx), f[("gas", "line")], shift, Bar())
+    ref = ref * (1 + z) ** 2 / (4 * np.pi * d_l ** 2)
+    np.testing.assert_allclose(spec, ref, rtol=1e-10, atol=ref.max() * 1e-13)
+
+
+def test_make_spectrum_thermal_counts_consistency(cuda):
+    """The source-frame count-rate spectrum integrates to the total expected photon rate used by
+    make_photons (sum of lambda at unit area*time, 4 pi D^2 removed)."""
+    kT_nodes, ebins, cosmic, metal, _ = synthetic.apec_like_tables(nT=36, nbins=800)
+    src = synthetic.beta_model_source(20, kT_range=(1.0, 9.0), v3d_sigma_kms=300.0, device="cuda")
+    sm = px.ThermalSpectralModel(ebins, kT_nodes, cosmic, metal)
+    model = px.ThermalSourceModel(sm, 0.1, 10.0, 800, 0.3, temperature_field=TF, prng=1)
+    eb, spec = model.make_spectrum(src, 0.1, 10.0, 800)
+    rate = (spec * np.diff(eb)).sum()
+    model.setup_model("photons", src, 0.0)
+    lam, _ = model.expected_counts(next(src.chunks()), 1.0)
+    np.testing.assert_allclose(rate, float(lam.sum()), rtol=1e-10)
+    with pytest.raises(RuntimeError):
+        model.make_spectrum(src, 0.1, 10.0, 10, normal="z")
