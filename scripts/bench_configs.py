@@ -154,6 +154,44 @@ def main():
 
     timed("power law (alpha field incl. 1 and 2) 256^3, z=0.5", run_d)
     timed("line 3.5 keV sigma 1000 km/s 256^3, z=0.5", run_e)
+    del f, src
+
+    # ---- spectrum mode (row f1): Doppler-regridded thermal spectrum of a whole dataset --------
+    import time
+
+    n = int(128 * s ** (1 / 3))
+    kT_nodes, ebins, cosmic, metal, _ = synthetic.apec_like_tables(nT=36, nbins=4000)
+    f = synthetic.beta_model_fields(n, kT_range=(1.0, 10.0), v3d_sigma_kms=300.0, device=dev)
+    src = px.ArrayDataSource(f, domain_left_edge=[-1000.0] * 3, domain_right_edge=[1000.0] * 3)
+    sm = px.ThermalSpectralModel(ebins, kT_nodes, cosmic, metal)
+    model = px.ThermalSourceModel(sm, 0.1, 10.0, 4000, 0.3, temperature_field=TF, prng=1)
+    for shifting, normal in ((False, None), (True, [0.3, -0.5, 0.8])):
+        model.make_spectrum(src, 0.2, 9.0, 2000, redshift=0.05, normal=normal)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(3):
+            model.make_spectrum(src, 0.2, 9.0, 2000, redshift=0.05, normal=normal)
+        torch.cuda.synchronize()
+        ms = (time.perf_counter() - t0) / 3 * 1e3
+        ncell = n ** 3
+        print(json.dumps({"config": f"make_spectrum thermal {n}^3 cells, 4000 -> 2000 bins, shifting={shifting}",
+                          "cells": ncell, "ms": round(ms, 2), "cells_per_s": ncell / (ms * 1e-3)}), flush=True)
+    # CPU reference on a sample: compiled reference shift_spectrum + interp1d_spec via the oracle
+    try:
+        from oracle import ref_glue as O
+
+        m_cpu = 4000
+        kT = f[TF][:m_cpu].cpu().numpy()
+        em = f[("gas", "emission_measure")][:m_cpu].cpu().numpy()
+        om = O.TableModel(ebins, kT_nodes, cosmic, metal)
+        cfg = dict(kT_min=0.025, kT_max=64.0, Zmet=0.3, spectral_norm=1.0)
+        t0 = time.perf_counter()
+        O.thermal_spectrum_mode(om, cfg, dict(kT=kT, em=em), np.linspace(0.2, 9.0, 2001), shift=np.full(m_cpu, 1.001))
+        dt = time.perf_counter() - t0
+        print(json.dumps({"config": "make_spectrum CPU reference (oracle, 1 core)", "cells": m_cpu,
+                          "ms": round(dt * 1e3, 1), "cells_per_s": m_cpu / dt}), flush=True)
+    except Exception as e:  # the oracle is optional for this script
+        print(json.dumps({"config": "make_spectrum CPU reference", "error": str(e)}))
 
 
 if __name__ == "__main__":
