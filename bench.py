@@ -263,6 +263,19 @@ def run_ours(args):
         "thermal_sample": Na * (2 * w + 24) + Np * w,
         "project": Na * (7 * w + 8) + Np * w + Ne_local * 3 * w,
     }
+    # measured DRAM traffic of the dominant stage from the committed ncu capture of this very
+    # workload (profiles/r1_final_traffic.json); null for any other workload
+    traffic = None
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r1_final_traffic.json")))
+        wl = tj["workload"]
+        if wl["grid"] == args.grid and wl["photons"] == args.photons and wl["nbins"] == args.nbins \
+                and args.kT_range is None:
+            kk = tj["kernels"]
+            traffic = {"project": kk["k_project_detect"]["dram_bytes"] + kk["k_project_emit<0>"]["dram_bytes"],
+                       "thermal_sample": kk["k_thermal_sample_staged"]["dram_bytes"]}
+    except Exception:
+        traffic = None
     stage_ms = {k: v[1] / v[0] for k, v in stages.items()}
     dominant = max(stage_ms, key=stage_ms.get) if stage_ms else None
     roofline = None
@@ -271,7 +284,8 @@ def run_ours(args):
         roofline = {"bound": "hbm", "kernel": {"thermal_sample": "k_thermal_sample_cta",
                                                "project": "pxb_project: k_project_detect + scan + k_project_emit"}.get(dominant, dominant),
                     "achieved": round(achieved, 2), "peak": peak_gbs, "unit": "GB/s",
-                    "frac": round(achieved / peak_gbs, 4), "traffic": None,
+                    "frac": round(achieved / peak_gbs, 4),
+                    "traffic": (traffic or {}).get(dominant),
                     "peak_source": peak_src, "ms_per_launch": round(stage_ms[dominant], 3),
                     "algorithmic_bytes_per_launch": int(alg[dominant]),
                     "stage_ms": {k: round(v, 3) for k, v in stage_ms.items()},
