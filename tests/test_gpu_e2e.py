@@ -76,7 +76,7 @@ def test_plugin_contract_and_file_roundtrip(cuda, tmp_path):
     assert ncells == nph.size == idxs.size and energies.size == nph.sum() and np.all(nph > 0)
     assert np.all(np.diff(idxs) > 0)
     with pytest.raises(NotImplementedError):
-        model.process_data("spectrum", next(src.chunks()), 1.0)
+        model.process_data("energy_field", next(src.chunks()), 1.0)
     prefix = str(tmp_path / "photons")
     model2 = px.ThermalSourceModel(sm, 0.1, 10.0, 500, 0.3, temperature_field=TF, prng=3)
     n1 = px.make_photons(prefix + ".h5", src, 0.05, 5.0e4, 1.0e5, model2)
