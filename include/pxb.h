@@ -26,6 +26,8 @@
  *   pxb_pixel_to_cel ............ pixel_to_cel, sky_functions.pyx:153-179
  *   pxb_absorb_transmission ..... AbsorptionModel.get_absorb, spectral_models.py:556-561
  *                                 (+ soxs get_wabs_absorb used by WabsModel :633-635)
+ *   pxb_absorb_decide ........... AbsorptionModel.absorb_photons, spectral_models.py:563-583
+ *                                 (diagnostic: explicit uniforms)
  *   pxb_project ................. the projection tile loop, photon_list.py:686-799:
  *                                 doppler_shift + absorb_photons (spectral_models.py:563-583)
  *                                 + scatter_events (sky_functions.pyx:40-147) or
@@ -344,6 +346,12 @@ int pxb_pixel_to_cel(int64_t n, double* xsky, double* ysky, double ra0_deg, doub
  * (absorb_kind, nH, abs_*). */
 int pxb_absorb_transmission(const pxb_project_params* params, int64_t n, const double* energy,
                             double* trans_out, void* stream);
+/* Diagnostic: the projection kernels' own absorption decision u < exp(-sigma(E)*nH) for n
+ * caller-supplied (energy, u) pairs (AbsorptionModel.absorb_photons, spectral_models.py:563-583,
+ * with the uniforms made explicit); survive_out[i] = 1 if photon i is detected.  Lets a test put
+ * u on either side of the threshold and E on the wabs piece edges. */
+int pxb_absorb_decide(const pxb_project_params* params, int64_t n, const double* energy,
+                      const double* u, uint8_t* survive_out, void* stream);
 
 #ifdef __cplusplus
 }

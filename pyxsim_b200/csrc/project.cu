@@ -326,6 +326,68 @@ __device__ __forceinline__ bool survives(double u, double tau) {
   return u < exp(-tau);
 }
 
+// ---- single-precision first look at the wabs decision ------------------------------------
+// u < exp(-sigma(E) nH) is decided in fp32 whenever the fp32 estimate is further from u than a
+// rigorous error bound; only the remaining ~1e-5 of the photons evaluate the fp64 formula.  The
+// decision is therefore the fp64 one in every case -- this is a speed-up, not an approximation.
+//  * piece index: rounding to float is monotone, so (float)E vs (float)edge orders like E vs
+//    edge unless the two floats are EQUAL (then fp64 decides).  The index comes from a
+//    128-entry table over [2^-4, 2^4) keV in steps of 1/16 octave (float bits >> 19); every
+//    sub-interval holds at most one edge and no edge is a sub-interval boundary (checked by
+//    tests/test_cpu_abi.py against the edge list).
+//  * tau32: float coefficients, Horner, approximate reciprocal: relative error < 4e-6
+//    (condition number of the piece polynomials <= 5); __expf: 2^-22 + 1.2e-7 |x| relative.
+//    Bound used: p32 * (2e-5 tau + 1e-6), i.e. > 1.6x the worst case, plus 2e-7 for (float)u.
+constexpr int WABS_LUT_N = 128;
+constexpr int WABS_LUT_BASE = (127 - 4) << 4;   // float bits >> 19 of 2^-4
+struct WabsFast {
+  float2 lut[WABS_LUT_N];   // x: the edge inside the sub-interval (+inf: none); y: piece index bits
+  float4 coef[14];          // c0, c1, c2 of the piece in float
+};
+
+__device__ __forceinline__ void wabs_fast_init(WabsFast& F) {
+  const double edges[13] = {0.1, 0.284, 0.4, 0.532, 0.707, 0.867, 1.303, 1.84, 2.471, 3.21,
+                            4.038, 7.111, 8.331};
+  for (int i = threadIdx.x; i < WABS_LUT_N; i += blockDim.x) {
+    const float lo = __int_as_float((WABS_LUT_BASE + i) << 19);
+    const float hi = __int_as_float((WABS_LUT_BASE + i + 1) << 19);
+    int k = 0;
+    float inside = __int_as_float(0x7f800000);
+#pragma unroll
+    for (int j = 0; j < 13; ++j) {
+      const float ef = (float)edges[j];
+      if (ef <= lo) ++k;
+      else if (ef < hi) inside = ef;
+    }
+    F.lut[i] = make_float2(inside, __int_as_float(k));
+  }
+  for (int i = threadIdx.x; i < 14; i += blockDim.x)
+    F.coef[i] = make_float4((float)g_wabs[i].c0, (float)g_wabs[i].c1, (float)g_wabs[i].c2, 0.0f);
+}
+
+// u < exp(-wabs_tau_per_nh(e) * nH), decided in fp32 when that is safe
+__device__ __forceinline__ bool wabs_survives(const WabsFast& F, double u, double e, double nH) {
+  const float ef = (float)e;
+  int idx = (__float_as_int(ef) >> 19) - WABS_LUT_BASE;
+  idx = max(0, min(idx, WABS_LUT_N - 1));
+  const float2 le = F.lut[idx];
+  if (ef != le.x) {   // (false for NaN too: falls through to fp64)
+    const int k = __float_as_int(le.y) + (ef > le.x ? 1 : 0);
+    const float4 c = F.coef[k];
+    float inv;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv) : "f"(ef));
+    const float tau = (c.x + ef * (c.y + ef * c.z)) * (inv * inv * inv) * (1.0e-2f * (float)nH);
+    const float p = __expf(-tau);
+    const float m = 2.0e-5f * tau + 1.2e-6f;
+    const float uf = (float)u;
+    // + 1e-37 absolute: below 2^-126 the exponential (and uf) are subnormal and only
+    // absolutely accurate; for normal p the extra 1e-37 is far inside the relative slack
+    if (uf < p * (1.0f - m) - 1.0e-37f) return true;
+    if (uf > p * (1.0f + m) + 1.0e-37f) return false;
+  }
+  return survives(u, wabs_tau_per_nh(e) * nH);
+}
+
 struct SkyConst {
   double sin_d0, cos_d0, ra0_rad, d0_rad, inv_DA;
 };
@@ -451,18 +513,24 @@ __device__ __forceinline__ void scatter_allsky(const pxb_project_params& P, cons
 
 // absorption decision of one photon (phase 1); kept out of line so the rolled item loop stays
 // small
-__device__ __forceinline__ bool absorb_decision(const pxb_project_params& P, int64_t c, int64_t draw,
-                                             double en) {
+__device__ __forceinline__ bool absorb_one(const pxb_project_params& P, const WabsFast& F, double u,
+                                           double e, double nH) {
+  if (P.absorb_kind == PXB_ABS_WABS) return wabs_survives(F, u, e, nH);
+  return survives(u, table_tau_per_nh(P, e) * nH);
+}
+
+__device__ __forceinline__ bool absorb_decision(const pxb_project_params& P, const WabsFast& F,
+                                                int64_t c, int64_t draw, double en) {
   const uint64_t cell_key = (uint64_t)(P.cell_id0 + c);
   bool det = true;
   if (P.nH_cell) {
     // internal absorption on the source-frame energy, photon_list.py:715-723
     const Philox4 rd = pxb_rand4(P.seed, STREAM_PROJ_D, cell_key, (uint64_t)draw);
-    det = survives(u53(rd.x, rd.y), tau_per_nh(P, en * P.oneplusz) * __ldg(P.nH_cell + c));
+    det = absorb_one(P, F, u53(rd.x, rd.y), en * P.oneplusz, __ldg(P.nH_cell + c));
   }
   if (det && P.nH > 0.0) {
     const Philox4 ra = pxb_rand4(P.seed, STREAM_PROJ_A, cell_key, (uint64_t)draw);
-    det = survives(u53(ra.x, ra.y), tau_per_nh(P, en) * P.nH);
+    det = absorb_one(P, F, u53(ra.x, ra.y), en, P.nH);
   }
   return det;
 }
@@ -489,6 +557,8 @@ k_project_photons(const __grid_constant__ pxb_photon_list L,
   int* s_rel = s_rel_all[wid];
   short* s_slot = s_slot_all[wid];
   const bool absorb = P.absorb_kind != PXB_ABS_NONE;
+  __shared__ WabsFast s_wabs;
+  if (P.absorb_kind == PXB_ABS_WABS) wabs_fast_init(s_wabs);   // published by the loop's barrier
 
   for (;;) {
     __syncthreads();
@@ -552,7 +622,7 @@ k_project_photons(const __grid_constant__ pxb_photon_list L,
         }
         const int64_t c = c0 + rel;
         const double en = s_e[it] * __ldg(D.shift + c);
-        det = absorb ? absorb_decision(P, c, p - first, en) : true;
+        det = absorb ? absorb_decision(P, s_wabs, c, p - first, en) : true;
         s_e[it] = en;
         s_rel[it] = rel;
         if (det) {
@@ -616,6 +686,11 @@ k_project_detect(const __grid_constant__ pxb_photon_list L,
                  const ProjWork W, uint32_t* __restrict__ masks, int64_t* __restrict__ counts,
                  int64_t n_wtiles) {
   __shared__ int64_t s_off_all[PROJ_WARPS][PROJ_WTILE + 2];
+  __shared__ WabsFast s_wabs;
+  if (P.absorb_kind == PXB_ABS_WABS) {
+    wabs_fast_init(s_wabs);
+    __syncthreads();
+  }
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   int64_t* s_off = s_off_all[wid];
   const int64_t wtile = (int64_t)blockIdx.x * PROJ_WARPS + wid;
@@ -665,7 +740,7 @@ k_project_detect(const __grid_constant__ pxb_photon_list L,
       }
       const int64_t c = c0 + rel;
       const double en = s_e[r * 32 + lane] * __ldg(D.shift + c);
-      det = absorb ? absorb_decision(P, c, p - first, en) : true;
+      det = absorb ? absorb_decision(P, s_wabs, c, p - first, en) : true;
       if (det) {
         tsum += en;
         tmin = fmin(tmin, en);
@@ -963,6 +1038,33 @@ extern "C" int pxb_pixel_to_cel(int64_t n, double* xsky, double* ysky, double ra
   const double d0 = dec0_deg * PXB_PI / 180.0;
   k_pixel_to_cel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
       n, xsky, ysky, ra0_deg * PXB_PI / 180.0, sin(d0), cos(d0));
+  PXB_LAUNCH_CHECK();
+  return PXB_OK;
+}
+
+__global__ void __launch_bounds__(256)
+k_absorb_decide(const __grid_constant__ pxb_project_params P, int64_t n,
+                const double* __restrict__ e, const double* __restrict__ u,
+                uint8_t* __restrict__ out) {
+  __shared__ WabsFast s_wabs;
+  if (P.absorb_kind == PXB_ABS_WABS) {
+    wabs_fast_init(s_wabs);
+    __syncthreads();
+  }
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  out[i] = (P.absorb_kind == PXB_ABS_NONE) ? 1 : (absorb_one(P, s_wabs, u[i], e[i], P.nH) ? 1 : 0);
+}
+
+extern "C" int pxb_absorb_decide(const pxb_project_params* params, int64_t n, const double* energy,
+                                 const double* u, uint8_t* survive_out, void* stream) {
+  int rc = check_params(params);
+  if (rc) return rc;
+  PXB_REQUIRE(n >= 0, "bad n");
+  if (n == 0) return PXB_OK;
+  PXB_REQUIRE(energy && u && survive_out, "NULL argument");
+  k_absorb_decide<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      *params, n, energy, u, survive_out);
   PXB_LAUNCH_CHECK();
   return PXB_OK;
 }

@@ -17,6 +17,7 @@ KERNELS_PER_CALL = {
     "pxb_powerlaw_counts": 1, "pxb_powerlaw_sample": 1, "pxb_line_counts": 1,
     "pxb_line_sample": 1, "pxb_project": 8, "pxb_doppler_shift": 1, "pxb_pixel_to_cel": 1,
     "pxb_absorb_transmission": 1,
+    "pxb_absorb_decide": 1,
 }
 
 

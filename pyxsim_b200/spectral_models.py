@@ -9,6 +9,7 @@ rejection (``AbsorptionModel.absorb_photons`` :563-583) run on the GPU through l
 import ctypes as C
 
 import numpy as np
+import torch
 
 from . import _lib, constants as K
 from .device import ptr, stream_ptr, to_device, empty, require_cuda
@@ -361,15 +362,25 @@ class AbsorptionModel:
         return out.cpu().numpy()
 
     def absorb_photons(self, eobs, prng=None):
-        """Boolean survival mask (spectral_models.py:563-583).  The projection kernel does this
-        in-flight; this method exists for API compatibility."""
+        """Boolean survival mask (spectral_models.py:563-583): the uniforms come from ``prng`` in
+        the reference's order (one per photon), the decision ``u < exp(-sigma(E) nH)`` is the
+        projection kernels' own (``pxb_absorb_decide``).  ``project_photons`` does not call this
+        -- it decides in flight with its counter-based generator."""
         from .utils import parse_prng
 
         prng = parse_prng(prng)
-        eobs = np.asarray(eobs, "float64")
+        eobs = np.ascontiguousarray(eobs, "float64")
         if eobs.size == 0:
             return np.array([], dtype="bool")
-        return prng.uniform(size=eobs.size) < self.get_absorb(eobs)
+        u = prng.uniform(size=eobs.size)
+        P = _lib.ProjectParams()
+        keep = self._fill_params(P)
+        de, du = to_device(eobs), to_device(u)
+        out = torch.empty(eobs.size, dtype=torch.uint8, device=de.device)
+        _lib.call("pxb_absorb_decide", C.byref(P), eobs.size, ptr(de), ptr(du), out.data_ptr(),
+                  stream_ptr())
+        del keep
+        return out.cpu().numpy().astype(bool)
 
 
 class TBabsModel(AbsorptionModel):

@@ -4,6 +4,7 @@ import ctypes as C
 import os
 import re
 
+import numpy as np
 import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -74,3 +75,21 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh")):
                 txt = open(os.path.join(dirpath, f)).read()
                 assert "import oracle" not in txt and "from oracle" not in txt, f
+
+
+def test_wabs_fast_index_table_invariants():
+    """project.cu's fp32 wabs piece lookup indexes a 128-entry table by (float bits >> 19) over
+    [2^-4, 2^4) keV; it is only exact if no sub-interval holds two edges and no (float) edge is a
+    sub-interval boundary.  Restated here so a change of the edge list cannot silently break it."""
+    edges = np.array([0.1, 0.284, 0.4, 0.532, 0.707, 0.867, 1.303, 1.84, 2.471, 3.21, 4.038, 7.111,
+                      8.331]).astype(np.float32)
+    base = (127 - 4) << 4
+    idx = (edges.view(np.int32) >> 19) - base
+    assert idx.min() >= 0 and idx.max() < 128
+    assert np.unique(idx).size == edges.size                      # at most one edge per sub-interval
+    lo = ((idx + base) << 19).astype(np.int32).view(np.float32)
+    assert np.all(edges > lo)                                     # never on a boundary
+    src = open(os.path.join(ROOT, "pyxsim_b200", "csrc", "project.cu")).read()
+    assert "WABS_LUT_BASE = (127 - 4) << 4" in src and "WABS_LUT_N = 128" in src
+    for v in ("0.284", "0.532", "0.707", "0.867", "1.303", "2.471", "4.038", "7.111", "8.331"):
+        assert src.count(v) >= 2                                  # immediate chain and table builder agree

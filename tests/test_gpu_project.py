@@ -98,6 +98,58 @@ def test_absorb_transmission(cuda, oracle, kind):
     np.testing.assert_allclose(prod.get_absorb(e), orc.get_absorb(e), rtol=1e-12, atol=1e-300)
 
 
+def test_absorb_decision_at_the_threshold(cuda, oracle):
+    """The kernels decide u < exp(-sigma nH) in fp32 first and fall back to fp64 inside a
+    rigorous error band: the decision must be the fp64 one for u arbitrarily close to the
+    threshold and for energies on / one ulp (float or double) either side of every wabs edge."""
+    rng = np.random.RandomState(4)
+    edges = np.array([0.03, 0.1, 0.284, 0.4, 0.532, 0.707, 0.867, 1.303, 1.84, 2.471, 3.21, 4.038,
+                      7.111, 8.331, 10.0])
+    ef = edges.astype(np.float32)
+    near = [edges, np.nextafter(edges, 0), np.nextafter(edges, 100),
+            ef.astype(np.float64), np.nextafter(ef, np.float32(0)).astype(np.float64),
+            np.nextafter(ef, np.float32(100)).astype(np.float64),
+            edges * (1 - 2.0 ** -25), edges * (1 + 2.0 ** -25), edges * (1 - 2.0 ** -24), edges * (1 + 2.0 ** -24)]
+    e = np.concatenate(near + [np.exp(rng.uniform(np.log(0.02), np.log(40.0), 200000))])
+    for nH in (0.02, 0.5, 30.0):
+        orc = oracle.WabsAbsorb(nH)
+        prod = px.WabsModel(nH)
+        p = orc.get_absorb(e)
+        for delta in (0.5, 1e-2, 1e-4, 1e-5, 1e-6, 1e-7, 1e-9, 1e-12):
+            for sign in (-1.0, 1.0):
+                u = p * (1.0 + sign * delta)
+                ok = (u < 1.0) & (u > 0.0) & (p > 1e-300)
+
+                class Fixed:
+                    def uniform(self, size=None):
+                        return u
+
+                got = prod.absorb_photons(e, prng=Fixed())
+                np.testing.assert_array_equal(got[ok], (u < p)[ok], err_msg=f"nH={nH} delta={sign * delta}")
+    # a table model takes the fp64 route throughout
+    en, sg = synthetic.tbabs_like_sigma(n=3000)
+    prod, orc = px.TBabsModel(0.3, energy=en, cross_section=sg), oracle.TableAbsorb(0.3, en, sg * 1.0e22)
+    e = np.exp(rng.uniform(np.log(0.05), np.log(15.0), 100000))
+    p = orc.get_absorb(e)
+    for delta in (-1e-9, 1e-9, -0.3, 0.3):
+        u = np.clip(p * (1 + delta), 0.0, 1.0 - 1e-16)
+
+        class Fixed2:
+            def uniform(self, size=None):
+                return u
+
+        np.testing.assert_array_equal(prod.absorb_photons(e, prng=Fixed2()), u < p)
+
+
+def test_absorb_photons_follows_reference_draw_order(cuda, oracle):
+    """Same RandomState, same energies -> the mask of the reference's absorb_photons."""
+    rng = np.random.RandomState(8)
+    e = np.exp(rng.uniform(np.log(0.1), np.log(10.0), 100000))
+    got = px.WabsModel(0.1).absorb_photons(e, prng=np.random.RandomState(77))
+    ref = np.random.RandomState(77).uniform(size=e.size) < oracle.WabsAbsorb(0.1).get_absorb(e)
+    np.testing.assert_array_equal(got, ref)
+
+
 # ---------------------------------------------------------------------------------------
 # projection invariants and distributions
 # ---------------------------------------------------------------------------------------
