@@ -141,6 +141,7 @@ k_pixel_to_cel(int64_t n, double* __restrict__ xs, double* __restrict__ ys, doub
 // per-cell pre-pass
 // ---------------------------------------------------------------------------------------
 constexpr int PROJ_WTILE_C = 256;   // photons per warp tile (== PROJ_WTILE below)
+constexpr int PROJ_STAGE_CELLS = 32;  // a tile's cells are staged in shared memory up to this many
 
 // what the scatter step needs of a cell, one 32-byte sector per cell
 struct __align__(32) CellGeom {
@@ -410,11 +411,10 @@ __device__ __forceinline__ double u32_centered(uint32_t w) {
 }
 
 // scatter + sky transform of one surviving photon (external observer)
-__device__ __forceinline__ void scatter_external(const pxb_project_params& P, const CellDerived& D,
-                                                 const SkyConst& K, int64_t c, uint64_t cell_key,
+__device__ __forceinline__ void scatter_external(const pxb_project_params& P, const CellGeom& g,
+                                                 const SkyConst& K, uint64_t cell_key,
                                                  uint64_t draw, double& xs_out, double& ys_out,
                                                  double& los_out) {
-  const CellGeom g = ld_geom(D.geom + c);
   const double w = g.w, cx = g.cx, cy = g.cy;
   los_out = g.cz;  // from the unscattered centre (sky_functions.pyx:124,143)
   const Philox4 rb = pxb_rand4(P.seed, STREAM_PROJ_B, cell_key, draw);
@@ -469,10 +469,9 @@ __device__ __forceinline__ void scatter_external(const pxb_project_params& P, co
 }
 
 // internal observer: sky_functions.pyx:205-248
-__device__ __forceinline__ void scatter_allsky(const pxb_project_params& P, const CellDerived& D,
-                                               int64_t c, uint64_t cell_key, uint64_t draw,
+__device__ __forceinline__ void scatter_allsky(const pxb_project_params& P, const CellGeom& g,
+                                               uint64_t cell_key, uint64_t draw,
                                                double& lon_out, double& lat_out, double& los_out) {
-  const CellGeom g = ld_geom(D.geom + c);
   const double w = g.w, cx = g.cx, cy = g.cy, cz = g.cz;
   double o0, o1, o2;
   const Philox4 rb = pxb_rand4(P.seed, STREAM_PROJ_B, cell_key, draw);
@@ -660,8 +659,9 @@ k_project_photons(const __grid_constant__ pxb_photon_list L,
       const uint64_t cell_key = (uint64_t)(P.cell_id0 + c);
       const uint64_t draw = (uint64_t)(p0 + it - first);
       double xs, ys, los;
-      if (OBS == 0) scatter_external(P, D, K, c, cell_key, draw, xs, ys, los);
-      else scatter_allsky(P, D, c, cell_key, draw, xs, ys, los);
+      const CellGeom g = ld_geom(D.geom + c);
+      if (OBS == 0) scatter_external(P, g, K, cell_key, draw, xs, ys, los);
+      else scatter_allsky(P, g, cell_key, draw, xs, ys, los);
       const int64_t o = base + sl;
       st_stream(xsky + o, xs);
       st_stream(ysky + o, ys);
@@ -683,7 +683,7 @@ k_project_photons(const __grid_constant__ pxb_photon_list L,
 __global__ void __launch_bounds__(PROJ_THREADS, 4)
 k_project_detect(const __grid_constant__ pxb_photon_list L,
                  const __grid_constant__ pxb_project_params P, const CellDerived D,
-                 const ProjWork W, uint32_t* __restrict__ masks, int64_t* __restrict__ counts,
+                 const ProjWork W, uint16_t* __restrict__ slots, int64_t* __restrict__ counts,
                  int64_t n_wtiles) {
   __shared__ int64_t s_off_all[PROJ_WARPS][PROJ_WTILE + 2];
   __shared__ WabsFast s_wabs;
@@ -697,19 +697,27 @@ k_project_detect(const __grid_constant__ pxb_photon_list L,
   if (wtile >= n_wtiles) return;
   const int64_t p0 = wtile * PROJ_WTILE;
   const int64_t p1 = min(p0 + (int64_t)PROJ_WTILE, L.n_photons);
+  // all eight energy loads of the lane go out first, together with the tile's cell range; the
+  // per-cell loads that depend on it follow while the energies are still in flight
+  __shared__ double s_e_all[PROJ_WARPS][PROJ_WTILE];
+  __shared__ double s_shift_all[PROJ_WARPS][PROJ_STAGE_CELLS];
+  double* s_e = s_e_all[wid];
+  double* s_shift = s_shift_all[wid];
+  double ev[PROJ_ITEMS];
+#pragma unroll
+  for (int r = 0; r < PROJ_ITEMS; ++r) {
+    const int64_t p = p0 + r * 32 + lane;
+    ev[r] = (p < p1) ? ld_stream(L.energy + p) : 0.0;
+  }
   const int64_t c0 = __ldg(D.tile_cell + wtile);
   const int64_t c1 = (wtile + 1 < n_wtiles) ? __ldg(D.tile_cell + wtile + 1) : L.n_cells - 1;
   const int nc = (c1 - c0 + 1 <= PROJ_WTILE + 1) ? (int)(c1 - c0 + 1) : 0;
   const int step0 = nc > 1 ? (1 << (31 - __clz(nc - 1))) : 0;
+  const bool staged = nc >= 1 && nc <= PROJ_STAGE_CELLS;
   for (int q = lane; q <= nc && nc > 0; q += 32) s_off[q] = __ldg(L.poff + c0 + q);
-  // all eight energy loads of the lane go out together (the item loop below is rolled)
-  __shared__ double s_e_all[PROJ_WARPS][PROJ_WTILE];
-  double* s_e = s_e_all[wid];
+  if (staged && lane < nc) s_shift[lane] = __ldg(D.shift + c0 + lane);
 #pragma unroll
-  for (int r = 0; r < PROJ_ITEMS; ++r) {
-    const int64_t p = p0 + r * 32 + lane;
-    if (p < p1) s_e[r * 32 + lane] = ld_stream(L.energy + p);
-  }
+  for (int r = 0; r < PROJ_ITEMS; ++r) s_e[r * 32 + lane] = ev[r];
   __syncwarp();
   const bool absorb = P.absorb_kind != PXB_ABS_NONE;
   int run = 0;
@@ -718,8 +726,8 @@ k_project_detect(const __grid_constant__ pxb_photon_list L,
   for (int r = 0; r < PROJ_ITEMS; ++r) {
     const int64_t p = p0 + r * 32 + lane;
     bool det = false;
+    int rel = 0;
     if (p < p1) {
-      int rel = 0;
       int64_t first;
       if (nc == 1) {
         first = s_off[0];
@@ -739,7 +747,7 @@ k_project_detect(const __grid_constant__ pxb_photon_list L,
         first = __ldg(L.poff + lo);
       }
       const int64_t c = c0 + rel;
-      const double en = s_e[r * 32 + lane] * __ldg(D.shift + c);
+      const double en = s_e[r * 32 + lane] * (staged ? s_shift[rel] : __ldg(D.shift + c));
       det = absorb ? absorb_decision(P, s_wabs, c, p - first, en) : true;
       if (det) {
         tsum += en;
@@ -748,7 +756,10 @@ k_project_detect(const __grid_constant__ pxb_photon_list L,
       }
     }
     const unsigned bal = __ballot_sync(0xffffffffu, det);
-    if (lane == 0) masks[wtile * PROJ_ITEMS + r] = bal;
+    // survivor record: position inside the tile (8 bits) | cell relative to the tile's first (8)
+    if (det)
+      slots[wtile * PROJ_WTILE + run + __popc(bal & ((1u << lane) - 1u))] =
+          (uint16_t)((r * 32 + lane) | ((rel & 255) << 8));
     run += __popc(bal);
   }
   tsum = warp_sum(tsum);
@@ -766,74 +777,97 @@ template <int OBS>
 __global__ void __launch_bounds__(PROJ_THREADS, 4)
 k_project_emit(const __grid_constant__ pxb_photon_list L,
                const __grid_constant__ pxb_project_params P, const CellDerived D,
-               const uint32_t* __restrict__ masks, const int64_t* __restrict__ offsets,
+               const uint16_t* __restrict__ slots, const int64_t* __restrict__ offsets,
                double* __restrict__ xsky, double* __restrict__ ysky,
                double* __restrict__ eobs_out, double* __restrict__ los_out,
                int64_t* __restrict__ n_events_out, int64_t n_wtiles, const SkyConst K) {
   __shared__ int64_t s_off_all[PROJ_WARPS][PROJ_WTILE + 2];
+  __shared__ double s_e_all[PROJ_WARPS][PROJ_WTILE];
+  __shared__ uint16_t s_rec_all[PROJ_WARPS][PROJ_WTILE];
+  __shared__ CellGeom s_geom_all[PROJ_WARPS][PROJ_STAGE_CELLS];
+  __shared__ double s_shift_all[PROJ_WARPS][PROJ_STAGE_CELLS];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   int64_t* s_off = s_off_all[wid];
+  double* s_e = s_e_all[wid];
+  uint16_t* s_rec = s_rec_all[wid];
+  CellGeom* s_geom = s_geom_all[wid];
+  double* s_shift = s_shift_all[wid];
   const int64_t wtile = (int64_t)blockIdx.x * PROJ_WARPS + wid;
   if (wtile >= n_wtiles) return;
   if (wtile == 0 && lane == 0) *n_events_out = __ldg(offsets + n_wtiles);
   const int64_t p0 = wtile * PROJ_WTILE;
-  const int64_t base = __ldg(offsets + wtile);
-  // the lane's eight mask words (warp-uniform values) and its survivors' energies
-  const uint32_t my_mask = (lane < PROJ_ITEMS) ? __ldg(masks + wtile * PROJ_ITEMS + lane) : 0u;
-  if (__ballot_sync(0xffffffffu, my_mask != 0u) == 0u) return;   // everything absorbed
-  const int64_t c0 = __ldg(D.tile_cell + wtile);
-  const int64_t c1 = (wtile + 1 < n_wtiles) ? __ldg(D.tile_cell + wtile + 1) : L.n_cells - 1;
-  const int nc = (c1 - c0 + 1 <= PROJ_WTILE + 1) ? (int)(c1 - c0 + 1) : 0;
-  const int step0 = nc > 1 ? (1 << (31 - __clz(nc - 1))) : 0;
-  for (int q = lane; q <= nc && nc > 0; q += 32) s_off[q] = __ldg(L.poff + c0 + q);
-  __shared__ double s_e_all[PROJ_WARPS][PROJ_WTILE];
-  double* s_e = s_e_all[wid];
+  const int64_t p1 = min(p0 + (int64_t)PROJ_WTILE, L.n_photons);
+  // ---- phase A: every load that does not depend on another goes out at once --------------
+  // (tile's energies and survivor records, its base/count, the cells it starts and ends in)
+  double ev[PROJ_ITEMS];
+  unsigned rv[PROJ_ITEMS];
 #pragma unroll
   for (int r = 0; r < PROJ_ITEMS; ++r) {
-    const uint32_t bal = __shfl_sync(0xffffffffu, my_mask, r);
-    if ((bal >> lane) & 1u) s_e[r * 32 + lane] = ld_stream(L.energy + p0 + r * 32 + lane);
+    const int64_t p = p0 + r * 32 + lane;
+    ev[r] = (p < p1) ? ld_stream(L.energy + p) : 0.0;
+    rv[r] = __ldg(slots + p);   // slot r*32+lane of this tile (garbage past the count: unused)
+  }
+  const int64_t base = __ldg(offsets + wtile);
+  const int count = (int)(__ldg(offsets + wtile + 1) - base);   // survivors of this tile
+  const int64_t c0 = __ldg(D.tile_cell + wtile);
+  const int64_t c1 = (wtile + 1 < n_wtiles) ? __ldg(D.tile_cell + wtile + 1) : L.n_cells - 1;
+  if (count == 0) return;                                       // everything absorbed
+  // ---- phase B: per-cell data of the tile (depends on c0) ---------------------------------
+  const int nc = (c1 - c0 + 1 <= PROJ_WTILE + 1) ? (int)(c1 - c0 + 1) : 0;
+  const bool packed_rel = nc >= 1 && nc <= 256;   // the record's 8 bits hold the cell
+  const bool staged = nc >= 1 && nc <= PROJ_STAGE_CELLS;
+  for (int q = lane; q <= nc && nc > 0; q += 32) s_off[q] = __ldg(L.poff + c0 + q);
+  if (staged && lane < nc) {
+    s_geom[lane] = ld_geom(D.geom + c0 + lane);
+    s_shift[lane] = __ldg(D.shift + c0 + lane);
+  }
+#pragma unroll
+  for (int r = 0; r < PROJ_ITEMS; ++r) {
+    s_e[r * 32 + lane] = ev[r];
+    s_rec[r * 32 + lane] = (uint16_t)rv[r];
   }
   __syncwarp();
-  int run = 0;
+  // survivors were numbered by the detect pass: slot s of the tile is photon p0 + (record & 255),
+  // so every round works on 32 live lanes and the event stores are dense
 #pragma unroll 1
-  for (int r = 0; r < PROJ_ITEMS; ++r) {
-    const uint32_t bal = __shfl_sync(0xffffffffu, my_mask, r);
-    const bool det = (bal >> lane) & 1u;
-    if (det) {
-      const int64_t p = p0 + r * 32 + lane;
-      int rel = 0;
-      int64_t first;
-      if (nc == 1) {
-        first = s_off[0];
-      } else if (nc > 0) {
-        for (int step = step0; step > 0; step >>= 1) {   // step0: largest power of two < nc
-          const int q = rel + step;
-          if (q < nc && s_off[q] <= p) rel = q;
-        }
-        first = s_off[rel];
-      } else {
-        int64_t lo = c0, hi = c1 + 1;
-        while (hi - lo > 1) {
-          const int64_t mid = (lo + hi) >> 1;
-          if (__ldg(L.poff + mid) <= p) lo = mid; else hi = mid;
-        }
-        rel = (int)(lo - c0);
-        first = __ldg(L.poff + lo);
+  for (int sl = lane; sl < count; sl += 32) {
+    const unsigned rec = s_rec[sl];
+    const int it = rec & 255u;
+    const int64_t p = p0 + it;
+    int rel;
+    int64_t first;
+    if (packed_rel) {
+      rel = (int)(rec >> 8);
+      first = s_off[rel];
+    } else if (nc > 0) {
+      rel = 0;
+      for (int step = 256; step > 0; step >>= 1) {
+        const int q = rel + step;
+        if (q < nc && s_off[q] <= p) rel = q;
       }
-      const int64_t c = c0 + rel;
-      const double en = s_e[r * 32 + lane] * __ldg(D.shift + c);
-      const uint64_t cell_key = (uint64_t)(P.cell_id0 + c);
-      const uint64_t draw = (uint64_t)(p - first);
-      double xs, ys, los;
-      if (OBS == 0) scatter_external(P, D, K, c, cell_key, draw, xs, ys, los);
-      else scatter_allsky(P, D, c, cell_key, draw, xs, ys, los);
-      const int64_t o = base + run + __popc(bal & ((1u << lane) - 1u));
-      st_stream(xsky + o, xs);
-      st_stream(ysky + o, ys);
-      st_stream(eobs_out + o, en);
-      if (los_out) st_stream(los_out + o, los);
+      first = s_off[rel];
+    } else {
+      int64_t lo = c0, hi = c1 + 1;
+      while (hi - lo > 1) {
+        const int64_t mid = (lo + hi) >> 1;
+        if (__ldg(L.poff + mid) <= p) lo = mid; else hi = mid;
+      }
+      rel = (int)(lo - c0);
+      first = __ldg(L.poff + lo);
     }
-    run += __popc(bal);
+    const int64_t c = c0 + rel;
+    const CellGeom g = staged ? s_geom[rel] : ld_geom(D.geom + c);
+    const double en = s_e[it] * (staged ? s_shift[rel] : __ldg(D.shift + c));
+    const uint64_t cell_key = (uint64_t)(P.cell_id0 + c);
+    const uint64_t draw = (uint64_t)(p - first);
+    double xs, ys, los;
+    if (OBS == 0) scatter_external(P, g, K, cell_key, draw, xs, ys, los);
+    else scatter_allsky(P, g, cell_key, draw, xs, ys, los);
+    const int64_t o = base + sl;
+    st_stream(xsky + o, xs);
+    st_stream(ysky + o, ys);
+    st_stream(eobs_out + o, en);
+    if (los_out) st_stream(los_out + o, los);
   }
 }
 
@@ -892,7 +926,7 @@ static ProjLayout proj_layout(int64_t n_cells, int64_t n_photons) {
   l.off_part = o;   o += align256(3 * l.ntiles * 8);
   l.off_red = o;    o += align256(3 * STATS_BLOCKS * 8);
   // two-pass variant
-  l.off_masks = o;   o += align256(l.ntiles * PROJ_ITEMS * 4);
+  l.off_masks = o;   o += align256(l.ntiles * PROJ_WTILE * 2);
   l.off_counts = o;  o += align256(l.ntiles * 8);
   l.off_offsets = o; o += align256((l.ntiles + 1) * 8);
   l.off_arank = o;   o += align256((l.ntiles + 1) * 8);
@@ -969,7 +1003,7 @@ extern "C" int pxb_project(const pxb_photon_list* L, const pxb_project_params* P
   const char* mode = getenv("PXB_PROJECT_MODE");
   const bool fused = mode && strcmp(mode, "fused") == 0;
   if (!fused) {
-    uint32_t* masks = (uint32_t*)(ws + lay.off_masks);
+    uint16_t* masks = (uint16_t*)(ws + lay.off_masks);   // survivor records
     int64_t* counts = (int64_t*)(ws + lay.off_counts);
     int64_t* offsets = (int64_t*)(ws + lay.off_offsets);
     int64_t* arank = (int64_t*)(ws + lay.off_arank);
