@@ -555,6 +555,20 @@ __device__ __forceinline__ FastCell fast_setup(const DevModel& M, const pxb_ther
   return fc;
 }
 
+// n / d for 0 <= n < d <= 1 (a position inside a CDF step): single-precision reciprocal seed,
+// two Newton steps and one residual correction in fp64 -- within one ulp of the IEEE quotient at
+// about a third of its instructions.  Steps too small for the fp32 seed take the IEEE division.
+__device__ __forceinline__ double cdf_fraction(double n, double d) {
+  if (d < 1.0e-30) return n / d;
+  float rf;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rf) : "f"((float)d));
+  double r = (double)rf;
+  r = fma(r, fma(-d, r, 1.0), r);
+  r = fma(r, fma(-d, r, 1.0), r);
+  const double q = n * r;
+  return fma(fma(-q, d, n), r, q);
+}
+
 // invert one table row's CDF at u2 (staged rows gather from shared memory)
 
 // Rows staged in shared memory by the persistent sampler: CDFs and guides of rows (tag, tag+1)
@@ -638,7 +652,31 @@ __device__ __forceinline__ double invert_row(const DevModel& M, const DevTable* 
     e0 = __ldg(M.edges + j);
     e1 = __ldg(M.edges + j + 1);
   }
-  return e0 + (u2 - c.x) / (c.y - c.x) * (e1 - e0);
+  return e0 + cdf_fraction(u2 - c.x, c.y - c.x) * (e1 - e0);
+}
+
+// invert_row for a row whose CDF and guide table sit in shared memory (32-bit addressing, no
+// per-photon pointer selection): s_cdf/s_guide point at the staged slot
+__device__ __forceinline__ double invert_row_staged(const DevModel& M, int nb, const double* s_cdf,
+                                                    const uint16_t* s_guide, double u2) {
+  const int k = min((int)(u2 * nb), nb - 1);
+  int j = s_guide[k];
+  int jhi = s_guide[k + 1];
+  while (jhi > j) {
+    const int mid = (j + jhi + 1) >> 1;
+    if (s_cdf[mid] <= u2) j = mid; else jhi = mid - 1;
+  }
+  if (M.method == 1) return __ldg(M.emid + j);
+  const double ca = s_cdf[j], cb = s_cdf[j + 1];
+  double e0, de;
+  if (M.edges_uniform) {
+    e0 = M.edge0 + j * M.dedge;
+    de = (M.edge0 + (j + 1) * M.dedge) - e0;
+  } else {
+    e0 = __ldg(M.edges + j);
+    de = __ldg(M.edges + j + 1) - e0;
+  }
+  return e0 + cdf_fraction(u2 - ca, cb - ca) * de;
 }
 
 // ---- mixture sampler with TMA-staged table rows -----------------------------------------
@@ -786,37 +824,53 @@ k_thermal_sample_staged(const DevModel M, const __grid_constant__ pxb_thermal_ce
         uint64_t blk_cell = ~0ull, blk_idx = ~0ull;
         double e2[2];
         bool have[2] = {false, false};
+        // the pair's cell: searched for the first photon, kept for the second unless it starts
+        // the next cell
+        int64_t first = 0, next = -1, i = 0, kc = 0;
+        uint64_t gid = 0;
+        int fz1 = 0, fmeta = 0;
+        long long fcnt0 = 0, fcnt1 = 0, fcnt2 = 0;
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
           const int64_t p = pa + h;
           if (p >= p1) continue;
-          int64_t first, k;
-          if (nc > 0) {
-            int rel = 0;
-            if (nc > 1) {
-              for (int step = step0; step > 0; step >>= 1) {   // largest power of two < nc
-                const int q = rel + step;
-                if (q < nc && s_off[q] <= p) rel = q;
+          if (p >= next) {
+            int64_t k;
+            if (nc > 0) {
+              int rel = 0;
+              if (nc > 1) {
+                for (int step = step0; step > 0; step >>= 1) {   // largest power of two < nc
+                  const int q = rel + step;
+                  if (q < nc && s_off[q] <= p) rel = q;
+                }
               }
+              k = c0 + rel;
+              first = s_off[rel];
+              next = s_off[rel + 1];
+            } else {  // more cells than photons in the tile (never for active lists)
+              int64_t lo = c0, hi = c1 + 1;
+              while (hi - lo > 1) {
+                const int64_t mid = (lo + hi) >> 1;
+                if (__ldg(poff + mid) <= p) lo = mid; else hi = mid;
+              }
+              k = lo;
+              first = __ldg(poff + k);
+              next = __ldg(poff + k + 1);
             }
-            k = c0 + rel;
-            first = s_off[rel];
-          } else {  // more cells than photons in the tile (never for active lists)
-            int64_t lo = c0, hi = c1 + 1;
-            while (hi - lo > 1) {
-              const int64_t mid = (lo + hi) >> 1;
-              if (__ldg(poff + mid) <= p) lo = mid; else hi = mid;
-            }
-            k = lo;
-            first = __ldg(poff + k);
+            const FastCell fc = fcs[k];
+            fz1 = fc.z1;
+            fmeta = fc.meta;
+            fcnt0 = fc.cnt[0];
+            fcnt1 = fc.cnt[1];
+            fcnt2 = fc.cnt[2];
+            kc = k;
+            i = __ldg(idx + k);
+            gid = (uint64_t)(C.cell_id0 + i);
           }
-          const FastCell fc = fcs[k];
-          if (!(fc.meta & 16)) continue;
-          const int64_t i = __ldg(idx + k);
-          const uint64_t gid = (uint64_t)(C.cell_id0 + i);
+          if (!(fmeta & 16)) continue;
           const uint64_t d = (uint64_t)(p - first);
           double e;
-          if (fc.meta & 32) {
+          if (fmeta & 32) {
             if (!(blk_cell == gid && blk_idx == (d >> 1))) {
               blk = pxb_rand4(C.seed, STREAM_ENERGY, gid, d >> 1);
               blk_cell = gid;
@@ -824,11 +878,19 @@ k_thermal_sample_staged(const DevModel M, const __grid_constant__ pxb_thermal_ce
             }
             const double u2 = (d & 1) ? u53(blk.z, blk.w) : u53(blk.x, blk.y);
             const long long dd = (long long)d;
-            const int comp = (dd >= fc.cnt[0]) + (dd >= fc.cnt[1]) + (dd >= fc.cnt[2]);
-            const bool prim = !(fc.meta & 8);
-            e = invert_row(M, prim ? &M.prim : &M.fb, comp & 1, fc.z1 + (comp >> 1), u2, S, prim);
+            const int comp = (dd >= fcnt0) + (dd >= fcnt1) + (dd >= fcnt2);
+            const bool prim = !(fmeta & 8);
+            const unsigned dr = (unsigned)(fz1 + (comp >> 1) - S.tag);
+            if (prim && S.tag >= 0 && dr < 2u) {
+              const int slot = (comp & 1) * 2 + (int)dr;
+              e = invert_row_staged(M, T.nbins, s_cdf + slot * T.cdf_stride,
+                                    s_guide + slot * T.guide_stride, u2);
+            } else {
+              e = invert_row(M, prim ? &M.prim : &M.fb, comp & 1, fz1 + (comp >> 1), u2, S, prim);
+            }
           } else {
             const Philox4 rn = pxb_rand4(C.seed, STREAM_ENERGY, gid, d);
+            const FastCell fc = fcs[kc];
             e = fast_draw(M, C, fc, i, u53(rn.x, rn.y), u53(rn.z, rn.w), S);
           }
           if (M.binscale_log) e = exp10(e);
