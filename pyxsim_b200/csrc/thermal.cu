@@ -686,7 +686,7 @@ __device__ __forceinline__ double invert_row_staged(const DevModel& M, int nb, c
 // completing on one mbarrier, and stay there across chunks while the temperature bin does not
 // change.  Inside a chunk every warp owns 64-photon tiles (no CTA barriers); photons whose
 // component lives in a staged row gather from shared memory, all others from L1/L2.
-constexpr int STG_THREADS = 768;
+constexpr int STG_THREADS = 1024;
 constexpr int STG_WARPS = STG_THREADS / 32;
 constexpr int STG_WTILE = 128;
 constexpr int STG_CHUNK = 32768;
