@@ -160,7 +160,8 @@ int pxb_interp_spec(const pxb_model* model, int64_t n, const double* x_vals,
  * (thread per photon); every other cell gets its own blended + clipped CDF in shared memory
  * (CTA per cell).  The order of the photons inside a cell is not a contract (the reference
  * sorts its uniforms, base.py:481). */
-int pxb_thermal_sample_workspace_bytes(int64_t n_active, int64_t n_photons, int64_t* bytes);
+int pxb_thermal_sample_workspace_bytes(const pxb_model* model, int64_t n_active,
+                                       int64_t n_photons, int64_t* bytes);
 int pxb_thermal_sample(const pxb_model* model, const pxb_thermal_cells* cells,
                        int64_t n_active, const int64_t* idx, const int64_t* nph,
                        const int64_t* poff, int64_t n_photons, double* energies,

@@ -4,6 +4,7 @@
 // Reference path: ThermalSourceModel.process_data photons branch,
 // pyxsim/source_models/thermal_sources/base.py:335-524, with the table lookup of
 // pyxsim/spectral_models.py:34-47,63-82,429-462 and pyxsim/lib/interpolate.pyx.
+#include <cstdlib>
 #include "thermal.cuh"
 #include <new>
 #include <vector>
@@ -469,7 +470,9 @@ k_thermal_sample_cta(const DevModel M, const __grid_constant__ pxb_thermal_cells
 struct FastCell {
   int z1;        // first row
   int meta;      // bits 0-2: number of rows, bit 3: fallback table, bit 4: eligible,
-                 // bit 5: split mode (cnt valid) instead of probability mode (cum valid)
+                 // bit 5: split mode (cnt valid) instead of probability mode (cum valid),
+                 // bit 6: general split (cnt = cumulative counts per ROW, the split over the
+                 //        row's tables is in the per-cell side array)
   union {
     double cum[3];     // cumulative row probabilities (last is implicitly 1)
     long long cnt[3];  // split mode: cumulative photon counts of the components
@@ -487,8 +490,13 @@ __device__ __forceinline__ int fast_row(const DevTable* t, int z1, int nr, int r
 // sequential binomial draws (a multinomial draw -- the same joint distribution as letting every
 // photon pick its component independently), so the per-photon work is just the CDF inversion
 // and one Philox block serves two photons.
+// GENERAL = false: everything except the general split, which is only REQUESTED (meta bit 7) so
+// that the few cells that want it can be handled by a compacted second pass instead of stalling
+// the 31 other lanes of their warp; GENERAL = true: that second pass.
+template <bool GENERAL>
 __device__ __forceinline__ FastCell fast_setup(const DevModel& M, const pxb_thermal_cells& C,
-                                            int64_t i, int64_t N) {
+                                            int64_t i, int64_t N, int64_t* tabcum,
+                                            int split_factor = 6) {
   FastCell fc;
   const double kT = C.kT[i];
   const double nH = C.nH ? C.nH[i] : 0.0;
@@ -551,6 +559,69 @@ __device__ __forceinline__ FastCell fast_setup(const DevModel& M, const pxb_ther
       for (int c = last_ne; c < 3; ++c) fc.cnt[c] += left;
     }
     fc.meta |= 32;
+  } else if (ok && tabcum && C.nvar > 0 && N >= split_factor * (int64_t)(mx.nr * (2 + C.nvar))) {
+    if (!GENERAL) {
+      fc.meta |= 128;
+      return fc;
+    }
+    // Any other table shape (2-D tables blend four rows; variable elements add tables): the
+    // same multinomial split done hierarchically -- N over the rows, then every row's share
+    // over its tables -- with the within-row cumulative counts in the side array.  Only with
+    // variable elements (whose per-photon component choice loops over the element tables; a
+    // binomial draw costs about as much as ten such choices, hence the threshold); without them
+    // the per-photon choice is cheap and the sampler is bound by the CDF gathers anyway
+    // (measured on the 2-D table configuration: the split made it slower).
+    const int ntab = 2 + C.nvar;
+    CellStream rs(C.seed, STREAM_SPLIT, (uint64_t)(C.cell_id0 + i));
+    double rest = tot;
+    int64_t left = N, acc = 0;
+    int64_t nrow[4] = {0, 0, 0, 0};
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      if (r < mx.nr) {
+        int64_t nk;
+        if (r == last) nk = left;
+        else if (r > last) nk = 0;
+        else nk = binomial_draw(left, rest > 0.0 ? fmin(fmax(s[r] / rest, 0.0), 1.0) : 0.0, rs);
+        left -= nk;
+        rest -= s[r];
+        nrow[r] = nk;
+        acc += nk;
+      }
+      if (r < 3) fc.cnt[r] = (r < mx.nr) ? acc : N;
+    }
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      if (r >= mx.nr) continue;
+      const int row = mx.row[r];
+      int64_t* tc = tabcum + r * ntab;
+      // the row's component weights: cosmic, Z * metal, e_k * var_k; last non-zero one takes
+      // whatever the conditional draws leave
+      double A = 0.0;
+      int last_t = 0;
+      for (int tb = 0; tb < ntab; ++tb) {
+        const double a = tb == 0 ? __ldg(t->rs_c + row)
+                       : tb == 1 ? Z * __ldg(t->rs_m + row)
+                                 : cell_elem(C, tb - 2, i, xh) * __ldg(t->rs_v + (size_t)(tb - 2) * t->nrows + row);
+        A += a;
+        if (a > 0.0) last_t = tb;
+      }
+      int64_t lt = nrow[r], at = 0;
+      for (int tb = 0; tb < ntab; ++tb) {
+        const double a = tb == 0 ? __ldg(t->rs_c + row)
+                       : tb == 1 ? Z * __ldg(t->rs_m + row)
+                                 : cell_elem(C, tb - 2, i, xh) * __ldg(t->rs_v + (size_t)(tb - 2) * t->nrows + row);
+        int64_t nk;
+        if (tb == last_t) nk = lt;
+        else if (tb > last_t || lt == 0) nk = 0;
+        else nk = binomial_draw(lt, A > 0.0 ? fmin(fmax(a / A, 0.0), 1.0) : 0.0, rs);
+        lt -= nk;
+        A -= a;
+        at += nk;
+        tc[tb] = at;
+      }
+    }
+    fc.meta |= 64;
   }
   return fc;
 }
@@ -734,17 +805,49 @@ k_thermal_cellprep(const DevModel M, const __grid_constant__ pxb_thermal_cells C
                    int64_t n_active, const int64_t* __restrict__ idx,
                    const int64_t* __restrict__ poff, FastCell* __restrict__ fcs,
                    int64_t* __restrict__ tile_cell, int64_t* __restrict__ list,
-                   unsigned long long* __restrict__ list_count) {
+                   unsigned long long* __restrict__ list_count, int64_t* __restrict__ tabcum,
+                   int64_t* __restrict__ glist, unsigned long long* __restrict__ glist_count,
+                   int split_factor) {
   const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (k >= n_active) return;
-  const int64_t a = poff[k], b = poff[k + 1];
-  const FastCell fc = fast_setup(M, C, idx[k], b - a);
-  fcs[k] = fc;
-  if (!(fc.meta & 16) && b > a) {
-    const unsigned long long slot = atomicAdd(list_count, 1ull);
-    list[slot] = k;
+  bool want_general = false;
+  if (k < n_active) {
+    const int64_t a = poff[k], b = poff[k + 1];
+    FastCell fc = fast_setup<false>(M, C, idx[k], b - a, tabcum, split_factor);
+    want_general = (fc.meta & 128) != 0;
+    fc.meta &= ~128;
+    fcs[k] = fc;
+    if (!(fc.meta & 16) && b > a) {
+      const unsigned long long slot = atomicAdd(list_count, 1ull);
+      list[slot] = k;
+    }
+    for (int64_t t = (a + STG_WTILE - 1) / STG_WTILE; t * STG_WTILE < b; ++t) tile_cell[t] = k;
   }
-  for (int64_t t = (a + STG_WTILE - 1) / STG_WTILE; t * STG_WTILE < b; ++t) tile_cell[t] = k;
+  // cells that want the general split: one warp-aggregated append
+  const unsigned bal = __ballot_sync(0xffffffffu, want_general);
+  if (bal) {
+    const int lane = threadIdx.x & 31;
+    unsigned long long base = 0;
+    if (lane == 0) base = atomicAdd(glist_count, (unsigned long long)__popc(bal));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (want_general) glist[base + __popc(bal & ((1u << lane) - 1u))] = k;
+  }
+}
+
+// second pass of the cell preparation: the general multinomial split for the cells that asked
+// for it (all lanes busy with binomial draws instead of one in a warp)
+__global__ void __launch_bounds__(128)
+k_thermal_cellsplit(const DevModel M, const __grid_constant__ pxb_thermal_cells C,
+                    const int64_t* __restrict__ idx, const int64_t* __restrict__ poff,
+                    FastCell* __restrict__ fcs, int64_t* __restrict__ tabcum, int tab_stride,
+                    const int64_t* __restrict__ glist,
+                    const unsigned long long* __restrict__ glist_count) {
+  const unsigned long long n = *glist_count;
+  for (unsigned long long j = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; j < n;
+       j += (unsigned long long)gridDim.x * blockDim.x) {
+    const int64_t k = glist[j];
+    FastCell fc = fast_setup<true>(M, C, idx[k], poff[k + 1] - poff[k], tabcum + k * tab_stride, 0);
+    fcs[k] = fc;
+  }
 }
 
 __global__ void __launch_bounds__(STG_THREADS, 1)
@@ -753,7 +856,8 @@ k_thermal_sample_staged(const DevModel M, const __grid_constant__ pxb_thermal_ce
                         const int64_t* __restrict__ poff, int64_t n_photons,
                         double* __restrict__ energies, const FastCell* __restrict__ fcs,
                         const int64_t* __restrict__ tile_cell,
-                        unsigned int* __restrict__ chunk_counter, int use_staging) {
+                        unsigned int* __restrict__ chunk_counter, int use_staging,
+                        const int64_t* __restrict__ tabcum, int tab_stride) {
   extern __shared__ __align__(128) unsigned char dyn[];
   const DevTable& T = M.prim;
   const size_t cdf_bytes = use_staging ? (size_t)T.cdf_stride * sizeof(double) : 0;
@@ -888,6 +992,33 @@ k_thermal_sample_staged(const DevModel M, const __grid_constant__ pxb_thermal_ce
             } else {
               e = invert_row(M, prim ? &M.prim : &M.fb, comp & 1, fz1 + (comp >> 1), u2, S, prim);
             }
+          } else if (fmeta & 64) {
+            // general split: row from the cumulative row counts, table from the side array
+            if (!(blk_cell == gid && blk_idx == (d >> 1))) {
+              blk = pxb_rand4(C.seed, STREAM_ENERGY, gid, d >> 1);
+              blk_cell = gid;
+              blk_idx = d >> 1;
+            }
+            const double u2 = (d & 1) ? u53(blk.z, blk.w) : u53(blk.x, blk.y);
+            const long long dd = (long long)d;
+            const int r = (dd >= fcnt0) + (dd >= fcnt1) + (dd >= fcnt2);
+            const long long din = dd - (r == 0 ? 0 : (r == 1 ? fcnt0 : (r == 2 ? fcnt1 : fcnt2)));
+            const int ntab = 2 + C.nvar;
+            const int64_t* tc = tabcum + kc * tab_stride + r * ntab;
+            int tab = 0;
+            if (ntab <= 8) {
+              for (int tb = 0; tb < ntab - 1; ++tb) tab += (din >= __ldg(tc + tb)) ? 1 : 0;
+            } else {
+              int lo = 0, hi = ntab - 1;     // first tb with din < tc[tb]
+              while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                if (din >= __ldg(tc + mid)) lo = mid + 1; else hi = mid;
+              }
+              tab = lo;
+            }
+            const bool prim = !(fmeta & 8);
+            const DevTable* tbl = prim ? &M.prim : &M.fb;
+            e = invert_row(M, tbl, tab, fast_row(tbl, fz1, fmeta & 7, r), u2, S, prim);
           } else {
             const Philox4 rn = pxb_rand4(C.seed, STREAM_ENERGY, gid, d);
             const FastCell fc = fcs[kc];
@@ -971,11 +1102,19 @@ extern "C" int pxb_interp_spec(const pxb_model* model, int64_t n, const double* 
   return PXB_OK;
 }
 
-extern "C" int pxb_thermal_sample_workspace_bytes(int64_t n_active, int64_t n_photons,
-                                                  int64_t* bytes) {
-  PXB_REQUIRE(bytes && n_active >= 0 && n_photons >= 0, "bad argument");
+// side array of the general split: cumulative counts per (row, table) of every active cell
+static int split_stride(const DevModel& D) {
+  if (D.nvar == 0) return 0;        // no variable elements: no general split (see fast_setup)
+  return (D.density_dependent ? 4 : 2) * (2 + D.nvar);
+}
+
+extern "C" int pxb_thermal_sample_workspace_bytes(const pxb_model* model, int64_t n_active,
+                                                  int64_t n_photons, int64_t* bytes) {
+  PXB_REQUIRE(model && bytes && n_active >= 0 && n_photons >= 0, "bad argument");
   const int64_t ntiles = (n_photons + STG_WTILE - 1) / STG_WTILE;
-  *bytes = (4 + n_active + ntiles + 1) * (int64_t)sizeof(int64_t) + n_active * (int64_t)sizeof(FastCell);
+  const int64_t stride = split_stride(model->dev);
+  *bytes = (4 + n_active + ntiles + 1) * (int64_t)sizeof(int64_t) + n_active * (int64_t)sizeof(FastCell) +
+           (stride ? n_active * (stride + 1) * (int64_t)sizeof(int64_t) : 0);
   return PXB_OK;
 }
 
@@ -1005,20 +1144,36 @@ extern "C" int pxb_thermal_sample(const pxb_model* model, const pxb_thermal_cell
   unsigned long long* count = nullptr;
   if (D.fast_ok) {
     int64_t need = 0;
-    pxb_thermal_sample_workspace_bytes(n_active, n_photons, &need);
+    pxb_thermal_sample_workspace_bytes(model, n_active, n_photons, &need);
     PXB_REQUIRE(workspace && workspace_bytes >= need, "sample workspace too small (%lld < %lld)",
                 (long long)workspace_bytes, (long long)need);
-    // workspace: [count, chunk counter, pad, pad | list[n_active] | tile_cell[ntiles+1] | FastCell[n_active]]
+    // workspace: [count, chunk counter, pad, pad | list[n_active] | tile_cell[ntiles+1] | FastCell[n_active]
+    //             | general-split side array [n_active][rows * tables] | general-split cell list [n_active]]
     const int64_t ntiles = (n_photons + STG_WTILE - 1) / STG_WTILE;
     count = (unsigned long long*)workspace;
     unsigned int* chunk_counter = (unsigned int*)((int64_t*)workspace + 2);
     list = (int64_t*)workspace + 4;
     int64_t* tile_cell = list + n_active;
     FastCell* fcs = (FastCell*)(tile_cell + ntiles + 1);
+    const int tab_stride = split_stride(D);
+    int64_t* tabcum = tab_stride ? (int64_t*)(fcs + n_active) : nullptr;
+    int64_t* glist = tab_stride ? tabcum + n_active * (int64_t)tab_stride : nullptr;
+    unsigned long long* glist_count = (unsigned long long*)workspace + 3;
+    if (getenv("PXB_NO_GENERAL_SPLIT")) tabcum = nullptr;   // diagnostic: per-photon component choice
+    int split_factor = 6;
+    if (const char* sf = getenv("PXB_SPLIT_FACTOR")) split_factor = atoi(sf) > 0 ? atoi(sf) : 6;
     PXB_CUDA(cudaMemsetAsync(workspace, 0, 4 * sizeof(int64_t), st));
     k_thermal_cellprep<<<(unsigned)((n_active + 255) / 256), 256, 0, st>>>(
-        D, *cells, n_active, idx, poff, fcs, tile_cell, list, count);
+        D, *cells, n_active, idx, poff, fcs, tile_cell, list, count, tabcum, glist, glist_count,
+        split_factor);
     PXB_LAUNCH_CHECK();
+    if (tabcum) {
+      int64_t gs = (n_active + 127) / 128;
+      if (gs > (int64_t)pxb_sm_count() * 16) gs = (int64_t)pxb_sm_count() * 16;
+      k_thermal_cellsplit<<<(unsigned)gs, 128, 0, st>>>(D, *cells, idx, poff, fcs, tabcum, tab_stride,
+                                                        glist, glist_count);
+      PXB_LAUNCH_CHECK();
+    }
     // rows are staged in shared memory when the model is a plain 1-D table whose four blended
     // rows fit beside the per-warp offsets; otherwise the same kernel gathers from L1/L2
     const size_t off_bytes = (size_t)STG_WARPS * (STG_WTILE + 2) * sizeof(int64_t);
@@ -1032,7 +1187,8 @@ extern "C" int pxb_thermal_sample(const pxb_model* model, const pxb_thermal_cell
     int64_t g2 = pxb_sm_count();
     if (g2 > nchunks) g2 = nchunks;
     k_thermal_sample_staged<<<(unsigned)g2, STG_THREADS, stg_smem, st>>>(
-        D, *cells, n_active, idx, poff, n_photons, energies, fcs, tile_cell, chunk_counter, use_staging);
+        D, *cells, n_active, idx, poff, n_photons, energies, fcs, tile_cell, chunk_counter, use_staging,
+        tabcum, tab_stride);
     PXB_LAUNCH_CHECK();
   }
   k_thermal_sample_cta<<<(unsigned)grid, SAMPLE_THREADS, smem, st>>>(

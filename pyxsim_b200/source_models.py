@@ -490,7 +490,7 @@ class ThermalSourceModel(SourceModel):
             return None
         out.energy = empty(out.n_photons)
         need = C.c_int64()
-        _lib.call("pxb_thermal_sample_workspace_bytes", out.n_cells, out.n_photons, C.byref(need))
+        _lib.call("pxb_thermal_sample_workspace_bytes", dm.handle, out.n_cells, out.n_photons, C.byref(need))
         ws = torch.empty(need.value, dtype=torch.uint8, device=out.energy.device)
         with stage("thermal_sample"):
             _lib.call("pxb_thermal_sample", dm.handle, C.byref(Cs), out.n_cells, ptr(out.idx),

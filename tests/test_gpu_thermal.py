@@ -423,6 +423,69 @@ def test_energy_distribution_with_variable_elements(cuda, oracle):
     H.assert_distributions_agree(run, seeds=((3, 4), (13, 14)))
 
 
+def test_component_split_fractions_with_disjoint_bands(cuda, oracle):
+    """Multinomial split of a cell's photons over its mixture components (4 rows-x-tables for a
+    plain table, rows x (2 + nvar) with variable elements).  The tables here emit in DISJOINT
+    energy bands, so every photon's table can be read off its energy: per table, the counts
+    summed over cells must match sum_cells N_cell * q_cell,table with q from the oracle's blended
+    spectrum, both for bright cells (split mode) and for cells with a handful of photons
+    (per-photon component choice)."""
+    nT, nbins, nvar = 12, 400, 2
+    rng = np.random.RandomState(21)
+    Tvals = np.logspace(np.log10(0.3), np.log10(20.0), nT)
+    ebins = np.linspace(0.1, 10.0, nbins + 1)
+    band = nbins // (2 + nvar)
+    tabs = np.zeros((2 + nvar, nT, nbins))
+    for tb in range(2 + nvar):
+        shape = rng.uniform(0.2, 1.0, band) * 1e-16
+        for r in range(nT):
+            tabs[tb, r, tb * band:(tb + 1) * band] = shape * (1.0 + 0.3 * tb) * (r + 1.0) ** (0.5 * (tb + 1))
+    t = dict(Tvals=Tvals, ebins=ebins, cosmic=tabs[0], metal=tabs[1], var=tabs[2:], binscale="linear")
+    om = H.oracle_model(oracle, t)
+    for target, label in ((100.0, "bright"), (3.0, "dim")):
+        n = 3000
+        kT = np.exp(rng.uniform(np.log(0.4), np.log(15.0), n))
+        em = 1.0e60 * rng.lognormal(0, 0.3, n)
+        extra = {("gas", "Z"): rng.uniform(0.0, 1.0, n), ("gas", "O"): rng.uniform(0.0, 2.0, n),
+                 ("gas", "Fe"): rng.uniform(0.0, 2.0, n)}
+        extra[("gas", "O")][::5] = 0.0          # empty components
+        cfg = dict(kT_min=0.025, kT_max=64.0, Zmet="Z", Zconvert=1.0, z_by_xh=False, spectral_norm=1.0,
+                   var_elem=[("O", 1.0, False), ("Fe", 1.0, False)])
+        a = dict(kT=kT, em=em, Z=extra[("gas", "Z")], O=extra[("gas", "O")], Fe=extra[("gas", "Fe")])
+        cut, tot, lam = oracle.thermal_spectra(om, cfg, a)
+        assert cut.all()
+        norm = target / np.median(lam)
+        src = H.cells_source(kT, em, extra=extra)
+        model = px.ThermalSourceModel(H.product_model(t), 0.1, 10.0, nbins, ("gas", "Z"),
+                                      var_elem={"O": ("gas", "O"), "Fe": ("gas", "Fe")},
+                                      temperature_field=TF, prng=31)
+        model.setup_model("photons", src, 0.0)
+        out = model.generate_chunk(_chunk(src), norm)
+        e = out.energy.cpu().numpy()
+        nph = out.nph.cpu().numpy()
+        idx = out.idx.cpu().numpy()
+        assert (np.median(nph) > 40) if label == "bright" else (np.median(nph) < 8)
+        q = np.stack([tot[:, tb * band:(tb + 1) * band].sum(axis=1) for tb in range(2 + nvar)], axis=1)
+        q /= q.sum(axis=1, keepdims=True)
+        comp = np.minimum(((e - 0.1) / (9.9 / nbins)).astype(int) // band, 1 + nvar)
+        cell_of = np.repeat(np.arange(idx.size), nph)
+        obs = np.zeros((idx.size, 2 + nvar))
+        np.add.at(obs, (cell_of, comp), 1.0)
+        N = nph[:, None].astype(float)
+        qa = q[idx]
+        assert np.all(obs[qa == 0.0] == 0.0)                       # empty components stay empty
+        z = (obs.sum(0) - (N * qa).sum(0)) / np.sqrt((N * qa * (1 - qa)).sum(0))
+        assert np.all(np.abs(z) < 4.5), (label, z)
+        # per-cell: chi^2 over cells with enough photons is chi^2-distributed with (ncomp-1) dof each
+        if label == "bright":
+            from scipy import stats
+
+            ok = (qa > 0).all(axis=1)
+            chi2 = (((obs - N * qa) ** 2 / np.where(qa > 0, N * qa, 1.0))[ok]).sum()
+            dof = ok.sum() * (1 + nvar)
+            assert stats.chi2.sf(chi2, dof) > 1e-4 and stats.chi2.cdf(chi2, dof) > 1e-4, (chi2, dof)
+
+
 def test_large_nbins_and_single_bright_cell(cuda, oracle):
     """nbins = 20000 (the reference's own test binning, tests/test_beta_model.py) does not fit
     the staged rows: the sampler gathers from L2 instead, and the general kernel holds a 160 KB
