@@ -28,6 +28,8 @@
  *                                 (+ soxs get_wabs_absorb used by WabsModel :633-635)
  *   pxb_absorb_decide ........... AbsorptionModel.absorb_photons, spectral_models.py:563-583
  *                                 (diagnostic: explicit uniforms)
+ *   pxb_column_lookup ........... nH cube interpolation at the rotated cell centres,
+ *                                 photon_list.py:672-680 (scipy interpn, linear, fill 0)
  *   pxb_project ................. the projection tile loop, photon_list.py:686-799:
  *                                 doppler_shift + absorb_photons (spectral_models.py:563-583)
  *                                 + scatter_events (sky_functions.pyx:40-147) or
@@ -347,6 +349,16 @@ int pxb_pixel_to_cel(int64_t n, double* xsky, double* ysky, double ra0_deg, doub
  * (absorb_kind, nH, abs_*). */
 int pxb_absorb_transmission(const pxb_project_params* params, int64_t n, const double* energy,
                             double* trans_out, void* stream);
+/* Internal-absorption columns (photon_list.py:672-680): rotate every cell centre into the
+ * projection frame, pos = (r.x_hat, r.y_hat, r.z_hat) with unit_vectors[9] row-major
+ * (east, north, normal), and interpolate the column-density cube nH_grid[nw][nw][nd] (C order)
+ * trilinearly at pos on the node arrays wmid[nw] (both sky axes) and dmid[nd] (depth):
+ * scipy.interpolate.interpn(..., method="linear", bounds_error=False, fill_value=0.0).  The
+ * result is what pxb_project_params.nH_cell expects. */
+int pxb_column_lookup(int64_t n_cells, const double* x, const double* y, const double* z,
+                      const double* unit_vectors, int64_t nw, int64_t nd, const double* wmid,
+                      const double* dmid, const double* nH_grid, double* nH_cell_out,
+                      void* stream);
 /* Diagnostic: the projection kernels' own absorption decision u < exp(-sigma(E)*nH) for n
  * caller-supplied (energy, u) pairs (AbsorptionModel.absorb_photons, spectral_models.py:563-583,
  * with the uniforms made explicit); survive_out[i] = 1 if photon i is detected.  Lets a test put

@@ -501,6 +501,18 @@ class WabsAbsorb(TableAbsorb):
         return np.exp(-sigma * self._nH * 1.0e22)
 
 
+def column_lookup(x, y, z, unit_vectors, wbins, dbins, nH_grid):
+    """Internal-absorption column of every cell (photon_list.py:542-546,672-680): the cube is
+    sampled at ``pos = unit_vectors . (x, y, z)`` with scipy's ``interpn`` exactly as the
+    reference calls it (linear, no bounds error, fill value 0)."""
+    from scipy.interpolate import interpn
+
+    wmid = 0.5 * (wbins[1:] + wbins[:-1])
+    dmid = 0.5 * (dbins[1:] + dbins[:-1])
+    pos = np.dot(unit_vectors, np.array([x, y, z]))
+    return interpn((wmid, wmid, dmid), nH_grid, pos.T, bounds_error=False, fill_value=0.0)
+
+
 # ---------------------------------------------------------------------------------------
 # projection: pyxsim/photon_list.py:661-808
 # ---------------------------------------------------------------------------------------

@@ -4,6 +4,12 @@
 Public names follow ``pyxsim/__init__.py:11-31`` for the parts that belong to the hot path.
 """
 from .data import ArrayDataSource, Cosmology
+from .internal_absorption import (
+    column_density_at_cells,
+    make_column_density_map,
+    read_column_file,
+    write_column_file,
+)
 from .photon_list import (
     DeviceList,
     drop_list,

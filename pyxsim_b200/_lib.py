@@ -165,6 +165,8 @@ SIGNATURES = {
                                    c_void_p]),
     "pxb_absorb_transmission": (C.c_int, [_P(ProjectParams), C.c_int64, c_void_p, c_void_p,
                                           c_void_p]),
+    "pxb_column_lookup": (C.c_int, [C.c_int64, c_void_p, c_void_p, c_void_p, c_void_p, C.c_int64,
+                                    C.c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "pxb_absorb_decide": (C.c_int, [_P(ProjectParams), C.c_int64, c_void_p, c_void_p, c_void_p,
                                     c_void_p]),
 }

@@ -1076,6 +1076,73 @@ extern "C" int pxb_pixel_to_cel(int64_t n, double* xsky, double* ysky, double ra
   return PXB_OK;
 }
 
+// ---------------------------------------------------------------------------------------
+// internal absorption: column-density cube lookup (photon_list.py:672-680)
+// ---------------------------------------------------------------------------------------
+// scipy RegularGridInterpolator, method="linear": per axis i = clip(searchsorted(g, x) - 1, 0,
+// n-2), t = (x - g[i]) / (g[i+1] - g[i]); outside [g[0], g[n-1]] on any axis -> fill value 0.
+__device__ __forceinline__ bool grid_locate(const double* __restrict__ g, int64_t n, double x,
+                                            int64_t& i, double& t) {
+  if (!(x >= __ldg(g)) || !(x <= __ldg(g + n - 1))) return false;   // NaN is outside too
+  int64_t lo = 0, hi = n - 1;   // g[lo] <= x <= g[hi]
+  while (hi - lo > 1) {
+    const int64_t mid = (lo + hi) >> 1;
+    if (__ldg(g + mid) <= x) lo = mid; else hi = mid;
+  }
+  // searchsorted(side="left") - 1 puts x == g[k] (k > 0) in interval k-1 with t = 1; the
+  // interpolant is continuous there, the choice only matters for bit patterns
+  if (lo > 0 && __ldg(g + lo) == x) --lo;
+  i = lo;
+  const double g0 = __ldg(g + lo), g1 = __ldg(g + lo + 1);
+  t = (x - g0) / (g1 - g0);
+  return true;
+}
+
+__global__ void __launch_bounds__(256)
+k_column_lookup(int64_t n, const double* __restrict__ x, const double* __restrict__ y,
+                const double* __restrict__ z, const double* __restrict__ uv, int64_t nw,
+                int64_t nd, const double* __restrict__ wmid, const double* __restrict__ dmid,
+                const double* __restrict__ grid, double* __restrict__ out) {
+  const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= n) return;
+  const double px = x[c], py = y[c], pz = z[c];
+  const double a = __ldg(uv + 0) * px + __ldg(uv + 1) * py + __ldg(uv + 2) * pz;
+  const double b = __ldg(uv + 3) * px + __ldg(uv + 4) * py + __ldg(uv + 5) * pz;
+  const double d = __ldg(uv + 6) * px + __ldg(uv + 7) * py + __ldg(uv + 8) * pz;
+  int64_t ia, ib, id;
+  double ta, tb, td;
+  double v = 0.0;
+  if (grid_locate(wmid, nw, a, ia, ta) && grid_locate(wmid, nw, b, ib, tb) &&
+      grid_locate(dmid, nd, d, id, td)) {
+#pragma unroll
+    for (int ca = 0; ca < 2; ++ca)
+#pragma unroll
+      for (int cb = 0; cb < 2; ++cb)
+#pragma unroll
+        for (int cd = 0; cd < 2; ++cd) {
+          // same association and no fused multiply-add: bit-identical to scipy's hypercube sum
+          const double w = __dmul_rn(__dmul_rn(ca ? ta : 1.0 - ta, cb ? tb : 1.0 - tb),
+                                     cd ? td : 1.0 - td);
+          v = __dadd_rn(v, __dmul_rn(__ldg(grid + ((ia + ca) * nw + (ib + cb)) * nd + (id + cd)), w));
+        }
+  }
+  out[c] = v;
+}
+
+extern "C" int pxb_column_lookup(int64_t n_cells, const double* x, const double* y, const double* z,
+                                 const double* unit_vectors, int64_t nw, int64_t nd,
+                                 const double* wmid, const double* dmid, const double* nH_grid,
+                                 double* nH_cell_out, void* stream) {
+  PXB_REQUIRE(n_cells >= 0, "bad n_cells");
+  PXB_REQUIRE(nw >= 2 && nd >= 2, "the column cube needs at least two nodes per axis");
+  if (n_cells == 0) return PXB_OK;
+  PXB_REQUIRE(x && y && z && unit_vectors && wmid && dmid && nH_grid && nH_cell_out, "NULL argument");
+  k_column_lookup<<<(unsigned)((n_cells + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      n_cells, x, y, z, unit_vectors, nw, nd, wmid, dmid, nH_grid, nH_cell_out);
+  PXB_LAUNCH_CHECK();
+  return PXB_OK;
+}
+
 __global__ void __launch_bounds__(256)
 k_absorb_decide(const __grid_constant__ pxb_project_params P, int64_t n,
                 const double* __restrict__ e, const double* __restrict__ u,

@@ -19,6 +19,7 @@ import torch
 from . import _lib, constants as K, parallel
 from .data import ArrayDataSource, Cosmology
 from .device import empty, ptr, stream_ptr, to_device, require_cuda
+from .internal_absorption import column_density_at_cells, read_column_file
 from .profiling import stage
 from .spectral_models import absorb_models
 from .utils import get_normal_and_north, mylog, parse_value, prng_seed
@@ -413,9 +414,15 @@ def _project_photons(obs, photon_prefix, event_prefix, normal, sky_center, absor
             raise ValueError("You must specify an absorption model if you are using an absorption file!")
         if obs == "internal":
             raise ValueError("You cannot use an absorption file with an internal observer!")
-        raise NotImplementedError(
-            "column_file (internal absorption maps made by yt projections) is a 'next' row; pass "
-            "per-cell columns with nH_cell= instead")
+        if nH_cell is not None:
+            raise ValueError("Give either column_file or nH_cell, not both!")
+        col = read_column_file(column_file)
+        if not np.isclose(col["normal"], L).all():
+            raise ValueError("The value of the normal vector in the absorption file does not match "
+                             "the value in the call to project_photons!")
+        if not np.isclose(col["north"], north_vector_out).all():
+            raise ValueError("The value of the north vector in the absorption file does not match "
+                             "the value in the call to project_photons!")
 
     sky_center = np.asarray(sky_center, dtype="float64")
     if isinstance(absorb_model, str):
@@ -510,6 +517,11 @@ def _project_photons(obs, photon_prefix, event_prefix, normal, sky_center, absor
             keep = absorb_model._fill_params(P)
             if nH is None:
                 P.nH = 0.0
+        if column_file is not None:
+            # photon_list.py:672-680: the cube is sampled at the cells' positions in the
+            # (east, north, normal) frame of the Orientation, also for an on-axis normal
+            nH_cell = column_density_at_cells(dev["x"], dev["y"], dev["z"], uv, col["wbins"],
+                                              col["dbins"], col["nH"])
         if nH_cell is not None:
             if absorb_model is None:
                 raise ValueError("You must specify an absorption model to use per-cell columns!")

@@ -18,6 +18,7 @@ KERNELS_PER_CALL = {
     "pxb_line_sample": 1, "pxb_project": 8, "pxb_doppler_shift": 1, "pxb_pixel_to_cel": 1,
     "pxb_absorb_transmission": 1,
     "pxb_absorb_decide": 1,
+    "pxb_column_lookup": 1,
 }
 
 

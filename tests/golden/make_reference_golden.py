@@ -70,6 +70,11 @@ def inputs():
                       vy=rng.normal(0, 500, nc), vz=rng.normal(100, 500, nc),
                       dx=rng.uniform(2.0, 30.0, nc), num_photons=nph,
                       energy=np.exp(rng.uniform(np.log(0.1), np.log(10.0), int(nph.sum()))))
+    # internal-absorption cube (internal_absorption.py:117-126) smaller than the cell cloud, so that
+    # some cells fall outside it (fill value 0)
+    nw, nd = 12, 9
+    I["col"] = dict(wbins=np.linspace(-260.0, 260.0, nw + 1), dbins=np.linspace(-240.0, 240.0, nd + 1),
+                    nH=0.4 * rng.lognormal(0.0, 1.0, (nw, nw, nd)))
     return I
 
 
@@ -87,13 +92,17 @@ PROJ_CASES = {
     # no absorption: every photon survives, eobs is the deterministic Doppler-shifted energy
     "doppler_only": dict(obs="external", data_type="cells", normal=[0.3, -0.5, 0.8], kw=dict(save_los=True),
                          seed=27, absorb=False),
+    # column_file: nH cube interpolated at the rotated cell centres + per-cell absorption at the
+    # source-frame energy (photon_list.py:524-546,672-680,715-723), on top of a foreground column
+    "column_file": dict(obs="external", data_type="cells", normal=[0.3, -0.4, 0.85],
+                        kw=dict(north_vector=[0.1, 0.9, 0.2], column_file="cols.h5"), seed=29),
     "doppler_internal": dict(obs="internal", data_type="cells", normal=[0.3, -0.5, 0.8], kw=dict(),
                              seed=28, absorb=False),
 }
 
 
 def run_reference(I):
-    from oracle import ref_import as R
+    from oracle import ref_glue as O, ref_import as R
 
     M = R.modules()
     U = R.UArray
@@ -208,6 +217,15 @@ def run_reference(I):
                abs_det=am.absorb_photons(ee, prng=np.random.RandomState(18)))
     pl_mod = M["photon_list"]
     d = I["plist"]
+    col = I["col"]
+    cc = PROJ_CASES["column_file"]
+    fc = R.FakeH5File("cols.h5", "w")
+    pc = fc.create_group("parameters")
+    pc.attrs["normal"] = np.array(cc["normal"])
+    pc.attrs["north"] = O.orientation(cc["normal"], cc["kw"]["north_vector"])[1]
+    gc = fc.create_group("data")
+    for k in ("wbins", "dbins", "nH"):
+        gc.create_dataset(k, data=col[k])
     for name, case in PROJ_CASES.items():
         fph = R.FakeH5File(f"ph_{name}.h5", "w")
         p = fph.create_group("parameters")

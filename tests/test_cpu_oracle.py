@@ -155,8 +155,13 @@ def _replay_reference_cases(O, I, cases):
                       fid_redshift=0.05 if ext else 0.0)
         akw = dict(absorb_model=O.TableAbsorb(0.15, ab["energy"], ab["sigma"]), nH=0.15) \
             if case.get("absorb", True) else {}
+        kw = dict(case["kw"])
+        if kw.pop("column_file", None):
+            col = I["col"]
+            uv = O.orientation(case["normal"], kw.get("north_vector"))
+            kw["nH_int"] = O.column_lookup(d["x"], d["y"], d["z"], uv, col["wbins"], col["dbins"], col["nH"])
         ref = O.project_photons({k: v.copy() for k, v in d.items()}, params, case["normal"], [30.0, 45.0],
-                                np.random.RandomState(case["seed"]), **akw, **case["kw"])
+                                np.random.RandomState(case["seed"]), **akw, **kw)
         out[f"pj_{name}_n"] = ref["n_events"]
         for k in ("xsky", "ysky", "eobs"):
             out[f"pj_{name}_{k}"] = ref[k]

@@ -284,6 +284,62 @@ def test_internal_absorption_per_cell(cuda, oracle):
     assert _ks_ok(ev["eobs"], ref["eobs"])
 
 
+def test_column_file_internal_absorption(cuda, oracle, tmp_path):
+    """column_file= (photon_list.py:524-546,672-680,715-723): the nH cube is interpolated at the
+    rotated cell centres -- scipy's interpn as the reference calls it, to 1e-13; cells
+    outside the cube get 0 -- and each cell's photons are absorbed at their source-frame energy
+    with that column.  Detected fractions per energy band against the oracle projection."""
+    rng = np.random.RandomState(5)
+    d, params = make_plist(n_cells=4000, mean_ph=60.0, seed=31)
+    normal, north = [0.3, -0.4, 0.85], [0.1, 0.9, 0.2]
+    L, north_out, uv = px.utils.get_normal_and_north(normal, north_vector=north)
+    nw, nd = 24, 16
+    wbins = np.linspace(-250.0, 250.0, nw + 1)       # smaller than the +-300 kpc box: some cells fall outside
+    dbins = np.linspace(-280.0, 280.0, nd + 1)
+    cube = 0.3 * rng.lognormal(0.0, 1.0, (nw, nw, nd))
+    fn = px.write_column_file(str(tmp_path / "columns.h5"), L, north_out, wbins, dbins, cube)
+    col = px.read_column_file(fn)
+    np.testing.assert_array_equal(col["nH"], cube)
+    # the lookup alone: exact nodes, cube faces and outside points included
+    x, y, z = d["x"].copy(), d["y"].copy(), d["z"].copy()
+    wmid = 0.5 * (wbins[1:] + wbins[:-1])
+    inv = np.linalg.inv(uv)
+    x[:3], y[:3], z[:3] = inv @ np.array([[wmid[0], wmid[5], wmid[-1]], [wmid[3], wmid[3], wmid[0]],
+                                          [0.5 * (dbins[0] + dbins[1]), 0.0, 0.5 * (dbins[-1] + dbins[-2])]])
+    got = px.column_density_at_cells(x, y, z, uv, wbins, dbins, cube).cpu().numpy()
+    ref = oracle.column_lookup(x, y, z, uv, wbins, dbins, cube)
+    assert (ref == 0.0).sum() > 50 and (ref > 0).sum() > 1000
+    # (not bit-for-bit: the rotated position comes from a BLAS dot product in the reference)
+    np.testing.assert_allclose(got, ref, rtol=1e-13, atol=0.0)
+    assert np.array_equal(got == 0.0, ref == 0.0)
+    # through project_photons
+    put("colf", d, params)
+    n_ev = px.project_photons("mem:colf", "mem:colf_ev", normal, [30.0, 45.0], absorb_model="wabs",
+                              nH=0.01, north_vector=north, column_file=fn, prng=77)
+    ev, _ = events("colf_ev")
+    nH_int = oracle.column_lookup(d["x"], d["y"], d["z"], uv, wbins, dbins, cube)
+
+    def run(seed_mine, seed_ref):
+        px.project_photons("mem:colf", "mem:colf_ev", normal, [30.0, 45.0], absorb_model="wabs",
+                           nH=0.01, north_vector=north, column_file=fn, prng=seed_mine)
+        e1, _ = events("colf_ev")
+        o = oracle.project_photons(d, params, normal, [30.0, 45.0], np.random.RandomState(seed_ref),
+                                   absorb_model=oracle.WabsAbsorb(0.01), nH=0.01, north_vector=north,
+                                   nH_int=nH_int)
+        assert abs(e1["eobs"].size - o["eobs"].size) < 6 * np.sqrt(o["eobs"].size)
+        return {"eobs": stats.ks_2samp(e1["eobs"], o["eobs"]).pvalue,
+                "xsky": stats.ks_2samp(e1["xsky"], o["xsky"]).pvalue}
+
+    H.assert_distributions_agree(run, seeds=((78, 79), (80, 81)))
+    assert n_ev == ev["eobs"].size
+    # error behaviour of the reference (photon_list.py:526-540)
+    with pytest.raises(ValueError):
+        px.project_photons("mem:colf", "mem:colf_ev", normal, [30.0, 45.0], column_file=fn)
+    with pytest.raises(ValueError):
+        px.project_photons("mem:colf", "mem:colf_ev", [0.0, 0.0, 1.0], [30.0, 45.0], absorb_model="wabs",
+                           nH=0.01, column_file=fn)
+
+
 def test_projection_bit_reproducible_and_stable_order(cuda):
     d, p = make_plist(n_cells=5000, mean_ph=30.0)
     put("rp_ph", d, p)
