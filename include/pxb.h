@@ -26,6 +26,8 @@
  *   pxb_pixel_to_cel ............ pixel_to_cel, sky_functions.pyx:153-179
  *   pxb_absorb_transmission ..... AbsorptionModel.get_absorb, spectral_models.py:556-561
  *                                 (+ soxs get_wabs_absorb used by WabsModel :633-635)
+ *   pxb_thermal_flux ............ make_fluxf + the "luminosity"/"photon_rate" branch of
+ *                                 process_data, spectral_models.py:101-134,464-537; base.py:501-511
  *   pxb_absorb_decide ........... AbsorptionModel.absorb_photons, spectral_models.py:563-583
  *                                 (diagnostic: explicit uniforms)
  *   pxb_column_lookup ........... nH cube interpolation at the rotated cell centres,
@@ -185,6 +187,27 @@ int pxb_thermal_spectrum(const pxb_model* model, const pxb_thermal_cells* cells,
  * the bins with ebins[j] >= emin/shift and ebins[j+1] <= emax/shift; 0 for cut cells. */
 int pxb_thermal_band(const pxb_model* model, const pxb_thermal_cells* cells, int use_energy,
                      double emin, double emax, const double* shift, double* out, void* stream);
+/* Band fluxes of a table, per table row (what make_fluxf tabulates, spectral_models.py:101-134,
+ * 464-478): device arrays [nrows] (vflux: [nvar][nrows] or NULL); fb_* describe the 1-D CIE
+ * fallback table of a density-dependent model (NULL otherwise). */
+typedef struct {
+  const double* cflux;
+  const double* mflux;
+  const double* vflux;
+  const double* fb_cflux;
+  const double* fb_mflux;
+  const double* fb_vflux;
+} pxb_band_flux;
+/* modes "luminosity" / "photon_rate" of ThermalSourceModel.process_data (base.py:501-511) with
+ * the flux function of make_fluxf: out[i] = cell_nrm_i * (cf(T_i) + Z_i mf(T_i) + sum_k e_ik
+ * vf_k(T_i)), 0 for cells failing the cut, NOT clipped.  cf/mf/vf: scipy interp1d (linear) of
+ * the row fluxes in the table's temperature coordinate (spectral_models.py:109-131); for a
+ * density-dependent model the bilinear _get_flux_2d divided by nH inside the (T, nH) table and
+ * the CIE fallback outside (spectral_models.py:482-537).  n_outside_out (device int64,
+ * ACCUMULATED) counts selected cells whose temperature lies outside the 1-D table -- where
+ * scipy's interp1d raises ValueError; their out[i] is NaN. */
+int pxb_thermal_flux(const pxb_model* model, const pxb_thermal_cells* cells,
+                     const pxb_band_flux* band, double* out, int64_t* n_outside_out, void* stream);
 /* power_law_spectrum (spectra.pyx:11-32): spec_out[j] += sum_i shift_i^2 K_i (emid_j/shift_i)^-alpha_i */
 int pxb_powerlaw_spectrum(int64_t ncell, const double* alpha, const double* K, const double* shift,
                           int64_t nbins, const double* emid, double* spec_out, void* stream);

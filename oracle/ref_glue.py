@@ -123,6 +123,37 @@ class TableModel:
         kT = np.atleast_1d(self._Tconv(kT))
         return self.si(kT)
 
+    def make_fluxf(self, emin, emax, energy=False):
+        """ThermalSpectralModel.make_fluxf, spectral_models.py:101-134 (scipy interp1d, linear,
+        bounds_error as scipy defaults it: out-of-table temperatures raise ValueError)."""
+        from scipy.interpolate import interp1d
+
+        eidxs = (self.ebins[:-1] > emin) & (self.ebins[1:] < emax)
+        emid = self.emid[eidxs]
+        if energy:
+            cosmic_flux = (self.cosmic_spec[:, eidxs] * emid).sum(axis=-1)
+            metal_flux = (self.metal_spec[:, eidxs] * emid).sum(axis=-1)
+        else:
+            cosmic_flux = self.cosmic_spec[:, eidxs].sum(axis=-1)
+            metal_flux = self.metal_spec[:, eidxs].sum(axis=-1)
+        cf = interp1d(self.Tvals, cosmic_flux, fill_value=0.0, assume_sorted=True, copy=False)
+        mf = interp1d(self.Tvals, metal_flux, fill_value=0.0, assume_sorted=True, copy=False)
+        if self.var_spec is not None:
+            if energy:
+                var_flux = (self.var_spec[:, :, eidxs] * emid).sum(axis=-1)
+            else:
+                var_flux = self.var_spec[:, :, eidxs].sum(axis=-1)
+            vf = interp1d(self.Tvals, var_flux, axis=1, fill_value=0.0, assume_sorted=True, copy=False)
+        else:
+            def vf(kT):
+                pass
+
+        def _fluxf(kT):
+            kT = self._Tconv(kT)
+            return cf(kT), mf(kT), vf(kT)
+
+        return _fluxf
+
 
 class PionModel:
     """PionSpectralModel.get_spectrum / _get_spectrum_2d, spectral_models.py:429-462"""
@@ -135,8 +166,11 @@ class PionModel:
         self.nbins = self.emid.size
         self.binscale = binscale
         self.Tvals, self.Dvals = np.asarray(Tvals, "float64"), np.asarray(Dvals, "float64")
+        self.cosmic_spec, self.metal_spec = cosmic, metal
         self.var_spec = var
         self.nvar_elem = 0 if var is None else var.shape[0]
+        self.n_T, self.n_D = self.Tvals.size, self.Dvals.size
+        self.dTvals, self.dDvals = np.diff(self.Tvals), np.diff(self.Dvals)
         self.min_table_kT = 10 ** self.Tvals[0] / K_per_keV
         self.max_table_kT = 10 ** self.Tvals[-1] / K_per_keV
         self.min_table_nH = 10 ** self.Dvals[0]
@@ -169,6 +203,118 @@ class PionModel:
             if self.var_spec is not None:
                 vspec[:, use_cie, :] = v2
         return cspec, mspec, vspec
+
+
+def _pion_make_fluxf(self, emin, emax, energy=False):
+    """PionSpectralModel.make_fluxf + _get_flux_2d, spectral_models.py:464-537"""
+    eidxs = (self.ebins[:-1] > emin) & (self.ebins[1:] < emax)
+    emid = self.emid[eidxs]
+    if energy:
+        cosmic_flux = (self.cosmic_spec[:, eidxs] * emid).sum(axis=-1)
+        metal_flux = (self.metal_spec[:, eidxs] * emid).sum(axis=-1)
+    else:
+        cosmic_flux = self.cosmic_spec[:, eidxs].sum(axis=-1)
+        metal_flux = self.metal_spec[:, eidxs].sum(axis=-1)
+    if self.var_spec is not None:
+        var_flux = (self.var_spec[:, :, eidxs] * emid).sum(axis=-1) if energy else \
+            self.var_spec[:, :, eidxs].sum(axis=-1)
+    else:
+        var_flux = None
+    cie_fluxf = self.cie_model.make_fluxf(emin, emax, energy=energy)
+
+    def get_flux_2d(kT, nH, cf, mf, vf):
+        lkT = np.atleast_1d(np.log10(kT * K_per_keV))
+        lnH = np.atleast_1d(np.log10(nH))
+        tidxs = np.searchsorted(self.Tvals, lkT) - 1
+        didxs = np.searchsorted(self.Dvals, lnH) - 1
+        dT = (lkT - self.Tvals[tidxs]) / self.dTvals[tidxs]
+        dn = (lnH - self.Dvals[didxs]) / self.dDvals[didxs]
+        idx1 = np.ravel_multi_index((didxs + 1, tidxs + 1), (self.n_D, self.n_T))
+        idx2 = np.ravel_multi_index((didxs + 1, tidxs), (self.n_D, self.n_T))
+        idx3 = np.ravel_multi_index((didxs, tidxs + 1), (self.n_D, self.n_T))
+        idx4 = np.ravel_multi_index((didxs, tidxs), (self.n_D, self.n_T))
+        dx1 = dT * dn
+        dx2 = dn - dx1
+        dx3 = dT - dx1
+        dx4 = 1.0 + dx1 - dT - dn
+        cflux = dx1 * cf[idx1] + dx2 * cf[idx2] + dx3 * cf[idx3] + dx4 * cf[idx4]
+        mflux = dx1 * mf[idx1] + dx2 * mf[idx2] + dx3 * mf[idx3] + dx4 * mf[idx4]
+        if vf is not None:
+            vflux = dx1[np.newaxis, :] * vf[:, idx1]
+            vflux += dx2[np.newaxis, :] * vf[:, idx2]
+            vflux += dx3[np.newaxis, :] * vf[:, idx3]
+            vflux += dx4[np.newaxis, :] * vf[:, idx4]
+        else:
+            vflux = None
+        return cflux, mflux, vflux
+
+    def _fluxf(kT, nH):
+        kT = np.atleast_1d(kT)
+        nH = np.atleast_1d(nH)
+        use_igm = (kT >= self.min_table_kT) & (kT <= self.max_table_kT)
+        use_igm &= (nH >= self.min_table_nH) & (nH <= self.max_table_nH)
+        use_cie = ~use_igm
+        cflux = np.zeros(kT.size)
+        mflux = np.zeros(kT.size)
+        vflux = np.zeros((self.nvar_elem, kT.size)) if self.var_spec is not None else None
+        if use_igm.sum() > 0:
+            nHi = nH[use_igm]
+            c1, m1, v1 = get_flux_2d(kT[use_igm], nHi, cosmic_flux, metal_flux, var_flux)
+            cflux[use_igm] = c1 / nHi
+            mflux[use_igm] = m1 / nHi
+            if self.var_spec is not None:
+                vflux[:, use_igm] = v1 / nHi[np.newaxis, :]
+        if use_cie.sum() > 0:
+            c2, m2, v2 = cie_fluxf(kT[use_cie])
+            cflux[use_cie] = c2
+            mflux[use_cie] = m2
+            if self.var_spec is not None:
+                vflux[:, use_cie] = v2
+        return cflux, mflux, vflux
+
+    return _fluxf
+
+
+PionModel.make_fluxf = _pion_make_fluxf
+
+
+def thermal_field_mode(model, cfg, a, mode, emin, emax, fluxf=None, shift=None):
+    """The per-cell field modes of ThermalSourceModel.process_data (base.py:304-332,497-511,526):
+    "luminosity" / "photon_rate" (and the unshifted intensities) through ``fluxf``; shifted
+    "intensity" / "photon_intensity" through the compiled reference ``make_band`` on the clipped
+    spectrum.  Returns the array over ALL cells (0 where the cut removes a cell).  ``shift``: per
+    selected cell; unlike the reference (which hands make_band the whole chunk's shift array for
+    every 100-cell tile, base.py:499) each tile gets its own slice."""
+    cut, kT, cell_nrm, nH, metalZ, elemZ = thermal_select(cfg, a)
+    n = kT.size
+    ret = np.zeros(cut.size)
+    idxs = np.where(cut)[0]
+    shifted = mode.endswith("intensity") and shift is not None
+    for b, e in _chunked(n):
+        if shifted:
+            if model._density_dependence:
+                cspec, mspec, vspec = model.get_spectrum(kT[b:e], nH[b:e])
+            else:
+                cspec, mspec, vspec = model.get_spectrum(kT[b:e])
+            t = cspec
+            t += metalZ[b:e, np.newaxis] * mspec
+            if elemZ is not None:
+                t += np.sum(elemZ[:, b:e, np.newaxis] * vspec, axis=0)
+            np.clip(t, 0.0, None, out=t)
+            I = ref()["spectra"].make_band(int(mode == "intensity"), emin, emax, model.ebins, model.emid, t,
+                                           np.ascontiguousarray(shift[b:e]))
+            ret[idxs[b:e]] = I * cell_nrm[b:e]
+        else:
+            if model._density_dependence:
+                cflux, mflux, vflux = fluxf(kT[b:e], nH[b:e])
+            else:
+                cflux, mflux, vflux = fluxf(kT[b:e])
+            tot_flux = cflux
+            tot_flux += metalZ[b:e] * mflux
+            if elemZ is not None:
+                tot_flux += np.sum(elemZ[:, b:e] * vflux, axis=0)
+            ret[idxs[b:e]] = tot_flux * cell_nrm[b:e]
+    return ret
 
 
 # ---------------------------------------------------------------------------------------

@@ -116,6 +116,12 @@ SKY_TAN, SKY_FLAT, SKY_PHYS = 0, 1, 2
 
 # name -> (restype, argtypes); every symbol include/pxb.h declares
 _P = C.POINTER
+class BandFluxDesc(C.Structure):
+    """pxb_band_flux"""
+    _fields_ = [("cflux", c_void_p), ("mflux", c_void_p), ("vflux", c_void_p),
+                ("fb_cflux", c_void_p), ("fb_mflux", c_void_p), ("fb_vflux", c_void_p)]
+
+
 SIGNATURES = {
     "pxb_last_error": (C.c_char_p, []),
     "pxb_version": (C.c_int, []),
@@ -165,6 +171,8 @@ SIGNATURES = {
                                    c_void_p]),
     "pxb_absorb_transmission": (C.c_int, [_P(ProjectParams), C.c_int64, c_void_p, c_void_p,
                                           c_void_p]),
+    "pxb_thermal_flux": (C.c_int, [c_void_p, _P(ThermalCells), _P(BandFluxDesc), c_void_p, c_void_p,
+                                   c_void_p]),
     "pxb_column_lookup": (C.c_int, [C.c_int64, c_void_p, c_void_p, c_void_p, c_void_p, C.c_int64,
                                     C.c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "pxb_absorb_decide": (C.c_int, [_P(ProjectParams), C.c_int64, c_void_p, c_void_p, c_void_p,
@@ -172,7 +180,7 @@ SIGNATURES = {
 }
 
 ABI_STRUCTS = [TableDesc, ModelDesc, ThermalCells, Geometry, PowerlawCells, LineCells,
-               PhotonList, ProjectParams]
+               PhotonList, ProjectParams, BandFluxDesc]
 
 _lib = None
 

@@ -53,7 +53,8 @@ extern "C" int pxb_struct_sizes(int64_t* out, int n) {
   const int64_t v[] = {(int64_t)sizeof(pxb_table_desc),    (int64_t)sizeof(pxb_model_desc),
                        (int64_t)sizeof(pxb_thermal_cells), (int64_t)sizeof(pxb_geometry),
                        (int64_t)sizeof(pxb_powerlaw_cells), (int64_t)sizeof(pxb_line_cells),
-                       (int64_t)sizeof(pxb_photon_list),   (int64_t)sizeof(pxb_project_params)};
+                       (int64_t)sizeof(pxb_photon_list),   (int64_t)sizeof(pxb_project_params),
+                       (int64_t)sizeof(pxb_band_flux)};
   const int m = (int)(sizeof(v) / sizeof(v[0]));
   if (!out || n < m) {
     pxb_set_error("pxb_struct_sizes needs room for %d entries", m);

@@ -293,6 +293,134 @@ extern "C" int pxb_thermal_band(const pxb_model* model, const pxb_thermal_cells*
   return PXB_OK;
 }
 
+// ---- band flux per cell from tabulated row fluxes (row f2) -------------------------------
+// scipy.interpolate.interp1d(kind="linear") as make_fluxf builds it (spectral_models.py:109-131):
+// idx = clip(searchsorted(x, xn), 1, n-1); slope = (y_hi - y_lo) / (x_hi - x_lo);
+// y = slope * (xn - x_lo) + y_lo -- same operations in the same order, no fused multiply-add.
+__device__ __forceinline__ int interp1d_hi(const double* __restrict__ x, int n, double xn) {
+  int lo = 0, hi = n;   // first index with x[idx] >= xn  (searchsorted side="left")
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (__ldg(x + mid) < xn) lo = mid + 1; else hi = mid;
+  }
+  return min(max(lo, 1), n - 1);
+}
+__device__ __forceinline__ double interp1d_eval(const double* __restrict__ x,
+                                                const double* __restrict__ y, int hi, double xn) {
+  const double xl = __ldg(x + hi - 1), xh = __ldg(x + hi);
+  const double yl = __ldg(y + hi - 1), yh = __ldg(y + hi);
+  const double slope = __ddiv_rn(__dsub_rn(yh, yl), __dsub_rn(xh, xl));
+  return __dadd_rn(__dmul_rn(slope, __dsub_rn(xn, xl)), yl);
+}
+
+// The same interpolant the way scipy evaluates it for an N-D y (interp1d._call_linear, used for
+// the variable-element fluxes): y = ((xn - x_lo)/(x_hi - x_lo)) * y_hi + ((x_hi - xn)/(x_hi - x_lo)) * y_lo.
+// (1-D y goes through np.interp, which is the slope form above.)
+__device__ __forceinline__ double interp1d_eval_nd(const double* __restrict__ x,
+                                                   const double* __restrict__ y, int hi, double xn) {
+  const double xl = __ldg(x + hi - 1), xh = __ldg(x + hi);
+  const double yl = __ldg(y + hi - 1), yh = __ldg(y + hi);
+  const double dx = __dsub_rn(xh, xl);
+  return __dadd_rn(__dmul_rn(__ddiv_rn(__dsub_rn(xn, xl), dx), yh),
+                   __dmul_rn(__ddiv_rn(__dsub_rn(xh, xn), dx), yl));
+}
+
+__global__ void __launch_bounds__(256)
+k_thermal_flux(const DevModel M, const __grid_constant__ pxb_thermal_cells C,
+               const pxb_band_flux B, double* __restrict__ out,
+               unsigned long long* __restrict__ n_outside) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= C.ncell) return;
+  const double kT = C.kT[i];
+  if (!cell_cut(C, i, kT)) {
+    out[i] = 0.0;
+    return;
+  }
+  const double xh = cell_xh(C, i);
+  const double Z = cell_metal(C, i, xh);
+  const double nH = C.nH ? C.nH[i] : 0.0;
+  bool use_prim = true;
+  if (M.density_dependent && M.has_fb)
+    use_prim = (kT >= M.kT_lo) && (kT <= M.kT_hi) && (nH >= M.nH_lo) && (nH <= M.nH_hi);
+  double tot;
+  if (use_prim && M.density_dependent) {
+    // _get_flux_2d, spectral_models.py:516-537 (indices from searchsorted - 1, no clipping: the
+    // cell is inside the table), then / nH (:500-504)
+    const DevTable& t = M.prim;
+    const double lkT = log10(kT * M.K_per_keV), lnH = log10(nH);
+    int ti = 0, di = 0;
+    {
+      int lo = 0, hi = t.nx;
+      while (lo < hi) { const int mid = (lo + hi) >> 1; if (__ldg(t.xnodes + mid) < lkT) lo = mid + 1; else hi = mid; }
+      ti = lo - 1;
+      lo = 0; hi = t.ny;
+      while (lo < hi) { const int mid = (lo + hi) >> 1; if (__ldg(t.ynodes + mid) < lnH) lo = mid + 1; else hi = mid; }
+      di = lo - 1;
+    }
+    // searchsorted - 1 is -1 exactly on the first node: numpy then wraps to the LAST interval
+    // (negative index); the reference inherits that, a lookup there is meaningless -> count it
+    if (ti < 0 || di < 0 || ti > t.nx - 2 || di > t.ny - 2) {
+      atomicAdd(n_outside, 1ull);
+      out[i] = __longlong_as_double(0x7ff8000000000000LL);
+      return;
+    }
+    const double dT = (lkT - __ldg(t.xnodes + ti)) / (__ldg(t.xnodes + ti + 1) - __ldg(t.xnodes + ti));
+    const double dn = (lnH - __ldg(t.ynodes + di)) / (__ldg(t.ynodes + di + 1) - __ldg(t.ynodes + di));
+    const int i1 = (di + 1) * t.nx + ti + 1, i2 = (di + 1) * t.nx + ti, i3 = di * t.nx + ti + 1,
+              i4 = di * t.nx + ti;
+    const double dx1 = __dmul_rn(dT, dn), dx2 = dn - dx1, dx3 = dT - dx1, dx4 = 1.0 + dx1 - dT - dn;
+    auto bil = [&](const double* f) {
+      return __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(dx1, __ldg(f + i1)), __dmul_rn(dx2, __ldg(f + i2))),
+                                 __dmul_rn(dx3, __ldg(f + i3))),
+                       __dmul_rn(dx4, __ldg(f + i4)));
+    };
+    tot = bil(B.cflux) / nH;
+    tot = __dadd_rn(tot, __dmul_rn(Z, bil(B.mflux) / nH));
+    double vs = 0.0;
+    for (int k = 0; k < C.nvar; ++k)
+      vs = __dadd_rn(vs, __dmul_rn(cell_elem(C, k, i, xh), bil(B.vflux + (size_t)k * t.nrows) / nH));
+    if (C.nvar) tot = __dadd_rn(tot, vs);
+  } else {
+    const DevTable& t = use_prim ? M.prim : M.fb;
+    const int lt = use_prim ? M.log_t : M.fb_log_t;
+    const double* cf = use_prim ? B.cflux : B.fb_cflux;
+    const double* mf = use_prim ? B.mflux : B.fb_mflux;
+    const double* vf = use_prim ? B.vflux : B.fb_vflux;
+    const double x = lt ? log10(kT * M.K_per_keV) : kT;
+    if (!(x >= __ldg(t.xnodes)) || !(x <= __ldg(t.xnodes + t.nx - 1))) {   // interp1d raises here
+      atomicAdd(n_outside, 1ull);
+      out[i] = __longlong_as_double(0x7ff8000000000000LL);
+      return;
+    }
+    const int hi = interp1d_hi(t.xnodes, t.nx, x);
+    tot = interp1d_eval(t.xnodes, cf, hi, x);
+    tot = __dadd_rn(tot, __dmul_rn(Z, interp1d_eval(t.xnodes, mf, hi, x)));
+    double vs = 0.0;
+    for (int k = 0; k < C.nvar; ++k)
+      vs = __dadd_rn(vs, __dmul_rn(cell_elem(C, k, i, xh),
+                                   interp1d_eval_nd(t.xnodes, vf + (size_t)k * t.nrows, hi, x)));
+    if (C.nvar) tot = __dadd_rn(tot, vs);
+  }
+  out[i] = __dmul_rn(tot, cell_norm(C, i));
+}
+
+extern "C" int pxb_thermal_flux(const pxb_model* model, const pxb_thermal_cells* cells,
+                                const pxb_band_flux* band, double* out, int64_t* n_outside_out,
+                                void* stream) {
+  PXB_REQUIRE(model && cells && band && n_outside_out, "NULL argument");
+  PXB_REQUIRE(cells->nvar == model->dev.nvar, "cells.nvar does not match the table");
+  if (cells->ncell == 0) return PXB_OK;
+  PXB_REQUIRE(out && cells->kT && cells->em && band->cflux && band->mflux, "NULL argument");
+  PXB_REQUIRE(model->dev.nvar == 0 || band->vflux, "variable-element fluxes missing");
+  PXB_REQUIRE(!model->dev.density_dependent || cells->nH, "density dependent model needs nH");
+  PXB_REQUIRE(!(model->dev.density_dependent && model->dev.has_fb) || (band->fb_cflux && band->fb_mflux),
+              "fallback-table fluxes missing");
+  k_thermal_flux<<<(unsigned)((cells->ncell + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      model->dev, *cells, *band, out, (unsigned long long*)n_outside_out);
+  PXB_LAUNCH_CHECK();
+  return PXB_OK;
+}
+
 extern "C" int pxb_powerlaw_spectrum(int64_t ncell, const double* alpha, const double* K,
                                      const double* shift, int64_t nbins, const double* emid,
                                      double* spec_out, void* stream) {

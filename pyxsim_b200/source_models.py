@@ -88,10 +88,15 @@ class SourceModel:
         ``mode="photons"``; ``mode="spectrum"`` returns the chunk's spectrum on ``ebins``."""
         if mode == "spectrum":
             return self._spectrum_chunk(chunk, spectral_norm, np.asarray(ebins, "float64"), shifting)
+        if mode in ("luminosity", "photon_rate", "intensity", "photon_intensity"):
+            # per-cell band quantities of make_source_fields / make_intensity_fields
+            # (sources.py:236-306,447-500; base.py:497-511): NumPy array shaped like the chunk
+            out = self._field_chunk(mode, chunk, spectral_norm, emin, emax, fluxf, shifting)
+            return out.cpu().numpy()
         if mode != "photons":
             raise NotImplementedError(
-                f"pyxsim_b200 implements mode='photons' and mode='spectrum' (got {mode!r}); the "
-                "per-cell field modes are not part of the photon hot path")
+                f"pyxsim_b200 implements the modes 'photons', 'spectrum', 'luminosity', 'photon_rate', "
+                f"'intensity' and 'photon_intensity' (got {mode!r})")
         out = self.generate_chunk(chunk, spectral_norm)
         if out is None:
             return None
@@ -178,6 +183,111 @@ class SourceModel:
     def _spectrum_chunk(self, chunk, spectral_norm, ebins, shifting):
         raise NotImplementedError
 
+    def _field_chunk(self, mode, chunk, spectral_norm, emin, emax, fluxf, shifting):
+        raise NotImplementedError(f"{type(self).__name__} has no per-cell field modes on the GPU yet")
+
+    def make_fluxf(self, emin, emax, energy=False):
+        raise NotImplementedError
+
+    def make_source_fields(self, data_source, emin, emax, force_override=False, band_name=None):
+        """Source-frame band fields of an :class:`ArrayDataSource` (sources.py:166-308):
+        ``xray_luminosity_*`` [erg/s], ``xray_emissivity_*`` [erg/cm^3/s], ``xray_count_rate_*``
+        [photons/s], ``xray_photon_emissivity_*`` [photons/cm^3/s] as device tensors added to
+        ``data_source.fields``; returns the field names in the reference's order.  (For yt
+        datasets the reference registers lazy derived fields with ``ds.add_field``; that
+        registration is yt plumbing, the per-chunk evaluation is ``process_data``.)"""
+        from .photon_list import _chunks
+
+        require_cuda()
+        emin, emax = parse_value(emin, "keV"), parse_value(emax, "keV")
+        self.setup_model("fields", data_source, 0.0)
+        ftype = self.ftype
+        if band_name is None:
+            band_name = f"{emin}_{emax}_keV"
+        emiss_name = (ftype, f"xray_emissivity_{band_name}")
+        lum_name = (ftype, f"xray_luminosity_{band_name}")
+        phot_emiss_name = (ftype, f"xray_photon_emissivity_{band_name}")
+        count_rate_name = (ftype, f"xray_count_rate_{band_name}")
+        names = [emiss_name, lum_name, phot_emiss_name, count_rate_name]
+        if not force_override:
+            clash = [n for n in names if n in data_source.fields]
+            if clash:
+                raise RuntimeError(f"fields {clash} exist already (use force_override=True)")
+        efluxf = self.make_fluxf(emin, emax, energy=True)
+        pfluxf = self.make_fluxf(emin, emax, energy=False)
+        lum, rate, idv = [], [], []
+        for chunk in _chunks(data_source):
+            lum.append(self._field_chunk("luminosity", chunk, 1.0, emin, emax, efluxf, False))
+            rate.append(self._field_chunk("photon_rate", chunk, 1.0, emin, emax, pfluxf, False))
+            idv.append(_inverse_volume(chunk, ftype))
+        lum = torch.cat(lum) * K.erg_per_keV      # keV/s -> erg/s
+        rate, idv = torch.cat(rate), torch.cat(idv)
+        data_source.fields[lum_name] = lum
+        data_source.fields[emiss_name] = lum * idv
+        data_source.fields[count_rate_name] = rate
+        data_source.fields[phot_emiss_name] = rate * idv
+        data_source.units.update({lum_name: "erg/s", emiss_name: "erg/cm**3/s",
+                                  count_rate_name: "photons/s", phot_emiss_name: "photons/cm**3/s"})
+        self.cleanup_model("fields")
+        return names
+
+    def make_intensity_fields(self, data_source, emin, emax, redshift=0.0, dist=None, cosmology=None,
+                              no_doppler=False, force_override=True, band_name=None, normal="z"):
+        """Observer-frame band intensity fields (sources.py:351-500): ``xray_intensity_*``
+        [erg/cm^3/s/arcsec^2] and ``xray_photon_intensity_*`` [photons/cm^3/s/arcsec^2] -- the
+        integrands of a projection along ``normal`` (the reference takes the axis from the
+        projection's field parameter; an array source has no such mechanism, so it is an
+        argument).  ``emin``/``emax`` are observer-frame energies."""
+        from .data import Cosmology
+        from .photon_list import _chunks
+
+        require_cuda()
+        if redshift == 0.0 and dist is None:
+            raise ValueError("Either 'redshift' must be > 0.0 or 'dist' must not be None!")
+        emin, emax = parse_value(emin, "keV"), parse_value(emax, "keV")
+        self.setup_model("fields", data_source, 0.0)
+        ftype = self.ftype
+        # _make_dist_fac(per_sa=True), sources.py:107-130
+        if dist is None:
+            cosmo = cosmology or getattr(data_source, "cosmology", None) or Cosmology()
+            d_a = cosmo.angular_diameter_distance_mpc(0.0, redshift) * K.cm_per_mpc
+            d_l = d_a * (1.0 + redshift) ** 2
+            angular_scale = d_a                      # cm per radian
+        else:
+            redshift = 0.0
+            d_l = parse_value(dist, "kpc") * K.cm_per_kpc
+            angular_scale = d_l
+        rad2_per_arcsec2 = (np.pi / 180.0 / 3600.0) ** 2
+        dist_fac = 1.0 / (4.0 * np.pi * d_l * d_l) * angular_scale ** 2 * rad2_per_arcsec2
+        emin_src, emax_src = emin * (1.0 + redshift), emax * (1.0 + redshift)
+        if band_name is None:
+            band_name = f"{emin}_{emax}_keV"
+        ei_name = (ftype, f"xray_intensity_{band_name}")
+        i_name = (ftype, f"xray_photon_intensity_{band_name}")
+        if not force_override and (ei_name in data_source.fields or i_name in data_source.fields):
+            raise RuntimeError(f"fields {ei_name}, {i_name} exist already (use force_override=True)")
+        efluxf = self.make_fluxf(emin_src, emax_src, energy=True) if no_doppler else None
+        pfluxf = self.make_fluxf(emin_src, emax_src, energy=False) if no_doppler else None
+        if isinstance(normal, str):
+            nv = np.zeros(3)
+            nv["xyz".index(normal)] = 1.0
+            normal = nv
+        self._spec_normal = np.asarray(normal, "float64")
+        if isinstance(data_source, ArrayDataSource):
+            self.v_fields = data_source.velocity_fields
+        ei, pi_, idv = [], [], []
+        for chunk in _chunks(data_source):
+            ei.append(self._field_chunk("intensity", chunk, 1.0, emin_src, emax_src, efluxf, not no_doppler))
+            pi_.append(self._field_chunk("photon_intensity", chunk, 1.0, emin_src, emax_src, pfluxf,
+                                         not no_doppler))
+            idv.append(_inverse_volume(chunk, ftype))
+        idv = torch.cat(idv)
+        data_source.fields[ei_name] = torch.cat(ei) * idv * (dist_fac * K.erg_per_keV)
+        data_source.fields[i_name] = torch.cat(pi_) * idv * ((1.0 + redshift) * dist_fac)
+        data_source.units.update({ei_name: "erg/cm**3/s/arcsec**2", i_name: "photons/cm**3/s/arcsec**2"})
+        self.cleanup_model("fields")
+        return [ei_name, i_name]
+
     def compute_shift(self, chunk):
         """Per-cell Doppler factor sqrt(1-beta^2)/(1-beta_n) along ``self._spec_normal``
         (sources.py:89-95), device tensor."""
@@ -235,6 +345,21 @@ class SourceModel:
 
     def _finish_spectrum(self, ebins, spec):
         return spec
+
+
+def _inverse_volume(chunk, ftype):
+    """1 / cell volume [cm^-3] (sources.py:141-164): ``cell_volume`` if present, else dx^3 for
+    cells, else density / mass."""
+    for f in (("index", "cell_volume"), (ftype, "cell_volume")):
+        if f in chunk:
+            return 1.0 / to_device(field_value(chunk, f, "cm**3"))
+    if ("index", "dx") in chunk:
+        dx = to_device(field_value(chunk, ("index", "dx"), "kpc")) * K.cm_per_kpc
+        return 1.0 / (dx * dx * dx)
+    if (ftype, "density") in chunk and (ftype, "mass") in chunk:
+        return to_device(field_value(chunk, (ftype, "density"), "g/cm**3")) / \
+            to_device(field_value(chunk, (ftype, "mass"), "g"))
+    raise RuntimeError("No way to compute inverse volume")
 
 
 # =======================================================================================
@@ -462,6 +587,25 @@ class ThermalSourceModel(SourceModel):
 
     def _finish_spectrum(self, ebins, spec):
         return spec / np.diff(ebins)      # base.py:297
+
+    def make_fluxf(self, emin, emax, energy=False):
+        """base.py:301-302"""
+        return self.spectral_model.make_fluxf(emin, emax, energy=energy)
+
+    def _field_chunk(self, mode, chunk, spectral_norm, emin, emax, fluxf, shifting):
+        """base.py:497-511: shifted intensities integrate the cell's Doppler-shifted spectrum
+        (make_band); everything else interpolates the tabulated band fluxes (fluxf)."""
+        require_cuda()
+        if self._chunk_size(chunk, self.temperature_field) == 0:
+            return empty(0)
+        if mode.endswith("intensity") and shifting:
+            return self.band_per_cell(chunk, spectral_norm, emin, emax, energy=(mode == "intensity"),
+                                      shifting=True)
+        if fluxf is None:
+            fluxf = self.make_fluxf(emin, emax, energy=mode in ("luminosity", "intensity"))
+        keep = []
+        Cs = self._cells_struct(chunk, spectral_norm, keep)
+        return fluxf.evaluate(Cs, keep)
 
     def band_per_cell(self, chunk, spectral_norm, emin, emax, energy=False, shifting=False):
         """make_band (spectra.pyx:96-126) times cell_nrm (base.py:497-500): per-cell band photon

@@ -144,6 +144,31 @@ class ThermalSpectralModel:
         vn = v.cpu().numpy().reshape(nv, n, self.nbins) if nv else None
         return cn, mn, vn
 
+    def _band_row_fluxes(self, emin, emax, energy):
+        """Per-row band sums exactly as make_fluxf tabulates them (spectral_models.py:102-117):
+        bins strictly inside (emin, emax); photon or energy (x emid) flux."""
+        eidxs = (self.ebins[:-1] > emin) & (self.ebins[1:] < emax)
+        emid = self.emid[eidxs]
+        if energy:
+            cf = (self.cosmic_spec[:, eidxs] * emid).sum(axis=-1)
+            mf = (self.metal_spec[:, eidxs] * emid).sum(axis=-1)
+        else:
+            cf = self.cosmic_spec[:, eidxs].sum(axis=-1)
+            mf = self.metal_spec[:, eidxs].sum(axis=-1)
+        vf = None
+        if self.var_spec is not None:
+            vf = (self.var_spec[:, :, eidxs] * emid).sum(axis=-1) if energy else self.var_spec[:, :, eidxs].sum(axis=-1)
+        return _f64(cf), _f64(mf), None if vf is None else _f64(vf)
+
+    def make_fluxf(self, emin, emax, energy=False):
+        """Band flux function (spectral_models.py:101-134): the row fluxes are tabulated on the
+        host from the tables (a one-off of nT x nbins adds), their interpolation at the cells'
+        temperatures runs on the GPU.  Returns a :class:`BandFlux`: callable like the reference's
+        ``_fluxf(kT)`` and accepted by ``ThermalSourceModel.process_data(fluxf=...)``."""
+        if self.cosmic_spec is None:
+            raise RuntimeError("call prepare_spectrum(zobs) before make_fluxf")
+        return BandFlux(self, float(emin), float(emax), bool(energy))
+
     # -- device ---------------------------------------------------------------------------
     def _bin_edges(self):
         return np.log10(self.ebins) if self.binscale == "log" else self.ebins
@@ -183,6 +208,88 @@ def _torch():
 
     return torch
 
+
+class BandFlux:
+    """What ``make_fluxf`` returns: the tabulated row fluxes of one energy band, resident on the
+    device, plus the reference's call signature ``fluxf(kT[, nH]) -> (cflux, mflux, vflux)``."""
+
+    def __init__(self, model, emin, emax, energy):
+        self.model, self.emin, self.emax, self.energy = model, emin, emax, energy
+        self.cf, self.mf, self.vf = model._band_row_fluxes(emin, emax, energy)
+        cie = getattr(model, "cie_model", None) if model._density_dependence else None
+        self.fb = cie._band_row_fluxes(emin, emax, energy) if cie is not None else None
+        self._dev = None
+
+    def desc(self):
+        """(pxb_band_flux, tensors to keep alive)"""
+        if self._dev is None:
+            arrs = [self.cf, self.mf, self.vf] + (list(self.fb) if self.fb is not None else [None] * 3)
+            self._dev = [None if a is None else to_device(a.reshape(-1)) for a in arrs]
+        B = _lib.BandFluxDesc()
+        for name, t in zip(("cflux", "mflux", "vflux", "fb_cflux", "fb_mflux", "fb_vflux"), self._dev):
+            setattr(B, name, None if t is None else t.data_ptr())
+        return B, self._dev
+
+    def evaluate(self, cells_struct, keep):
+        """out[i] = cell_nrm * (cf + Z mf + sum e_k vf_k) for a filled ``pxb_thermal_cells``;
+        raises ValueError like scipy's interp1d when a selected cell lies outside the table."""
+        dm = self.model.device_model()
+        B, tensors = self.desc()
+        out = empty(cells_struct.ncell)
+        bad = _torch().zeros(1, dtype=_torch().int64, device=out.device)
+        _lib.call("pxb_thermal_flux", dm.handle, C.byref(cells_struct), C.byref(B), ptr(out),
+                  bad.data_ptr(), stream_ptr())
+        nbad = int(bad.cpu()[0])
+        del tensors, keep
+        if nbad:
+            raise ValueError(f"A value in x_new is outside the interpolation range "
+                             f"({nbad} cells outside the temperature table).")
+        return out
+
+    def __call__(self, kT, nH=None):
+        """Reference signature: per-table fluxes at temperatures ``kT`` [keV] (and ``nH`` for a
+        density-dependent model) as NumPy arrays.  One launch per table: the kernel's "cosmic"
+        slot is pointed at the table wanted and every abundance is zero."""
+        kT = np.atleast_1d(np.asarray(kT, "float64"))
+        n = kT.size
+        nv = 0 if self.vf is None else self.vf.shape[0]
+        dkT = to_device(kT)
+        dem = _torch().ones(n, dtype=_torch().float64, device=dkT.device)
+        dnH = None if nH is None else to_device(np.atleast_1d(np.asarray(nH, "float64")))
+        dm = self.model.device_model()
+        B0, tensors = self.desc()
+        nrows, nrows_fb = self.cf.size, (0 if self.fb is None else self.fb[0].size)
+        bad = _torch().zeros(1, dtype=_torch().int64, device=dkT.device)
+        zeros = _torch().zeros(max(nrows, nrows_fb), dtype=_torch().float64, device=dkT.device)
+        outs = []
+        for which in ["c", "m"] + list(range(nv)):
+            B = _lib.BandFluxDesc()
+            for name in ("cflux", "mflux", "vflux", "fb_cflux", "fb_mflux", "fb_vflux"):
+                setattr(B, name, getattr(B0, name))
+            if which == "m":
+                B.cflux, B.fb_cflux = B0.mflux, B0.fb_mflux
+            elif which != "c":
+                # through the element slot itself (scipy evaluates an N-D y with a different
+                # but equivalent expression, and so does the kernel): zero cosmic, weight 1
+                B.cflux = zeros.data_ptr()
+                B.fb_cflux = zeros.data_ptr() if B0.fb_cflux else None
+            Cs = _lib.ThermalCells()
+            Cs.ncell, Cs.nvar = n, nv
+            Cs.kT, Cs.em = dkT.data_ptr(), dem.data_ptr()
+            Cs.nH = None if dnH is None else dnH.data_ptr()
+            Cs.kT_min, Cs.kT_max = -1.0e300, 1.0e300
+            Cs.max_density, Cs.min_entropy = 1.0e300, -1.0e300
+            Cs.spectral_norm, Cs.xh_const, Cs.zmet_const = 1.0, 1.0, 0.0
+            if which not in ("c", "m"):
+                Cs.elem_const[which] = 1.0
+            out = empty(n)
+            _lib.call("pxb_thermal_flux", dm.handle, C.byref(Cs), C.byref(B), ptr(out), bad.data_ptr(),
+                      stream_ptr())
+            outs.append(out.cpu().numpy())
+        del tensors
+        if int(bad.cpu()[0]):
+            raise ValueError("A value in x_new is outside the interpolation range.")
+        return outs[0], outs[1], (np.stack(outs[2:]) if nv else None)
 
 class TableCIEModel(ThermalSpectralModel):
     """APEC/SPEX table model.  Same constructor as the reference (spectral_models.py:203-251);

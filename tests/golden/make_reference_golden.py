@@ -128,6 +128,9 @@ def run_reference(I):
         s = object.__new__(cls)
         s.si = sm_mod.SpectralInterpolator1D(t["Tvals"], t["cosmic"], t["metal"], t["var"])
         s.nbins = t["ebins"].size - 1
+        # what make_fluxf reads (spectral_models.py:101-134)
+        s.ebins, s.emid = t["ebins"], 0.5 * (t["ebins"][1:] + t["ebins"][:-1])
+        s.Tvals, s.cosmic_spec, s.metal_spec, s.var_spec = t["Tvals"], t["cosmic"], t["metal"], t["var"]
         return s
 
     # ---- t1 --------------------------------------------------------------------------------
@@ -146,6 +149,14 @@ def run_reference(I):
     m.pbar = R.NoBar()
     ebnew = np.linspace(0.3, 7.0, 41)
     out.update(t1_spec=m.process_data("spectrum", chunk, a["norm"], ebins=ebnew, shifting=False))
+
+    # band fluxes of the same model: make_fluxf + the "luminosity" / "photon_rate" branch
+    # (spectral_models.py:101-134, base.py:501-511); also the bare flux function
+    for tag, energy, mode in (("lum", True, "luminosity"), ("rate", False, "photon_rate")):
+        fl = m.make_fluxf(0.5, 2.0, energy=energy)
+        out[f"t1_{tag}"] = m.process_data(mode, chunk, a["norm"], emin=0.5, emax=2.0, fluxf=fl)
+        c_, m_, v_ = fl(np.array([0.05, 0.3, 1.0, 7.7, 40.0]))
+        out.update({f"t1_{tag}_cf": c_, f"t1_{tag}_mf": m_, f"t1_{tag}_vf": v_})
 
     # ---- t2: log bins, both sampling methods -----------------------------------------------
     a = I["t2"]
@@ -176,6 +187,16 @@ def run_reference(I):
                       var_elem={"O": 0.4, "Ne": 1.1}, var_elem_keys=["O", "Ne"], prng=np.random.RandomState(14))
     nc, nph, idx, e = m.process_data("photons", chunk, a["norm"])
     out.update(pion_nph=nph, pion_idx=idx, pion_e=np.asarray(e))
+    # band fluxes of the 2-D model (_get_flux_2d + CIE fallback, spectral_models.py:464-537); the
+    # cut keeps kT >= 0.1 keV so that every fallback cell lies inside the CIE table (interp1d raises
+    # outside it)
+    pm.__dict__.update(ebins=a["ebins"], emid=0.5 * (a["ebins"][1:] + a["ebins"][:-1]), Tvals=a["Tv"],
+                       Dvals=a["Dv"], dTvals=np.diff(a["Tv"]), dDvals=np.diff(a["Dv"]), n_T=a["Tv"].size,
+                       n_D=a["Dv"].size, cosmic_spec=a["c2"], metal_spec=a["m2"])
+    m.kT_min = 0.1
+    for tag, energy, mode in (("lum", True, "luminosity"), ("rate", False, "photon_rate")):
+        fl = m.make_fluxf(0.4, 1.2, energy=energy)
+        out[f"pion_{tag}"] = m.process_data(mode, chunk, a["norm"], emin=0.4, emax=1.2, fluxf=fl)
 
     # ---- power law ---------------------------------------------------------------------------
     a = I["pl"]

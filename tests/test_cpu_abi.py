@@ -40,9 +40,10 @@ def test_binding_covers_header(lib):
 def test_struct_layout_matches(lib):
     from pyxsim_b200 import _lib
 
-    sizes = (C.c_int64 * 8)()
-    n = lib.pxb_struct_sizes(sizes, 8)
-    assert n == 8
+    nst = len(_lib.ABI_STRUCTS)
+    sizes = (C.c_int64 * nst)()
+    n = lib.pxb_struct_sizes(sizes, nst)
+    assert n == nst
     assert [int(v) for v in sizes] == [C.sizeof(t) for t in _lib.ABI_STRUCTS]
     assert lib.pxb_struct_sizes(sizes, 2) < 0
     assert b"room" in lib.pxb_last_error()

@@ -110,6 +110,13 @@ def _replay_reference_cases(O, I, cases):
     out.update(t1_spec=O.thermal_spectrum_mode(
         om, cfg, dict(kT=a["kT"], em=a["em"], Z=a["Z"], Fe=a["Fe"], density=a["dens"]), np.linspace(0.3, 7.0, 41)))
 
+    cells = dict(kT=a["kT"], em=a["em"], Z=a["Z"], Fe=a["Fe"], density=a["dens"])
+    for tag, energy, mode in (("lum", True, "luminosity"), ("rate", False, "photon_rate")):
+        fl = om.make_fluxf(0.5, 2.0, energy=energy)
+        out[f"t1_{tag}"] = O.thermal_field_mode(om, cfg, cells, mode, 0.5, 2.0, fluxf=fl)
+        c_, m_, v_ = fl(np.array([0.05, 0.3, 1.0, 7.7, 40.0]))
+        out.update({f"t1_{tag}_cf": c_, f"t1_{tag}_mf": m_, f"t1_{tag}_vf": v_})
+
     a = I["t2"]
     t = a["tables"]
     om = O.TableModel(t["ebins"], t["Tvals"], t["cosmic"], t["metal"], t["var"], binscale=t["binscale"])
@@ -130,6 +137,11 @@ def _replay_reference_cases(O, I, cases):
     nc, nph, idx, e = O.thermal_process_data(pm, cfg, dict(kT=a["kT"], em=a["em"], nH=a["nH"]),
                                              np.random.RandomState(14))
     out.update(pion_nph=nph, pion_idx=idx, pion_e=e)
+    cfg["kT_min"] = 0.1
+    for tag, energy, mode in (("lum", True, "luminosity"), ("rate", False, "photon_rate")):
+        fl = pm.make_fluxf(0.4, 1.2, energy=energy)
+        out[f"pion_{tag}"] = O.thermal_field_mode(pm, cfg, dict(kT=a["kT"], em=a["em"], nH=a["nH"]), mode,
+                                                  0.4, 1.2, fluxf=fl)
 
     a = I["pl"]
     cfg = dict(e0=1.0, emin=0.5, emax=40.0, spectral_norm=a["norm"], scale_factor=1.0 / (1.0 + a["z"]))

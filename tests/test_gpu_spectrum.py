@@ -150,3 +150,107 @@ def test_make_spectrum_thermal_counts_consistency(cuda):
     np.testing.assert_allclose(rate, float(lam.sum()), rtol=1e-10)
     with pytest.raises(RuntimeError):
         model.make_spectrum(src, 0.1, 10.0, 10, normal="z")
+
+
+# ---------------------------------------------------------------------------------------
+# row f2: band flux functions (make_fluxf) and the per-cell field modes
+# ---------------------------------------------------------------------------------------
+def _golden():
+    import importlib.util
+
+    here = os.path.dirname(os.path.abspath(__file__))
+    spec_ = importlib.util.spec_from_file_location("mrg", os.path.join(here, "golden", "make_reference_golden.py"))
+    mrg = importlib.util.module_from_spec(spec_)
+    spec_.loader.exec_module(mrg)
+    return mrg.inputs(), np.load(os.path.join(here, "golden", "reference_golden.npz"))
+
+
+def test_band_flux_modes_vs_reference_python(cuda):
+    """make_fluxf + process_data("luminosity" / "photon_rate") against the reference's own Python
+    run (fixtures t1_lum, t1_rate, t1_*_cf/mf/vf; pion_lum, pion_rate): 1-D table with a
+    mass-fraction metallicity field, one constant and one field element; 2-D table with the CIE
+    fallback."""
+    I, R = _golden()
+    a = I["t1"]
+    t = a["tables"]
+    src = H.cells_source(a["kT"], a["em"], extra={("gas", "Zf"): a["Z"], ("gas", "Fef"): a["Fe"],
+                                                  ("gas", "density"): a["dens"]})
+    src.units[("gas", "Zf")] = "dimensionless"
+    model = px.ThermalSourceModel(H.product_model(t), 0.1, 10.0, 64, ("gas", "Zf"), temperature_field=TF,
+                                  var_elem={"O": 0.5, "Fe": ("gas", "Fef")}, h_fraction=a["h_fraction"],
+                                  max_density=3e-26, prng=1)
+    model.setup_model("fields", src, 0.0)
+    model.Zconvert = a["Zconvert"]
+    chunk = next(src.chunks())
+    for tag, energy, mode in (("lum", True, "luminosity"), ("rate", False, "photon_rate")):
+        fl = model.make_fluxf(0.5, 2.0, energy=energy)
+        got = model.process_data(mode, chunk, a["norm"], emin=0.5, emax=2.0, fluxf=fl)
+        ref = R[f"t1_{tag}"]
+        assert got.shape == ref.shape and np.array_equal(got == 0.0, ref == 0.0)
+        np.testing.assert_allclose(got, ref, rtol=2e-15, atol=0.0)
+        c_, m_, v_ = fl(np.array([0.05, 0.3, 1.0, 7.7, 40.0]))
+        np.testing.assert_array_equal(c_, R[f"t1_{tag}_cf"])        # same operations, same order
+        np.testing.assert_array_equal(m_, R[f"t1_{tag}_mf"])
+        np.testing.assert_array_equal(v_, R[f"t1_{tag}_vf"])
+        # without fluxf= the model tabulates the band itself
+        got2 = model.process_data(mode, chunk, a["norm"], emin=0.5, emax=2.0)
+        np.testing.assert_array_equal(got2, got)
+    # outside the table scipy's interp1d raises; so does the GPU path
+    with pytest.raises(ValueError):
+        model.make_fluxf(0.5, 2.0)(np.array([1.0, 500.0]))
+
+    a = I["pion"]
+    cie_T, cc, cm, cv = a["cie"]
+    cie_prod = px.ThermalSpectralModel(a["ebins"], cie_T, cc, cm, cv, logT=True, binscale="log")
+    prod = px.PionSpectralModel(a["ebins"], a["Tv"], a["Dv"], a["c2"], a["m2"], a["v2"], cie_model=cie_prod,
+                                var_elem_names=["O", "Ne"], binscale="log")
+    src = H.cells_source(a["kT"], a["em"], extra={("gas", "H_nuclei_density"): a["nH"]})
+    model = px.IGMSourceModel(0.3, 1.4, 40, 0.3, binscale="log", temperature_field=TF,
+                              var_elem={"O": 0.4, "Ne": 1.1}, kT_min=0.1, prng=1, spectral_model=prod)
+    model.setup_model("fields", src, 0.0)
+    chunk = next(src.chunks())
+    for tag, energy, mode in (("lum", True, "luminosity"), ("rate", False, "photon_rate")):
+        got = model.process_data(mode, chunk, a["norm"], emin=0.4, emax=1.2,
+                                 fluxf=model.make_fluxf(0.4, 1.2, energy=energy))
+        ref = R[f"pion_{tag}"]
+        assert np.array_equal(got == 0.0, ref == 0.0) and (ref > 0).sum() > 50
+        np.testing.assert_allclose(got, ref, rtol=1e-12, atol=0.0)   # log10 differs in the last ulp
+
+
+def test_source_and_intensity_fields(cuda, oracle):
+    """make_source_fields / make_intensity_fields on an array source: field names and units of the
+    reference (sources.py:166-308,351-500); luminosity = emissivity * volume; the Doppler-free
+    intensity equals the shifted one for a gas at rest up to the band-edge convention
+    (make_fluxf keeps bins strictly inside the band, make_band bins touching it as well)."""
+    t = H.make_tables(nbins=400, nvar=0)
+    kT, em = H.random_cells(3000, seed=9, kT_range=(0.3, 20.0))
+    src = H.cells_source(kT, em)
+    for f in src.velocity_fields:
+        src.fields[f] = np.zeros_like(src.fields[f])
+    model = px.ThermalSourceModel(H.product_model(t), 0.1, 10.0, 400, 0.3, temperature_field=TF, prng=1)
+    names = model.make_source_fields(src, 0.5, 2.0)
+    assert [n[1] for n in names] == ["xray_emissivity_0.5_2.0_keV", "xray_luminosity_0.5_2.0_keV",
+                                    "xray_photon_emissivity_0.5_2.0_keV", "xray_count_rate_0.5_2.0_keV"]
+    lum, emis = src.fields[names[1]].cpu().numpy(), src.fields[names[0]].cpu().numpy()
+    vol = (src.fields[("index", "dx")] * 3.0856775809623245e21) ** 3
+    np.testing.assert_allclose(emis * vol, lum, rtol=1e-13)
+    om = H.oracle_model(oracle, t)
+    cfg = dict(kT_min=0.025, kT_max=64.0, Zmet=0.3, spectral_norm=1.0)
+    ref = oracle.thermal_field_mode(om, cfg, dict(kT=kT, em=em), "luminosity", 0.5, 2.0,
+                                    fluxf=om.make_fluxf(0.5, 2.0, energy=True)) * 1.602176634e-9
+    np.testing.assert_allclose(lum, ref, rtol=1e-13)
+    with pytest.raises(RuntimeError):
+        model.make_source_fields(src, 0.5, 2.0)                    # exists, no force_override
+    with pytest.raises(ValueError):
+        model.make_intensity_fields(src, 0.5, 2.0)                 # needs redshift or dist
+    # band edges placed mid-bin so both conventions select the same bins
+    eb = t["ebins"]
+    lo, hi = 0.5 * (eb[40] + eb[41]) , 0.5 * (eb[150] + eb[151])
+    z = 0.05
+    n1 = model.make_intensity_fields(src, lo / (1 + z), hi / (1 + z), redshift=z, no_doppler=True, band_name="b")
+    i_nd = {k: src.fields[k].cpu().numpy() for k in n1}
+    n2 = model.make_intensity_fields(src, lo / (1 + z), hi / (1 + z), redshift=z, no_doppler=False, band_name="b")
+    assert n1 == n2 and [n[1] for n in n1] == ["xray_intensity_b", "xray_photon_intensity_b"]
+    for k in n1:
+        np.testing.assert_allclose(src.fields[k].cpu().numpy(), i_nd[k], rtol=1e-12)
+        assert (i_nd[k] > 0).all()
