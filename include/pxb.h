@@ -30,6 +30,8 @@
  *                                 process_data, spectral_models.py:101-134,464-537; base.py:501-511
  *   pxb_absorb_decide ........... AbsorptionModel.absorb_photons, spectral_models.py:563-583
  *                                 (diagnostic: explicit uniforms)
+ *   pxb_cel_to_pixel, pxb_event_image, pxb_event_spectrum ... EventList binning,
+ *                                 pyxsim/event_list.py:106-134,254-318,344-349
  *   pxb_column_lookup ........... nH cube interpolation at the rotated cell centres,
  *                                 photon_list.py:672-680 (scipy interpn, linear, fill 0)
  *   pxb_project ................. the projection tile loop, photon_list.py:686-799:
@@ -388,6 +390,27 @@ int pxb_column_lookup(int64_t n_cells, const double* x, const double* y, const d
  * u on either side of the threshold and E on the wabs piece edges. */
 int pxb_absorb_decide(const pxb_project_params* params, int64_t n, const double* energy,
                       const double* u, uint8_t* survive_out, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * Event-list consumers (pyxsim/event_list.py)
+ * ---------------------------------------------------------------------------------- */
+/* wcs_world2pix (origin 1) for the TAN header EventList builds (event_list.py:106-112,281-287):
+ * CRVAL = (ra0, dec0), CRPIX = crpix on both axes, CDELT = (cdelt1, cdelt2) in degrees.  Points
+ * on the far hemisphere give NaN. */
+int pxb_cel_to_pixel(int64_t n, const double* ra_deg, const double* dec_deg, double ra0_deg,
+                     double dec0_deg, double crpix, double cdelt1, double cdelt2,
+                     double* xpix_out, double* ypix_out, void* stream);
+/* write_fits_image's binning (event_list.py:254-318): counts of the events with
+ * emin <= eobs <= emax per pixel of an nx x nx TAN image of pixel size dtheta_deg centred on
+ * (ra0, dec0); np.histogram2d edge semantics; image[iy*nx + ix] (the H.T the reference writes),
+ * uint64, ACCUMULATED. */
+int pxb_event_image(int64_t n, const double* xsky, const double* ysky, const double* eobs,
+                    double emin, double emax, double ra0_deg, double dec0_deg, int nx,
+                    double dtheta_deg, uint64_t* image, void* stream);
+/* write_spectrum's binning (event_list.py:344-349): np.histogram(eobs, bins=edges), edges device
+ * [nchan+1] ascending; counts uint64 [nchan], ACCUMULATED. */
+int pxb_event_spectrum(int64_t n, const double* eobs, int nchan, const double* edges,
+                       uint64_t* counts, void* stream);
 
 #ifdef __cplusplus
 }

@@ -769,3 +769,44 @@ def tan_known_answer(x, y, ra0_deg, dec0_deg):
     ra = a0 + np.arctan2(xi, den)
     dec = np.arctan2(np.sin(d0) + eta * np.cos(d0), np.hypot(xi, den))
     return np.rad2deg(ra), np.rad2deg(dec)
+
+
+# ---------------------------------------------------------------------------------------
+# event-list consumers: pyxsim/event_list.py:106-134,254-318,344-349
+# ---------------------------------------------------------------------------------------
+def world2pix_tan(ra_deg, dec_deg, sky_center, nx, dtheta):
+    """``wcs.wcs_world2pix(ra, dec, 1)`` for the header EventList builds (event_list.py:106-112):
+    CTYPE RA---TAN/DEC--TAN, CRVAL = sky_center, CRPIX = (nx+1)/2, CDELT = (-dtheta, dtheta).
+    astropy/wcslib is third-party and absent (pyproject.toml: astropy unpinned): this is the
+    published gnomonic projection (Calabretta & Greisen 2002, eqs. 5, 54-55) -- the inverse of
+    the reference's own pixel_to_cel, which tests/ use to pin it."""
+    a0, d0 = np.deg2rad(sky_center[0]), np.deg2rad(sky_center[1])
+    a, d = np.deg2rad(ra_deg), np.deg2rad(dec_deg)
+    D = np.sin(d0) * np.sin(d) + np.cos(d0) * np.cos(d) * np.cos(a - a0)
+    x = np.rad2deg(np.cos(d) * np.sin(a - a0) / D)
+    y = np.rad2deg((np.cos(d0) * np.sin(d) - np.sin(d0) * np.cos(d) * np.cos(a - a0)) / D)
+    crpix = 0.5 * (nx + 1)
+    return crpix + x / (-dtheta), crpix + y / dtheta
+
+
+def event_image(xsky, ysky, eobs, sky_center, fov_arcmin, nx, emin=None, emax=None, pix=None):
+    """EventList.write_fits_image's array (event_list.py:273-295): returns H.T.  ``pix``: use
+    these pixel coordinates instead of world2pix_tan's (to test the binning in isolation)."""
+    emin = -1.0 if emin is None else emin
+    emax = 1.0e10 if emax is None else emax
+    dtheta = fov_arcmin / 60.0 / nx
+    xbins = np.linspace(0.5, float(nx) + 0.5, nx + 1, endpoint=True)
+    ybins = np.linspace(0.5, float(nx) + 0.5, nx + 1, endpoint=True)
+    mask = np.logical_and(eobs >= emin, eobs <= emax)
+    if pix is None:
+        xx, yy = world2pix_tan(xsky[mask], ysky[mask], sky_center, nx, dtheta)
+    else:
+        xx, yy = pix[0][mask], pix[1][mask]
+    H = np.histogram2d(xx, yy, bins=[xbins, ybins])[0]
+    return H.T
+
+
+def event_spectrum(eobs, emin, emax, nchan):
+    """EventList.write_spectrum's counts (event_list.py:344-349)."""
+    ebins = np.linspace(emin, emax, nchan + 1, endpoint=True)
+    return ebins, np.histogram(eobs, bins=ebins)[0]

@@ -4,6 +4,7 @@
 Public names follow ``pyxsim/__init__.py:11-31`` for the parts that belong to the hot path.
 """
 from .data import ArrayDataSource, Cosmology
+from .event_list import EventList, merge_files
 from .internal_absorption import (
     column_density_at_cells,
     make_column_density_map,

@@ -173,6 +173,11 @@ SIGNATURES = {
                                           c_void_p]),
     "pxb_thermal_flux": (C.c_int, [c_void_p, _P(ThermalCells), _P(BandFluxDesc), c_void_p, c_void_p,
                                    c_void_p]),
+    "pxb_cel_to_pixel": (C.c_int, [C.c_int64, c_void_p, c_void_p, C.c_double, C.c_double, C.c_double,
+                                   C.c_double, C.c_double, c_void_p, c_void_p, c_void_p]),
+    "pxb_event_image": (C.c_int, [C.c_int64, c_void_p, c_void_p, c_void_p, C.c_double, C.c_double,
+                                  C.c_double, C.c_double, C.c_int, C.c_double, c_void_p, c_void_p]),
+    "pxb_event_spectrum": (C.c_int, [C.c_int64, c_void_p, C.c_int, c_void_p, c_void_p, c_void_p]),
     "pxb_column_lookup": (C.c_int, [C.c_int64, c_void_p, c_void_p, c_void_p, c_void_p, C.c_int64,
                                     C.c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "pxb_absorb_decide": (C.c_int, [_P(ProjectParams), C.c_int64, c_void_p, c_void_p, c_void_p,

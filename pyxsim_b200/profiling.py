@@ -19,6 +19,7 @@ KERNELS_PER_CALL = {
     "pxb_absorb_transmission": 1,
     "pxb_absorb_decide": 1,
     "pxb_column_lookup": 1,
+    "pxb_cel_to_pixel": 1, "pxb_event_image": 1, "pxb_event_spectrum": 1,
     "pxb_thermal_flux": 1,
 }
 

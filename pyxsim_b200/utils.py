@@ -55,7 +55,8 @@ _LENGTH = {"cm": 1.0 / K.cm_per_kpc, "m": 1e2 / K.cm_per_kpc, "km": 1e5 / K.cm_p
 _TIME = {"s": 1.0, "ks": 1e3, "Ms": 1e6, "yr": 3.15576e7, "kyr": 3.15576e10}
 _AREA = {"cm**2": 1.0, "cm^2": 1.0, "cm2": 1.0, "m**2": 1e4, "m^2": 1e4}
 _ENERGY = {"keV": 1.0, "eV": 1e-3, "MeV": 1e3}
-_FAMILIES = [_LENGTH, _TIME, _AREA, _ENERGY]
+_ANGLE = {"arcsec": 1.0 / 60.0, "arcmin": 1.0, "deg": 60.0, "rad": 60.0 * 180.0 / np.pi}
+_FAMILIES = [_LENGTH, _TIME, _AREA, _ENERGY, _ANGLE]
 
 
 def parse_value(value, default_units):

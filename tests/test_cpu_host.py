@@ -154,3 +154,48 @@ def test_gloo_world_size_2(tmp_path):
     p = subprocess.run(cmd, capture_output=True, text=True, env=env, timeout=240)
     assert p.returncode == 0, p.stdout + p.stderr
     assert "rank0ok" in p.stdout and "rank1ok" in p.stdout
+
+
+def test_fits_writer_roundtrip_and_merge_validation(tmp_path):
+    """The self-contained FITS writer (event_list.py; astropy is absent) produces standard
+    2880-byte blocks that its reader parses back; merge_files' parameter validation
+    (pyxsim/utils.py:63-89) on host lists."""
+    from pyxsim_b200 import event_list as E
+    from pyxsim_b200.photon_list import DeviceList, save_list, load_list
+
+    img = np.arange(35.0).reshape(5, 7)
+    f1 = str(tmp_path / "a.fits")
+    E._write_fits(f1, [E._primary_hdu(img, [("CRPIX1", 4.0), ("CTYPE1", "RA---TAN"), ("CDELT1", -1.0 / 3.0)])], False)
+    assert os.path.getsize(f1) % 2880 == 0
+    (h, data), = E.read_fits(f1)
+    assert h["NAXIS1"] == 7 and h["NAXIS2"] == 5 and h["CTYPE1"] == "RA---TAN" and h["CDELT1"] == -1.0 / 3.0
+    np.testing.assert_array_equal(data, img)
+    cols = [("CHANNEL", "J", None, np.arange(9, dtype="int32")), ("ENERGY", "D", "keV", np.linspace(0, 1, 9)),
+            ("RATE", "E", None, np.linspace(0, 2, 9))]
+    f2 = str(tmp_path / "b.fits")
+    E._write_fits(f2, [E._primary_hdu(), E._bintable_hdu("SPECTRUM", cols, [("POISSERR", True), ("TOTCTS", 12.0)])], False)
+    hd = E.read_fits(f2)
+    assert hd[0][0]["NAXIS"] == 0 and hd[1][0]["TFIELDS"] == 3 and hd[1][0]["TUNIT2"] == "keV" and hd[1][0]["POISSERR"] is True
+    np.testing.assert_array_equal(hd[1][1]["ENERGY"], np.linspace(0, 1, 9))
+    with pytest.raises(OSError):
+        E._write_fits(f2, [E._primary_hdu()], False)
+
+    p = dict(exp_time=10.0, area=2.0, sky_center=np.array([1.0, 2.0]), observer="external")
+    a = DeviceList({"x": 1}, p, {"eobs": np.arange(3.0), "xsky": np.zeros(3), "ysky": np.zeros(3)})
+    b = DeviceList({"x": 2}, dict(p, exp_time=30.0), {"eobs": np.arange(4.0), "xsky": np.ones(4), "ysky": np.ones(4)})
+    fa, fb = str(tmp_path / "la"), str(tmp_path / "lb")
+    save_list(fa, a)
+    save_list(fb, b)
+    with pytest.raises(RuntimeError):
+        E.merge_files([fa, fb], str(tmp_path / "lm"))
+    E.merge_files([fa, fb], str(tmp_path / "lm"), add_exposure_times=True)
+    m = load_list(str(tmp_path / "lm"))
+    assert float(m.parameters["exp_time"]) == 40.0 and m.numpy("eobs").size == 7
+    np.testing.assert_array_equal(m.numpy("xsky"), np.concatenate([np.zeros(3), np.ones(4)]))
+    with pytest.raises(OSError):
+        E.merge_files([fa, fb], str(tmp_path / "lm"), add_exposure_times=True)
+    with pytest.raises(RuntimeError):
+        E.validate_parameters(p, dict(p, area=3.0))
+    with pytest.raises(RuntimeError):
+        E.validate_parameters(p, dict(p, extra=1))
+    E.validate_parameters(p, dict(p, area=2.0 + 1e-12))
