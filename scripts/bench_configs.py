@@ -52,9 +52,9 @@ def scale_exposure(src, model, target, z=0.05):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--scale", type=float, default=1.0)
-    ap.add_argument("--only", default="", help="comma list of a,b,c,d,e,f (default: all)")
+    ap.add_argument("--only", default="", help="comma list of a,b,c,d,f,g (default: all)")
     args = ap.parse_args()
-    only = set(args.only.split(",")) if args.only else set("abcdef")
+    only = set(args.only.split(",")) if args.only else set("abcdefg")
     s = args.scale
     dev = "cuda"
     D_A = px.Cosmology().angular_diameter_distance_mpc(0.0, 0.05) * 3.0856775809623245e24
@@ -210,6 +210,49 @@ def main():
 
     if "f" in only:
         section_f()
+
+    def section_g():
+        # ---- event-list consumers (row f4): image + spectrum binning of a large event list ---------
+        import time
+
+        n = int(3.0e8 * s)
+        g = torch.Generator(device=dev).manual_seed(21)
+        ra = 30.0 + 0.3 * torch.randn(n, generator=g, dtype=torch.float64, device=dev)
+        dec = 45.0 + 0.2 * torch.randn(n, generator=g, dtype=torch.float64, device=dev)
+        e = torch.exp(torch.empty(n, dtype=torch.float64, device=dev).uniform_(np.log(0.1), np.log(10.0), generator=g))
+        from pyxsim_b200.photon_list import DeviceList, save_list
+
+        save_list("mem:g_ev", DeviceList({}, dict(exp_time=1e5, area=1000.0, sky_center=np.array([30.0, 45.0])),
+                                         {"xsky": ra, "ysky": dec, "eobs": e}))
+        ev = px.EventList("mem:g_ev")
+        for label, fn in (("image 2048^2, 0.5-7 keV", lambda: ev.image(60.0, 2048, 0.5, 7.0)),
+                          ("spectrum 4096 channels", lambda: ev.spectrum(0.1, 10.0, 4096))):
+            fn()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(3):
+                fn()
+            torch.cuda.synchronize()
+            ms = (time.perf_counter() - t0) / 3 * 1e3
+            print(json.dumps({"config": f"EventList {label}", "events": n, "ms": round(ms, 2),
+                              "events_per_s": n / (ms * 1e-3)}), flush=True)
+        try:   # CPU reference on a sample: what event_list.py does with NumPy (WCS restated)
+            from oracle import ref_glue as O
+
+            m = 5_000_000
+            xs, ys, es = ra[:m].cpu().numpy(), dec[:m].cpu().numpy(), e[:m].cpu().numpy()
+            t0 = time.perf_counter()
+            O.event_image(xs, ys, es, [30.0, 45.0], 60.0, 2048, 0.5, 7.0)
+            t1 = time.perf_counter()
+            O.event_spectrum(es, 0.1, 10.0, 4096)
+            t2 = time.perf_counter()
+            print(json.dumps({"config": "EventList CPU (NumPy histogram2d / histogram, 1 core)", "events": m,
+                              "image_events_per_s": m / (t1 - t0), "spectrum_events_per_s": m / (t2 - t1)}), flush=True)
+        except Exception as ex:
+            print(json.dumps({"config": "EventList CPU", "error": str(ex)}))
+
+    if "g" in only:
+        section_g()
 
 if __name__ == "__main__":
     main()
