@@ -751,8 +751,8 @@ k_project_detect(const __grid_constant__ pxb_photon_list L,
       det = absorb ? absorb_decision(P, s_wabs, c, p - first, en) : true;
       if (det) {
         tsum += en;
-        tmin = fmin(tmin, en);
-        tmax = fmax(tmax, en);
+        tmin = en < tmin ? en : tmin;   // (energies are never NaN: plain compares, no fmin/fmax)
+        tmax = en > tmax ? en : tmax;
       }
     }
     const unsigned bal = __ballot_sync(0xffffffffu, det);
