@@ -133,6 +133,23 @@ struct CellStream {
   }
 };
 
+// log(k!) for an integer-valued k >= 0 (the only way the samplers below use lgamma): exact
+// table below 16, Stirling's series above (next term < 7e-15 absolute at k = 16) -- one log and
+// one division instead of the general-argument lgamma.
+__device__ const double g_logfact[16] = {
+    0.0, 0.0, 0.69314718055994530942, 1.79175946922805500081, 3.17805383034794561965,
+    4.78749174278204599425, 6.57925121201010099506, 8.52516136106541430017,
+    10.60460290274525022842, 12.80182748008146961121, 15.10441257307551529523,
+    17.50230784587388583929, 19.98721449566188614952, 22.55216385312342288557,
+    25.19122118273868150009, 27.89927138384089156609};
+__device__ __forceinline__ double log_factorial(double k) {
+  if (k < 16.0) return g_logfact[(int)k];
+  const double x = k + 1.0;
+  const double r = 1.0 / x, r2 = r * r;
+  const double series = r * (1.0 / 12.0 - r2 * (1.0 / 360.0 - r2 * (1.0 / 1260.0 - r2 * (1.0 / 1680.0))));
+  return (k + 0.5) * log(x) - x + 0.91893853320467274178 + series;
+}
+
 // Poisson(lam): multiplication method below 10 (Knuth), transformed rejection PTRS above
 // (Hoermann 1993, "The transformed rejection method for generating Poisson random variables").
 __device__ inline int64_t poisson_draw(double lam, CellStream& rs) {
@@ -161,7 +178,7 @@ __device__ inline int64_t poisson_draw(double lam, CellStream& rs) {
     if (us >= 0.07 && V <= vr) return (int64_t)kf;
     if (kf < 0.0 || (us < 0.013 && V > us)) continue;
     if (log(V) + log(invalpha) - log(a / (us * us) + b) <=
-        -lam + kf * loglam - lgamma(kf + 1.0))
+        -lam + kf * loglam - log_factorial(kf))
       return (int64_t)kf;
   }
   return (int64_t)floor(lam + 0.5);  // unreachable in practice
@@ -199,7 +216,7 @@ __device__ inline int64_t binomial_draw(int64_t n, double p, CellStream& rs) {
     const double alpha = (2.83 + 5.1 / b) * spq;
     const double lpq = log(pp / (1.0 - pp));
     const double m = floor((nd + 1.0) * pp);
-    const double h = lgamma(m + 1.0) + lgamma(nd - m + 1.0);
+    const double h = log_factorial(m) + log_factorial(nd - m);
     k = (int64_t)floor(nd * pp + 0.5);
     for (int it = 0; it < 1000; ++it) {
       const double u = rs.next() - 0.5;
@@ -209,7 +226,7 @@ __device__ inline int64_t binomial_draw(int64_t n, double p, CellStream& rs) {
       if (us >= 0.07 && v <= vr) { k = (int64_t)kf; break; }
       if (kf < 0.0 || kf > nd) continue;
       v = log(v * alpha / (a / (us * us) + b));
-      if (v <= h - lgamma(kf + 1.0) - lgamma(nd - kf + 1.0) + (kf - m) * lpq) { k = (int64_t)kf; break; }
+      if (v <= h - log_factorial(kf) - log_factorial(nd - kf) + (kf - m) * lpq) { k = (int64_t)kf; break; }
     }
   }
   return flip ? n - k : k;
