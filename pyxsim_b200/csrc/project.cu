@@ -672,14 +672,16 @@ k_project_photons(const __grid_constant__ pxb_photon_list L,
 }
 
 // ---------------------------------------------------------------------------------------
-// two-pass variant: detect (mask + per-tile counts) -> scan -> emit
+// two-pass variant (default): detect (survivor records + per-tile counts) -> scan -> emit
 // ---------------------------------------------------------------------------------------
 // Same arithmetic and the same event list as the fused kernel, organised without any
-// inter-tile dependency: pass 1 decides absorption for every photon and leaves one 32-bit
-// survivor mask per (tile, round) plus the tile's count; an exclusive scan of the counts gives
-// every tile its base; pass 2 scatters the survivors.  Costs one more read of the energies
-// (+8 B/photon) and buys: no tickets, no look-back spinning, no per-photon state in shared
-// memory.
+// inter-tile dependency: pass 1 decides absorption for every photon and leaves, for every
+// SURVIVOR in photon order, a 16-bit record (position inside the tile | cell relative to the
+// tile's first) plus the tile's count; an exclusive scan of the counts gives every tile its
+// base; pass 2 walks the dense records, so all 32 lanes of a round scatter a survivor and the
+// event stores are contiguous.  Costs one more read of the energies (+8 B/photon) and the
+// records (+4 B/event) and buys: no tickets, no look-back spinning, no idle lanes for absorbed
+// photons.
 __global__ void __launch_bounds__(PROJ_THREADS, 4)
 k_project_detect(const __grid_constant__ pxb_photon_list L,
                  const __grid_constant__ pxb_project_params P, const CellDerived D,

@@ -755,7 +755,7 @@ __device__ __forceinline__ double invert_row_staged(const DevModel& M, int nb, c
 // chunk's first cell blends (t, t+1 of the cosmic and metal tables: 4 x (32 KB CDF + 8 KB
 // guide) at nbins = 4000) are brought into shared memory with four+four cp.async.bulk copies
 // completing on one mbarrier, and stay there across chunks while the temperature bin does not
-// change.  Inside a chunk every warp owns 64-photon tiles (no CTA barriers); photons whose
+// change.  Inside a chunk every warp owns 128-photon tiles (no CTA barriers); photons whose
 // component lives in a staged row gather from shared memory, all others from L1/L2.
 constexpr int STG_THREADS = 1024;
 constexpr int STG_WARPS = STG_THREADS / 32;
