@@ -168,6 +168,53 @@ def test_large_properties(cuda, n, photons):
         px.drop_list(k)
 
 
+def test_more_than_2_31_photons(cuda):
+    """Offsets, tile indices and output ranks are 64-bit throughout: a photon list with more than
+    2^31 photons ("int64 offsets mandatory") generates and projects with
+    consistent bookkeeping, stays bit-reproducible, and detects the same fraction as a list
+    twenty times smaller."""
+    free, _ = torch.cuda.mem_get_info()
+    if free < 110 * 2 ** 30:
+        pytest.skip("needs ~100 GB of free HBM")
+    n = 128
+    src, sm, (kT_nodes, ebins, cosmic, metal) = _cluster(n, nbins=4000, device="cuda")
+    em_sum = float(src.fields[("gas", "emission_measure")].sum())
+    ss = float(np.interp(6.0, kT_nodes, cosmic.sum(1) + 0.3 * metal.sum(1)))
+    D_A = px.Cosmology().angular_diameter_distance_mpc(0.0, 0.05)
+    per_photon = em_sum * ss / (4 * np.pi * (D_A * 3.0856775809623245e24) ** 2 * 1.05 ** 2)
+    frac = {}
+    for tag, photons in (("small", 1.2e8), ("big", 2.4e9)):
+        model = px.ThermalSourceModel(sm, 0.1, 10.0, 4000, 0.3, temperature_field=TF, prng=41)
+        n_ph, n_c = px.make_photons("mem:i64", src, 0.05, photons / per_photon / 1e5, 1e5, model)
+        assert abs(n_ph - photons) < 6 * np.sqrt(photons)
+        lst = px.load_list("mem:i64")
+        nph, e = lst.data["num_photons"], lst.data["energy"]
+        assert e.numel() == n_ph and int(nph.sum()) == n_ph and nph.numel() == n_c
+        if tag == "big":
+            assert n_ph > 2 ** 31
+        # both ends of the energy array were written (the last tiles are the ones whose indices
+        # overflow 32 bits)
+        assert float(e[:1000].min()) >= ebins[0] and float(e[-1000:].min()) >= ebins[0]
+        assert float(e[-1000:].max()) <= ebins[-1]
+        assert float(e.min()) >= ebins[0] and float(e.max()) <= ebins[-1]
+        n1 = px.project_photons("mem:i64", "mem:i64_ev", "z", [30.0, 45.0], absorb_model="wabs", nH=0.3, prng=9)
+        ev = px.load_list("mem:i64_ev")
+        assert ev.data["eobs"].numel() == n1
+        ck = (float(ev.data["eobs"].sum()), float(ev.data["xsky"].sum()), float(ev.data["ysky"][-1]))
+        n2 = px.project_photons("mem:i64", "mem:i64_ev", "z", [30.0, 45.0], absorb_model="wabs", nH=0.3, prng=9)
+        ev2 = px.load_list("mem:i64_ev")
+        assert n1 == n2 and ck == (float(ev2.data["eobs"].sum()), float(ev2.data["xsky"].sum()),
+                                    float(ev2.data["ysky"][-1]))
+        assert float(ev2.data["eobs"].min()) == ev2.parameters["emin"]
+        frac[tag] = (n1 / n_ph, n_ph)
+        px.drop_list("mem:i64")
+        px.drop_list("mem:i64_ev")
+        del lst, ev, ev2, nph, e
+        torch.cuda.empty_cache()
+    (f_s, n_s), (f_b, n_b) = frac["small"], frac["big"]
+    assert abs(f_s - f_b) < 6 * np.sqrt(f_s * (1 - f_s) * (1 / n_s + 1 / n_b))
+
+
 def test_sph_particles_igm_model_end_to_end(cuda, oracle):
     """configs[3]-shaped run at test size: SPH-like particles, density-dependent (kT, nH) table
     with the CIE fallback, log energy binning, SPH-kernel position smoothing."""
