@@ -180,10 +180,15 @@ int pxb_thermal_sample(const pxb_model* model, const pxb_thermal_cells* cells,
  * shift_spectrum (pyxsim/lib/spectra.pyx:67-93): spec_out[j] += sum over cells passing the
  * cut of shift^3 * cell_nrm * (C(ebnew[j+1]/shift) - C(ebnew[j]/shift)), C = np.interp of the
  * cell's cumulative clipped spectrum on the model's linear bin edges.  shift is per cell
- * (device) or NULL (= 1).  ebnew: device [nnew+1]; spec_out: device [nnew], ACCUMULATED. */
+ * (device) or NULL (= 1).  ebnew: device [nnew+1]; spec_out: device [nnew], ACCUMULATED.
+ * Without a shift and with a workspace (pxb_thermal_spectrum_workspace_bytes; may be NULL) the
+ * sum is assembled by linearity from per-row weights -- O(1) per cell -- for every cell whose
+ * clip is a no-op; the others take the per-cell path. */
+int pxb_thermal_spectrum_workspace_bytes(const pxb_model* model, int64_t ncell, int64_t* bytes);
 int pxb_thermal_spectrum(const pxb_model* model, const pxb_thermal_cells* cells,
                          const double* shift, int64_t nnew, const double* ebnew,
-                         double* spec_out, void* stream);
+                         double* spec_out, void* workspace, int64_t workspace_bytes,
+                         void* stream);
 /* make_band (spectra.pyx:96-126) on the cell's clipped spectrum, times cell_nrm
  * (base.py:497-500): out[i] = cell_nrm * shift^(3 + use_energy) * sum_j ener_j * spec_ij over
  * the bins with ebins[j] >= emin/shift and ebins[j+1] <= emax/shift; 0 for cut cells. */

@@ -2,6 +2,7 @@
 // routines (pyxsim/lib/spectra.pyx: shift_spectrum :67-93, make_band :96-126,
 // power_law_spectrum :11-32, line_spectrum :35-64), the thermal ones fused with the table
 // lookup + abundance combine + clip of ThermalSourceModel.process_data (base.py:453-460).
+#include <cstdlib>
 #include "thermal.cuh"
 
 // total spectrum value of bin j for a cell (clipped at 0): base.py:456-460
@@ -30,15 +31,28 @@ __device__ __forceinline__ double spec_bin(const CellMix& mx, double Z, const do
   return fmax(tot, 0.0);
 }
 
-// np.interp(x, xp, fp) with xp ascending in global memory and fp in shared memory
+// np.interp(x, xp, fp) with xp ascending in global memory and fp in shared memory.  When the
+// nodes are uniformly spaced (linear energy binning: uni != 0, xp[j] ~ x0 + j*dx) the interval
+// comes from one division and a fix-up against the stored nodes instead of a binary search --
+// the same interval either way.
 __device__ __forceinline__ double interp_cum(double x, const double* __restrict__ xp,
-                                             const double* fp, int n) {
+                                             const double* fp, int n, int uni = 0, double x0n = 0.0,
+                                             double inv_dx = 0.0) {
   if (x <= __ldg(xp)) return fp[0];
   if (x >= __ldg(xp + n - 1)) return fp[n - 1];
-  int lo = 0, hi = n - 1;  // xp[lo] <= x < xp[hi]
-  while (hi - lo > 1) {
-    const int mid = (lo + hi) >> 1;
-    if (__ldg(xp + mid) <= x) lo = mid; else hi = mid;
+  int lo;
+  if (uni) {
+    lo = (int)((x - x0n) * inv_dx);
+    lo = min(max(lo, 0), n - 2);
+    while (lo > 0 && __ldg(xp + lo) > x) --lo;
+    while (lo < n - 2 && __ldg(xp + lo + 1) <= x) ++lo;
+  } else {
+    lo = 0;
+    int hi = n - 1;  // xp[lo] <= x < xp[hi]
+    while (hi - lo > 1) {
+      const int mid = (lo + hi) >> 1;
+      if (__ldg(xp + mid) <= x) lo = mid; else hi = mid;
+    }
   }
   const double x0 = __ldg(xp + lo), x1 = __ldg(xp + lo + 1);
   const double slope = (fp[lo + 1] - fp[lo]) / (x1 - x0);
@@ -51,7 +65,8 @@ constexpr int SPEC_THREADS = 256;
 __global__ void __launch_bounds__(SPEC_THREADS)
 k_thermal_spectrum(const DevModel M, const __grid_constant__ pxb_thermal_cells C,
                    const double* __restrict__ shift, int nnew, const double* __restrict__ ebnew,
-                   double* __restrict__ spec_out) {
+                   double* __restrict__ spec_out, const int64_t* __restrict__ list,
+                   const unsigned long long* __restrict__ list_count) {
   extern __shared__ double smem[];
   const int nbins = M.nbins;
   double* cum = smem;                      // nbins + 1
@@ -62,7 +77,12 @@ k_thermal_spectrum(const DevModel M, const __grid_constant__ pxb_thermal_cells C
   constexpr int NW = SPEC_THREADS / 32;
   const int seg = ((nbins + NW - 1) / NW + 31) & ~31;
   for (int j = threadIdx.x; j < nnew; j += blockDim.x) acc[j] = 0.0;
-  for (int64_t i = blockIdx.x; i < C.ncell; i += gridDim.x) {
+  // linear binning: M.edges are the keV edges themselves and uniformly spaced
+  const int uni = (M.edges_uniform && !M.binscale_log) ? 1 : 0;
+  const double inv_de = uni ? 1.0 / M.dedge : 0.0;
+  const int64_t nwork = list ? (int64_t)*list_count : C.ncell;   // a list: only the cells on it
+  for (int64_t it = blockIdx.x; it < nwork; it += gridDim.x) {
+    const int64_t i = list ? list[it] : it;
     const double kT = C.kT[i];
     if (!cell_cut(C, i, kT)) continue;                  // uniform across the CTA
     const double nH = C.nH ? C.nH[i] : 0.0;
@@ -95,8 +115,8 @@ k_thermal_spectrum(const DevModel M, const __grid_constant__ pxb_thermal_cells C
     const double inv_s = 1.0 / s;
     for (int j = threadIdx.x; j < nnew; j += blockDim.x) {
       // ebnew / shift as in the reference (a division, not a multiplication by 1/shift)
-      const double a = interp_cum(__ldg(ebnew + j) / s, M.ebins, cum, nbins + 1);
-      const double b = interp_cum(__ldg(ebnew + j + 1) / s, M.ebins, cum, nbins + 1);
+      const double a = interp_cum(__ldg(ebnew + j) / s, M.ebins, cum, nbins + 1, uni, M.edge0, inv_de);
+      const double b = interp_cum(__ldg(ebnew + j + 1) / s, M.ebins, cum, nbins + 1, uni, M.edge0, inv_de);
       acc[j] += wgt * (b - a);
     }
     (void)inv_s;
@@ -104,6 +124,117 @@ k_thermal_spectrum(const DevModel M, const __grid_constant__ pxb_thermal_cells C
   __syncthreads();
   for (int j = threadIdx.x; j < nnew; j += blockDim.x)
     if (acc[j] != 0.0) atomicAdd(spec_out + j, acc[j]);
+}
+
+// ---- unshifted spectra by linearity ------------------------------------------------------
+// Without a Doppler shift the regridding of shift_spectrum is ONE linear map applied to every
+// cell's spectrum, and for a cell whose clip (base.py:460) is a no-op -- non-negative tables,
+// abundances and interpolation weights -- that spectrum is a weighted sum of table rows.  So
+//   sum_cells cnm * regrid(tot_spec) = regrid( sum_rows W[table][row] * table[row] ),
+//   W[table][row] = sum_cells cnm * w_row * coefficient_table,
+// O(1) work per cell instead of O(nbins).  Cells that do need the clip go, through a list, to
+// the per-cell kernel above.
+__global__ void __launch_bounds__(256)
+k_spectrum_weights(const DevModel M, const __grid_constant__ pxb_thermal_cells C,
+                   double* __restrict__ W, int64_t* __restrict__ list,
+                   unsigned long long* __restrict__ list_count, int use_smem) {
+  // W layout: primary table [(2+nvar)][nrows_prim], then fallback table [(2+nvar)][nrows_fb]
+  extern __shared__ double s_w[];
+  const int ntab = 2 + C.nvar;
+  const int np = M.prim.nrows, nf = M.has_fb ? M.fb.nrows : 0;
+  const int nw = ntab * (np + nf);
+  if (use_smem) {
+    for (int j = threadIdx.x; j < nw; j += blockDim.x) s_w[j] = 0.0;
+    __syncthreads();
+  }
+  double* acc = use_smem ? s_w : W;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < C.ncell; i += stride) {
+    const double kT = C.kT[i];
+    if (!cell_cut(C, i, kT)) continue;
+    const double nH = C.nH ? C.nH[i] : 0.0;
+    CellMix mx;
+    cell_mix(M, kT, nH, mx);
+    const double xh = cell_xh(C, i);
+    const double Z = cell_metal(C, i, xh);
+    bool lin = mx.t->nonneg && mx.interior && (Z >= 0.0);
+    for (int k = 0; k < C.nvar; ++k) lin = lin && (cell_elem(C, k, i, xh) >= 0.0);
+    if (!lin) {
+      list[atomicAdd(list_count, 1ull)] = i;
+      continue;
+    }
+    const double cnm = cell_norm(C, i);
+    const bool prim = mx.t == &M.prim;
+    double* base = acc + (prim ? 0 : ntab * np);
+    const int nr_t = prim ? np : nf;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      if (r >= mx.nr) continue;
+      const double wr = cnm * mx.w[r];
+      if (wr == 0.0) continue;
+      atomicAdd(base + mx.row[r], wr);
+      atomicAdd(base + nr_t + mx.row[r], wr * Z);
+      for (int k = 0; k < C.nvar; ++k)
+        atomicAdd(base + (2 + k) * nr_t + mx.row[r], wr * cell_elem(C, k, i, xh));
+    }
+  }
+  if (use_smem) {
+    __syncthreads();
+    for (int j = threadIdx.x; j < nw; j += blockDim.x)
+      if (s_w[j] != 0.0) atomicAdd(W + j, s_w[j]);
+  }
+}
+
+// one CTA: summed spectrum on the model's bins from the row weights, cumulative, np.interp at
+// the new edges (shift_spectrum with shift = 1, spectra.pyx:67-93), accumulate into spec_out
+__global__ void __launch_bounds__(1024)
+k_spectrum_from_weights(const DevModel M, int nvar, const double* __restrict__ W, int nnew,
+                        const double* __restrict__ ebnew, double* __restrict__ spec_out) {
+  extern __shared__ double smem[];
+  const int nbins = M.nbins;
+  double* cum = smem;                 // nbins + 1
+  double* s_wtot = cum + (nbins + 1);  // warps
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int NW = blockDim.x / 32;
+  const int seg = ((nbins + NW - 1) / NW + 31) & ~31;
+  const int ntab = 2 + nvar;
+  if (threadIdx.x == 0) cum[0] = 0.0;
+  const int j0 = wid * seg, j1 = min(j0 + seg, nbins);
+  double carry = 0.0;
+  for (int jb = j0; jb < j1; jb += 32) {
+    const int j = jb + lane;
+    double v = 0.0;
+    if (j < j1) {
+      for (int tb = 0; tb < 2; ++tb) {           // primary, fallback
+        const DevTable& t = tb == 0 ? M.prim : M.fb;
+        if (tb == 1 && !M.has_fb) break;
+        const double* Wt = W + (tb == 0 ? 0 : (size_t)ntab * M.prim.nrows);
+        for (int q = 0; q < ntab; ++q) {
+          const double* tab = q == 0 ? t.cosmic : (q == 1 ? t.metal : t.var + (size_t)(q - 2) * t.nrows * nbins);
+          for (int r = 0; r < t.nrows; ++r) {
+            const double w = __ldg(Wt + (size_t)q * t.nrows + r);
+            if (w != 0.0) v += w * __ldg(tab + (size_t)r * nbins + j);
+          }
+        }
+      }
+    }
+    v = warp_incl_scan(v, lane) + carry;
+    if (j < j1) cum[j + 1] = v;
+    carry = __shfl_sync(0xffffffffu, v, 31);
+  }
+  if (lane == 0) s_wtot[wid] = carry;
+  __syncthreads();
+  double basev = 0.0;
+  for (int w = 0; w < wid; ++w) basev += s_wtot[w];
+  if (wid > 0)
+    for (int j = j0 + lane; j < j1; j += 32) cum[j + 1] += basev;
+  __syncthreads();
+  for (int j = threadIdx.x; j < nnew; j += blockDim.x) {
+    const double a = interp_cum(__ldg(ebnew + j), M.ebins, cum, nbins + 1);
+    const double b = interp_cum(__ldg(ebnew + j + 1), M.ebins, cum, nbins + 1);
+    const double d = b - a;
+    if (d != 0.0) atomicAdd(spec_out + j, d);
+  }
 }
 
 // make_band: one warp per cell
@@ -255,24 +386,71 @@ static int check_model_cells(const pxb_model* model, const pxb_thermal_cells* c)
   return PXB_OK;
 }
 
+static int64_t spectrum_weight_count(const DevModel& D) {
+  return (int64_t)(2 + D.nvar) * (D.prim.nrows + (D.has_fb ? D.fb.nrows : 0));
+}
+
+extern "C" int pxb_thermal_spectrum_workspace_bytes(const pxb_model* model, int64_t ncell,
+                                                    int64_t* bytes) {
+  PXB_REQUIRE(model && bytes && ncell >= 0, "bad argument");
+  // [list count, pad | row weights | list of cells that need the per-cell path]
+  *bytes = (2 + spectrum_weight_count(model->dev) + ncell) * (int64_t)sizeof(double);
+  return PXB_OK;
+}
+
 extern "C" int pxb_thermal_spectrum(const pxb_model* model, const pxb_thermal_cells* cells,
                                     const double* shift, int64_t nnew, const double* ebnew,
-                                    double* spec_out, void* stream) {
+                                    double* spec_out, void* workspace, int64_t workspace_bytes,
+                                    void* stream) {
   int rc = check_model_cells(model, cells);
   if (rc) return rc;
   PXB_REQUIRE(nnew >= 1 && ebnew && spec_out, "bad output grid");
   if (cells->ncell == 0) return PXB_OK;
-  const size_t smem = ((size_t)model->dev.nbins + 1 + nnew + PXB_MAX_VAR + SPEC_THREADS / 32) * sizeof(double);
+  cudaStream_t st = (cudaStream_t)stream;
+  const DevModel& D = model->dev;
+  const size_t smem = ((size_t)D.nbins + 1 + nnew + PXB_MAX_VAR + SPEC_THREADS / 32) * sizeof(double);
   PXB_REQUIRE(smem <= 227 * 1024, "nbins + output bins = %lld needs %zu B of shared memory (max 227 KB)",
-              (long long)(model->dev.nbins + nnew), smem);
+              (long long)(D.nbins + nnew), smem);
   PXB_CUDA(cudaFuncSetAttribute(k_thermal_spectrum, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = 0;
   PXB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_thermal_spectrum, SPEC_THREADS, smem));
   if (per_sm < 1) per_sm = 1;
   int64_t grid = (int64_t)pxb_sm_count() * per_sm;
   if (grid > cells->ncell) grid = cells->ncell;
-  k_thermal_spectrum<<<(unsigned)grid, SPEC_THREADS, smem, (cudaStream_t)stream>>>(
-      model->dev, *cells, shift, (int)nnew, ebnew, spec_out);
+  // Without a shift and with a workspace the spectrum is assembled from per-row weights; only
+  // the cells whose clip matters take the per-cell path.
+  const bool linear = shift == nullptr && workspace != nullptr &&
+                      (D.prim.nonneg || (D.has_fb && D.fb.nonneg)) && !getenv("PXB_SPECTRUM_PER_CELL");
+  if (linear) {
+    int64_t need = 0;
+    pxb_thermal_spectrum_workspace_bytes(model, cells->ncell, &need);
+    PXB_REQUIRE(workspace_bytes >= need, "spectrum workspace too small (%lld < %lld)",
+                (long long)workspace_bytes, (long long)need);
+    const int64_t nw = spectrum_weight_count(D);
+    unsigned long long* count = (unsigned long long*)workspace;
+    double* W = (double*)workspace + 2;
+    int64_t* list = (int64_t*)(W + nw);
+    PXB_CUDA(cudaMemsetAsync(workspace, 0, (size_t)(2 + nw) * sizeof(double), st));
+    const size_t wsm = (size_t)nw * sizeof(double);
+    const int use_smem = wsm <= 96 * 1024 ? 1 : 0;
+    if (use_smem)
+      PXB_CUDA(cudaFuncSetAttribute(k_spectrum_weights, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wsm));
+    int64_t g = (cells->ncell + 255) / 256;
+    const int64_t cap = (int64_t)pxb_sm_count() * 4;
+    if (g > cap) g = cap;
+    k_spectrum_weights<<<(unsigned)g, 256, use_smem ? wsm : 0, st>>>(D, *cells, W, list, count, use_smem);
+    PXB_LAUNCH_CHECK();
+    const size_t fsm = ((size_t)D.nbins + 1 + 32) * sizeof(double);
+    PXB_CUDA(cudaFuncSetAttribute(k_spectrum_from_weights, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsm));
+    k_spectrum_from_weights<<<1, 1024, fsm, st>>>(D, cells->nvar, W, (int)nnew, ebnew, spec_out);
+    PXB_LAUNCH_CHECK();
+    k_thermal_spectrum<<<(unsigned)grid, SPEC_THREADS, smem, st>>>(D, *cells, shift, (int)nnew, ebnew,
+                                                                  spec_out, list, count);
+    PXB_LAUNCH_CHECK();
+    return PXB_OK;
+  }
+  k_thermal_spectrum<<<(unsigned)grid, SPEC_THREADS, smem, st>>>(D, *cells, shift, (int)nnew, ebnew,
+                                                                spec_out, nullptr, nullptr);
   PXB_LAUNCH_CHECK();
   return PXB_OK;
 }

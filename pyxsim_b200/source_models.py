@@ -580,9 +580,13 @@ class ThermalSourceModel(SourceModel):
         shift = self.compute_shift(chunk) if shifting else None
         eb = to_device(ebins)
         spec = torch.zeros(ebins.size - 1, dtype=torch.float64, device=eb.device)
+        need = C.c_int64()
+        _lib.call("pxb_thermal_spectrum_workspace_bytes", dm.handle, Cs.ncell, C.byref(need))
+        ws = torch.empty(need.value, dtype=torch.uint8, device=eb.device)
         with stage("thermal_spectrum"):
             _lib.call("pxb_thermal_spectrum", dm.handle, C.byref(Cs), ptr(shift), ebins.size - 1,
-                      ptr(eb), ptr(spec), stream_ptr())
+                      ptr(eb), ptr(spec), ptr(ws), need.value, stream_ptr())
+        del ws
         return spec.cpu().numpy()
 
     def _finish_spectrum(self, ebins, spec):

@@ -254,3 +254,32 @@ def test_source_and_intensity_fields(cuda, oracle):
     for k in n1:
         np.testing.assert_allclose(src.fields[k].cpu().numpy(), i_nd[k], rtol=1e-12)
         assert (i_nd[k] > 0).all()
+
+
+def test_unshifted_spectrum_by_linearity_equals_per_cell_path(cuda, oracle, monkeypatch):
+    """Without a Doppler shift the spectrum is assembled from per-row weights (O(1) per cell);
+    cells whose clip matters (here: temperatures outside the table, which extrapolate to negative
+    spectra) are listed and take the per-cell kernel.  Both routes against the reference Cython,
+    and against each other."""
+    t = H.make_tables(nT=12, nbins=300, nvar=2)
+    t["Tvals"] = np.logspace(np.log10(0.8), np.log10(9.0), 12)       # narrow table: many cells extrapolate
+    kT, em = H.random_cells(5000, seed=12, kT_range=(0.1, 40.0))
+    extra = {("gas", "Z"): np.random.RandomState(1).uniform(0, 1, kT.size)}
+    src = H.cells_source(kT, em, extra=extra)
+    model = px.ThermalSourceModel(H.product_model(t), 0.1, 10.0, 300, ("gas", "Z"), temperature_field=TF,
+                                  var_elem={"O": 0.5, "Fe": 1.5}, prng=1)
+    model.setup_model("spectrum", src, 0.0)
+    chunk = next(src.chunks())
+    ebnew = np.linspace(0.3, 8.0, 151)
+    lin = model.process_data("spectrum", chunk, 3e-44, ebins=ebnew, shifting=False)
+    monkeypatch.setenv("PXB_SPECTRUM_PER_CELL", "1")
+    per = model.process_data("spectrum", chunk, 3e-44, ebins=ebnew, shifting=False)
+    monkeypatch.delenv("PXB_SPECTRUM_PER_CELL")
+    np.testing.assert_allclose(lin, per, rtol=1e-11, atol=per.max() * 1e-14)
+    om = H.oracle_model(oracle, t)
+    cfg = dict(kT_min=0.025, kT_max=64.0, Zmet="Z", Zconvert=1.0, z_by_xh=False, spectral_norm=3e-44,
+               var_elem=[(0.5, 1.0, False), (1.5, 1.0, False)])
+    ref = oracle.thermal_spectrum_mode(om, cfg, dict(kT=kT, em=em, Z=extra[("gas", "Z")]), ebnew)
+    np.testing.assert_allclose(lin, ref, rtol=1e-11, atol=ref.max() * 1e-14)
+    inside = (kT >= t["Tvals"][0]) & (kT <= t["Tvals"][-1])
+    assert 500 < inside.sum() < 4500          # both routes carried a real share of the cells
