@@ -12,17 +12,19 @@ struct PlCoef {
   double a;      // ei^(1-alpha)
   double nf;     // norm_fac = e0^alpha * (ef^(1-alpha) - ei^(1-alpha))   (power_law_sources.py:214)
   double inv;    // 1/(1-alpha); 0 flags alpha == 1
+  double lognf;  // alpha == 1: log(ef/ei)
 };
 
 __device__ __forceinline__ PlCoef pl_coef(const pxb_powerlaw_cells& C, double alpha) {
   PlCoef k;
   if (alpha == 1.0) {
-    k.a = C.emin; k.nf = C.emax / C.emin; k.inv = 0.0;
+    k.a = C.emin; k.nf = C.emax / C.emin; k.inv = 0.0; k.lognf = log(k.nf);
   } else {
     const double om = 1.0 - alpha;
     k.a = pow(C.emin, om);
     k.nf = pow(C.e0, alpha) * (pow(C.emax, om) - k.a);
     k.inv = 1.0 / om;
+    k.lognf = 0.0;
   }
   return k;
 }
@@ -68,23 +70,32 @@ k_powerlaw_sample(const __grid_constant__ pxb_powerlaw_cells C, int64_t n_active
   const int64_t p1 = min(p0 + (int64_t)SRC_TILE, n_photons);
   TileMap<SRC_TILE> tm;
   tm.build(poff, n_active, p0, p1, s_off, s_c);
-  const PlCoef kc = pl_coef(C, C.alpha_const);
-  if (C.alpha && tm.nc > 0) {
+  // sampler coefficients (three pow() each): once per cell of the tile, or once per CTA for a
+  // constant photon index -- never per thread
+  __shared__ PlCoef s_kc;
+  if (!C.alpha) {
+    if (threadIdx.x == 0) s_kc = pl_coef(C, C.alpha_const);
+    __syncthreads();
+  } else if (tm.nc > 0) {
     for (int q = threadIdx.x; q < tm.nc; q += blockDim.x)
       s_k[q] = pl_coef(C, C.alpha[idx[tm.c0 + q]]);
     __syncthreads();
   }
   for (int64_t p = p0 + threadIdx.x; p < p1; p += blockDim.x) {
     const int64_t c = tm.cell_of(p, s_off);
-    PlCoef k = kc;
-    if (C.alpha) k = (tm.nc > 0) ? s_k[c - tm.c0] : pl_coef(C, C.alpha[idx[c]]);
+    PlCoef k;
+    if (!C.alpha) k = s_kc;
+    else k = (tm.nc > 0) ? s_k[c - tm.c0] : pl_coef(C, C.alpha[idx[c]]);
     const uint64_t gid = (uint64_t)(C.cell_id0 + idx[c]);
     const uint64_t draw = (uint64_t)(p - __ldg(poff + c));
-    const Philox4 r = pxb_rand4(C.seed, STREAM_POWERLAW, gid, draw);
-    const double u = u53(r.x, r.y);
+    // photons 2m and 2m+1 of a cell use the two halves of one Philox block
+    const Philox4 r = pxb_rand4(C.seed, STREAM_POWERLAW, gid, draw >> 1);
+    const double u = (draw & 1) ? u53(r.z, r.w) : u53(r.x, r.y);
+    // x**y as exp(y log x): both bases are positive and |y log x| stays of order one (it is the
+    // log of an energy ratio), so this is within a few ulp of pow() at a third of its cost
     double e;
-    if (k.inv == 0.0) e = k.a * pow(k.nf, u);          // ei * (ef/ei)**u, :233-234
-    else e = pow(k.a + u * k.nf, k.inv);               // :236-237
+    if (k.inv == 0.0) e = k.a * exp(u * k.lognf);      // ei * (ef/ei)**u, :233-234
+    else e = exp(k.inv * log(k.a + u * k.nf));         // :236-237
     st_stream(energies + p, e * C.scale_factor);
   }
 }

@@ -795,13 +795,15 @@ class PowerLawSourceModel(SourceModel):
         keep = []
         Cs = self._cells_struct(chunk, spectral_norm, keep)
         counts = empty(Cs.ncell, torch.int64)
-        _lib.call("pxb_powerlaw_counts", C.byref(Cs), None, ptr(counts), stream_ptr())
+        with stage("powerlaw_counts"):
+            _lib.call("pxb_powerlaw_counts", C.byref(Cs), None, ptr(counts), stream_ptr())
         out = self._scan_and_compact(counts, chunk, gather)
         if out.n_photons == 0:
             return None
         out.energy = empty(out.n_photons)
-        _lib.call("pxb_powerlaw_sample", C.byref(Cs), out.n_cells, ptr(out.idx), ptr(out.nph),
-                  ptr(out.poff), out.n_photons, ptr(out.energy), stream_ptr())
+        with stage("powerlaw_sample"):
+            _lib.call("pxb_powerlaw_sample", C.byref(Cs), out.n_cells, ptr(out.idx), ptr(out.nph),
+                      ptr(out.poff), out.n_photons, ptr(out.energy), stream_ptr())
         return out
 
     def _spectrum_chunk(self, chunk, spectral_norm, ebins, shifting):
@@ -900,13 +902,15 @@ class LineSourceModel(SourceModel):
         keep = []
         Cs = self._cells_struct(chunk, spectral_norm, keep)
         counts = empty(Cs.ncell, torch.int64)
-        _lib.call("pxb_line_counts", C.byref(Cs), None, ptr(counts), stream_ptr())
+        with stage("line_counts"):
+            _lib.call("pxb_line_counts", C.byref(Cs), None, ptr(counts), stream_ptr())
         out = self._scan_and_compact(counts, chunk, gather)
         if out.n_photons == 0:
             return None
         out.energy = empty(out.n_photons)
-        _lib.call("pxb_line_sample", C.byref(Cs), out.n_cells, ptr(out.idx), ptr(out.nph),
-                  ptr(out.poff), out.n_photons, ptr(out.energy), stream_ptr())
+        with stage("line_sample"):
+            _lib.call("pxb_line_sample", C.byref(Cs), out.n_cells, ptr(out.idx), ptr(out.nph),
+                      ptr(out.poff), out.n_photons, ptr(out.energy), stream_ptr())
         return out
 
     _gauss = None
