@@ -7,14 +7,13 @@ binning the reference does on the host (astropy WCS ``wcs_world2pix`` + ``np.his
 small self-contained writer (primary image HDU and binary tables with the reference's header
 keywords -- astropy is not required).  SIMPUT export is soxs' and is not reimplemented.
 """
-import ctypes as C
 import os
 from glob import glob
 
 import numpy as np
 import torch
 
-from . import _lib, constants as K
+from . import _lib
 from .device import ptr, stream_ptr, to_device
 from .photon_list import DeviceList, load_list, save_list, _strip
 from .utils import mylog, parse_value

@@ -15,7 +15,6 @@ cell's rotated position, then absorbs that cell's photons at their source-frame 
   reference calls it (agreement 1e-13: the rotated position is a BLAS product there);
 * the per-cell absorption itself is fused into the projection kernel (``nH_cell``).
 """
-import ctypes as C
 import os
 
 import numpy as np
