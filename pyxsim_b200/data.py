@@ -16,7 +16,6 @@ Unit conventions of an ArrayDataSource (override per field with ``units={field: 
   luminosity (power law)  keV/s  (or "erg/s");  line emission  photons/s
 """
 import numpy as np
-import torch
 
 from . import constants as K
 
