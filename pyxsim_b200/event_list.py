@@ -283,6 +283,44 @@ class EventList:
                ("HDUCLAS1", "EVENTS"), ("HDUCLAS2", "ACCEPTED")]
         _write_fits(fitsfile, [_primary_hdu(), _bintable_hdu("EVENTS", cols, hdr)], overwrite)
 
+    # -- region filters (event_list.py:387-432) --------------------------------------------
+    def _filter(self, prefix, keep_condition):
+        """Write, per input list, a list named ``f"{prefix}_{name}"`` holding the events for which
+        ``keep_condition(xsky, ysky)`` (device tensors) is true, with flux / emin / emax recomputed
+        (the reference assigns emax to the ``emin`` key, event_list.py:413-414 -- a typo; both keys
+        are set properly here).  Returns the new names."""
+        new_names = []
+        for nm, lst in zip(self.filenames, self._lists):
+            x, y = self._dev(lst, "xsky"), self._dev(lst, "ysky")
+            keep = keep_condition(x, y)
+            data = {k: to_device(v, dtype=v.dtype if isinstance(v, torch.Tensor) else torch.float64)[keep]
+                    for k, v in lst.data.items()}
+            params = dict(lst.parameters)
+            e = data["eobs"]
+            if e.numel() == 0:
+                params.update(flux=0.0, emin=float("nan"), emax=float("nan"))
+            else:
+                params.update(flux=float(e.sum()) * 1.602176634e-9 / float(params["exp_time"]) / float(params["area"]),
+                              emin=float(e.min()), emax=float(e.max()))
+            if nm.startswith("mem:"):
+                new = "mem:" + prefix + "_" + nm[4:]
+            else:
+                new = os.path.join(os.path.dirname(nm), prefix + "_" + os.path.basename(nm))
+            info = dict(lst.info)
+            save_list(new, DeviceList(info, params, data))
+            new_names.append(new)
+        return new_names
+
+    def filter_circle(self, prefix, center, radius):
+        """Events inside a circle of ``radius`` around ``center`` (both in the units of xsky/ysky,
+        plain Euclidean distance as in event_list.py:417-423)."""
+        return self._filter(prefix, lambda x, y: (x - center[0]) ** 2 + (y - center[1]) ** 2 <= radius * radius)
+
+    def filter_rectangle(self, prefix, left_edge, right_edge):
+        """Events with left_edge <= (xsky, ysky) < right_edge (event_list.py:425-431)."""
+        return self._filter(prefix, lambda x, y: (x >= left_edge[0]) & (x < right_edge[0])
+                            & (y >= left_edge[1]) & (y < right_edge[1]))
+
     def write_to_simput(self, prefix, overwrite=False):
         raise NotImplementedError("SIMPUT export is soxs' SimputCatalog (event_list.py:214-252); "
                                   "install soxs and use the reference EventList for it")

@@ -144,3 +144,23 @@ def test_fits_writers_and_merge(cuda, oracle, tmp_path):
         px.merge_files(["mem:ev_a", "mem:ev_c"], "mem:ev_ac")          # exposure times differ
     px.merge_files(["mem:ev_a", "mem:ev_c"], "mem:ev_ac", add_exposure_times=True)
     assert px.EventList("mem:ev_ac").parameters["exp_time"] == 1.5e5
+
+
+def test_region_filters(cuda):
+    d, p = _events(n=60000, name="ev_flt", seed=8)
+    ev = px.EventList("mem:ev_flt")
+    (name,) = ev.filter_circle("circ", [30.0, 45.0], 0.15)
+    assert name == "mem:circ_ev_flt"
+    c = px.EventList(name)
+    keep = (d["xsky"] - 30.0) ** 2 + (d["ysky"] - 45.0) ** 2 <= 0.15 ** 2
+    np.testing.assert_array_equal(c["eobs"], d["eobs"][keep])
+    np.testing.assert_array_equal(c["xsky"], d["xsky"][keep])
+    assert c.parameters["emin"] == d["eobs"][keep].min() and c.parameters["emax"] == d["eobs"][keep].max()
+    np.testing.assert_allclose(c.parameters["flux"], d["eobs"][keep].sum() * 1.602176634e-9 / 1.0e5 / 1000.0, rtol=1e-12)
+    (name,) = ev.filter_rectangle("rect", [29.9, 44.9], [30.1, 45.2])
+    r = px.EventList(name)
+    keep = (d["xsky"] >= 29.9) & (d["xsky"] < 30.1) & (d["ysky"] >= 44.9) & (d["ysky"] < 45.2)
+    np.testing.assert_array_equal(r["ysky"], d["ysky"][keep])
+    (name,) = ev.filter_circle("none", [0.0, 0.0], 1e-3)
+    lst = px.load_list(name)
+    assert lst.data["eobs"].numel() == 0 and lst.parameters["flux"] == 0.0 and np.isnan(lst.parameters["emin"])
