@@ -191,9 +191,13 @@ int pxb_thermal_spectrum(const pxb_model* model, const pxb_thermal_cells* cells,
                          void* stream);
 /* make_band (spectra.pyx:96-126) on the cell's clipped spectrum, times cell_nrm
  * (base.py:497-500): out[i] = cell_nrm * shift^(3 + use_energy) * sum_j ener_j * spec_ij over
- * the bins with ebins[j] >= emin/shift and ebins[j+1] <= emax/shift; 0 for cut cells. */
+ * the bins with ebins[j] >= emin/shift and ebins[j+1] <= emax/shift; 0 for cut cells.  With a
+ * workspace (pxb_thermal_band_workspace_bytes; may be NULL) cells whose clip is a no-op are done
+ * in O(1) from per-row prefix sums, the others per cell. */
+int pxb_thermal_band_workspace_bytes(int64_t ncell, int64_t* bytes);
 int pxb_thermal_band(const pxb_model* model, const pxb_thermal_cells* cells, int use_energy,
-                     double emin, double emax, const double* shift, double* out, void* stream);
+                     double emin, double emax, const double* shift, double* out, void* workspace,
+                     int64_t workspace_bytes, void* stream);
 /* Band fluxes of a table, per table row (what make_fluxf tabulates, spectral_models.py:101-134,
  * 464-478): device arrays [nrows] (vflux: [nvar][nrows] or NULL); fb_* describe the 1-D CIE
  * fallback table of a density-dependent model (NULL otherwise). */

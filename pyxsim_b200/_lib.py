@@ -140,8 +140,9 @@ SIGNATURES = {
     "pxb_thermal_spectrum_workspace_bytes": (C.c_int, [c_void_p, C.c_int64, _P(C.c_int64)]),
     "pxb_thermal_spectrum": (C.c_int, [c_void_p, _P(ThermalCells), c_void_p, C.c_int64, c_void_p,
                                        c_void_p, c_void_p, C.c_int64, c_void_p]),
+    "pxb_thermal_band_workspace_bytes": (C.c_int, [C.c_int64, _P(C.c_int64)]),
     "pxb_thermal_band": (C.c_int, [c_void_p, _P(ThermalCells), C.c_int, C.c_double, C.c_double,
-                                   c_void_p, c_void_p, c_void_p]),
+                                   c_void_p, c_void_p, c_void_p, C.c_int64, c_void_p]),
     "pxb_powerlaw_spectrum": (C.c_int, [C.c_int64, c_void_p, c_void_p, c_void_p, C.c_int64, c_void_p,
                                         c_void_p, c_void_p]),
     "pxb_line_spectrum": (C.c_int, [C.c_int64, C.c_double, c_void_p, c_void_p, c_void_p, C.c_int64,

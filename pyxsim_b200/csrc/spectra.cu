@@ -237,15 +237,78 @@ k_spectrum_from_weights(const DevModel M, int nvar, const double* __restrict__ W
   }
 }
 
-// make_band: one warp per cell
+// make_band in O(1) per cell.  For a cell whose clip is a no-op the band sum of its blended
+// spectrum is the blend of the rows' band sums, and a band sum over whole bins is a difference of
+// two prefix sums:  sum_{j in band} ener_j spec_ij = sum_rows w_r (P_r[j1] - P_r[j0]).  The band's
+// bins are those with ebins[j] >= emin/shift and ebins[j+1] <= emax/shift (spectra.pyx:115-118):
+// j0 = first j with ebins[j] >= lo, j1 = last q with ebins[q] <= hi.  Other cells are listed for
+// the warp-per-cell kernel.
+__global__ void __launch_bounds__(256)
+k_thermal_band_fast(const DevModel M, const __grid_constant__ pxb_thermal_cells C, int use_energy,
+                    double emin, double emax, const double* __restrict__ shift,
+                    double* __restrict__ out, int64_t* __restrict__ list,
+                    unsigned long long* __restrict__ list_count) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= C.ncell) return;
+  const double kT = C.kT[i];
+  if (!cell_cut(C, i, kT)) {
+    out[i] = 0.0;
+    return;
+  }
+  const double nH = C.nH ? C.nH[i] : 0.0;
+  CellMix mx;
+  cell_mix(M, kT, nH, mx);
+  const double xh = cell_xh(C, i);
+  const double Z = cell_metal(C, i, xh);
+  const DevTable* t = mx.t;
+  bool lin = t->nonneg && t->pre_n && mx.interior && (Z >= 0.0);
+  for (int k = 0; k < C.nvar; ++k) lin = lin && (cell_elem(C, k, i, xh) >= 0.0);
+  if (!lin) {
+    list[atomicAdd(list_count, 1ull)] = i;
+    return;
+  }
+  const double s = shift ? shift[i] : 1.0;
+  const double lo = emin / s, hi = emax / s;
+  const int nb = M.nbins;
+  int j0, j1;
+  {
+    int a = 0, b = nb + 1;                  // first j in [0, nb] with ebins[j] >= lo
+    while (a < b) { const int m = (a + b) >> 1; if (__ldg(M.ebins + m) < lo) a = m + 1; else b = m; }
+    j0 = a;
+    a = 0; b = nb + 1;                      // number of edges <= hi
+    while (a < b) { const int m = (a + b) >> 1; if (__ldg(M.ebins + m) <= hi) a = m + 1; else b = m; }
+    j1 = a - 1;
+  }
+  double sum = 0.0;
+  if (j1 > j0) {
+    const double* P = use_energy ? t->pre_e : t->pre_n;
+    const size_t rs = (size_t)(nb + 1), ts = (size_t)t->nrows * rs;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      if (r >= mx.nr) continue;
+      const double* pr = P + (size_t)mx.row[r] * rs;
+      double v = (__ldg(pr + j1) - __ldg(pr + j0)) + Z * (__ldg(pr + ts + j1) - __ldg(pr + ts + j0));
+      for (int k = 0; k < C.nvar; ++k)
+        v += cell_elem(C, k, i, xh) * (__ldg(pr + (2 + k) * ts + j1) - __ldg(pr + (2 + k) * ts + j0));
+      sum += mx.w[r] * v;
+    }
+  }
+  double sh = s * s * s;
+  if (use_energy) sh *= s;
+  out[i] = sh * sum * cell_norm(C, i);
+}
+
+// make_band: one warp per cell (or per listed cell)
 __global__ void __launch_bounds__(256)
 k_thermal_band(const DevModel M, const __grid_constant__ pxb_thermal_cells C, int use_energy,
                double emin, double emax, const double* __restrict__ shift,
-               double* __restrict__ out) {
+               double* __restrict__ out, const int64_t* __restrict__ list,
+               const unsigned long long* __restrict__ list_count) {
   __shared__ double s_eZ[8][PXB_MAX_VAR];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-  const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  if (i >= C.ncell) return;
+  const int64_t it = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (it >= (list ? (int64_t)*list_count : C.ncell)) return;
+  const int64_t i = list ? list[it] : it;
   const double kT = C.kT[i];
   if (!cell_cut(C, i, kT)) {
     if (lane == 0) out[i] = 0.0;
@@ -455,18 +518,43 @@ extern "C" int pxb_thermal_spectrum(const pxb_model* model, const pxb_thermal_ce
   return PXB_OK;
 }
 
+extern "C" int pxb_thermal_band_workspace_bytes(int64_t ncell, int64_t* bytes) {
+  PXB_REQUIRE(bytes && ncell >= 0, "bad argument");
+  *bytes = (2 + ncell) * (int64_t)sizeof(int64_t);   // [list count, pad | list]
+  return PXB_OK;
+}
+
 extern "C" int pxb_thermal_band(const pxb_model* model, const pxb_thermal_cells* cells, int use_energy,
                                 double emin, double emax, const double* shift, double* out,
-                                void* stream) {
+                                void* workspace, int64_t workspace_bytes, void* stream) {
   int rc = check_model_cells(model, cells);
   if (rc) return rc;
   if (cells->ncell == 0) return PXB_OK;
   PXB_REQUIRE(out, "out is NULL");
+  cudaStream_t st = (cudaStream_t)stream;
+  const DevModel& D = model->dev;
   const int64_t nwarp = cells->ncell;
   const int64_t blocks = (nwarp + 7) / 8;
   PXB_REQUIRE(blocks < (1LL << 31), "too many cells for one call");
-  k_thermal_band<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(model->dev, *cells, use_energy,
-                                                                    emin, emax, shift, out);
+  const bool fast = workspace != nullptr && (D.prim.pre_n || (D.has_fb && D.fb.pre_n)) &&
+                    !getenv("PXB_BAND_PER_CELL");
+  if (fast) {
+    int64_t need = 0;
+    pxb_thermal_band_workspace_bytes(cells->ncell, &need);
+    PXB_REQUIRE(workspace_bytes >= need, "band workspace too small (%lld < %lld)",
+                (long long)workspace_bytes, (long long)need);
+    unsigned long long* count = (unsigned long long*)workspace;
+    int64_t* list = (int64_t*)workspace + 2;
+    PXB_CUDA(cudaMemsetAsync(workspace, 0, 2 * sizeof(int64_t), st));
+    k_thermal_band_fast<<<(unsigned)((cells->ncell + 255) / 256), 256, 0, st>>>(
+        D, *cells, use_energy, emin, emax, shift, out, list, count);
+    PXB_LAUNCH_CHECK();
+    k_thermal_band<<<(unsigned)blocks, 256, 0, st>>>(D, *cells, use_energy, emin, emax, shift, out, list, count);
+    PXB_LAUNCH_CHECK();
+    return PXB_OK;
+  }
+  k_thermal_band<<<(unsigned)blocks, 256, 0, st>>>(D, *cells, use_energy, emin, emax, shift, out,
+                                                  nullptr, nullptr);
   PXB_LAUNCH_CHECK();
   return PXB_OK;
 }

@@ -113,6 +113,34 @@ static int build_table(pxb_model* m, const pxb_table_desc& d, DevTable& t) {
   return PXB_OK;
 }
 
+// unnormalised per-row prefix sums (photon and energy weighted) for the O(1) band sums
+static int build_prefix(pxb_model* m, const pxb_table_desc& d, DevTable& t, const double* emid) {
+  if (d.nx == 0 || !t.nonneg) return PXB_OK;
+  const int ntab = 2 + d.nvar;
+  const size_t nb = (size_t)d.nbins;
+  std::vector<double> pn((size_t)ntab * t.nrows * (nb + 1)), pe(pn.size());
+  for (int tb = 0; tb < ntab; ++tb) {
+    const double* tab = tb == 0 ? d.cosmic : (tb == 1 ? d.metal : d.var + (size_t)(tb - 2) * t.nrows * nb);
+    for (int r = 0; r < t.nrows; ++r) {
+      const double* p = tab + (size_t)r * nb;
+      double* a = pn.data() + ((size_t)tb * t.nrows + r) * (nb + 1);
+      double* b = pe.data() + ((size_t)tb * t.nrows + r) * (nb + 1);
+      long double sa = 0.0L, sb = 0.0L;
+      a[0] = 0.0;
+      b[0] = 0.0;
+      for (size_t j = 0; j < nb; ++j) {
+        sa += p[j];
+        sb += (long double)emid[j] * p[j];
+        a[j + 1] = (double)sa;
+        b[j + 1] = (double)sb;
+      }
+    }
+  }
+  int rc;
+  if ((rc = upload(m, pn.data(), pn.size() * sizeof(double), (const void**)&t.pre_n))) return rc;
+  return upload(m, pe.data(), pe.size() * sizeof(double), (const void**)&t.pre_e);
+}
+
 extern "C" int pxb_model_destroy(pxb_model* m) {
   if (!m) return PXB_OK;
   for (int i = 0; i < m->nalloc; ++i) cudaFree(m->allocs[i]);
@@ -160,6 +188,8 @@ extern "C" int pxb_model_create(const pxb_model_desc* desc, pxb_model** out) {
     if (!rc) rc = upload(m, desc->ebins ? desc->ebins : desc->bin_edges, (D.nbins + 1) * sizeof(double),
                          (const void**)&D.ebins);
     D.fast_ok = D.prim.rowcdf != nullptr && (!D.has_fb || D.fb.rowcdf != nullptr);
+    if (!rc) rc = build_prefix(m, desc->primary, D.prim, desc->emid);
+    if (!rc && D.has_fb) rc = build_prefix(m, desc->fallback, D.fb, desc->emid);
     {
       const double* eb = desc->bin_edges;
       const int nb = D.nbins;

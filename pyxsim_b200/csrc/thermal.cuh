@@ -28,6 +28,10 @@ struct DevTable {
   const double* rowcdf;    // row stride cdf_stride doubles (even: rows are 16-byte aligned for TMA)
   const uint16_t* guide;   // row stride guide_stride entries (multiple of 8)
   int cdf_stride, guide_stride;
+  // band sums in O(1) (only when nonneg): unnormalised prefix sums over the bins of every row,
+  // pre_n[tab][row][j] = sum_{q<j} T[q], pre_e[...] = sum_{q<j} emid_q T[q]; [(2+nvar), nrows, nbins+1]
+  const double* pre_n;
+  const double* pre_e;
 };
 
 struct DevModel {

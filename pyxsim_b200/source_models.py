@@ -619,8 +619,12 @@ class ThermalSourceModel(SourceModel):
         dm = self.spectral_model.device_model(self.method)
         shift = self.compute_shift(chunk) if shifting else None
         out = empty(Cs.ncell)
+        need = C.c_int64()
+        _lib.call("pxb_thermal_band_workspace_bytes", Cs.ncell, C.byref(need))
+        ws = torch.empty(need.value, dtype=torch.uint8, device=out.device)
         _lib.call("pxb_thermal_band", dm.handle, C.byref(Cs), int(bool(energy)), C.c_double(emin),
-                  C.c_double(emax), ptr(shift), ptr(out), stream_ptr())
+                  C.c_double(emax), ptr(shift), ptr(out), ptr(ws), need.value, stream_ptr())
+        del ws
         return out
 
     def generate_chunk(self, chunk, spectral_norm, gather=None):

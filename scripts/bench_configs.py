@@ -191,6 +191,23 @@ def main():
             ncell = n ** 3
             print(json.dumps({"config": f"make_spectrum thermal {n}^3 cells, 4000 -> 2000 bins, shifting={shifting}",
                               "cells": ncell, "ms": round(ms, 2), "cells_per_s": ncell / (ms * 1e-3)}), flush=True)
+        # Doppler-shifted band per cell (make_band, the integrand of make_intensity_fields)
+        model._spec_normal = np.array([0.3, -0.5, 0.8])
+        model.v_fields = src.velocity_fields
+        chunk = next(src.chunks())
+        for label, env in (("O(1) prefix sums", None), ("per-cell sum", "1")):
+            if env:
+                os.environ["PXB_BAND_PER_CELL"] = env
+            model.band_per_cell(chunk, 1.0, 0.5, 2.0, energy=True, shifting=True)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(3):
+                model.band_per_cell(chunk, 1.0, 0.5, 2.0, energy=True, shifting=True)
+            torch.cuda.synchronize()
+            ms = (time.perf_counter() - t0) / 3 * 1e3
+            os.environ.pop("PXB_BAND_PER_CELL", None)
+            print(json.dumps({"config": f"shifted intensity band per cell, {label}", "cells": n ** 3,
+                              "ms": round(ms, 3), "cells_per_s": n ** 3 / (ms * 1e-3)}), flush=True)
         # CPU reference on a sample: compiled reference shift_spectrum + interp1d_spec via the oracle
         try:
             from oracle import ref_glue as O

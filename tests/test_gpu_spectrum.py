@@ -283,3 +283,32 @@ def test_unshifted_spectrum_by_linearity_equals_per_cell_path(cuda, oracle, monk
     np.testing.assert_allclose(lin, ref, rtol=1e-11, atol=ref.max() * 1e-14)
     inside = (kT >= t["Tvals"][0]) & (kT <= t["Tvals"][-1])
     assert 500 < inside.sum() < 4500          # both routes carried a real share of the cells
+    # the same split for make_band: O(1) prefix-sum differences for the clip-free cells, the
+    # warp-per-cell sum for the others; shifted and unshifted, photon and energy bands
+    model.v_fields = src.velocity_fields
+    model._spec_normal = np.array([0.3, -0.5, 0.8])
+    v = np.stack([src.fields[f] for f in src.velocity_fields]) / 299792.458
+    nh = model._spec_normal / np.linalg.norm(model._spec_normal)
+    shift = np.sqrt(1.0 - (v ** 2).sum(0)) / (1.0 - nh @ v)
+    emid = 0.5 * (t["ebins"][1:] + t["ebins"][:-1])
+    cut, tot, lam = oracle.thermal_spectra(om, cfg, dict(kT=kT, em=em, Z=extra[("gas", "Z")]))
+    cnm = em[cut] * 3e-44
+    mb = oracle.ref()["spectra"].make_band
+    for use_energy in (0, 1):
+        for shifting in (False, True):
+            for band in ((0.5, 7.0), (1.0, 1.2), (0.05, 20.0), (3.0, 3.001)):
+                fast = model.band_per_cell(chunk, 3e-44, band[0], band[1], energy=bool(use_energy),
+                                           shifting=shifting).cpu().numpy()
+                monkeypatch.setenv("PXB_BAND_PER_CELL", "1")
+                slow = model.band_per_cell(chunk, 3e-44, band[0], band[1], energy=bool(use_energy),
+                                           shifting=shifting).cpu().numpy()
+                monkeypatch.delenv("PXB_BAND_PER_CELL")
+                sh = shift[cut] if shifting else np.ones(cut.sum())
+                refb = mb(use_energy, band[0], band[1], t["ebins"], emid, np.ascontiguousarray(tot),
+                          np.ascontiguousarray(sh)) * cnm
+                scale = np.abs(refb).max() + 1e-300
+                np.testing.assert_allclose(slow[cut], refb, rtol=1e-12, atol=scale * 1e-15)
+                # prefix differences cancel: absolute accuracy is that of the row totals
+                np.testing.assert_allclose(fast[cut], refb, rtol=1e-10, atol=scale * 1e-13)
+                assert np.array_equal(fast[~cut], np.zeros((~cut).sum()))
+                assert np.array_equal(fast == 0.0, slow == 0.0) or band == (3.0, 3.001)
