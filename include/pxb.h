@@ -26,6 +26,14 @@
  *   pxb_pixel_to_cel ............ pixel_to_cel, sky_functions.pyx:153-179
  *   pxb_absorb_transmission ..... AbsorptionModel.get_absorb, spectral_models.py:556-561
  *                                 (+ soxs get_wabs_absorb used by WabsModel :633-635)
+ *   pxb_thermal_spectrum ........ process_data("spectrum") + shift_spectrum,
+ *                                 base.py:453-460,494-495; pyxsim/lib/spectra.pyx:67-93
+ *   pxb_thermal_band ............ process_data("*intensity") + make_band, base.py:497-500;
+ *                                 spectra.pyx:96-126
+ *   pxb_powerlaw_spectrum, pxb_powerlaw_norm ... power_law_spectrum, spectra.pyx:11-32;
+ *                                 power_law_sources.py:198-206
+ *   pxb_line_spectrum ........... line_spectrum, spectra.pyx:35-64
+ *   pxb_shift_factor ............ SourceModel.compute_shift, source_models/sources.py:89-95
  *   pxb_thermal_flux ............ make_fluxf + the "luminosity"/"photon_rate" branch of
  *                                 process_data, spectral_models.py:101-134,464-537; base.py:501-511
  *   pxb_absorb_decide ........... AbsorptionModel.absorb_photons, spectral_models.py:563-583
