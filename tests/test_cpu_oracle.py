@@ -222,3 +222,59 @@ def test_reference_golden_is_reproducible_from_the_reference_tree():
     assert sorted(fresh) == sorted(stored.files)
     for k in stored.files:
         assert np.array_equal(np.asarray(fresh[k]), stored[k]), k
+
+
+def test_list_files_interoperate_with_the_reference(oracle, monkeypatch):
+    """The HDF5 branch of save_list/load_list (h5py is absent here, so it is driven through the
+    in-memory h5py stand-in of oracle/ref_import.py) writes a photon list the reference's own
+    _project_photons reads, and reads back the event list the reference writes: same /info,
+    /parameters, /data layout (photon_list.py:345-399,605-646).  The reference's events equal the
+    oracle's for the same RandomState."""
+    if not os.path.isdir("/root/reference/pyxsim"):
+        pytest.skip("reference tree not available")
+    import types
+
+    from oracle import ref_import as R
+    from pyxsim_b200 import photon_list as PL
+
+    M = R.modules()
+    monkeypatch.setattr(PL, "h5py", types.SimpleNamespace(File=R.FakeH5File))
+    real_exists = os.path.exists
+    monkeypatch.setattr(PL.os.path, "exists", lambda p: p in R.FILES or real_exists(p))
+
+    rng = np.random.RandomState(77)
+    nc = 300
+    nph = rng.poisson(15.0 * rng.lognormal(0, 1.0, nc)).astype(np.int64)
+    d = dict(x=rng.uniform(-300, 300, nc), y=rng.uniform(-300, 300, nc), z=rng.uniform(-300, 300, nc),
+             vx=rng.normal(0, 500, nc), vy=rng.normal(0, 500, nc), vz=rng.normal(100, 500, nc),
+             dx=rng.uniform(2.0, 30.0, nc), num_photons=nph,
+             energy=np.exp(rng.uniform(np.log(0.1), np.log(10.0), int(nph.sum()))))
+    params = dict(fid_exp_time=1.0e5, fid_area=1000.0, fid_redshift=0.05, fid_d_a=200.0, hubble=0.71,
+                  omega_matter=0.27, omega_lambda=0.73, data_type="cells", observer="external",
+                  center=np.zeros(3), bulk_velocity=np.zeros(3),
+                  velocity_fields=np.array(["('gas', 'velocity_x')", "('gas', 'velocity_y')", "('gas', 'velocity_z')"]))
+    info = dict(pyxsim_version="0.1.0", yt_version="n/a", soxs_version="n/a", dataset="test", data_source="all",
+                source_model="test", filenames=["interop_ph.h5"])
+    fn = PL.save_list("interop_ph", PL.DeviceList(info, params, d))
+    assert fn == "interop_ph.h5" and fn in R.FILES
+    back = PL.load_list("interop_ph")
+    assert back.parameters["data_type"] == "cells" and np.array_equal(back.numpy("energy"), d["energy"])
+
+    # the reference projects OUR photon list ...
+    n_ev = M["photon_list"]._project_photons("external", "interop_ph", "interop_ev", [0.3, -0.4, 0.85],
+                                             [30.0, 45.0], prng=np.random.RandomState(5), save_los=True)
+    # ... and we read ITS event list
+    ev = PL.load_list("interop_ev")
+    assert ev.numpy("eobs").size == n_ev == d["energy"].size
+    assert str(ev.parameters["absoption_model"]) == "none" and str(ev.parameters["observer"]) == "external"
+    ref = oracle.project_photons({k: v.copy() for k, v in d.items()},
+                                 dict(data_type="cells", observer="external", fid_d_a=200.0, fid_redshift=0.05),
+                                 [0.3, -0.4, 0.85], [30.0, 45.0], np.random.RandomState(5), save_los=True)
+    for k in ("xsky", "ysky", "eobs", "los"):
+        assert np.array_equal(ev.numpy(k), ref[k]), k
+    # EventList / merge_files work on files the reference wrote
+    from pyxsim_b200 import event_list as E
+
+    monkeypatch.setattr(E, "load_list", PL.load_list)
+    lst = PL.load_list("interop_ev")
+    assert float(lst.parameters["exp_time"]) == 1.0e5 and np.allclose(lst.parameters["sky_center"], [30.0, 45.0])
