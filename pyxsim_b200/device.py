@@ -5,11 +5,18 @@ import numpy as np
 import torch
 
 
+_cuda_ok = False
+
+
 def require_cuda():
+    global _cuda_ok
+    if _cuda_ok:                      # (a positive answer cannot change within a process)
+        return
     if not torch.cuda.is_available():
         raise RuntimeError(
             "pyxsim_b200 needs a CUDA device (sm_100a): there is no CPU fallback for the hot path"
         )
+    _cuda_ok = True
 
 
 def current_device():
