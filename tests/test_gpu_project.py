@@ -385,6 +385,47 @@ def test_photon_list_with_empty_cells_and_errors(cuda):
         px.project_photons("mem:z2_ph", "mem:z_ev", "z", [0.0, 0.0], sigma_pos=1.0)
 
 
+@pytest.mark.parametrize("mode", ["twopass", "fused"])
+def test_tiles_spanning_hundreds_of_empty_cells(cuda, oracle, mode, monkeypatch):
+    """A photon list whose cells are mostly empty (long runs of zero-photon cells between the
+    active ones): warp tiles then span more than 256 / 257 cells, which takes the unpacked-cell
+    and the global-search branches of the detect and emit passes.  Doppler-only projection is
+    deterministic: every event must carry exactly its own cell's shift and line-of-sight."""
+    if mode == "fused":
+        monkeypatch.setenv("PXB_PROJECT_MODE", "fused")
+    rng = np.random.RandomState(17)
+    n_cells = 60000
+    nph = np.zeros(n_cells, dtype=np.int64)
+    active = np.sort(rng.choice(n_cells, 900, replace=False))
+    nph[active] = rng.randint(1, 6, active.size)           # few photons per active cell
+    nph[30000:31000] = 0                                    # a run of 1000 empty cells
+    nph[31000] = 700                                        # then a bright one
+    nph[active[:5]] = [300, 1, 257, 256, 2]
+    d = dict(x=rng.uniform(-300, 300, n_cells), y=rng.uniform(-300, 300, n_cells),
+             z=rng.uniform(-300, 300, n_cells), vx=rng.normal(0, 500, n_cells),
+             vy=rng.normal(0, 500, n_cells), vz=rng.normal(100, 500, n_cells),
+             dx=rng.uniform(2.0, 30.0, n_cells), num_photons=nph,
+             energy=np.exp(rng.uniform(np.log(0.1), np.log(10.0), int(nph.sum()))))
+    params = dict(fid_exp_time=1.0e5, fid_area=1000.0, fid_redshift=0.05, fid_d_a=200.0,
+                  data_type="cells", observer="external")
+    put("sparse_ph", d, params)
+    normal = [0.3, -0.5, 0.8]
+    n = px.project_photons("mem:sparse_ph", "mem:sparse_ev", normal, [30.0, 45.0], save_los=True, prng=3)
+    ev, _ = events("sparse_ev")
+    assert n == d["energy"].size
+    ref = oracle.project_photons({k: v.copy() for k, v in d.items()}, params, normal, [30.0, 45.0],
+                                 np.random.RandomState(4), save_los=True)
+    np.testing.assert_allclose(ev["eobs"], ref["eobs"], rtol=4e-16, atol=0)      # per-cell Doppler factor
+    np.testing.assert_allclose(ev["los"], ref["los"], rtol=1e-12, atol=1e-11)    # per-cell line of sight
+    # with absorption the survivors still carry their own cell's data
+    n2 = px.project_photons("mem:sparse_ph", "mem:sparse_ev", normal, [30.0, 45.0], absorb_model="wabs",
+                            nH=0.3, save_los=True, prng=3)
+    ev2, _ = events("sparse_ev")
+    assert 0 < n2 < n
+    pairs = {(e, l) for e, l in zip(np.round(ref["eobs"], 12), np.round(ref["los"], 7))}
+    assert all((e, l) in pairs for e, l in zip(np.round(ev2["eobs"], 12), np.round(ev2["los"], 7)))
+
+
 # ---------------------------------------------------------------------------------------
 # power law / line
 # ---------------------------------------------------------------------------------------
