@@ -84,6 +84,40 @@ __device__ __forceinline__ Philox4 philox4x32_10(uint32_t c0, uint32_t c1, uint3
   return Philox4{c0, c1, c2, c3};
 }
 
+// The ten round keys of a call depend on the seed only.  Kernels that draw per photon receive
+// them precomputed as a __grid_constant__ parameter: the round XORs then take their key straight
+// from the constant bank and the twenty key-schedule additions per call disappear.  Same
+// numbers as philox4x32_10 above.
+struct PhiloxKeys {
+  uint32_t k[20];   // k[2r] = seed_lo + r*W0, k[2r+1] = seed_hi + r*W1
+};
+static inline PhiloxKeys pxb_make_keys(uint64_t seed) {
+  PhiloxKeys K;
+  uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+  for (int r = 0; r < 10; ++r) {
+    K.k[2 * r] = k0;
+    K.k[2 * r + 1] = k1;
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+  return K;
+}
+__device__ __forceinline__ Philox4 pxb_rand4(const PhiloxKeys& K, uint32_t stream, uint64_t cell,
+                                             uint64_t draw) {
+  const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u;
+  uint32_t c0 = (uint32_t)draw, c1 = (uint32_t)(draw >> 32), c2 = (uint32_t)cell,
+           c3 = (((uint32_t)(cell >> 32)) << 16) | (stream & 0xFFFFu);
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(M0, c0), lo0 = M0 * c0;
+    const uint32_t hi1 = __umulhi(M1, c2), lo1 = M1 * c2;
+    const uint32_t n0 = hi1 ^ c1 ^ K.k[2 * r];
+    const uint32_t n2 = hi0 ^ c3 ^ K.k[2 * r + 1];
+    c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+  }
+  return Philox4{c0, c1, c2, c3};
+}
+
 __device__ __forceinline__ Philox4 pxb_rand4(uint64_t seed, uint32_t stream, uint64_t cell,
                                              uint64_t draw) {
   return philox4x32_10((uint32_t)draw, (uint32_t)(draw >> 32), (uint32_t)cell,

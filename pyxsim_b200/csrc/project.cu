@@ -411,13 +411,13 @@ __device__ __forceinline__ double u32_centered(uint32_t w) {
 }
 
 // scatter + sky transform of one surviving photon (external observer)
-__device__ __forceinline__ void scatter_external(const pxb_project_params& P, const CellGeom& g,
-                                                 const SkyConst& K, uint64_t cell_key,
+__device__ __forceinline__ void scatter_external(const pxb_project_params& P, const PhiloxKeys& RK,
+                                                 const CellGeom& g, const SkyConst& K, uint64_t cell_key,
                                                  uint64_t draw, double& xs_out, double& ys_out,
                                                  double& los_out) {
   const double w = g.w, cx = g.cx, cy = g.cy;
   los_out = g.cz;  // from the unscattered centre (sky_functions.pyx:124,143)
-  const Philox4 rb = pxb_rand4(P.seed, STREAM_PROJ_B, cell_key, draw);
+  const Philox4 rb = pxb_rand4(RK, STREAM_PROJ_B, cell_key, draw);
   double ox, oy;  // offsets in the sky plane in units of w
   if (P.data_type == 0) {
     // cells: uniform inside the cube, rotated into the sky plane (sky_functions.pyx:74-76,
@@ -444,7 +444,7 @@ __device__ __forceinline__ void scatter_external(const pxb_project_params& P, co
   double xs = cx + ox * w, ys = cy + oy * w;
   if (P.has_sigma_pos && P.data_type == 0) {
     // photon_list.py:753-756: sigma = sigma_pos * dx
-    const Philox4 rc = pxb_rand4(P.seed, STREAM_PROJ_C, cell_key, draw);
+    const Philox4 rc = pxb_rand4(RK, STREAM_PROJ_C, cell_key, draw);
     double n0, n1;
     normal2(rc, n0, n1);
     const double sg = P.sigma_pos * w;
@@ -469,23 +469,23 @@ __device__ __forceinline__ void scatter_external(const pxb_project_params& P, co
 }
 
 // internal observer: sky_functions.pyx:205-248
-__device__ __forceinline__ void scatter_allsky(const pxb_project_params& P, const CellGeom& g,
-                                               uint64_t cell_key, uint64_t draw,
+__device__ __forceinline__ void scatter_allsky(const pxb_project_params& P, const PhiloxKeys& RK,
+                                               const CellGeom& g, uint64_t cell_key, uint64_t draw,
                                                double& lon_out, double& lat_out, double& los_out) {
   const double w = g.w, cx = g.cx, cy = g.cy, cz = g.cz;
   double o0, o1, o2;
-  const Philox4 rb = pxb_rand4(P.seed, STREAM_PROJ_B, cell_key, draw);
+  const Philox4 rb = pxb_rand4(RK, STREAM_PROJ_B, cell_key, draw);
   if (P.data_type == 0) {
     o0 = u32_centered(rb.x);
     o1 = u32_centered(rb.y);
     o2 = u32_centered(rb.z);
   } else if (P.kernel == 1) {
-    const Philox4 rc = pxb_rand4(P.seed, STREAM_PROJ_C, cell_key, draw);
+    const Philox4 rc = pxb_rand4(RK, STREAM_PROJ_C, cell_key, draw);
     double dump;
     normal2(rb, o0, o1);
     normal2(rc, o2, dump);
   } else {
-    const Philox4 rc = pxb_rand4(P.seed, STREAM_PROJ_C, cell_key, draw);
+    const Philox4 rc = pxb_rand4(RK, STREAM_PROJ_C, cell_key, draw);
     const double r = u53(rc.x, rc.y);
     double sp, cp;
     sincospi(2.0 * u53(rb.x, rb.y), &sp, &cp);
@@ -518,17 +518,17 @@ __device__ __forceinline__ bool absorb_one(const pxb_project_params& P, const Wa
   return survives(u, table_tau_per_nh(P, e) * nH);
 }
 
-__device__ __forceinline__ bool absorb_decision(const pxb_project_params& P, const WabsFast& F,
-                                                int64_t c, int64_t draw, double en) {
+__device__ __forceinline__ bool absorb_decision(const pxb_project_params& P, const PhiloxKeys& RK,
+                                                const WabsFast& F, int64_t c, int64_t draw, double en) {
   const uint64_t cell_key = (uint64_t)(P.cell_id0 + c);
   bool det = true;
   if (P.nH_cell) {
     // internal absorption on the source-frame energy, photon_list.py:715-723
-    const Philox4 rd = pxb_rand4(P.seed, STREAM_PROJ_D, cell_key, (uint64_t)draw);
+    const Philox4 rd = pxb_rand4(RK, STREAM_PROJ_D, cell_key, (uint64_t)draw);
     det = absorb_one(P, F, u53(rd.x, rd.y), en * P.oneplusz, __ldg(P.nH_cell + c));
   }
   if (det && P.nH > 0.0) {
-    const Philox4 ra = pxb_rand4(P.seed, STREAM_PROJ_A, cell_key, (uint64_t)draw);
+    const Philox4 ra = pxb_rand4(RK, STREAM_PROJ_A, cell_key, (uint64_t)draw);
     det = absorb_one(P, F, u53(ra.x, ra.y), en, P.nH);
   }
   return det;
@@ -537,7 +537,7 @@ __device__ __forceinline__ bool absorb_decision(const pxb_project_params& P, con
 template <int OBS>
 __global__ void __launch_bounds__(PROJ_THREADS, 4)
 k_project_photons(const __grid_constant__ pxb_photon_list L,
-                  const __grid_constant__ pxb_project_params P, const CellDerived D,
+                  const __grid_constant__ pxb_project_params P, const __grid_constant__ PhiloxKeys RK, const CellDerived D,
                   const ProjWork W, double* __restrict__ xsky, double* __restrict__ ysky,
                   double* __restrict__ eobs_out, double* __restrict__ los_out,
                   int64_t* __restrict__ n_events_out, int64_t n_wtiles, int64_t n_ctiles,
@@ -621,7 +621,7 @@ k_project_photons(const __grid_constant__ pxb_photon_list L,
         }
         const int64_t c = c0 + rel;
         const double en = s_e[it] * __ldg(D.shift + c);
-        det = absorb ? absorb_decision(P, s_wabs, c, p - first, en) : true;
+        det = absorb ? absorb_decision(P, RK, s_wabs, c, p - first, en) : true;
         s_e[it] = en;
         s_rel[it] = rel;
         if (det) {
@@ -660,8 +660,8 @@ k_project_photons(const __grid_constant__ pxb_photon_list L,
       const uint64_t draw = (uint64_t)(p0 + it - first);
       double xs, ys, los;
       const CellGeom g = ld_geom(D.geom + c);
-      if (OBS == 0) scatter_external(P, g, K, cell_key, draw, xs, ys, los);
-      else scatter_allsky(P, g, cell_key, draw, xs, ys, los);
+      if (OBS == 0) scatter_external(P, RK, g, K, cell_key, draw, xs, ys, los);
+      else scatter_allsky(P, RK, g, cell_key, draw, xs, ys, los);
       const int64_t o = base + sl;
       st_stream(xsky + o, xs);
       st_stream(ysky + o, ys);
@@ -684,7 +684,7 @@ k_project_photons(const __grid_constant__ pxb_photon_list L,
 // photons.
 __global__ void __launch_bounds__(PROJ_THREADS, 4)
 k_project_detect(const __grid_constant__ pxb_photon_list L,
-                 const __grid_constant__ pxb_project_params P, const CellDerived D,
+                 const __grid_constant__ pxb_project_params P, const __grid_constant__ PhiloxKeys RK, const CellDerived D,
                  const ProjWork W, uint16_t* __restrict__ slots, int64_t* __restrict__ counts,
                  int64_t n_wtiles) {
   __shared__ int64_t s_off_all[PROJ_WARPS][PROJ_WTILE + 2];
@@ -750,7 +750,7 @@ k_project_detect(const __grid_constant__ pxb_photon_list L,
       }
       const int64_t c = c0 + rel;
       const double en = s_e[r * 32 + lane] * (staged ? s_shift[rel] : __ldg(D.shift + c));
-      det = absorb ? absorb_decision(P, s_wabs, c, p - first, en) : true;
+      det = absorb ? absorb_decision(P, RK, s_wabs, c, p - first, en) : true;
       if (det) {
         tsum += en;
         tmin = en < tmin ? en : tmin;   // (energies are never NaN: plain compares, no fmin/fmax)
@@ -778,7 +778,7 @@ k_project_detect(const __grid_constant__ pxb_photon_list L,
 template <int OBS>
 __global__ void __launch_bounds__(PROJ_THREADS, 4)
 k_project_emit(const __grid_constant__ pxb_photon_list L,
-               const __grid_constant__ pxb_project_params P, const CellDerived D,
+               const __grid_constant__ pxb_project_params P, const __grid_constant__ PhiloxKeys RK, const CellDerived D,
                const uint16_t* __restrict__ slots, const int64_t* __restrict__ offsets,
                double* __restrict__ xsky, double* __restrict__ ysky,
                double* __restrict__ eobs_out, double* __restrict__ los_out,
@@ -863,8 +863,8 @@ k_project_emit(const __grid_constant__ pxb_photon_list L,
     const uint64_t cell_key = (uint64_t)(P.cell_id0 + c);
     const uint64_t draw = (uint64_t)(p - first);
     double xs, ys, los;
-    if (OBS == 0) scatter_external(P, g, K, cell_key, draw, xs, ys, los);
-    else scatter_allsky(P, g, cell_key, draw, xs, ys, los);
+    if (OBS == 0) scatter_external(P, RK, g, K, cell_key, draw, xs, ys, los);
+    else scatter_allsky(P, RK, g, cell_key, draw, xs, ys, los);
     const int64_t o = base + sl;
     st_stream(xsky + o, xs);
     st_stream(ysky + o, ys);
@@ -1002,6 +1002,7 @@ extern "C" int pxb_project(const pxb_photon_list* L, const pxb_project_params* P
   // the single-pass kernel (DRAM traffic == algorithmic bytes, decoupled look-back), which
   // produces the identical event list; on B200 it is ~10 % slower while the path is ALU-bound.
   const SkyConst K = make_sky_const(P);
+  const PhiloxKeys RK = pxb_make_keys(P->seed);
   const char* mode = getenv("PXB_PROJECT_MODE");
   const bool fused = mode && strcmp(mode, "fused") == 0;
   if (!fused) {
@@ -1011,16 +1012,16 @@ extern "C" int pxb_project(const pxb_photon_list* L, const pxb_project_params* P
     int64_t* arank = (int64_t*)(ws + lay.off_arank);
     int64_t* totals = (int64_t*)(ws + lay.off_totals);
     const unsigned g = (unsigned)n_ctiles;
-    k_project_detect<<<g, PROJ_THREADS, 0, st>>>(*L, *P, D, W, masks, counts, lay.ntiles);
+    k_project_detect<<<g, PROJ_THREADS, 0, st>>>(*L, *P, RK, D, W, masks, counts, lay.ntiles);
     PXB_LAUNCH_CHECK();
     rc = pxb_scan_counts(counts, lay.ntiles, offsets, arank, totals, ws + lay.off_scanws,
                          lay.scanws_bytes, stream);
     if (rc) return rc;
     if (P->observer == 0) {
-      k_project_emit<0><<<g, PROJ_THREADS, 0, st>>>(*L, *P, D, masks, offsets, xsky, ysky, eobs,
+      k_project_emit<0><<<g, PROJ_THREADS, 0, st>>>(*L, *P, RK, D, masks, offsets, xsky, ysky, eobs,
                                                    P->save_los ? los : nullptr, n_events_out, lay.ntiles, K);
     } else {
-      k_project_emit<1><<<g, PROJ_THREADS, 0, st>>>(*L, *P, D, masks, offsets, xsky, ysky, eobs,
+      k_project_emit<1><<<g, PROJ_THREADS, 0, st>>>(*L, *P, RK, D, masks, offsets, xsky, ysky, eobs,
                                                    P->save_los ? los : nullptr, n_events_out, lay.ntiles, K);
     }
     PXB_LAUNCH_CHECK();
@@ -1036,10 +1037,10 @@ extern "C" int pxb_project(const pxb_photon_list* L, const pxb_project_params* P
   if (grid > n_ctiles) grid = n_ctiles;
   if (P->observer == 0) {
     k_project_photons<0><<<(unsigned)grid, PROJ_THREADS, 0, st>>>(
-        *L, *P, D, W, xsky, ysky, eobs, P->save_los ? los : nullptr, n_events_out, lay.ntiles, n_ctiles, K);
+        *L, *P, RK, D, W, xsky, ysky, eobs, P->save_los ? los : nullptr, n_events_out, lay.ntiles, n_ctiles, K);
   } else {
     k_project_photons<1><<<(unsigned)grid, PROJ_THREADS, 0, st>>>(
-        *L, *P, D, W, xsky, ysky, eobs, P->save_los ? los : nullptr, n_events_out, lay.ntiles, n_ctiles, K);
+        *L, *P, RK, D, W, xsky, ysky, eobs, P->save_los ? los : nullptr, n_events_out, lay.ntiles, n_ctiles, K);
   }
   PXB_LAUNCH_CHECK();
   }

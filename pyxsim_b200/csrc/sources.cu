@@ -60,7 +60,8 @@ k_powerlaw_counts(const __grid_constant__ pxb_powerlaw_cells C, double* __restri
 constexpr int SRC_TILE = 1024;
 
 __global__ void __launch_bounds__(256)
-k_powerlaw_sample(const __grid_constant__ pxb_powerlaw_cells C, int64_t n_active,
+k_powerlaw_sample(const __grid_constant__ pxb_powerlaw_cells C,
+                  const __grid_constant__ PhiloxKeys RK, int64_t n_active,
                   const int64_t* __restrict__ idx, const int64_t* __restrict__ poff,
                   int64_t n_photons, double* __restrict__ energies) {
   __shared__ int64_t s_off[SRC_TILE + 1];
@@ -89,7 +90,7 @@ k_powerlaw_sample(const __grid_constant__ pxb_powerlaw_cells C, int64_t n_active
     const uint64_t gid = (uint64_t)(C.cell_id0 + idx[c]);
     const uint64_t draw = (uint64_t)(p - __ldg(poff + c));
     // photons 2m and 2m+1 of a cell use the two halves of one Philox block
-    const Philox4 r = pxb_rand4(C.seed, STREAM_POWERLAW, gid, draw >> 1);
+    const Philox4 r = pxb_rand4(RK, STREAM_POWERLAW, gid, draw >> 1);
     const double u = (draw & 1) ? u53(r.z, r.w) : u53(r.x, r.y);
     // x**y as exp(y log x): both bases are positive and |y log x| stays of order one (it is the
     // log of an energy ratio), so this is within a few ulp of pow() at a third of its cost
@@ -121,7 +122,8 @@ extern "C" int pxb_powerlaw_sample(const pxb_powerlaw_cells* cells, int64_t n_ac
   PXB_REQUIRE(idx && poff && energies, "NULL argument");
   const int64_t ntiles = (n_photons + SRC_TILE - 1) / SRC_TILE;
   PXB_REQUIRE(ntiles < (1LL << 31), "too many photons for one call");
-  k_powerlaw_sample<<<(unsigned)ntiles, 256, 0, (cudaStream_t)stream>>>(*cells, n_active, idx, poff,
+  k_powerlaw_sample<<<(unsigned)ntiles, 256, 0, (cudaStream_t)stream>>>(*cells, pxb_make_keys(cells->seed),
+                                                                       n_active, idx, poff,
                                                                        n_photons, energies);
   PXB_LAUNCH_CHECK();
   return PXB_OK;
@@ -143,7 +145,8 @@ k_line_counts(const __grid_constant__ pxb_line_cells C, double* __restrict__ lam
 }
 
 __global__ void __launch_bounds__(256)
-k_line_sample(const __grid_constant__ pxb_line_cells C, int64_t n_active,
+k_line_sample(const __grid_constant__ pxb_line_cells C, const __grid_constant__ PhiloxKeys RK,
+              int64_t n_active,
               const int64_t* __restrict__ idx, const int64_t* __restrict__ poff,
               int64_t n_photons, double* __restrict__ energies) {
   __shared__ int64_t s_off[SRC_TILE + 1];
@@ -158,7 +161,7 @@ k_line_sample(const __grid_constant__ pxb_line_cells C, int64_t n_active,
     const double sigma = C.sigma ? __ldg(C.sigma + i) : C.sigma_const;
     const uint64_t draw = (uint64_t)(p - __ldg(poff + c));
     // one Philox block -> two normals: photon pairs (2m, 2m+1) share block m
-    const Philox4 r = pxb_rand4(C.seed, STREAM_LINE, (uint64_t)(C.cell_id0 + i), draw >> 1);
+    const Philox4 r = pxb_rand4(RK, STREAM_LINE, (uint64_t)(C.cell_id0 + i), draw >> 1);
     double n0, n1;
     normal2(r, n0, n1);
     const double g = (draw & 1) ? n1 : n0;
@@ -187,7 +190,8 @@ extern "C" int pxb_line_sample(const pxb_line_cells* cells, int64_t n_active, co
   PXB_REQUIRE(idx && poff && energies, "NULL argument");
   const int64_t ntiles = (n_photons + SRC_TILE - 1) / SRC_TILE;
   PXB_REQUIRE(ntiles < (1LL << 31), "too many photons for one call");
-  k_line_sample<<<(unsigned)ntiles, 256, 0, (cudaStream_t)stream>>>(*cells, n_active, idx, poff,
+  k_line_sample<<<(unsigned)ntiles, 256, 0, (cudaStream_t)stream>>>(*cells, pxb_make_keys(cells->seed),
+                                                                   n_active, idx, poff,
                                                                    n_photons, energies);
   PXB_LAUNCH_CHECK();
   return PXB_OK;

@@ -882,7 +882,7 @@ k_thermal_cellsplit(const DevModel M, const __grid_constant__ pxb_thermal_cells 
 
 __global__ void __launch_bounds__(STG_THREADS, 1)
 k_thermal_sample_staged(const DevModel M, const __grid_constant__ pxb_thermal_cells C,
-                        int64_t n_active, const int64_t* __restrict__ idx,
+                        const __grid_constant__ PhiloxKeys RK, int64_t n_active, const int64_t* __restrict__ idx,
                         const int64_t* __restrict__ poff, int64_t n_photons,
                         double* __restrict__ energies, const FastCell* __restrict__ fcs,
                         const int64_t* __restrict__ tile_cell,
@@ -1006,7 +1006,7 @@ k_thermal_sample_staged(const DevModel M, const __grid_constant__ pxb_thermal_ce
           double e;
           if (fmeta & 32) {
             if (!(blk_cell == gid && blk_idx == (d >> 1))) {
-              blk = pxb_rand4(C.seed, STREAM_ENERGY, gid, d >> 1);
+              blk = pxb_rand4(RK, STREAM_ENERGY, gid, d >> 1);
               blk_cell = gid;
               blk_idx = d >> 1;
             }
@@ -1025,7 +1025,7 @@ k_thermal_sample_staged(const DevModel M, const __grid_constant__ pxb_thermal_ce
           } else if (fmeta & 64) {
             // general split: row from the cumulative row counts, table from the side array
             if (!(blk_cell == gid && blk_idx == (d >> 1))) {
-              blk = pxb_rand4(C.seed, STREAM_ENERGY, gid, d >> 1);
+              blk = pxb_rand4(RK, STREAM_ENERGY, gid, d >> 1);
               blk_cell = gid;
               blk_idx = d >> 1;
             }
@@ -1050,7 +1050,7 @@ k_thermal_sample_staged(const DevModel M, const __grid_constant__ pxb_thermal_ce
             const DevTable* tbl = prim ? &M.prim : &M.fb;
             e = invert_row(M, tbl, tab, fast_row(tbl, fz1, fmeta & 7, r), u2, S, prim);
           } else {
-            const Philox4 rn = pxb_rand4(C.seed, STREAM_ENERGY, gid, d);
+            const Philox4 rn = pxb_rand4(RK, STREAM_ENERGY, gid, d);
             const FastCell fc = fcs[kc];
             e = fast_draw(M, C, fc, i, u53(rn.x, rn.y), u53(rn.z, rn.w), S);
           }
@@ -1217,7 +1217,8 @@ extern "C" int pxb_thermal_sample(const pxb_model* model, const pxb_thermal_cell
     int64_t g2 = pxb_sm_count();
     if (g2 > nchunks) g2 = nchunks;
     k_thermal_sample_staged<<<(unsigned)g2, STG_THREADS, stg_smem, st>>>(
-        D, *cells, n_active, idx, poff, n_photons, energies, fcs, tile_cell, chunk_counter, use_staging,
+        D, *cells, pxb_make_keys(cells->seed), n_active, idx, poff, n_photons, energies, fcs, tile_cell,
+        chunk_counter, use_staging,
         tabcum, tab_stride);
     PXB_LAUNCH_CHECK();
   }
