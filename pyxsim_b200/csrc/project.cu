@@ -410,7 +410,11 @@ __device__ __forceinline__ double u32_centered(uint32_t w) {
   return (d + 0.5) * (1.0 / 4294967296.0) - 0.5;
 }
 
-// scatter + sky transform of one surviving photon (external observer)
+// scatter + sky transform of one surviving photon (external observer).  SPEC = 0 reads every
+// option from the parameter block; SPEC = 1 / 2 are the common case compiled with its options
+// fixed (cells, TAN sky, no sigma_pos; on-axis / off-axis normal), which removes the per-photon
+// constant loads and uniform branches on those options.
+template <int SPEC = 0>
 __device__ __forceinline__ void scatter_external(const pxb_project_params& P, const PhiloxKeys& RK,
                                                  const CellGeom& g, const SkyConst& K, uint64_t cell_key,
                                                  uint64_t draw, double& xs_out, double& ys_out,
@@ -419,11 +423,11 @@ __device__ __forceinline__ void scatter_external(const pxb_project_params& P, co
   los_out = g.cz;  // from the unscattered centre (sky_functions.pyx:124,143)
   const Philox4 rb = pxb_rand4(RK, STREAM_PROJ_B, cell_key, draw);
   double ox, oy;  // offsets in the sky plane in units of w
-  if (P.data_type == 0) {
+  if (SPEC != 0 || P.data_type == 0) {
     // cells: uniform inside the cube, rotated into the sky plane (sky_functions.pyx:74-76,
     // 110-121; on-axis x_hat/y_hat are axis vectors so only two of the draws contribute)
     const double u0 = u32_centered(rb.x), u1 = u32_centered(rb.y);
-    if (P.vn_axis >= 0) {   // on-axis: x_hat, y_hat are coordinate axes, two draws suffice
+    if (SPEC == 1 || (SPEC == 0 && P.vn_axis >= 0)) {   // on-axis: x_hat, y_hat are coordinate axes, two draws suffice
       ox = u0;
       oy = u1;
     } else {
@@ -442,7 +446,7 @@ __device__ __forceinline__ void scatter_external(const pxb_project_params& P, co
     oy = r * sn;
   }
   double xs = cx + ox * w, ys = cy + oy * w;
-  if (P.has_sigma_pos && P.data_type == 0) {
+  if (SPEC == 0 && P.has_sigma_pos && P.data_type == 0) {
     // photon_list.py:753-756: sigma = sigma_pos * dx
     const Philox4 rc = pxb_rand4(RK, STREAM_PROJ_C, cell_key, draw);
     double n0, n1;
@@ -451,10 +455,10 @@ __device__ __forceinline__ void scatter_external(const pxb_project_params& P, co
     xs += sg * n0;
     ys += sg * n1;
   }
-  if (P.sky_mode != PXB_SKY_PHYS) {
+  if (SPEC != 0 || P.sky_mode != PXB_SKY_PHYS) {
     xs *= K.inv_DA;
     ys *= K.inv_DA;
-    if (P.sky_mode == PXB_SKY_FLAT) {
+    if (SPEC == 0 && P.sky_mode == PXB_SKY_FLAT) {
       xs = P.sky_center[0] - xs * PXB_RAD2DEG;   // photon_list.py:762-764
       ys = P.sky_center[1] + ys * PXB_RAD2DEG;
     } else {
@@ -775,7 +779,7 @@ k_project_detect(const __grid_constant__ pxb_photon_list L,
   }
 }
 
-template <int OBS>
+template <int OBS, int SPEC>
 __global__ void __launch_bounds__(PROJ_THREADS, 4)
 k_project_emit(const __grid_constant__ pxb_photon_list L,
                const __grid_constant__ pxb_project_params P, const __grid_constant__ PhiloxKeys RK, const CellDerived D,
@@ -863,7 +867,7 @@ k_project_emit(const __grid_constant__ pxb_photon_list L,
     const uint64_t cell_key = (uint64_t)(P.cell_id0 + c);
     const uint64_t draw = (uint64_t)(p - first);
     double xs, ys, los;
-    if (OBS == 0) scatter_external(P, RK, g, K, cell_key, draw, xs, ys, los);
+    if (OBS == 0) scatter_external<SPEC>(P, RK, g, K, cell_key, draw, xs, ys, los);
     else scatter_allsky(P, RK, g, cell_key, draw, xs, ys, los);
     const int64_t o = base + sl;
     st_stream(xsky + o, xs);
@@ -1017,13 +1021,18 @@ extern "C" int pxb_project(const pxb_photon_list* L, const pxb_project_params* P
     rc = pxb_scan_counts(counts, lay.ntiles, offsets, arank, totals, ws + lay.off_scanws,
                          lay.scanws_bytes, stream);
     if (rc) return rc;
-    if (P->observer == 0) {
-      k_project_emit<0><<<g, PROJ_THREADS, 0, st>>>(*L, *P, RK, D, masks, offsets, xsky, ysky, eobs,
-                                                   P->save_los ? los : nullptr, n_events_out, lay.ntiles, K);
-    } else {
-      k_project_emit<1><<<g, PROJ_THREADS, 0, st>>>(*L, *P, RK, D, masks, offsets, xsky, ysky, eobs,
-                                                   P->save_los ? los : nullptr, n_events_out, lay.ntiles, K);
-    }
+    // the common external case (cells, TAN sky, no sigma_pos) runs a kernel compiled for it
+    const bool common = P->observer == 0 && P->data_type == 0 && !P->has_sigma_pos &&
+                        P->sky_mode == PXB_SKY_TAN;
+    double* losp = P->save_los ? los : nullptr;
+#define PXB_EMIT(OBS_, SPEC_)                                                                   \
+  k_project_emit<OBS_, SPEC_><<<g, PROJ_THREADS, 0, st>>>(*L, *P, RK, D, masks, offsets, xsky, ysky, \
+                                                         eobs, losp, n_events_out, lay.ntiles, K)
+    if (P->observer != 0) PXB_EMIT(1, 0);
+    else if (common && P->vn_axis >= 0) PXB_EMIT(0, 1);
+    else if (common) PXB_EMIT(0, 2);
+    else PXB_EMIT(0, 0);
+#undef PXB_EMIT
     PXB_LAUNCH_CHECK();
   } else {
   int per_sm = 0;
