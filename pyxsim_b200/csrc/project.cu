@@ -522,9 +522,15 @@ __device__ __forceinline__ bool absorb_one(const pxb_project_params& P, const Wa
   return survives(u, table_tau_per_nh(P, e) * nH);
 }
 
+// SPEC = 1: the common case compiled with its options fixed (wabs, a foreground column only)
+template <int SPEC = 0>
 __device__ __forceinline__ bool absorb_decision(const pxb_project_params& P, const PhiloxKeys& RK,
                                                 const WabsFast& F, int64_t c, int64_t draw, double en) {
   const uint64_t cell_key = (uint64_t)(P.cell_id0 + c);
+  if (SPEC == 1) {
+    const Philox4 ra = pxb_rand4(RK, STREAM_PROJ_A, cell_key, (uint64_t)draw);
+    return wabs_survives(F, u53(ra.x, ra.y), en, P.nH);
+  }
   bool det = true;
   if (P.nH_cell) {
     // internal absorption on the source-frame energy, photon_list.py:715-723
@@ -686,6 +692,7 @@ k_project_photons(const __grid_constant__ pxb_photon_list L,
 // event stores are contiguous.  Costs one more read of the energies (+8 B/photon) and the
 // records (+4 B/event) and buys: no tickets, no look-back spinning, no idle lanes for absorbed
 // photons.
+template <int SPEC>
 __global__ void __launch_bounds__(PROJ_THREADS, 4)
 k_project_detect(const __grid_constant__ pxb_photon_list L,
                  const __grid_constant__ pxb_project_params P, const __grid_constant__ PhiloxKeys RK, const CellDerived D,
@@ -754,7 +761,8 @@ k_project_detect(const __grid_constant__ pxb_photon_list L,
       }
       const int64_t c = c0 + rel;
       const double en = s_e[r * 32 + lane] * (staged ? s_shift[rel] : __ldg(D.shift + c));
-      det = absorb ? absorb_decision(P, RK, s_wabs, c, p - first, en) : true;
+      det = SPEC == 1 ? absorb_decision<1>(P, RK, s_wabs, c, p - first, en)
+                      : (absorb ? absorb_decision(P, RK, s_wabs, c, p - first, en) : true);
       if (det) {
         tsum += en;
         tmin = en < tmin ? en : tmin;   // (energies are never NaN: plain compares, no fmin/fmax)
@@ -1016,7 +1024,10 @@ extern "C" int pxb_project(const pxb_photon_list* L, const pxb_project_params* P
     int64_t* arank = (int64_t*)(ws + lay.off_arank);
     int64_t* totals = (int64_t*)(ws + lay.off_totals);
     const unsigned g = (unsigned)n_ctiles;
-    k_project_detect<<<g, PROJ_THREADS, 0, st>>>(*L, *P, RK, D, W, masks, counts, lay.ntiles);
+    if (P->absorb_kind == PXB_ABS_WABS && !P->nH_cell && P->nH > 0.0)
+      k_project_detect<1><<<g, PROJ_THREADS, 0, st>>>(*L, *P, RK, D, W, masks, counts, lay.ntiles);
+    else
+      k_project_detect<0><<<g, PROJ_THREADS, 0, st>>>(*L, *P, RK, D, W, masks, counts, lay.ntiles);
     PXB_LAUNCH_CHECK();
     rc = pxb_scan_counts(counts, lay.ntiles, offsets, arank, totals, ws + lay.off_scanws,
                          lay.scanws_bytes, stream);
