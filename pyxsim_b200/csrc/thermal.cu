@@ -680,6 +680,7 @@ struct StagedRows {
   const uint16_t* guide;   // [4][guide_stride]
 };
 
+template <int SPEC = 0>
 __device__ __forceinline__ double invert_row(const DevModel& M, const DevTable* t, int tab, int row,
                                              double u2, const StagedRows& S, bool prim);
 
@@ -720,6 +721,8 @@ __device__ __forceinline__ double fast_draw(const DevModel& M, const pxb_thermal
   return invert_row(M, t, tab, row, u2, S, !(fc.meta & 8));
 }
 
+// SPEC = 1: compiled for inverse-CDF sampling on uniformly spaced linear bins
+template <int SPEC>
 __device__ __forceinline__ double invert_row(const DevModel& M, const DevTable* t, int tab, int row,
                                              double u2, const StagedRows& S, bool prim) {
   const int nb = t->nbins;
@@ -744,9 +747,9 @@ __device__ __forceinline__ double invert_row(const DevModel& M, const DevTable* 
   double2 c;
   c.x = cdf[j];
   c.y = cdf[j + 1];
-  if (M.method == 1) return __ldg(M.emid + j);
+  if (SPEC == 0 && M.method == 1) return __ldg(M.emid + j);
   double e0, e1;
-  if (M.edges_uniform) {
+  if (SPEC == 1 || M.edges_uniform) {
     e0 = M.edge0 + j * M.dedge;
     e1 = M.edge0 + (j + 1) * M.dedge;
   } else {
@@ -758,6 +761,7 @@ __device__ __forceinline__ double invert_row(const DevModel& M, const DevTable* 
 
 // invert_row for a row whose CDF and guide table sit in shared memory (32-bit addressing, no
 // per-photon pointer selection): s_cdf/s_guide point at the staged slot
+template <int SPEC = 0>
 __device__ __forceinline__ double invert_row_staged(const DevModel& M, int nb, const double* s_cdf,
                                                     const uint16_t* s_guide, double u2) {
   const int k = min((int)(u2 * nb), nb - 1);
@@ -767,10 +771,10 @@ __device__ __forceinline__ double invert_row_staged(const DevModel& M, int nb, c
     const int mid = (j + jhi + 1) >> 1;
     if (s_cdf[mid] <= u2) j = mid; else jhi = mid - 1;
   }
-  if (M.method == 1) return __ldg(M.emid + j);
+  if (SPEC == 0 && M.method == 1) return __ldg(M.emid + j);
   const double ca = s_cdf[j], cb = s_cdf[j + 1];
   double e0, de;
-  if (M.edges_uniform) {
+  if (SPEC == 1 || M.edges_uniform) {
     e0 = M.edge0 + j * M.dedge;
     de = (M.edge0 + (j + 1) * M.dedge) - e0;
   } else {
@@ -880,6 +884,10 @@ k_thermal_cellsplit(const DevModel M, const __grid_constant__ pxb_thermal_cells 
   }
 }
 
+// SPEC = 1: the common case compiled with its options fixed -- a plain 1-D table without
+// variable elements (every eligible cell is in four-component split mode), inverse-CDF sampling,
+// uniformly spaced linear bins.
+template <int SPEC>
 __global__ void __launch_bounds__(STG_THREADS, 1)
 k_thermal_sample_staged(const DevModel M, const __grid_constant__ pxb_thermal_cells C,
                         const __grid_constant__ PhiloxKeys RK, int64_t n_active, const int64_t* __restrict__ idx,
@@ -1004,7 +1012,7 @@ k_thermal_sample_staged(const DevModel M, const __grid_constant__ pxb_thermal_ce
           if (!(fmeta & 16)) continue;
           const uint64_t d = (uint64_t)(p - first);
           double e;
-          if (fmeta & 32) {
+          if (SPEC == 1 || (fmeta & 32)) {
             if (!(blk_cell == gid && blk_idx == (d >> 1))) {
               blk = pxb_rand4(RK, STREAM_ENERGY, gid, d >> 1);
               blk_cell = gid;
@@ -1013,14 +1021,14 @@ k_thermal_sample_staged(const DevModel M, const __grid_constant__ pxb_thermal_ce
             const double u2 = (d & 1) ? u53(blk.z, blk.w) : u53(blk.x, blk.y);
             const long long dd = (long long)d;
             const int comp = (dd >= fcnt0) + (dd >= fcnt1) + (dd >= fcnt2);
-            const bool prim = !(fmeta & 8);
+            const bool prim = SPEC == 1 || !(fmeta & 8);
             const unsigned dr = (unsigned)(fz1 + (comp >> 1) - S.tag);
             if (prim && S.tag >= 0 && dr < 2u) {
               const int slot = (comp & 1) * 2 + (int)dr;
-              e = invert_row_staged(M, T.nbins, s_cdf + slot * T.cdf_stride,
-                                    s_guide + slot * T.guide_stride, u2);
+              e = invert_row_staged<SPEC>(M, T.nbins, s_cdf + slot * T.cdf_stride,
+                                          s_guide + slot * T.guide_stride, u2);
             } else {
-              e = invert_row(M, prim ? &M.prim : &M.fb, comp & 1, fz1 + (comp >> 1), u2, S, prim);
+              e = invert_row<SPEC>(M, prim ? &M.prim : &M.fb, comp & 1, fz1 + (comp >> 1), u2, S, prim);
             }
           } else if (fmeta & 64) {
             // general split: row from the cumulative row counts, table from the side array
@@ -1054,7 +1062,7 @@ k_thermal_sample_staged(const DevModel M, const __grid_constant__ pxb_thermal_ce
             const FastCell fc = fcs[kc];
             e = fast_draw(M, C, fc, i, u53(rn.x, rn.y), u53(rn.z, rn.w), S);
           }
-          if (M.binscale_log) e = exp10(e);
+          if (SPEC == 0 && M.binscale_log) e = exp10(e);
           e2[h] = e;
           have[h] = true;
         }
@@ -1211,12 +1219,14 @@ extern "C" int pxb_thermal_sample(const pxb_model* model, const pxb_thermal_cell
     const int use_staging = (!D.density_dependent && !D.has_fb && row_bytes + off_bytes <= 220 * 1024) ? 1 : 0;
     const size_t stg_smem = off_bytes + (use_staging ? row_bytes : 0);
     PXB_REQUIRE(n_photons < (int64_t)STG_CHUNK * ((1LL << 32) - 4096), "too many photons for one call");
-    PXB_CUDA(cudaFuncSetAttribute(k_thermal_sample_staged,
-                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stg_smem));
+    const bool common = D.method == 0 && !D.binscale_log && D.edges_uniform && D.nvar == 0 &&
+                        !D.density_dependent && !D.has_fb;
+    auto kern = common ? k_thermal_sample_staged<1> : k_thermal_sample_staged<0>;
+    PXB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stg_smem));
     const int64_t nchunks = (n_photons + STG_CHUNK - 1) / STG_CHUNK;
     int64_t g2 = pxb_sm_count();
     if (g2 > nchunks) g2 = nchunks;
-    k_thermal_sample_staged<<<(unsigned)g2, STG_THREADS, stg_smem, st>>>(
+    kern<<<(unsigned)g2, STG_THREADS, stg_smem, st>>>(
         D, *cells, pxb_make_keys(cells->seed), n_active, idx, poff, n_photons, energies, fcs, tile_cell,
         chunk_counter, use_staging,
         tabcum, tab_stride);
