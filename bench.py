@@ -272,8 +272,12 @@ def run_ours(args):
         if wl["grid"] == args.grid and wl["photons"] == args.photons and wl["nbins"] == args.nbins \
                 and args.kT_range is None:
             kk = tj["kernels"]
-            traffic = {"project": kk["k_project_detect"]["dram_bytes"] + kk["k_project_emit<0>"]["dram_bytes"],
-                       "thermal_sample": kk["k_thermal_sample_staged"]["dram_bytes"]}
+
+            def dram(prefix):      # kernel names carry template arguments: match by prefix
+                return sum(v["dram_bytes"] for k, v in kk.items() if k.startswith(prefix))
+
+            traffic = {"project": dram("k_project_detect") + dram("k_project_emit"),
+                       "thermal_sample": dram("k_thermal_sample_staged") + dram("k_thermal_cellprep")}
     except Exception:
         traffic = None
     stage_ms = {k: v[1] / v[0] for k, v in stages.items()}
