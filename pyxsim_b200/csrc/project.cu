@@ -693,7 +693,7 @@ k_project_photons(const __grid_constant__ pxb_photon_list L,
 // records (+4 B/event) and buys: no tickets, no look-back spinning, no idle lanes for absorbed
 // photons.
 template <int SPEC>
-__global__ void __launch_bounds__(PROJ_THREADS, 4)
+__global__ void __launch_bounds__(PROJ_THREADS, SPEC == 1 ? 5 : 4)
 k_project_detect(const __grid_constant__ pxb_photon_list L,
                  const __grid_constant__ pxb_project_params P, const __grid_constant__ PhiloxKeys RK, const CellDerived D,
                  const ProjWork W, uint16_t* __restrict__ slots, int64_t* __restrict__ counts,
