@@ -895,14 +895,17 @@ k_thermal_sample_staged(const DevModel M, const __grid_constant__ pxb_thermal_ce
                         double* __restrict__ energies, const FastCell* __restrict__ fcs,
                         const int64_t* __restrict__ tile_cell,
                         unsigned int* __restrict__ chunk_counter, int use_staging,
-                        const int64_t* __restrict__ tabcum, int tab_stride) {
+                        const int64_t* __restrict__ tabcum, int tab_stride, int guide_off,
+                        int soff_off) {
+  // shared memory: [4 staged CDF rows | 4 staged guide rows | per-warp cell offsets]; the two
+  // byte offsets come precomputed from the host (kernel parameters are constant-bank operands)
   extern __shared__ __align__(128) unsigned char dyn[];
   const DevTable& T = M.prim;
   const size_t cdf_bytes = use_staging ? (size_t)T.cdf_stride * sizeof(double) : 0;
   const size_t gd_bytes = use_staging ? (size_t)T.guide_stride * sizeof(uint16_t) : 0;
   double* s_cdf = reinterpret_cast<double*>(dyn);
-  uint16_t* s_guide = reinterpret_cast<uint16_t*>(dyn + 4 * cdf_bytes);
-  int64_t* s_off_all = reinterpret_cast<int64_t*>(dyn + 4 * cdf_bytes + 4 * gd_bytes);
+  uint16_t* s_guide = reinterpret_cast<uint16_t*>(dyn + guide_off);
+  int64_t* s_off_all = reinterpret_cast<int64_t*>(dyn + soff_off);
   __shared__ uint64_t s_bar;
   __shared__ unsigned int s_chunk;
 
@@ -1229,7 +1232,8 @@ extern "C" int pxb_thermal_sample(const pxb_model* model, const pxb_thermal_cell
     kern<<<(unsigned)g2, STG_THREADS, stg_smem, st>>>(
         D, *cells, pxb_make_keys(cells->seed), n_active, idx, poff, n_photons, energies, fcs, tile_cell,
         chunk_counter, use_staging,
-        tabcum, tab_stride);
+        tabcum, tab_stride, (int)(use_staging ? row_bytes - 4 * (size_t)D.prim.guide_stride * 2 : 0),
+        (int)(use_staging ? row_bytes : 0));
     PXB_LAUNCH_CHECK();
   }
   k_thermal_sample_cta<<<(unsigned)grid, SAMPLE_THREADS, smem, st>>>(
