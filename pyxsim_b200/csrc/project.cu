@@ -1024,7 +1024,8 @@ extern "C" int pxb_project(const pxb_photon_list* L, const pxb_project_params* P
     int64_t* arank = (int64_t*)(ws + lay.off_arank);
     int64_t* totals = (int64_t*)(ws + lay.off_totals);
     const unsigned g = (unsigned)n_ctiles;
-    if (P->absorb_kind == PXB_ABS_WABS && !P->nH_cell && P->nH > 0.0)
+    const bool generic = getenv("PXB_GENERIC_KERNELS") != nullptr;   // diagnostic: no specialisation
+    if (!generic && P->absorb_kind == PXB_ABS_WABS && !P->nH_cell && P->nH > 0.0)
       k_project_detect<1><<<g, PROJ_THREADS, 0, st>>>(*L, *P, RK, D, W, masks, counts, lay.ntiles);
     else
       k_project_detect<0><<<g, PROJ_THREADS, 0, st>>>(*L, *P, RK, D, W, masks, counts, lay.ntiles);
@@ -1033,7 +1034,7 @@ extern "C" int pxb_project(const pxb_photon_list* L, const pxb_project_params* P
                          lay.scanws_bytes, stream);
     if (rc) return rc;
     // the common external case (cells, TAN sky, no sigma_pos) runs a kernel compiled for it
-    const bool common = P->observer == 0 && P->data_type == 0 && !P->has_sigma_pos &&
+    const bool common = !generic && P->observer == 0 && P->data_type == 0 && !P->has_sigma_pos &&
                         P->sky_mode == PXB_SKY_TAN;
     double* losp = P->save_los ? los : nullptr;
 #define PXB_EMIT(OBS_, SPEC_)                                                                   \

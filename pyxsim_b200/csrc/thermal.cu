@@ -1223,7 +1223,7 @@ extern "C" int pxb_thermal_sample(const pxb_model* model, const pxb_thermal_cell
     const size_t stg_smem = off_bytes + (use_staging ? row_bytes : 0);
     PXB_REQUIRE(n_photons < (int64_t)STG_CHUNK * ((1LL << 32) - 4096), "too many photons for one call");
     const bool common = D.method == 0 && !D.binscale_log && D.edges_uniform && D.nvar == 0 &&
-                        !D.density_dependent && !D.has_fb;
+                        !D.density_dependent && !D.has_fb && !getenv("PXB_GENERIC_KERNELS");
     auto kern = common ? k_thermal_sample_staged<1> : k_thermal_sample_staged<0>;
     PXB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stg_smem));
     const int64_t nchunks = (n_photons + STG_CHUNK - 1) / STG_CHUNK;
