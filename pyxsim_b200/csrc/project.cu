@@ -404,10 +404,11 @@ static SkyConst make_sky_const(const pxb_project_params* P) {
 }
 
 __device__ __forceinline__ double u32_centered(uint32_t w) {
-  // (w + 0.5) / 2^32 - 0.5: uniform in (-1/2, 1/2) with 32-bit resolution; the conversion is
-  // the exact 2^52 + w mantissa trick
-  const double d = __hiloint2double(0x43300000, w) - 4503599627370496.0;
-  return (d + 0.5) * (1.0 / 4294967296.0) - 0.5;
+  // (w + 0.5) / 2^32 - 0.5: uniform in (-1/2, 1/2) with 32-bit resolution.  w goes into the top
+  // mantissa bits of a double in [1, 2) (= 1 + w/2^32, exact); one exact addition of
+  // -1.5 + 2^-33 finishes it -- a single fp64 instruction.
+  const double d = __hiloint2double((int)(0x3FF00000u | (w >> 12)), (int)(w << 20));
+  return d + (-1.5 + 1.0 / 8589934592.0);
 }
 
 // scatter + sky transform of one surviving photon (external observer).  SPEC = 0 reads every
