@@ -283,6 +283,16 @@ __device__ __forceinline__ double atan_small(double t) {
   return t + t * z * p;
 }
 
+// the same series cut after t^9: exact to fp64 rounding for |t| <= 1/64
+__device__ __forceinline__ double atan_tiny(double t) {
+  const double z = t * t;
+  double p = 1.0 / 9.0;
+  p = p * z - 1.0 / 7.0;
+  p = p * z + 1.0 / 5.0;
+  p = p * z - 1.0 / 3.0;
+  return t + t * z * p;
+}
+
 // inverse gnomonic projection for the fused kernel.  Same map as tan_to_cel, arranged so that
 // both angles are small-argument arctangents (no atan2, no cancellation):
 //   RA  - RA0  = atan(-x / den),                      den = cos d0 - y sin d0
@@ -300,7 +310,11 @@ __device__ __forceinline__ void tan_to_cel_fast(double x, double y, double ra0_r
   const double inv = 1.0 / (den * den2);
   const double t1 = -x * den2 * inv;
   const double t2 = num2 * den * inv;
-  if (den > 0.0 && fabs(t1) <= 0.0625 && fabs(t2) <= 0.0625) {
+  if (den > 0.0 && fabs(t1) <= 0.015625 && fabs(t2) <= 0.015625) {
+    // within ~0.9 degrees of the centre the series can stop at t^9 (next term < 8e-20 relative)
+    ra_deg = (ra0_rad + atan_tiny(t1)) * PXB_RAD2DEG;
+    dec_deg = (d0_rad + atan_tiny(t2)) * PXB_RAD2DEG;
+  } else if (den > 0.0 && fabs(t1) <= 0.0625 && fabs(t2) <= 0.0625) {
     ra_deg = (ra0_rad + atan_small(t1)) * PXB_RAD2DEG;
     dec_deg = (d0_rad + atan_small(t2)) * PXB_RAD2DEG;
   } else {
