@@ -192,6 +192,14 @@ k_project_cells(const __grid_constant__ pxb_photon_list L,
   g.cy = x * P.y_hat[0] + y * P.y_hat[1] + z * P.y_hat[2];
   g.cz = x * P.z_hat[0] + y * P.z_hat[1] + z * P.z_hat[2];
   g.w = w;
+  if (P.observer == 0 && P.sky_mode != PXB_SKY_PHYS) {
+    // angular sky modes: the plane coordinates are wanted in radians (/D_A, photon_list.py:758-760);
+    // scaling the centre and the scatter width here saves two multiplications per event
+    const double inv_DA = P.D_A_kpc != 0.0 ? 1.0 / P.D_A_kpc : 0.0;
+    g.cx *= inv_DA;
+    g.cy *= inv_DA;
+    g.w *= inv_DA;
+  }
   D.geom[c] = g;
   // every warp tile that starts inside this cell's photon range starts in this cell
   const int64_t a = L.poff[c], b = L.poff[c + 1];
@@ -470,9 +478,7 @@ __device__ __forceinline__ void scatter_external(const pxb_project_params& P, co
     xs += sg * n0;
     ys += sg * n1;
   }
-  if (SPEC != 0 || P.sky_mode != PXB_SKY_PHYS) {
-    xs *= K.inv_DA;
-    ys *= K.inv_DA;
+  if (SPEC != 0 || P.sky_mode != PXB_SKY_PHYS) {   // (cx, cy, w are already in radians)
     if (SPEC == 0 && P.sky_mode == PXB_SKY_FLAT) {
       xs = P.sky_center[0] - xs * PXB_RAD2DEG;   // photon_list.py:762-764
       ys = P.sky_center[1] + ys * PXB_RAD2DEG;
