@@ -50,6 +50,8 @@ def parse_args():
     ap.add_argument("--nbins", type=int, default=NBINS)
     ap.add_argument("--kT-range", type=float, nargs=2, default=None,
                     help="log-uniform kT range instead of the isothermal 6 keV cluster")
+    ap.add_argument("--traffic-from", default=None,
+                    help="JSON summary of an ncu --set full capture of this same command")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample-cells", type=int, default=120000)
@@ -263,23 +265,21 @@ def run_ours(args):
         "thermal_sample": Na * (2 * w + 24) + Np * w,
         "project": Na * (7 * w + 8) + Np * w + Ne_local * 3 * w,
     }
-    # measured DRAM traffic of the dominant stage from the committed ncu capture of this very
-    # workload (profiles/r1_final_traffic.json); null for any other workload
+    # measured DRAM traffic of the dominant stage: only from an ncu capture of THIS command
+    # handed in with --traffic-from (a JSON {"kernels": {name: {"dram_bytes": ...}}} made by
+    # scripts/summarise_profile.py); otherwise null -- the ncu numbers live under profiles/
     traffic = None
-    try:
-        tj = json.load(open(os.path.join(ROOT, "profiles", "r1_final_traffic.json")))
-        wl = tj["workload"]
-        if wl["grid"] == args.grid and wl["photons"] == args.photons and wl["nbins"] == args.nbins \
-                and args.kT_range is None:
-            kk = tj["kernels"]
+    if args.traffic_from:
+        try:
+            kk = json.load(open(args.traffic_from))["kernels"]
 
             def dram(prefix):      # kernel names carry template arguments: match by prefix
                 return sum(v["dram_bytes"] for k, v in kk.items() if k.startswith(prefix))
 
             traffic = {"project": dram("k_project_detect") + dram("k_project_emit"),
-                       "thermal_sample": dram("k_thermal_sample_staged") + dram("k_thermal_cellprep")}
-    except Exception:
-        traffic = None
+                       "thermal_sample": dram("k_thermal_sample") + dram("k_thermal_cellprep")}
+        except Exception:
+            traffic = None
     stage_ms = {k: v[1] / v[0] for k, v in stages.items()}
     dominant = max(stage_ms, key=stage_ms.get) if stage_ms else None
     roofline = None

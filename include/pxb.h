@@ -84,6 +84,10 @@ int pxb_device_info(int* sm_count, int* cc_major, int* cc_minor);
  * pxb_powerlaw_cells, pxb_line_cells, pxb_photon_list, pxb_project_params (in that order);
  * returns the number of entries written.  Lets a binding verify its struct layout. */
 int pxb_struct_sizes(int64_t* out, int n);
+/* Number of kernels libpxb has launched in this process since the last reset (every launch in
+ * the library goes through one checked macro that counts it). */
+int64_t pxb_launch_count(void);
+void pxb_launch_count_reset(void);
 
 /* ------------------------------------------------------------------------------------
  * Thermal spectral tables
@@ -127,7 +131,10 @@ int pxb_model_nonnegative(const pxb_model* model);
 /* Per-chunk inputs of the thermal source (all per-cell arrays are device, length ncell). */
 typedef struct {
   int64_t ncell;
-  int64_t cell_id0;            /* global id of cell 0: RNG counters use cell_id0 + i */
+  int64_t cell_id0;            /* global id of cell 0: RNG counters use the global id of cell i,
+                                  cell_id0 + i, or -- when id_block > 0 (a block-cyclic shard of a
+                                  larger dataset gathered into one chunk) --
+                                  cell_id0 + (i / id_block) * id_stride + i % id_block */
   const double* kT;            /* keV */
   const double* em;            /* emission measure, cm^-3 */
   const double* nH;            /* H nuclei density cm^-3, or NULL */
@@ -149,6 +156,13 @@ typedef struct {
   double kT_min, kT_max;
   double max_density, min_entropy;
   uint64_t seed;
+  int64_t id_block, id_stride; /* see cell_id0; 0 => contiguous ids */
+  int32_t generic_kernels;     /* diagnostic: never take the kernels compiled for the common
+                                  option set (same results, used by the parity tests) */
+  int32_t split_factor;        /* variable-element tables: a cell's photons are split over its
+                                  (row, table) components once per cell when it holds at least
+                                  split_factor * components photons; 0 => default (6),
+                                  < 0 => never (per-photon component choice) */
 } pxb_thermal_cells;
 
 /* lambda_out (nullable) receives spec_sum*cell_nrm, counts_out the Poisson draws.
@@ -285,6 +299,7 @@ typedef struct {
   double spectral_norm;
   double scale_factor;    /* 1/(1+z) */
   uint64_t seed;
+  int64_t id_block, id_stride;  /* as in pxb_thermal_cells */
 } pxb_powerlaw_cells;
 
 int pxb_powerlaw_counts(const pxb_powerlaw_cells* cells, double* lambda_out,
@@ -304,6 +319,7 @@ typedef struct {
   double spectral_norm;
   double scale_factor;
   uint64_t seed;
+  int64_t id_block, id_stride;  /* as in pxb_thermal_cells */
 } pxb_line_cells;
 
 /* K = L / K_fac and the per-cell alpha (power_law_sources.py:196-206), inputs of the spectrum mode */
@@ -338,6 +354,9 @@ typedef struct {
   const double* vz;
   const double* dx;      /* kpc (cell width or smoothing length) */
   const double* energy;  /* [n_photons] keV */
+  const int64_t* cell_id; /* [n_cells] global id of every active cell (keys the projection's RNG
+                             counters, so the events of a cell do not depend on how the dataset was
+                             chunked or sharded over ranks), or NULL -> params.cell_id0 + c */
 } pxb_photon_list;
 
 enum { PXB_ABS_NONE = 0, PXB_ABS_TABLE = 1, PXB_ABS_WABS = 2 };
@@ -353,7 +372,9 @@ typedef struct {
   int32_t save_los;
   int32_t absorb_kind;   /* PXB_ABS_* */
   int32_t has_sigma_pos;
-  int32_t reserved;
+  int32_t single_pass;   /* 0 (default): detect -> scan -> emit; 1: one pass with a decoupled
+                            look-back over per-tile counts (DRAM traffic == algorithmic bytes);
+                            identical event list either way */
   double sigma_pos;
   double x_hat[3], y_hat[3], z_hat[3];
   double D_A_kpc;
@@ -364,7 +385,8 @@ typedef struct {
   int64_t abs_n;
   int32_t abs_grid;          /* 0 arbitrary ascending grid (binary search), 1 uniform in E,
                                 2 uniform in log10(E): index = (x - abs_x0) * abs_inv_dx */
-  int32_t reserved2;
+  int32_t generic_kernels;   /* diagnostic: never take the kernels compiled for the common
+                                option set (same events; used by the parity tests) */
   double abs_x0, abs_inv_dx;
   const double* nH_cell;     /* device per-cell internal column (1e22 cm^-2) or NULL */
   double oneplusz;

@@ -55,6 +55,8 @@ class ThermalCells(C.Structure):
         ("kT_min", C.c_double), ("kT_max", C.c_double),
         ("max_density", C.c_double), ("min_entropy", C.c_double),
         ("seed", C.c_uint64),
+        ("id_block", C.c_int64), ("id_stride", C.c_int64),
+        ("generic_kernels", C.c_int32), ("split_factor", C.c_int32),
     ]
 
 
@@ -72,6 +74,7 @@ class PowerlawCells(C.Structure):
         ("lum", c_void_p), ("alpha", c_void_p), ("r2", c_void_p),
         ("alpha_const", C.c_double), ("e0", C.c_double), ("emin", C.c_double), ("emax", C.c_double),
         ("spectral_norm", C.c_double), ("scale_factor", C.c_double), ("seed", C.c_uint64),
+        ("id_block", C.c_int64), ("id_stride", C.c_int64),
     ]
 
 
@@ -81,6 +84,7 @@ class LineCells(C.Structure):
         ("rate", c_void_p), ("sigma", c_void_p), ("r2", c_void_p),
         ("sigma_const", C.c_double), ("e0", C.c_double),
         ("spectral_norm", C.c_double), ("scale_factor", C.c_double), ("seed", C.c_uint64),
+        ("id_block", C.c_int64), ("id_stride", C.c_int64),
     ]
 
 
@@ -90,7 +94,7 @@ class PhotonList(C.Structure):
         ("nph", c_void_p), ("poff", c_void_p),
         ("x", c_void_p), ("y", c_void_p), ("z", c_void_p),
         ("vx", c_void_p), ("vy", c_void_p), ("vz", c_void_p),
-        ("dx", c_void_p), ("energy", c_void_p),
+        ("dx", c_void_p), ("energy", c_void_p), ("cell_id", c_void_p),
     ]
 
 
@@ -99,12 +103,12 @@ class ProjectParams(C.Structure):
         ("observer", C.c_int32), ("data_type", C.c_int32), ("kernel", C.c_int32),
         ("no_shifting", C.c_int32), ("vn_axis", C.c_int32), ("sky_mode", C.c_int32),
         ("save_los", C.c_int32), ("absorb_kind", C.c_int32), ("has_sigma_pos", C.c_int32),
-        ("reserved", C.c_int32),
+        ("single_pass", C.c_int32),
         ("sigma_pos", C.c_double),
         ("x_hat", C.c_double * 3), ("y_hat", C.c_double * 3), ("z_hat", C.c_double * 3),
         ("D_A_kpc", C.c_double), ("sky_center", C.c_double * 2), ("nH", C.c_double),
         ("abs_energy", c_void_p), ("abs_sigma", c_void_p), ("abs_n", C.c_int64),
-        ("abs_grid", C.c_int32), ("reserved2", C.c_int32),
+        ("abs_grid", C.c_int32), ("generic_kernels", C.c_int32),
         ("abs_x0", C.c_double), ("abs_inv_dx", C.c_double),
         ("nH_cell", c_void_p), ("oneplusz", C.c_double),
         ("seed", C.c_uint64), ("cell_id0", C.c_int64),
@@ -127,6 +131,8 @@ SIGNATURES = {
     "pxb_version": (C.c_int, []),
     "pxb_device_info": (C.c_int, [_P(C.c_int), _P(C.c_int), _P(C.c_int)]),
     "pxb_struct_sizes": (C.c_int, [_P(C.c_int64), C.c_int]),
+    "pxb_launch_count": (C.c_int64, []),
+    "pxb_launch_count_reset": (None, []),
     "pxb_model_create": (C.c_int, [_P(ModelDesc), _P(c_void_p)]),
     "pxb_model_destroy": (C.c_int, [c_void_p]),
     "pxb_model_nonnegative": (C.c_int, [c_void_p]),
@@ -224,7 +230,13 @@ def check(status):
 
 
 def call(name, *args):
-    from . import profiling
-
-    profiling.count_call(name)
     check(getattr(load(), name)(*args))
+
+
+def launch_count():
+    """Kernels launched by libpxb in this process since the last reset (counted in the library)."""
+    return int(load().pxb_launch_count())
+
+
+def launch_count_reset():
+    load().pxb_launch_count_reset()

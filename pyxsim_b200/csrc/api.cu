@@ -13,6 +13,12 @@ void pxb_set_error(const char* fmt, ...) {
 
 extern "C" const char* pxb_last_error(void) { return g_err; }
 
+#include <atomic>
+static std::atomic<long long> g_launches{0};
+void pxb_count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+extern "C" int64_t pxb_launch_count(void) { return (int64_t)g_launches.load(std::memory_order_relaxed); }
+extern "C" void pxb_launch_count_reset(void) { g_launches.store(0, std::memory_order_relaxed); }
+
 extern "C" int pxb_version(void) { return 100; }  // 0.1.0
 
 int pxb_sm_count() {

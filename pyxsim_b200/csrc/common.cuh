@@ -33,8 +33,11 @@ void pxb_set_error(const char* fmt, ...);
     }                                                                                  \
   } while (0)
 
+void pxb_count_launch();   // api.cu: process-wide kernel launch counter (pxb_launch_count)
+
 #define PXB_LAUNCH_CHECK()                                                             \
   do {                                                                                 \
+    pxb_count_launch();                                                                \
     cudaError_t _e = cudaGetLastError();                                               \
     if (_e != cudaSuccess) {                                                           \
       pxb_set_error("kernel launch failed at %s:%d: %s", __FILE__, __LINE__,           \
@@ -44,6 +47,14 @@ void pxb_set_error(const char* fmt, ...);
   } while (0)
 
 int pxb_sm_count();  // cached SM count of the current device (148 on B200)
+
+// global id of cell i of a chunk (pxb_thermal_cells.cell_id0 / id_block / id_stride and the same
+// triple of the power-law and line structs): contiguous, or block-cyclic shard of a larger dataset
+template <class Cells>
+__device__ __forceinline__ uint64_t cell_gid(const Cells& C, int64_t i) {
+  if (C.id_block > 0) return (uint64_t)(C.cell_id0 + (i / C.id_block) * C.id_stride + i % C.id_block);
+  return (uint64_t)(C.cell_id0 + i);
+}
 
 // ---------------------------------------------------------------------------------------
 // RNG: Philox4x32-10 (Salmon et al. 2011), counter-based.

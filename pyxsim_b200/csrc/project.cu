@@ -155,6 +155,7 @@ struct CellDerived {
   double* shift;       // Doppler factor (1 when no_shifting)
   CellGeom* geom;
   int64_t* tile_cell;  // [n_wtiles + 1]: cell holding the first photon of every warp tile
+  int64_t* gid;        // global cell id: the RNG counter key (photon_list.cell_id, or cell_id0 + c)
 };
 
 __device__ __forceinline__ CellGeom ld_geom(const CellGeom* p) {
@@ -185,6 +186,7 @@ k_project_cells(const __grid_constant__ pxb_photon_list L,
     shift = doppler_factor(vn * ss, v2 * (ss * ss));
   }
   D.shift[c] = shift;
+  D.gid[c] = L.cell_id ? L.cell_id[c] : P.cell_id0 + c;
   double w = L.dx ? L.dx[c] : 0.0;
   if (P.observer == 0 && P.data_type == 1) w *= 0.5;  // photon_list.py:733-734
   CellGeom g;
@@ -546,8 +548,8 @@ __device__ __forceinline__ bool absorb_one(const pxb_project_params& P, const Wa
 // SPEC = 1: the common case compiled with its options fixed (wabs, a foreground column only)
 template <int SPEC = 0>
 __device__ __forceinline__ bool absorb_decision(const pxb_project_params& P, const PhiloxKeys& RK,
-                                                const WabsFast& F, int64_t c, int64_t draw, double en) {
-  const uint64_t cell_key = (uint64_t)(P.cell_id0 + c);
+                                                const WabsFast& F, int64_t c, uint64_t cell_key,
+                                                int64_t draw, double en) {
   if (SPEC == 1) {
     const Philox4 ra = pxb_rand4(RK, STREAM_PROJ_A, cell_key, (uint64_t)draw);
     return wabs_survives(F, u53(ra.x, ra.y), en, P.nH);
@@ -652,7 +654,7 @@ k_project_photons(const __grid_constant__ pxb_photon_list L,
         }
         const int64_t c = c0 + rel;
         const double en = s_e[it] * __ldg(D.shift + c);
-        det = absorb ? absorb_decision(P, RK, s_wabs, c, p - first, en) : true;
+        det = absorb ? absorb_decision(P, RK, s_wabs, c, (uint64_t)__ldg(D.gid + c), p - first, en) : true;
         s_e[it] = en;
         s_rel[it] = rel;
         if (det) {
@@ -687,7 +689,7 @@ k_project_photons(const __grid_constant__ pxb_photon_list L,
       const int rel = s_rel[it];
       const int64_t c = c0 + rel;
       const int64_t first = (nc > 0) ? s_off[rel] : __ldg(L.poff + c);
-      const uint64_t cell_key = (uint64_t)(P.cell_id0 + c);
+      const uint64_t cell_key = (uint64_t)__ldg(D.gid + c);
       const uint64_t draw = (uint64_t)(p0 + it - first);
       double xs, ys, los;
       const CellGeom g = ld_geom(D.geom + c);
@@ -782,8 +784,9 @@ k_project_detect(const __grid_constant__ pxb_photon_list L,
       }
       const int64_t c = c0 + rel;
       const double en = s_e[r * 32 + lane] * (staged ? s_shift[rel] : __ldg(D.shift + c));
-      det = SPEC == 1 ? absorb_decision<1>(P, RK, s_wabs, c, p - first, en)
-                      : (absorb ? absorb_decision(P, RK, s_wabs, c, p - first, en) : true);
+      const uint64_t cell_key = (uint64_t)__ldg(D.gid + c);
+      det = SPEC == 1 ? absorb_decision<1>(P, RK, s_wabs, c, cell_key, p - first, en)
+                      : (absorb ? absorb_decision(P, RK, s_wabs, c, cell_key, p - first, en) : true);
       if (det) {
         tsum += en;
         tmin = en < tmin ? en : tmin;   // (energies are never NaN: plain compares, no fmin/fmax)
@@ -893,7 +896,7 @@ k_project_emit(const __grid_constant__ pxb_photon_list L,
     const int64_t c = c0 + rel;
     const CellGeom g = staged ? s_geom[rel] : ld_geom(D.geom + c);
     const double en = s_e[it] * (staged ? s_shift[rel] : __ldg(D.shift + c));
-    const uint64_t cell_key = (uint64_t)(P.cell_id0 + c);
+    const uint64_t cell_key = (uint64_t)__ldg(D.gid + c);
     const uint64_t draw = (uint64_t)(p - first);
     double xs, ys, los;
     if (OBS == 0) scatter_external<SPEC>(P, RK, g, K, cell_key, draw, xs, ys, los);
@@ -954,7 +957,7 @@ static ProjLayout proj_layout(int64_t n_cells, int64_t n_photons) {
   ProjLayout l;
   l.ntiles = (n_photons + PROJ_WTILE - 1) / PROJ_WTILE;   // warp tiles
   int64_t o = 0;
-  l.off_cells = o;  o += align256(5 * n_cells * (int64_t)sizeof(double));
+  l.off_cells = o;  o += align256(6 * n_cells * (int64_t)sizeof(double));
   l.off_tilecell = o; o += align256((l.ntiles + 1) * 8);
   l.off_status = o; o += align256(l.ntiles * 8);
   l.off_ticket = o; o += 256;
@@ -1018,6 +1021,7 @@ extern "C" int pxb_project(const pxb_photon_list* L, const pxb_project_params* P
   CellDerived D;
   D.geom = (CellGeom*)(ws + lay.off_cells);                 // 32-byte records first (alignment)
   D.shift = (double*)(ws + lay.off_cells + 4 * L->n_cells * (int64_t)sizeof(double));
+  D.gid = (int64_t*)(ws + lay.off_cells + 5 * L->n_cells * (int64_t)sizeof(double));
   D.tile_cell = (int64_t*)(ws + lay.off_tilecell);
   ProjWork W;
   W.status = (unsigned long long*)(ws + lay.off_status);
@@ -1031,13 +1035,12 @@ extern "C" int pxb_project(const pxb_photon_list* L, const pxb_project_params* P
   k_project_cells<<<(unsigned)((L->n_cells + 255) / 256), 256, 0, st>>>(*L, *P, D);
   PXB_LAUNCH_CHECK();
   // default: two passes (detect -> scan -> emit): no inter-tile waiting, small rolled kernels,
-  // at the price of reading the energies twice (+8 B/photon).  PXB_PROJECT_MODE=fused selects
+  // at the price of reading the energies twice (+8 B/photon).  params.single_pass selects
   // the single-pass kernel (DRAM traffic == algorithmic bytes, decoupled look-back), which
   // produces the identical event list; on B200 it is ~10 % slower while the path is ALU-bound.
   const SkyConst K = make_sky_const(P);
   const PhiloxKeys RK = pxb_make_keys(P->seed);
-  const char* mode = getenv("PXB_PROJECT_MODE");
-  const bool fused = mode && strcmp(mode, "fused") == 0;
+  const bool fused = P->single_pass != 0;
   if (!fused) {
     uint16_t* masks = (uint16_t*)(ws + lay.off_masks);   // survivor records
     int64_t* counts = (int64_t*)(ws + lay.off_counts);
@@ -1045,7 +1048,7 @@ extern "C" int pxb_project(const pxb_photon_list* L, const pxb_project_params* P
     int64_t* arank = (int64_t*)(ws + lay.off_arank);
     int64_t* totals = (int64_t*)(ws + lay.off_totals);
     const unsigned g = (unsigned)n_ctiles;
-    const bool generic = getenv("PXB_GENERIC_KERNELS") != nullptr;   // diagnostic: no specialisation
+    const bool generic = P->generic_kernels != 0;   // diagnostic: no specialisation
     if (!generic && P->absorb_kind == PXB_ABS_WABS && !P->nH_cell && P->nH > 0.0)
       k_project_detect<1><<<g, PROJ_THREADS, 0, st>>>(*L, *P, RK, D, W, masks, counts, lay.ntiles);
     else

@@ -53,7 +53,7 @@ k_powerlaw_counts(const __grid_constant__ pxb_powerlaw_cells C, double* __restri
   if (i >= C.ncell) return;
   const double lam = pl_lambda(C, i);
   if (lambda_out) lambda_out[i] = lam;
-  CellStream rs(C.seed, STREAM_POISSON, (uint64_t)(C.cell_id0 + i));
+  CellStream rs(C.seed, STREAM_POISSON, cell_gid(C, i));
   counts_out[i] = poisson_draw(lam, rs);
 }
 
@@ -87,7 +87,7 @@ k_powerlaw_sample(const __grid_constant__ pxb_powerlaw_cells C,
     PlCoef k;
     if (!C.alpha) k = s_kc;
     else k = (tm.nc > 0) ? s_k[c - tm.c0] : pl_coef(C, C.alpha[idx[c]]);
-    const uint64_t gid = (uint64_t)(C.cell_id0 + idx[c]);
+    const uint64_t gid = cell_gid(C, idx[c]);
     const uint64_t draw = (uint64_t)(p - __ldg(poff + c));
     // photons 2m and 2m+1 of a cell use the two halves of one Philox block
     const Philox4 r = pxb_rand4(RK, STREAM_POWERLAW, gid, draw >> 1);
@@ -140,7 +140,7 @@ k_line_counts(const __grid_constant__ pxb_line_cells C, double* __restrict__ lam
   double lam = C.rate[i] * C.spectral_norm * C.scale_factor;   // line_sources.py:205
   if (C.r2) lam /= C.r2[i];
   if (lambda_out) lambda_out[i] = lam;
-  CellStream rs(C.seed, STREAM_POISSON, (uint64_t)(C.cell_id0 + i));
+  CellStream rs(C.seed, STREAM_POISSON, cell_gid(C, i));
   counts_out[i] = poisson_draw(lam, rs);
 }
 
@@ -161,7 +161,7 @@ k_line_sample(const __grid_constant__ pxb_line_cells C, const __grid_constant__ 
     const double sigma = C.sigma ? __ldg(C.sigma + i) : C.sigma_const;
     const uint64_t draw = (uint64_t)(p - __ldg(poff + c));
     // one Philox block -> two normals: photon pairs (2m, 2m+1) share block m
-    const Philox4 r = pxb_rand4(RK, STREAM_LINE, (uint64_t)(C.cell_id0 + i), draw >> 1);
+    const Philox4 r = pxb_rand4(RK, STREAM_LINE, cell_gid(C, i), draw >> 1);
     double n0, n1;
     normal2(r, n0, n1);
     const double g = (draw & 1) ? n1 : n0;

@@ -483,7 +483,7 @@ extern "C" int pxb_thermal_spectrum(const pxb_model* model, const pxb_thermal_ce
   // Without a shift and with a workspace the spectrum is assembled from per-row weights; only
   // the cells whose clip matters take the per-cell path.
   const bool linear = shift == nullptr && workspace != nullptr &&
-                      (D.prim.nonneg || (D.has_fb && D.fb.nonneg)) && !getenv("PXB_SPECTRUM_PER_CELL");
+                      (D.prim.nonneg || (D.has_fb && D.fb.nonneg));
   if (linear) {
     int64_t need = 0;
     pxb_thermal_spectrum_workspace_bytes(model, cells->ncell, &need);
@@ -536,8 +536,7 @@ extern "C" int pxb_thermal_band(const pxb_model* model, const pxb_thermal_cells*
   const int64_t nwarp = cells->ncell;
   const int64_t blocks = (nwarp + 7) / 8;
   PXB_REQUIRE(blocks < (1LL << 31), "too many cells for one call");
-  const bool fast = workspace != nullptr && (D.prim.pre_n || (D.has_fb && D.fb.pre_n)) &&
-                    !getenv("PXB_BAND_PER_CELL");
+  const bool fast = workspace != nullptr && (D.prim.pre_n || (D.has_fb && D.fb.pre_n));
   if (fast) {
     int64_t need = 0;
     pxb_thermal_band_workspace_bytes(cells->ncell, &need);

@@ -285,7 +285,7 @@ k_thermal_counts_fast(const DevModel M, const __grid_constant__ pxb_thermal_cell
   }
   const double lam = s * cell_norm(C, i);
   if (lambda_out) lambda_out[i] = lam;
-  CellStream rs(C.seed, STREAM_POISSON, (uint64_t)(C.cell_id0 + i));
+  CellStream rs(C.seed, STREAM_POISSON, cell_gid(C, i));
   counts_out[i] = poisson_draw(lam, rs);
 }
 
@@ -320,7 +320,7 @@ k_thermal_counts_general(const DevModel M, const __grid_constant__ pxb_thermal_c
     if (lane == 0) {
       const double lam = acc * cell_norm(C, i);
       if (lambda_out) lambda_out[i] = lam;
-      CellStream rs(C.seed, STREAM_POISSON, (uint64_t)(C.cell_id0 + i));
+      CellStream rs(C.seed, STREAM_POISSON, cell_gid(C, i));
       counts_out[i] = poisson_draw(lam, rs);
     }
   }
@@ -468,7 +468,7 @@ k_thermal_sample_cta(const DevModel M, const __grid_constant__ pxb_thermal_cells
       for (int j = j0 + lane; j < j1; j += 32) cdf[j + 1] += basev;
     __syncthreads();
     const double total = cdf[nbins];
-    const uint64_t gid = (uint64_t)(C.cell_id0 + i);
+    const uint64_t gid = cell_gid(C, i);
     // sampling: one Philox block -> two photons
     const int64_t npair = (N + 1) >> 1;
     for (int64_t p = threadIdx.x; p < npair; p += blockDim.x) {
@@ -571,7 +571,7 @@ __device__ __forceinline__ FastCell fast_setup(const DevModel& M, const pxb_ther
     q[1] = mx.w[0] * Z * __ldg(t->rs_m + mx.row[0]);
     q[2] = mx.w[1] * __ldg(t->rs_c + mx.row[1]);
     q[3] = mx.w[1] * Z * __ldg(t->rs_m + mx.row[1]);
-    CellStream rs(C.seed, STREAM_SPLIT, (uint64_t)(C.cell_id0 + i));
+    CellStream rs(C.seed, STREAM_SPLIT, cell_gid(C, i));
     double rest = q[0] + q[1] + q[2] + q[3];
     int64_t left = N, acc = 0;
 #pragma unroll
@@ -602,7 +602,7 @@ __device__ __forceinline__ FastCell fast_setup(const DevModel& M, const pxb_ther
     // the per-photon choice is cheap and the sampler is bound by the CDF gathers anyway
     // (measured on the 2-D table configuration: the split made it slower).
     const int ntab = 2 + C.nvar;
-    CellStream rs(C.seed, STREAM_SPLIT, (uint64_t)(C.cell_id0 + i));
+    CellStream rs(C.seed, STREAM_SPLIT, cell_gid(C, i));
     double rest = tot;
     int64_t left = N, acc = 0;
     int64_t nrow[4] = {0, 0, 0, 0};
@@ -1010,7 +1010,7 @@ k_thermal_sample_staged(const DevModel M, const __grid_constant__ pxb_thermal_ce
             fcnt2 = fc.cnt[2];
             kc = k;
             i = __ldg(idx + k);
-            gid = (uint64_t)(C.cell_id0 + i);
+            gid = cell_gid(C, i);
           }
           if (!(fmeta & 16)) continue;
           const uint64_t d = (uint64_t)(p - first);
@@ -1173,12 +1173,19 @@ extern "C" int pxb_thermal_sample(const pxb_model* model, const pxb_thermal_cell
   const size_t smem = ((size_t)D.nbins + 1 + PXB_MAX_VAR + SAMPLE_THREADS / 32) * sizeof(double);
   PXB_REQUIRE(smem <= 227 * 1024, "nbins=%d needs %zu B of shared memory for the per-cell CDF (max 227 KB)",
               D.nbins, smem);
-  PXB_CUDA(cudaFuncSetAttribute(k_thermal_sample_cta, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                (int)smem));
-  int per_sm = 0;
-  PXB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_thermal_sample_cta,
-                                                         SAMPLE_THREADS, smem));
-  if (per_sm < 1) per_sm = 1;
+  // attribute + occupancy query once per (process, shared-memory size), not per call
+  static thread_local size_t cta_smem_set = 0;
+  static thread_local int cta_per_sm = 1;
+  if (cta_smem_set != smem) {
+    PXB_CUDA(cudaFuncSetAttribute(k_thermal_sample_cta, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)smem));
+    int q = 0;
+    PXB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&q, k_thermal_sample_cta,
+                                                           SAMPLE_THREADS, smem));
+    cta_per_sm = q < 1 ? 1 : q;
+    cta_smem_set = smem;
+  }
+  const int per_sm = cta_per_sm;
   int64_t grid = (int64_t)pxb_sm_count() * per_sm;
   if (grid > n_active) grid = n_active;
   int64_t* list = nullptr;
@@ -1200,9 +1207,8 @@ extern "C" int pxb_thermal_sample(const pxb_model* model, const pxb_thermal_cell
     int64_t* tabcum = tab_stride ? (int64_t*)(fcs + n_active) : nullptr;
     int64_t* glist = tab_stride ? tabcum + n_active * (int64_t)tab_stride : nullptr;
     unsigned long long* glist_count = (unsigned long long*)workspace + 3;
-    if (getenv("PXB_NO_GENERAL_SPLIT")) tabcum = nullptr;   // diagnostic: per-photon component choice
-    int split_factor = 6;
-    if (const char* sf = getenv("PXB_SPLIT_FACTOR")) split_factor = atoi(sf) > 0 ? atoi(sf) : 6;
+    if (cells->split_factor < 0) tabcum = nullptr;   // per-photon component choice
+    const int split_factor = cells->split_factor > 0 ? cells->split_factor : 6;
     PXB_CUDA(cudaMemsetAsync(workspace, 0, 4 * sizeof(int64_t), st));
     k_thermal_cellprep<<<(unsigned)((n_active + 255) / 256), 256, 0, st>>>(
         D, *cells, n_active, idx, poff, fcs, tile_cell, list, count, tabcum, glist, glist_count,
@@ -1223,9 +1229,13 @@ extern "C" int pxb_thermal_sample(const pxb_model* model, const pxb_thermal_cell
     const size_t stg_smem = off_bytes + (use_staging ? row_bytes : 0);
     PXB_REQUIRE(n_photons < (int64_t)STG_CHUNK * ((1LL << 32) - 4096), "too many photons for one call");
     const bool common = D.method == 0 && !D.binscale_log && D.edges_uniform && D.nvar == 0 &&
-                        !D.density_dependent && !D.has_fb && !getenv("PXB_GENERIC_KERNELS");
+                        !D.density_dependent && !D.has_fb && !cells->generic_kernels;
     auto kern = common ? k_thermal_sample_staged<1> : k_thermal_sample_staged<0>;
-    PXB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stg_smem));
+    static thread_local size_t stg_set[2] = {0, 0};
+    if (stg_set[common ? 1 : 0] != stg_smem + 1) {
+      PXB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stg_smem));
+      stg_set[common ? 1 : 0] = stg_smem + 1;
+    }
     const int64_t nchunks = (n_photons + STG_CHUNK - 1) / STG_CHUNK;
     int64_t g2 = pxb_sm_count();
     if (g2 > nchunks) g2 = nchunks;

@@ -110,6 +110,58 @@ class ArrayChunk:
     def to_value(self, field, unit=None):
         return convert(self[field], self.units(field), unit)
 
+    def id_map(self):
+        """(cell_id0, id_block, id_stride) of ``pxb_thermal_cells``: global id of local cell i."""
+        return self.start + self.src.global_offset, 0, 0
+
+    def global_ids(self, idx):
+        """Global cell ids of the chunk-local indices ``idx`` (torch tensor)."""
+        return idx + (self.start + self.src.global_offset)
+
+
+class ShardedChunk(ArrayChunk):
+    """One rank's block-cyclic share of an ArrayDataSource gathered into a single chunk: the rank
+    owns blocks ``rank, rank + size, ...`` of ``block`` cells (``parallel.shard_bounds``), so the
+    photon-rich core of a cluster is spread over all ranks.  Cells keep their global ids (RNG
+    counters are keyed by them), which is what makes an N-rank run reproduce the 1-rank run."""
+
+    def __init__(self, src, block, rank, size):
+        super().__init__(src, 0, src.size)
+        self.block, self.rank, self.nranks = int(block), int(rank), int(size)
+        n, b, s, r = src.size, self.block, self.nranks, self.rank
+        self._nfull = n // (b * s)                       # complete rounds of s blocks
+        t0 = self._nfull * b * s + r * b                 # this rank's block of the last, partial round
+        self._tail = (t0, min(t0 + b, n)) if t0 < n else None
+        self._cache = {}
+
+    @property
+    def size(self):
+        return self._nfull * self.block + (self._tail[1] - self._tail[0] if self._tail else 0)
+
+    def __getitem__(self, field):
+        if field in self._cache:
+            return self._cache[field]
+        v = self.src.fields[field]
+        b, s, r, nf = self.block, self.nranks, self.rank, self._nfull
+        head = v[: nf * b * s].reshape(nf, s, b)[:, r, :].reshape(-1)
+        if self._tail is not None:
+            tail = v[self._tail[0]:self._tail[1]]
+            if not isinstance(v, np.ndarray) and hasattr(v, "device"):     # torch tensor
+                import torch
+
+                head = torch.cat([head, tail])
+            else:
+                head = np.concatenate([head, tail])
+        self._cache[field] = head
+        return head
+
+    def id_map(self):
+        return self.src.global_offset + self.rank * self.block, self.block, self.block * self.nranks
+
+    def global_ids(self, idx):
+        id0, blk, stride = self.id_map()
+        return id0 + (idx // blk) * stride + idx % blk
+
 
 class ArrayDataSource:
     """Array-backed data object (cells or particles).
@@ -123,7 +175,8 @@ class ArrayDataSource:
                  domain_right_edge=None, periodicity=(False, False, False), left_edge=None,
                  right_edge=None, center=None, position_fields=None, velocity_fields=None,
                  width_field="default", units=None, chunk_size=None, cosmology=None,
-                 name="ArrayDataSource", ftype="gas", rank_local=False, global_offset=0):
+                 name="ArrayDataSource", ftype="gas", rank_local=False, global_offset=0,
+                 shard_block=4096):
         self.fields = dict(fields)
         self.units = dict(units or {})
         self.data_type = data_type
@@ -170,14 +223,24 @@ class ArrayDataSource:
         # over ranks again); global_offset: global id of its first cell (RNG counters)
         self.rank_local = rank_local
         self.global_offset = int(global_offset)
+        # cells per block of the block-cyclic split used when several ranks share this object
+        self.shard_block = int(shard_block)
 
     def chunks(self, rank=0, size=1):
-        """Yield chunks; with ``size`` > 1 chunks are dealt round-robin over ranks like yt's
-        ``parallel_objects`` (photon_list.py:401)."""
-        cs = self.chunk_size or self.size
-        starts = list(range(0, self.size, cs)) or [0]
+        """Yield this rank's chunks.  With ``size`` > 1 the cells are split block-cyclically over
+        the ranks: with a ``chunk_size`` the chunks are dealt round-robin like yt's
+        ``parallel_objects`` (photon_list.py:401), i.e. blocks of ``chunk_size`` cells; without one
+        the rank's blocks of ``shard_block`` cells are gathered into ONE chunk so the kernels
+        still see a large batch.  ``rank_local`` objects already hold only this rank's share."""
         if self.rank_local:
             rank, size = 0, 1
+        if size > 1 and not self.chunk_size:
+            ch = ShardedChunk(self, self.shard_block, rank, size)
+            if ch.size > 0:
+                yield ch
+            return
+        cs = self.chunk_size or self.size
+        starts = list(range(0, self.size, cs)) or [0]
         for j, s in enumerate(starts):
             if j % size == rank:
                 yield ArrayChunk(self, s, min(s + cs, self.size))

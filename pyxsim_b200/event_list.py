@@ -341,9 +341,12 @@ def validate_parameters(first, second, skip=()):
             continue
         v1, v2 = first[k], second[k]
         if isinstance(v1, (str, bytes)) or isinstance(v2, (str, bytes)):
-            ok = str(v1) == str(v2)
+            ok = _as_str(v1) == _as_str(v2)
         elif np.shape(v1) != np.shape(v2):
             ok = False
+        elif np.asarray(v1).dtype.kind in "SUO" or np.asarray(v2).dtype.kind in "SUO":
+            # string arrays (velocity_fields): utils.py:79-83 compares them with np.char.equal
+            ok = np.array_equal(np.asarray(v1).astype("U"), np.asarray(v2).astype("U"))
         else:
             ok = np.allclose(np.array(v1, "float64"), np.array(v2, "float64"), rtol=0.0, atol=1.0e-10)
         if not ok:
@@ -351,10 +354,22 @@ def validate_parameters(first, second, skip=()):
                                f"({v1} vs. {v2})!")
 
 
+def _as_str(v):
+    return v.decode() if isinstance(v, bytes) else str(v)
+
+
+# per-list summaries of an event list (photon_list.py:816-820): they differ between any two
+# real lists, so they are not compared but recomputed for the merged list.  (In the reference the
+# value check can never fire -- see validate_parameters -- so merging such lists works there and
+# the merged file silently keeps the first list's flux/emin/emax.)
+_DERIVED = ("flux", "emin", "emax")
+
+
 def merge_files(input_files, output_file, overwrite=False, add_exposure_times=False):
     """Merge photon or event lists (utils.py:92-173): every parameter except the exposure time
-    must agree; exposure times are added (``add_exposure_times``) or their maximum is kept; the
-    ``/data`` arrays are concatenated in input order (on the device for ``"mem:"`` lists)."""
+    (and an event list's derived flux/emin/emax, which are recomputed) must agree; exposure times
+    are added (``add_exposure_times``) or their maximum is kept; the ``/data`` arrays are
+    concatenated in input order (on the device for ``"mem:"`` lists)."""
     out_base = _strip(output_file)
     if not out_base.startswith("mem:") and not overwrite and \
             (os.path.exists(out_base + ".h5") or os.path.exists(out_base + ".npz")):
@@ -363,7 +378,7 @@ def merge_files(input_files, output_file, overwrite=False, add_exposure_times=Fa
     lists = [load_list(f if f.startswith("mem:") else _strip(f)) for f in input_files]
     first = lists[0]
     exp_time_key = next((k for k in first.parameters if k.endswith("exp_time")), "")
-    skip = [exp_time_key] if add_exposure_times else []
+    skip = ([exp_time_key] if add_exposure_times else []) + list(_DERIVED)
     for lst in lists[1:]:
         validate_parameters(first.parameters, lst.parameters, skip=skip)
     params = {k: v for k, v in first.parameters.items() if k != exp_time_key}
@@ -384,4 +399,13 @@ def merge_files(input_files, output_file, overwrite=False, add_exposure_times=Fa
         else:
             data[k] = np.concatenate([p.cpu().numpy() if isinstance(p, torch.Tensor) else np.asarray(p)
                                       for p in parts])
+    if "eobs" in data and all(k in params for k in _DERIVED):
+        e = data["eobs"]
+        n = int(e.shape[0])
+        if n == 0:
+            params.update(flux=0.0, emin=1.0e99, emax=-1.0e99)
+        else:
+            area = float(params["area"])
+            params.update(flux=float(e.sum()) * 1.602176634e-9 / tot / area, emin=float(e.min()),
+                          emax=float(e.max()))
     return save_list(out_base, DeviceList(info, params, data))

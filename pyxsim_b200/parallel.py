@@ -28,7 +28,8 @@ def init_from_env(backend=None):
     WORLD_SIZE is unset or 1).  Binds this process to ``cuda:LOCAL_RANK`` when CUDA exists."""
     ws = int(os.environ.get("WORLD_SIZE", "1"))
     if torch.cuda.is_available():
-        torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
+        # more ranks than GPUs (tests on a one-GPU box): ranks share devices round-robin
+        torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")) % torch.cuda.device_count())
     if ws <= 1 or is_initialized():
         return
     if backend is None:

@@ -17,7 +17,7 @@ import numpy as np
 import torch
 
 from . import _lib, constants as K, parallel
-from .data import ArrayDataSource, Cosmology
+from .data import ArrayChunk, ArrayDataSource, Cosmology
 from .device import empty, ptr, stream_ptr, to_device, require_cuda
 from .internal_absorption import column_density_at_cells, read_column_file
 from .profiling import stage
@@ -84,6 +84,8 @@ def save_list(prefix, lst):
                 g.attrs[k] = v
             p = f.create_group("parameters")
             for k, v in host.parameters.items():
+                if isinstance(v, np.ndarray) and v.dtype.kind == "U":
+                    v = v.astype("S")      # h5py cannot store NumPy unicode arrays
                 p.create_dataset(k, data=v)
             d = f.create_group("data")
             for k, v in host.data.items():
@@ -288,7 +290,9 @@ def make_photons(photon_prefix, data_source, redshift, area, exp_time, source_mo
     if velocity_fields is not None:
         v_fields = velocity_fields
     parameters["data_type"] = data_type
-    parameters["velocity_fields"] = np.array([str(f) for f in v_fields])
+    # stored like the reference does (photon_list.py:371): a byte-string array, shape (3, 2) for
+    # (ftype, name) tuples -- h5py has no conversion path for NumPy unicode arrays
+    parameters["velocity_fields"] = np.array(v_fields).astype("S")
     source_model.set_pv(p_fields, v_fields, le=le, re=re, dw=dw, c=c, periodicity=periodicity,
                         observer=observer)
 
@@ -296,13 +300,25 @@ def make_photons(photon_prefix, data_source, redshift, area, exp_time, source_mo
     native = hasattr(source_model, "generate_chunk")
     pieces = []
     n_photons = n_cells = 0
+    host_cursor = 0          # running global cell id for host (reference-style) models on yt chunks
     for chunk in _chunks(data_source):
         if native:
             out = source_model.generate_chunk(chunk, spectral_norm, gather=gather)
         else:
             out = _generate_with_reference_model(source_model, chunk, spectral_norm, gather)
+            if not isinstance(chunk, ArrayChunk) and out is not None:
+                out._id0 = host_cursor
+                host_cursor += out._chunk_cells
         if out is None or out.n_photons == 0:
             continue
+        # global ids of the active cells: the projection keys its RNG counters by them, so the
+        # events of a cell do not depend on chunking or on the number of ranks
+        if native:
+            out.gid = source_model._global_ids(out.idx)
+        elif isinstance(chunk, ArrayChunk):
+            out.gid = chunk.global_ids(out.idx)
+        else:
+            out.gid = out.idx + out._id0
         if fields_to_keep:
             from .source_models import field_value
 
@@ -320,12 +336,13 @@ def make_photons(photon_prefix, data_source, redshift, area, exp_time, source_mo
     def cat(name):
         ts = [getattr(p, name) for p, _ in pieces]
         if not ts:
-            return empty(0, torch.int64 if name == "nph" else torch.float64)
+            return empty(0, torch.int64 if name in ("nph", "gid") else torch.float64)
         return ts[0] if len(ts) == 1 else torch.cat(ts)
 
     data = {k: cat(k) for k in ("x", "y", "z", "vx", "vy", "vz", "dx")}
     data["num_photons"] = cat("nph")
     data["energy"] = cat("energy")
+    data["cell_id"] = cat("gid") if pieces else empty(0, torch.int64)
     if fields_to_keep:
         for name in pieces[0][1] if pieces else []:
             data[name] = torch.cat([e[name] for _, e in pieces])
@@ -348,13 +365,18 @@ def _generate_with_reference_model(source_model, chunk, spectral_norm, gather):
     from .source_models import ChunkPhotons, field_value
 
     res = source_model.process_data("photons", chunk, spectral_norm)
+    n_chunk = int(np.prod(np.shape(field_value(chunk, gather["p_fields"][0], "kpc"))))
     if res is None:
-        return None
+        out = ChunkPhotons()
+        out.n_cells = out.n_photons = 0
+        out._chunk_cells = n_chunk
+        return out
     ncells, nph, idxs, energies = res
     idxs = np.asarray(idxs)
     if idxs.dtype == bool:
         idxs = np.where(idxs)[0]
     out = ChunkPhotons()
+    out._chunk_cells = n_chunk
     out.n_cells, out.n_photons = int(ncells), int(np.sum(nph))
     if out.n_photons == 0:
         return out
@@ -431,8 +453,9 @@ def _project_photons(obs, photon_prefix, event_prefix, normal, sky_center, absor
         absorb_model = absorb_models[absorb_model]
     if absorb_model is not None and isinstance(absorb_model, type):
         absorb_model = absorb_model(nH, abund_table=abund_table)
+    # (a ready-made instance is accepted too; it is never modified: ``nH`` travels in the
+    # parameter block)
     if absorb_model is not None and nH is not None:
-        absorb_model.nH = nH
         if parallel.rank() == 0:
             mylog.info("Foreground galactic absorption: using the %s model and nH = %g.",
                        absorb_model._name, nH)
@@ -467,15 +490,22 @@ def _project_photons(obs, photon_prefix, event_prefix, normal, sky_center, absor
         params["north_vector"] = np.asarray(north_vector, "float64")
     params["absoption_model"] = abs_model_name  # (sic) key spelled as in photon_list.py:626
     if absorb_model is not None:
-        params["nH"] = -1.0 if nH is None else nH
+        if nH is not None:           # (a column_file-only run has no foreground column to record)
+            params["nH"] = nH
         params["abund_table"] = abund_table
     if sigma_pos is not None:
         params["sigma_pos"] = sigma_pos
     params["kernel"] = kernel
     params["redshift"] = redshift
     info = dict(pyxsim_version=__version__, yt_version="n/a", soxs_version="n/a",
-                photon_file=_file_name(photon_prefix), filenames=_file_names(event_prefix))
+                photon_file=(_file_name(photon_prefix) if photon_prefix.startswith("mem:")
+                             else _file_name(photon_prefix) + ".h5"),
+                filenames=_file_names(event_prefix))
 
+    cell_id0 = 0
+    if "cell_id" not in d and parallel.size() > 1:      # (collective: every rank, photons or not)
+        per_rank = parallel.allgather_counts([n_cells])[:, 0].tolist()
+        cell_id0 = int(sum(per_rank[:parallel.rank()]))
     n_events = 0
     if n_photons == 0:
         mylog.warning("No photons are in file %s, so I am done.", photon_prefix)
@@ -489,6 +519,14 @@ def _project_photons(obs, photon_prefix, event_prefix, normal, sky_center, absor
         for k in ("x", "y", "z", "vx", "vy", "vz", "dx"):
             setattr(PL, k, dev[k].data_ptr())
         PL.energy = dev["energy"].data_ptr()
+        # RNG counters are keyed by the cells' GLOBAL ids.  Lists written by this package carry
+        # them; for any other list (the reference's) the rank's exclusive prefix of the active
+        # cell counts makes the keys distinct across ranks (the event-count all-gather of the
+        # reference's MPI mode, photon_list.py:826, applied to the cells).
+        cid = None
+        if "cell_id" in d:
+            cid = to_device(d["cell_id"], torch.int64)
+            PL.cell_id = cid.data_ptr()
 
         P = _lib.ProjectParams()
         P.observer = int(observer == "internal")
@@ -515,8 +553,7 @@ def _project_photons(obs, photon_prefix, event_prefix, normal, sky_center, absor
         keep = []
         if absorb_model is not None:
             keep = absorb_model._fill_params(P)
-            if nH is None:
-                P.nH = 0.0
+            P.nH = 0.0 if nH is None else float(nH)
         if column_file is not None:
             # photon_list.py:672-680: the cube is sampled at the cells' positions in the
             # (east, north, normal) frame of the Orientation, also for an on-axis normal
@@ -530,7 +567,9 @@ def _project_photons(obs, photon_prefix, event_prefix, normal, sky_center, absor
             P.nH_cell = nhc.data_ptr()
         P.oneplusz = 1.0 + redshift
         P.seed = seed
-        P.cell_id0 = 0
+        P.cell_id0 = cell_id0
+        P.single_pass = int(os.environ.get("PXB_PROJECT_MODE", "") == "fused")
+        P.generic_kernels = int(bool(os.environ.get("PXB_GENERIC_KERNELS")))
 
         need = C.c_int64()
         _lib.call("pxb_project_workspace_bytes", n_cells, n_photons, C.byref(need))
@@ -544,7 +583,7 @@ def _project_photons(obs, photon_prefix, event_prefix, normal, sky_center, absor
                       ptr(los), ptr(nev), ptr(stats), ptr(ws), need.value, stream_ptr())
         n_events = int(nev.cpu()[0])
         st = stats.cpu().numpy()
-        del keep, ws
+        del keep, ws, cid
         data = {"xsky": xsky[:n_events], "ysky": ysky[:n_events], "eobs": eobs[:n_events]}
         if save_los:
             data["los"] = los[:n_events]

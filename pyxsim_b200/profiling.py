@@ -8,20 +8,6 @@ import torch
 
 _enabled = False
 _records = []       # (name, start_event, stop_event)
-_launches = 0
-
-# kernels launched by each C-ABI entry point (see pyxsim_b200/csrc/*.cu host functions)
-KERNELS_PER_CALL = {
-    "pxb_thermal_counts": 2, "pxb_thermal_sample": 3, "pxb_thermal_spectra": 1,
-    "pxb_interp_spec": 1, "pxb_scan_counts": 3, "pxb_compact_cells": 1, "pxb_radius2": 1,
-    "pxb_powerlaw_counts": 1, "pxb_powerlaw_sample": 1, "pxb_line_counts": 1,
-    "pxb_line_sample": 1, "pxb_project": 8, "pxb_doppler_shift": 1, "pxb_pixel_to_cel": 1,
-    "pxb_absorb_transmission": 1,
-    "pxb_absorb_decide": 1,
-    "pxb_column_lookup": 1,
-    "pxb_cel_to_pixel": 1, "pxb_event_image": 1, "pxb_event_spectrum": 1,
-    "pxb_thermal_flux": 1,
-}
 
 
 def enable(flag=True):
@@ -31,19 +17,19 @@ def enable(flag=True):
 
 
 def reset():
-    global _records, _launches
+    global _records
     _records = []
-    _launches = 0
+    from . import _lib
 
-
-def count_call(name):
-    global _launches
-    if _enabled:
-        _launches += KERNELS_PER_CALL.get(name, 0)
+    _lib.launch_count_reset()
 
 
 def launches():
-    return _launches
+    """Kernels libpxb launched since ``enable``/``reset`` (counted inside the library at every
+    launch site, ``pxb_launch_count``)."""
+    from . import _lib
+
+    return _lib.launch_count()
 
 
 @contextlib.contextmanager

@@ -8,6 +8,7 @@ runs in libpxb on the GPU.  Only ``mode="photons"`` is implemented (the hot path
 spectrum / intensity / field modes are "next" rows.
 """
 import ctypes as C
+import os
 from numbers import Number, Real
 
 import numpy as np
@@ -40,7 +41,7 @@ class ChunkPhotons:
     """Device-resident result of one chunk: the photon list rows of its active cells."""
 
     __slots__ = ("n_cells", "n_photons", "idx", "nph", "poff", "energy", "x", "y", "z", "vx",
-                 "vy", "vz", "dx", "counts")
+                 "vy", "vz", "dx", "counts", "gid", "_id0", "_chunk_cells")
 
     def __init__(self):
         for s in self.__slots__:
@@ -119,12 +120,23 @@ class SourceModel:
         v = chunk[field]
         return int(np.prod(v.shape)) if hasattr(v, "shape") else len(v)
 
-    def _cell_id0(self, chunk, n):
+    def _cell_ids(self, Cs, chunk, n):
+        """Fill the global-id triple of a cells struct (cell_id0, id_block, id_stride): the RNG
+        counters of cell i are keyed by its GLOBAL id so results do not depend on chunking or on
+        how the dataset is sharded over ranks.  yt chunks get a running cursor."""
         if isinstance(chunk, ArrayChunk):
-            return chunk.start + chunk.src.global_offset
-        base = self._cell_cursor
-        self._cell_cursor += n
-        return base
+            Cs.cell_id0, Cs.id_block, Cs.id_stride = chunk.id_map()
+        else:
+            Cs.cell_id0, Cs.id_block, Cs.id_stride = self._cell_cursor, 0, 0
+            self._cell_cursor += n
+        self._last_id_map = (Cs.cell_id0, Cs.id_block, Cs.id_stride)
+
+    def _global_ids(self, idx):
+        """Global ids of the chunk-local active-cell indices ``idx`` of the chunk last processed."""
+        id0, blk, stride = self._last_id_map
+        if blk > 0:
+            return id0 + (idx // blk) * stride + idx % blk
+        return idx + id0
 
     def compute_radius(self, chunk):
         """r^2 in cm^2 on the device (sources.py:77-87)."""
@@ -497,7 +509,7 @@ class ThermalSourceModel(SourceModel):
         em = to_device(field_value(chunk, self.emission_measure_field, "cm**-3"))
         keep += [kT, em]
         Cs.ncell = kT.numel()
-        Cs.cell_id0 = self._cell_id0(chunk, Cs.ncell)
+        self._cell_ids(Cs, chunk, Cs.ncell)
         Cs.kT, Cs.em = kT.data_ptr(), em.data_ptr()
         if self.nh_field is not None:
             nH = to_device(field_value(chunk, self.nh_field, "cm**-3"))
@@ -547,6 +559,12 @@ class ThermalSourceModel(SourceModel):
         Cs.spectral_norm = float(spectral_norm)
         Cs.kT_min, Cs.kT_max = float(self.kT_min), float(self.kT_max)
         Cs.seed = self._seed
+        # diagnostic switches (read once per chunk on the host, never inside the library)
+        Cs.generic_kernels = int(bool(os.environ.get("PXB_GENERIC_KERNELS")))
+        if os.environ.get("PXB_NO_GENERAL_SPLIT"):
+            Cs.split_factor = -1
+        elif os.environ.get("PXB_SPLIT_FACTOR"):
+            Cs.split_factor = max(int(os.environ["PXB_SPLIT_FACTOR"]), 0)
         return Cs
 
     def expected_counts(self, chunk, spectral_norm):
@@ -582,10 +600,12 @@ class ThermalSourceModel(SourceModel):
         spec = torch.zeros(ebins.size - 1, dtype=torch.float64, device=eb.device)
         need = C.c_int64()
         _lib.call("pxb_thermal_spectrum_workspace_bytes", dm.handle, Cs.ncell, C.byref(need))
-        ws = torch.empty(need.value, dtype=torch.uint8, device=eb.device)
+        # (diagnostic switch: without a workspace the library takes the per-cell path everywhere)
+        ws = None if os.environ.get("PXB_SPECTRUM_PER_CELL") else \
+            torch.empty(need.value, dtype=torch.uint8, device=eb.device)
         with stage("thermal_spectrum"):
             _lib.call("pxb_thermal_spectrum", dm.handle, C.byref(Cs), ptr(shift), ebins.size - 1,
-                      ptr(eb), ptr(spec), ptr(ws), need.value, stream_ptr())
+                      ptr(eb), ptr(spec), ptr(ws), need.value if ws is not None else 0, stream_ptr())
         del ws
         return spec.cpu().numpy()
 
@@ -621,9 +641,11 @@ class ThermalSourceModel(SourceModel):
         out = empty(Cs.ncell)
         need = C.c_int64()
         _lib.call("pxb_thermal_band_workspace_bytes", Cs.ncell, C.byref(need))
-        ws = torch.empty(need.value, dtype=torch.uint8, device=out.device)
+        ws = None if os.environ.get("PXB_BAND_PER_CELL") else \
+            torch.empty(need.value, dtype=torch.uint8, device=out.device)
         _lib.call("pxb_thermal_band", dm.handle, C.byref(Cs), int(bool(energy)), C.c_double(emin),
-                  C.c_double(emax), ptr(shift), ptr(out), ptr(ws), need.value, stream_ptr())
+                  C.c_double(emax), ptr(shift), ptr(out), ptr(ws), need.value if ws is not None else 0,
+                  stream_ptr())
         del ws
         return out
 
@@ -767,7 +789,7 @@ class PowerLawSourceModel(SourceModel):
         lum = to_device(field_value(chunk, self.luminosity_field, "keV/s"))
         keep.append(lum)
         Cs.ncell = lum.numel()
-        Cs.cell_id0 = self._cell_id0(chunk, Cs.ncell)
+        self._cell_ids(Cs, chunk, Cs.ncell)
         Cs.lum = lum.data_ptr()
         if isinstance(self.alpha, Real):   # any real number (the reference mixes Number/float)
             Cs.alpha_const = float(self.alpha)
@@ -873,7 +895,7 @@ class LineSourceModel(SourceModel):
         rate = to_device(field_value(chunk, self.emission_field, "photons/s"))
         keep.append(rate)
         Cs.ncell = rate.numel()
-        Cs.cell_id0 = self._cell_id0(chunk, Cs.ncell)
+        self._cell_ids(Cs, chunk, Cs.ncell)
         Cs.rate = rate.data_ptr()
         if self.sigma_field is None:
             Cs.sigma_const = float(self.sigma)

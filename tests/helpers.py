@@ -53,16 +53,13 @@ def ks_2samp_p(a, b):
     return ks_2samp(a, b).pvalue
 
 
-def assert_distributions_agree(run, seeds=((17, 5), (18, 6)), pmin=0.01):
-    """``run(seed_mine, seed_ref) -> {name: p-value}``.  Every comparison must reach
-    p > 0.01 (BASELINE.json north_star); a comparison that falls below gets ONE retry with
-    fresh, independent seeds and must pass then, which puts the false-alarm rate of a correct
-    implementation near 1e-4 per comparison instead of 1e-2 while a real discrepancy still
-    fails twice."""
+def assert_distributions_agree(run, seeds=((17, 5),), pmin=0.01):
+    """``run(seed_mine, seed_ref) -> {name: p-value}``: ONE run, one gate.  The family of m
+    comparisons a test makes must hold at the north_star's level p > 0.01 jointly, i.e. every
+    single comparison at the Bonferroni threshold 0.01 / m -- no retries, no second draw.  Power
+    comes from the sample sizes the callers choose (>= 1e5 photons per comparison), not from
+    repeated looks."""
     ps = run(*seeds[0])
-    bad = [k for k, v in ps.items() if not v > pmin]
-    if not bad:
-        return
-    ps2 = run(*seeds[1])
-    still = {k: (ps[k], ps2[k]) for k in bad if not ps2[k] > pmin}
-    assert not still, f"distributions disagree twice: {still}"
+    thr = pmin / max(len(ps), 1)
+    bad = {k: v for k, v in ps.items() if not v > thr}
+    assert not bad, f"distributions disagree (Bonferroni threshold {thr:.2e} over {len(ps)} comparisons): {bad}"

@@ -97,6 +97,54 @@ def test_shard_bounds_cover_everything():
     assert np.all(seen == 1)
 
 
+@pytest.mark.parametrize("n,block,size", [(100000, 4096, 4), (10, 4, 3), (4096 * 6, 4096, 2), (5, 8, 2)])
+def test_sharded_chunk_is_the_block_cyclic_share(n, block, size):
+    """ArrayDataSource.chunks(rank, size) without a chunk_size: ONE chunk per rank holding the
+    blocks parallel.shard_bounds assigns to it, with the global-id map the kernels use
+    (cell_id0 + (i // id_block) * id_stride + i % id_block)."""
+    import torch
+
+    x = np.arange(n, dtype="float64")
+    src = px.ArrayDataSource({("index", "x"): x, ("index", "y"): torch.arange(n, dtype=torch.float64),
+                              ("index", "z"): x}, shard_block=block, global_offset=1000)
+    seen = []
+    for r in range(size):
+        want = np.concatenate([np.arange(a, b) for a, b in parallel.shard_bounds(n, block=block, r=r, s=size)]
+                              or [np.array([], dtype=int)])
+        chunks = list(src.chunks(rank=r, size=size))
+        if want.size == 0:
+            assert chunks == []
+            continue
+        (ch,) = chunks
+        assert ch.size == want.size
+        np.testing.assert_array_equal(ch[("index", "x")], want.astype("float64"))
+        np.testing.assert_array_equal(ch[("index", "y")].numpy(), want.astype("float64"))
+        id0, blk, stride = ch.id_map()
+        i = np.arange(ch.size)
+        np.testing.assert_array_equal(id0 + (i // blk) * stride + i % blk, want + 1000)
+        np.testing.assert_array_equal(ch.global_ids(torch.arange(ch.size)).numpy(), want + 1000)
+        seen.append(want)
+    assert np.array_equal(np.sort(np.concatenate(seen)), np.arange(n))
+    # with a chunk_size the chunks are dealt round-robin (blocks of chunk_size cells)
+    src.chunk_size = block
+    got = [(c.start, c.stop) for c in src.chunks(rank=1, size=size)]
+    assert got == parallel.shard_bounds(n, block=block, r=1, s=size)
+    assert all(c.id_map() == (c.start + 1000, 0, 0) for c in src.chunks(rank=1, size=size))
+
+
+def test_merge_validation_handles_string_arrays_and_derived_keys():
+    """velocity_fields is a byte-string array; flux/emin/emax differ between any two
+    real event lists and must not block a merge (they are recomputed)."""
+    from pyxsim_b200 import event_list as E
+
+    vf = np.array([("gas", "velocity_x"), ("gas", "velocity_y"), ("gas", "velocity_z")]).astype("S")
+    a = dict(fid_exp_time=1.0, velocity_fields=vf, data_type="cells")
+    b = dict(fid_exp_time=1.0, velocity_fields=vf.astype("U"), data_type=b"cells")
+    E.validate_parameters(a, b)
+    with pytest.raises(RuntimeError):
+        E.validate_parameters(a, dict(b, velocity_fields=vf[::-1].copy()))
+
+
 def test_absorb_model_registry():
     assert set(px.absorb_models) == {"wabs", "tbabs"}
     m = px.WabsModel(0.1)

@@ -146,6 +146,63 @@ def test_fits_writers_and_merge(cuda, oracle, tmp_path):
     assert px.EventList("mem:ev_ac").parameters["exp_time"] == 1.5e5
 
 
+def test_merge_real_photon_and_event_lists(cuda, tmp_path):
+    """merge two lists as make_photons / project_photons actually write them --
+    per-list flux/emin/emax differ (recomputed for the merged list), velocity_fields is a
+    byte-string array."""
+    from pyxsim_b200 import synthetic
+
+    kT_nodes, ebins, cosmic, metal, _ = synthetic.apec_like_tables(nT=36, nbins=300)
+    src = synthetic.beta_model_source(12, kT_range=(2.0, 8.0), v3d_sigma_kms=200.0)
+    sm = px.ThermalSpectralModel(ebins, kT_nodes, cosmic, metal)
+    names = []
+    for j, mem in enumerate((True, True, False, False)):
+        model = px.ThermalSourceModel(sm, 0.1, 10.0, 300, 0.3, temperature_field=("gas", "kT"), prng=40 + j)
+        ph = f"mem:mg_ph{j}" if mem else str(tmp_path / f"ph{j}")
+        ev = f"mem:mg_ev{j}" if mem else str(tmp_path / f"ev{j}")
+        px.make_photons(ph, src, 0.05, 3.0e4, 1.0e5, model)
+        px.project_photons(ph, ev, "z", [30.0, 45.0], absorb_model="wabs", nH=0.02, prng=60 + j)
+        names.append((ph, ev))
+    for a, b, out in ((0, 1, "mem:mg"), (2, 3, str(tmp_path / "mg"))):
+        px.merge_files([names[a][0], names[b][0]], out + "_ph")
+        px.merge_files([names[a][1], names[b][1]], out + "_ev")
+        pa, pb, pm = (px.load_list(n) for n in (names[a][0], names[b][0], out + "_ph"))
+        assert pm.numpy("energy").size == pa.numpy("energy").size + pb.numpy("energy").size
+        assert np.array_equal(pm.numpy("num_photons"), np.concatenate([pa.numpy("num_photons"), pb.numpy("num_photons")]))
+        ea, eb, em = (px.load_list(n) for n in (names[a][1], names[b][1], out + "_ev"))
+        assert float(ea.parameters["flux"]) != float(eb.parameters["flux"])
+        e = np.concatenate([ea.numpy("eobs"), eb.numpy("eobs")])
+        assert np.array_equal(em.numpy("eobs"), e)
+        assert float(em.parameters["emin"]) == e.min() and float(em.parameters["emax"]) == e.max()
+        np.testing.assert_allclose(float(em.parameters["flux"]), e.sum() * 1.602176634e-9 / 1.0e5 / 3.0e4, rtol=1e-12)
+    # a projected list does not record a foreground column it did not use, and names its photon file
+    px.project_photons(names[2][0], str(tmp_path / "ev_nonh"), "z", [30.0, 45.0], prng=1)
+    lst = px.load_list(str(tmp_path / "ev_nonh"))
+    assert "nH" not in lst.parameters and str(lst.info["photon_file"]).endswith("ph2.h5")
+    w = px.WabsModel(0.3)
+    px.project_photons(names[0][0], "mem:mg_inst", "z", [30.0, 45.0], absorb_model=w, nH=0.02, prng=60)
+    assert w.nH == 0.3                                    # a user's instance is not modified
+    assert np.array_equal(px.load_list("mem:mg_inst").numpy("eobs"), px.load_list(names[0][1]).numpy("eobs"))
+
+
+def test_h5py_roundtrip_when_available(cuda, tmp_path):
+    """With a real h5py the lists are HDF5 files in the reference's schema (velocity_fields as a
+    byte-string array, photon_list.py:371)."""
+    h5py = pytest.importorskip("h5py")
+    from pyxsim_b200 import synthetic
+
+    kT_nodes, ebins, cosmic, metal, _ = synthetic.apec_like_tables(nT=36, nbins=300)
+    src = synthetic.beta_model_source(8, kT_range=(2.0, 8.0))
+    sm = px.ThermalSpectralModel(ebins, kT_nodes, cosmic, metal)
+    model = px.ThermalSourceModel(sm, 0.1, 10.0, 300, 0.3, temperature_field=("gas", "kT"), prng=4)
+    px.make_photons(str(tmp_path / "p.h5"), src, 0.05, 3.0e4, 1.0e5, model)
+    with h5py.File(tmp_path / "p.h5", "r") as f:
+        assert f["parameters"]["velocity_fields"].shape == (3, 2)
+        assert f["parameters"]["velocity_fields"].dtype.kind == "S"
+    n = px.project_photons(str(tmp_path / "p"), str(tmp_path / "e"), "z", [30.0, 45.0], prng=5)
+    assert n == px.load_list(str(tmp_path / "p")).numpy("energy").size
+
+
 def test_region_filters(cuda):
     d, p = _events(n=60000, name="ev_flt", seed=8)
     ev = px.EventList("mem:ev_flt")
