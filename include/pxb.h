@@ -42,6 +42,7 @@
  *                                 pyxsim/event_list.py:106-134,254-318,344-349
  *   pxb_column_lookup ........... nH cube interpolation at the rotated cell centres,
  *                                 photon_list.py:672-680 (scipy interpn, linear, fill 0)
+ *   pxb_make_events ............. both stages fused: base.py:462-492 -> photon_list.py:686-799
  *   pxb_project ................. the projection tile loop, photon_list.py:686-799:
  *                                 doppler_shift + absorb_photons (spectral_models.py:563-583)
  *                                 + scatter_events (sky_functions.pyx:40-147) or
@@ -182,18 +183,24 @@ int pxb_interp_spec(const pxb_model* model, int64_t n, const double* x_vals,
                     double* c_out, double* m_out, double* v_out, void* stream);
 
 /* Inverse-CDF energy sampling for the active cells.  idx[k] is the chunk-local cell index,
- * nph[k] its photon count, poff[k] its first slot in `energies` (poff has n_active+1 entries).
+ * nph[k] its photon count, poff[k] its first slot in `energies`, qoff[k] its first photon PAIR
+ * (both have n_active+1 entries; pxb_scan_counts / pxb_compact_cells produce them).
  * Two device paths with the same output distribution: cells whose tables, abundances and
- * interpolation weights are all non-negative are sampled as a mixture of per-row CDFs
- * (thread per photon); every other cell gets its own blended + clipped CDF in shared memory
+ * interpolation weights are all non-negative are sampled as a mixture of per-row alias tables
+ * (thread per photon pair); every other cell gets its own blended + clipped CDF in shared memory
  * (CTA per cell).  The order of the photons inside a cell is not a contract (the reference
  * sorts its uniforms, base.py:481). */
 int pxb_thermal_sample_workspace_bytes(const pxb_model* model, int64_t n_active,
-                                       int64_t n_photons, int64_t* bytes);
+                                       int64_t n_pairs, int64_t* bytes);
 int pxb_thermal_sample(const pxb_model* model, const pxb_thermal_cells* cells,
                        int64_t n_active, const int64_t* idx, const int64_t* nph,
-                       const int64_t* poff, int64_t n_photons, double* energies,
-                       void* workspace, int64_t workspace_bytes, void* stream);
+                       const int64_t* poff, const int64_t* qoff, int64_t n_photons,
+                       int64_t n_pairs, double* energies, void* workspace,
+                       int64_t workspace_bytes, void* stream);
+/* Diagnostic, host only (no GPU needed): the Walker alias table libpxb builds for one table row
+ * (bin j is produced directly with probability thr[j] / 2^32 / nbins and as the alternative of
+ * every bin k with other[k] == j), so a CPU test can check the implied bin probabilities. */
+int pxb_alias_table_host(const double* row, int nbins, uint32_t* thr_out, uint32_t* other_out);
 
 /* ------------------------------------------------------------------------------------
  * Spectrum / band modes ("next" row f1 of the scope table)
@@ -260,9 +267,11 @@ int pxb_shift_factor(int64_t n, const double* vx, const double* vy, const double
  * ---------------------------------------------------------------------------------- */
 int pxb_scan_workspace_bytes(int64_t n, int64_t* bytes);
 /* offsets[n+1]: exclusive prefix of counts; arank[n+1]: exclusive prefix of (counts>0);
- * totals[2] (device) = {sum(counts), number of active cells}. */
+ * pairoff[n+1]: exclusive prefix of ceil(counts/2) (photon pairs: the unit of work of the photon
+ * kernels); totals[3] (device) = {sum(counts), number of active cells, number of pairs}. */
 int pxb_scan_counts(const int64_t* counts, int64_t n, int64_t* offsets, int64_t* arank,
-                    int64_t* totals, void* workspace, int64_t workspace_bytes, void* stream);
+                    int64_t* pairoff, int64_t* totals, void* workspace, int64_t workspace_bytes,
+                    void* stream);
 
 typedef struct {
   double c[3];        /* centre, kpc */
@@ -275,11 +284,11 @@ typedef struct {
 /* Gather the active cells: idx/nph/poff plus recentred, periodically unwrapped positions
  * (photon_list.py:423-451) and bulk-subtracted velocities.  dx may be NULL (point sources). */
 int pxb_compact_cells(int64_t n, const int64_t* counts, const int64_t* offsets,
-                      const int64_t* arank, const double* x, const double* y, const double* z,
-                      const double* vx, const double* vy, const double* vz, const double* dx,
-                      const pxb_geometry* geom, int64_t* idx_out, int64_t* nph_out,
-                      int64_t* poff_out, double* xo, double* yo, double* zo, double* vxo,
-                      double* vyo, double* vzo, double* dxo, void* stream);
+                      const int64_t* arank, const int64_t* pairoff, const double* x, const double* y,
+                      const double* z, const double* vx, const double* vy, const double* vz,
+                      const double* dx, const pxb_geometry* geom, int64_t* idx_out,
+                      int64_t* nph_out, int64_t* poff_out, int64_t* qoff_out, double* xo, double* yo,
+                      double* zo, double* vxo, double* vyo, double* vzo, double* dxo, void* stream);
 
 /* r2[i] = |pos - c|^2 * cm2_per_kpc2 with periodic unwrap (sources.py:77-87). */
 int pxb_radius2(int64_t n, const double* x, const double* y, const double* z,
@@ -344,8 +353,11 @@ int pxb_rng_binomial(int64_t n, double p, uint64_t seed, int64_t count, int64_t*
 typedef struct {
   int64_t n_cells;
   int64_t n_photons;
-  const int64_t* nph;    /* [n_cells] */
+  int64_t n_pairs;       /* sum over cells of ceil(nph / 2) == qoff[n_cells] */
+  const int64_t* nph;    /* [n_cells] (may be NULL: poff carries the counts) */
   const int64_t* poff;   /* [n_cells+1] exclusive offsets into energy */
+  const int64_t* qoff;   /* [n_cells+1] exclusive prefix of ceil(nph / 2): the photon kernels walk
+                            the photons of a cell in pairs (pxb_scan_counts produces it) */
   const double* x;       /* kpc, centred */
   const double* y;
   const double* z;
@@ -353,7 +365,7 @@ typedef struct {
   const double* vy;
   const double* vz;
   const double* dx;      /* kpc (cell width or smoothing length) */
-  const double* energy;  /* [n_photons] keV */
+  const double* energy;  /* [n_photons] keV (NULL for pxb_make_events) */
   const int64_t* cell_id; /* [n_cells] global id of every active cell (keys the projection's RNG
                              counters, so the events of a cell do not depend on how the dataset was
                              chunked or sharded over ranks), or NULL -> params.cell_id0 + c */
@@ -372,9 +384,7 @@ typedef struct {
   int32_t save_los;
   int32_t absorb_kind;   /* PXB_ABS_* */
   int32_t has_sigma_pos;
-  int32_t single_pass;   /* 0 (default): detect -> scan -> emit; 1: one pass with a decoupled
-                            look-back over per-tile counts (DRAM traffic == algorithmic bytes);
-                            identical event list either way */
+  int32_t reserved;
   double sigma_pos;
   double x_hat[3], y_hat[3], z_hat[3];
   double D_A_kpc;
@@ -394,7 +404,7 @@ typedef struct {
   int64_t cell_id0;
 } pxb_project_params;
 
-int pxb_project_workspace_bytes(int64_t n_cells, int64_t n_photons, int64_t* bytes);
+int pxb_project_workspace_bytes(int64_t n_cells, int64_t n_pairs, int64_t* bytes);
 /* Outputs xsky/ysky/eobs (and los when save_los) must hold n_photons entries; the first
  * n_events are valid and keep the photon-list order (stable compaction).
  * n_events_out: device int64[1].  stats_out: device double[3] = {sum(eobs), min, max}. */
@@ -402,6 +412,22 @@ int pxb_project(const pxb_photon_list* photons, const pxb_project_params* params
                 double* xsky, double* ysky, double* eobs, double* los,
                 int64_t* n_events_out, double* stats_out, void* workspace,
                 int64_t workspace_bytes, void* stream);
+
+/* Generation and projection of a thermal source in ONE pass, without a photon list in between
+ * (the two reference stages base.py:462-492 -> photon_list.py:686-799 back to back): `photons`
+ * describes the active cells as pxb_compact_cells wrote them (energy = NULL), idx their
+ * chunk-local indices, cells/model the thermal source as for pxb_thermal_sample.  The events are
+ * bit for bit those of pxb_thermal_sample followed by pxb_project with the same seeds.
+ * n_declined_out (device int64[1]) receives the number of active cells the mixture sampler cannot
+ * take (extrapolating beyond the table, negative abundance): they produce NO events here, so a
+ * caller must fall back to the two-stage path when it is not zero.  Needs non-negative tables. */
+int pxb_make_events_workspace_bytes(const pxb_model* model, int64_t n_cells, int64_t n_pairs,
+                                    int64_t* bytes);
+int pxb_make_events(const pxb_model* model, const pxb_thermal_cells* cells, const int64_t* idx,
+                    const pxb_photon_list* photons, const pxb_project_params* params,
+                    double* xsky, double* ysky, double* eobs, double* los, int64_t* n_events_out,
+                    double* stats_out, int64_t* n_declined_out, void* workspace,
+                    int64_t workspace_bytes, void* stream);
 
 /* In-place Doppler shift with per-cell factors (sky_functions.pyx:20-34). */
 int pxb_doppler_shift(int64_t n_cells, const double* beta_n, const double* beta2,
@@ -429,6 +455,13 @@ int pxb_column_lookup(int64_t n_cells, const double* x, const double* y, const d
  * u on either side of the threshold and E on the wabs piece edges. */
 int pxb_absorb_decide(const pxb_project_params* params, int64_t n, const double* energy,
                       const double* u, uint8_t* survive_out, void* stream);
+/* Diagnostic: the decision as the photon kernels take it, from random WORDS.  The absorption
+ * uniform of photon i is U = (w[i] + w2 / 2^32) / 2^32, where w2 -- drawn only when w[i] alone
+ * does not decide -- is word 0 of Philox4x32-10(key = params->seed, counter = (draw0 + i,
+ * cell_key, stream 10)); survive_out[i] = (U < exp(-sigma(E_i) nH)). */
+int pxb_absorb_decide_words(const pxb_project_params* params, int64_t n, const double* energy,
+                            const uint32_t* w, uint64_t cell_key, uint64_t draw0,
+                            uint8_t* survive_out, void* stream);
 
 /* ------------------------------------------------------------------------------------
  * Event-list consumers (pyxsim/event_list.py)

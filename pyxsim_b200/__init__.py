@@ -15,6 +15,7 @@ from .photon_list import (
     DeviceList,
     drop_list,
     load_list,
+    make_events,
     make_photons,
     project_photons,
     project_photons_allsky,

@@ -90,8 +90,8 @@ class LineCells(C.Structure):
 
 class PhotonList(C.Structure):
     _fields_ = [
-        ("n_cells", C.c_int64), ("n_photons", C.c_int64),
-        ("nph", c_void_p), ("poff", c_void_p),
+        ("n_cells", C.c_int64), ("n_photons", C.c_int64), ("n_pairs", C.c_int64),
+        ("nph", c_void_p), ("poff", c_void_p), ("qoff", c_void_p),
         ("x", c_void_p), ("y", c_void_p), ("z", c_void_p),
         ("vx", c_void_p), ("vy", c_void_p), ("vz", c_void_p),
         ("dx", c_void_p), ("energy", c_void_p), ("cell_id", c_void_p),
@@ -103,7 +103,7 @@ class ProjectParams(C.Structure):
         ("observer", C.c_int32), ("data_type", C.c_int32), ("kernel", C.c_int32),
         ("no_shifting", C.c_int32), ("vn_axis", C.c_int32), ("sky_mode", C.c_int32),
         ("save_los", C.c_int32), ("absorb_kind", C.c_int32), ("has_sigma_pos", C.c_int32),
-        ("single_pass", C.c_int32),
+        ("reserved", C.c_int32),
         ("sigma_pos", C.c_double),
         ("x_hat", C.c_double * 3), ("y_hat", C.c_double * 3), ("z_hat", C.c_double * 3),
         ("D_A_kpc", C.c_double), ("sky_center", C.c_double * 2), ("nH", C.c_double),
@@ -142,7 +142,15 @@ SIGNATURES = {
                                   c_void_p, c_void_p, c_void_p, c_void_p]),
     "pxb_thermal_sample_workspace_bytes": (C.c_int, [c_void_p, C.c_int64, C.c_int64, _P(C.c_int64)]),
     "pxb_thermal_sample": (C.c_int, [c_void_p, _P(ThermalCells), C.c_int64, c_void_p, c_void_p,
-                                     c_void_p, C.c_int64, c_void_p, c_void_p, C.c_int64, c_void_p]),
+                                     c_void_p, c_void_p, C.c_int64, C.c_int64, c_void_p, c_void_p,
+                                     C.c_int64, c_void_p]),
+    "pxb_alias_table_host": (C.c_int, [c_void_p, C.c_int, c_void_p, c_void_p]),
+    "pxb_make_events_workspace_bytes": (C.c_int, [c_void_p, C.c_int64, C.c_int64, _P(C.c_int64)]),
+    "pxb_make_events": (C.c_int, [c_void_p, _P(ThermalCells), c_void_p, _P(PhotonList),
+                                  _P(ProjectParams), c_void_p, c_void_p, c_void_p, c_void_p,
+                                  c_void_p, c_void_p, c_void_p, c_void_p, C.c_int64, c_void_p]),
+    "pxb_absorb_decide_words": (C.c_int, [_P(ProjectParams), C.c_int64, c_void_p, c_void_p,
+                                          C.c_uint64, C.c_uint64, c_void_p, c_void_p]),
     "pxb_thermal_spectrum_workspace_bytes": (C.c_int, [c_void_p, C.c_int64, _P(C.c_int64)]),
     "pxb_thermal_spectrum": (C.c_int, [c_void_p, _P(ThermalCells), c_void_p, C.c_int64, c_void_p,
                                        c_void_p, c_void_p, C.c_int64, c_void_p]),
@@ -158,8 +166,8 @@ SIGNATURES = {
     "pxb_powerlaw_norm": (C.c_int, [_P(PowerlawCells), c_void_p, c_void_p, c_void_p]),
     "pxb_scan_workspace_bytes": (C.c_int, [C.c_int64, _P(C.c_int64)]),
     "pxb_scan_counts": (C.c_int, [c_void_p, C.c_int64, c_void_p, c_void_p, c_void_p, c_void_p,
-                                  C.c_int64, c_void_p]),
-    "pxb_compact_cells": (C.c_int, [C.c_int64] + [c_void_p] * 10 + [_P(Geometry)] + [c_void_p] * 11),
+                                  c_void_p, C.c_int64, c_void_p]),
+    "pxb_compact_cells": (C.c_int, [C.c_int64] + [c_void_p] * 11 + [_P(Geometry)] + [c_void_p] * 12),
     "pxb_radius2": (C.c_int, [C.c_int64, c_void_p, c_void_p, c_void_p, _P(Geometry), c_void_p,
                               c_void_p]),
     "pxb_powerlaw_counts": (C.c_int, [_P(PowerlawCells), c_void_p, c_void_p, c_void_p]),

@@ -73,6 +73,7 @@ enum PxbStream : uint32_t {
   STREAM_POWERLAW = 7,
   STREAM_LINE = 8,
   STREAM_SPLIT = 9,    // multinomial split of a cell's photons over its table rows
+  STREAM_PROJ_R = 10,  // low word of an absorption uniform whose top word does not decide
 };
 
 struct Philox4 {

@@ -10,23 +10,24 @@ constexpr int SCAN_THREADS = 256;
 constexpr int SCAN_ITEMS = 8;
 constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
 
-struct I64x2 { int64_t a, b; };  // (photons, active cells)
+struct I64x2 { int64_t a, b, c; };  // (photons, active cells, photon pairs)
 
 __device__ __forceinline__ I64x2 block_excl_scan(I64x2 v, I64x2& total) {
-  __shared__ int64_t sa[SCAN_THREADS / 32], sb[SCAN_THREADS / 32];
+  __shared__ int64_t sa[SCAN_THREADS / 32], sb[SCAN_THREADS / 32], sc[SCAN_THREADS / 32];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  int64_t ia = warp_incl_scan_i64(v.a, lane), ib = warp_incl_scan_i64(v.b, lane);
+  int64_t ia = warp_incl_scan_i64(v.a, lane), ib = warp_incl_scan_i64(v.b, lane),
+          ic = warp_incl_scan_i64(v.c, lane);
   __syncthreads();
-  if (lane == 31) { sa[wid] = ia; sb[wid] = ib; }
+  if (lane == 31) { sa[wid] = ia; sb[wid] = ib; sc[wid] = ic; }
   __syncthreads();
-  int64_t ba = 0, bb = 0, ta = 0, tb = 0;
+  int64_t ba = 0, bb = 0, bc = 0, ta = 0, tb = 0, tc = 0;
 #pragma unroll
   for (int w = 0; w < SCAN_THREADS / 32; ++w) {
-    if (w < wid) { ba += sa[w]; bb += sb[w]; }
-    ta += sa[w]; tb += sb[w];
+    if (w < wid) { ba += sa[w]; bb += sb[w]; bc += sc[w]; }
+    ta += sa[w]; tb += sb[w]; tc += sc[w];
   }
-  total = I64x2{ta, tb};
-  return I64x2{ba + ia - v.a, bb + ib - v.b};
+  total = I64x2{ta, tb, tc};
+  return I64x2{ba + ia - v.a, bb + ib - v.b, bc + ic - v.c};
 }
 
 __device__ __forceinline__ void load_items(const int64_t* __restrict__ counts, int64_t n,
@@ -46,72 +47,82 @@ __device__ __forceinline__ void load_items(const int64_t* __restrict__ counts, i
 
 __global__ void __launch_bounds__(SCAN_THREADS)
 k_scan_reduce(const int64_t* __restrict__ counts, int64_t n, int64_t* __restrict__ tile_ph,
-              int64_t* __restrict__ tile_act) {
+              int64_t* __restrict__ tile_act, int64_t* __restrict__ tile_pr) {
   const int64_t first = (int64_t)blockIdx.x * SCAN_TILE + (int64_t)threadIdx.x * SCAN_ITEMS;
   int64_t c[SCAN_ITEMS];
   load_items(counts, n, first, c);
-  I64x2 v{0, 0};
+  I64x2 v{0, 0, 0};
 #pragma unroll
-  for (int q = 0; q < SCAN_ITEMS; ++q) { v.a += c[q]; v.b += (c[q] > 0); }
+  for (int q = 0; q < SCAN_ITEMS; ++q) { v.a += c[q]; v.b += (c[q] > 0); v.c += (c[q] + 1) >> 1; }
   I64x2 tot;
   block_excl_scan(v, tot);
-  if (threadIdx.x == 0) { tile_ph[blockIdx.x] = tot.a; tile_act[blockIdx.x] = tot.b; }
+  if (threadIdx.x == 0) { tile_ph[blockIdx.x] = tot.a; tile_act[blockIdx.x] = tot.b; tile_pr[blockIdx.x] = tot.c; }
 }
 
 // single CTA: in-place exclusive scan of the per-tile sums; totals[0..1] = grand totals
 __global__ void __launch_bounds__(SCAN_THREADS)
-k_scan_tiles(int64_t* __restrict__ tile_ph, int64_t* __restrict__ tile_act, int64_t ntiles,
-             int64_t* __restrict__ totals) {
-  I64x2 carry{0, 0};
+k_scan_tiles(int64_t* __restrict__ tile_ph, int64_t* __restrict__ tile_act,
+             int64_t* __restrict__ tile_pr, int64_t ntiles, int64_t* __restrict__ totals) {
+  I64x2 carry{0, 0, 0};
   for (int64_t base = 0; base < ntiles; base += SCAN_THREADS) {
     const int64_t t = base + threadIdx.x;
-    I64x2 v{0, 0};
-    if (t < ntiles) { v.a = tile_ph[t]; v.b = tile_act[t]; }
+    I64x2 v{0, 0, 0};
+    if (t < ntiles) { v.a = tile_ph[t]; v.b = tile_act[t]; v.c = tile_pr[t]; }
     I64x2 tot;
     I64x2 ex = block_excl_scan(v, tot);
-    if (t < ntiles) { tile_ph[t] = carry.a + ex.a; tile_act[t] = carry.b + ex.b; }
-    carry.a += tot.a; carry.b += tot.b;
+    if (t < ntiles) { tile_ph[t] = carry.a + ex.a; tile_act[t] = carry.b + ex.b; tile_pr[t] = carry.c + ex.c; }
+    carry.a += tot.a; carry.b += tot.b; carry.c += tot.c;
   }
-  if (threadIdx.x == 0) { totals[0] = carry.a; totals[1] = carry.b; }
+  if (threadIdx.x == 0) { totals[0] = carry.a; totals[1] = carry.b; totals[2] = carry.c; }
 }
 
 __global__ void __launch_bounds__(SCAN_THREADS)
 k_scan_final(const int64_t* __restrict__ counts, int64_t n, const int64_t* __restrict__ tile_ph,
-             const int64_t* __restrict__ tile_act, int64_t* __restrict__ offsets,
-             int64_t* __restrict__ arank, const int64_t* __restrict__ totals) {
+             const int64_t* __restrict__ tile_act, const int64_t* __restrict__ tile_pr,
+             int64_t* __restrict__ offsets, int64_t* __restrict__ arank,
+             int64_t* __restrict__ pairoff, const int64_t* __restrict__ totals) {
   const int64_t first = (int64_t)blockIdx.x * SCAN_TILE + (int64_t)threadIdx.x * SCAN_ITEMS;
   int64_t c[SCAN_ITEMS];
   load_items(counts, n, first, c);
-  I64x2 v{0, 0};
+  I64x2 v{0, 0, 0};
 #pragma unroll
-  for (int q = 0; q < SCAN_ITEMS; ++q) { v.a += c[q]; v.b += (c[q] > 0); }
+  for (int q = 0; q < SCAN_ITEMS; ++q) { v.a += c[q]; v.b += (c[q] > 0); v.c += (c[q] + 1) >> 1; }
   I64x2 tot;
   I64x2 ex = block_excl_scan(v, tot);
-  int64_t a = tile_ph[blockIdx.x] + ex.a, b = tile_act[blockIdx.x] + ex.b;
+  int64_t a = tile_ph[blockIdx.x] + ex.a, b = tile_act[blockIdx.x] + ex.b, p = tile_pr[blockIdx.x] + ex.c;
 #pragma unroll
   for (int q = 0; q < SCAN_ITEMS; ++q) {
-    if (first + q < n) { offsets[first + q] = a; arank[first + q] = b; }
-    a += c[q]; b += (c[q] > 0);
+    if (first + q < n) {
+      offsets[first + q] = a;
+      arank[first + q] = b;
+      if (pairoff) pairoff[first + q] = p;
+    }
+    a += c[q]; b += (c[q] > 0); p += (c[q] + 1) >> 1;
   }
-  if (blockIdx.x == 0 && threadIdx.x == 0) { offsets[n] = totals[0]; arank[n] = totals[1]; }
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    offsets[n] = totals[0];
+    arank[n] = totals[1];
+    if (pairoff) pairoff[n] = totals[2];
+  }
 }
 
 extern "C" int pxb_scan_workspace_bytes(int64_t n, int64_t* bytes) {
   PXB_REQUIRE(bytes && n >= 0, "bad argument");
   const int64_t ntiles = (n + SCAN_TILE - 1) / SCAN_TILE;
-  *bytes = 2 * (ntiles + 1) * (int64_t)sizeof(int64_t);
+  *bytes = 3 * (ntiles + 1) * (int64_t)sizeof(int64_t);
   return PXB_OK;
 }
 
 extern "C" int pxb_scan_counts(const int64_t* counts, int64_t n, int64_t* offsets, int64_t* arank,
-                               int64_t* totals, void* workspace, int64_t workspace_bytes,
-                               void* stream) {
+                               int64_t* pairoff, int64_t* totals, void* workspace,
+                               int64_t workspace_bytes, void* stream) {
   PXB_REQUIRE(n >= 0 && offsets && arank && totals, "bad argument");
   cudaStream_t st = (cudaStream_t)stream;
   if (n == 0) {
-    PXB_CUDA(cudaMemsetAsync(totals, 0, 2 * sizeof(int64_t), st));
+    PXB_CUDA(cudaMemsetAsync(totals, 0, 3 * sizeof(int64_t), st));
     PXB_CUDA(cudaMemsetAsync(offsets, 0, sizeof(int64_t), st));
     PXB_CUDA(cudaMemsetAsync(arank, 0, sizeof(int64_t), st));
+    if (pairoff) PXB_CUDA(cudaMemsetAsync(pairoff, 0, sizeof(int64_t), st));
     return PXB_OK;
   }
   PXB_REQUIRE(counts, "counts is NULL");
@@ -124,12 +135,13 @@ extern "C" int pxb_scan_counts(const int64_t* counts, int64_t n, int64_t* offset
   PXB_REQUIRE(ntiles < (1LL << 31), "too many cells");
   int64_t* tile_ph = (int64_t*)workspace;
   int64_t* tile_act = tile_ph + ntiles + 1;
-  k_scan_reduce<<<(unsigned)ntiles, SCAN_THREADS, 0, st>>>(counts, n, tile_ph, tile_act);
+  int64_t* tile_pr = tile_act + ntiles + 1;
+  k_scan_reduce<<<(unsigned)ntiles, SCAN_THREADS, 0, st>>>(counts, n, tile_ph, tile_act, tile_pr);
   PXB_LAUNCH_CHECK();
-  k_scan_tiles<<<1, SCAN_THREADS, 0, st>>>(tile_ph, tile_act, ntiles, totals);
+  k_scan_tiles<<<1, SCAN_THREADS, 0, st>>>(tile_ph, tile_act, tile_pr, ntiles, totals);
   PXB_LAUNCH_CHECK();
-  k_scan_final<<<(unsigned)ntiles, SCAN_THREADS, 0, st>>>(counts, n, tile_ph, tile_act, offsets,
-                                                         arank, totals);
+  k_scan_final<<<(unsigned)ntiles, SCAN_THREADS, 0, st>>>(counts, n, tile_ph, tile_act, tile_pr,
+                                                         offsets, arank, pairoff, totals);
   PXB_LAUNCH_CHECK();
   return PXB_OK;
 }
@@ -148,7 +160,8 @@ __device__ __forceinline__ double unwrap(double pos, double dx, double le, doubl
 
 __global__ void __launch_bounds__(256)
 k_compact_cells(int64_t n, const int64_t* __restrict__ counts, const int64_t* __restrict__ offsets,
-                const int64_t* __restrict__ arank, const double* __restrict__ x,
+                const int64_t* __restrict__ arank, const int64_t* __restrict__ pairoff,
+                int64_t* __restrict__ qoff_out, const double* __restrict__ x,
                 const double* __restrict__ y, const double* __restrict__ z,
                 const double* __restrict__ vx, const double* __restrict__ vy,
                 const double* __restrict__ vz, const double* __restrict__ dx,
@@ -158,7 +171,10 @@ k_compact_cells(int64_t n, const int64_t* __restrict__ counts, const int64_t* __
                 double* __restrict__ vxo, double* __restrict__ vyo, double* __restrict__ vzo,
                 double* __restrict__ dxo) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i == 0) poff_out[arank[n]] = offsets[n];
+  if (i == 0) {
+    poff_out[arank[n]] = offsets[n];
+    if (qoff_out) qoff_out[arank[n]] = pairoff[n];
+  }
   if (i >= n) return;
   const int64_t c = ld_stream_i64(counts + i);
   if (c <= 0) return;
@@ -166,6 +182,7 @@ k_compact_cells(int64_t n, const int64_t* __restrict__ counts, const int64_t* __
   idx_out[k] = i;
   nph_out[k] = c;
   poff_out[k] = offsets[i];
+  if (qoff_out) qoff_out[k] = pairoff[i];
   const double w = dx ? dx[i] : 0.0;
   if (xo) {
     // NB the reference tests the *cell edge* against the object bounds (pos +/- dx)
@@ -182,20 +199,22 @@ k_compact_cells(int64_t n, const int64_t* __restrict__ counts, const int64_t* __
 }
 
 extern "C" int pxb_compact_cells(int64_t n, const int64_t* counts, const int64_t* offsets,
-                                 const int64_t* arank, const double* x, const double* y,
-                                 const double* z, const double* vx, const double* vy,
-                                 const double* vz, const double* dx, const pxb_geometry* geom,
-                                 int64_t* idx_out, int64_t* nph_out, int64_t* poff_out, double* xo,
-                                 double* yo, double* zo, double* vxo, double* vyo, double* vzo,
-                                 double* dxo, void* stream) {
+                                 const int64_t* arank, const int64_t* pairoff, const double* x,
+                                 const double* y, const double* z, const double* vx,
+                                 const double* vy, const double* vz, const double* dx,
+                                 const pxb_geometry* geom, int64_t* idx_out, int64_t* nph_out,
+                                 int64_t* poff_out, int64_t* qoff_out, double* xo, double* yo,
+                                 double* zo, double* vxo, double* vyo, double* vzo, double* dxo,
+                                 void* stream) {
+  PXB_REQUIRE(!qoff_out || pairoff, "qoff_out needs pairoff");
   PXB_REQUIRE(n >= 0 && offsets && arank && idx_out && nph_out && poff_out && geom, "bad argument");
   PXB_REQUIRE(!xo || (x && y && z && yo && zo), "position arrays incomplete");
   PXB_REQUIRE(!vxo || (vx && vy && vz && vyo && vzo), "velocity arrays incomplete");
   const int64_t blocks = n == 0 ? 1 : (n + 255) / 256;
   PXB_REQUIRE(n == 0 || counts, "counts is NULL");
   k_compact_cells<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
-      n, counts, offsets, arank, x, y, z, vx, vy, vz, dx, *geom, idx_out, nph_out, poff_out, xo, yo,
-      zo, vxo, vyo, vzo, dxo);
+      n, counts, offsets, arank, pairoff, qoff_out, x, y, z, vx, vy, vz, dx, *geom, idx_out, nph_out,
+      poff_out, xo, yo, zo, vxo, vyo, vzo, dxo);
   PXB_LAUNCH_CHECK();
   return PXB_OK;
 }

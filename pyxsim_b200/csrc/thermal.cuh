@@ -22,12 +22,13 @@ struct DevTable {
   const double* rs_c;     // row sums [nrows]
   const double* rs_m;
   const double* rs_v;     // [nvar, nrows]
-  // mixture fast path (only when nonneg): per-row normalised CDFs [(2+nvar), nrows, nbins+1]
-  // (table order cosmic, metal, var_0..) and guide tables [(2+nvar), nrows, nbins]:
-  // guide[k] = bin holding the quantile k/nbins.
-  const double* rowcdf;    // row stride cdf_stride doubles (even: rows are 16-byte aligned for TMA)
-  const uint16_t* guide;   // row stride guide_stride entries (multiple of 8)
-  int cdf_stride, guide_stride;
+  // mixture fast path (only when nonneg): one Walker alias table per table row,
+  // [(2+nvar), nrows, alias_stride] (table order cosmic, metal, var_0..).  Entry j = {thr, other}:
+  // a 64-bit uniform u picks bin j = floor(u nbins / 2^64); the top 32 bits of the remaining
+  // fraction are compared with thr -- below: bin j, else bin `other`; the low 32 bits are the
+  // position inside the chosen bin.  No search, no data-dependent loop.
+  const uint2* alias;      // row stride alias_stride entries (even: rows are 16-byte multiples for TMA)
+  int alias_stride;
   // band sums in O(1) (only when nonneg): unnormalised prefix sums over the bins of every row,
   // pre_n[tab][row][j] = sum_{q<j} T[q], pre_e[...] = sum_{q<j} emid_q T[q]; [(2+nvar), nrows, nbins+1]
   const double* pre_n;
@@ -134,3 +135,31 @@ __device__ __forceinline__ double cell_norm(const pxb_thermal_cells& C, int64_t 
   if (C.r2) cnm /= ld_stream(C.r2 + i);
   return cnm;
 }
+
+__device__ __forceinline__ double tot_bin(const CellMix& mx, double Z, const double* eZ,
+                                          int nvar, int j) {
+  const DevTable* t = mx.t;
+  const int nb = t->nbins;
+  double c = 0.0, m = 0.0;
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    if (r < mx.nr) {
+      const size_t o = (size_t)mx.row[r] * nb + j;
+      c += __ldg(t->cosmic + o) * mx.w[r];
+      m += __ldg(t->metal + o) * mx.w[r];
+    }
+  }
+  double tot = c + Z * m;
+  for (int k = 0; k < nvar; ++k) {
+    double v = 0.0;
+    const double* vt = t->var + (size_t)k * t->nrows * nb;
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+      if (r < mx.nr) v += __ldg(vt + (size_t)mx.row[r] * nb + j) * mx.w[r];
+    tot += eZ[k] * v;
+  }
+  return fmax(tot, 0.0);
+}
+
+// host: argument checks shared by every entry point that takes (model, cells)
+int pxb_check_cells(const pxb_model* model, const pxb_thermal_cells* c);

@@ -203,14 +203,14 @@ def _chunks(data_source):
     return (c for j, c in enumerate(citer) if j % parallel.size() == parallel.rank())
 
 
-def make_photons(photon_prefix, data_source, redshift, area, exp_time, source_model,
-                 point_sources=False, parameters=None, center=None, dist=None, cosmology=None,
-                 velocity_fields=None, bulk_velocity=None, observer="external",
-                 fields_to_keep=None):
-    """Generate a photon list; signature and return value of pyxsim.make_photons
-    (photon_list.py:111-127,478): returns ``(n_photons, n_cells)`` summed over ranks."""
-    require_cuda()
-    photon_prefix = _strip(photon_prefix)
+class _Generation:
+    """What make_photons derives from its arguments before it touches a chunk
+    (photon_list.py:214-343): distance / redshift rules, centre, the ``parameters`` group of the
+    photon list, ``spectral_norm``, the fields to gather; the source model is set up."""
+
+
+def _setup_generation(data_source, redshift, area, exp_time, source_model, point_sources,
+                      parameters, center, dist, cosmology, velocity_fields, bulk_velocity, observer):
     is_array = isinstance(data_source, ArrayDataSource)
     ds = data_source if is_array else data_source.ds
     parameters = dict(parameters or {})
@@ -296,7 +296,25 @@ def make_photons(photon_prefix, data_source, redshift, area, exp_time, source_mo
     source_model.set_pv(p_fields, v_fields, le=le, re=re, dw=dw, c=c, periodicity=periodicity,
                         observer=observer)
 
-    gather = dict(p_fields=p_fields, v_fields=v_fields, w_field=w_field, bulk_velocity=bulk_velocity)
+    G = _Generation()
+    G.ds, G.parameters, G.spectral_norm, G.data_type = ds, parameters, spectral_norm, data_type
+    G.redshift, G.D_A_mpc, G.observer = redshift, D_A_mpc, observer
+    G.exp_time, G.area = exp_time_s, area_cm2
+    G.gather = dict(p_fields=p_fields, v_fields=v_fields, w_field=w_field, bulk_velocity=bulk_velocity)
+    return G
+
+
+def make_photons(photon_prefix, data_source, redshift, area, exp_time, source_model,
+                 point_sources=False, parameters=None, center=None, dist=None, cosmology=None,
+                 velocity_fields=None, bulk_velocity=None, observer="external",
+                 fields_to_keep=None):
+    """Generate a photon list; signature and return value of pyxsim.make_photons
+    (photon_list.py:111-127,478): returns ``(n_photons, n_cells)`` summed over ranks."""
+    require_cuda()
+    photon_prefix = _strip(photon_prefix)
+    G = _setup_generation(data_source, redshift, area, exp_time, source_model, point_sources,
+                          parameters, center, dist, cosmology, velocity_fields, bulk_velocity, observer)
+    ds, parameters, spectral_norm, gather = G.ds, G.parameters, G.spectral_norm, G.gather
     native = hasattr(source_model, "generate_chunk")
     pieces = []
     n_photons = n_cells = 0
@@ -404,78 +422,169 @@ def _generate_with_reference_model(source_model, chunk, spectral_norm, gather):
 # stage 2: project_photons
 # =======================================================================================
 def _exclusive_offsets(counts):
-    """int64[n+1] exclusive prefix of ``counts`` via libpxb's scan."""
+    """``(poff, qoff, n_pairs)``: int64[n+1] exclusive prefixes of ``counts`` and of
+    ``ceil(counts / 2)`` (photon pairs, the photon kernels' unit of work) via libpxb's scan."""
     n = counts.numel()
     need = C.c_int64()
     _lib.call("pxb_scan_workspace_bytes", n, C.byref(need))
     ws = torch.empty(max(need.value, 1), dtype=torch.uint8, device=counts.device)
-    offsets, arank, totals = empty(n + 1, torch.int64), empty(n + 1, torch.int64), empty(2, torch.int64)
-    _lib.call("pxb_scan_counts", ptr(counts), n, ptr(offsets), ptr(arank), ptr(totals), ptr(ws),
-              ws.numel(), stream_ptr())
-    return offsets
+    offsets, arank, pairoff = (empty(n + 1, torch.int64) for _ in range(3))
+    totals = empty(3, torch.int64)
+    _lib.call("pxb_scan_counts", ptr(counts), n, ptr(offsets), ptr(arank), ptr(pairoff), ptr(totals),
+              ptr(ws), ws.numel(), stream_ptr())
+    return offsets, pairoff, int(totals.cpu()[2])
 
 
 def _as_device_f64(v):
     return to_device(v, torch.float64)
 
 
-def _project_photons(obs, photon_prefix, event_prefix, normal, sky_center, absorb_model=None,
-                     nH=None, abund_table="angr", no_shifting=False, north_vector=None,
-                     flat_sky=False, sigma_pos=None, kernel="top_hat", save_los=False,
-                     phys_coord=False, prng=None, column_file=None, nH_cell=None):
+class _Projection:
+    """Everything ``_project_photons`` derives from its arguments (photon_list.py:481-570,
+    596-640): validation, the absorption model, the column file, the ``parameters`` group of the
+    event list and the ``pxb_project_params`` block.  Shared by ``project_photons`` and the fused
+    ``make_events``."""
+
+    def __init__(self, obs, normal, sky_center, absorb_model=None, nH=None, abund_table="angr",
+                 no_shifting=False, north_vector=None, flat_sky=False, sigma_pos=None,
+                 kernel="top_hat", save_los=False, phys_coord=False, prng=None, column_file=None,
+                 nH_cell=None):
+        self.obs, self.normal, self.nH, self.abund_table = obs, normal, nH, abund_table
+        self.no_shifting, self.north_vector, self.flat_sky = no_shifting, north_vector, flat_sky
+        self.sigma_pos, self.kernel, self.save_los, self.phys_coord = sigma_pos, kernel, save_los, phys_coord
+        self.nH_cell = nH_cell
+        self.seed = prng_seed(prng)
+        L, self.north_out, self.uv = get_normal_and_north(normal, north_vector=north_vector)
+        self.col = None
+        if column_file is not None:
+            if absorb_model is None:
+                raise ValueError("You must specify an absorption model if you are using an absorption file!")
+            if obs == "internal":
+                raise ValueError("You cannot use an absorption file with an internal observer!")
+            if nH_cell is not None:
+                raise ValueError("Give either column_file or nH_cell, not both!")
+            self.col = read_column_file(column_file)
+            if not np.isclose(self.col["normal"], L).all():
+                raise ValueError("The value of the normal vector in the absorption file does not match "
+                                 "the value in the call to project_photons!")
+            if not np.isclose(self.col["north"], self.north_out).all():
+                raise ValueError("The value of the north vector in the absorption file does not match "
+                                 "the value in the call to project_photons!")
+        self.sky_center = np.asarray(sky_center, dtype="float64")
+        if isinstance(absorb_model, str):
+            if absorb_model not in absorb_models:
+                raise KeyError(f"{absorb_model} is not a known absorption model!")
+            absorb_model = absorb_models[absorb_model]
+        if absorb_model is not None and isinstance(absorb_model, type):
+            absorb_model = absorb_model(nH, abund_table=abund_table)
+        # (a ready-made instance is accepted too; it is never modified: ``nH`` travels in the
+        # parameter block)
+        if absorb_model is not None and nH is not None and parallel.rank() == 0:
+            mylog.info("Foreground galactic absorption: using the %s model and nH = %g.",
+                       absorb_model._name, nH)
+        self.absorb_model = absorb_model
+        if kernel not in ("top_hat", "gaussian"):
+            raise ValueError(f"unknown kernel {kernel!r}")
+        if nH_cell is not None and absorb_model is None:
+            raise ValueError("You must specify an absorption model to use per-cell columns!")
+
+    def check_list(self, observer, data_type):
+        """photon_list.py:581-594"""
+        if self.obs != observer:
+            which = {"external": "", "internal": "_allsky"}
+            raise RuntimeError(f"The function 'project_photons{which[self.obs]}' does not work with "
+                               f"'{observer}' photon lists!")
+        if observer == "internal" and isinstance(self.normal, str):
+            raise RuntimeError("Must specify a vector for 'normal' if you are doing an 'internal' observation!")
+        if self.sigma_pos is not None and data_type == "particles":
+            raise RuntimeError("The 'smooth_positions' argument should not be used with particle-based datasets!")
+
+    def event_params(self, exp_time, area, observer, redshift):
+        """The ``parameters`` group of the event list (photon_list.py:614-640)."""
+        normal = self.normal
+        params = dict(exp_time=exp_time, area=area, sky_center=self.sky_center, observer=observer,
+                      no_shifting=int(self.no_shifting), flat_sky=int(self.flat_sky),
+                      phys_coord=int(self.phys_coord),
+                      normal=normal if isinstance(normal, str) else np.asarray(normal, "float64"))
+        if self.north_vector is not None:
+            params["north_vector"] = np.asarray(self.north_vector, "float64")
+        # (sic) key spelled as in photon_list.py:626
+        params["absoption_model"] = self.absorb_model._name if self.absorb_model else "none"
+        if self.absorb_model is not None:
+            if self.nH is not None:      # (a column_file-only run has no foreground column to record)
+                params["nH"] = self.nH
+            params["abund_table"] = self.abund_table
+        if self.sigma_pos is not None:
+            params["sigma_pos"] = self.sigma_pos
+        params["kernel"] = self.kernel
+        params["redshift"] = redshift
+        return params
+
+    def fill(self, observer, data_type, redshift, D_A_kpc, xyz, cell_id0=0):
+        """``(pxb_project_params, tensors to keep alive)``; ``xyz``: device positions of the active
+        cells (needed for a column file)."""
+        normal = self.normal
+        x_hat, y_hat, z_hat = self.uv[0], self.uv[1], self.uv[2]
+        P = _lib.ProjectParams()
+        P.observer = int(observer == "internal")
+        P.data_type = int(data_type == "particles")
+        P.kernel = int(self.kernel == "gaussian")
+        P.no_shifting = int(bool(self.no_shifting))
+        if isinstance(normal, str) and observer == "external":
+            ax = "xyz".index(normal)
+            P.vn_axis = ax
+            # on-axis scatter_events: (xsky, ysky, los) <- axes (ax+1, ax+2, ax)
+            # (sky_functions.pyx:60-70,92-104)
+            eye = np.identity(3)
+            x_hat, y_hat, z_hat = eye[(ax + 1) % 3], eye[(ax + 2) % 3], eye[ax]
+        else:
+            P.vn_axis = -1
+        P.sky_mode = _lib.SKY_PHYS if self.phys_coord else (_lib.SKY_FLAT if self.flat_sky else _lib.SKY_TAN)
+        P.save_los = int(bool(self.save_los))
+        P.has_sigma_pos = int(self.sigma_pos is not None)
+        P.sigma_pos = 0.0 if self.sigma_pos is None else float(self.sigma_pos)
+        for i in range(3):
+            P.x_hat[i], P.y_hat[i], P.z_hat[i] = x_hat[i], y_hat[i], z_hat[i]
+        P.D_A_kpc = D_A_kpc
+        P.sky_center[0], P.sky_center[1] = float(self.sky_center[0]), float(self.sky_center[1])
+        keep = []
+        if self.absorb_model is not None:
+            keep = self.absorb_model._fill_params(P)
+            P.nH = 0.0 if self.nH is None else float(self.nH)
+        nH_cell = self.nH_cell
+        if self.col is not None:
+            # photon_list.py:672-680: the cube is sampled at the cells' positions in the
+            # (east, north, normal) frame of the Orientation, also for an on-axis normal
+            nH_cell = column_density_at_cells(xyz[0], xyz[1], xyz[2], self.uv, self.col["wbins"],
+                                              self.col["dbins"], self.col["nH"])
+        if nH_cell is not None:
+            nhc = to_device(nH_cell)
+            keep.append(nhc)
+            P.nH_cell = nhc.data_ptr()
+        P.oneplusz = 1.0 + redshift
+        P.seed = self.seed
+        P.cell_id0 = cell_id0
+        P.generic_kernels = int(bool(os.environ.get("PXB_GENERIC_KERNELS")))
+        return P, keep
+
+
+def _event_info(photon_file, event_prefix):
+    return dict(pyxsim_version=__version__, yt_version="n/a", soxs_version="n/a",
+                photon_file=photon_file, filenames=_file_names(event_prefix))
+
+
+def _project_photons(obs, photon_prefix, event_prefix, normal, sky_center, **kw):
     require_cuda()
     photon_prefix = _strip(photon_prefix)
     event_prefix = _strip(event_prefix)
-    seed = prng_seed(prng)
-
-    L, north_vector_out, uv = get_normal_and_north(normal, north_vector=north_vector)
-    x_hat, y_hat, z_hat = uv[0], uv[1], uv[2]
-
-    if column_file is not None:
-        if absorb_model is None:
-            raise ValueError("You must specify an absorption model if you are using an absorption file!")
-        if obs == "internal":
-            raise ValueError("You cannot use an absorption file with an internal observer!")
-        if nH_cell is not None:
-            raise ValueError("Give either column_file or nH_cell, not both!")
-        col = read_column_file(column_file)
-        if not np.isclose(col["normal"], L).all():
-            raise ValueError("The value of the normal vector in the absorption file does not match "
-                             "the value in the call to project_photons!")
-        if not np.isclose(col["north"], north_vector_out).all():
-            raise ValueError("The value of the north vector in the absorption file does not match "
-                             "the value in the call to project_photons!")
-
-    sky_center = np.asarray(sky_center, dtype="float64")
-    if isinstance(absorb_model, str):
-        if absorb_model not in absorb_models:
-            raise KeyError(f"{absorb_model} is not a known absorption model!")
-        absorb_model = absorb_models[absorb_model]
-    if absorb_model is not None and isinstance(absorb_model, type):
-        absorb_model = absorb_model(nH, abund_table=abund_table)
-    # (a ready-made instance is accepted too; it is never modified: ``nH`` travels in the
-    # parameter block)
-    if absorb_model is not None and nH is not None:
-        if parallel.rank() == 0:
-            mylog.info("Foreground galactic absorption: using the %s model and nH = %g.",
-                       absorb_model._name, nH)
-    abs_model_name = absorb_model._name if absorb_model else "none"
+    pr = _Projection(obs, normal, sky_center, **kw)
 
     plist = load_list(photon_prefix)
     p = plist.parameters
     redshift = float(p["fid_redshift"])
-    data_type = str(p["data_type"])
-    observer = str(p.get("observer", "external"))
-    if obs != observer:
-        which = {"external": "", "internal": "_allsky"}
-        raise RuntimeError(
-            f"The function 'project_photons{which[obs]}' does not work with '{observer}' photon lists!")
-    if observer == "internal" and isinstance(normal, str):
-        raise RuntimeError("Must specify a vector for 'normal' if you are doing an 'internal' observation!")
-    if sigma_pos is not None and data_type == "particles":
-        raise RuntimeError("The 'smooth_positions' argument should not be used with particle-based datasets!")
-    if kernel not in ("top_hat", "gaussian"):
-        raise ValueError(f"unknown kernel {kernel!r}")
+    data_type = _as_str(p["data_type"])
+    observer = _as_str(p.get("observer", "external"))
+    pr.check_list(observer, data_type)
     D_A = float(p["fid_d_a"]) * 1.0e3  # Mpc -> kpc, photon_list.py:596
 
     d = plist.data
@@ -483,25 +592,14 @@ def _project_photons(obs, photon_prefix, event_prefix, normal, sky_center, absor
     n_cells = int(d["num_photons"].shape[0])
     exp_time = float(p["fid_exp_time"])
     area = float(p["fid_area"])
-    params = dict(exp_time=exp_time, area=area, sky_center=sky_center, observer=observer,
-                  no_shifting=int(no_shifting), flat_sky=int(flat_sky), phys_coord=int(phys_coord),
-                  normal=normal if isinstance(normal, str) else np.asarray(normal, "float64"))
-    if north_vector is not None:
-        params["north_vector"] = np.asarray(north_vector, "float64")
-    params["absoption_model"] = abs_model_name  # (sic) key spelled as in photon_list.py:626
-    if absorb_model is not None:
-        if nH is not None:           # (a column_file-only run has no foreground column to record)
-            params["nH"] = nH
-        params["abund_table"] = abund_table
-    if sigma_pos is not None:
-        params["sigma_pos"] = sigma_pos
-    params["kernel"] = kernel
-    params["redshift"] = redshift
-    info = dict(pyxsim_version=__version__, yt_version="n/a", soxs_version="n/a",
-                photon_file=(_file_name(photon_prefix) if photon_prefix.startswith("mem:")
-                             else _file_name(photon_prefix) + ".h5"),
-                filenames=_file_names(event_prefix))
+    params = pr.event_params(exp_time, area, observer, redshift)
+    info = _event_info(_file_name(photon_prefix) if photon_prefix.startswith("mem:")
+                       else _file_name(photon_prefix) + ".h5", event_prefix)
 
+    # RNG counters are keyed by the cells' GLOBAL ids.  Lists written by this package carry them;
+    # for any other list (the reference's) the rank's exclusive prefix of the active cell counts
+    # makes the keys distinct across ranks (the event-count all-gather of the reference's MPI
+    # mode, photon_list.py:826, applied to the cells).
     cell_id0 = 0
     if "cell_id" not in d and parallel.size() > 1:      # (collective: every rank, photons or not)
         per_rank = parallel.allgather_counts([n_cells])[:, 0].tolist()
@@ -512,70 +610,24 @@ def _project_photons(obs, photon_prefix, event_prefix, normal, sky_center, absor
     else:
         dev = {k: (_as_device_f64(d[k]) if k != "num_photons" else to_device(d[k], torch.int64))
                for k in ("x", "y", "z", "vx", "vy", "vz", "dx", "num_photons", "energy")}
-        poff = _exclusive_offsets(dev["num_photons"])
+        poff, qoff, n_pairs = _exclusive_offsets(dev["num_photons"])
         PL = _lib.PhotonList()
-        PL.n_cells, PL.n_photons = n_cells, n_photons
-        PL.nph, PL.poff = dev["num_photons"].data_ptr(), poff.data_ptr()
+        PL.n_cells, PL.n_photons, PL.n_pairs = n_cells, n_photons, n_pairs
+        PL.nph, PL.poff, PL.qoff = dev["num_photons"].data_ptr(), poff.data_ptr(), qoff.data_ptr()
         for k in ("x", "y", "z", "vx", "vy", "vz", "dx"):
             setattr(PL, k, dev[k].data_ptr())
         PL.energy = dev["energy"].data_ptr()
-        # RNG counters are keyed by the cells' GLOBAL ids.  Lists written by this package carry
-        # them; for any other list (the reference's) the rank's exclusive prefix of the active
-        # cell counts makes the keys distinct across ranks (the event-count all-gather of the
-        # reference's MPI mode, photon_list.py:826, applied to the cells).
         cid = None
         if "cell_id" in d:
             cid = to_device(d["cell_id"], torch.int64)
             PL.cell_id = cid.data_ptr()
-
-        P = _lib.ProjectParams()
-        P.observer = int(observer == "internal")
-        P.data_type = int(data_type == "particles")
-        P.kernel = int(kernel == "gaussian")
-        P.no_shifting = int(bool(no_shifting))
-        if isinstance(normal, str) and observer == "external":
-            ax = "xyz".index(normal)
-            P.vn_axis = ax
-            # on-axis scatter_events: (xsky, ysky, los) <- axes (ax+1, ax+2, ax)
-            # (sky_functions.pyx:60-70,92-104)
-            eye = np.identity(3)
-            x_hat, y_hat, z_hat = eye[(ax + 1) % 3], eye[(ax + 2) % 3], eye[ax]
-        else:
-            P.vn_axis = -1
-        P.sky_mode = _lib.SKY_PHYS if phys_coord else (_lib.SKY_FLAT if flat_sky else _lib.SKY_TAN)
-        P.save_los = int(bool(save_los))
-        P.has_sigma_pos = int(sigma_pos is not None)
-        P.sigma_pos = 0.0 if sigma_pos is None else float(sigma_pos)
-        for i in range(3):
-            P.x_hat[i], P.y_hat[i], P.z_hat[i] = x_hat[i], y_hat[i], z_hat[i]
-        P.D_A_kpc = D_A
-        P.sky_center[0], P.sky_center[1] = float(sky_center[0]), float(sky_center[1])
-        keep = []
-        if absorb_model is not None:
-            keep = absorb_model._fill_params(P)
-            P.nH = 0.0 if nH is None else float(nH)
-        if column_file is not None:
-            # photon_list.py:672-680: the cube is sampled at the cells' positions in the
-            # (east, north, normal) frame of the Orientation, also for an on-axis normal
-            nH_cell = column_density_at_cells(dev["x"], dev["y"], dev["z"], uv, col["wbins"],
-                                              col["dbins"], col["nH"])
-        if nH_cell is not None:
-            if absorb_model is None:
-                raise ValueError("You must specify an absorption model to use per-cell columns!")
-            nhc = to_device(nH_cell)
-            keep.append(nhc)
-            P.nH_cell = nhc.data_ptr()
-        P.oneplusz = 1.0 + redshift
-        P.seed = seed
-        P.cell_id0 = cell_id0
-        P.single_pass = int(os.environ.get("PXB_PROJECT_MODE", "") == "fused")
-        P.generic_kernels = int(bool(os.environ.get("PXB_GENERIC_KERNELS")))
+        P, keep = pr.fill(observer, data_type, redshift, D_A, (dev["x"], dev["y"], dev["z"]), cell_id0)
 
         need = C.c_int64()
-        _lib.call("pxb_project_workspace_bytes", n_cells, n_photons, C.byref(need))
+        _lib.call("pxb_project_workspace_bytes", n_cells, n_pairs, C.byref(need))
         ws = torch.empty(need.value, dtype=torch.uint8, device=dev["energy"].device)
         xsky, ysky, eobs = empty(n_photons), empty(n_photons), empty(n_photons)
-        los = empty(n_photons) if save_los else None
+        los = empty(n_photons) if pr.save_los else None
         nev = empty(1, torch.int64)
         stats = empty(3)
         with stage("project"):
@@ -585,7 +637,7 @@ def _project_photons(obs, photon_prefix, event_prefix, normal, sky_center, absor
         st = stats.cpu().numpy()
         del keep, ws, cid
         data = {"xsky": xsky[:n_events], "ysky": ysky[:n_events], "eobs": eobs[:n_events]}
-        if save_los:
+        if pr.save_los:
             data["los"] = los[:n_events]
         params["flux"] = float(st[0]) * K.erg_per_keV / exp_time / area   # photon_list.py:816
         params["emin"] = float(st[1])
@@ -595,6 +647,131 @@ def _project_photons(obs, photon_prefix, event_prefix, normal, sky_center, absor
     all_nevents = parallel.allreduce_sum(n_events)
     mylog.info("Detected %d events.", all_nevents)
     return all_nevents
+
+
+def _as_str(v):
+    return v.decode() if isinstance(v, bytes) else str(v)
+
+
+# =======================================================================================
+# both stages in one pass: make_events
+# =======================================================================================
+def make_events(event_prefix, data_source, redshift, area, exp_time, source_model, normal,
+                sky_center, absorb_model=None, nH=None, abund_table="angr", no_shifting=False,
+                north_vector=None, sigma_pos=None, flat_sky=False, kernel="top_hat", save_los=False,
+                phys_coord=False, prng=None, point_sources=False, parameters=None, center=None,
+                dist=None, cosmology=None, velocity_fields=None, bulk_velocity=None):
+    """``make_photons`` followed by ``project_photons`` (external observer) in ONE pass over the
+    cells: energies are sampled, shifted, absorbed and -- for the survivors only -- scattered onto
+    the sky without ever writing a photon list (the two reference stages,
+    thermal_sources/base.py:462-492 and photon_list.py:686-799, back to back).  The arguments are
+    those of the two reference calls; ``source_model.prng`` seeds the generation, ``prng`` the
+    projection.  The event list is bit for bit the one ``make_photons`` + ``project_photons``
+    produce with the same seeds.  Returns ``(n_photons, n_cells, n_events)`` summed over ranks.
+
+    Thermal sources with non-negative tables run fused; anything else (power-law / line sources,
+    tables with negative entries, cells extrapolating beyond the table, reference-style host
+    models) takes the two stages through an in-memory photon list."""
+    require_cuda()
+    event_prefix = _strip(event_prefix)
+    pr = _Projection("external", normal, sky_center, absorb_model=absorb_model, nH=nH,
+                     abund_table=abund_table, no_shifting=no_shifting, north_vector=north_vector,
+                     flat_sky=flat_sky, sigma_pos=sigma_pos, kernel=kernel, save_los=save_los,
+                     phys_coord=phys_coord, prng=prng)
+    fusable = hasattr(source_model, "count_chunk") and hasattr(source_model, "spectral_model")
+    if fusable:
+        G = _setup_generation(data_source, redshift, area, exp_time, source_model, point_sources,
+                              parameters, center, dist, cosmology, velocity_fields, bulk_velocity,
+                              "external")
+        pr.check_list("external", G.data_type)
+        dm = source_model.spectral_model.device_model(source_model.method)
+        fusable = bool(_lib.load().pxb_model_nonnegative(dm.handle))
+    if not fusable:
+        return _make_events_two_stage(event_prefix, data_source, redshift, area, exp_time, source_model,
+                                      pr, point_sources, parameters, center, dist, cosmology,
+                                      velocity_fields, bulk_velocity)
+    D_A_kpc = G.D_A_mpc * 1.0e3
+    pieces = []
+    n_photons = n_cells = n_events = 0
+    flux_sum, emin, emax = 0.0, 1.0e99, -1.0e99
+    declined = False
+    for chunk in _chunks(data_source):
+        out, Cs, keep_c = source_model.count_chunk(chunk, G.spectral_norm, gather=G.gather)
+        if out is None or out.n_photons == 0:
+            continue
+        gid = source_model._global_ids(out.idx)
+        PL = _lib.PhotonList()
+        PL.n_cells, PL.n_photons, PL.n_pairs = out.n_cells, out.n_photons, out.n_pairs
+        PL.nph, PL.poff, PL.qoff = out.nph.data_ptr(), out.poff.data_ptr(), out.qoff.data_ptr()
+        for k in ("x", "y", "z", "vx", "vy", "vz"):
+            setattr(PL, k, getattr(out, k).data_ptr())
+        PL.dx = out.dx.data_ptr() if out.dx is not None else None
+        PL.cell_id = gid.data_ptr()
+        P, keep_p = pr.fill("external", G.data_type, G.redshift, D_A_kpc, (out.x, out.y, out.z))
+        need = C.c_int64()
+        _lib.call("pxb_make_events_workspace_bytes", dm.handle, out.n_cells, out.n_pairs, C.byref(need))
+        ws = torch.empty(need.value, dtype=torch.uint8, device=out.idx.device)
+        xsky, ysky, eobs = empty(out.n_photons), empty(out.n_photons), empty(out.n_photons)
+        los = empty(out.n_photons) if pr.save_los else None
+        nev = empty(2, torch.int64)          # [events, cells the mixture sampler declined]
+        stats = empty(3)
+        with stage("make_events"):
+            _lib.call("pxb_make_events", dm.handle, C.byref(Cs), ptr(out.idx), C.byref(PL), C.byref(P),
+                      ptr(xsky), ptr(ysky), ptr(eobs), ptr(los), ptr(nev), ptr(stats),
+                      C.c_void_p(nev.data_ptr() + 8), ptr(ws), need.value, stream_ptr())
+        ne, nd = (int(v) for v in nev.cpu())
+        del ws, keep_p, keep_c
+        if nd > 0:
+            declined = True
+            break
+        st = stats.cpu().numpy()
+        pieces.append((xsky[:ne], ysky[:ne], eobs[:ne], los[:ne] if pr.save_los else None))
+        n_photons += out.n_photons
+        n_cells += out.n_cells
+        n_events += ne
+        flux_sum += float(st[0])
+        emin, emax = min(emin, float(st[1])), max(emax, float(st[2]))
+    source_model.cleanup_model("photons")
+    # (collective: every rank must agree before any of them falls back)
+    if parallel.allreduce_sum(int(declined)) > 0:
+        mylog.info("Some cells lie outside the spectral table: taking the two-stage path.")
+        return _make_events_two_stage(event_prefix, data_source, redshift, area, exp_time, source_model,
+                                      pr, point_sources, parameters, center, dist, cosmology,
+                                      velocity_fields, bulk_velocity)
+
+    def cat(j):
+        ts = [pc[j] for pc in pieces]
+        return empty(0) if not ts else (ts[0] if len(ts) == 1 else torch.cat(ts))
+
+    data = {"xsky": cat(0), "ysky": cat(1), "eobs": cat(2)}
+    if pr.save_los:
+        data["los"] = cat(3)
+    params = pr.event_params(G.exp_time, G.area, "external", G.redshift)
+    params["flux"] = flux_sum * K.erg_per_keV / G.exp_time / G.area
+    params["emin"], params["emax"] = emin, emax
+    save_list(event_prefix, DeviceList(_event_info("none (fused make_events)", event_prefix), params, data))
+    tot = [parallel.allreduce_sum(v) for v in (n_photons, n_cells, n_events)]
+    mylog.info("Generated %d photons in %d cells; detected %d events.", *tot)
+    return tuple(tot)
+
+
+def _make_events_two_stage(event_prefix, data_source, redshift, area, exp_time, source_model, pr,
+                           point_sources, parameters, center, dist, cosmology, velocity_fields,
+                           bulk_velocity):
+    tmp = f"mem:__make_events_{id(pr):x}"
+    n_ph, n_c = make_photons(tmp, data_source, redshift, area, exp_time, source_model,
+                             point_sources=point_sources, parameters=parameters, center=center,
+                             dist=dist, cosmology=cosmology, velocity_fields=velocity_fields,
+                             bulk_velocity=bulk_velocity)
+    try:
+        n_ev = _project_photons("external", tmp, event_prefix, pr.normal, pr.sky_center,
+                                absorb_model=pr.absorb_model, nH=pr.nH, abund_table=pr.abund_table,
+                                no_shifting=pr.no_shifting, north_vector=pr.north_vector,
+                                flat_sky=pr.flat_sky, sigma_pos=pr.sigma_pos, kernel=pr.kernel,
+                                save_los=pr.save_los, phys_coord=pr.phys_coord, prng=pr.seed)
+    finally:
+        drop_list(tmp)
+    return n_ph, n_c, n_ev
 
 
 def project_photons(photon_prefix, event_prefix, normal, sky_center, absorb_model=None, nH=None,

@@ -41,7 +41,7 @@ class ChunkPhotons:
     """Device-resident result of one chunk: the photon list rows of its active cells."""
 
     __slots__ = ("n_cells", "n_photons", "idx", "nph", "poff", "energy", "x", "y", "z", "vx",
-                 "vy", "vz", "dx", "counts", "gid", "_id0", "_chunk_cells")
+                 "vy", "vz", "dx", "counts", "gid", "_id0", "_chunk_cells", "qoff", "n_pairs")
 
     def __init__(self):
         for s in self.__slots__:
@@ -157,19 +157,21 @@ class SourceModel:
             self._scan_ws = torch.empty(max(need.value, 1), dtype=torch.uint8, device=counts.device)
         offsets = empty(n + 1, torch.int64)
         arank = empty(n + 1, torch.int64)
-        totals = empty(2, torch.int64)
+        pairoff = empty(n + 1, torch.int64)
+        totals = empty(3, torch.int64)
         with stage("scan_counts"):
-            _lib.call("pxb_scan_counts", ptr(counts), n, ptr(offsets), ptr(arank), ptr(totals),
-                      ptr(self._scan_ws), self._scan_ws.numel(), stream_ptr())
-        n_photons, n_active = (int(v) for v in totals.cpu())  # the one sync of the chunk
+            _lib.call("pxb_scan_counts", ptr(counts), n, ptr(offsets), ptr(arank), ptr(pairoff),
+                      ptr(totals), ptr(self._scan_ws), self._scan_ws.numel(), stream_ptr())
+        n_photons, n_active, n_pairs = (int(v) for v in totals.cpu())  # the one sync of the chunk
         out = ChunkPhotons()
-        out.n_cells, out.n_photons = n_active, n_photons
+        out.n_cells, out.n_photons, out.n_pairs = n_active, n_photons, n_pairs
         out.counts = counts
         if n_photons == 0:
             return out
         out.idx = empty(n_active, torch.int64)
         out.nph = empty(n_active, torch.int64)
         out.poff = empty(n_active + 1, torch.int64)
+        out.qoff = empty(n_active + 1, torch.int64)
         x = y = z = vx = vy = vz = dx = None
         G = self._geometry()
         if gather is not None:
@@ -182,10 +184,10 @@ class SourceModel:
             for name in ("x", "y", "z", "vx", "vy", "vz", "dx"):
                 setattr(out, name, empty(n_active))
         with stage("compact_cells"):
-            _lib.call("pxb_compact_cells", n, ptr(counts), ptr(offsets), ptr(arank), ptr(x), ptr(y),
-                      ptr(z), ptr(vx), ptr(vy), ptr(vz), ptr(dx), C.byref(G), ptr(out.idx),
-                      ptr(out.nph), ptr(out.poff), ptr(out.x), ptr(out.y), ptr(out.z), ptr(out.vx),
-                      ptr(out.vy), ptr(out.vz), ptr(out.dx), stream_ptr())
+            _lib.call("pxb_compact_cells", n, ptr(counts), ptr(offsets), ptr(arank), ptr(pairoff),
+                      ptr(x), ptr(y), ptr(z), ptr(vx), ptr(vy), ptr(vz), ptr(dx), C.byref(G),
+                      ptr(out.idx), ptr(out.nph), ptr(out.poff), ptr(out.qoff), ptr(out.x), ptr(out.y),
+                      ptr(out.z), ptr(out.vx), ptr(out.vy), ptr(out.vz), ptr(out.dx), stream_ptr())
         return out
 
     def generate_chunk(self, chunk, spectral_norm, gather=None):
@@ -664,13 +666,29 @@ class ThermalSourceModel(SourceModel):
             return None
         out.energy = empty(out.n_photons)
         need = C.c_int64()
-        _lib.call("pxb_thermal_sample_workspace_bytes", dm.handle, out.n_cells, out.n_photons, C.byref(need))
+        _lib.call("pxb_thermal_sample_workspace_bytes", dm.handle, out.n_cells, out.n_pairs, C.byref(need))
         ws = torch.empty(need.value, dtype=torch.uint8, device=out.energy.device)
         with stage("thermal_sample"):
             _lib.call("pxb_thermal_sample", dm.handle, C.byref(Cs), out.n_cells, ptr(out.idx),
-                      ptr(out.nph), ptr(out.poff), out.n_photons, ptr(out.energy), ptr(ws),
-                      need.value, stream_ptr())
+                      ptr(out.nph), ptr(out.poff), ptr(out.qoff), out.n_photons, out.n_pairs,
+                      ptr(out.energy), ptr(ws), need.value, stream_ptr())
         return out
+
+    def count_chunk(self, chunk, spectral_norm, gather=None):
+        """First half of ``generate_chunk``: expected counts, Poisson draws, offsets and the
+        gather of the active cells -- everything except the energies.  Returns ``(out, Cs, keep)``
+        for the fused ``make_events`` path (``keep`` holds the tensors ``Cs`` points into)."""
+        require_cuda()
+        if self._chunk_size(chunk, self.temperature_field) == 0:
+            return None, None, None
+        keep = []
+        Cs = self._cells_struct(chunk, spectral_norm, keep)
+        dm = self.spectral_model.device_model(self.method)
+        counts = empty(Cs.ncell, torch.int64)
+        with stage("thermal_counts"):
+            _lib.call("pxb_thermal_counts", dm.handle, C.byref(Cs), None, ptr(counts), stream_ptr())
+        out = self._scan_and_compact(counts, chunk, gather)
+        return out, Cs, keep
 
 
 class CIESourceModel(ThermalSourceModel):

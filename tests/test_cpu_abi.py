@@ -90,7 +90,42 @@ def test_wabs_fast_index_table_invariants():
     assert np.unique(idx).size == edges.size                      # at most one edge per sub-interval
     lo = ((idx + base) << 19).astype(np.int32).view(np.float32)
     assert np.all(edges > lo)                                     # never on a boundary
-    src = open(os.path.join(ROOT, "pyxsim_b200", "csrc", "project.cu")).read()
+    src = open(os.path.join(ROOT, "pyxsim_b200", "csrc", "projection.cuh")).read()
     assert "WABS_LUT_BASE = (127 - 4) << 4" in src and "WABS_LUT_N = 128" in src
     for v in ("0.284", "0.532", "0.707", "0.867", "1.303", "2.471", "4.038", "7.111", "8.331"):
         assert src.count(v) >= 2                                  # immediate chain and table builder agree
+
+
+def test_alias_tables_reproduce_the_row_distribution(lib):
+    """The sampler's per-row Walker alias tables (built on the host, pxb_alias_table_host): the
+    implied bin probabilities (thr_j + sum_{k: other_k = j} (2^32 - thr_k)) / (2^32 nb) must equal
+    the normalised row to the table's resolution 2^-32 / nb, bins of zero probability must be
+    unreachable, and every alternative must be a valid bin."""
+    from pyxsim_b200 import synthetic
+
+    kT, ebins, cosmic, metal, _ = synthetic.apec_like_tables(nT=36, nbins=4000)
+    rng = np.random.RandomState(5)
+    rows = [cosmic[3], metal[20], metal[35], rng.uniform(0, 1, 7), np.array([0.0, 0.0, 5.0, 0.0]),
+            np.array([1.0]), np.where(rng.uniform(size=513) < 0.7, 0.0, rng.lognormal(0, 3, 513)),
+            np.full(64, 0.25)]
+    for row in rows:
+        row = np.ascontiguousarray(row, "float64")
+        nb = row.size
+        thr = np.zeros(nb, dtype=np.uint32)
+        oth = np.zeros(nb, dtype=np.uint32)
+        rc = lib.pxb_alias_table_host(row.ctypes.data_as(C.c_void_p), nb, thr.ctypes.data_as(C.c_void_p),
+                                      oth.ctypes.data_as(C.c_void_p))
+        assert rc == 0
+        assert oth.max() < nb
+        # the kernel takes bin j when top32 < thr_j, else other_j; thr = 2^32 - 1 with other = j is "always j"
+        direct = thr.astype(np.float64)
+        spill = 4294967296.0 - direct
+        P = direct.copy()
+        np.add.at(P, oth, spill)
+        P /= 4294967296.0 * nb
+        want = row / row.sum()
+        assert abs(P.sum() - 1.0) < 1e-12
+        # every table entry is rounded to 2^-32: a bin collects one rounding per entry pointing at it
+        fan_in = 1.0 + np.bincount(oth, minlength=nb).max()
+        assert np.max(np.abs(P - want)) <= fan_in * 2.0 ** -32 / nb
+        assert np.all(P[want == 0.0] == 0.0)

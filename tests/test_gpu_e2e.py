@@ -411,3 +411,99 @@ def test_specialised_kernels_are_bit_identical_to_the_generic_ones(cuda, monkeyp
         assert a[nm][0] == b[nm][0] > 0 and a[nm][2:] == b[nm][2:]
         for k in a[nm][1]:
             assert torch.equal(a[nm][1][k], b[nm][1][k]), (nm, k)
+
+
+# ---------------------------------------------------------------------------------------
+# fused make_events == make_photons + project_photons
+# ---------------------------------------------------------------------------------------
+def _two_stage(tag, src, z, area, texp, model, normal, center, **kw):
+    n_ph, n_c = px.make_photons(f"mem:{tag}_ph", src, z, area, texp, model)
+    n_ev = px.project_photons(f"mem:{tag}_ph", f"mem:{tag}_ev2", normal, center, **kw)
+    return (n_ph, n_c, n_ev), px.load_list(f"mem:{tag}_ev2")
+
+
+def _same_events(a, b, keys=("xsky", "ysky", "eobs")):
+    for k in keys:
+        assert np.array_equal(a.numpy(k), b.numpy(k)), k
+    for k in ("flux", "emin", "emax"):
+        assert float(a.parameters[k]) == float(b.parameters[k]), k
+
+
+@pytest.mark.parametrize("case", ["common_on", "common_off", "generic_opts", "var_elem", "log_ar", "chunks"])
+def test_fused_make_events_equals_the_two_stages(cuda, case, monkeypatch):
+    """``make_events`` (sample -> shift -> absorb -> scatter in one kernel, no photon list) must
+    give the event list of ``make_photons`` + ``project_photons`` bit for bit: same survivors, same
+    order, same sky positions, same flux -- for the kernels compiled for the common option set and
+    for the option-generic ones."""
+    nbins, nvar, binscale, method = 800, 0, "linear", "invert_cdf"
+    kw = dict(absorb_model="wabs", nH=0.05, prng=9)
+    normal = "z"
+    src_kw = dict(kT_range=(1.0, 9.0), v3d_sigma_kms=300.0, device="cuda")
+    if case == "common_off":
+        normal = [0.3, -0.5, 0.8]
+    elif case == "generic_opts":
+        en, sg = synthetic.tbabs_like_sigma()
+        kw = dict(absorb_model=px.TBabsModel(0.03, energy=en, cross_section=sg), nH=0.03, prng=9,
+                  sigma_pos=0.4, flat_sky=True, save_los=True, north_vector=[0.0, 1.0, 0.2])
+        normal = [0.1, 0.9, -0.3]
+    elif case == "var_elem":
+        nvar = 3
+        src_kw["metallicity"] = (0.1, 0.6)
+    elif case == "log_ar":
+        binscale, method = "log", "accept_reject"
+    kT_nodes, ebins, cosmic, metal, var = synthetic.apec_like_tables(nT=36, nbins=nbins, nvar=nvar,
+                                                                      binscale=binscale)
+    src = synthetic.beta_model_source(40, chunk_size=(17000 if case == "chunks" else None), **src_kw)
+    names = tuple(f"El{k}" for k in range(nvar))
+    sm = px.ThermalSpectralModel(ebins, kT_nodes, cosmic, metal, var, var_elem_names=names, binscale=binscale)
+
+    def model():
+        ve = {nm: 0.2 + 0.3 * k for k, nm in enumerate(names)} or None
+        zm = ("gas", "metallicity") if case == "var_elem" else 0.3
+        return px.ThermalSourceModel(sm, 0.1, 10.0, nbins, zm, binscale=binscale, method=method,
+                                     temperature_field=TF, var_elem=ve, prng=8)
+
+    area, texp, z = 6.0e4, 1.0e5, 0.05
+    tot2, ev2 = _two_stage(case, src, z, area, texp, model(), normal, [30.0, 45.0], **kw)
+    tot1 = px.make_events(f"mem:{case}_ev1", src, z, area, texp, model(), normal, [30.0, 45.0], **kw)
+    assert tot1 == tot2 and tot1[2] > 1.0e5
+    ev1 = px.load_list(f"mem:{case}_ev1")
+    _same_events(ev1, ev2, ("xsky", "ysky", "eobs") + (("los",) if kw.get("save_los") else ()))
+    assert ev1.parameters["absoption_model"] == ev2.parameters["absoption_model"]
+    if case == "common_on":
+        # the option-generic fused kernel gives the same list as well
+        monkeypatch.setenv("PXB_GENERIC_KERNELS", "1")
+        tot3 = px.make_events("mem:common_on_ev3", src, z, area, texp, model(), normal, [30.0, 45.0], **kw)
+        assert tot3 == tot1
+        _same_events(px.load_list("mem:common_on_ev3"), ev2)
+
+
+def test_make_events_falls_back_to_two_stages(cuda):
+    """Sources the fused kernel does not take -- tables with negative entries (the clip of
+    base.py:460 matters), cells extrapolating beyond the table, power-law sources -- run the two
+    stages behind the same call and give the two-stage result."""
+    kT_nodes, ebins, cosmic, metal, _ = synthetic.apec_like_tables(nT=36, nbins=300, negative=True)
+    src = synthetic.beta_model_source(16, kT_range=(1.0, 9.0), v3d_sigma_kms=300.0, device="cuda")
+    sm = px.ThermalSpectralModel(ebins, kT_nodes, cosmic, metal)
+    kw = dict(absorb_model="wabs", nH=0.05, prng=9)
+
+    def model():
+        return px.ThermalSourceModel(sm, 0.1, 10.0, 300, 0.3, temperature_field=TF, prng=8)
+
+    tot2, ev2 = _two_stage("fbneg", src, 0.05, 6.0e4, 1.0e5, model(), "z", [30.0, 45.0], **kw)
+    tot1 = px.make_events("mem:fbneg_ev1", src, 0.05, 6.0e4, 1.0e5, model(), "z", [30.0, 45.0], **kw)
+    assert tot1 == tot2 and tot1[2] > 0
+    _same_events(px.load_list("mem:fbneg_ev1"), ev2)
+    # cells hotter than the last table row are declined by the mixture sampler
+    kT_nodes, ebins, cosmic, metal, _ = synthetic.apec_like_tables(nT=20, nbins=300)
+    src = synthetic.beta_model_source(16, kT_range=(0.5, 20.0), v3d_sigma_kms=300.0, device="cuda")
+    sm = px.ThermalSpectralModel(ebins, kT_nodes, cosmic, metal)
+    assert float(src.fields[TF].max()) > kT_nodes[-1]
+    tot2, ev2 = _two_stage("fbext", src, 0.05, 6.0e4, 1.0e5, model(), "z", [30.0, 45.0], **kw)
+    tot1 = px.make_events("mem:fbext_ev1", src, 0.05, 6.0e4, 1.0e5, model(), "z", [30.0, 45.0], **kw)
+    assert tot1 == tot2 and tot1[2] > 0
+    _same_events(px.load_list("mem:fbext_ev1"), ev2)
+    pl = px.PowerLawSourceModel(1.0, 0.5, 8.0, ("gas", "emission_measure"), 1.7, prng=3)
+    src.units[("gas", "emission_measure")] = "keV/s"
+    tot = px.make_events("mem:fbpl_ev", src, 0.05, 1.0e-20, 1.0, pl, "z", [30.0, 45.0], prng=4)
+    assert len(tot) == 3

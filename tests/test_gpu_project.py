@@ -413,14 +413,12 @@ def test_in_kernel_tan_transform_is_the_reference_pixel_to_cel(cuda, oracle, fie
         np.testing.assert_allclose(ev["ysky"], ys, rtol=0, atol=3e-13)
 
 
-@pytest.mark.parametrize("mode", ["twopass", "fused"])
-def test_tiles_spanning_hundreds_of_empty_cells(cuda, oracle, mode, monkeypatch):
+def test_tiles_spanning_hundreds_of_empty_cells(cuda, oracle):
     """A photon list whose cells are mostly empty (long runs of zero-photon cells between the
-    active ones): warp tiles then span more than 256 / 257 cells, which takes the unpacked-cell
-    and the global-search branches of the detect and emit passes.  Doppler-only projection is
-    deterministic: every event must carry exactly its own cell's shift and line-of-sight."""
-    if mode == "fused":
-        monkeypatch.setenv("PXB_PROJECT_MODE", "fused")
+    active ones): the pair tiles then hold empty cells (shared-memory bisection instead of the
+    ballot look-up) or span more cells than are staged (global bisection).  Doppler-only projection
+    is deterministic: every event must carry exactly its own cell's shift and line-of-sight, in
+    photon order."""
     rng = np.random.RandomState(17)
     n_cells = 60000
     nph = np.zeros(n_cells, dtype=np.int64)
@@ -517,27 +515,3 @@ def test_line_counts_and_energies(cuda, oracle):
         assert abs(e.size - F.sum()) < 1.645 * 4 * np.sqrt(F.sum())
         assert _ks_ok(e, oe)
         assert abs(e.mean() - 3.5 / 1.2) < 5 * e.std() / np.sqrt(e.size)
-
-
-def test_two_pass_variant_is_bit_identical(cuda):
-    """The default two-pass projection (detect -> scan -> emit) and the fused single-pass kernel
-    (PXB_PROJECT_MODE=fused) must give exactly the same event list: decisions, order, flux."""
-    import os
-
-    d, p = make_plist(n_cells=6000, mean_ph=25.0, zero_cells=True)
-    put("tp_ph", d, p)
-    res = {}
-    for mode in ("fused", "twopass"):
-        os.environ["PXB_PROJECT_MODE"] = mode
-        try:
-            n = px.project_photons("mem:tp_ph", "mem:tp_ev", [0.3, 0.2, 0.9], [30.0, 45.0],
-                                   absorb_model="wabs", nH=0.08, save_los=True, sigma_pos=0.3, prng=5)
-        finally:
-            os.environ.pop("PXB_PROJECT_MODE", None)
-        ev, par = events("tp_ev")
-        res[mode] = (n, ev, par)
-    assert res["fused"][0] == res["twopass"][0] > 0
-    for k in res["fused"][1]:
-        assert np.array_equal(res["fused"][1][k], res["twopass"][1][k]), k
-    for k in ("flux", "emin", "emax"):
-        assert res["fused"][2][k] == res["twopass"][2][k]
