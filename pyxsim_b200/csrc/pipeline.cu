@@ -17,10 +17,12 @@
 // cell look-up, its per-cell data and its three Philox blocks (see projection.cuh), and a lane
 // owns one pair per round.  Pairs are numbered cell by cell (qoff = exclusive prefix of
 // ceil(N/2) over the active cells); a warp owns a tile of 128 consecutive pair slots (<= 256
-// photons, four rounds), a persistent CTA (one per SM, 32 warps) takes chunks of 128 tiles by
-// ticket and keeps the four alias rows of the chunk's temperature bin in shared memory (TMA bulk
-// copies, one mbarrier), the event list keeps the photon order through a warp-wide decoupled
-// look-back over per-tile survivor counts (the reference's cursor `k`, sky_functions.pyx:87-105).
+// photons, four rounds) that it draws from a global ticket, so tiles are started in increasing
+// order over the whole grid; the CTAs are persistent (one per SM, 32 warps) and keep the four
+// alias rows of the temperature bin being worked on in shared memory (TMA bulk copies, one
+// mbarrier, re-decided every 16 tiles per warp); the event list keeps the photon order through
+// a warp-wide decoupled look-back over per-tile survivor counts (the reference's cursor `k`,
+// sky_functions.pyx:87-105).
 // DRAM traffic is the algorithmic minimum: per-cell records in, (energies in/out,) events out.
 #include "sampling.cuh"
 #include "projection.cuh"
@@ -31,7 +33,7 @@ constexpr int PL_THREADS = 1024;
 constexpr int PL_WARPS = PL_THREADS / 32;
 constexpr int PL_ROUNDS = 4;
 constexpr int PL_TSLOTS = 32 * PL_ROUNDS;          // pair slots per warp tile
-constexpr int PL_CHUNK_TILES = 4 * PL_WARPS;       // tiles per ticket
+constexpr int PL_EPOCH = 16;                       // tiles per warp between two staging decisions
 constexpr int PL_MAXC = PL_TSLOTS + 4;             // cell starts staged per tile (>= 129)
 
 // everything the photon kernels need of an active cell: 64 bytes, four 16-byte loads
@@ -55,7 +57,7 @@ struct PipeArgs {
   const int64_t* tabcum;      // general split side array
   int tab_stride;
   int use_staging;
-  int64_t n_cells, n_pairs, n_tiles, n_chunks;
+  int64_t n_cells, n_pairs, n_tiles;
   unsigned int* ticket;
   double* energies;           // sample: out; project: in
   double* xsky;
@@ -115,6 +117,11 @@ constexpr unsigned long long ST_MASK = 3ull << 62;
 __device__ __forceinline__ unsigned long long ld_status(const unsigned long long* p) {
   unsigned long long v;
   asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ unsigned int ld_ticket(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p));
   return v;
 }
 __device__ __forceinline__ void st_status(unsigned long long* p, unsigned long long v) {
@@ -402,7 +409,7 @@ k_pipeline(const DevModel M, const __grid_constant__ pxb_thermal_cells C,
   const DevTable& T = M.prim;
   uint2* s_alias = reinterpret_cast<uint2*>(dyn);
   __shared__ uint64_t s_bar;
-  __shared__ unsigned int s_chunk;
+  __shared__ int s_live, s_want;
   __shared__ WabsFast s_wabs;
 
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -415,36 +422,58 @@ k_pipeline(const DevModel M, const __grid_constant__ pxb_thermal_cells C,
   uint32_t parity = 0;
   const unsigned lt = (1u << lane) - 1u;
   const bool absorb = MODE != MODE_SAMPLE && P.absorb_kind != PXB_ABS_NONE;
+  const bool staging = MODE != MODE_PROJECT && A.use_staging;
+  if (threadIdx.x == 0) s_live = PL_WARPS;
+  __syncthreads();
 
-  for (;;) {
-    if (threadIdx.x == 0) s_chunk = atomicAdd(A.ticket, 1u);
-    __syncthreads();     // also: every warp is done with the previous chunk's staged rows
-    const int64_t chunk = s_chunk;
-    if (chunk >= A.n_chunks) break;
-    const int64_t tile0 = chunk * PL_CHUNK_TILES;
-    const int ntile = (int)min((int64_t)PL_CHUNK_TILES, A.n_tiles - tile0);
-    if (MODE != MODE_PROJECT && A.use_staging) {
-      // the temperature bin of the chunk's first cell decides what is staged
-      const CellRec* f0 = A.recs + __ldg(A.tile_cell + tile0);
-      const int meta0 = __ldg(&f0->meta);
-      const int want = ((meta0 & 7) == 2 && !(meta0 & 8)) ? __ldg(&f0->z1) : -1;
-      if (want >= 0 && want != tag) {
+  // Every WARP draws its tiles one at a time from a global ticket: tiles are then started in
+  // increasing order across the whole grid, which is what keeps the look-back short (a tile only
+  // ever waits for tiles that were started before it).  Warps never meet at a CTA barrier except
+  // at the staging epochs below.
+  bool out = false;
+  for (int it = 0;; ++it) {
+    if (staging && (it & (PL_EPOCH - 1)) == 0) {
+      // staging epoch: all warps of the CTA (also those that have run out of tiles) meet, and the
+      // rows of the temperature bin the grid is currently working in are (re)staged
+      __syncthreads();     // every warp is done with the previously staged rows
+      if (s_live == 0) break;
+      if (threadIdx.x == 0) {
+        // the tile the grid will hand out next tells which temperature bin is being worked on
+        const int64_t tnext = min((int64_t)ld_ticket(A.ticket), A.n_tiles - 1);
+        const CellRec* f0 = A.recs + __ldg(A.tile_cell + tnext);
+        const int meta0 = __ldg(&f0->meta);
+        s_want = ((meta0 & 7) == 2 && !(meta0 & 8)) ? __ldg(&f0->z1) : -1;
+      }
+      __syncthreads();     // one decision for the whole CTA
+      const int w = s_want;
+      if (w >= 0 && w != tag) {
         const uint32_t row_bytes = (uint32_t)T.alias_stride * (uint32_t)sizeof(uint2);
         if (threadIdx.x == 0) {
           mbar_expect_tx(&s_bar, 4u * row_bytes);
 #pragma unroll
-          for (int slot = 0; slot < 4; ++slot)   // slot = 2 * table + (row - want)
+          for (int slot = 0; slot < 4; ++slot)   // slot = 2 * table + (row - w)
             tma_bulk_g2s(s_alias + (size_t)slot * T.alias_stride,
-                         alias_row(&T, slot >> 1, want + (slot & 1)), row_bytes, &s_bar);
+                         alias_row(&T, slot >> 1, w + (slot & 1)), row_bytes, &s_bar);
         }
         mbar_wait(&s_bar, parity);
         parity ^= 1u;
-        tag = want;
+        tag = w;
       }
     }
-
-    for (int tl = wid; tl < ntile; tl += PL_WARPS) {
-      const int64_t tile = tile0 + tl;
+    if (out) {
+      if (!staging) break;
+      continue;
+    }
+    {
+      unsigned int tk = 0;
+      if (lane == 0) tk = atomicAdd(A.ticket, 1u);
+      const int64_t tile = (int64_t)__shfl_sync(0xffffffffu, tk, 0);
+      if (tile >= A.n_tiles) {
+        out = true;
+        if (lane == 0) atomicSub(&s_live, 1);
+        if (!staging) break;
+        continue;
+      }
       const int64_t slot0 = tile * PL_TSLOTS;
       const int nslots = (int)min((int64_t)PL_TSLOTS, A.n_pairs - slot0);
       const int64_t c0 = __ldg(A.tile_cell + tile);
@@ -819,8 +848,9 @@ static int launch_pipeline(const DevModel& D, const pxb_thermal_cells& C, const 
                                   (int)sp.total));
     attr_set = sp.total + 1;
   }
-  int64_t grid = pxb_sm_count();
-  if (grid > A.n_chunks) grid = A.n_chunks;
+  int64_t grid = pxb_sm_count();                       // persistent: one CTA per SM
+  const int64_t enough = (A.n_tiles + PL_WARPS - 1) / PL_WARPS;
+  if (grid > enough) grid = enough;
   const SkyConst K = make_sky_const(&P);
   k_pipeline<MODE, SPEC><<<(unsigned)grid, PL_THREADS, sp.total, st>>>(
       D, C, P, pxb_make_keys(C.seed), pxb_make_keys(P.seed), A, K);
@@ -918,7 +948,7 @@ extern "C" int pxb_thermal_sample(const pxb_model* model, const pxb_thermal_cell
                 (long long)workspace_bytes, (long long)lay.total);
     char* ws = (char*)workspace;
     const PipeHeader H = pipe_header(ws, lay);
-    PXB_REQUIRE(lay.ntiles / PL_CHUNK_TILES < (1LL << 32) - 4096, "too many photons for one call");
+    PXB_REQUIRE(lay.ntiles < (1LL << 32) - (1 << 20), "too many photons for one call");
     PXB_CUDA(cudaMemsetAsync(ws + lay.off_hdr, 0, 256, st));
     int tab_stride = 0;
     int64_t* tabcum = nullptr;
@@ -938,7 +968,6 @@ extern "C" int pxb_thermal_sample(const pxb_model* model, const pxb_thermal_cell
     A.n_cells = n_active;
     A.n_pairs = n_pairs;
     A.n_tiles = lay.ntiles;
-    A.n_chunks = (lay.ntiles + PL_CHUNK_TILES - 1) / PL_CHUNK_TILES;
     A.ticket = H.ticket;
     A.energies = energies;
     A.off_e = sp.off_e;
@@ -991,7 +1020,6 @@ static void fill_project_args(PipeArgs& A, char* ws, const PipeLayout& lay, cons
   A.n_cells = L->n_cells;
   A.n_pairs = L->n_pairs;
   A.n_tiles = lay.ntiles;
-  A.n_chunks = (lay.ntiles + PL_CHUNK_TILES - 1) / PL_CHUNK_TILES;
   A.ticket = H.ticket;
   A.xsky = xsky;
   A.ysky = ysky;
@@ -1032,7 +1060,7 @@ extern "C" int pxb_project(const pxb_photon_list* L, const pxb_project_params* P
   PXB_REQUIRE(workspace && workspace_bytes >= lay.total,
               "projection workspace too small (%lld < %lld)", (long long)workspace_bytes,
               (long long)lay.total);
-  PXB_REQUIRE(lay.ntiles / PL_CHUNK_TILES < (1LL << 32) - 4096, "too many photons for one projection call");
+  PXB_REQUIRE(lay.ntiles < (1LL << 32) - (1 << 20), "too many photons for one projection call");
   char* ws = (char*)workspace;
   const PipeHeader H = pipe_header(ws, lay);
   // header + look-back status words are adjacent: one memset
@@ -1089,7 +1117,7 @@ extern "C" int pxb_make_events(const pxb_model* model, const pxb_thermal_cells* 
   PXB_REQUIRE(workspace && workspace_bytes >= lay.total,
               "make_events workspace too small (%lld < %lld)", (long long)workspace_bytes,
               (long long)lay.total);
-  PXB_REQUIRE(lay.ntiles / PL_CHUNK_TILES < (1LL << 32) - 4096, "too many photons for one call");
+  PXB_REQUIRE(lay.ntiles < (1LL << 32) - (1 << 20), "too many photons for one call");
   char* ws = (char*)workspace;
   const PipeHeader H = pipe_header(ws, lay);
   PXB_CUDA(cudaMemsetAsync(ws + lay.off_hdr, 0, (size_t)(lay.off_recs - lay.off_hdr), st));

@@ -163,6 +163,21 @@ class ShardedChunk(ArrayChunk):
         return id0 + (idx // blk) * stride + idx % blk
 
 
+class LocalShardChunk(ArrayChunk):
+    """A slab of an ArrayDataSource that holds ONE RANK'S block-cyclic share of a larger dataset
+    (``shard_of``): local cell i is global cell
+    ``(rank + (i // block) * size) * block + i % block``."""
+
+    def id_map(self):
+        block, rank, size = self.src.shard_of
+        return (self.src.global_offset + rank * block + (self.start // block) * block * size, block,
+                block * size)
+
+    def global_ids(self, idx):
+        id0, blk, stride = self.id_map()
+        return id0 + (idx // blk) * stride + idx % blk
+
+
 class ArrayDataSource:
     """Array-backed data object (cells or particles).
 
@@ -176,7 +191,7 @@ class ArrayDataSource:
                  right_edge=None, center=None, position_fields=None, velocity_fields=None,
                  width_field="default", units=None, chunk_size=None, cosmology=None,
                  name="ArrayDataSource", ftype="gas", rank_local=False, global_offset=0,
-                 shard_block=4096):
+                 shard_block=4096, shard_of=None):
         self.fields = dict(fields)
         self.units = dict(units or {})
         self.data_type = data_type
@@ -225,6 +240,13 @@ class ArrayDataSource:
         self.global_offset = int(global_offset)
         # cells per block of the block-cyclic split used when several ranks share this object
         self.shard_block = int(shard_block)
+        # (block, rank, size): the arrays ARE rank `rank`'s block-cyclic share of a larger dataset
+        # (every rank materialised only the cells it owns); implies rank_local
+        self.shard_of = None if shard_of is None else tuple(int(v) for v in shard_of)
+        if self.shard_of is not None:
+            self.rank_local = True
+            if self.chunk_size and self.chunk_size % self.shard_of[0]:
+                raise ValueError("chunk_size of a sharded source must be a multiple of the shard block")
 
     def chunks(self, rank=0, size=1):
         """Yield this rank's chunks.  With ``size`` > 1 the cells are split block-cyclically over
@@ -241,9 +263,10 @@ class ArrayDataSource:
             return
         cs = self.chunk_size or self.size
         starts = list(range(0, self.size, cs)) or [0]
+        kind = LocalShardChunk if self.shard_of is not None else ArrayChunk
         for j, s in enumerate(starts):
             if j % size == rank:
-                yield ArrayChunk(self, s, min(s + cs, self.size))
+                yield kind(self, s, min(s + cs, self.size))
 
     def __repr__(self):
         return f"{self.name}({self.data_type}, n={self.size})"

@@ -422,11 +422,13 @@ def _two_stage(tag, src, z, area, texp, model, normal, center, **kw):
     return (n_ph, n_c, n_ev), px.load_list(f"mem:{tag}_ev2")
 
 
-def _same_events(a, b, keys=("xsky", "ysky", "eobs")):
+def _same_events(a, b, keys=("xsky", "ysky", "eobs"), flux_rtol=0.0):
     for k in keys:
         assert np.array_equal(a.numpy(k), b.numpy(k)), k
-    for k in ("flux", "emin", "emax"):
+    for k in ("emin", "emax"):
         assert float(a.parameters[k]) == float(b.parameters[k]), k
+    # the flux is a sum over per-tile partials: identical when both runs tile the photons alike
+    assert abs(float(a.parameters["flux"]) - float(b.parameters["flux"])) <= flux_rtol * float(b.parameters["flux"])
 
 
 @pytest.mark.parametrize("case", ["common_on", "common_off", "generic_opts", "var_elem", "log_ar", "chunks"])
@@ -468,7 +470,10 @@ def test_fused_make_events_equals_the_two_stages(cuda, case, monkeypatch):
     tot1 = px.make_events(f"mem:{case}_ev1", src, z, area, texp, model(), normal, [30.0, 45.0], **kw)
     assert tot1 == tot2 and tot1[2] > 1.0e5
     ev1 = px.load_list(f"mem:{case}_ev1")
-    _same_events(ev1, ev2, ("xsky", "ysky", "eobs") + (("los",) if kw.get("save_los") else ()))
+    # (with several chunks the fused path sums the flux chunk by chunk, the two-stage path over the
+    # concatenated list: same events, the sum differs in the last bits)
+    _same_events(ev1, ev2, ("xsky", "ysky", "eobs") + (("los",) if kw.get("save_los") else ()),
+                 flux_rtol=1e-13 if case == "chunks" else 0.0)
     assert ev1.parameters["absoption_model"] == ev2.parameters["absoption_model"]
     if case == "common_on":
         # the option-generic fused kernel gives the same list as well
