@@ -429,6 +429,12 @@ int pxb_make_events(const pxb_model* model, const pxb_thermal_cells* cells, cons
                     double* stats_out, int64_t* n_declined_out, void* workspace,
                     int64_t workspace_bytes, void* stream);
 
+/* Diagnostic: the variant of the photon kernel the calling thread's last pxb_thermal_sample /
+ * pxb_project / pxb_make_events launched: mode 0 sample, 1 project, 2 fused; spec 0 = option-generic
+ * kernel, 1 / 2 = compiled for the common option set (on- / off-axis); staged = table rows kept in
+ * shared memory.  Returns PXB_ERR_INVALID before the first launch. */
+int pxb_last_pipeline_launch(int* mode, int* spec, int* staged);
+
 /* In-place Doppler shift with per-cell factors (sky_functions.pyx:20-34). */
 int pxb_doppler_shift(int64_t n_cells, const double* beta_n, const double* beta2,
                       const int64_t* poff, int64_t n_photons, double* eobs, void* stream);

@@ -149,6 +149,7 @@ SIGNATURES = {
     "pxb_make_events": (C.c_int, [c_void_p, _P(ThermalCells), c_void_p, _P(PhotonList),
                                   _P(ProjectParams), c_void_p, c_void_p, c_void_p, c_void_p,
                                   c_void_p, c_void_p, c_void_p, c_void_p, C.c_int64, c_void_p]),
+    "pxb_last_pipeline_launch": (C.c_int, [_P(C.c_int), _P(C.c_int), _P(C.c_int)]),
     "pxb_absorb_decide_words": (C.c_int, [_P(ProjectParams), C.c_int64, c_void_p, c_void_p,
                                           C.c_uint64, C.c_uint64, c_void_p, c_void_p]),
     "pxb_thermal_spectrum_workspace_bytes": (C.c_int, [c_void_p, C.c_int64, _P(C.c_int64)]),
@@ -239,6 +240,13 @@ def check(status):
 
 def call(name, *args):
     check(getattr(load(), name)(*args))
+
+
+def last_pipeline_launch():
+    """(mode, spec, staged) of the photon kernel this thread launched last (see pxb.h)."""
+    m, s, g = C.c_int(-1), C.c_int(-1), C.c_int(-1)
+    load().pxb_last_pipeline_launch(C.byref(m), C.byref(s), C.byref(g))
+    return m.value, s.value, g.value
 
 
 def launch_count():

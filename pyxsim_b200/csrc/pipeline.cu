@@ -140,6 +140,7 @@ __device__ __forceinline__ int64_t warp_lookback(unsigned long long* status, int
   if (lane == 0) st_status(status + tile, ST_AGG | (unsigned long long)total);
   int64_t prefix = 0;
   int64_t j = tile - 1;
+  unsigned nap = 128;    // back-off: a waiting warp must not eat the issue slots of the one it waits for
   for (;;) {
     const int64_t idx = j - lane;
     unsigned long long sv = (idx >= 0) ? ld_status(status + idx) : ST_INC;
@@ -148,7 +149,8 @@ __device__ __forceinline__ int64_t warp_lookback(unsigned long long* status, int
     const int first = inc ? (__ffs(inc) - 1) : 32;           // nearest tile with an inclusive prefix
     const unsigned need = first >= 31 ? 0xffffffffu : ((2u << first) - 1u);
     if (emp & need) {                                        // a needed predecessor is not ready
-      __nanosleep(200);
+      __nanosleep(nap);
+      nap = min(nap * 2u, 4096u);
       continue;
     }
     int64_t v = (lane <= first) ? (int64_t)(sv & ~ST_MASK) : 0;
@@ -478,12 +480,14 @@ k_pipeline(const DevModel M, const __grid_constant__ pxb_thermal_cells C,
       const int nslots = (int)min((int64_t)PL_TSLOTS, A.n_pairs - slot0);
       const int64_t c0 = __ldg(A.tile_cell + tile);
       const int64_t c1 = (tile + 1 < A.n_tiles) ? __ldg(A.tile_cell + tile + 1) : A.n_cells - 1;
-      // cell starts of the tile, relative to its first slot (clamped: only the order matters).
+      // cell starts of the tile, relative to its first slot (the first cell's is clamped to -1:
+      // only the order matters for the look-up).
       // how = 0: every cell of the tile is non-empty -> ballot look-up; 1: empty cells (lists from
       // elsewhere) -> shared-memory bisection; 2: more cells than fit -> global bisection.
       const int64_t ncl = c1 - c0 + 1;
       const int nc = ncl <= PL_MAXC ? (int)ncl : 0;
       int how = nc == 0 ? 2 : 0;
+      const int64_t m00 = slot0 - __ldg(A.qoff + c0);      // pair index of slot 0 inside cell c0
       __syncwarp();
       {
         bool dup = false;
@@ -496,35 +500,52 @@ k_pipeline(const DevModel M, const __grid_constant__ pxb_thermal_cells C,
       }
       __syncwarp();
 
-      // cell of pair slot srel of this tile (relative to c0)
-      auto find_cell = [&](int r, int srel) -> int64_t {
-        if (how == 0) {
-          int cnt_le = 0;   // cells starting at or before the slot
-          for (int qb = 0; qb < nc; qb += 32) {
-            const int q = qb + lane;
-            const int qs = q < nc ? s_qs[q] : 0x7fffffff;
+      // Cell of every pair slot of the tile, relative to c0, for the four rounds at once (one
+      // byte per round; PL_MAXC < 256).  how = 0: the cell of a slot is the number of cells
+      // starting at or before it, minus one -- a ballot for the cells that start before the
+      // round's 32 slots plus a warp-wide OR of start bits inside them.
+      unsigned relpack = 0;
+      if (how == 0) {
+        unsigned cnt = 0;
+        for (int qb = 0; qb < nc; qb += 32) {
+          const int q = qb + lane;
+          const int qs = q < nc ? s_qs[q] : 0x7fffffff;
+#pragma unroll
+          for (int r = 0; r < PL_ROUNDS; ++r) {
             const unsigned before = __ballot_sync(0xffffffffu, qs < r * 32);
             const unsigned d = (unsigned)(qs - r * 32);
             const unsigned mask = __reduce_or_sync(0xffffffffu, d < 32u ? (1u << d) : 0u);
-            cnt_le += __popc(before) + __popc(mask & ((2u << lane) - 1u));
+            cnt += (unsigned)(__popc(before) + __popc(mask & ((2u << lane) - 1u))) << (8 * r);
           }
-          return (int64_t)(cnt_le - 1);
         }
-        if (how == 1) {
+        relpack = cnt - 0x01010101u;    // (every byte is >= 1: cell c0 starts at or before slot 0)
+      } else if (how == 1) {
+#pragma unroll
+        for (int r = 0; r < PL_ROUNDS; ++r) {
+          const int srel = min(r * 32 + lane, nslots - 1);
           int rel = 0;   // largest q with s_qs[q] <= srel
           for (int step = 128; step > 0; step >>= 1) {
             const int q = rel + step;
             if (q < nc && s_qs[q] <= srel) rel = q;
           }
-          return (int64_t)rel;
+          relpack |= (unsigned)rel << (8 * r);
         }
-        const int64_t slot = slot0 + srel;
-        int64_t lo = c0, hi = c1 + 1;   // qoff[lo] <= slot < qoff[hi]
-        while (hi - lo > 1) {
-          const int64_t mid = (lo + hi) >> 1;
-          if (__ldg(A.qoff + mid) <= slot) lo = mid; else hi = mid;
+      }
+      // (cell relative to c0, pair index inside the cell) of slot r*32 + lane
+      auto locate = [&](int r, int srel, int& rel, int64_t& m) {
+        if (how != 2) {
+          rel = (int)((relpack >> (8 * r)) & 255u);
+          m = rel == 0 ? m00 + srel : (int64_t)(srel - s_qs[rel]);
+        } else {
+          const int64_t slot = slot0 + min(srel, nslots - 1);
+          int64_t lo = c0, hi = c1 + 1;   // qoff[lo] <= slot < qoff[hi]
+          while (hi - lo > 1) {
+            const int64_t mid = (lo + hi) >> 1;
+            if (__ldg(A.qoff + mid) <= slot) lo = mid; else hi = mid;
+          }
+          rel = (int)(lo - c0);
+          m = slot0 + srel - __ldg(A.qoff + lo);
         }
-        return lo - c0;
       };
 
       // ---- phase 1: energies (sampled or loaded), Doppler shift, absorption decisions --------
@@ -536,13 +557,13 @@ k_pipeline(const DevModel M, const __grid_constant__ pxb_thermal_cells C,
         if (r * 32 >= nslots) break;
         const int srel = r * 32 + lane;
         const bool valid = srel < nslots;
-        const int64_t rel = find_cell(r, valid ? srel : nslots - 1);
-        const int64_t c = c0 + rel;
-        const CellRec* rp = A.recs + c;
+        int rel;
+        int64_t m;
+        locate(r, srel, rel, m);
+        const CellRec* rp = A.recs + (c0 + rel);
         const longlong2 q0 = __ldg(reinterpret_cast<const longlong2*>(rp));
         const longlong2 q1 = __ldg(reinterpret_cast<const longlong2*>(rp) + 1);
         const uint64_t gid = (uint64_t)q0.x;
-        const int64_t m = slot0 + srel - __ldg(A.qoff + c);
         const uint64_t d0 = 2ull * (uint64_t)m;
         const bool hasA = valid;
         const bool hasB = valid && (int64_t)(d0 + 1) < q1.y;
@@ -555,56 +576,57 @@ k_pipeline(const DevModel M, const __grid_constant__ pxb_thermal_cells C,
           const long long cn0 = q2.y, cn1 = q3.x, cn2 = q3.y;
           elig = (meta & 16) != 0;
           if (valid && elig) {
-            if (SPEC != 0 || (meta & 32)) {
-              // four-component split: (row0,cosmic), (row0,metal), (row1,cosmic), (row1,metal)
+            if (SPEC != 0 || (meta & (32 | 64))) {
+              // split modes: the photon's component follows from its index inside the cell
               const Philox4 E = pxb_rand4(RKE, STREAM_ENERGY, gid, (uint64_t)m);
               const bool prim = SPEC != 0 || !(meta & 8);
               const DevTable* tb = prim ? &M.prim : &M.fb;
+              const bool four = SPEC != 0 || (meta & 32);
+              // counts below 2^31: 32-bit compares (any cell in practice)
+              const bool small = q1.y < 0x7fffffffll;
 #pragma unroll
               for (int h = 0; h < 2; ++h) {
                 const long long dd = (long long)d0 + h;
-                const int comp = (dd >= cn0) + (dd >= cn1) + (dd >= cn2);
-                const int row = z1 + (comp >> 1);
-                const unsigned dr = (unsigned)(row - tag);
-                const uint2* ar = (prim && tag >= 0 && dr < 2u)
-                                      ? s_alias + (size_t)((comp & 1) * 2 + (int)dr) * T.alias_stride
-                                      : alias_row(tb, comp & 1, row);
-                uint32_t v;
-                const int j = alias_pick(ar, (unsigned)T.nbins, h ? E.z : E.x, h ? E.w : E.y, v);
-                const double e = alias_energy<(SPEC != 0) ? 1 : 0>(M, j, v);
-                if (h) eB = e; else eA = e;
-              }
-            } else if (meta & 64) {
-              // general split: row from the cumulative row counts, table from the side array
-              const Philox4 E = pxb_rand4(RKE, STREAM_ENERGY, gid, (uint64_t)m);
-              const bool prim = !(meta & 8);
-              const DevTable* tb = prim ? &M.prim : &M.fb;
-              const int ntab = 2 + C.nvar;
-#pragma unroll
-              for (int h = 0; h < 2; ++h) {
-                const long long dd = (long long)d0 + h;
-                const int rr = (dd >= cn0) + (dd >= cn1) + (dd >= cn2);
-                const long long din = dd - (rr == 0 ? 0 : (rr == 1 ? cn0 : (rr == 2 ? cn1 : cn2)));
-                const int64_t* tc = A.tabcum + c * A.tab_stride + rr * ntab;
-                int tab = 0;
-                if (ntab <= 8) {
-                  for (int t2 = 0; t2 < ntab - 1; ++t2) tab += (din >= __ldg(tc + t2)) ? 1 : 0;
+                int comp;
+                if (small) {
+                  const int d32 = (int)dd;
+                  comp = (d32 >= (int)cn0) + (d32 >= (int)cn1) + (d32 >= (int)cn2);
                 } else {
-                  int lo = 0, hi = ntab - 1;     // first tab with din < tc[tab]
-                  while (lo < hi) {
-                    const int mid = (lo + hi) >> 1;
-                    if (din >= __ldg(tc + mid)) lo = mid + 1; else hi = mid;
-                  }
-                  tab = lo;
+                  comp = (dd >= cn0) + (dd >= cn1) + (dd >= cn2);
                 }
-                const int row = fast_row(tb, z1, meta & 7, rr);
+                int tab, row;
+                if (four) {
+                  // four components: (row0,cosmic), (row0,metal), (row1,cosmic), (row1,metal)
+                  tab = comp & 1;
+                  row = z1 + (comp >> 1);
+                } else {
+                  // general split: comp is the ROW, the table comes from the side array
+                  const long long din = dd - (comp == 0 ? 0 : (comp == 1 ? cn0 : (comp == 2 ? cn1 : cn2)));
+                  const int ntab = 2 + C.nvar;
+                  const int64_t* tc = A.tabcum + (c0 + rel) * A.tab_stride + comp * ntab;
+                  tab = 0;
+                  if (ntab <= 8) {
+                    for (int t2 = 0; t2 < ntab - 1; ++t2) tab += (din >= __ldg(tc + t2)) ? 1 : 0;
+                  } else {
+                    int lo = 0, hi = ntab - 1;     // first tab with din < tc[tab]
+                    while (lo < hi) {
+                      const int mid = (lo + hi) >> 1;
+                      if (din >= __ldg(tc + mid)) lo = mid + 1; else hi = mid;
+                    }
+                    tab = lo;
+                  }
+                  row = fast_row(tb, z1, meta & 7, comp);
+                }
+                const uint32_t w0 = h ? E.z : E.x, w1 = h ? E.w : E.y;
                 const unsigned dr = (unsigned)(row - tag);
-                const uint2* ar = (prim && tab < 2 && tag >= 0 && dr < 2u)
-                                      ? s_alias + (size_t)(tab * 2 + (int)dr) * T.alias_stride
-                                      : alias_row(tb, tab, row);
                 uint32_t v;
-                const int j = alias_pick(ar, (unsigned)T.nbins, h ? E.z : E.x, h ? E.w : E.y, v);
-                const double e = alias_energy<0>(M, j, v);
+                int j;
+                if (prim && tab < 2 && tag >= 0 && dr < 2u)   // staged row: shared-memory gather
+                  j = alias_pick(s_alias + (unsigned)(tab * 2 + (int)dr) * (unsigned)T.alias_stride,
+                                 (unsigned)T.nbins, w0, w1, v);
+                else
+                  j = alias_pick(alias_row(tb, tab, row), (unsigned)T.nbins, w0, w1, v);
+                const double e = alias_energy<(SPEC != 0) ? 1 : 0>(M, j, v);
                 if (h) eB = e; else eA = e;
               }
             } else {
@@ -613,7 +635,7 @@ k_pipeline(const DevModel M, const __grid_constant__ pxb_thermal_cells C,
               fc.z1 = z1;
               fc.meta = meta;
               fc.cnt[0] = cn0; fc.cnt[1] = cn1; fc.cnt[2] = cn2;
-              const int64_t i = __ldg(A.idx + c);
+              const int64_t i = __ldg(A.idx + c0 + rel);
 #pragma unroll
               for (int h = 0; h < 2; ++h) {
                 if (h && !hasB) break;
@@ -653,8 +675,8 @@ k_pipeline(const DevModel M, const __grid_constant__ pxb_thermal_cells C,
           const Philox4 Aw = pxb_rand4(RKP, STREAM_PROJ_A, gid, (uint64_t)m);
           Philox4 Dw{0u, 0u, 0u, 0u};
           if (SPEC == 0 && P.nH_cell) Dw = pxb_rand4(RKP, STREAM_PROJ_D, gid, (uint64_t)m);
-          if (detA) detA = absorb_decision<SPEC>(P, RKP, s_wabs, c, gid, d0, Aw.x, Dw.x, eA);
-          if (detB) detB = absorb_decision<SPEC>(P, RKP, s_wabs, c, gid, d0 + 1, Aw.y, Dw.y, eB);
+          if (detA) detA = absorb_decision<SPEC>(P, RKP, s_wabs, c0 + rel, gid, d0, Aw.x, Dw.x, eA);
+          if (detB) detB = absorb_decision<SPEC>(P, RKP, s_wabs, c0 + rel, gid, d0 + 1, Aw.y, Dw.y, eB);
         }
         s_e[2 * srel] = eA;
         s_e[2 * srel + 1] = eB;
@@ -688,6 +710,11 @@ k_pipeline(const DevModel M, const __grid_constant__ pxb_thermal_cells C,
       if (run == 0) continue;                                   // everything absorbed
 
       // ---- phase 3: scatter the survivors into their final, order-preserving slots -----------
+      // (tile-uniform 64-bit bases, 32-bit offsets inside the tile)
+      double* const xb = A.xsky + base;
+      double* const yb = A.ysky + base;
+      double* const eb = A.eobs + base;
+      double* const lb = A.los ? A.los + base : nullptr;
       int done = 0;
 #pragma unroll 1
       for (int r = 0; r < PL_ROUNDS; ++r) {
@@ -695,16 +722,16 @@ k_pipeline(const DevModel M, const __grid_constant__ pxb_thermal_cells C,
         const bool detA = (detpack >> (2 * r)) & 1u, detB = (detpack >> (2 * r + 1)) & 1u;
         const unsigned balA = __ballot_sync(0xffffffffu, detA), balB = __ballot_sync(0xffffffffu, detB);
         if (!(balA | balB)) continue;
-        const int srel = r * 32 + lane;
-        const int64_t rel = find_cell(r, srel < nslots ? srel : nslots - 1);
-        const int64_t o0 = base + done + __popc(balA & lt) + __popc(balB & lt);
+        const int o0 = done + __popc(balA & lt) + __popc(balB & lt);
         done += __popc(balA) + __popc(balB);
         if (!(detA || detB)) continue;
-        const int64_t c = c0 + rel;
-        const uint64_t gid = (uint64_t)__ldg(&A.recs[c].gid);
-        const int64_t m = slot0 + srel - __ldg(A.qoff + c);
+        const int srel = r * 32 + lane;
+        int rel;
+        int64_t m;
+        locate(r, srel, rel, m);
+        const uint64_t gid = (uint64_t)__ldg(&A.recs[c0 + rel].gid);
         const uint64_t d0 = 2ull * (uint64_t)m;
-        const CellGeom g = ld_geom(A.geom + c);
+        const CellGeom g = ld_geom(A.geom + c0 + rel);
         const Philox4 Bw = pxb_rand4(RKP, STREAM_PROJ_B, gid, (uint64_t)m);
         // the third scatter word lives in the absorption block: recomputed only where it is used
         // (off-axis cells, particle kernels, all-sky)
@@ -720,11 +747,11 @@ k_pipeline(const DevModel M, const __grid_constant__ pxb_thermal_cells C,
             scatter_external<SPEC>(P, RKP, g, K, w0, w1, w2, gid, d0 + h, xs, ys, los);
           else
             scatter_allsky(P, RKP, g, w0, w1, w2, gid, d0 + h, xs, ys, los);
-          const int64_t o = o0 + (h && detA ? 1 : 0);
-          st_stream(A.xsky + o, xs);
-          st_stream(A.ysky + o, ys);
-          st_stream(A.eobs + o, s_e[2 * srel + h]);
-          if (A.los) st_stream(A.los + o, los);
+          const int o = o0 + (h && detA ? 1 : 0);
+          st_stream(xb + o, xs);
+          st_stream(yb + o, ys);
+          st_stream(eb + o, s_e[2 * srel + h]);
+          if (lb) st_stream(lb + o, los);
         }
       }
     }
@@ -839,6 +866,16 @@ static SmemPlan smem_plan(const DevModel* D, int mode) {
   return s;
 }
 
+// which variant of the photon kernel the last pxb_thermal_sample / pxb_project / pxb_make_events of
+// this thread launched (diagnostic: lets a test assert that the path it means to test was taken)
+static thread_local int g_last_mode = -1, g_last_spec = -1, g_last_staged = -1;
+extern "C" int pxb_last_pipeline_launch(int* mode, int* spec, int* staged) {
+  if (mode) *mode = g_last_mode;
+  if (spec) *spec = g_last_spec;
+  if (staged) *staged = g_last_staged;
+  return g_last_mode < 0 ? PXB_ERR_INVALID : PXB_OK;
+}
+
 template <int MODE, int SPEC>
 static int launch_pipeline(const DevModel& D, const pxb_thermal_cells& C, const pxb_project_params& P,
                            PipeArgs A, const SmemPlan& sp, cudaStream_t st) {
@@ -852,6 +889,9 @@ static int launch_pipeline(const DevModel& D, const pxb_thermal_cells& C, const 
   const int64_t enough = (A.n_tiles + PL_WARPS - 1) / PL_WARPS;
   if (grid > enough) grid = enough;
   const SkyConst K = make_sky_const(&P);
+  g_last_mode = MODE;
+  g_last_spec = SPEC;
+  g_last_staged = MODE != MODE_PROJECT && A.use_staging;
   k_pipeline<MODE, SPEC><<<(unsigned)grid, PL_THREADS, sp.total, st>>>(
       D, C, P, pxb_make_keys(C.seed), pxb_make_keys(P.seed), A, K);
   PXB_LAUNCH_CHECK();

@@ -134,6 +134,25 @@ __device__ __forceinline__ void tan_to_cel_fast(double x, double y, double ra0_r
                                                 double sin_d0, double cos_d0, double& ra_deg,
                                                 double& dec_deg) {
   const double den = cos_d0 - y * sin_d0;
+  {
+    // Within ~0.9 degrees of the centre: one reciprocal, no square root.  With r = 1/den,
+    // t1 = -x r and q = t1^2:  s = hypot(x, den) - den = (x^2 r / 2)(1 - q/4 + q^2/8 - 5q^3/64 +
+    // 7q^4/128) and 1/(1 + s cos d0) by its geometric series (s <= 1.3e-4); both truncation errors
+    // are below 2e-16 relative, the arctangent series can stop at t^9 (next term < 8e-20).
+    const double r = 1.0 / den;
+    const double t1 = -x * r;
+    if (den > 0.0 && fabs(t1) <= 0.015625 && fabs(y) <= 0.015625) {
+      const double q = t1 * t1;
+      const double s = 0.5 * x * x * r * (1.0 + q * (-0.25 + q * (0.125 + q * (-5.0 / 64.0 + q * (7.0 / 128.0)))));
+      const double e = s * cos_d0;
+      const double t2 = (y - s * sin_d0) * (1.0 + e * (-1.0 + e * (1.0 + e * (-1.0 + e))));
+      if (fabs(t2) <= 0.015625) {
+        ra_deg = (ra0_rad + atan_tiny(t1)) * PXB_RAD2DEG;
+        dec_deg = (d0_rad + atan_tiny(t2)) * PXB_RAD2DEG;
+        return;
+      }
+    }
+  }
   const double h = sqrt(x * x + den * den);
   // three quotients x^2/(h+den), -x/den, num2/den2 share one reciprocal
   const double hd = h + den;
@@ -142,11 +161,7 @@ __device__ __forceinline__ void tan_to_cel_fast(double x, double y, double ra0_r
   const double inv = 1.0 / (den * den2);
   const double t1 = -x * den2 * inv;
   const double t2 = num2 * den * inv;
-  if (den > 0.0 && fabs(t1) <= 0.015625 && fabs(t2) <= 0.015625) {
-    // within ~0.9 degrees of the centre the series can stop at t^9 (next term < 8e-20 relative)
-    ra_deg = (ra0_rad + atan_tiny(t1)) * PXB_RAD2DEG;
-    dec_deg = (d0_rad + atan_tiny(t2)) * PXB_RAD2DEG;
-  } else if (den > 0.0 && fabs(t1) <= 0.0625 && fabs(t2) <= 0.0625) {
+  if (den > 0.0 && fabs(t1) <= 0.0625 && fabs(t2) <= 0.0625) {
     ra_deg = (ra0_rad + atan_small(t1)) * PXB_RAD2DEG;
     dec_deg = (d0_rad + atan_small(t2)) * PXB_RAD2DEG;
   } else {
