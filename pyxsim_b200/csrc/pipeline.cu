@@ -31,10 +31,22 @@ enum { MODE_SAMPLE = 0, MODE_PROJECT = 1, MODE_FUSED = 2 };
 
 constexpr int PL_THREADS = 1024;
 constexpr int PL_WARPS = PL_THREADS / 32;
-constexpr int PL_ROUNDS = 4;
-constexpr int PL_TSLOTS = 32 * PL_ROUNDS;          // pair slots per warp tile
 constexpr int PL_EPOCH = 16;                       // tiles per warp between two staging decisions
-constexpr int PL_MAXC = PL_TSLOTS + 4;             // cell starts staged per tile (>= 129)
+constexpr int PL_BATCH = 32;                       // tiles a CTA draws from the global ticket at a time
+
+// Tile geometry per mode.  A warp tile is ROUNDS x 32 pair slots.  The sampler keeps nothing
+// between rounds and takes 128-slot tiles; the modes that project keep a tile's energies in
+// shared memory from the absorption decisions to the scatter step, DOUBLE buffered (a tile whose
+// predecessors have not all reported yet is finished after the next tile's decisions instead of
+// waiting), so their tiles are 64 slots.
+template <int MODE>
+struct Tiling {
+  static constexpr int ROUNDS = MODE == 0 ? 4 : 2;
+  static constexpr int TSLOTS = 32 * ROUNDS;       // pair slots per warp tile
+  static constexpr int MAXC = TSLOTS + 4;          // cell starts staged per tile
+  static constexpr int NBUF = MODE == 0 ? 1 : 2;
+};
+static inline int tslots_of(int mode) { return mode == 0 ? Tiling<0>::TSLOTS : Tiling<1>::TSLOTS; }
 
 // everything the photon kernels need of an active cell: 64 bytes, four 16-byte loads
 struct __align__(16) CellRec {
@@ -128,20 +140,18 @@ __device__ __forceinline__ void st_status(unsigned long long* p, unsigned long l
   asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v));
 }
 
-// exclusive prefix of the counts of all earlier tiles; whole warp participates.  Progress: tiles
-// are handed out in increasing order to CTAs that are all resident, and a warp publishes its
-// aggregate before it waits, so every predecessor a warp waits on is being worked on.
-__device__ __forceinline__ int64_t warp_lookback(unsigned long long* status, int64_t tile,
-                                                 int64_t total, int lane) {
-  if (tile == 0) {
-    if (lane == 0) st_status(status, ST_INC | (unsigned long long)total);
-    return 0;
-  }
-  if (lane == 0) st_status(status + tile, ST_AGG | (unsigned long long)total);
-  int64_t prefix = 0;
-  int64_t j = tile - 1;
-  unsigned nap = 128;    // back-off: a waiting warp must not eat the issue slots of the one it waits for
+// Exclusive prefix of the counts of all earlier tiles, resumable: walks back from tile `j` over
+// the status words, adding aggregates until it meets an inclusive prefix.  Returns true when the
+// prefix is complete; with blocking = false it returns false as soon as a needed predecessor has
+// not reported yet (the caller does something useful and comes back), keeping its progress in
+// (j, prefix).  Whole warp participates.  Progress: a warp publishes its aggregate before it looks
+// back, tiles are handed out in increasing order, and a tile whose aggregate is missing is being
+// worked on by a resident warp that waits for nothing.
+__device__ __forceinline__ bool lookback_run(const unsigned long long* status, int64_t& j,
+                                             int64_t& prefix, int lane, bool blocking) {
+  unsigned nap = 64;   // back-off: a waiting warp must not eat the issue slots of the one it waits for
   for (;;) {
+    if (j < 0) return true;                                   // walked past tile 0
     const int64_t idx = j - lane;
     unsigned long long sv = (idx >= 0) ? ld_status(status + idx) : ST_INC;
     const unsigned inc = __ballot_sync(0xffffffffu, (sv & ST_MASK) == ST_INC);
@@ -149,19 +159,18 @@ __device__ __forceinline__ int64_t warp_lookback(unsigned long long* status, int
     const int first = inc ? (__ffs(inc) - 1) : 32;           // nearest tile with an inclusive prefix
     const unsigned need = first >= 31 ? 0xffffffffu : ((2u << first) - 1u);
     if (emp & need) {                                        // a needed predecessor is not ready
+      if (!blocking) return false;
       __nanosleep(nap);
-      nap = min(nap * 2u, 4096u);
+      nap = min(nap * 2u, 2048u);
       continue;
     }
     int64_t v = (lane <= first) ? (int64_t)(sv & ~ST_MASK) : 0;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     prefix += v;
-    if (first < 32) break;
+    if (first < 32) return true;
     j -= 32;
   }
-  if (lane == 0) st_status(status + tile, ST_INC | (unsigned long long)(prefix + total));
-  return prefix;
 }
 
 // ---------------------------------------------------------------------------------------
@@ -176,8 +185,9 @@ __device__ __forceinline__ void rec_set_fast(CellRec& r, const FastCell& fc) {
 }
 
 // every pair tile that starts inside the cell's slot range starts in this cell
-__device__ __forceinline__ void mark_tiles(int64_t* tile_cell, int64_t qa, int64_t qb, int64_t k) {
-  for (int64_t t = (qa + PL_TSLOTS - 1) / PL_TSLOTS; t * PL_TSLOTS < qb; ++t) tile_cell[t] = k;
+__device__ __forceinline__ void mark_tiles(int64_t* tile_cell, int64_t qa, int64_t qb, int64_t k,
+                                           int tslots) {
+  for (int64_t t = (qa + tslots - 1) / tslots; t * tslots < qb; ++t) tile_cell[t] = k;
 }
 
 // Sampling side: one thread per ACTIVE cell computes the cell's mixture weights and, where it
@@ -192,7 +202,7 @@ k_prep_sample(const DevModel M, const __grid_constant__ pxb_thermal_cells C, int
               int64_t* __restrict__ tile_cell, int64_t* __restrict__ list,
               unsigned long long* __restrict__ list_count, int64_t* __restrict__ tabcum,
               int64_t* __restrict__ glist, unsigned long long* __restrict__ glist_count,
-              int split_factor) {
+              int split_factor, int tslots) {
   const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   bool want_general = false;
   if (k < n_active) {
@@ -212,7 +222,7 @@ k_prep_sample(const DevModel M, const __grid_constant__ pxb_thermal_cells C, int
       const unsigned long long slot = atomicAdd(list_count, 1ull);
       list[slot] = k;
     }
-    mark_tiles(tile_cell, qoff[k], qoff[k + 1], k);
+    mark_tiles(tile_cell, qoff[k], qoff[k + 1], k, tslots);
   }
   // cells that want the general split: one warp-aggregated append
   const unsigned bal = __ballot_sync(0xffffffffu, want_general);
@@ -250,7 +260,7 @@ template <bool INIT>
 __global__ void __launch_bounds__(256)
 k_prep_project(const __grid_constant__ pxb_photon_list L, const __grid_constant__ pxb_project_params P,
                CellRec* __restrict__ recs, CellGeom* __restrict__ geom,
-               int64_t* __restrict__ tile_cell) {
+               int64_t* __restrict__ tile_cell, int tslots) {
   const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= L.n_cells) return;
   const double x = L.x[c], y = L.y[c], z = L.z[c];
@@ -279,7 +289,7 @@ k_prep_project(const __grid_constant__ pxb_photon_list L, const __grid_constant_
     r.meta = 16;
     r.c0 = r.c1 = r.c2 = 0;
     recs[c] = r;
-    mark_tiles(tile_cell, L.qoff[c], L.qoff[c + 1], c);
+    mark_tiles(tile_cell, L.qoff[c], L.qoff[c + 1], c, tslots);
   } else {
     recs[c].shift = shift;
   }
@@ -406,33 +416,61 @@ k_pipeline(const DevModel M, const __grid_constant__ pxb_thermal_cells C,
            const __grid_constant__ pxb_project_params P, const __grid_constant__ PhiloxKeys RKE,
            const __grid_constant__ PhiloxKeys RKP, const __grid_constant__ PipeArgs A,
            const SkyConst K) {
+  constexpr int ROUNDS = Tiling<MODE>::ROUNDS, TSLOTS = Tiling<MODE>::TSLOTS;
+  constexpr int MAXC = Tiling<MODE>::MAXC, NBUF = Tiling<MODE>::NBUF;
   // dynamic shared memory: [4 staged alias rows | per-warp energies | per-warp cell starts]
   extern __shared__ __align__(128) unsigned char dyn[];
   const DevTable& T = M.prim;
   uint2* s_alias = reinterpret_cast<uint2*>(dyn);
   __shared__ uint64_t s_bar;
   __shared__ int s_live, s_want;
+  __shared__ unsigned long long s_tk;                  // CTA ticket cache: (batch << 32) | tiles taken
+  __shared__ long long s_pend[PL_WARPS][2][4];         // per warp and buffer: tile, prefix, j, info
   __shared__ WabsFast s_wabs;
 
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  double* s_e = reinterpret_cast<double*>(dyn + A.off_e) + (size_t)wid * (2 * PL_TSLOTS);
-  int* s_qs = reinterpret_cast<int*>(dyn + A.off_qs) + (size_t)wid * PL_MAXC;
+  // (32-bit offsets into the dynamic shared memory: the buffers are addressed as shared memory)
+  const unsigned se_off = (unsigned)A.off_e + (unsigned)wid * (unsigned)(NBUF * 2 * TSLOTS * sizeof(double));
+  const unsigned qs_off = (unsigned)A.off_qs + (unsigned)wid * (unsigned)(NBUF * MAXC * sizeof(int));
   if (MODE != MODE_SAMPLE && P.absorb_kind == PXB_ABS_WABS) wabs_fast_init(s_wabs);
-  if (threadIdx.x == 0) mbar_init(&s_bar, 1);
+  if (threadIdx.x == 0) {
+    mbar_init(&s_bar, 1);
+    s_live = PL_WARPS;
+    s_tk = (0xFFFFFFFFull << 32) | (unsigned long long)PL_BATCH;    // empty: the first taker refills
+  }
   __syncthreads();
   int tag = -1;
   uint32_t parity = 0;
   const unsigned lt = (1u << lane) - 1u;
   const bool absorb = MODE != MODE_SAMPLE && P.absorb_kind != PXB_ABS_NONE;
   const bool staging = MODE != MODE_PROJECT && A.use_staging;
-  if (threadIdx.x == 0) s_live = PL_WARPS;
-  __syncthreads();
 
-  // Every WARP draws its tiles one at a time from a global ticket: tiles are then started in
-  // increasing order across the whole grid, which is what keeps the look-back short (a tile only
-  // ever waits for tiles that were started before it).  Warps never meet at a CTA barrier except
-  // at the staging epochs below.
-  bool out = false;
+  // (cell relative to c0, pair index inside the cell) of slot r*32 + lane of a tile
+  auto locate = [&](int how, unsigned relpack, const int* s_qs, int64_t slot0, int nslots, int64_t c0,
+                    int64_t c1, int64_t m00, int r, int srel, int& rel, int64_t& m) {
+    if (how != 2) {
+      rel = (int)((relpack >> (8 * r)) & 255u);
+      m = rel == 0 ? m00 + srel : (int64_t)(srel - s_qs[rel]);
+    } else {
+      const int64_t slot = slot0 + min(srel, nslots - 1);
+      int64_t lo = c0, hi = c1 + 1;   // qoff[lo] <= slot < qoff[hi]
+      while (hi - lo > 1) {
+        const int64_t mid = (lo + hi) >> 1;
+        if (__ldg(A.qoff + mid) <= slot) lo = mid; else hi = mid;
+      }
+      rel = (int)(lo - c0);
+      m = slot0 + srel - __ldg(A.qoff + lo);
+    }
+  };
+
+  // Every WARP takes its tiles one at a time, in increasing order over the whole grid (a global
+  // ticket hands batches of 32 tiles to a CTA, the CTA's warps take them from shared memory), so
+  // a tile only ever waits for tiles that were started before it.  Warps never meet at a CTA
+  // barrier except at the staging epochs below.
+  bool out = false;            // no more tiles to draw
+  bool have_pend = false;      // a tile whose decisions are made and whose scatter step is still due
+  unsigned pend_bits = 0;      // its per-lane survivor bits and cell bytes
+  int buf = 0;
   for (int it = 0;; ++it) {
     if (staging && (it & (PL_EPOCH - 1)) == 0) {
       // staging epoch: all warps of the CTA (also those that have run out of tiles) meet, and the
@@ -441,7 +479,7 @@ k_pipeline(const DevModel M, const __grid_constant__ pxb_thermal_cells C,
       if (s_live == 0) break;
       if (threadIdx.x == 0) {
         // the tile the grid will hand out next tells which temperature bin is being worked on
-        const int64_t tnext = min((int64_t)ld_ticket(A.ticket), A.n_tiles - 1);
+        const int64_t tnext = min((int64_t)ld_ticket(A.ticket) * PL_BATCH, A.n_tiles - 1);
         const CellRec* f0 = A.recs + __ldg(A.tile_cell + tnext);
         const int meta0 = __ldg(&f0->meta);
         s_want = ((meta0 & 7) == 2 && !(meta0 & 8)) ? __ldg(&f0->z1) : -1;
@@ -462,298 +500,350 @@ k_pipeline(const DevModel M, const __grid_constant__ pxb_thermal_cells C,
         tag = w;
       }
     }
-    if (out) {
-      if (!staging) break;
-      continue;
-    }
-    {
-      unsigned int tk = 0;
-      if (lane == 0) tk = atomicAdd(A.ticket, 1u);
-      const int64_t tile = (int64_t)__shfl_sync(0xffffffffu, tk, 0);
+
+    // ---- (A) a new tile: energies (sampled or loaded), Doppler shift, absorption decisions -----
+    bool have_new = false;
+    int64_t tile = 0;
+    int run = 0, how = 0;
+    unsigned new_bits = 0;
+    if (!out) {
+      {
+        unsigned long long old = 0;
+        if (lane == 0) {
+          for (;;) {
+            old = atomicAdd(&s_tk, 1ull);
+            const unsigned n = (unsigned)old;
+            if (n < (unsigned)PL_BATCH) break;
+            if (n == (unsigned)PL_BATCH) {                    // this warp refills the CTA's cache
+              const unsigned long long b = atomicAdd(A.ticket, 1u);
+              atomicExch(&s_tk, (b << 32) | 1ull);
+              old = b << 32;                                  // ... and takes its first tile
+              break;
+            }
+            const unsigned long long seen = old >> 32;        // somebody else is refilling
+            while ((*reinterpret_cast<volatile unsigned long long*>(&s_tk) >> 32) == seen) __nanosleep(32);
+          }
+        }
+        old = __shfl_sync(0xffffffffu, old, 0);
+        tile = (int64_t)(old >> 32) * PL_BATCH + (int64_t)(unsigned)old;
+      }
       if (tile >= A.n_tiles) {
         out = true;
         if (lane == 0) atomicSub(&s_live, 1);
-        if (!staging) break;
-        continue;
-      }
-      const int64_t slot0 = tile * PL_TSLOTS;
-      const int nslots = (int)min((int64_t)PL_TSLOTS, A.n_pairs - slot0);
-      const int64_t c0 = __ldg(A.tile_cell + tile);
-      const int64_t c1 = (tile + 1 < A.n_tiles) ? __ldg(A.tile_cell + tile + 1) : A.n_cells - 1;
-      // cell starts of the tile, relative to its first slot (the first cell's is clamped to -1:
-      // only the order matters for the look-up).
-      // how = 0: every cell of the tile is non-empty -> ballot look-up; 1: empty cells (lists from
-      // elsewhere) -> shared-memory bisection; 2: more cells than fit -> global bisection.
-      const int64_t ncl = c1 - c0 + 1;
-      const int nc = ncl <= PL_MAXC ? (int)ncl : 0;
-      int how = nc == 0 ? 2 : 0;
-      const int64_t m00 = slot0 - __ldg(A.qoff + c0);      // pair index of slot 0 inside cell c0
-      __syncwarp();
-      {
-        bool dup = false;
-        for (int q = lane; q < nc; q += 32) {
-          const int64_t a = __ldg(A.qoff + c0 + q) - slot0, b = __ldg(A.qoff + c0 + q + 1) - slot0;
-          s_qs[q] = (int)max(a, (int64_t)-1);
-          dup |= (a == b);
+      } else {
+        have_new = true;
+        double* const s_e = reinterpret_cast<double*>(dyn + se_off + (unsigned)buf * (unsigned)(2 * TSLOTS * sizeof(double)));
+        int* const s_qs = reinterpret_cast<int*>(dyn + qs_off + (unsigned)buf * (unsigned)(MAXC * sizeof(int)));
+        const int64_t slot0 = tile * TSLOTS;
+        const int nslots = (int)min((int64_t)TSLOTS, A.n_pairs - slot0);
+        const int64_t c0 = __ldg(A.tile_cell + tile);
+        const int64_t c1 = (tile + 1 < A.n_tiles) ? __ldg(A.tile_cell + tile + 1) : A.n_cells - 1;
+        // cell starts of the tile, relative to its first slot (the first cell's is clamped to -1:
+        // only the order matters for the look-up).
+        // how = 0: every cell of the tile is non-empty -> ballot look-up; 1: empty cells (lists
+        // from elsewhere) -> shared-memory bisection; 2: more cells than fit -> global bisection.
+        const int64_t ncl = c1 - c0 + 1;
+        const int nc = ncl <= MAXC ? (int)ncl : 0;
+        how = nc == 0 ? 2 : 0;
+        const int64_t m00 = slot0 - __ldg(A.qoff + c0);      // pair index of slot 0 inside cell c0
+        __syncwarp();
+        {
+          bool dup = false;
+          for (int q = lane; q < nc; q += 32) {
+            const int64_t a = __ldg(A.qoff + c0 + q) - slot0, b = __ldg(A.qoff + c0 + q + 1) - slot0;
+            s_qs[q] = (int)max(a, (int64_t)-1);
+            dup |= (a == b);
+          }
+          if (how == 0 && __any_sync(0xffffffffu, dup)) how = 1;
         }
-        if (how == 0 && __any_sync(0xffffffffu, dup)) how = 1;
-      }
-      __syncwarp();
-
-      // Cell of every pair slot of the tile, relative to c0, for the four rounds at once (one
-      // byte per round; PL_MAXC < 256).  how = 0: the cell of a slot is the number of cells
-      // starting at or before it, minus one -- a ballot for the cells that start before the
-      // round's 32 slots plus a warp-wide OR of start bits inside them.
-      unsigned relpack = 0;
-      if (how == 0) {
-        unsigned cnt = 0;
-        for (int qb = 0; qb < nc; qb += 32) {
-          const int q = qb + lane;
-          const int qs = q < nc ? s_qs[q] : 0x7fffffff;
+        __syncwarp();
+        // Cell of every pair slot of the tile, relative to c0, for all rounds at once (one byte
+        // per round; MAXC < 256).  how = 0: the cell of a slot is the number of cells starting at
+        // or before it, minus one -- a ballot for the cells that start before the round's 32
+        // slots plus a warp-wide OR of start bits inside them.
+        unsigned relpack = 0;
+        if (how == 0) {
+          unsigned cnt = 0;
+          for (int qb = 0; qb < nc; qb += 32) {
+            const int q = qb + lane;
+            const int qs = q < nc ? s_qs[q] : 0x7fffffff;
 #pragma unroll
-          for (int r = 0; r < PL_ROUNDS; ++r) {
-            const unsigned before = __ballot_sync(0xffffffffu, qs < r * 32);
-            const unsigned d = (unsigned)(qs - r * 32);
-            const unsigned mask = __reduce_or_sync(0xffffffffu, d < 32u ? (1u << d) : 0u);
-            cnt += (unsigned)(__popc(before) + __popc(mask & ((2u << lane) - 1u))) << (8 * r);
+            for (int r = 0; r < ROUNDS; ++r) {
+              const unsigned before = __ballot_sync(0xffffffffu, qs < r * 32);
+              const unsigned d = (unsigned)(qs - r * 32);
+              const unsigned mask = __reduce_or_sync(0xffffffffu, d < 32u ? (1u << d) : 0u);
+              cnt += (unsigned)(__popc(before) + __popc(mask & ((2u << lane) - 1u))) << (8 * r);
+            }
           }
-        }
-        relpack = cnt - 0x01010101u;    // (every byte is >= 1: cell c0 starts at or before slot 0)
-      } else if (how == 1) {
+          relpack = cnt - (ROUNDS == 4 ? 0x01010101u : 0x00000101u);   // (every byte is >= 1)
+        } else if (how == 1) {
 #pragma unroll
-        for (int r = 0; r < PL_ROUNDS; ++r) {
-          const int srel = min(r * 32 + lane, nslots - 1);
-          int rel = 0;   // largest q with s_qs[q] <= srel
-          for (int step = 128; step > 0; step >>= 1) {
-            const int q = rel + step;
-            if (q < nc && s_qs[q] <= srel) rel = q;
+          for (int r = 0; r < ROUNDS; ++r) {
+            const int srel = min(r * 32 + lane, nslots - 1);
+            int rel = 0;   // largest q with s_qs[q] <= srel
+            for (int step = 128; step > 0; step >>= 1) {
+              const int q = rel + step;
+              if (q < nc && s_qs[q] <= srel) rel = q;
+            }
+            relpack |= (unsigned)rel << (8 * r);
           }
-          relpack |= (unsigned)rel << (8 * r);
         }
-      }
-      // (cell relative to c0, pair index inside the cell) of slot r*32 + lane
-      auto locate = [&](int r, int srel, int& rel, int64_t& m) {
-        if (how != 2) {
-          rel = (int)((relpack >> (8 * r)) & 255u);
-          m = rel == 0 ? m00 + srel : (int64_t)(srel - s_qs[rel]);
-        } else {
-          const int64_t slot = slot0 + min(srel, nslots - 1);
-          int64_t lo = c0, hi = c1 + 1;   // qoff[lo] <= slot < qoff[hi]
-          while (hi - lo > 1) {
-            const int64_t mid = (lo + hi) >> 1;
-            if (__ldg(A.qoff + mid) <= slot) lo = mid; else hi = mid;
-          }
-          rel = (int)(lo - c0);
-          m = slot0 + srel - __ldg(A.qoff + lo);
-        }
-      };
 
-      // ---- phase 1: energies (sampled or loaded), Doppler shift, absorption decisions --------
-      int run = 0;
-      unsigned detpack = 0;
-      double tsum = 0.0, tmin = 1.0e99, tmax = -1.0e99;
+        unsigned detpack = 0;
+        double tsum = 0.0, tmin = 1.0e99, tmax = -1.0e99;
 #pragma unroll 1
-      for (int r = 0; r < PL_ROUNDS; ++r) {
-        if (r * 32 >= nslots) break;
-        const int srel = r * 32 + lane;
-        const bool valid = srel < nslots;
-        int rel;
-        int64_t m;
-        locate(r, srel, rel, m);
-        const CellRec* rp = A.recs + (c0 + rel);
-        const longlong2 q0 = __ldg(reinterpret_cast<const longlong2*>(rp));
-        const longlong2 q1 = __ldg(reinterpret_cast<const longlong2*>(rp) + 1);
-        const uint64_t gid = (uint64_t)q0.x;
-        const uint64_t d0 = 2ull * (uint64_t)m;
-        const bool hasA = valid;
-        const bool hasB = valid && (int64_t)(d0 + 1) < q1.y;
-        double eA = 0.0, eB = 0.0;
-        bool elig = true;
-        if (MODE != MODE_PROJECT) {
-          const longlong2 q2 = __ldg(reinterpret_cast<const longlong2*>(rp) + 2);
-          const longlong2 q3 = __ldg(reinterpret_cast<const longlong2*>(rp) + 3);
-          const int z1 = (int)(q2.x & 0xffffffffll), meta = (int)(q2.x >> 32);
-          const long long cn0 = q2.y, cn1 = q3.x, cn2 = q3.y;
-          elig = (meta & 16) != 0;
-          if (valid && elig) {
-            if (SPEC != 0 || (meta & (32 | 64))) {
-              // split modes: the photon's component follows from its index inside the cell
-              const Philox4 E = pxb_rand4(RKE, STREAM_ENERGY, gid, (uint64_t)m);
-              const bool prim = SPEC != 0 || !(meta & 8);
-              const DevTable* tb = prim ? &M.prim : &M.fb;
-              const bool four = SPEC != 0 || (meta & 32);
-              // counts below 2^31: 32-bit compares (any cell in practice)
-              const bool small = q1.y < 0x7fffffffll;
+        for (int r = 0; r < ROUNDS; ++r) {
+          if (r * 32 >= nslots) break;
+          const int srel = r * 32 + lane;
+          const bool valid = srel < nslots;
+          int rel;
+          int64_t m;
+          locate(how, relpack, s_qs, slot0, nslots, c0, c1, m00, r, srel, rel, m);
+          const CellRec* rp = A.recs + (c0 + rel);
+          const longlong2 q0 = __ldg(reinterpret_cast<const longlong2*>(rp));
+          const longlong2 q1 = __ldg(reinterpret_cast<const longlong2*>(rp) + 1);
+          const uint64_t gid = (uint64_t)q0.x;
+          const uint64_t d0 = 2ull * (uint64_t)m;
+          const bool hasA = valid;
+          const bool hasB = valid && (int64_t)(d0 + 1) < q1.y;
+          double eA = 0.0, eB = 0.0;
+          bool elig = true;
+          if (MODE != MODE_PROJECT) {
+            const longlong2 q2 = __ldg(reinterpret_cast<const longlong2*>(rp) + 2);
+            const longlong2 q3 = __ldg(reinterpret_cast<const longlong2*>(rp) + 3);
+            const int z1 = (int)(q2.x & 0xffffffffll), meta = (int)(q2.x >> 32);
+            const long long cn0 = q2.y, cn1 = q3.x, cn2 = q3.y;
+            elig = (meta & 16) != 0;
+            if (valid && elig) {
+              if (SPEC != 0 || (meta & (32 | 64))) {
+                // split modes: the photon's component follows from its index inside the cell
+                const Philox4 E = pxb_rand4(RKE, STREAM_ENERGY, gid, (uint64_t)m);
+                const bool prim = SPEC != 0 || !(meta & 8);
+                const DevTable* tb = prim ? &M.prim : &M.fb;
+                const bool four = SPEC != 0 || (meta & 32);
+                // counts below 2^31: 32-bit compares (any cell in practice)
+                const bool small = q1.y < 0x7fffffffll;
 #pragma unroll
-              for (int h = 0; h < 2; ++h) {
-                const long long dd = (long long)d0 + h;
-                int comp;
-                if (small) {
-                  const int d32 = (int)dd;
-                  comp = (d32 >= (int)cn0) + (d32 >= (int)cn1) + (d32 >= (int)cn2);
-                } else {
-                  comp = (dd >= cn0) + (dd >= cn1) + (dd >= cn2);
-                }
-                int tab, row;
-                if (four) {
-                  // four components: (row0,cosmic), (row0,metal), (row1,cosmic), (row1,metal)
-                  tab = comp & 1;
-                  row = z1 + (comp >> 1);
-                } else {
-                  // general split: comp is the ROW, the table comes from the side array
-                  const long long din = dd - (comp == 0 ? 0 : (comp == 1 ? cn0 : (comp == 2 ? cn1 : cn2)));
-                  const int ntab = 2 + C.nvar;
-                  const int64_t* tc = A.tabcum + (c0 + rel) * A.tab_stride + comp * ntab;
-                  tab = 0;
-                  if (ntab <= 8) {
-                    for (int t2 = 0; t2 < ntab - 1; ++t2) tab += (din >= __ldg(tc + t2)) ? 1 : 0;
+                for (int h = 0; h < 2; ++h) {
+                  const long long dd = (long long)d0 + h;
+                  int comp;
+                  if (small) {
+                    const int d32 = (int)dd;
+                    comp = (d32 >= (int)cn0) + (d32 >= (int)cn1) + (d32 >= (int)cn2);
                   } else {
-                    int lo = 0, hi = ntab - 1;     // first tab with din < tc[tab]
-                    while (lo < hi) {
-                      const int mid = (lo + hi) >> 1;
-                      if (din >= __ldg(tc + mid)) lo = mid + 1; else hi = mid;
-                    }
-                    tab = lo;
+                    comp = (dd >= cn0) + (dd >= cn1) + (dd >= cn2);
                   }
-                  row = fast_row(tb, z1, meta & 7, comp);
+                  int tab, row;
+                  if (four) {
+                    // four components: (row0,cosmic), (row0,metal), (row1,cosmic), (row1,metal)
+                    tab = comp & 1;
+                    row = z1 + (comp >> 1);
+                  } else {
+                    // general split: comp is the ROW, the table comes from the side array
+                    const long long din = dd - (comp == 0 ? 0 : (comp == 1 ? cn0 : (comp == 2 ? cn1 : cn2)));
+                    const int ntab = 2 + C.nvar;
+                    const int64_t* tc = A.tabcum + (c0 + rel) * A.tab_stride + comp * ntab;
+                    tab = 0;
+                    if (ntab <= 8) {
+                      for (int t2 = 0; t2 < ntab - 1; ++t2) tab += (din >= __ldg(tc + t2)) ? 1 : 0;
+                    } else {
+                      int lo = 0, hi = ntab - 1;     // first tab with din < tc[tab]
+                      while (lo < hi) {
+                        const int mid = (lo + hi) >> 1;
+                        if (din >= __ldg(tc + mid)) lo = mid + 1; else hi = mid;
+                      }
+                      tab = lo;
+                    }
+                    row = fast_row(tb, z1, meta & 7, comp);
+                  }
+                  const uint32_t w0 = h ? E.z : E.x, w1 = h ? E.w : E.y;
+                  const unsigned dr = (unsigned)(row - tag);
+                  uint32_t v;
+                  int j;
+                  if (prim && tab < 2 && tag >= 0 && dr < 2u)   // staged row: shared-memory gather
+                    j = alias_pick(s_alias + (unsigned)(tab * 2 + (int)dr) * (unsigned)T.alias_stride,
+                                   (unsigned)T.nbins, w0, w1, v);
+                  else
+                    j = alias_pick(alias_row(tb, tab, row), (unsigned)T.nbins, w0, w1, v);
+                  const double e = alias_energy<(SPEC != 0) ? 1 : 0>(M, j, v);
+                  if (h) eB = e; else eA = e;
                 }
-                const uint32_t w0 = h ? E.z : E.x, w1 = h ? E.w : E.y;
-                const unsigned dr = (unsigned)(row - tag);
-                uint32_t v;
-                int j;
-                if (prim && tab < 2 && tag >= 0 && dr < 2u)   // staged row: shared-memory gather
-                  j = alias_pick(s_alias + (unsigned)(tab * 2 + (int)dr) * (unsigned)T.alias_stride,
-                                 (unsigned)T.nbins, w0, w1, v);
-                else
-                  j = alias_pick(alias_row(tb, tab, row), (unsigned)T.nbins, w0, w1, v);
-                const double e = alias_energy<(SPEC != 0) ? 1 : 0>(M, j, v);
-                if (h) eB = e; else eA = e;
-              }
-            } else {
-              // probability mode: every photon picks its component itself (one block per photon)
-              FastCell fc;
-              fc.z1 = z1;
-              fc.meta = meta;
-              fc.cnt[0] = cn0; fc.cnt[1] = cn1; fc.cnt[2] = cn2;
-              const int64_t i = __ldg(A.idx + c0 + rel);
+              } else {
+                // probability mode: every photon picks its component itself (one block per photon)
+                FastCell fc;
+                fc.z1 = z1;
+                fc.meta = meta;
+                fc.cnt[0] = cn0; fc.cnt[1] = cn1; fc.cnt[2] = cn2;
+                const int64_t i = __ldg(A.idx + c0 + rel);
 #pragma unroll
-              for (int h = 0; h < 2; ++h) {
-                if (h && !hasB) break;
-                const Philox4 rn = pxb_rand4(RKE, STREAM_ENERGY, gid, d0 + h);
-                const double e = fast_draw<0>(M, C, fc, i, u53(rn.x, rn.y), rn.z, rn.w);
-                if (h) eB = e; else eA = e;
+                for (int h = 0; h < 2; ++h) {
+                  if (h && !hasB) break;
+                  const Philox4 rn = pxb_rand4(RKE, STREAM_ENERGY, gid, d0 + h);
+                  const double e = fast_draw<0>(M, C, fc, i, u53(rn.x, rn.y), rn.z, rn.w);
+                  if (h) eB = e; else eA = e;
+                }
+              }
+              if (SPEC == 0 && M.binscale_log) {
+                eA = exp10(eA);
+                eB = exp10(eB);
               }
             }
-            if (SPEC == 0 && M.binscale_log) {
-              eA = exp10(eA);
-              eB = exp10(eB);
-            }
           }
-        }
-        if (MODE == MODE_SAMPLE) {
-          if (elig) {
-            double* dst = A.energies + q1.x + (int64_t)d0;
-            if (hasB && (((uintptr_t)dst) & 15) == 0) {
-              asm volatile("st.global.L1::no_allocate.v2.f64 [%0], {%1, %2};" ::"l"(dst), "d"(eA), "d"(eB));
-            } else {
-              if (hasA) st_stream(dst, eA);
-              if (hasB) st_stream(dst + 1, eB);
+          if (MODE == MODE_SAMPLE) {
+            if (elig) {
+              double* dst = A.energies + q1.x + (int64_t)d0;
+              if (hasB && (((uintptr_t)dst) & 15) == 0) {
+                asm volatile("st.global.L1::no_allocate.v2.f64 [%0], {%1, %2};" ::"l"(dst), "d"(eA), "d"(eB));
+              } else {
+                if (hasA) st_stream(dst, eA);
+                if (hasB) st_stream(dst + 1, eB);
+              }
             }
+            continue;
           }
-          continue;
+          if (MODE == MODE_PROJECT) {
+            const double* src = A.energies + q1.x + (int64_t)d0;
+            if (hasA) eA = ld_stream(src);
+            if (hasB) eB = ld_stream(src + 1);
+          }
+          const double shift = __longlong_as_double(q0.y);
+          eA *= shift;
+          eB *= shift;
+          bool detA = hasA && elig, detB = hasB && elig;
+          if (absorb) {
+            const Philox4 Aw = pxb_rand4(RKP, STREAM_PROJ_A, gid, (uint64_t)m);
+            Philox4 Dw{0u, 0u, 0u, 0u};
+            if (SPEC == 0 && P.nH_cell) Dw = pxb_rand4(RKP, STREAM_PROJ_D, gid, (uint64_t)m);
+            if (detA) detA = absorb_decision<SPEC>(P, RKP, s_wabs, c0 + rel, gid, d0, Aw.x, Dw.x, eA);
+            if (detB) detB = absorb_decision<SPEC>(P, RKP, s_wabs, c0 + rel, gid, d0 + 1, Aw.y, Dw.y, eB);
+          }
+          s_e[2 * srel] = eA;
+          s_e[2 * srel + 1] = eB;
+          if (detA) {
+            tsum += eA;
+            tmin = eA < tmin ? eA : tmin;   // (energies are never NaN: plain compares)
+            tmax = eA > tmax ? eA : tmax;
+          }
+          if (detB) {
+            tsum += eB;
+            tmin = eB < tmin ? eB : tmin;
+            tmax = eB > tmax ? eB : tmax;
+          }
+          run += __popc(__ballot_sync(0xffffffffu, detA)) + __popc(__ballot_sync(0xffffffffu, detB));
+          detpack |= ((detA ? 1u : 0u) | (detB ? 2u : 0u)) << (2 * r);
         }
-        if (MODE == MODE_PROJECT) {
-          const double* src = A.energies + q1.x + (int64_t)d0;
-          if (hasA) eA = ld_stream(src);
-          if (hasB) eB = ld_stream(src + 1);
+        if (MODE != MODE_SAMPLE) {
+          tsum = warp_sum(tsum);
+          tmin = warp_min(tmin);
+          tmax = warp_max(tmax);
+          if (lane == 0) {
+            A.part_sum[tile] = tsum;
+            A.part_min[tile] = tmin;
+            A.part_max[tile] = tmax;
+          }
+          new_bits = detpack | (relpack << 8);
         }
-        const double shift = __longlong_as_double(q0.y);
-        eA *= shift;
-        eB *= shift;
-        bool detA = hasA && elig, detB = hasB && elig;
-        if (absorb) {
-          const Philox4 Aw = pxb_rand4(RKP, STREAM_PROJ_A, gid, (uint64_t)m);
-          Philox4 Dw{0u, 0u, 0u, 0u};
-          if (SPEC == 0 && P.nH_cell) Dw = pxb_rand4(RKP, STREAM_PROJ_D, gid, (uint64_t)m);
-          if (detA) detA = absorb_decision<SPEC>(P, RKP, s_wabs, c0 + rel, gid, d0, Aw.x, Dw.x, eA);
-          if (detB) detB = absorb_decision<SPEC>(P, RKP, s_wabs, c0 + rel, gid, d0 + 1, Aw.y, Dw.y, eB);
-        }
-        s_e[2 * srel] = eA;
-        s_e[2 * srel + 1] = eB;
-        if (detA) {
-          tsum += eA;
-          tmin = eA < tmin ? eA : tmin;   // (energies are never NaN: plain compares)
-          tmax = eA > tmax ? eA : tmax;
-        }
-        if (detB) {
-          tsum += eB;
-          tmin = eB < tmin ? eB : tmin;
-          tmax = eB > tmax ? eB : tmax;
-        }
-        run += __popc(__ballot_sync(0xffffffffu, detA)) + __popc(__ballot_sync(0xffffffffu, detB));
-        detpack |= ((detA ? 1u : 0u) | (detB ? 2u : 0u)) << (2 * r);
       }
-      if (MODE == MODE_SAMPLE) continue;
+    }
+    if (MODE == MODE_SAMPLE) {
+      if (out && !staging) break;
+      continue;
+    }
 
-      tsum = warp_sum(tsum);
-      tmin = warp_min(tmin);
-      tmax = warp_max(tmax);
+    // ---- (B) report the new tile's count; a first, non-blocking look at its predecessors ------
+    if (have_new) {
+      if (lane == 0)
+        st_status(A.status + tile, (tile == 0 ? ST_INC : ST_AGG) | (unsigned long long)run);
+      int64_t nj = tile - 1, nprefix = 0;
+      const bool ndone = lookback_run(A.status, nj, nprefix, lane, false);
       if (lane == 0) {
-        A.part_sum[tile] = tsum;
-        A.part_min[tile] = tmin;
-        A.part_max[tile] = tmax;
+        if (ndone && tile > 0) st_status(A.status + tile, ST_INC | (unsigned long long)(nprefix + run));
+        s_pend[wid][buf][0] = tile;
+        s_pend[wid][buf][1] = nprefix;
+        s_pend[wid][buf][2] = nj;
+        s_pend[wid][buf][3] = (long long)(run | (how << 16) | ((ndone ? 1 : 0) << 20));
       }
+    }
 
-      // ---- phase 2: exclusive prefix over tiles ----------------------------------------------
-      const int64_t base = warp_lookback(A.status, tile, (int64_t)run, lane);
-      if (tile == A.n_tiles - 1 && lane == 0) *A.n_events = base + run;
-      if (run == 0) continue;                                   // everything absorbed
-
-      // ---- phase 3: scatter the survivors into their final, order-preserving slots -----------
-      // (tile-uniform 64-bit bases, 32-bit offsets inside the tile)
-      double* const xb = A.xsky + base;
-      double* const yb = A.ysky + base;
-      double* const eb = A.eobs + base;
-      double* const lb = A.los ? A.los + base : nullptr;
-      int done = 0;
+    // ---- (C) finish the pending tile: its prefix (blocking now: it has had a whole tile's time),
+    //          then scatter its survivors into their final, order-preserving slots ---------------
+    if (have_pend) {
+      __syncwarp();
+      const int64_t ptile = s_pend[wid][buf ^ 1][0];
+      int64_t base = s_pend[wid][buf ^ 1][1];
+      int64_t pj = s_pend[wid][buf ^ 1][2];
+      const int info = (int)s_pend[wid][buf ^ 1][3];
+      const int prun = info & 0xffff, phow = (info >> 16) & 3;
+      if (!((info >> 20) & 1)) {
+        lookback_run(A.status, pj, base, lane, true);
+        if (lane == 0) st_status(A.status + ptile, ST_INC | (unsigned long long)(base + prun));
+      }
+      if (ptile == A.n_tiles - 1 && lane == 0) *A.n_events = base + prun;
+      if (prun > 0) {
+        const double* const s_e = reinterpret_cast<const double*>(dyn + se_off + (unsigned)(buf ^ 1) * (unsigned)(2 * TSLOTS * sizeof(double)));
+        const int* const s_qs = reinterpret_cast<const int*>(dyn + qs_off + (unsigned)(buf ^ 1) * (unsigned)(MAXC * sizeof(int)));
+        const int64_t slot0 = ptile * TSLOTS;
+        const int nslots = (int)min((int64_t)TSLOTS, A.n_pairs - slot0);
+        const int64_t c0 = __ldg(A.tile_cell + ptile);
+        const int64_t c1 = (ptile + 1 < A.n_tiles) ? __ldg(A.tile_cell + ptile + 1) : A.n_cells - 1;
+        const int64_t m00 = slot0 - __ldg(A.qoff + c0);
+        const unsigned detpack = pend_bits & 255u, relpack = pend_bits >> 8;
+        // (tile-uniform 64-bit bases, 32-bit offsets inside the tile)
+        double* const xb = A.xsky + base;
+        double* const yb = A.ysky + base;
+        double* const eb = A.eobs + base;
+        double* const lb = A.los ? A.los + base : nullptr;
+        int done = 0;
 #pragma unroll 1
-      for (int r = 0; r < PL_ROUNDS; ++r) {
-        if (r * 32 >= nslots) break;
-        const bool detA = (detpack >> (2 * r)) & 1u, detB = (detpack >> (2 * r + 1)) & 1u;
-        const unsigned balA = __ballot_sync(0xffffffffu, detA), balB = __ballot_sync(0xffffffffu, detB);
-        if (!(balA | balB)) continue;
-        const int o0 = done + __popc(balA & lt) + __popc(balB & lt);
-        done += __popc(balA) + __popc(balB);
-        if (!(detA || detB)) continue;
-        const int srel = r * 32 + lane;
-        int rel;
-        int64_t m;
-        locate(r, srel, rel, m);
-        const uint64_t gid = (uint64_t)__ldg(&A.recs[c0 + rel].gid);
-        const uint64_t d0 = 2ull * (uint64_t)m;
-        const CellGeom g = ld_geom(A.geom + c0 + rel);
-        const Philox4 Bw = pxb_rand4(RKP, STREAM_PROJ_B, gid, (uint64_t)m);
-        // the third scatter word lives in the absorption block: recomputed only where it is used
-        // (off-axis cells, particle kernels, all-sky)
-        Philox4 Aw{0u, 0u, 0u, 0u};
-        if (SPEC == 2 || (SPEC == 0 && !(P.observer == 0 && P.data_type == 0 && P.vn_axis >= 0)))
-          Aw = pxb_rand4(RKP, STREAM_PROJ_A, gid, (uint64_t)m);
+        for (int r = 0; r < ROUNDS; ++r) {
+          if (r * 32 >= nslots) break;
+          const bool detA = (detpack >> (2 * r)) & 1u, detB = (detpack >> (2 * r + 1)) & 1u;
+          const unsigned balA = __ballot_sync(0xffffffffu, detA), balB = __ballot_sync(0xffffffffu, detB);
+          if (!(balA | balB)) continue;
+          const int o0 = done + __popc(balA & lt) + __popc(balB & lt);
+          done += __popc(balA) + __popc(balB);
+          if (!(detA || detB)) continue;
+          const int srel = r * 32 + lane;
+          int rel;
+          int64_t m;
+          locate(phow, relpack, s_qs, slot0, nslots, c0, c1, m00, r, srel, rel, m);
+          const uint64_t gid = (uint64_t)__ldg(&A.recs[c0 + rel].gid);
+          const uint64_t d0 = 2ull * (uint64_t)m;
+          const CellGeom g = ld_geom(A.geom + c0 + rel);
+          const Philox4 Bw = pxb_rand4(RKP, STREAM_PROJ_B, gid, (uint64_t)m);
+          // the third scatter word lives in the absorption block: recomputed only where it is
+          // used (off-axis cells, particle kernels, all-sky)
+          Philox4 Aw{0u, 0u, 0u, 0u};
+          if (SPEC == 2 || (SPEC == 0 && !(P.observer == 0 && P.data_type == 0 && P.vn_axis >= 0)))
+            Aw = pxb_rand4(RKP, STREAM_PROJ_A, gid, (uint64_t)m);
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          if (!(h ? detB : detA)) continue;
-          double xs, ys, los;
-          const uint32_t w0 = h ? Bw.z : Bw.x, w1 = h ? Bw.w : Bw.y, w2 = h ? Aw.w : Aw.z;
-          if (SPEC != 0 || P.observer == 0)
-            scatter_external<SPEC>(P, RKP, g, K, w0, w1, w2, gid, d0 + h, xs, ys, los);
-          else
-            scatter_allsky(P, RKP, g, w0, w1, w2, gid, d0 + h, xs, ys, los);
-          const int o = o0 + (h && detA ? 1 : 0);
-          st_stream(xb + o, xs);
-          st_stream(yb + o, ys);
-          st_stream(eb + o, s_e[2 * srel + h]);
-          if (lb) st_stream(lb + o, los);
+          for (int h = 0; h < 2; ++h) {
+            if (!(h ? detB : detA)) continue;
+            double xs, ys, los;
+            const uint32_t w0 = h ? Bw.z : Bw.x, w1 = h ? Bw.w : Bw.y, w2 = h ? Aw.w : Aw.z;
+            if (SPEC != 0 || P.observer == 0)
+              scatter_external<SPEC>(P, RKP, g, K, w0, w1, w2, gid, d0 + h, xs, ys, los);
+            else
+              scatter_allsky(P, RKP, g, w0, w1, w2, gid, d0 + h, xs, ys, los);
+            const int o = o0 + (h && detA ? 1 : 0);
+            st_stream(xb + o, xs);
+            st_stream(yb + o, ys);
+            st_stream(eb + o, s_e[2 * srel + h]);
+            if (lb) st_stream(lb + o, los);
+          }
         }
       }
+      have_pend = false;
+    }
+
+    // ---- (D) the new tile becomes the pending one ------------------------------------------------
+    if (have_new) {
+      __syncwarp();
+      pend_bits = new_bits;
+      have_pend = true;
+      buf ^= 1;
+    } else if (!staging) {
+      break;             // no tile left to draw and nothing pending
     }
   }
 }
@@ -795,7 +885,6 @@ __global__ void k_reduce_stats_final(const double* __restrict__ part, int nb,
 constexpr int STATS_BLOCKS = 256;
 
 static inline int64_t align256(int64_t v) { return (v + 255) & ~(int64_t)255; }
-static inline int64_t n_tiles_of(int64_t n_pairs) { return (n_pairs + PL_TSLOTS - 1) / PL_TSLOTS; }
 
 // side array of the general split: cumulative counts per (row, table) of every active cell
 static int split_stride(const DevModel& D) {
@@ -807,6 +896,7 @@ static int split_stride(const DevModel& D) {
 // use it)
 struct PipeLayout {
   int64_t ntiles;
+  int tslots;          // pair slots per tile of the mode (Tiling<MODE>::TSLOTS)
   int64_t off_hdr, off_recs, off_geom, off_tilecell, off_status, off_part, off_red;
   int64_t off_list, off_tabcum, off_glist, total;
 };
@@ -814,7 +904,8 @@ struct PipeLayout {
 static PipeLayout pipe_layout(const DevModel* D, int64_t n_cells, int64_t n_pairs, bool sample,
                               bool project) {
   PipeLayout l;
-  l.ntiles = n_tiles_of(n_pairs);
+  l.tslots = tslots_of(project ? MODE_PROJECT : MODE_SAMPLE);
+  l.ntiles = (n_pairs + l.tslots - 1) / l.tslots;
   int64_t o = 0;
   l.off_hdr = o;      o += 256;                                  // counters + ticket
   l.off_status = o;   o += project ? align256(l.ntiles * 8) : 0; // (header + status: one memset)
@@ -849,8 +940,10 @@ struct SmemPlan {
 };
 static SmemPlan smem_plan(const DevModel* D, int mode) {
   SmemPlan s;
-  const size_t e_bytes = mode == MODE_SAMPLE ? 0 : (size_t)PL_WARPS * 2 * PL_TSLOTS * sizeof(double);
-  const size_t qs_bytes = (size_t)PL_WARPS * PL_MAXC * sizeof(int);
+  const size_t e_bytes = mode == MODE_SAMPLE ? 0
+                         : (size_t)PL_WARPS * Tiling<1>::NBUF * 2 * Tiling<1>::TSLOTS * sizeof(double);
+  const size_t qs_bytes = mode == MODE_SAMPLE ? (size_t)PL_WARPS * Tiling<0>::MAXC * sizeof(int)
+                                              : (size_t)PL_WARPS * Tiling<1>::NBUF * Tiling<1>::MAXC * sizeof(int);
   size_t rows = 0;
   s.use_staging = 0;
   if (mode != MODE_PROJECT && D && !D->density_dependent && !D->has_fb) {
@@ -937,7 +1030,7 @@ static int prep_sample(const pxb_model* model, const pxb_thermal_cells* cells, i
   const int split_factor = cells->split_factor > 0 ? cells->split_factor : 6;
   k_prep_sample<<<(unsigned)((n_active + 255) / 256), 256, 0, st>>>(
       D, *cells, n_active, idx, poff, qoff, recs, tile_cell, list, H.list_count, tabcum, glist,
-      H.glist_count, split_factor);
+      H.glist_count, split_factor, lay.tslots);
   PXB_LAUNCH_CHECK();
   if (tabcum) {
     int64_t gs = (n_active + 127) / 128;
@@ -1107,7 +1200,7 @@ extern "C" int pxb_project(const pxb_photon_list* L, const pxb_project_params* P
   PXB_CUDA(cudaMemsetAsync(ws + lay.off_hdr, 0, (size_t)(lay.off_recs - lay.off_hdr), st));
   k_prep_project<true><<<(unsigned)((L->n_cells + 255) / 256), 256, 0, st>>>(
       *L, *P, (CellRec*)(ws + lay.off_recs), (CellGeom*)(ws + lay.off_geom),
-      (int64_t*)(ws + lay.off_tilecell));
+      (int64_t*)(ws + lay.off_tilecell), lay.tslots);
   PXB_LAUNCH_CHECK();
   const SmemPlan sp = smem_plan(nullptr, MODE_PROJECT);
   PipeArgs A{};
@@ -1167,7 +1260,7 @@ extern "C" int pxb_make_events(const pxb_model* model, const pxb_thermal_cells* 
   if (rc) return rc;
   k_prep_project<false><<<(unsigned)((L->n_cells + 255) / 256), 256, 0, st>>>(
       *L, *P, (CellRec*)(ws + lay.off_recs), (CellGeom*)(ws + lay.off_geom),
-      (int64_t*)(ws + lay.off_tilecell));
+      (int64_t*)(ws + lay.off_tilecell), lay.tslots);
   PXB_LAUNCH_CHECK();
   const SmemPlan sp = smem_plan(&D, MODE_FUSED);
   PipeArgs A{};
