@@ -384,7 +384,10 @@ typedef struct {
   int32_t save_los;
   int32_t absorb_kind;   /* PXB_ABS_* */
   int32_t has_sigma_pos;
-  int32_t reserved;
+  int32_t events_f32;    /* 1: xsky / ysky / eobs / los are FLOAT arrays (arithmetic stays fp64): eobs
+                            rounded to single precision, xsky / ysky as offsets from sky_center
+                            for the angular sky modes of an external observer (absolute values
+                            otherwise) -- half the bytes of an event list */
   double sigma_pos;
   double x_hat[3], y_hat[3], z_hat[3];
   double D_A_kpc;
@@ -405,8 +408,9 @@ typedef struct {
 } pxb_project_params;
 
 int pxb_project_workspace_bytes(int64_t n_cells, int64_t n_pairs, int64_t* bytes);
-/* Outputs xsky/ysky/eobs (and los when save_los) must hold n_photons entries; the first
- * n_events are valid and keep the photon-list order (stable compaction).
+/* Outputs xsky/ysky/eobs (and los when save_los) must hold n_photons entries (doubles, or floats
+ * with params->events_f32); the first n_events are valid and keep the photon-list order (stable
+ * compaction).
  * n_events_out: device int64[1].  stats_out: device double[3] = {sum(eobs), min, max}. */
 int pxb_project(const pxb_photon_list* photons, const pxb_project_params* params,
                 double* xsky, double* ysky, double* eobs, double* los,

@@ -103,7 +103,7 @@ class ProjectParams(C.Structure):
         ("observer", C.c_int32), ("data_type", C.c_int32), ("kernel", C.c_int32),
         ("no_shifting", C.c_int32), ("vn_axis", C.c_int32), ("sky_mode", C.c_int32),
         ("save_los", C.c_int32), ("absorb_kind", C.c_int32), ("has_sigma_pos", C.c_int32),
-        ("reserved", C.c_int32),
+        ("events_f32", C.c_int32),
         ("sigma_pos", C.c_double),
         ("x_hat", C.c_double * 3), ("y_hat", C.c_double * 3), ("z_hat", C.c_double * 3),
         ("D_A_kpc", C.c_double), ("sky_center", C.c_double * 2), ("nH", C.c_double),

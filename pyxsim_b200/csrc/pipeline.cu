@@ -77,11 +77,15 @@ struct PipeArgs {
   double* eobs;
   double* los;
   int64_t* n_events;
-  unsigned long long* status; // [n_tiles] look-back words
+  unsigned long long* status; // [n_tiles] look-back words of the tiles
+  unsigned long long* bstatus;   // [n_batches] look-back words of the batches
+  unsigned long long* bcount;    // [n_batches] packed (tiles reported, sum of counts)
   double* part_sum;           // [n_tiles] per-tile partial statistics
   double* part_min;
   double* part_max;
   int off_e, off_qs;          // byte offsets of the per-warp scratch in dynamic shared memory
+  int f32;                    // events are written as float (xsky / ysky minus sky0 / sky1)
+  double sky0, sky1;
 };
 
 // ---------------------------------------------------------------------------------------
@@ -140,25 +144,56 @@ __device__ __forceinline__ void st_status(unsigned long long* p, unsigned long l
   asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v));
 }
 
-// Exclusive prefix of the counts of all earlier tiles, resumable: walks back from tile `j` over
-// the status words, adding aggregates until it meets an inclusive prefix.  Returns true when the
-// prefix is complete; with blocking = false it returns false as soon as a needed predecessor has
-// not reported yet (the caller does something useful and comes back), keeping its progress in
-// (j, prefix).  Whole warp participates.  Progress: a warp publishes its aggregate before it looks
-// back, tiles are handed out in increasing order, and a tile whose aggregate is missing is being
-// worked on by a resident warp that waits for nothing.
-__device__ __forceinline__ bool lookback_run(const unsigned long long* status, int64_t& j,
+// Exclusive prefix of the survivor counts of all earlier tiles -- a two-level decoupled look-back.
+// Level 1: every tile publishes its own count (tile word, flag ST_AGG).  Level 2: tiles are handed
+// out in batches of PL_BATCH consecutive tiles; the tile that completes a batch (a packed atomic
+// counter per batch) publishes the batch total (batch word, ST_AGG), and any tile that has worked
+// out the prefix at the start of its batch publishes it as the inclusive prefix of the batch
+// before (ST_INC).  A tile's prefix = counts of the earlier tiles of its own batch (one window of
+// tile words) + a walk back over BATCH words until an inclusive prefix: with a few hundred batches
+// in flight the walk is a handful of windows, however long inclusive prefixes take to appear.
+// Resumable: returns false as soon as something it needs has not been reported yet (blocking =
+// false), keeping its progress in (stage_j, prefix); whole warp participates.  Progress: a warp
+// publishes its count before it looks back, tiles are handed out in increasing order, and a tile
+// whose count is missing is being worked on by a resident warp that waits for nothing.
+struct LookBack {
+  const unsigned long long* tiles;   // [n_tiles]
+  unsigned long long* batches;       // [n_batches]
+};
+
+// stage_j: >= 0: own batch done, next batch word to read; -1: finished; -2: own batch still due
+__device__ __forceinline__ bool lookback_run(const LookBack& S, int64_t tile, int64_t& stage_j,
                                              int64_t& prefix, int lane, bool blocking) {
   unsigned nap = 64;   // back-off: a waiting warp must not eat the issue slots of the one it waits for
+  const int64_t b = tile / PL_BATCH;
+  const int n = (int)(tile - b * PL_BATCH);
   for (;;) {
-    if (j < 0) return true;                                   // walked past tile 0
-    const int64_t idx = j - lane;
-    unsigned long long sv = (idx >= 0) ? ld_status(status + idx) : ST_INC;
+    if (stage_j == -2) {
+      // the earlier tiles of the own batch
+      const unsigned long long sv = lane < n ? ld_status(S.tiles + b * PL_BATCH + lane) : ST_AGG;
+      if (__any_sync(0xffffffffu, (sv & ST_MASK) == 0ull)) {
+        if (!blocking) return false;
+        __nanosleep(nap);
+        nap = min(nap * 2u, 2048u);
+        continue;
+      }
+      int64_t v = lane < n ? (int64_t)(sv & ~ST_MASK) : 0;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      prefix = v;
+      stage_j = b - 1;
+    }
+    if (stage_j < 0) {                                        // walked past batch 0
+      stage_j = -1;
+      return true;
+    }
+    const int64_t idx = stage_j - lane;
+    const unsigned long long sv = (idx >= 0) ? ld_status(S.batches + idx) : ST_INC;
     const unsigned inc = __ballot_sync(0xffffffffu, (sv & ST_MASK) == ST_INC);
     const unsigned emp = __ballot_sync(0xffffffffu, (sv & ST_MASK) == 0ull);
-    const int first = inc ? (__ffs(inc) - 1) : 32;           // nearest tile with an inclusive prefix
+    const int first = inc ? (__ffs(inc) - 1) : 32;           // nearest batch with an inclusive prefix
     const unsigned need = first >= 31 ? 0xffffffffu : ((2u << first) - 1u);
-    if (emp & need) {                                        // a needed predecessor is not ready
+    if (emp & need) {                                        // a needed batch is not complete
       if (!blocking) return false;
       __nanosleep(nap);
       nap = min(nap * 2u, 2048u);
@@ -168,9 +203,39 @@ __device__ __forceinline__ bool lookback_run(const unsigned long long* status, i
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     prefix += v;
-    if (first < 32) return true;
-    j -= 32;
+    if (first < 32) {
+      stage_j = -1;
+      return true;
+    }
+    stage_j -= 32;
   }
+}
+
+// after a tile's prefix is complete: the prefix at the start of its batch is the inclusive prefix
+// of the batch before (every finisher of the batch writes the same value)
+__device__ __forceinline__ void lookback_publish(const LookBack& S, int64_t tile, int64_t prefix,
+                                                 int lane) {
+  const int64_t b = tile / PL_BATCH;
+  const int n = (int)(tile - b * PL_BATCH);
+  if (b == 0) return;
+  // subtract the own batch's earlier tiles again
+  const unsigned long long sv = lane < n ? ld_status(S.tiles + b * PL_BATCH + lane) : 0ull;
+  int64_t v = (int64_t)(sv & ~ST_MASK);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  if (lane == 0) st_status(S.batches + (b - 1), ST_INC | (unsigned long long)(prefix - v));
+}
+
+// a tile reports its count: tile word, and the batch word when it completes the batch
+__device__ __forceinline__ void lookback_report(const LookBack& S, unsigned long long* bcount,
+                                                int64_t tile, int64_t n_tiles, int run) {
+  st_status(const_cast<unsigned long long*>(S.tiles) + tile, ST_AGG | (unsigned long long)run);
+  const int64_t b = tile / PL_BATCH;
+  const int64_t in_batch = min((int64_t)PL_BATCH, n_tiles - b * PL_BATCH);
+  // packed counter: tiles reported << 40 | sum of their counts
+  const unsigned long long old = atomicAdd(bcount + b, (1ull << 40) | (unsigned long long)run);
+  if ((int64_t)(old >> 40) == in_batch - 1)
+    st_status(S.batches + b, ST_AGG | ((old & ((1ull << 40) - 1ull)) + (unsigned long long)run));
 }
 
 // ---------------------------------------------------------------------------------------
@@ -751,13 +816,13 @@ k_pipeline(const DevModel M, const __grid_constant__ pxb_thermal_cells C,
     }
 
     // ---- (B) report the new tile's count; a first, non-blocking look at its predecessors ------
+    const LookBack LB{A.status, A.bstatus};
     if (have_new) {
-      if (lane == 0)
-        st_status(A.status + tile, (tile == 0 ? ST_INC : ST_AGG) | (unsigned long long)run);
-      int64_t nj = tile - 1, nprefix = 0;
-      const bool ndone = lookback_run(A.status, nj, nprefix, lane, false);
+      if (lane == 0) lookback_report(LB, A.bcount, tile, A.n_tiles, run);
+      int64_t nj = -2, nprefix = 0;
+      const bool ndone = lookback_run(LB, tile, nj, nprefix, lane, false);
+      if (ndone) lookback_publish(LB, tile, nprefix, lane);
       if (lane == 0) {
-        if (ndone && tile > 0) st_status(A.status + tile, ST_INC | (unsigned long long)(nprefix + run));
         s_pend[wid][buf][0] = tile;
         s_pend[wid][buf][1] = nprefix;
         s_pend[wid][buf][2] = nj;
@@ -775,8 +840,8 @@ k_pipeline(const DevModel M, const __grid_constant__ pxb_thermal_cells C,
       const int info = (int)s_pend[wid][buf ^ 1][3];
       const int prun = info & 0xffff, phow = (info >> 16) & 3;
       if (!((info >> 20) & 1)) {
-        lookback_run(A.status, pj, base, lane, true);
-        if (lane == 0) st_status(A.status + ptile, ST_INC | (unsigned long long)(base + prun));
+        lookback_run(LB, ptile, pj, base, lane, true);
+        lookback_publish(LB, ptile, base, lane);
       }
       if (ptile == A.n_tiles - 1 && lane == 0) *A.n_events = base + prun;
       if (prun > 0) {
@@ -788,11 +853,13 @@ k_pipeline(const DevModel M, const __grid_constant__ pxb_thermal_cells C,
         const int64_t c1 = (ptile + 1 < A.n_tiles) ? __ldg(A.tile_cell + ptile + 1) : A.n_cells - 1;
         const int64_t m00 = slot0 - __ldg(A.qoff + c0);
         const unsigned detpack = pend_bits & 255u, relpack = pend_bits >> 8;
-        // (tile-uniform 64-bit bases, 32-bit offsets inside the tile)
-        double* const xb = A.xsky + base;
-        double* const yb = A.ysky + base;
-        double* const eb = A.eobs + base;
-        double* const lb = A.los ? A.los + base : nullptr;
+        // (tile-uniform 64-bit bases, 32-bit offsets inside the tile; float events: half the bytes)
+        const int64_t ob = A.f32 ? base / 2 : base;         // (float arrays: base counts 4-byte slots)
+        double* const xb = A.xsky + ob;
+        double* const yb = A.ysky + ob;
+        double* const eb = A.eobs + ob;
+        double* const lb = A.los ? A.los + ob : nullptr;
+        const int fo = (int)(base & 1);
         int done = 0;
 #pragma unroll 1
         for (int r = 0; r < ROUNDS; ++r) {
@@ -826,10 +893,18 @@ k_pipeline(const DevModel M, const __grid_constant__ pxb_thermal_cells C,
             else
               scatter_allsky(P, RKP, g, w0, w1, w2, gid, d0 + h, xs, ys, los);
             const int o = o0 + (h && detA ? 1 : 0);
-            st_stream(xb + o, xs);
-            st_stream(yb + o, ys);
-            st_stream(eb + o, s_e[2 * srel + h]);
-            if (lb) st_stream(lb + o, los);
+            if (!A.f32) {
+              st_stream(xb + o, xs);
+              st_stream(yb + o, ys);
+              st_stream(eb + o, s_e[2 * srel + h]);
+              if (lb) st_stream(lb + o, los);
+            } else {
+              // sky offsets from the fp64 centre and energies in single precision
+              __stcs(reinterpret_cast<float*>(xb) + fo + o, (float)(xs - A.sky0));
+              __stcs(reinterpret_cast<float*>(yb) + fo + o, (float)(ys - A.sky1));
+              __stcs(reinterpret_cast<float*>(eb) + fo + o, (float)s_e[2 * srel + h]);
+              if (lb) __stcs(reinterpret_cast<float*>(lb) + fo + o, (float)los);
+            }
           }
         }
       }
@@ -897,7 +972,7 @@ static int split_stride(const DevModel& D) {
 struct PipeLayout {
   int64_t ntiles;
   int tslots;          // pair slots per tile of the mode (Tiling<MODE>::TSLOTS)
-  int64_t off_hdr, off_recs, off_geom, off_tilecell, off_status, off_part, off_red;
+  int64_t off_hdr, off_recs, off_geom, off_tilecell, off_status, off_bstatus, off_bcount, off_part, off_red;
   int64_t off_list, off_tabcum, off_glist, total;
 };
 
@@ -908,7 +983,10 @@ static PipeLayout pipe_layout(const DevModel* D, int64_t n_cells, int64_t n_pair
   l.ntiles = (n_pairs + l.tslots - 1) / l.tslots;
   int64_t o = 0;
   l.off_hdr = o;      o += 256;                                  // counters + ticket
-  l.off_status = o;   o += project ? align256(l.ntiles * 8) : 0; // (header + status: one memset)
+  const int64_t nbatch = (l.ntiles + PL_BATCH - 1) / PL_BATCH;
+  l.off_status = o;   o += project ? align256(l.ntiles * 8) : 0; // (header + look-back words: one memset)
+  l.off_bstatus = o;  o += project ? align256(nbatch * 8) : 0;
+  l.off_bcount = o;   o += project ? align256(nbatch * 8) : 0;
   l.off_recs = o;     o += align256(n_cells * (int64_t)sizeof(CellRec));
   l.off_geom = o;     o += project ? align256(n_cells * (int64_t)sizeof(CellGeom)) : 0;
   l.off_tilecell = o; o += align256((l.ntiles + 1) * 8);
@@ -1159,7 +1237,14 @@ static void fill_project_args(PipeArgs& A, char* ws, const PipeLayout& lay, cons
   A.eobs = eobs;
   A.los = P->save_los ? los : nullptr;
   A.n_events = n_events_out;
+  A.f32 = P->events_f32 != 0;
+  // float events carry sky OFFSETS from the centre wherever the sky coordinates are angles about it
+  const bool about_centre = P->observer == 0 && P->sky_mode != PXB_SKY_PHYS;
+  A.sky0 = about_centre ? P->sky_center[0] : 0.0;
+  A.sky1 = about_centre ? P->sky_center[1] : 0.0;
   A.status = (unsigned long long*)(ws + lay.off_status);
+  A.bstatus = (unsigned long long*)(ws + lay.off_bstatus);
+  A.bcount = (unsigned long long*)(ws + lay.off_bcount);
   A.part_sum = (double*)(ws + lay.off_part);
   A.part_min = A.part_sum + lay.ntiles;
   A.part_max = A.part_min + lay.ntiles;

@@ -183,12 +183,18 @@ class EventList:
 
     def __getitem__(self, item):
         if item not in self._data:
-            self._data[item] = np.concatenate([lst.numpy(item) for lst in self._lists]) \
+            self._data[item] = np.concatenate([self._dev(lst, item).cpu().numpy() for lst in self._lists]) \
                 if self._lists else np.array([])
         return self._data[item]
 
     def _dev(self, lst, key):
-        return to_device(lst.data[key])
+        """Column ``key`` of one list as a float64 device tensor.  Lists written with
+        ``event_dtype="float32"`` are widened, and their sky positions -- stored as offsets from
+        the fp64 sky centre -- are made absolute again."""
+        t = to_device(lst.data[key])
+        if key in ("xsky", "ysky") and int(lst.parameters.get("sky_offsets", 0)):
+            t = t + float(np.asarray(lst.parameters["sky_center"], "float64")[0 if key == "xsky" else 1])
+        return t
 
     # -- binning on the device ----------------------------------------------------------
     def pixel_coordinates(self, fov, nx):

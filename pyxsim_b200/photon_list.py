@@ -448,8 +448,15 @@ class _Projection:
     def __init__(self, obs, normal, sky_center, absorb_model=None, nH=None, abund_table="angr",
                  no_shifting=False, north_vector=None, flat_sky=False, sigma_pos=None,
                  kernel="top_hat", save_los=False, phys_coord=False, prng=None, column_file=None,
-                 nH_cell=None):
+                 nH_cell=None, event_dtype="float64"):
         self.obs, self.normal, self.nH, self.abund_table = obs, normal, nH, abund_table
+        if str(event_dtype) not in ("float64", "float32"):
+            raise ValueError("event_dtype must be 'float64' or 'float32'")
+        # float32 events (an extension; the reference writes float64): energies rounded to single
+        # precision and sky positions stored as single-precision OFFSETS from the fp64 sky centre
+        # (the kernels compute in fp64 either way); half the bytes per event
+        self.f32 = str(event_dtype) == "float32"
+        self.tdtype = torch.float32 if self.f32 else torch.float64
         self.no_shifting, self.north_vector, self.flat_sky = no_shifting, north_vector, flat_sky
         self.sigma_pos, self.kernel, self.save_los, self.phys_coord = sigma_pos, kernel, save_los, phys_coord
         self.nH_cell = nH_cell
@@ -518,6 +525,9 @@ class _Projection:
             params["sigma_pos"] = self.sigma_pos
         params["kernel"] = self.kernel
         params["redshift"] = redshift
+        if self.f32:
+            params["event_dtype"] = "float32"
+            params["sky_offsets"] = int(observer == "external" and not self.phys_coord)
         return params
 
     def fill(self, observer, data_type, redshift, D_A_kpc, xyz, cell_id0=0):
@@ -565,6 +575,7 @@ class _Projection:
         P.seed = self.seed
         P.cell_id0 = cell_id0
         P.generic_kernels = int(bool(os.environ.get("PXB_GENERIC_KERNELS")))
+        P.events_f32 = int(self.f32)
         return P, keep
 
 
@@ -626,8 +637,8 @@ def _project_photons(obs, photon_prefix, event_prefix, normal, sky_center, **kw)
         need = C.c_int64()
         _lib.call("pxb_project_workspace_bytes", n_cells, n_pairs, C.byref(need))
         ws = torch.empty(need.value, dtype=torch.uint8, device=dev["energy"].device)
-        xsky, ysky, eobs = empty(n_photons), empty(n_photons), empty(n_photons)
-        los = empty(n_photons) if pr.save_los else None
+        xsky, ysky, eobs = (empty(n_photons, pr.tdtype) for _ in range(3))
+        los = empty(n_photons, pr.tdtype) if pr.save_los else None
         nev = empty(1, torch.int64)
         stats = empty(3)
         with stage("project"):
@@ -660,7 +671,8 @@ def make_events(event_prefix, data_source, redshift, area, exp_time, source_mode
                 sky_center, absorb_model=None, nH=None, abund_table="angr", no_shifting=False,
                 north_vector=None, sigma_pos=None, flat_sky=False, kernel="top_hat", save_los=False,
                 phys_coord=False, prng=None, point_sources=False, parameters=None, center=None,
-                dist=None, cosmology=None, velocity_fields=None, bulk_velocity=None):
+                dist=None, cosmology=None, velocity_fields=None, bulk_velocity=None,
+                event_dtype="float64"):
     """``make_photons`` followed by ``project_photons`` (external observer) in ONE pass over the
     cells: energies are sampled, shifted, absorbed and -- for the survivors only -- scattered onto
     the sky without ever writing a photon list (the two reference stages,
@@ -677,7 +689,7 @@ def make_events(event_prefix, data_source, redshift, area, exp_time, source_mode
     pr = _Projection("external", normal, sky_center, absorb_model=absorb_model, nH=nH,
                      abund_table=abund_table, no_shifting=no_shifting, north_vector=north_vector,
                      flat_sky=flat_sky, sigma_pos=sigma_pos, kernel=kernel, save_los=save_los,
-                     phys_coord=phys_coord, prng=prng)
+                     phys_coord=phys_coord, prng=prng, event_dtype=event_dtype)
     fusable = hasattr(source_model, "count_chunk") and hasattr(source_model, "spectral_model")
     if fusable:
         G = _setup_generation(data_source, redshift, area, exp_time, source_model, point_sources,
@@ -711,8 +723,8 @@ def make_events(event_prefix, data_source, redshift, area, exp_time, source_mode
         need = C.c_int64()
         _lib.call("pxb_make_events_workspace_bytes", dm.handle, out.n_cells, out.n_pairs, C.byref(need))
         ws = torch.empty(need.value, dtype=torch.uint8, device=out.idx.device)
-        xsky, ysky, eobs = empty(out.n_photons), empty(out.n_photons), empty(out.n_photons)
-        los = empty(out.n_photons) if pr.save_los else None
+        xsky, ysky, eobs = (empty(out.n_photons, pr.tdtype) for _ in range(3))
+        los = empty(out.n_photons, pr.tdtype) if pr.save_los else None
         nev = empty(2, torch.int64)          # [events, cells the mixture sampler declined]
         stats = empty(3)
         with stage("make_events"):
@@ -741,7 +753,7 @@ def make_events(event_prefix, data_source, redshift, area, exp_time, source_mode
 
     def cat(j):
         ts = [pc[j] for pc in pieces]
-        return empty(0) if not ts else (ts[0] if len(ts) == 1 else torch.cat(ts))
+        return empty(0, pr.tdtype) if not ts else (ts[0] if len(ts) == 1 else torch.cat(ts))
 
     data = {"xsky": cat(0), "ysky": cat(1), "eobs": cat(2)}
     if pr.save_los:
@@ -768,7 +780,8 @@ def _make_events_two_stage(event_prefix, data_source, redshift, area, exp_time, 
                                 absorb_model=pr.absorb_model, nH=pr.nH, abund_table=pr.abund_table,
                                 no_shifting=pr.no_shifting, north_vector=pr.north_vector,
                                 flat_sky=pr.flat_sky, sigma_pos=pr.sigma_pos, kernel=pr.kernel,
-                                save_los=pr.save_los, phys_coord=pr.phys_coord, prng=pr.seed)
+                                save_los=pr.save_los, phys_coord=pr.phys_coord, prng=pr.seed,
+                                event_dtype="float32" if pr.f32 else "float64")
     finally:
         drop_list(tmp)
     return n_ph, n_c, n_ev
@@ -777,21 +790,23 @@ def _make_events_two_stage(event_prefix, data_source, redshift, area, exp_time, 
 def project_photons(photon_prefix, event_prefix, normal, sky_center, absorb_model=None, nH=None,
                     abund_table="angr", no_shifting=False, north_vector=None, sigma_pos=None,
                     flat_sky=False, kernel="top_hat", save_los=False, column_file=None,
-                    phys_coord=False, prng=None, nH_cell=None):
-    """pyxsim.project_photons (photon_list.py:833-962); returns the number of events."""
+                    phys_coord=False, prng=None, nH_cell=None, event_dtype="float64"):
+    """pyxsim.project_photons (photon_list.py:833-962); returns the number of events.
+    ``nH_cell`` (per-cell internal columns) and ``event_dtype`` ("float32": single-precision
+    energies and sky offsets from ``sky_center``, half the bytes) are extensions."""
     return _project_photons("external", photon_prefix, event_prefix, normal, sky_center,
                             absorb_model=absorb_model, nH=nH, abund_table=abund_table,
                             no_shifting=no_shifting, north_vector=north_vector,
                             sigma_pos=sigma_pos, flat_sky=flat_sky, kernel=kernel,
                             save_los=save_los, phys_coord=phys_coord, prng=prng,
-                            column_file=column_file, nH_cell=nH_cell)
+                            column_file=column_file, nH_cell=nH_cell, event_dtype=event_dtype)
 
 
 def project_photons_allsky(photon_prefix, event_prefix, normal, absorb_model=None, nH=None,
                            abund_table="angr", no_shifting=False, center_vector=None,
-                           kernel="top_hat", save_los=False, prng=None):
+                           kernel="top_hat", save_los=False, prng=None, event_dtype="float64"):
     """pyxsim.project_photons_allsky (photon_list.py:964-1060)."""
     return _project_photons("internal", photon_prefix, event_prefix, normal, [0.0, 0.0],
                             absorb_model=absorb_model, nH=nH, abund_table=abund_table,
                             no_shifting=no_shifting, kernel=kernel, save_los=save_los,
-                            north_vector=center_vector, prng=prng)
+                            north_vector=center_vector, prng=prng, event_dtype=event_dtype)

@@ -220,6 +220,7 @@ def test_table_cie_model_through_a_fake_soxs(monkeypatch):
 
 def test_tbabs_and_pion_need_their_tables_or_soxs(monkeypatch):
     monkeypatch.setitem(sys.modules, "soxs", None)
+    monkeypatch.setitem(sys.modules, "soxs.spectra", None)     # (also a stand-in another test installed)
     with pytest.raises(ImportError):
         px.TBabsModel(0.02)
     with pytest.raises(ImportError):
