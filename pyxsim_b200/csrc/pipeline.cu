@@ -32,7 +32,7 @@ enum { MODE_SAMPLE = 0, MODE_PROJECT = 1, MODE_FUSED = 2 };
 constexpr int PL_THREADS = 1024;
 constexpr int PL_WARPS = PL_THREADS / 32;
 constexpr int PL_EPOCH = 16;                       // tiles per warp between two staging decisions
-constexpr int PL_BATCH = 32;                       // tiles a CTA draws from the global ticket at a time
+constexpr int PL_BATCH = PL_WARPS;                 // tiles a CTA works on together (one per warp)
 
 // Tile geometry per mode.  A warp tile is ROUNDS x 32 pair slots.  The sampler keeps nothing
 // between rounds and takes 128-slot tiles; the modes that project keep a tile's energies in
@@ -77,9 +77,7 @@ struct PipeArgs {
   double* eobs;
   double* los;
   int64_t* n_events;
-  unsigned long long* status; // [n_tiles] look-back words of the tiles
-  unsigned long long* bstatus;   // [n_batches] look-back words of the batches
-  unsigned long long* bcount;    // [n_batches] packed (tiles reported, sum of counts)
+  unsigned long long* bstatus;   // [n_batches] look-back words (a batch = PL_WARPS tiles)
   double* part_sum;           // [n_tiles] per-tile partial statistics
   double* part_min;
   double* part_max;
@@ -144,59 +142,31 @@ __device__ __forceinline__ void st_status(unsigned long long* p, unsigned long l
   asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v));
 }
 
-// Exclusive prefix of the survivor counts of all earlier tiles -- a two-level decoupled look-back.
-// Level 1: every tile publishes its own count (tile word, flag ST_AGG).  Level 2: tiles are handed
-// out in batches of PL_BATCH consecutive tiles; the tile that completes a batch (a packed atomic
-// counter per batch) publishes the batch total (batch word, ST_AGG), and any tile that has worked
-// out the prefix at the start of its batch publishes it as the inclusive prefix of the batch
-// before (ST_INC).  A tile's prefix = counts of the earlier tiles of its own batch (one window of
-// tile words) + a walk back over BATCH words until an inclusive prefix: with a few hundred batches
-// in flight the walk is a handful of windows, however long inclusive prefixes take to appear.
-// Resumable: returns false as soon as something it needs has not been reported yet (blocking =
-// false), keeping its progress in (stage_j, prefix); whole warp participates.  Progress: a warp
-// publishes its count before it looks back, tiles are handed out in increasing order, and a tile
-// whose count is missing is being worked on by a resident warp that waits for nothing.
-struct LookBack {
-  const unsigned long long* tiles;   // [n_tiles]
-  unsigned long long* batches;       // [n_batches]
-};
-
-// stage_j: >= 0: own batch done, next batch word to read; -1: finished; -2: own batch still due
-__device__ __forceinline__ bool lookback_run(const LookBack& S, int64_t tile, int64_t& stage_j,
+// Exclusive prefix of the survivor counts of all earlier BATCHES (a batch = the PL_WARPS tiles a
+// CTA works on together) -- decoupled look-back over one status word per batch: the CTA publishes
+// its batch's count (ST_AGG) as soon as the absorption decisions of the batch are made, walks
+// back over the earlier batches' words, adding counts until it meets an inclusive prefix, and
+// publishes its own inclusive prefix (ST_INC).  One warp per CTA does this; with one batch per SM
+// in flight the walk is a handful of 32-word windows.  Resumable: with blocking = false it returns
+// false as soon as a needed batch has not reported yet, keeping its progress in (j, prefix).
+// Progress: a CTA publishes its count before it looks back, batches are handed out in increasing
+// order, and a batch whose count is missing is being worked on by a resident CTA whose decision
+// phase waits for nothing.
+__device__ __forceinline__ bool lookback_run(const unsigned long long* status, int64_t& j,
                                              int64_t& prefix, int lane, bool blocking) {
-  unsigned nap = 64;   // back-off: a waiting warp must not eat the issue slots of the one it waits for
-  const int64_t b = tile / PL_BATCH;
-  const int n = (int)(tile - b * PL_BATCH);
+  unsigned nap = 32;
   for (;;) {
-    if (stage_j == -2) {
-      // the earlier tiles of the own batch
-      const unsigned long long sv = lane < n ? ld_status(S.tiles + b * PL_BATCH + lane) : ST_AGG;
-      if (__any_sync(0xffffffffu, (sv & ST_MASK) == 0ull)) {
-        if (!blocking) return false;
-        __nanosleep(nap);
-        nap = min(nap * 2u, 2048u);
-        continue;
-      }
-      int64_t v = lane < n ? (int64_t)(sv & ~ST_MASK) : 0;
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-      prefix = v;
-      stage_j = b - 1;
-    }
-    if (stage_j < 0) {                                        // walked past batch 0
-      stage_j = -1;
-      return true;
-    }
-    const int64_t idx = stage_j - lane;
-    const unsigned long long sv = (idx >= 0) ? ld_status(S.batches + idx) : ST_INC;
+    if (j < 0) return true;                                   // walked past batch 0
+    const int64_t idx = j - lane;
+    const unsigned long long sv = (idx >= 0) ? ld_status(status + idx) : ST_INC;
     const unsigned inc = __ballot_sync(0xffffffffu, (sv & ST_MASK) == ST_INC);
     const unsigned emp = __ballot_sync(0xffffffffu, (sv & ST_MASK) == 0ull);
     const int first = inc ? (__ffs(inc) - 1) : 32;           // nearest batch with an inclusive prefix
     const unsigned need = first >= 31 ? 0xffffffffu : ((2u << first) - 1u);
-    if (emp & need) {                                        // a needed batch is not complete
+    if (emp & need) {                                        // a needed batch has not reported yet
       if (!blocking) return false;
       __nanosleep(nap);
-      nap = min(nap * 2u, 2048u);
+      nap = min(nap * 2u, 1024u);
       continue;
     }
     int64_t v = (lane <= first) ? (int64_t)(sv & ~ST_MASK) : 0;
@@ -204,38 +174,11 @@ __device__ __forceinline__ bool lookback_run(const LookBack& S, int64_t tile, in
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     prefix += v;
     if (first < 32) {
-      stage_j = -1;
+      j = -1;
       return true;
     }
-    stage_j -= 32;
+    j -= 32;
   }
-}
-
-// after a tile's prefix is complete: the prefix at the start of its batch is the inclusive prefix
-// of the batch before (every finisher of the batch writes the same value)
-__device__ __forceinline__ void lookback_publish(const LookBack& S, int64_t tile, int64_t prefix,
-                                                 int lane) {
-  const int64_t b = tile / PL_BATCH;
-  const int n = (int)(tile - b * PL_BATCH);
-  if (b == 0) return;
-  // subtract the own batch's earlier tiles again
-  const unsigned long long sv = lane < n ? ld_status(S.tiles + b * PL_BATCH + lane) : 0ull;
-  int64_t v = (int64_t)(sv & ~ST_MASK);
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  if (lane == 0) st_status(S.batches + (b - 1), ST_INC | (unsigned long long)(prefix - v));
-}
-
-// a tile reports its count: tile word, and the batch word when it completes the batch
-__device__ __forceinline__ void lookback_report(const LookBack& S, unsigned long long* bcount,
-                                                int64_t tile, int64_t n_tiles, int run) {
-  st_status(const_cast<unsigned long long*>(S.tiles) + tile, ST_AGG | (unsigned long long)run);
-  const int64_t b = tile / PL_BATCH;
-  const int64_t in_batch = min((int64_t)PL_BATCH, n_tiles - b * PL_BATCH);
-  // packed counter: tiles reported << 40 | sum of their counts
-  const unsigned long long old = atomicAdd(bcount + b, (1ull << 40) | (unsigned long long)run);
-  if ((int64_t)(old >> 40) == in_batch - 1)
-    st_status(S.batches + b, ST_AGG | ((old & ((1ull << 40) - 1ull)) + (unsigned long long)run));
 }
 
 // ---------------------------------------------------------------------------------------
@@ -488,9 +431,11 @@ k_pipeline(const DevModel M, const __grid_constant__ pxb_thermal_cells C,
   const DevTable& T = M.prim;
   uint2* s_alias = reinterpret_cast<uint2*>(dyn);
   __shared__ uint64_t s_bar;
-  __shared__ int s_live, s_want;
-  __shared__ unsigned long long s_tk;                  // CTA ticket cache: (batch << 32) | tiles taken
-  __shared__ long long s_pend[PL_WARPS][2][4];         // per warp and buffer: tile, prefix, j, info
+  __shared__ int s_want;
+  __shared__ long long s_batch[2];                     // batch per buffer (-1: none)
+  __shared__ long long s_base[2];                      // its exclusive prefix, once known
+  __shared__ int s_cnt[2][PL_WARPS];                   // survivors of its tiles
+  __shared__ long long s_lbj, s_lbprefix;              // warp 0: look-back progress of the pending batch
   __shared__ WabsFast s_wabs;
 
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -498,11 +443,7 @@ k_pipeline(const DevModel M, const __grid_constant__ pxb_thermal_cells C,
   const unsigned se_off = (unsigned)A.off_e + (unsigned)wid * (unsigned)(NBUF * 2 * TSLOTS * sizeof(double));
   const unsigned qs_off = (unsigned)A.off_qs + (unsigned)wid * (unsigned)(NBUF * MAXC * sizeof(int));
   if (MODE != MODE_SAMPLE && P.absorb_kind == PXB_ABS_WABS) wabs_fast_init(s_wabs);
-  if (threadIdx.x == 0) {
-    mbar_init(&s_bar, 1);
-    s_live = PL_WARPS;
-    s_tk = (0xFFFFFFFFull << 32) | (unsigned long long)PL_BATCH;    // empty: the first taker refills
-  }
+  if (threadIdx.x == 0) mbar_init(&s_bar, 1);
   __syncthreads();
   int tag = -1;
   uint32_t parity = 0;
@@ -528,398 +469,422 @@ k_pipeline(const DevModel M, const __grid_constant__ pxb_thermal_cells C,
     }
   };
 
-  // Every WARP takes its tiles one at a time, in increasing order over the whole grid (a global
-  // ticket hands batches of 32 tiles to a CTA, the CTA's warps take them from shared memory), so
-  // a tile only ever waits for tiles that were started before it.  Warps never meet at a CTA
-  // barrier except at the staging epochs below.
-  bool out = false;            // no more tiles to draw
-  bool have_pend = false;      // a tile whose decisions are made and whose scatter step is still due
-  unsigned pend_bits = 0;      // its per-lane survivor bits and cell bytes
-  int buf = 0;
-  for (int it = 0;; ++it) {
-    if (staging && (it & (PL_EPOCH - 1)) == 0) {
-      // staging epoch: all warps of the CTA (also those that have run out of tiles) meet, and the
-      // rows of the temperature bin the grid is currently working in are (re)staged
-      __syncthreads();     // every warp is done with the previously staged rows
-      if (s_live == 0) break;
-      if (threadIdx.x == 0) {
-        // the tile the grid will hand out next tells which temperature bin is being worked on
-        const int64_t tnext = min((int64_t)ld_ticket(A.ticket) * PL_BATCH, A.n_tiles - 1);
-        const CellRec* f0 = A.recs + __ldg(A.tile_cell + tnext);
-        const int meta0 = __ldg(&f0->meta);
-        s_want = ((meta0 & 7) == 2 && !(meta0 & 8)) ? __ldg(&f0->z1) : -1;
+  // ---- a tile's decisions: energies (sampled or loaded), Doppler shift, absorption -------------
+  // (writes the tile's energies and cell starts into buffer `buf`; returns its survivor count and
+  // the per-lane survivor bits / cell bytes the scatter step needs)
+  auto decide = [&](int64_t tile, int buf, int& run, int& how, unsigned& bits) {
+    double* const s_e = reinterpret_cast<double*>(dyn + se_off + (unsigned)buf * (unsigned)(2 * TSLOTS * sizeof(double)));
+    int* const s_qs = reinterpret_cast<int*>(dyn + qs_off + (unsigned)buf * (unsigned)(MAXC * sizeof(int)));
+    const int64_t slot0 = tile * TSLOTS;
+    const int nslots = (int)min((int64_t)TSLOTS, A.n_pairs - slot0);
+    const int64_t c0 = __ldg(A.tile_cell + tile);
+    const int64_t c1 = (tile + 1 < A.n_tiles) ? __ldg(A.tile_cell + tile + 1) : A.n_cells - 1;
+    // cell starts of the tile, relative to its first slot (the first cell's is clamped to -1:
+    // only the order matters for the look-up).
+    // how = 0: every cell of the tile is non-empty -> ballot look-up; 1: empty cells (lists
+    // from elsewhere) -> shared-memory bisection; 2: more cells than fit -> global bisection.
+    const int64_t ncl = c1 - c0 + 1;
+    const int nc = ncl <= MAXC ? (int)ncl : 0;
+    how = nc == 0 ? 2 : 0;
+    const int64_t m00 = slot0 - __ldg(A.qoff + c0);      // pair index of slot 0 inside cell c0
+    __syncwarp();
+    {
+      bool dup = false;
+      for (int q = lane; q < nc; q += 32) {
+        const int64_t a = __ldg(A.qoff + c0 + q) - slot0, b = __ldg(A.qoff + c0 + q + 1) - slot0;
+        s_qs[q] = (int)max(a, (int64_t)-1);
+        dup |= (a == b);
       }
-      __syncthreads();     // one decision for the whole CTA
-      const int w = s_want;
-      if (w >= 0 && w != tag) {
-        const uint32_t row_bytes = (uint32_t)T.alias_stride * (uint32_t)sizeof(uint2);
-        if (threadIdx.x == 0) {
-          mbar_expect_tx(&s_bar, 4u * row_bytes);
+      if (how == 0 && __any_sync(0xffffffffu, dup)) how = 1;
+    }
+    __syncwarp();
+    // Cell of every pair slot of the tile, relative to c0, for all rounds at once (one byte
+    // per round; MAXC < 256).  how = 0: the cell of a slot is the number of cells starting at
+    // or before it, minus one -- a ballot for the cells that start before the round's 32
+    // slots plus a warp-wide OR of start bits inside them.
+    unsigned relpack = 0;
+    if (how == 0) {
+      unsigned cnt = 0;
+      for (int qb = 0; qb < nc; qb += 32) {
+        const int q = qb + lane;
+        const int qs = q < nc ? s_qs[q] : 0x7fffffff;
 #pragma unroll
-          for (int slot = 0; slot < 4; ++slot)   // slot = 2 * table + (row - w)
-            tma_bulk_g2s(s_alias + (size_t)slot * T.alias_stride,
-                         alias_row(&T, slot >> 1, w + (slot & 1)), row_bytes, &s_bar);
+        for (int r = 0; r < ROUNDS; ++r) {
+          const unsigned before = __ballot_sync(0xffffffffu, qs < r * 32);
+          const unsigned d = (unsigned)(qs - r * 32);
+          const unsigned mask = __reduce_or_sync(0xffffffffu, d < 32u ? (1u << d) : 0u);
+          cnt += (unsigned)(__popc(before) + __popc(mask & ((2u << lane) - 1u))) << (8 * r);
         }
-        mbar_wait(&s_bar, parity);
-        parity ^= 1u;
-        tag = w;
+      }
+      relpack = cnt - (ROUNDS == 4 ? 0x01010101u : 0x00000101u);   // (every byte is >= 1)
+    } else if (how == 1) {
+#pragma unroll
+      for (int r = 0; r < ROUNDS; ++r) {
+        const int srel = min(r * 32 + lane, nslots - 1);
+        int rel = 0;   // largest q with s_qs[q] <= srel
+        for (int step = 128; step > 0; step >>= 1) {
+          const int q = rel + step;
+          if (q < nc && s_qs[q] <= srel) rel = q;
+        }
+        relpack |= (unsigned)rel << (8 * r);
       }
     }
 
-    // ---- (A) a new tile: energies (sampled or loaded), Doppler shift, absorption decisions -----
-    bool have_new = false;
-    int64_t tile = 0;
-    int run = 0, how = 0;
-    unsigned new_bits = 0;
-    if (!out) {
-      {
-        unsigned long long old = 0;
-        if (lane == 0) {
-          for (;;) {
-            old = atomicAdd(&s_tk, 1ull);
-            const unsigned n = (unsigned)old;
-            if (n < (unsigned)PL_BATCH) break;
-            if (n == (unsigned)PL_BATCH) {                    // this warp refills the CTA's cache
-              const unsigned long long b = atomicAdd(A.ticket, 1u);
-              atomicExch(&s_tk, (b << 32) | 1ull);
-              old = b << 32;                                  // ... and takes its first tile
-              break;
+    unsigned detpack = 0;
+    double tsum = 0.0, tmin = 1.0e99, tmax = -1.0e99;
+#pragma unroll 1
+    for (int r = 0; r < ROUNDS; ++r) {
+      if (r * 32 >= nslots) break;
+      const int srel = r * 32 + lane;
+      const bool valid = srel < nslots;
+      int rel;
+      int64_t m;
+      locate(how, relpack, s_qs, slot0, nslots, c0, c1, m00, r, srel, rel, m);
+      const CellRec* rp = A.recs + (c0 + rel);
+      const longlong2 q0 = __ldg(reinterpret_cast<const longlong2*>(rp));
+      const longlong2 q1 = __ldg(reinterpret_cast<const longlong2*>(rp) + 1);
+      const uint64_t gid = (uint64_t)q0.x;
+      const uint64_t d0 = 2ull * (uint64_t)m;
+      const bool hasA = valid;
+      const bool hasB = valid && (int64_t)(d0 + 1) < q1.y;
+      double eA = 0.0, eB = 0.0;
+      bool elig = true;
+      if (MODE != MODE_PROJECT) {
+        const longlong2 q2 = __ldg(reinterpret_cast<const longlong2*>(rp) + 2);
+        const longlong2 q3 = __ldg(reinterpret_cast<const longlong2*>(rp) + 3);
+        const int z1 = (int)(q2.x & 0xffffffffll), meta = (int)(q2.x >> 32);
+        const long long cn0 = q2.y, cn1 = q3.x, cn2 = q3.y;
+        elig = (meta & 16) != 0;
+        if (valid && elig) {
+          if (SPEC != 0 || (meta & (32 | 64))) {
+            // split modes: the photon's component follows from its index inside the cell
+            const Philox4 E = pxb_rand4(RKE, STREAM_ENERGY, gid, (uint64_t)m);
+            const bool prim = SPEC != 0 || !(meta & 8);
+            const DevTable* tb = prim ? &M.prim : &M.fb;
+            const bool four = SPEC != 0 || (meta & 32);
+            // counts below 2^31: 32-bit compares (any cell in practice)
+            const bool small = q1.y < 0x7fffffffll;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              const long long dd = (long long)d0 + h;
+              int comp;
+              if (small) {
+                const int d32 = (int)dd;
+                comp = (d32 >= (int)cn0) + (d32 >= (int)cn1) + (d32 >= (int)cn2);
+              } else {
+                comp = (dd >= cn0) + (dd >= cn1) + (dd >= cn2);
+              }
+              int tab, row;
+              if (four) {
+                // four components: (row0,cosmic), (row0,metal), (row1,cosmic), (row1,metal)
+                tab = comp & 1;
+                row = z1 + (comp >> 1);
+              } else {
+                // general split: comp is the ROW, the table comes from the side array
+                const long long din = dd - (comp == 0 ? 0 : (comp == 1 ? cn0 : (comp == 2 ? cn1 : cn2)));
+                const int ntab = 2 + C.nvar;
+                const int64_t* tc = A.tabcum + (c0 + rel) * A.tab_stride + comp * ntab;
+                tab = 0;
+                if (ntab <= 8) {
+                  for (int t2 = 0; t2 < ntab - 1; ++t2) tab += (din >= __ldg(tc + t2)) ? 1 : 0;
+                } else {
+                  int lo = 0, hi = ntab - 1;     // first tab with din < tc[tab]
+                  while (lo < hi) {
+                    const int mid = (lo + hi) >> 1;
+                    if (din >= __ldg(tc + mid)) lo = mid + 1; else hi = mid;
+                  }
+                  tab = lo;
+                }
+                row = fast_row(tb, z1, meta & 7, comp);
+              }
+              const uint32_t w0 = h ? E.z : E.x, w1 = h ? E.w : E.y;
+              const unsigned dr = (unsigned)(row - tag);
+              uint32_t v;
+              int j;
+              if (prim && tab < 2 && tag >= 0 && dr < 2u)   // staged row: shared-memory gather
+                j = alias_pick(s_alias + (unsigned)(tab * 2 + (int)dr) * (unsigned)T.alias_stride,
+                               (unsigned)T.nbins, w0, w1, v);
+              else
+                j = alias_pick(alias_row(tb, tab, row), (unsigned)T.nbins, w0, w1, v);
+              const double e = alias_energy<(SPEC != 0) ? 1 : 0>(M, j, v);
+              if (h) eB = e; else eA = e;
             }
-            const unsigned long long seen = old >> 32;        // somebody else is refilling
-            while ((*reinterpret_cast<volatile unsigned long long*>(&s_tk) >> 32) == seen) __nanosleep(32);
+          } else {
+            // probability mode: every photon picks its component itself (one block per photon)
+            FastCell fc;
+            fc.z1 = z1;
+            fc.meta = meta;
+            fc.cnt[0] = cn0; fc.cnt[1] = cn1; fc.cnt[2] = cn2;
+            const int64_t i = __ldg(A.idx + c0 + rel);
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              if (h && !hasB) break;
+              const Philox4 rn = pxb_rand4(RKE, STREAM_ENERGY, gid, d0 + h);
+              const double e = fast_draw<0>(M, C, fc, i, u53(rn.x, rn.y), rn.z, rn.w);
+              if (h) eB = e; else eA = e;
+            }
+          }
+          if (SPEC == 0 && M.binscale_log) {
+            eA = exp10(eA);
+            eB = exp10(eB);
           }
         }
-        old = __shfl_sync(0xffffffffu, old, 0);
-        tile = (int64_t)(old >> 32) * PL_BATCH + (int64_t)(unsigned)old;
       }
+      if (MODE == MODE_SAMPLE) {
+        if (elig) {
+          double* dst = A.energies + q1.x + (int64_t)d0;
+          if (hasB && (((uintptr_t)dst) & 15) == 0) {
+            asm volatile("st.global.L1::no_allocate.v2.f64 [%0], {%1, %2};" ::"l"(dst), "d"(eA), "d"(eB));
+          } else {
+            if (hasA) st_stream(dst, eA);
+            if (hasB) st_stream(dst + 1, eB);
+          }
+        }
+        continue;
+      }
+      if (MODE == MODE_PROJECT) {
+        const double* src = A.energies + q1.x + (int64_t)d0;
+        if (hasA) eA = ld_stream(src);
+        if (hasB) eB = ld_stream(src + 1);
+      }
+      const double shift = __longlong_as_double(q0.y);
+      eA *= shift;
+      eB *= shift;
+      bool detA = hasA && elig, detB = hasB && elig;
+      if (absorb) {
+        const Philox4 Aw = pxb_rand4(RKP, STREAM_PROJ_A, gid, (uint64_t)m);
+        Philox4 Dw{0u, 0u, 0u, 0u};
+        if (SPEC == 0 && P.nH_cell) Dw = pxb_rand4(RKP, STREAM_PROJ_D, gid, (uint64_t)m);
+        if (detA) detA = absorb_decision<SPEC>(P, RKP, s_wabs, c0 + rel, gid, d0, Aw.x, Dw.x, eA);
+        if (detB) detB = absorb_decision<SPEC>(P, RKP, s_wabs, c0 + rel, gid, d0 + 1, Aw.y, Dw.y, eB);
+      }
+      s_e[2 * srel] = eA;
+      s_e[2 * srel + 1] = eB;
+      if (detA) {
+        tsum += eA;
+        tmin = eA < tmin ? eA : tmin;   // (energies are never NaN: plain compares)
+        tmax = eA > tmax ? eA : tmax;
+      }
+      if (detB) {
+        tsum += eB;
+        tmin = eB < tmin ? eB : tmin;
+        tmax = eB > tmax ? eB : tmax;
+      }
+      run += __popc(__ballot_sync(0xffffffffu, detA)) + __popc(__ballot_sync(0xffffffffu, detB));
+      detpack |= ((detA ? 1u : 0u) | (detB ? 2u : 0u)) << (2 * r);
+    }
+
+    if (MODE != MODE_SAMPLE) {
+      tsum = warp_sum(tsum);
+      tmin = warp_min(tmin);
+      tmax = warp_max(tmax);
+      if (lane == 0) {
+        A.part_sum[tile] = tsum;
+        A.part_min[tile] = tmin;
+        A.part_max[tile] = tmax;
+      }
+      bits = detpack | (relpack << 8);
+    }
+  };
+
+  // ---- a tile's scatter step: survivors -> their final, order-preserving slots ------------------
+  auto scatter = [&](int64_t ptile, int pbuf, int64_t base, int phow, unsigned pend_bits) {
+    const double* const s_e = reinterpret_cast<const double*>(dyn + se_off + (unsigned)pbuf * (unsigned)(2 * TSLOTS * sizeof(double)));
+    const int* const s_qs = reinterpret_cast<const int*>(dyn + qs_off + (unsigned)pbuf * (unsigned)(MAXC * sizeof(int)));
+    const int64_t slot0 = ptile * TSLOTS;
+    const int nslots = (int)min((int64_t)TSLOTS, A.n_pairs - slot0);
+    const int64_t c0 = __ldg(A.tile_cell + ptile);
+    const int64_t c1 = (ptile + 1 < A.n_tiles) ? __ldg(A.tile_cell + ptile + 1) : A.n_cells - 1;
+    const int64_t m00 = slot0 - __ldg(A.qoff + c0);
+    const unsigned detpack = pend_bits & 255u, relpack = pend_bits >> 8;
+    // (tile-uniform 64-bit bases, 32-bit offsets inside the tile; float events: half the bytes)
+    const int64_t ob = A.f32 ? base / 2 : base;         // (float arrays: base counts 4-byte slots)
+    double* const xb = A.xsky + ob;
+    double* const yb = A.ysky + ob;
+    double* const eb = A.eobs + ob;
+    double* const lb = A.los ? A.los + ob : nullptr;
+    const int fo = (int)(base & 1);
+    int done = 0;
+#pragma unroll 1
+    for (int r = 0; r < ROUNDS; ++r) {
+      if (r * 32 >= nslots) break;
+      const bool detA = (detpack >> (2 * r)) & 1u, detB = (detpack >> (2 * r + 1)) & 1u;
+      const unsigned balA = __ballot_sync(0xffffffffu, detA), balB = __ballot_sync(0xffffffffu, detB);
+      if (!(balA | balB)) continue;
+      const int o0 = done + __popc(balA & lt) + __popc(balB & lt);
+      done += __popc(balA) + __popc(balB);
+      if (!(detA || detB)) continue;
+      const int srel = r * 32 + lane;
+      int rel;
+      int64_t m;
+      locate(phow, relpack, s_qs, slot0, nslots, c0, c1, m00, r, srel, rel, m);
+      const uint64_t gid = (uint64_t)__ldg(&A.recs[c0 + rel].gid);
+      const uint64_t d0 = 2ull * (uint64_t)m;
+      const CellGeom g = ld_geom(A.geom + c0 + rel);
+      const Philox4 Bw = pxb_rand4(RKP, STREAM_PROJ_B, gid, (uint64_t)m);
+      // the third scatter word lives in the absorption block: recomputed only where it is
+      // used (off-axis cells, particle kernels, all-sky)
+      Philox4 Aw{0u, 0u, 0u, 0u};
+      if (SPEC == 2 || (SPEC == 0 && !(P.observer == 0 && P.data_type == 0 && P.vn_axis >= 0)))
+        Aw = pxb_rand4(RKP, STREAM_PROJ_A, gid, (uint64_t)m);
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        if (!(h ? detB : detA)) continue;
+        double xs, ys, los;
+        const uint32_t w0 = h ? Bw.z : Bw.x, w1 = h ? Bw.w : Bw.y, w2 = h ? Aw.w : Aw.z;
+        if (SPEC != 0 || P.observer == 0)
+          scatter_external<SPEC>(P, RKP, g, K, w0, w1, w2, gid, d0 + h, xs, ys, los);
+        else
+          scatter_allsky(P, RKP, g, w0, w1, w2, gid, d0 + h, xs, ys, los);
+        const int o = o0 + (h && detA ? 1 : 0);
+        if (!A.f32) {
+          st_stream(xb + o, xs);
+          st_stream(yb + o, ys);
+          st_stream(eb + o, s_e[2 * srel + h]);
+          if (lb) st_stream(lb + o, los);
+        } else {
+          // sky offsets from the fp64 centre and energies in single precision
+          __stcs(reinterpret_cast<float*>(xb) + fo + o, (float)(xs - A.sky0));
+          __stcs(reinterpret_cast<float*>(yb) + fo + o, (float)(ys - A.sky1));
+          __stcs(reinterpret_cast<float*>(eb) + fo + o, (float)s_e[2 * srel + h]);
+          if (lb) __stcs(reinterpret_cast<float*>(lb) + fo + o, (float)los);
+        }
+      }
+    }
+  };
+
+  // the rows of the temperature bin the grid is working in are (re)staged; every thread of the CTA
+  // calls this at a point where no warp is sampling (tnext: the tile about to be handed out)
+  auto restage = [&](int64_t tnext) {
+    if (threadIdx.x == 0) {
+      const CellRec* f0 = A.recs + __ldg(A.tile_cell + min(tnext, A.n_tiles - 1));
+      const int meta0 = __ldg(&f0->meta);
+      s_want = ((meta0 & 7) == 2 && !(meta0 & 8)) ? __ldg(&f0->z1) : -1;
+    }
+    __syncthreads();     // one decision for the whole CTA
+    const int w = s_want;
+    if (w >= 0 && w != tag) {
+      const uint32_t row_bytes = (uint32_t)T.alias_stride * (uint32_t)sizeof(uint2);
+      if (threadIdx.x == 0) {
+        mbar_expect_tx(&s_bar, 4u * row_bytes);
+#pragma unroll
+        for (int slot = 0; slot < 4; ++slot)   // slot = 2 * table + (row - w)
+          tma_bulk_g2s(s_alias + (size_t)slot * T.alias_stride,
+                       alias_row(&T, slot >> 1, w + (slot & 1)), row_bytes, &s_bar);
+      }
+      mbar_wait(&s_bar, parity);
+      parity ^= 1u;
+      tag = w;
+    }
+  };
+
+  if (MODE == MODE_SAMPLE) {
+    // Sampling keeps nothing between tiles: every WARP draws its tiles one at a time from the
+    // global ticket; the warps of a CTA only meet at the staging epochs.
+    __shared__ int s_live;
+    if (threadIdx.x == 0) s_live = PL_WARPS;
+    __syncthreads();
+    bool out = false;
+    for (int it = 0;; ++it) {
+      if (staging && (it & (PL_EPOCH - 1)) == 0) {
+        __syncthreads();     // every warp is done with the previously staged rows
+        if (s_live == 0) break;
+        restage((int64_t)ld_ticket(A.ticket));
+      }
+      if (out) {
+        if (!staging) break;
+        continue;
+      }
+      unsigned int tk = 0;
+      if (lane == 0) tk = atomicAdd(A.ticket, 1u);
+      const int64_t tile = (int64_t)__shfl_sync(0xffffffffu, tk, 0);
       if (tile >= A.n_tiles) {
         out = true;
         if (lane == 0) atomicSub(&s_live, 1);
-      } else {
-        have_new = true;
-        double* const s_e = reinterpret_cast<double*>(dyn + se_off + (unsigned)buf * (unsigned)(2 * TSLOTS * sizeof(double)));
-        int* const s_qs = reinterpret_cast<int*>(dyn + qs_off + (unsigned)buf * (unsigned)(MAXC * sizeof(int)));
-        const int64_t slot0 = tile * TSLOTS;
-        const int nslots = (int)min((int64_t)TSLOTS, A.n_pairs - slot0);
-        const int64_t c0 = __ldg(A.tile_cell + tile);
-        const int64_t c1 = (tile + 1 < A.n_tiles) ? __ldg(A.tile_cell + tile + 1) : A.n_cells - 1;
-        // cell starts of the tile, relative to its first slot (the first cell's is clamped to -1:
-        // only the order matters for the look-up).
-        // how = 0: every cell of the tile is non-empty -> ballot look-up; 1: empty cells (lists
-        // from elsewhere) -> shared-memory bisection; 2: more cells than fit -> global bisection.
-        const int64_t ncl = c1 - c0 + 1;
-        const int nc = ncl <= MAXC ? (int)ncl : 0;
-        how = nc == 0 ? 2 : 0;
-        const int64_t m00 = slot0 - __ldg(A.qoff + c0);      // pair index of slot 0 inside cell c0
-        __syncwarp();
-        {
-          bool dup = false;
-          for (int q = lane; q < nc; q += 32) {
-            const int64_t a = __ldg(A.qoff + c0 + q) - slot0, b = __ldg(A.qoff + c0 + q + 1) - slot0;
-            s_qs[q] = (int)max(a, (int64_t)-1);
-            dup |= (a == b);
-          }
-          if (how == 0 && __any_sync(0xffffffffu, dup)) how = 1;
-        }
-        __syncwarp();
-        // Cell of every pair slot of the tile, relative to c0, for all rounds at once (one byte
-        // per round; MAXC < 256).  how = 0: the cell of a slot is the number of cells starting at
-        // or before it, minus one -- a ballot for the cells that start before the round's 32
-        // slots plus a warp-wide OR of start bits inside them.
-        unsigned relpack = 0;
-        if (how == 0) {
-          unsigned cnt = 0;
-          for (int qb = 0; qb < nc; qb += 32) {
-            const int q = qb + lane;
-            const int qs = q < nc ? s_qs[q] : 0x7fffffff;
-#pragma unroll
-            for (int r = 0; r < ROUNDS; ++r) {
-              const unsigned before = __ballot_sync(0xffffffffu, qs < r * 32);
-              const unsigned d = (unsigned)(qs - r * 32);
-              const unsigned mask = __reduce_or_sync(0xffffffffu, d < 32u ? (1u << d) : 0u);
-              cnt += (unsigned)(__popc(before) + __popc(mask & ((2u << lane) - 1u))) << (8 * r);
-            }
-          }
-          relpack = cnt - (ROUNDS == 4 ? 0x01010101u : 0x00000101u);   // (every byte is >= 1)
-        } else if (how == 1) {
-#pragma unroll
-          for (int r = 0; r < ROUNDS; ++r) {
-            const int srel = min(r * 32 + lane, nslots - 1);
-            int rel = 0;   // largest q with s_qs[q] <= srel
-            for (int step = 128; step > 0; step >>= 1) {
-              const int q = rel + step;
-              if (q < nc && s_qs[q] <= srel) rel = q;
-            }
-            relpack |= (unsigned)rel << (8 * r);
-          }
-        }
-
-        unsigned detpack = 0;
-        double tsum = 0.0, tmin = 1.0e99, tmax = -1.0e99;
-#pragma unroll 1
-        for (int r = 0; r < ROUNDS; ++r) {
-          if (r * 32 >= nslots) break;
-          const int srel = r * 32 + lane;
-          const bool valid = srel < nslots;
-          int rel;
-          int64_t m;
-          locate(how, relpack, s_qs, slot0, nslots, c0, c1, m00, r, srel, rel, m);
-          const CellRec* rp = A.recs + (c0 + rel);
-          const longlong2 q0 = __ldg(reinterpret_cast<const longlong2*>(rp));
-          const longlong2 q1 = __ldg(reinterpret_cast<const longlong2*>(rp) + 1);
-          const uint64_t gid = (uint64_t)q0.x;
-          const uint64_t d0 = 2ull * (uint64_t)m;
-          const bool hasA = valid;
-          const bool hasB = valid && (int64_t)(d0 + 1) < q1.y;
-          double eA = 0.0, eB = 0.0;
-          bool elig = true;
-          if (MODE != MODE_PROJECT) {
-            const longlong2 q2 = __ldg(reinterpret_cast<const longlong2*>(rp) + 2);
-            const longlong2 q3 = __ldg(reinterpret_cast<const longlong2*>(rp) + 3);
-            const int z1 = (int)(q2.x & 0xffffffffll), meta = (int)(q2.x >> 32);
-            const long long cn0 = q2.y, cn1 = q3.x, cn2 = q3.y;
-            elig = (meta & 16) != 0;
-            if (valid && elig) {
-              if (SPEC != 0 || (meta & (32 | 64))) {
-                // split modes: the photon's component follows from its index inside the cell
-                const Philox4 E = pxb_rand4(RKE, STREAM_ENERGY, gid, (uint64_t)m);
-                const bool prim = SPEC != 0 || !(meta & 8);
-                const DevTable* tb = prim ? &M.prim : &M.fb;
-                const bool four = SPEC != 0 || (meta & 32);
-                // counts below 2^31: 32-bit compares (any cell in practice)
-                const bool small = q1.y < 0x7fffffffll;
-#pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                  const long long dd = (long long)d0 + h;
-                  int comp;
-                  if (small) {
-                    const int d32 = (int)dd;
-                    comp = (d32 >= (int)cn0) + (d32 >= (int)cn1) + (d32 >= (int)cn2);
-                  } else {
-                    comp = (dd >= cn0) + (dd >= cn1) + (dd >= cn2);
-                  }
-                  int tab, row;
-                  if (four) {
-                    // four components: (row0,cosmic), (row0,metal), (row1,cosmic), (row1,metal)
-                    tab = comp & 1;
-                    row = z1 + (comp >> 1);
-                  } else {
-                    // general split: comp is the ROW, the table comes from the side array
-                    const long long din = dd - (comp == 0 ? 0 : (comp == 1 ? cn0 : (comp == 2 ? cn1 : cn2)));
-                    const int ntab = 2 + C.nvar;
-                    const int64_t* tc = A.tabcum + (c0 + rel) * A.tab_stride + comp * ntab;
-                    tab = 0;
-                    if (ntab <= 8) {
-                      for (int t2 = 0; t2 < ntab - 1; ++t2) tab += (din >= __ldg(tc + t2)) ? 1 : 0;
-                    } else {
-                      int lo = 0, hi = ntab - 1;     // first tab with din < tc[tab]
-                      while (lo < hi) {
-                        const int mid = (lo + hi) >> 1;
-                        if (din >= __ldg(tc + mid)) lo = mid + 1; else hi = mid;
-                      }
-                      tab = lo;
-                    }
-                    row = fast_row(tb, z1, meta & 7, comp);
-                  }
-                  const uint32_t w0 = h ? E.z : E.x, w1 = h ? E.w : E.y;
-                  const unsigned dr = (unsigned)(row - tag);
-                  uint32_t v;
-                  int j;
-                  if (prim && tab < 2 && tag >= 0 && dr < 2u)   // staged row: shared-memory gather
-                    j = alias_pick(s_alias + (unsigned)(tab * 2 + (int)dr) * (unsigned)T.alias_stride,
-                                   (unsigned)T.nbins, w0, w1, v);
-                  else
-                    j = alias_pick(alias_row(tb, tab, row), (unsigned)T.nbins, w0, w1, v);
-                  const double e = alias_energy<(SPEC != 0) ? 1 : 0>(M, j, v);
-                  if (h) eB = e; else eA = e;
-                }
-              } else {
-                // probability mode: every photon picks its component itself (one block per photon)
-                FastCell fc;
-                fc.z1 = z1;
-                fc.meta = meta;
-                fc.cnt[0] = cn0; fc.cnt[1] = cn1; fc.cnt[2] = cn2;
-                const int64_t i = __ldg(A.idx + c0 + rel);
-#pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                  if (h && !hasB) break;
-                  const Philox4 rn = pxb_rand4(RKE, STREAM_ENERGY, gid, d0 + h);
-                  const double e = fast_draw<0>(M, C, fc, i, u53(rn.x, rn.y), rn.z, rn.w);
-                  if (h) eB = e; else eA = e;
-                }
-              }
-              if (SPEC == 0 && M.binscale_log) {
-                eA = exp10(eA);
-                eB = exp10(eB);
-              }
-            }
-          }
-          if (MODE == MODE_SAMPLE) {
-            if (elig) {
-              double* dst = A.energies + q1.x + (int64_t)d0;
-              if (hasB && (((uintptr_t)dst) & 15) == 0) {
-                asm volatile("st.global.L1::no_allocate.v2.f64 [%0], {%1, %2};" ::"l"(dst), "d"(eA), "d"(eB));
-              } else {
-                if (hasA) st_stream(dst, eA);
-                if (hasB) st_stream(dst + 1, eB);
-              }
-            }
-            continue;
-          }
-          if (MODE == MODE_PROJECT) {
-            const double* src = A.energies + q1.x + (int64_t)d0;
-            if (hasA) eA = ld_stream(src);
-            if (hasB) eB = ld_stream(src + 1);
-          }
-          const double shift = __longlong_as_double(q0.y);
-          eA *= shift;
-          eB *= shift;
-          bool detA = hasA && elig, detB = hasB && elig;
-          if (absorb) {
-            const Philox4 Aw = pxb_rand4(RKP, STREAM_PROJ_A, gid, (uint64_t)m);
-            Philox4 Dw{0u, 0u, 0u, 0u};
-            if (SPEC == 0 && P.nH_cell) Dw = pxb_rand4(RKP, STREAM_PROJ_D, gid, (uint64_t)m);
-            if (detA) detA = absorb_decision<SPEC>(P, RKP, s_wabs, c0 + rel, gid, d0, Aw.x, Dw.x, eA);
-            if (detB) detB = absorb_decision<SPEC>(P, RKP, s_wabs, c0 + rel, gid, d0 + 1, Aw.y, Dw.y, eB);
-          }
-          s_e[2 * srel] = eA;
-          s_e[2 * srel + 1] = eB;
-          if (detA) {
-            tsum += eA;
-            tmin = eA < tmin ? eA : tmin;   // (energies are never NaN: plain compares)
-            tmax = eA > tmax ? eA : tmax;
-          }
-          if (detB) {
-            tsum += eB;
-            tmin = eB < tmin ? eB : tmin;
-            tmax = eB > tmax ? eB : tmax;
-          }
-          run += __popc(__ballot_sync(0xffffffffu, detA)) + __popc(__ballot_sync(0xffffffffu, detB));
-          detpack |= ((detA ? 1u : 0u) | (detB ? 2u : 0u)) << (2 * r);
-        }
-        if (MODE != MODE_SAMPLE) {
-          tsum = warp_sum(tsum);
-          tmin = warp_min(tmin);
-          tmax = warp_max(tmax);
-          if (lane == 0) {
-            A.part_sum[tile] = tsum;
-            A.part_min[tile] = tmin;
-            A.part_max[tile] = tmax;
-          }
-          new_bits = detpack | (relpack << 8);
-        }
+        if (!staging) break;
+        continue;
       }
+      int run = 0, how = 0;
+      unsigned bits = 0;
+      decide(tile, 0, run, how, bits);
     }
-    if (MODE == MODE_SAMPLE) {
-      if (out && !staging) break;
-      continue;
-    }
+    return;
+  }
 
-    // ---- (B) report the new tile's count; a first, non-blocking look at its predecessors ------
-    const LookBack LB{A.status, A.bstatus};
-    if (have_new) {
-      if (lane == 0) lookback_report(LB, A.bcount, tile, A.n_tiles, run);
-      int64_t nj = -2, nprefix = 0;
-      const bool ndone = lookback_run(LB, tile, nj, nprefix, lane, false);
-      if (ndone) lookback_publish(LB, tile, nprefix, lane);
+  // Projecting modes.  The CTA works on BATCHES of PL_WARPS consecutive tiles (one per warp) that
+  // it draws from the global ticket, in two half-steps per iteration separated by CTA barriers:
+  //   decide(batch k) | scatter(batch k-1)
+  // The survivor count of batch k is published right after its decisions; its exclusive prefix
+  // over all earlier batches is looked up by warp 0 -- first without blocking, and for good one
+  // iteration later, just before the scatter step that needs it -- so the latency of the
+  // look-back hides behind the next batch's decisions, nobody spins on a per-warp basis, and the
+  // barriers keep the warps of an SM in step (the scheduler's fixed warp priorities would
+  // otherwise let some warps starve while everybody waits for their tiles).
+  int buf = 0;
+  bool have_pend = false;      // this warp's tile of the previous batch still has its scatter step due
+  unsigned pend_bits = 0;
+  int pend_how = 0;
+  bool lbdone = true, cta_out = false, pend_batch = false;
+  for (int it = 0;; ++it) {
+    if (threadIdx.x == 0) s_batch[buf] = cta_out ? -1ll : (long long)atomicAdd(A.ticket, 1u);
+    __syncthreads();     // (1) the batch is known; every warp is done with the previous iteration
+    const int64_t batch = s_batch[buf];
+    if (batch < 0 || batch * PL_WARPS >= A.n_tiles) cta_out = true;
+    if (staging && !cta_out && (it & (PL_EPOCH - 1)) == 0) restage(batch * PL_WARPS);
+    const int64_t tile = batch * PL_WARPS + wid;
+    const bool have_new = !cta_out && tile < A.n_tiles;
+    int run = 0, how = 0;
+    unsigned bits = 0;
+    if (have_new) decide(tile, buf, run, how, bits);
+    if (lane == 0) s_cnt[buf][wid] = run;
+    if (wid == 0 && pend_batch && !lbdone) {
+      // the pending batch's prefix, for good now: it has had a whole batch's time
+      int64_t lbj = s_lbj, lbprefix = s_lbprefix;
+      lookback_run(A.bstatus, lbj, lbprefix, lane, true);
       if (lane == 0) {
-        s_pend[wid][buf][0] = tile;
-        s_pend[wid][buf][1] = nprefix;
-        s_pend[wid][buf][2] = nj;
-        s_pend[wid][buf][3] = (long long)(run | (how << 16) | ((ndone ? 1 : 0) << 20));
+        int tot = 0;
+        for (int w = 0; w < PL_WARPS; ++w) tot += s_cnt[buf ^ 1][w];
+        st_status(A.bstatus + s_batch[buf ^ 1], ST_INC | (unsigned long long)(lbprefix + tot));
+        s_base[buf ^ 1] = lbprefix;
       }
+      lbdone = true;
     }
-
-    // ---- (C) finish the pending tile: its prefix (blocking now: it has had a whole tile's time),
-    //          then scatter its survivors into their final, order-preserving slots ---------------
-    if (have_pend) {
-      __syncwarp();
-      const int64_t ptile = s_pend[wid][buf ^ 1][0];
-      int64_t base = s_pend[wid][buf ^ 1][1];
-      int64_t pj = s_pend[wid][buf ^ 1][2];
-      const int info = (int)s_pend[wid][buf ^ 1][3];
-      const int prun = info & 0xffff, phow = (info >> 16) & 3;
-      if (!((info >> 20) & 1)) {
-        lookback_run(LB, ptile, pj, base, lane, true);
-        lookback_publish(LB, ptile, base, lane);
-      }
-      if (ptile == A.n_tiles - 1 && lane == 0) *A.n_events = base + prun;
-      if (prun > 0) {
-        const double* const s_e = reinterpret_cast<const double*>(dyn + se_off + (unsigned)(buf ^ 1) * (unsigned)(2 * TSLOTS * sizeof(double)));
-        const int* const s_qs = reinterpret_cast<const int*>(dyn + qs_off + (unsigned)(buf ^ 1) * (unsigned)(MAXC * sizeof(int)));
-        const int64_t slot0 = ptile * TSLOTS;
-        const int nslots = (int)min((int64_t)TSLOTS, A.n_pairs - slot0);
-        const int64_t c0 = __ldg(A.tile_cell + ptile);
-        const int64_t c1 = (ptile + 1 < A.n_tiles) ? __ldg(A.tile_cell + ptile + 1) : A.n_cells - 1;
-        const int64_t m00 = slot0 - __ldg(A.qoff + c0);
-        const unsigned detpack = pend_bits & 255u, relpack = pend_bits >> 8;
-        // (tile-uniform 64-bit bases, 32-bit offsets inside the tile; float events: half the bytes)
-        const int64_t ob = A.f32 ? base / 2 : base;         // (float arrays: base counts 4-byte slots)
-        double* const xb = A.xsky + ob;
-        double* const yb = A.ysky + ob;
-        double* const eb = A.eobs + ob;
-        double* const lb = A.los ? A.los + ob : nullptr;
-        const int fo = (int)(base & 1);
-        int done = 0;
-#pragma unroll 1
-        for (int r = 0; r < ROUNDS; ++r) {
-          if (r * 32 >= nslots) break;
-          const bool detA = (detpack >> (2 * r)) & 1u, detB = (detpack >> (2 * r + 1)) & 1u;
-          const unsigned balA = __ballot_sync(0xffffffffu, detA), balB = __ballot_sync(0xffffffffu, detB);
-          if (!(balA | balB)) continue;
-          const int o0 = done + __popc(balA & lt) + __popc(balB & lt);
-          done += __popc(balA) + __popc(balB);
-          if (!(detA || detB)) continue;
-          const int srel = r * 32 + lane;
-          int rel;
-          int64_t m;
-          locate(phow, relpack, s_qs, slot0, nslots, c0, c1, m00, r, srel, rel, m);
-          const uint64_t gid = (uint64_t)__ldg(&A.recs[c0 + rel].gid);
-          const uint64_t d0 = 2ull * (uint64_t)m;
-          const CellGeom g = ld_geom(A.geom + c0 + rel);
-          const Philox4 Bw = pxb_rand4(RKP, STREAM_PROJ_B, gid, (uint64_t)m);
-          // the third scatter word lives in the absorption block: recomputed only where it is
-          // used (off-axis cells, particle kernels, all-sky)
-          Philox4 Aw{0u, 0u, 0u, 0u};
-          if (SPEC == 2 || (SPEC == 0 && !(P.observer == 0 && P.data_type == 0 && P.vn_axis >= 0)))
-            Aw = pxb_rand4(RKP, STREAM_PROJ_A, gid, (uint64_t)m);
-#pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            if (!(h ? detB : detA)) continue;
-            double xs, ys, los;
-            const uint32_t w0 = h ? Bw.z : Bw.x, w1 = h ? Bw.w : Bw.y, w2 = h ? Aw.w : Aw.z;
-            if (SPEC != 0 || P.observer == 0)
-              scatter_external<SPEC>(P, RKP, g, K, w0, w1, w2, gid, d0 + h, xs, ys, los);
-            else
-              scatter_allsky(P, RKP, g, w0, w1, w2, gid, d0 + h, xs, ys, los);
-            const int o = o0 + (h && detA ? 1 : 0);
-            if (!A.f32) {
-              st_stream(xb + o, xs);
-              st_stream(yb + o, ys);
-              st_stream(eb + o, s_e[2 * srel + h]);
-              if (lb) st_stream(lb + o, los);
-            } else {
-              // sky offsets from the fp64 centre and energies in single precision
-              __stcs(reinterpret_cast<float*>(xb) + fo + o, (float)(xs - A.sky0));
-              __stcs(reinterpret_cast<float*>(yb) + fo + o, (float)(ys - A.sky1));
-              __stcs(reinterpret_cast<float*>(eb) + fo + o, (float)s_e[2 * srel + h]);
-              if (lb) __stcs(reinterpret_cast<float*>(lb) + fo + o, (float)los);
-            }
-          }
+    __syncthreads();     // (2) the new batch's counts and the pending batch's prefix are in place
+    if (wid == 0 && !cta_out) {
+      // publish the new batch's count; a first, non-blocking look at its predecessors
+      const int cw = s_cnt[buf][lane];
+      const int tot = __reduce_add_sync(0xffffffffu, cw);
+      if (lane == 0) st_status(A.bstatus + batch, (batch == 0 ? ST_INC : ST_AGG) | (unsigned long long)tot);
+      int64_t lbj = batch - 1, lbprefix = 0;
+      lbdone = lookback_run(A.bstatus, lbj, lbprefix, lane, false);
+      if (lane == 0) {
+        if (lbdone) {
+          if (batch > 0) st_status(A.bstatus + batch, ST_INC | (unsigned long long)(lbprefix + tot));
+          s_base[buf] = lbprefix;
+        } else {
+          s_lbj = lbj;
+          s_lbprefix = lbprefix;
         }
       }
-      have_pend = false;
     }
-
-    // ---- (D) the new tile becomes the pending one ------------------------------------------------
-    if (have_new) {
-      __syncwarp();
-      pend_bits = new_bits;
-      have_pend = true;
-      buf ^= 1;
-    } else if (!staging) {
-      break;             // no tile left to draw and nothing pending
+    if (have_pend) {
+      int before = 0, mine = 0;
+      {
+        const int cw = s_cnt[buf ^ 1][lane];
+        before = __reduce_add_sync(0xffffffffu, lane < wid ? cw : 0);
+        mine = __shfl_sync(0xffffffffu, cw, wid);
+      }
+      const int64_t ptile = s_batch[buf ^ 1] * PL_WARPS + wid;
+      const int64_t base = s_base[buf ^ 1] + before;
+      if (ptile == A.n_tiles - 1 && lane == 0) *A.n_events = base + mine;
+      if (mine > 0) scatter(ptile, buf ^ 1, base, pend_how, pend_bits);
     }
+    if (cta_out) break;          // nothing new was decided: the batch just scattered was the last
+    have_pend = have_new;
+    pend_batch = true;
+    pend_bits = bits;
+    pend_how = how;
+    buf ^= 1;
   }
 }
 
@@ -972,7 +937,7 @@ static int split_stride(const DevModel& D) {
 struct PipeLayout {
   int64_t ntiles;
   int tslots;          // pair slots per tile of the mode (Tiling<MODE>::TSLOTS)
-  int64_t off_hdr, off_recs, off_geom, off_tilecell, off_status, off_bstatus, off_bcount, off_part, off_red;
+  int64_t off_hdr, off_recs, off_geom, off_tilecell, off_bstatus, off_part, off_red;
   int64_t off_list, off_tabcum, off_glist, total;
 };
 
@@ -984,9 +949,7 @@ static PipeLayout pipe_layout(const DevModel* D, int64_t n_cells, int64_t n_pair
   int64_t o = 0;
   l.off_hdr = o;      o += 256;                                  // counters + ticket
   const int64_t nbatch = (l.ntiles + PL_BATCH - 1) / PL_BATCH;
-  l.off_status = o;   o += project ? align256(l.ntiles * 8) : 0; // (header + look-back words: one memset)
-  l.off_bstatus = o;  o += project ? align256(nbatch * 8) : 0;
-  l.off_bcount = o;   o += project ? align256(nbatch * 8) : 0;
+  l.off_bstatus = o;  o += project ? align256(nbatch * 8) : 0;   // (header + look-back words: one memset)
   l.off_recs = o;     o += align256(n_cells * (int64_t)sizeof(CellRec));
   l.off_geom = o;     o += project ? align256(n_cells * (int64_t)sizeof(CellGeom)) : 0;
   l.off_tilecell = o; o += align256((l.ntiles + 1) * 8);
@@ -1242,9 +1205,7 @@ static void fill_project_args(PipeArgs& A, char* ws, const PipeLayout& lay, cons
   const bool about_centre = P->observer == 0 && P->sky_mode != PXB_SKY_PHYS;
   A.sky0 = about_centre ? P->sky_center[0] : 0.0;
   A.sky1 = about_centre ? P->sky_center[1] : 0.0;
-  A.status = (unsigned long long*)(ws + lay.off_status);
   A.bstatus = (unsigned long long*)(ws + lay.off_bstatus);
-  A.bcount = (unsigned long long*)(ws + lay.off_bcount);
   A.part_sum = (double*)(ws + lay.off_part);
   A.part_min = A.part_sum + lay.ntiles;
   A.part_max = A.part_min + lay.ntiles;

@@ -515,3 +515,115 @@ def test_line_counts_and_energies(cuda, oracle):
         assert abs(e.size - F.sum()) < 1.645 * 4 * np.sqrt(F.sum())
         assert _ks_ok(e, oe)
         assert abs(e.mean() - 3.5 / 1.2) < 5 * e.std() / np.sqrt(e.size)
+
+
+# ---------------------------------------------------------------------------------------
+# decisions from random words; float32 events
+# ---------------------------------------------------------------------------------------
+def _philox4x32_10(c0, c1, c2, c3, k0, k1):
+    """Philox4x32-10 (Salmon et al. 2011) on uint64-held 32-bit lanes; returns the four words."""
+    M0, M1, W0, W1, MASK = 0xD2511F53, 0xCD9E8D57, 0x9E3779B9, 0xBB67AE85, 0xFFFFFFFF
+    c0, c1, c2, c3 = (np.asarray(v, dtype=np.uint64) & np.uint64(MASK) for v in (c0, c1, c2, c3))
+    k0, k1 = int(k0) & MASK, int(k1) & MASK
+    for _ in range(10):
+        p0 = c0 * np.uint64(M0)
+        p1 = c2 * np.uint64(M1)
+        hi0, lo0 = p0 >> np.uint64(32), p0 & np.uint64(MASK)
+        hi1, lo1 = p1 >> np.uint64(32), p1 & np.uint64(MASK)
+        c0, c1, c2, c3 = hi1 ^ c1 ^ np.uint64(k0), lo1, hi0 ^ c3 ^ np.uint64(k1), lo0
+        k0, k1 = (k0 + W0) & MASK, (k1 + W1) & MASK
+    return c0, c1, c2, c3
+
+
+def test_philox_known_answer():
+    """Random123's published known-answer vectors for Philox4x32-10."""
+    out = _philox4x32_10(0, 0, 0, 0, 0, 0)
+    assert [int(v) for v in out] == [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]
+    out = _philox4x32_10(0xffffffff, 0xffffffff, 0xffffffff, 0xffffffff, 0xffffffff, 0xffffffff)
+    assert [int(v) for v in out] == [0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd]
+    out = _philox4x32_10(0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344, 0xa4093822, 0x299f31d0)
+    assert [int(v) for v in out] == [0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1]
+
+
+@pytest.mark.parametrize("kind", ["wabs", "table"])
+def test_absorb_decision_from_random_words(cuda, oracle, kind):
+    """The photon kernels decide absorption from the TOP 32-bit word of a 64-bit uniform and draw
+    the low word (refinement stream, Philox counter (draw, cell, stream 10)) only when the top
+    word alone does not decide.  Against U = (w + w2 / 2^32) / 2^32 < exp(-sigma nH) evaluated on
+    the host with the same Philox words: top words chosen ON the threshold (so the low word
+    decides), one either side of it, and at random."""
+    from pyxsim_b200 import _lib
+    from pyxsim_b200.device import ptr, stream_ptr, to_device
+    import ctypes as C
+
+    rng = np.random.RandomState(11)
+    n = 60000
+    e = np.exp(rng.uniform(np.log(0.05), np.log(12.0), n))
+    seed, gid, d0 = 0x1234567890ABCDEF, 987654321012, 5_000_000_000
+    for nH in (0.02, 1.0, 20.0):
+        if kind == "wabs":
+            prod, orc = px.WabsModel(nH), oracle.WabsAbsorb(nH)
+        else:
+            en, sg = synthetic.tbabs_like_sigma(n=3000)
+            prod, orc = px.TBabsModel(nH, energy=en, cross_section=sg), oracle.TableAbsorb(nH, en, sg * 1.0e22)
+        p = orc.get_absorb(e)
+        d = d0 + np.arange(n, dtype=np.uint64)
+        c3 = ((np.uint64(gid) >> np.uint64(32)) << np.uint64(16)) | np.uint64(10)
+        w2 = _philox4x32_10(d & np.uint64(0xFFFFFFFF), d >> np.uint64(32), np.uint64(gid) & np.uint64(0xFFFFFFFF),
+                            c3, seed & 0xFFFFFFFF, seed >> 32)[0].astype(np.float64)
+        on = np.clip(np.floor(p * 4294967296.0), 0, 4294967295)
+        for w in (on, np.clip(on - 1, 0, None), np.clip(on + 1, None, 4294967295),
+                  rng.randint(0, 2 ** 32, n, dtype=np.uint64).astype(np.float64)):
+            U = (w + w2 / 4294967296.0) / 4294967296.0
+            want = U < p
+            sure = np.abs(U - p) > 4e-16 * np.maximum(p, 1e-300) + 1e-300      # (the host's p is fp64 too)
+            P = _lib.ProjectParams()
+            keep = prod._fill_params(P)
+            P.nH = nH
+            P.seed = seed
+            de = to_device(e)
+            dw = torch.from_numpy(w.astype(np.uint32).view(np.int32)).cuda()
+            out = torch.empty(n, dtype=torch.uint8, device="cuda")
+            _lib.call("pxb_absorb_decide_words", C.byref(P), n, ptr(de), ptr(dw), C.c_uint64(gid), C.c_uint64(d0),
+                      ptr(out), stream_ptr())
+            got = out.cpu().numpy().astype(bool)
+            del keep
+            assert np.array_equal(got[sure], want[sure]), (kind, nH)
+        # on the threshold both outcomes occur: the low word really decides
+        U = (on + w2 / 4294967296.0) / 4294967296.0
+        mid = (p > 1e-6) & (p < 1 - 1e-6)
+        assert 0.2 < (U < p)[mid].mean() < 0.8
+
+
+def test_float32_events(cuda):
+    """event_dtype="float32": the same survivors in the same order, energies rounded to single
+    precision, sky positions as single-precision offsets from the fp64 centre (so they keep
+    ~1e-7 deg at any RA); flux / emin / emax stay fp64; EventList gives absolute positions back."""
+    d, p = make_plist(n_cells=4000, mean_ph=40.0)
+    put("f32_ph", d, p)
+    center = [310.0, -67.5]
+    kw = dict(absorb_model="wabs", nH=0.05, save_los=True, prng=5)
+    n64 = px.project_photons("mem:f32_ph", "mem:f32_ev64", [0.3, 0.2, 0.9], center, **kw)
+    n32 = px.project_photons("mem:f32_ph", "mem:f32_ev32", [0.3, 0.2, 0.9], center, event_dtype="float32", **kw)
+    a, b = px.load_list("mem:f32_ev64"), px.load_list("mem:f32_ev32")
+    assert n64 == n32 > 1000 and b.data["eobs"].dtype == torch.float32
+    assert b.parameters["event_dtype"] == "float32" and b.parameters["sky_offsets"] == 1
+    assert np.array_equal(b.numpy("eobs"), a.numpy("eobs").astype(np.float32))
+    assert np.array_equal(b.numpy("los"), a.numpy("los").astype(np.float32))
+    assert np.array_equal(b.numpy("xsky"), (a.numpy("xsky") - center[0]).astype(np.float32))
+    assert np.array_equal(b.numpy("ysky"), (a.numpy("ysky") - center[1]).astype(np.float32))
+    for k in ("flux", "emin", "emax"):
+        assert a.parameters[k] == b.parameters[k]
+    ev = px.EventList("mem:f32_ev32")
+    np.testing.assert_allclose(ev["xsky"], a.numpy("xsky"), rtol=0, atol=1e-7)
+    np.testing.assert_allclose(ev["ysky"], a.numpy("ysky"), rtol=0, atol=1e-7)
+    np.testing.assert_allclose(ev["eobs"], a.numpy("eobs"), rtol=1e-7)
+    img64 = px.EventList("mem:f32_ev64").image(20.0, 128).cpu().numpy()
+    img32 = ev.image(20.0, 128).cpu().numpy()
+    assert img64.sum() == img32.sum() and np.abs(img64 - img32).sum() <= 1e-4 * img64.sum()
+    # physical coordinates have no centre to be relative to
+    px.project_photons("mem:f32_ph", "mem:f32_evp", "x", center, phys_coord=True, event_dtype="float32", prng=5)
+    c = px.load_list("mem:f32_evp")
+    assert c.parameters["sky_offsets"] == 0
+    px.project_photons("mem:f32_ph", "mem:f32_evp64", "x", center, phys_coord=True, prng=5)
+    assert np.array_equal(c.numpy("xsky"), px.load_list("mem:f32_evp64").numpy("xsky").astype(np.float32))
