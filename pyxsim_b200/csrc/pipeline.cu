@@ -29,10 +29,9 @@
 
 enum { MODE_SAMPLE = 0, MODE_PROJECT = 1, MODE_FUSED = 2 };
 
-constexpr int PL_THREADS = 1024;
-constexpr int PL_WARPS = PL_THREADS / 32;
+constexpr int PL_WARPS = 32;                       // warps of a persistent CTA holding staged rows
+constexpr int PL_WARPS_SMALL = 8;                  // warps of a CTA that stages nothing (4 CTAs per SM)
 constexpr int PL_EPOCH = 16;                       // tiles per warp between two staging decisions
-constexpr int PL_BATCH = PL_WARPS;                 // tiles a CTA works on together (one per warp)
 
 // Tile geometry per mode.  A warp tile is ROUNDS x 32 pair slots.  The sampler keeps nothing
 // between rounds and takes 128-slot tiles; the modes that project keep a tile's energies in
@@ -77,7 +76,7 @@ struct PipeArgs {
   double* eobs;
   double* los;
   int64_t* n_events;
-  unsigned long long* bstatus;   // [n_batches] look-back words (a batch = PL_WARPS tiles)
+  unsigned long long* bstatus;   // [n_batches] look-back words (a batch = the tiles of one CTA step)
   double* part_sum;           // [n_tiles] per-tile partial statistics
   double* part_min;
   double* part_max;
@@ -142,8 +141,8 @@ __device__ __forceinline__ void st_status(unsigned long long* p, unsigned long l
   asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v));
 }
 
-// Exclusive prefix of the survivor counts of all earlier BATCHES (a batch = the PL_WARPS tiles a
-// CTA works on together) -- decoupled look-back over one status word per batch: the CTA publishes
+// Exclusive prefix of the survivor counts of all earlier BATCHES (a batch = the tiles a CTA works
+// on together, one per warp) -- decoupled look-back over one status word per batch: the CTA publishes
 // its batch's count (ST_AGG) as soon as the absorption decisions of the batch are made, walks
 // back over the earlier batches' words, adding counts until it meets an inclusive prefix, and
 // publishes its own inclusive prefix (ST_INC).  One warp per CTA does this; with one batch per SM
@@ -418,8 +417,10 @@ k_thermal_sample_cta(const DevModel M, const __grid_constant__ pxb_thermal_cells
 // four-component split mode), inverse-CDF sampling, uniformly spaced linear bins; projection:
 // wabs with a foreground column only, cells, TAN sky, no sigma_pos, on-axis (1) / off-axis (2)
 // normal.  Same results as SPEC = 0, fewer instructions and registers.
-template <int MODE, int SPEC>
-__global__ void __launch_bounds__(PL_THREADS, 1)
+// WARPS: warps per CTA -- 32 (one persistent CTA per SM, room for the staged rows) or 8 (four CTAs
+// per SM, nothing staged: while one CTA sits at a barrier the others issue).
+template <int MODE, int SPEC, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, WARPS == PL_WARPS ? 1 : 4)
 k_pipeline(const DevModel M, const __grid_constant__ pxb_thermal_cells C,
            const __grid_constant__ pxb_project_params P, const __grid_constant__ PhiloxKeys RKE,
            const __grid_constant__ PhiloxKeys RKP, const __grid_constant__ PipeArgs A,
@@ -434,7 +435,7 @@ k_pipeline(const DevModel M, const __grid_constant__ pxb_thermal_cells C,
   __shared__ int s_want;
   __shared__ long long s_batch[2];                     // batch per buffer (-1: none)
   __shared__ long long s_base[2];                      // its exclusive prefix, once known
-  __shared__ int s_cnt[2][PL_WARPS];                   // survivors of its tiles
+  __shared__ int s_cnt[2][WARPS];                      // survivors of its tiles
   __shared__ long long s_lbj, s_lbprefix;              // warp 0: look-back progress of the pending batch
   __shared__ WabsFast s_wabs;
 
@@ -782,7 +783,7 @@ k_pipeline(const DevModel M, const __grid_constant__ pxb_thermal_cells C,
     // Sampling keeps nothing between tiles: every WARP draws its tiles one at a time from the
     // global ticket; the warps of a CTA only meet at the staging epochs.
     __shared__ int s_live;
-    if (threadIdx.x == 0) s_live = PL_WARPS;
+    if (threadIdx.x == 0) s_live = WARPS;
     __syncthreads();
     bool out = false;
     for (int it = 0;; ++it) {
@@ -811,7 +812,7 @@ k_pipeline(const DevModel M, const __grid_constant__ pxb_thermal_cells C,
     return;
   }
 
-  // Projecting modes.  The CTA works on BATCHES of PL_WARPS consecutive tiles (one per warp) that
+  // Projecting modes.  The CTA works on BATCHES of WARPS consecutive tiles (one per warp) that
   // it draws from the global ticket, in two half-steps per iteration separated by CTA barriers:
   //   decide(batch k) | scatter(batch k-1)
   // The survivor count of batch k is published right after its decisions; its exclusive prefix
@@ -829,9 +830,9 @@ k_pipeline(const DevModel M, const __grid_constant__ pxb_thermal_cells C,
     if (threadIdx.x == 0) s_batch[buf] = cta_out ? -1ll : (long long)atomicAdd(A.ticket, 1u);
     __syncthreads();     // (1) the batch is known; every warp is done with the previous iteration
     const int64_t batch = s_batch[buf];
-    if (batch < 0 || batch * PL_WARPS >= A.n_tiles) cta_out = true;
-    if (staging && !cta_out && (it & (PL_EPOCH - 1)) == 0) restage(batch * PL_WARPS);
-    const int64_t tile = batch * PL_WARPS + wid;
+    if (batch < 0 || batch * WARPS >= A.n_tiles) cta_out = true;
+    if (staging && !cta_out && (it & (PL_EPOCH - 1)) == 0) restage(batch * WARPS);
+    const int64_t tile = batch * WARPS + wid;
     const bool have_new = !cta_out && tile < A.n_tiles;
     int run = 0, how = 0;
     unsigned bits = 0;
@@ -843,7 +844,7 @@ k_pipeline(const DevModel M, const __grid_constant__ pxb_thermal_cells C,
       lookback_run(A.bstatus, lbj, lbprefix, lane, true);
       if (lane == 0) {
         int tot = 0;
-        for (int w = 0; w < PL_WARPS; ++w) tot += s_cnt[buf ^ 1][w];
+        for (int w = 0; w < WARPS; ++w) tot += s_cnt[buf ^ 1][w];
         st_status(A.bstatus + s_batch[buf ^ 1], ST_INC | (unsigned long long)(lbprefix + tot));
         s_base[buf ^ 1] = lbprefix;
       }
@@ -852,7 +853,7 @@ k_pipeline(const DevModel M, const __grid_constant__ pxb_thermal_cells C,
     __syncthreads();     // (2) the new batch's counts and the pending batch's prefix are in place
     if (wid == 0 && !cta_out) {
       // publish the new batch's count; a first, non-blocking look at its predecessors
-      const int cw = s_cnt[buf][lane];
+      const int cw = lane < WARPS ? s_cnt[buf][lane] : 0;
       const int tot = __reduce_add_sync(0xffffffffu, cw);
       if (lane == 0) st_status(A.bstatus + batch, (batch == 0 ? ST_INC : ST_AGG) | (unsigned long long)tot);
       int64_t lbj = batch - 1, lbprefix = 0;
@@ -870,11 +871,11 @@ k_pipeline(const DevModel M, const __grid_constant__ pxb_thermal_cells C,
     if (have_pend) {
       int before = 0, mine = 0;
       {
-        const int cw = s_cnt[buf ^ 1][lane];
+        const int cw = lane < WARPS ? s_cnt[buf ^ 1][lane] : 0;
         before = __reduce_add_sync(0xffffffffu, lane < wid ? cw : 0);
         mine = __shfl_sync(0xffffffffu, cw, wid);
       }
-      const int64_t ptile = s_batch[buf ^ 1] * PL_WARPS + wid;
+      const int64_t ptile = s_batch[buf ^ 1] * WARPS + wid;
       const int64_t base = s_base[buf ^ 1] + before;
       if (ptile == A.n_tiles - 1 && lane == 0) *A.n_events = base + mine;
       if (mine > 0) scatter(ptile, buf ^ 1, base, pend_how, pend_bits);
@@ -948,7 +949,7 @@ static PipeLayout pipe_layout(const DevModel* D, int64_t n_cells, int64_t n_pair
   l.ntiles = (n_pairs + l.tslots - 1) / l.tslots;
   int64_t o = 0;
   l.off_hdr = o;      o += 256;                                  // counters + ticket
-  const int64_t nbatch = (l.ntiles + PL_BATCH - 1) / PL_BATCH;
+  const int64_t nbatch = (l.ntiles + PL_WARPS_SMALL - 1) / PL_WARPS_SMALL;   // (enough for either CTA size)
   l.off_bstatus = o;  o += project ? align256(nbatch * 8) : 0;   // (header + look-back words: one memset)
   l.off_recs = o;     o += align256(n_cells * (int64_t)sizeof(CellRec));
   l.off_geom = o;     o += project ? align256(n_cells * (int64_t)sizeof(CellGeom)) : 0;
@@ -976,18 +977,22 @@ static PipeHeader pipe_header(char* ws, const PipeLayout& l) {
 
 // shared-memory plan of a k_pipeline launch
 struct SmemPlan {
-  int use_staging, off_e, off_qs;
+  int use_staging, off_e, off_qs, warps;
   size_t total;
 };
-static SmemPlan smem_plan(const DevModel* D, int mode) {
+// mode project stages nothing and runs small CTAs; sampling and the fused mode run one big CTA per
+// SM with the four alias rows of the temperature bin staged when they fit (small_fused: the fused
+// mode with small CTAs and the rows left to L1/L2 instead)
+static SmemPlan smem_plan(const DevModel* D, int mode, bool small_fused = false) {
   SmemPlan s;
+  s.warps = (mode == MODE_PROJECT || (mode == MODE_FUSED && small_fused)) ? PL_WARPS_SMALL : PL_WARPS;
   const size_t e_bytes = mode == MODE_SAMPLE ? 0
-                         : (size_t)PL_WARPS * Tiling<1>::NBUF * 2 * Tiling<1>::TSLOTS * sizeof(double);
-  const size_t qs_bytes = mode == MODE_SAMPLE ? (size_t)PL_WARPS * Tiling<0>::MAXC * sizeof(int)
-                                              : (size_t)PL_WARPS * Tiling<1>::NBUF * Tiling<1>::MAXC * sizeof(int);
+                         : (size_t)s.warps * Tiling<1>::NBUF * 2 * Tiling<1>::TSLOTS * sizeof(double);
+  const size_t qs_bytes = mode == MODE_SAMPLE ? (size_t)s.warps * Tiling<0>::MAXC * sizeof(int)
+                                              : (size_t)s.warps * Tiling<1>::NBUF * Tiling<1>::MAXC * sizeof(int);
   size_t rows = 0;
   s.use_staging = 0;
-  if (mode != MODE_PROJECT && D && !D->density_dependent && !D->has_fb) {
+  if (s.warps == PL_WARPS && mode != MODE_PROJECT && D && !D->density_dependent && !D->has_fb) {
     rows = 4 * (size_t)D->prim.alias_stride * sizeof(uint2);
     // rows are staged when the four of them fit beside the per-warp scratch
     if (rows + e_bytes + qs_bytes + 2048 <= 227 * 1024) s.use_staging = 1;
@@ -1010,31 +1015,39 @@ extern "C" int pxb_last_pipeline_launch(int* mode, int* spec, int* staged) {
   return g_last_mode < 0 ? PXB_ERR_INVALID : PXB_OK;
 }
 
-template <int MODE, int SPEC>
-static int launch_pipeline(const DevModel& D, const pxb_thermal_cells& C, const pxb_project_params& P,
-                           PipeArgs A, const SmemPlan& sp, cudaStream_t st) {
+template <int MODE, int SPEC, int WARPS>
+static int launch_pipeline_w(const DevModel& D, const pxb_thermal_cells& C, const pxb_project_params& P,
+                             PipeArgs A, const SmemPlan& sp, cudaStream_t st) {
   static thread_local size_t attr_set = 0;
   if (attr_set != sp.total + 1) {   // once per (process, shared-memory size), not per call
-    PXB_CUDA(cudaFuncSetAttribute(k_pipeline<MODE, SPEC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    PXB_CUDA(cudaFuncSetAttribute(k_pipeline<MODE, SPEC, WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)sp.total));
     attr_set = sp.total + 1;
   }
-  int64_t grid = pxb_sm_count();                       // persistent: one CTA per SM
-  const int64_t enough = (A.n_tiles + PL_WARPS - 1) / PL_WARPS;
+  // persistent CTAs: one per SM (big CTAs) or four per SM (small ones)
+  int64_t grid = (int64_t)pxb_sm_count() * (WARPS == PL_WARPS ? 1 : 4);
+  const int64_t enough = (A.n_tiles + WARPS - 1) / WARPS;
   if (grid > enough) grid = enough;
   const SkyConst K = make_sky_const(&P);
   g_last_mode = MODE;
   g_last_spec = SPEC;
   g_last_staged = MODE != MODE_PROJECT && A.use_staging;
-  k_pipeline<MODE, SPEC><<<(unsigned)grid, PL_THREADS, sp.total, st>>>(
+  k_pipeline<MODE, SPEC, WARPS><<<(unsigned)grid, WARPS * 32, sp.total, st>>>(
       D, C, P, pxb_make_keys(C.seed), pxb_make_keys(P.seed), A, K);
   PXB_LAUNCH_CHECK();
   return PXB_OK;
 }
+template <int MODE, int SPEC>
+static int launch_pipeline(const DevModel& D, const pxb_thermal_cells& C, const pxb_project_params& P,
+                           PipeArgs A, const SmemPlan& sp, cudaStream_t st) {
+  if (MODE != MODE_SAMPLE && sp.warps == PL_WARPS_SMALL)
+    return launch_pipeline_w<MODE, SPEC, (MODE == MODE_SAMPLE ? PL_WARPS : PL_WARPS_SMALL)>(D, C, P, A, sp, st);
+  return launch_pipeline_w<MODE, SPEC, PL_WARPS>(D, C, P, A, sp, st);
+}
 
 static bool sample_is_common(const DevModel& D, const pxb_thermal_cells* cells) {
   return D.method == 0 && !D.binscale_log && D.edges_uniform && D.nvar == 0 &&
-         !D.density_dependent && !D.has_fb && !cells->generic_kernels;
+         !D.density_dependent && !D.has_fb && !(cells->generic_kernels & 1);
 }
 // 0: generic; 1: common on-axis; 2: common off-axis
 static int project_spec(const pxb_project_params* P) {
@@ -1308,7 +1321,8 @@ extern "C" int pxb_make_events(const pxb_model* model, const pxb_thermal_cells* 
       *L, *P, (CellRec*)(ws + lay.off_recs), (CellGeom*)(ws + lay.off_geom),
       (int64_t*)(ws + lay.off_tilecell), lay.tslots);
   PXB_LAUNCH_CHECK();
-  const SmemPlan sp = smem_plan(&D, MODE_FUSED);
+  // (cells->generic_kernels bit 1: diagnostic -- small CTAs with unstaged rows for the fused mode)
+  const SmemPlan sp = smem_plan(&D, MODE_FUSED, (cells->generic_kernels & 2) != 0);
   PipeArgs A{};
   fill_project_args(A, ws, lay, H, L, P, xsky, ysky, eobs, los, n_events_out);
   A.idx = idx;
