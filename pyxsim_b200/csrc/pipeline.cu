@@ -420,7 +420,7 @@ k_thermal_sample_cta(const DevModel M, const __grid_constant__ pxb_thermal_cells
 // WARPS: warps per CTA -- 32 (one persistent CTA per SM, room for the staged rows) or 8 (four CTAs
 // per SM, nothing staged: while one CTA sits at a barrier the others issue).
 template <int MODE, int SPEC, int WARPS>
-__global__ void __launch_bounds__(WARPS * 32, WARPS == PL_WARPS ? 1 : 4)
+__global__ void __launch_bounds__(WARPS * 32, WARPS == PL_WARPS ? 1 : 3)
 k_pipeline(const DevModel M, const __grid_constant__ pxb_thermal_cells C,
            const __grid_constant__ pxb_project_params P, const __grid_constant__ PhiloxKeys RKE,
            const __grid_constant__ PhiloxKeys RKP, const __grid_constant__ PipeArgs A,
@@ -1025,7 +1025,7 @@ static int launch_pipeline_w(const DevModel& D, const pxb_thermal_cells& C, cons
     attr_set = sp.total + 1;
   }
   // persistent CTAs: one per SM (big CTAs) or four per SM (small ones)
-  int64_t grid = (int64_t)pxb_sm_count() * (WARPS == PL_WARPS ? 1 : 4);
+  int64_t grid = (int64_t)pxb_sm_count() * (WARPS == PL_WARPS ? 1 : 3);
   const int64_t enough = (A.n_tiles + WARPS - 1) / WARPS;
   if (grid > enough) grid = enough;
   const SkyConst K = make_sky_const(&P);

@@ -33,7 +33,8 @@ def init_from_env(backend=None):
     if ws <= 1 or is_initialized():
         return
     if backend is None:
-        backend = "nccl" if torch.cuda.is_available() else "gloo"
+        # (PXB_DIST_BACKEND=gloo lets several ranks share one GPU in tests; NCCL wants one each)
+        backend = os.environ.get("PXB_DIST_BACKEND") or ("nccl" if torch.cuda.is_available() else "gloo")
     os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
     dist.init_process_group(backend=backend)
 
@@ -42,6 +43,11 @@ def _device():
     if is_initialized() and dist.get_backend() == "nccl":
         return torch.device("cuda", torch.cuda.current_device())
     return torch.device("cpu")
+
+
+def reduce_device():
+    """Device on which tensors handed to the collectives must live."""
+    return _device()
 
 
 def allreduce_sum(value):
