@@ -253,12 +253,12 @@ def wl_amr(args, px, torch, dist, dev, rank, world):
     W.n_cells_global = ncell
     tables = build_tables(args, nvar=nvar)
     kT_nodes, ebins, cosmic, metal, var = tables
-    names = tuple(f"El{k}" for k in range(nvar))
+    names = ("O", "Ne", "Mg", "Si", "S", "Fe")[:nvar]
     sm = px.ThermalSpectralModel(ebins, kT_nodes, cosmic, metal, var, var_elem_names=names)
-    ve = {nm: ("gas", f"{nm}_fraction") for nm in names}
+    ve = {nm: ("gas", f"El{k}_fraction") for k, nm in enumerate(names)}
     model = px.ThermalSourceModel(sm, 0.1, 10.0, args.nbins, ("gas", "metallicity"), var_elem=ve,
                                   temperature_field=("gas", "kT"), prng=SEED_GEN)
-    units = {("gas", f"{nm}_fraction"): "Zsun" for nm in names}
+    units = {("gas", f"El{k}_fraction"): "Zsun" for k in range(nvar)}
     units[("gas", "metallicity")] = "Zsun"
 
     def make_source(f):
@@ -354,14 +354,14 @@ def wl_plline(args, px, torch, dist, dev, rank, world):
     f[("gas", "pl_luminosity")] = em                                  # keV/s up to the exposure scale
     f[("gas", "pl_alpha")] = 1.2 + 1.3 * synthetic.hash_uniform(idx, 77)
     f[("gas", "line_emission")] = em.clone()
-    f[("gas", "line_sigma")] = 0.01 + 0.04 * synthetic.hash_uniform(idx, 78)
+    f[("gas", "line_sigma")] = 500.0 + 1500.0 * synthetic.hash_uniform(idx, 78)      # km/s
     del idx
     W.fields = f
     W.n_cells_global = ncell
     pl = px.PowerLawSourceModel(1.0, 0.5, 8.0, ("gas", "pl_luminosity"), ("gas", "pl_alpha"), prng=SEED_GEN)
     ln = px.LineSourceModel(6.4, ("gas", "line_emission"), sigma=("gas", "line_sigma"), prng=SEED_GEN + 1)
     units = {("gas", "pl_luminosity"): "keV/s", ("gas", "line_emission"): "photons/s",
-             ("gas", "line_sigma"): "keV"}
+             ("gas", "line_sigma"): "km/s"}
 
     def make_source(ff):
         s = _source(px, ff, world, rank, f"Grid{n}^3")
@@ -389,7 +389,7 @@ def wl_plline(args, px, torch, dist, dev, rank, world):
     W.pfx, W.efx = pfx + "_0", efx + "_0"
     W.extra_lists = [(pfx + "_1", efx + "_1")]
     W.nZ, W.nD, W.h2d_skip = 0, 0, []
-    W.desc = (f"PowerLawSourceModel (alpha field 1.2-2.5) + LineSourceModel (6.4 keV, sigma field) on a {n}^3 grid "
+    W.desc = (f"PowerLawSourceModel (alpha field 1.2-2.5) + LineSourceModel (6.4 keV, velocity-dispersion field 500-2000 km/s) on a {n}^3 grid "
               f"(configs[4]), redshift {z}, off-axis normal, wabs nH={NH}, {tot_target:.3g} expected photons in total")
     W.scaling = "weak"
     return W

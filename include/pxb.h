@@ -160,8 +160,9 @@ typedef struct {
   int64_t id_block, id_stride; /* see cell_id0; 0 => contiguous ids */
   int32_t generic_kernels;     /* diagnostic switches, same results either way.  bit 0: never take
                                   the kernels compiled for the common option set (parity tests);
-                                  bit 1: pxb_make_events with small CTAs (four per SM) and the table
-                                  rows left to L1/L2 instead of one CTA per SM with staged rows */
+                                  bit 1: pxb_make_events with one big CTA per SM and the table rows
+                                  staged in shared memory instead of small CTAs (four per SM) that
+                                  gather the rows through L1/L2 */
   int32_t split_factor;        /* variable-element tables: a cell's photons are split over its
                                   (row, table) components once per cell when it holds at least
                                   split_factor * components photons; 0 => default (6),

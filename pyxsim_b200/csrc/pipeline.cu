@@ -420,7 +420,7 @@ k_thermal_sample_cta(const DevModel M, const __grid_constant__ pxb_thermal_cells
 // WARPS: warps per CTA -- 32 (one persistent CTA per SM, room for the staged rows) or 8 (four CTAs
 // per SM, nothing staged: while one CTA sits at a barrier the others issue).
 template <int MODE, int SPEC, int WARPS>
-__global__ void __launch_bounds__(WARPS * 32, WARPS == PL_WARPS ? 1 : 3)
+__global__ void __launch_bounds__(WARPS * 32, WARPS == PL_WARPS ? 1 : 4)
 k_pipeline(const DevModel M, const __grid_constant__ pxb_thermal_cells C,
            const __grid_constant__ pxb_project_params P, const __grid_constant__ PhiloxKeys RKE,
            const __grid_constant__ PhiloxKeys RKP, const __grid_constant__ PipeArgs A,
@@ -1025,7 +1025,7 @@ static int launch_pipeline_w(const DevModel& D, const pxb_thermal_cells& C, cons
     attr_set = sp.total + 1;
   }
   // persistent CTAs: one per SM (big CTAs) or four per SM (small ones)
-  int64_t grid = (int64_t)pxb_sm_count() * (WARPS == PL_WARPS ? 1 : 3);
+  int64_t grid = (int64_t)pxb_sm_count() * (WARPS == PL_WARPS ? 1 : 4);
   const int64_t enough = (A.n_tiles + WARPS - 1) / WARPS;
   if (grid > enough) grid = enough;
   const SkyConst K = make_sky_const(&P);
@@ -1321,8 +1321,9 @@ extern "C" int pxb_make_events(const pxb_model* model, const pxb_thermal_cells* 
       *L, *P, (CellRec*)(ws + lay.off_recs), (CellGeom*)(ws + lay.off_geom),
       (int64_t*)(ws + lay.off_tilecell), lay.tslots);
   PXB_LAUNCH_CHECK();
-  // (cells->generic_kernels bit 1: diagnostic -- small CTAs with unstaged rows for the fused mode)
-  const SmemPlan sp = smem_plan(&D, MODE_FUSED, (cells->generic_kernels & 2) != 0);
+  // small CTAs with the table rows left to L1/L2 measure faster than one big CTA per SM with
+  // staged rows (23.0 vs 24.6 ms on the bench workload); generic_kernels bit 1 selects the latter
+  const SmemPlan sp = smem_plan(&D, MODE_FUSED, (cells->generic_kernels & 2) == 0);
   PipeArgs A{};
   fill_project_args(A, ws, lay, H, L, P, xsky, ysky, eobs, los, n_events_out);
   A.idx = idx;

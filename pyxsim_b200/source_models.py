@@ -562,9 +562,9 @@ class ThermalSourceModel(SourceModel):
         Cs.kT_min, Cs.kT_max = float(self.kT_min), float(self.kT_max)
         Cs.seed = self._seed
         # diagnostic switches (read once per chunk on the host, never inside the library)
-        # (bit 0: option-generic kernels; bit 1: fused mode with small CTAs and unstaged table rows)
+        # (bit 0: option-generic kernels; bit 1: fused mode with one big CTA per SM and staged rows)
         Cs.generic_kernels = int(bool(os.environ.get("PXB_GENERIC_KERNELS"))) | \
-            (2 if os.environ.get("PXB_FUSED_SMALL_CTA") else 0)
+            (2 if os.environ.get("PXB_FUSED_BIG_CTA") else 0)
         if os.environ.get("PXB_NO_GENERAL_SPLIT"):
             Cs.split_factor = -1
         elif os.environ.get("PXB_SPLIT_FACTOR"):

@@ -64,7 +64,7 @@ def test_bench_configuration_against_the_oracle(cuda, oracle):
         model = px.ThermalSourceModel(sm, 0.1, 10.0, NB, 0.3, temperature_field=TF, prng=seed_mine)
         tot1 = px.make_events("mem:bs_ev1", src, Z, area, texp, model, "z", [30.0, 45.0], absorb_model="wabs",
                               nH=NH, prng=seed_mine + 1)
-        assert _lib.last_pipeline_launch() == (2, 1, 1)       # fused, common option set, staged rows
+        assert _lib.last_pipeline_launch() == (2, 1, 0)       # fused, common option set (small CTAs, rows via L1)
         ev1 = px.load_list("mem:bs_ev1")
         assert tot1 == (n_ph, n_c, n_ev)
         for k in ("xsky", "ysky", "eobs"):

@@ -481,6 +481,13 @@ def test_fused_make_events_equals_the_two_stages(cuda, case, monkeypatch):
         tot3 = px.make_events("mem:common_on_ev3", src, z, area, texp, model(), normal, [30.0, 45.0], **kw)
         assert tot3 == tot1
         _same_events(px.load_list("mem:common_on_ev3"), ev2)
+        # ... and so does the variant with one big CTA per SM and the table rows staged in shared memory
+        monkeypatch.delenv("PXB_GENERIC_KERNELS")
+        monkeypatch.setenv("PXB_FUSED_BIG_CTA", "1")
+        from pyxsim_b200 import _lib
+        tot4 = px.make_events("mem:common_on_ev4", src, z, area, texp, model(), normal, [30.0, 45.0], **kw)
+        assert tot4 == tot1 and _lib.last_pipeline_launch() == (2, 1, 1)
+        _same_events(px.load_list("mem:common_on_ev4"), ev2)
 
 
 def test_make_events_falls_back_to_two_stages(cuda):
