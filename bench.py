@@ -229,6 +229,8 @@ def wl_cluster(args, px, torch, dist, dev, rank, world):
                               absorb_model="wabs", nH=NH, prng=SEED_PROJ)
 
     W.step, W.step_fused = step, step_fused
+    W.step_fused_f32 = lambda src: px.make_events(efx, src, REDSHIFT, area, exp_time, model, "z", [30.0, 45.0],
+                                                  absorb_model="wabs", nH=NH, prng=SEED_PROJ, event_dtype="float32")
     W.cpu = (tables, area_time / world, D_A)
     W.nZ, W.nD, W.h2d_skip = 0, 0, [("gas", "density")]
     W.desc = (f"synthetic uniform grid {n}^3 thermal beta-model cluster (configs[1]"
@@ -560,16 +562,36 @@ def run_ours(args):
         cpu = cpu_baseline(args, W.fields, tables, area_time, D_A, ncores=1)
 
     if rank == 0:
+        two_stage = {"value": value, "unit": UNIT, "ms_per_step": ms_per_step,
+                     "api": "pyxsim_b200.make_photons + project_photons (the reference's two calls, the photon "
+                            "list resident in HBM between them)",
+                     "photons_per_step": n_ph_all, "events_per_step": n_ev_all,
+                     "whole_step_hbm_frac": round(whole / peak_gbs, 4),
+                     "algorithmic_bytes_per_step": int(B_G + B_P), "roofline": roofline,
+                     "gpu_launches": launches}
+        if fused is not None:
+            # headline: the fused step -- it generates and projects the same photons and leaves the
+            # same event list bit for bit (checked every run: same counts; tests: same arrays)
+            head = dict(value=fused["value"], ms_per_step=fused["ms_per_step"], roofline=fused["roofline"],
+                        whole=fused["whole_step_hbm_frac"], bytes=fused["algorithmic_bytes_per_step"],
+                        launches=fused["gpu_launches"], api=fused["api"])
+        else:
+            head = dict(value=value, ms_per_step=ms_per_step, roofline=roofline, whole=round(whole / peak_gbs, 4),
+                        bytes=int(B_G + B_P), launches=launches, api=two_stage["api"])
+        cfg = workload_config(args, W, world)
+        cfg["step_api"] = head["api"]
         out = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+            "metric": METRIC, "value": head["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": head["ms_per_step"], "higher_is_better": True,
             "scaling": W.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": workload_config(args, W, world),
+            "config": cfg,
             "photons_per_step": n_ph_all, "active_cells": n_c_all, "events_per_step": n_ev_all,
-            "whole_step_hbm_frac": round(whole / peak_gbs, 4),
-            "algorithmic_bytes_per_step": int(B_G + B_P),
-            "roofline": roofline, "fused": fused, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks,
-            "gpu_launches": launches,
+            "whole_step_hbm_frac": head["whole"],
+            "algorithmic_bytes_per_step": head["bytes"],
+            "roofline": head["roofline"], "two_stage": two_stage,
+            "fused_same_counts_as_two_stage": None if fused is None else fused["same_counts_as_two_stage"],
+            "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks,
+            "gpu_launches": head["launches"],
         }
         emit(out)
     if world > 1:
@@ -579,13 +601,46 @@ def run_ours(args):
 
 def run_e2e(args, px, torch, dist, world, dev, W, sync_all):
     """Same step through the public API with HOST inputs (pinned NumPy-visible tensors) and the
-    event list read back into pinned host memory, copies inside the timed region."""
+    event list read back into pinned host memory, copies inside the timed region.  The default
+    (float64 events, the reference's file format) is the `e2e` value; `f32_events` repeats it with
+    event_dtype="float32" (single-precision energies and sky offsets: half the bytes over PCIe),
+    `d2h_ceiling` is a plain pinned device-to-host copy of the same number of bytes."""
     import psutil
 
     host_fields = {k: v.cpu().pin_memory() for k, v in W.fields.items()}
     src_host = W.make_source(host_fields)
     h2d = sum(v.numel() * v.element_size() for k, v in host_fields.items() if k not in W.h2d_skip)
-    step = W.step_fused or W.step
+    res = _e2e_leg(args, px, torch, dist, world, dev, W, sync_all, src_host, h2d, W.step_fused or W.step,
+                   torch.float64, psutil)
+    if getattr(W, "step_fused_f32", None) is not None:
+        leg = _e2e_leg(args, px, torch, dist, world, dev, W, sync_all, src_host, h2d, W.step_fused_f32,
+                       torch.float32, psutil)
+        res["f32_events"] = {k: leg[k] for k in ("value", "unit", "d2h_bytes_per_step", "steps", "host_landing")}
+    # what the PCIe link gives for a plain copy of one step's events (pinned, one stream)
+    nbytes = int(res["d2h_bytes_per_step"])
+    if nbytes > 0:
+        chunk = min(nbytes, 1 << 30)
+        dsrc = torch.empty(chunk, dtype=torch.uint8, device=dev)
+        hdst = torch.empty(chunk, dtype=torch.uint8, pin_memory=True)
+        hdst.copy_(dsrc, non_blocking=True)
+        sync_all()
+        t0 = time.perf_counter()
+        for _ in range(max(1, nbytes // chunk)):
+            hdst.copy_(dsrc, non_blocking=True)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        gbs = max(1, nbytes // chunk) * chunk / dt / 1e9
+        tt = torch.tensor([gbs], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MIN)
+        res["d2h_ceiling"] = {"gb_per_s_per_gpu": round(float(tt.item()), 2),
+                              "photons_per_s_if_only_the_event_copy": round(
+                                  res["photons_per_step"] / (nbytes / world / (float(tt.item()) * 1e9)), 1),
+                              "note": "slowest rank's pinned D2H rate with all ranks copying at once"}
+    return res
+
+
+def _e2e_leg(args, px, torch, dist, world, dev, W, sync_all, src_host, h2d, step, dtype, psutil):
     efxs = [W.efx] + [e for _, e in getattr(W, "extra_lists", [])]
     # pinned landing buffers for the events, sized from a dry run.  When host memory allows (per
     # rank share) the whole event list lands in pinned memory; otherwise it is streamed through
@@ -596,7 +651,8 @@ def run_e2e(args, px, torch, dist, world, dev, W, sync_all):
     budget = 0.25 * psutil.virtual_memory().available / max(world, 1)
     cap = full_cap if 3 * 8 * full_cap <= budget else max(1 << 20, int(budget // 24))
     cap = min(cap, full_cap)
-    landing = {k: torch.empty(cap, dtype=torch.float64, pin_memory=True) for k in ("xsky", "ysky", "eobs")}
+    esz = 8 if dtype == torch.float64 else 4
+    landing = {k: torch.empty(cap, dtype=dtype, pin_memory=True) for k in ("xsky", "ysky", "eobs")}
     n_steps = max(2, min(args.steps, 8))
     # the device->host copies of a step's events run on their own stream, so the next step's
     # upload and kernels overlap them (what a pipeline that consumes the events would do); every
@@ -622,7 +678,7 @@ def run_e2e(args, px, torch, dist, world, dev, W, sync_all):
                     for a in range(0, m, cap):
                         b = min(a + cap, m)
                         landing[k][: b - a].copy_(src_t[a:b], non_blocking=True)
-            d2h += 3 * 8 * m
+            d2h += 3 * esz * m
         tot_ph = n_ph
     copy_stream.synchronize()
     sync_all()
@@ -632,10 +688,10 @@ def run_e2e(args, px, torch, dist, world, dev, W, sync_all):
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
     dt = float(tt.item())
     return {"value": tot_ph * n_steps / dt, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
-            "d2h_bytes_per_step": int(d2h), "steps": n_steps,
+            "d2h_bytes_per_step": int(d2h), "steps": n_steps, "photons_per_step": tot_ph,
             "api": "make_events" if W.step_fused else "make_photons + project_photons",
             "host_landing": "full event list in pinned memory" if cap == full_cap else
-            f"streamed through a {3 * 8 * cap / 2**30:.1f} GiB pinned ring",
+            f"streamed through a {3 * esz * cap / 2**30:.1f} GiB pinned ring",
             "note": "host cell arrays -> generate + project -> events in pinned host memory (per rank: its "
                     "own shard in, its own events out); a step's event download overlaps the next step's "
                     "upload and kernels"}
