@@ -237,6 +237,231 @@ k_spectrum_from_weights(const DevModel M, int nvar, const double* __restrict__ W
   }
 }
 
+// ---- Doppler-shifted spectra of cells whose clip is a no-op: bucketed by table row ----------
+// For such a cell (non-negative 1-D table, Z >= 0, interior temperature) the cumulative
+// spectrum that shift_spectrum interpolates (spectra.pyx:80-90) is a blend of four per-row
+// prefix sums,
+//   cum = w0 (Pc[r0] + Z Pm[r0]) + w1 (Pc[r0+1] + Z Pm[r0+1]),
+// and np.interp is linear in its ordinates, so the cell's contribution at a new edge e is the
+// same blend of the rows' interpolants at e / shift.  Cells are counting-sorted by r0; a CTA
+// stages the four rows of one bucket in shared memory once per 1024 cells, each LANE owns one
+// cell (its five constants in registers) and walks the new edges; the 32 cells x 32 bins of a
+// warp are summed by a transposing butterfly (lane L ends with bin L's total) and added to the
+// CTA's accumulator.  Linear model bins only (the interval is one multiply-add); everything
+// else goes through the list to the per-cell kernel above.
+constexpr int SB_CHUNK = 1024;      // cells per work item
+constexpr int SB_THREADS = 512;
+
+struct SpecBuckets {
+  int* key;                  // [ncell] bucket of the cell, -1: not on this path
+  double* par;               // [5][ncell] sorted cells: a0..a3 (blend x weight), k1 = 1/(shift*de)
+  unsigned* hist;            // [nb] cells per bucket
+  unsigned* start;           // [nb] first sorted slot of the bucket
+  unsigned* cursor;          // [nb]
+  int2* items;               // work items: (bucket, first sorted slot); count in n_items
+  unsigned* n_items;
+  unsigned* ticket;
+  int nb;
+};
+
+__device__ __forceinline__ bool spec_bucket_cell(const DevModel& M, const pxb_thermal_cells& C,
+                                                 int64_t i, CellMix& mx, double& Z, bool& listed) {
+  listed = false;
+  const double kT = C.kT[i];
+  if (!cell_cut(C, i, kT)) return false;
+  const double nH = C.nH ? C.nH[i] : 0.0;
+  cell_mix(M, kT, nH, mx);
+  const double xh = cell_xh(C, i);
+  Z = cell_metal(C, i, xh);
+  const bool ok = mx.t->nonneg && mx.t->pre_n && mx.interior && (Z >= 0.0) && mx.nr == 2;
+  listed = !ok;
+  return ok;
+}
+
+__global__ void __launch_bounds__(256)
+k_spec_bucket_count(const DevModel M, const __grid_constant__ pxb_thermal_cells C, SpecBuckets B,
+                    int64_t* __restrict__ list, unsigned long long* __restrict__ list_count) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i0 = (int64_t)blockIdx.x * blockDim.x; i0 < C.ncell; i0 += stride) {
+    const int64_t i = i0 + threadIdx.x;
+    int key = -1;
+    if (i < C.ncell) {
+      CellMix mx;
+      double Z;
+      bool listed;
+      if (spec_bucket_cell(M, C, i, mx, Z, listed))
+        key = (mx.t == &M.prim ? 0 : M.prim.nrows) + mx.row[0];
+      else if (listed)
+        list[atomicAdd(list_count, 1ull)] = i;
+      B.key[i] = key;
+    }
+    // one atomic per distinct bucket of the warp
+    const unsigned act = __ballot_sync(0xffffffffu, key >= 0);
+    if (key >= 0) {
+      const unsigned same = __match_any_sync(act, key);
+      if ((int)(threadIdx.x & 31) == __ffs(same) - 1) atomicAdd(B.hist + key, (unsigned)__popc(same));
+    }
+  }
+}
+
+// one CTA: bucket starts and the work items (nb is a few hundred at most)
+__global__ void k_spec_bucket_plan(SpecBuckets B) {
+  if (threadIdx.x != 0) return;
+  unsigned at = 0, ni = 0;
+  for (int b = 0; b < B.nb; ++b) {
+    const unsigned n = B.hist[b];
+    B.start[b] = at;
+    B.cursor[b] = at;
+    for (unsigned o = 0; o < n; o += SB_CHUNK) B.items[ni++] = make_int2(b, (int)(at + o));
+    at += n;
+  }
+  *B.n_items = ni;
+}
+
+__global__ void __launch_bounds__(256)
+k_spec_bucket_fill(const DevModel M, const __grid_constant__ pxb_thermal_cells C, SpecBuckets B,
+                   const double* __restrict__ shift) {
+  const int lane = threadIdx.x & 31;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const double inv_de = 1.0 / M.dedge;
+  for (int64_t i0 = (int64_t)blockIdx.x * blockDim.x; i0 < C.ncell; i0 += stride) {
+    const int64_t i = i0 + threadIdx.x;
+    const int key = i < C.ncell ? B.key[i] : -1;
+    const unsigned act = __ballot_sync(0xffffffffu, key >= 0);
+    if (key < 0) continue;
+    const unsigned same = __match_any_sync(act, key);
+    const int leader = __ffs(same) - 1;
+    unsigned pos = 0;
+    if (lane == leader) pos = atomicAdd(B.cursor + key, (unsigned)__popc(same));
+    pos = __shfl_sync(same, pos, leader) + (unsigned)__popc(same & ((1u << lane) - 1u));
+    CellMix mx;
+    double Z;
+    bool listed;
+    spec_bucket_cell(M, C, i, mx, Z, listed);
+    const double s = shift[i];
+    const double wgt = s * s * s * cell_norm(C, i);          // spectra.pyx:91 with the cell's norm
+    const int64_t n = C.ncell;
+    B.par[pos] = wgt * mx.w[0];
+    B.par[n + pos] = wgt * mx.w[0] * Z;
+    B.par[2 * n + pos] = wgt * mx.w[1];
+    B.par[3 * n + pos] = wgt * mx.w[1] * Z;
+    B.par[4 * n + pos] = inv_de / s;
+  }
+}
+
+// value of the blended cumulative spectrum at model-bin coordinate u (bins from the first edge)
+template <bool CLAMP>
+__device__ __forceinline__ double sb_eval(const double2* __restrict__ s_c, const double2* __restrict__ s_m,
+                                          double u, int nbins, double a0, double a1, double a2,
+                                          double a3) {
+  if (CLAMP) u = fmin(fmax(u, 0.0), (double)nbins);          // np.interp holds the end values
+  int lo = __double2int_rd(u);
+  if (CLAMP) lo = min(lo, nbins - 1);
+  const double t = u - (double)lo;
+  const double2 c0 = s_c[lo], c1 = s_c[lo + 1], m0 = s_m[lo], m1 = s_m[lo + 1];
+  const double f0 = fma(a3, m0.y, fma(a2, c0.y, fma(a1, m0.x, a0 * c0.x)));
+  const double f1 = fma(a3, m1.y, fma(a2, c1.y, fma(a1, m1.x, a0 * c1.x)));
+  return fma(t, f1 - f0, f0);
+}
+
+__global__ void __launch_bounds__(SB_THREADS, 1)
+k_spec_bucket_run(const DevModel M, SpecBuckets B, int64_t ncell, int nnew,
+                  const double* __restrict__ ebnew, double* __restrict__ spec_out) {
+  extern __shared__ __align__(16) unsigned char sb_dyn[];
+  const int nbins = M.nbins;
+  double2* s_c = reinterpret_cast<double2*>(sb_dyn);           // [nbins+1] {Pc[r0], Pc[r0+1]}
+  double2* s_m = s_c + (nbins + 1);                             // [nbins+1] {Pm[r0], Pm[r0+1]}
+  double* s_acc = reinterpret_cast<double*>(s_m + (nbins + 1)); // [ngrp*32]
+  const int ngrp = (nnew + 31) / 32;
+  double* s_eb = s_acc + ngrp * 32;                             // [ngrp*32 + 1], padded with the last edge
+  __shared__ int s_item;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  for (int j = threadIdx.x; j < ngrp * 32; j += blockDim.x) s_acc[j] = 0.0;
+  for (int j = threadIdx.x; j <= ngrp * 32; j += blockDim.x) s_eb[j] = __ldg(ebnew + min(j, nnew));
+  const double c0 = -M.edge0 / M.dedge;
+  const double e_first = __ldg(ebnew), e_last = __ldg(ebnew + nnew);
+  const unsigned n_items = *B.n_items;
+  int cur = -1;
+  while (true) {
+    __syncthreads();
+    if (threadIdx.x == 0) s_item = (int)atomicAdd(B.ticket, 1u);
+    __syncthreads();
+    const unsigned it = (unsigned)s_item;
+    if (it >= n_items) break;
+    const int2 item = B.items[it];
+    if (item.x != cur) {
+      cur = item.x;
+      const bool prim = cur < M.prim.nrows;
+      const DevTable& t = prim ? M.prim : M.fb;
+      const int r0 = prim ? cur : cur - M.prim.nrows;
+      const size_t rs = (size_t)(nbins + 1);
+      const double* pc = t.pre_n + (size_t)r0 * rs;
+      const double* pm = t.pre_n + ((size_t)t.nrows + r0) * rs;
+      for (int j = threadIdx.x; j <= nbins; j += blockDim.x) {
+        s_c[j] = make_double2(__ldg(pc + j), __ldg(pc + rs + j));
+        s_m[j] = make_double2(__ldg(pm + j), __ldg(pm + rs + j));
+      }
+      __syncthreads();
+    }
+    const unsigned bend = B.start[cur] + B.hist[cur];
+    const unsigned iend = min((unsigned)item.y + SB_CHUNK, bend);
+    for (unsigned base = (unsigned)item.y + wid * 32; base < iend; base += SB_THREADS) {
+      const unsigned p = base + lane;
+      const bool valid = p < iend;
+      const double a0 = valid ? B.par[p] : 0.0, a1 = valid ? B.par[ncell + p] : 0.0;
+      const double a2 = valid ? B.par[2 * ncell + p] : 0.0, a3 = valid ? B.par[3 * ncell + p] : 0.0;
+      const double k1 = B.par[4 * ncell + (valid ? p : base)];
+      // do all the warp's cells keep every new edge inside the model's range?
+      double kmin = k1, kmax = k1;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        kmin = fmin(kmin, __shfl_xor_sync(0xffffffffu, kmin, o));
+        kmax = fmax(kmax, __shfl_xor_sync(0xffffffffu, kmax, o));
+      }
+      const bool inside = fma(e_first, kmin, c0) >= 0.0 && fma(e_first, kmax, c0) >= 0.0 &&
+                          fma(e_last, kmax, c0) < (double)nbins && fma(e_last, kmin, c0) < (double)nbins;
+      double vprev = inside ? sb_eval<false>(s_c, s_m, fma(s_eb[0], k1, c0), nbins, a0, a1, a2, a3)
+                            : sb_eval<true>(s_c, s_m, fma(s_eb[0], k1, c0), nbins, a0, a1, a2, a3);
+#pragma unroll 1
+      for (int g = 0; g < ngrp; ++g) {
+        double d[32];
+        const double* eb = s_eb + g * 32 + 1;
+        if (inside) {
+#pragma unroll
+          for (int q = 0; q < 32; ++q) {
+            const double v = sb_eval<false>(s_c, s_m, fma(eb[q], k1, c0), nbins, a0, a1, a2, a3);
+            d[q] = v - vprev;
+            vprev = v;
+          }
+        } else {
+#pragma unroll
+          for (int q = 0; q < 32; ++q) {
+            const double v = sb_eval<true>(s_c, s_m, fma(eb[q], k1, c0), nbins, a0, a1, a2, a3);
+            d[q] = v - vprev;
+            vprev = v;
+          }
+        }
+        // transposing butterfly: after the five steps d[0] of lane L is bin (32 g + L) summed
+        // over the warp's 32 cells
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          const bool up = (lane & o) != 0;
+#pragma unroll
+          for (int q = 0; q < o; ++q) {
+            const double keep = up ? d[q + o] : d[q];
+            const double send = up ? d[q] : d[q + o];
+            d[q] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+          }
+        }
+        if (d[0] != 0.0) atomicAdd(s_acc + g * 32 + lane, d[0]);
+      }
+    }
+  }
+  __syncthreads();
+  for (int j = threadIdx.x; j < nnew; j += blockDim.x)
+    if (s_acc[j] != 0.0) atomicAdd(spec_out + j, s_acc[j]);
+}
+
 // make_band in O(1) per cell.  For a cell whose clip is a no-op the band sum of its blended
 // spectrum is the blend of the rows' band sums, and a band sum over whole bins is a difference of
 // two prefix sums:  sum_{j in band} ener_j spec_ij = sum_rows w_r (P_r[j1] - P_r[j0]).  The band's
@@ -449,6 +674,14 @@ static int check_model_cells(const pxb_model* model, const pxb_thermal_cells* c)
   return PXB_OK;
 }
 
+// workspace of the bucketed shifted path: [keys | par | hist,start,cursor | n_items,ticket | items]
+static int spec_bucket_count(const DevModel& D) { return D.prim.nrows + (D.has_fb ? D.fb.nrows : 0); }
+static int64_t spec_bucket_bytes(const DevModel& D, int64_t ncell) {
+  const int64_t nb = spec_bucket_count(D);
+  const int64_t items = ncell / SB_CHUNK + nb + 1;
+  return ((ncell + 1) / 2 + 5 * ncell + (3 * nb + 2 + 1) / 2 + 1 + items) * (int64_t)sizeof(double);
+}
+
 static int64_t spectrum_weight_count(const DevModel& D) {
   return (int64_t)(2 + D.nvar) * (D.prim.nrows + (D.has_fb ? D.fb.nrows : 0));
 }
@@ -457,7 +690,8 @@ extern "C" int pxb_thermal_spectrum_workspace_bytes(const pxb_model* model, int6
                                                     int64_t* bytes) {
   PXB_REQUIRE(model && bytes && ncell >= 0, "bad argument");
   // [list count, pad | row weights | list of cells that need the per-cell path]
-  *bytes = (2 + spectrum_weight_count(model->dev) + ncell) * (int64_t)sizeof(double);
+  *bytes = (2 + spectrum_weight_count(model->dev) + ncell) * (int64_t)sizeof(double) +
+           spec_bucket_bytes(model->dev, ncell);
   return PXB_OK;
 }
 
@@ -507,6 +741,53 @@ extern "C" int pxb_thermal_spectrum(const pxb_model* model, const pxb_thermal_ce
     PXB_CUDA(cudaFuncSetAttribute(k_spectrum_from_weights, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsm));
     k_spectrum_from_weights<<<1, 1024, fsm, st>>>(D, cells->nvar, W, (int)nnew, ebnew, spec_out);
     PXB_LAUNCH_CHECK();
+    k_thermal_spectrum<<<(unsigned)grid, SPEC_THREADS, smem, st>>>(D, *cells, shift, (int)nnew, ebnew,
+                                                                  spec_out, list, count);
+    PXB_LAUNCH_CHECK();
+    return PXB_OK;
+  }
+  // Doppler-shifted, linear model bins, no variable elements: cells bucketed by table row
+  const int ngrp = (int)((nnew + 31) / 32);
+  const size_t bsm = ((size_t)(D.nbins + 1) * 4 + (size_t)ngrp * 64 + 2) * sizeof(double);
+  const bool bucketed = shift != nullptr && workspace != nullptr && D.nvar == 0 &&
+                        D.edges_uniform && !D.binscale_log && bsm <= 227 * 1024 &&
+                        cells->ncell < (1LL << 31) && (D.prim.pre_n || (D.has_fb && D.fb.pre_n));
+  if (bucketed) {
+    int64_t need = 0;
+    pxb_thermal_spectrum_workspace_bytes(model, cells->ncell, &need);
+    PXB_REQUIRE(workspace_bytes >= need, "spectrum workspace too small (%lld < %lld)",
+                (long long)workspace_bytes, (long long)need);
+    const int64_t n = cells->ncell, nw = spectrum_weight_count(D);
+    unsigned long long* count = (unsigned long long*)workspace;
+    int64_t* list = (int64_t*)((double*)workspace + 2 + nw);
+    SpecBuckets B;
+    B.nb = spec_bucket_count(D);
+    double* p = (double*)(list + n);
+    B.key = (int*)p;                p += (n + 1) / 2;
+    B.par = p;                      p += 5 * n;
+    B.hist = (unsigned*)p;
+    B.start = B.hist + B.nb;
+    B.cursor = B.start + B.nb;
+    B.n_items = B.cursor + B.nb;
+    B.ticket = B.n_items + 1;       p += (3 * B.nb + 2 + 1) / 2 + 1;
+    B.items = (int2*)p;
+    PXB_CUDA(cudaMemsetAsync(workspace, 0, 2 * sizeof(double), st));
+    PXB_CUDA(cudaMemsetAsync(B.hist, 0, (size_t)(3 * B.nb + 2) * sizeof(unsigned), st));
+    int64_t g = (n + 255) / 256;
+    const int64_t cap = (int64_t)pxb_sm_count() * 8;
+    if (g > cap) g = cap;
+    k_spec_bucket_count<<<(unsigned)g, 256, 0, st>>>(D, *cells, B, list, count);
+    PXB_LAUNCH_CHECK();
+    k_spec_bucket_plan<<<1, 32, 0, st>>>(B);
+    PXB_LAUNCH_CHECK();
+    k_spec_bucket_fill<<<(unsigned)g, 256, 0, st>>>(D, *cells, B, shift);
+    PXB_LAUNCH_CHECK();
+    PXB_CUDA(cudaFuncSetAttribute(k_spec_bucket_run, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bsm));
+    int64_t gr = n / SB_CHUNK + B.nb;
+    if (gr > pxb_sm_count()) gr = pxb_sm_count();
+    k_spec_bucket_run<<<(unsigned)gr, SB_THREADS, bsm, st>>>(D, B, n, (int)nnew, ebnew, spec_out);
+    PXB_LAUNCH_CHECK();
+    // the cells whose clip matters (or with four rows): per-cell kernel over the list
     k_thermal_spectrum<<<(unsigned)grid, SPEC_THREADS, smem, st>>>(D, *cells, shift, (int)nnew, ebnew,
                                                                   spec_out, list, count);
     PXB_LAUNCH_CHECK();

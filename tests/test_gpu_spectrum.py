@@ -312,3 +312,41 @@ def test_unshifted_spectrum_by_linearity_equals_per_cell_path(cuda, oracle, monk
                 np.testing.assert_allclose(fast[cut], refb, rtol=1e-10, atol=scale * 1e-13)
                 assert np.array_equal(fast[~cut], np.zeros((~cut).sum()))
                 assert np.array_equal(fast == 0.0, slow == 0.0) or band == (3.0, 3.001)
+
+
+@pytest.mark.parametrize("wide", [False, True])
+def test_shifted_spectrum_bucketed_by_row_vs_reference_cython(cuda, oracle, monkeypatch, wide):
+    """Doppler-shifted spectra without variable elements: cells whose clip is a no-op are
+    bucketed by table row and regridded from the rows' prefix sums (one lane per cell); the
+    others (temperatures outside a narrow table) take the per-cell kernel.  Against the
+    reference's compiled shift_spectrum and against the per-cell route; ``wide``: new edges
+    beyond both ends of the model's range (np.interp holds the end values there)."""
+    t = H.make_tables(nT=12, nbins=300, nvar=0)
+    t["Tvals"] = np.logspace(np.log10(0.8), np.log10(9.0), 12)
+    kT, em = H.random_cells(6000, seed=21, kT_range=(0.1, 40.0))
+    extra = {("gas", "Z"): np.random.RandomState(2).uniform(0, 1, kT.size)}
+    src = H.cells_source(kT, em, extra=extra)
+    model = px.ThermalSourceModel(H.product_model(t), 0.1, 10.0, 300, ("gas", "Z"), temperature_field=TF,
+                                  prng=1)
+    model.setup_model("spectrum", src, 0.0)
+    model.v_fields = src.velocity_fields
+    model._spec_normal = np.array([0.3, -0.5, 0.8])
+    chunk = next(src.chunks())
+    ebnew = np.linspace(0.02, 14.0, 333) if wide else np.linspace(0.3, 8.0, 151)
+    got = model.process_data("spectrum", chunk, 3e-44, ebins=ebnew, shifting=True)
+    monkeypatch.setenv("PXB_SPECTRUM_PER_CELL", "1")
+    per = model.process_data("spectrum", chunk, 3e-44, ebins=ebnew, shifting=True)
+    monkeypatch.delenv("PXB_SPECTRUM_PER_CELL")
+    np.testing.assert_allclose(got, per, rtol=1e-11, atol=per.max() * 1e-14)
+    v = np.stack([src.fields[f] for f in src.velocity_fields]) / 299792.458
+    nh = model._spec_normal / np.linalg.norm(model._spec_normal)
+    shift = np.sqrt(1.0 - (v ** 2).sum(0)) / (1.0 - nh @ v)
+    om = H.oracle_model(oracle, t)
+    cfg = dict(kT_min=0.025, kT_max=64.0, Zmet="Z", Zconvert=1.0, z_by_xh=False, spectral_norm=3e-44)
+    cut, tot, lam = oracle.thermal_spectra(om, cfg, dict(kT=kT, em=em, Z=extra[("gas", "Z")]))
+    ref = oracle.thermal_spectrum_mode(om, cfg, dict(kT=kT, em=em, Z=extra[("gas", "Z")]), ebnew,
+                                       shift=shift[cut])
+    np.testing.assert_allclose(got, ref, rtol=1e-11, atol=ref.max() * 1e-14)
+    inside = (kT >= t["Tvals"][0]) & (kT <= t["Tvals"][-1])
+    assert 500 < inside.sum() < 5500          # both routes carried a real share of the cells
+    assert np.abs(shift - 1.0).max() > 1e-3
