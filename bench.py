@@ -137,6 +137,7 @@ class Workload:
     """fields: this rank's share (device tensors); make_source(fields) -> ArrayDataSource;
     step(src) / step_fused(src) -> (n_photons, n_cells, n_events) summed over ranks."""
     step_fused = None
+    step_e2e = None  # make_events where it is not the headline (it runs the two stages itself)
     cpu = None       # (tables, area_time, D_A) for the oracle arm (cluster only)
 
 
@@ -295,7 +296,9 @@ def wl_amr(args, px, torch, dist, dev, rank, world):
         return px.make_events(efx, src, REDSHIFT, area, exp_time, model, normal, [30.0, 45.0],
                               absorb_model="wabs", nH=NH, prng=SEED_PROJ)
 
-    W.step, W.step_fused = step, step_fused
+    # (variable elements: option-generic sampler -- make_events itself takes the two stages there,
+    # they are faster; the headline is the two-stage step and the e2e leg calls make_events)
+    W.step, W.step_e2e = step, step_fused
     W.nZ, W.nD, W.h2d_skip = 1 + nvar, 0, [("gas", "density")]
     W.desc = (f"synthetic 4-level nested AMR beta-model cluster, {ncell:.4g} leaf cells (4 x {n}^3 patches, "
               f"configs[2]), thermal + metallicity field + {nvar} var_elem fields, table {NT}x{args.nbins}x{2 + nvar}, "
@@ -342,7 +345,8 @@ def wl_sph(args, px, torch, dist, dev, rank, world):
         return px.make_events(efx, src, REDSHIFT, area, exp_time, model, normal, [30.0, 45.0],
                               absorb_model=absm, nH=NH, kernel="gaussian", prng=SEED_PROJ)
 
-    W.step, W.step_fused = step, step_fused
+    # (2-D log-binned table: option-generic sampler, see wl_amr)
+    W.step, W.step_e2e = step, step_fused
     W.nZ, W.nD, W.h2d_skip = 0, 1, []
     W.desc = (f"synthetic SPH/Gadget-like {npart} gas particles (2^{int(np.log2(npart))}, configs[3]), IGM-style 2-D "
               f"(kT,nH) table 24x12x{nb} log bins + CIE fallback, gaussian SPH-kernel position smoothing, "
@@ -621,7 +625,7 @@ def run_e2e(args, px, torch, dist, world, dev, W, sync_all):
     host_fields = {k: v.cpu().pin_memory() for k, v in W.fields.items()}
     src_host = W.make_source(host_fields)
     h2d = sum(v.numel() * v.element_size() for k, v in host_fields.items() if k not in W.h2d_skip)
-    res = _e2e_leg(args, px, torch, dist, world, dev, W, sync_all, src_host, h2d, W.step_fused or W.step,
+    res = _e2e_leg(args, px, torch, dist, world, dev, W, sync_all, src_host, h2d, W.step_fused or W.step_e2e or W.step,
                    torch.float64, psutil)
     if getattr(W, "step_fused_f32", None) is not None:
         leg = _e2e_leg(args, px, torch, dist, world, dev, W, sync_all, src_host, h2d, W.step_fused_f32,
@@ -700,7 +704,7 @@ def _e2e_leg(args, px, torch, dist, world, dev, W, sync_all, src_host, h2d, step
     dt = float(tt.item())
     return {"value": tot_ph * n_steps / dt, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
             "d2h_bytes_per_step": int(d2h), "steps": n_steps, "photons_per_step": tot_ph,
-            "api": "make_events" if W.step_fused else "make_photons + project_photons",
+            "api": "make_events" if (W.step_fused or W.step_e2e) else "make_photons + project_photons",
             "host_landing": "full event list in pinned memory" if cap == full_cap else
             f"streamed through a {3 * esz * cap / 2**30:.1f} GiB pinned ring",
             "note": "host cell arrays -> generate + project -> events in pinned host memory (per rank: its "

@@ -128,6 +128,10 @@ int pxb_model_create(const pxb_model_desc* desc, pxb_model** out);
 int pxb_model_destroy(pxb_model* model);
 /* 1 when every table entry is >= 0 (the O(1) row-sum / mixture fast paths are legal) */
 int pxb_model_nonnegative(const pxb_model* model);
+/* 1 when pxb_make_events is expected to beat pxb_thermal_sample + pxb_project for this model (the
+ * common sampler applies: linear uniform bins, invert_cdf, no variable elements, 1-D table); 0:
+ * the two calls are faster, although pxb_make_events still gives the same events */
+int pxb_model_fusion_pays(const pxb_model* model);
 
 /* Per-chunk inputs of the thermal source (all per-cell arrays are device, length ncell). */
 typedef struct {
@@ -165,8 +169,10 @@ typedef struct {
                                   gather the rows through L1/L2 */
   int32_t split_factor;        /* variable-element tables: a cell's photons are split over its
                                   (row, table) components once per cell when it holds at least
-                                  split_factor * components photons; 0 => default (6),
-                                  < 0 => never (per-photon component choice) */
+                                  split_factor * components photons (below that every photon
+                                  picks its component from cumulative probabilities stored per
+                                  cell); 0 => default (40), < 0 => never, and the per-photon
+                                  choice re-derives the weights instead of storing them */
 } pxb_thermal_cells;
 
 /* lambda_out (nullable) receives spec_sum*cell_nrm, counts_out the Poisson draws.

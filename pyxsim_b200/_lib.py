@@ -136,6 +136,7 @@ SIGNATURES = {
     "pxb_model_create": (C.c_int, [_P(ModelDesc), _P(c_void_p)]),
     "pxb_model_destroy": (C.c_int, [c_void_p]),
     "pxb_model_nonnegative": (C.c_int, [c_void_p]),
+    "pxb_model_fusion_pays": (C.c_int, [c_void_p]),
     "pxb_thermal_counts": (C.c_int, [c_void_p, _P(ThermalCells), c_void_p, c_void_p, c_void_p]),
     "pxb_thermal_spectra": (C.c_int, [c_void_p, _P(ThermalCells), c_void_p, c_void_p]),
     "pxb_interp_spec": (C.c_int, [c_void_p, C.c_int64, c_void_p, c_void_p, c_void_p, c_void_p,

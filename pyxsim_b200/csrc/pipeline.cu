@@ -209,13 +209,13 @@ k_prep_sample(const DevModel M, const __grid_constant__ pxb_thermal_cells C, int
               int64_t* __restrict__ tile_cell, int64_t* __restrict__ list,
               unsigned long long* __restrict__ list_count, int64_t* __restrict__ tabcum,
               int64_t* __restrict__ glist, unsigned long long* __restrict__ glist_count,
-              int split_factor, int tslots) {
+              int split_factor, int tslots, int tab_stride) {
   const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   bool want_general = false;
   if (k < n_active) {
     const int64_t a = poff[k], b = poff[k + 1];
     const int64_t i = idx[k];
-    FastCell fc = fast_setup<false>(M, C, i, b - a, tabcum, split_factor);
+    FastCell fc = fast_setup<false>(M, C, i, b - a, tabcum ? tabcum + k * tab_stride : nullptr, split_factor);
     want_general = (fc.meta & 128) != 0;
     fc.meta &= ~128;
     CellRec r;
@@ -617,11 +617,13 @@ k_pipeline(const DevModel M, const __grid_constant__ pxb_thermal_cells C,
             fc.meta = meta;
             fc.cnt[0] = cn0; fc.cnt[1] = cn1; fc.cnt[2] = cn2;
             const int64_t i = __ldg(A.idx + c0 + rel);
+            const double* th = (meta & 256)
+                ? reinterpret_cast<const double*>(A.tabcum + (c0 + rel) * A.tab_stride) : nullptr;
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
               if (h && !hasB) break;
               const Philox4 rn = pxb_rand4(RKE, STREAM_ENERGY, gid, d0 + h);
-              const double e = fast_draw<0>(M, C, fc, i, u53(rn.x, rn.y), rn.z, rn.w);
+              const double e = fast_draw<0>(M, C, fc, i, th, u53(rn.x, rn.y), rn.z, rn.w);
               if (h) eB = e; else eA = e;
             }
           }
@@ -1049,6 +1051,16 @@ static bool sample_is_common(const DevModel& D, const pxb_thermal_cells* cells) 
   return D.method == 0 && !D.binscale_log && D.edges_uniform && D.nvar == 0 &&
          !D.density_dependent && !D.has_fb && !(cells->generic_kernels & 1);
 }
+// The fused kernel pays where sampling is cheap enough for the step to be bound by the photon
+// list's memory traffic -- the common sampler.  With the option-generic sampler (variable elements,
+// 2-D or log-binned tables, accept-reject) the step is bound by table gathers and the two
+// stages, each with its own CTA shape, are faster (measured at the named sizes: amr 37.8 vs 41.3 ms,
+// sph 29.3 vs 35.7 ms per step on 8 GPUs); callers ask here which route to take.
+extern "C" int pxb_model_fusion_pays(const pxb_model* m) {
+  if (!m) return 0;
+  pxb_thermal_cells none{};
+  return (m->dev.fast_ok && sample_is_common(m->dev, &none)) ? 1 : 0;
+}
 // 0: generic; 1: common on-axis; 2: common off-axis
 static int project_spec(const pxb_project_params* P) {
   if (P->generic_kernels) return 0;
@@ -1081,10 +1093,13 @@ static int prep_sample(const pxb_model* model, const pxb_thermal_cells* cells, i
   int64_t* tabcum = tab_stride ? (int64_t*)(ws + lay.off_tabcum) : nullptr;
   int64_t* glist = tab_stride ? (int64_t*)(ws + lay.off_glist) : nullptr;
   if (cells->split_factor < 0) tabcum = nullptr;   // per-photon component choice
-  const int split_factor = cells->split_factor > 0 ? cells->split_factor : 6;
+  // (photons per component from which the multinomial split is taken instead of the per-photon
+  // choice from stored cumulative probabilities; measured on the amr configuration, 38 photons per
+  // cell on average: sampling stage 59.2 ms at 6, 46.9 at 16, 43.6 at 40, 43.2 never splitting)
+  const int split_factor = cells->split_factor > 0 ? cells->split_factor : 40;
   k_prep_sample<<<(unsigned)((n_active + 255) / 256), 256, 0, st>>>(
       D, *cells, n_active, idx, poff, qoff, recs, tile_cell, list, H.list_count, tabcum, glist,
-      H.glist_count, split_factor, lay.tslots);
+      H.glist_count, split_factor, lay.tslots, tab_stride);
   PXB_LAUNCH_CHECK();
   if (tabcum) {
     int64_t gs = (n_active + 127) / 128;

@@ -41,7 +41,7 @@ __device__ __forceinline__ int fast_row(const DevTable* t, int z1, int nr, int r
 template <bool GENERAL>
 __device__ __forceinline__ FastCell fast_setup(const DevModel& M, const pxb_thermal_cells& C,
                                             int64_t i, int64_t N, int64_t* tabcum,
-                                            int split_factor = 6) {
+                                            int split_factor = 40) {
   FastCell fc;
   const double kT = C.kT[i];
   const double nH = C.nH ? C.nH[i] : 0.0;
@@ -51,22 +51,25 @@ __device__ __forceinline__ FastCell fast_setup(const DevModel& M, const pxb_ther
   const double Z = cell_metal(C, i, xh);
   const DevTable* t = mx.t;
   bool ok = mx.interior && (Z >= 0.0);
-  double s[4] = {0.0, 0.0, 0.0, 0.0};
+  // (explicit multiply-adds: the threshold mode below re-accumulates the same sums and relies on
+  // reaching exactly these totals)
+  double s[4] = {0.0, 0.0, 0.0, 0.0}, sraw[4] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll
   for (int r = 0; r < 4; ++r)
-    if (r < mx.nr) s[r] = __ldg(t->rs_c + mx.row[r]) + Z * __ldg(t->rs_m + mx.row[r]);
+    if (r < mx.nr) s[r] = fma(Z, __ldg(t->rs_m + mx.row[r]), __ldg(t->rs_c + mx.row[r]));
   for (int k = 0; k < C.nvar; ++k) {
     const double e = cell_elem(C, k, i, xh);
     ok = ok && (e >= 0.0);
 #pragma unroll
     for (int r = 0; r < 4; ++r)
-      if (r < mx.nr) s[r] += e * __ldg(t->rs_v + (size_t)k * t->nrows + mx.row[r]);
+      if (r < mx.nr) s[r] = fma(e, __ldg(t->rs_v + (size_t)k * t->nrows + mx.row[r]), s[r]);
   }
   double tot = 0.0;
   int last = 0;
 #pragma unroll
   for (int r = 0; r < 4; ++r)
     if (r < mx.nr) {
+      sraw[r] = s[r];
       s[r] *= mx.w[r];
       tot += s[r];
       if (s[r] > 0.0) last = r;
@@ -112,9 +115,10 @@ __device__ __forceinline__ FastCell fast_setup(const DevModel& M, const pxb_ther
     // Any other table shape (2-D tables blend four rows; variable elements add tables): the
     // same multinomial split done hierarchically -- N over the rows, then every row's share
     // over its tables -- with the within-row cumulative counts in the side array.  Only with
-    // variable elements (whose per-photon component choice loops over the element tables; a
-    // binomial draw costs about as much as ten such choices, hence the threshold); without them
-    // the per-photon choice is cheap and the sampler is bound by the CDF gathers anyway
+    // variable elements and only for cells with many photons: a split photon shares its Philox
+    // block with its pair partner, but the split costs one binomial draw per component, and the
+    // per-photon choice from the stored thresholds below is cheap.  Without variable elements
+    // the per-photon choice is one compare and the sampler is bound by the table gathers anyway
     // (measured on the 2-D table configuration: the split made it slower).
     const int ntab = 2 + C.nvar;
     CellStream rs(C.seed, STREAM_SPLIT, cell_gid(C, i));
@@ -167,6 +171,37 @@ __device__ __forceinline__ FastCell fast_setup(const DevModel& M, const pxb_ther
       }
     }
     fc.meta |= 64;
+  } else if (!GENERAL && ok && tabcum && C.nvar > 0 && N > 0) {
+    // Variable elements, too few photons for the split to pay: every photon picks its component
+    // itself, from ONE ascending array of nr x ntab cumulative probabilities written here (the
+    // side array's slot of the cell, as doubles) instead of re-deriving the element weights per
+    // photon.  Component c = row r, table tb is chosen for th[c-1] <= u < th[c]; zero-weight
+    // components have zero width, and everything from a row's last non-empty table on carries
+    // the row's upper end, so rounding never selects an empty table.
+    const int ntab = 2 + C.nvar;
+    double* th = reinterpret_cast<double*>(tabcum);
+    double c[4] = {0.0, 0.0, 0.0, 0.0}, scale[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const double lo = r > 0 ? fc.cum[r - 1] : 0.0;
+      const double hi = r < 3 ? fc.cum[r] : 1.0;
+      scale[r] = (r < mx.nr && sraw[r] > 0.0) ? (hi - lo) / sraw[r] : 0.0;
+    }
+    for (int tb = 0; tb < ntab; ++tb) {
+      const double e = tb == 0 ? 1.0 : (tb == 1 ? Z : cell_elem(C, tb - 2, i, xh));
+      const double* rs = tb == 0 ? t->rs_c : (tb == 1 ? t->rs_m : t->rs_v + (size_t)(tb - 2) * t->nrows);
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        if (r >= mx.nr) continue;
+        // the running sum of the row's table weights, accumulated exactly as sraw[r] was: from the
+        // row's last non-empty table on it EQUALS sraw[r]
+        c[r] = tb == 0 ? __ldg(rs + mx.row[r]) : fma(e, __ldg(rs + mx.row[r]), c[r]);
+        const double lo = r > 0 ? fc.cum[r - 1] : 0.0;
+        const double hi = r < 3 ? fc.cum[r] : 1.0;
+        th[r * ntab + tb] = (c[r] >= sraw[r]) ? hi : fmin(fma(c[r], scale[r], lo), hi);
+      }
+    }
+    fc.meta |= 256;
   }
   return fc;
 }
@@ -208,12 +243,25 @@ __device__ __forceinline__ const uint2* alias_row(const DevTable* t, int tab, in
 
 // probability mode (no split): the photon picks its component with u1, then samples that row
 // with (w0, w1).  Component order and weights as in fast_setup.
+// th != nullptr: the cell's cumulative component probabilities (fast_setup, meta bit 256).
 template <int SPEC>
 __device__ __forceinline__ double fast_draw(const DevModel& M, const pxb_thermal_cells& C,
-                                            const FastCell& fc, int64_t i, double u1, uint32_t w0,
-                                            uint32_t w1) {
+                                            const FastCell& fc, int64_t i, const double* th,
+                                            double u1, uint32_t w0, uint32_t w1) {
   const DevTable* t = (fc.meta & 8) ? &M.fb : &M.prim;
   const int nr = fc.meta & 7;
+  if (th) {
+    const int ntab = 2 + C.nvar;
+    int lo = 0, hi = nr * ntab - 1;          // first component with u1 < th[c]
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      if (u1 >= __ldg(th + mid)) lo = mid + 1; else hi = mid;
+    }
+    const int r = lo / ntab;
+    uint32_t v;
+    const int j = alias_pick(alias_row(t, lo - r * ntab, fast_row(t, fc.z1, nr, r)), (unsigned)t->nbins, w0, w1, v);
+    return alias_energy<SPEC>(M, j, v);
+  }
   int r = (u1 >= fc.cum[0]) + (u1 >= fc.cum[1]) + (u1 >= fc.cum[2]);
   r = min(r, nr - 1);
   const double lo = r > 0 ? fc.cum[r - 1] : 0.0;

@@ -349,8 +349,9 @@ k_spec_bucket_fill(const DevModel M, const __grid_constant__ pxb_thermal_cells C
   }
 }
 
-// value of the blended cumulative spectrum at model-bin coordinate u (bins from the first edge)
-template <bool CLAMP>
+// value of the blended cumulative spectrum at model-bin coordinate u (bins from the first edge).
+// ZCONST (one metallicity for the whole call): the staged rows are already Pc + Z Pm.
+template <bool CLAMP, bool ZCONST>
 __device__ __forceinline__ double sb_eval(const double2* __restrict__ s_c, const double2* __restrict__ s_m,
                                           double u, int nbins, double a0, double a1, double a2,
                                           double a3) {
@@ -358,20 +359,29 @@ __device__ __forceinline__ double sb_eval(const double2* __restrict__ s_c, const
   int lo = __double2int_rd(u);
   if (CLAMP) lo = min(lo, nbins - 1);
   const double t = u - (double)lo;
-  const double2 c0 = s_c[lo], c1 = s_c[lo + 1], m0 = s_m[lo], m1 = s_m[lo + 1];
-  const double f0 = fma(a3, m0.y, fma(a2, c0.y, fma(a1, m0.x, a0 * c0.x)));
-  const double f1 = fma(a3, m1.y, fma(a2, c1.y, fma(a1, m1.x, a0 * c1.x)));
+  const double2 c0 = s_c[lo], c1 = s_c[lo + 1];
+  double f0, f1;
+  if (ZCONST) {
+    f0 = fma(a2, c0.y, a0 * c0.x);
+    f1 = fma(a2, c1.y, a0 * c1.x);
+  } else {
+    const double2 m0 = s_m[lo], m1 = s_m[lo + 1];
+    f0 = fma(a3, m0.y, fma(a2, c0.y, fma(a1, m0.x, a0 * c0.x)));
+    f1 = fma(a3, m1.y, fma(a2, c1.y, fma(a1, m1.x, a0 * c1.x)));
+  }
   return fma(t, f1 - f0, f0);
 }
 
+// CPL cells per lane: the butterfly, the edge loads and the loop are shared by 32 CPL cells
+template <bool ZCONST, int CPL>
 __global__ void __launch_bounds__(SB_THREADS, 1)
-k_spec_bucket_run(const DevModel M, SpecBuckets B, int64_t ncell, int nnew,
+k_spec_bucket_run(const DevModel M, SpecBuckets B, int64_t ncell, double zconst, int nnew,
                   const double* __restrict__ ebnew, double* __restrict__ spec_out) {
   extern __shared__ __align__(16) unsigned char sb_dyn[];
   const int nbins = M.nbins;
   double2* s_c = reinterpret_cast<double2*>(sb_dyn);           // [nbins+1] {Pc[r0], Pc[r0+1]}
-  double2* s_m = s_c + (nbins + 1);                             // [nbins+1] {Pm[r0], Pm[r0+1]}
-  double* s_acc = reinterpret_cast<double*>(s_m + (nbins + 1)); // [ngrp*32]
+  double2* s_m = s_c + (nbins + 1);                             // [nbins+1] {Pm[r0], Pm[r0+1]} (!ZCONST)
+  double* s_acc = reinterpret_cast<double*>(ZCONST ? s_m : s_m + (nbins + 1));   // [ngrp*32]
   const int ngrp = (nnew + 31) / 32;
   double* s_eb = s_acc + ngrp * 32;                             // [ngrp*32 + 1], padded with the last edge
   __shared__ int s_item;
@@ -398,21 +408,34 @@ k_spec_bucket_run(const DevModel M, SpecBuckets B, int64_t ncell, int nnew,
       const double* pc = t.pre_n + (size_t)r0 * rs;
       const double* pm = t.pre_n + ((size_t)t.nrows + r0) * rs;
       for (int j = threadIdx.x; j <= nbins; j += blockDim.x) {
-        s_c[j] = make_double2(__ldg(pc + j), __ldg(pc + rs + j));
-        s_m[j] = make_double2(__ldg(pm + j), __ldg(pm + rs + j));
+        if (ZCONST) {
+          s_c[j] = make_double2(fma(zconst, __ldg(pm + j), __ldg(pc + j)),
+                                fma(zconst, __ldg(pm + rs + j), __ldg(pc + rs + j)));
+        } else {
+          s_c[j] = make_double2(__ldg(pc + j), __ldg(pc + rs + j));
+          s_m[j] = make_double2(__ldg(pm + j), __ldg(pm + rs + j));
+        }
       }
       __syncthreads();
     }
     const unsigned bend = B.start[cur] + B.hist[cur];
     const unsigned iend = min((unsigned)item.y + SB_CHUNK, bend);
-    for (unsigned base = (unsigned)item.y + wid * 32; base < iend; base += SB_THREADS) {
-      const unsigned p = base + lane;
-      const bool valid = p < iend;
-      const double a0 = valid ? B.par[p] : 0.0, a1 = valid ? B.par[ncell + p] : 0.0;
-      const double a2 = valid ? B.par[2 * ncell + p] : 0.0, a3 = valid ? B.par[3 * ncell + p] : 0.0;
-      const double k1 = B.par[4 * ncell + (valid ? p : base)];
+    for (unsigned base = (unsigned)item.y + wid * (32 * CPL); base < iend; base += SB_THREADS * CPL) {
+      double a0[CPL], a1[CPL], a2[CPL], a3[CPL], k1[CPL], vprev[CPL];
+      double kmin = 1.0e300, kmax = 0.0;
+#pragma unroll
+      for (int c = 0; c < CPL; ++c) {
+        const unsigned p = base + c * 32 + lane;
+        const bool valid = p < iend;
+        a0[c] = valid ? B.par[p] : 0.0;
+        a2[c] = valid ? B.par[2 * ncell + p] : 0.0;
+        a1[c] = (valid && !ZCONST) ? B.par[ncell + p] : 0.0;
+        a3[c] = (valid && !ZCONST) ? B.par[3 * ncell + p] : 0.0;
+        k1[c] = B.par[4 * ncell + (valid ? p : base)];
+        kmin = fmin(kmin, k1[c]);
+        kmax = fmax(kmax, k1[c]);
+      }
       // do all the warp's cells keep every new edge inside the model's range?
-      double kmin = k1, kmax = k1;
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) {
         kmin = fmin(kmin, __shfl_xor_sync(0xffffffffu, kmin, o));
@@ -420,8 +443,9 @@ k_spec_bucket_run(const DevModel M, SpecBuckets B, int64_t ncell, int nnew,
       }
       const bool inside = fma(e_first, kmin, c0) >= 0.0 && fma(e_first, kmax, c0) >= 0.0 &&
                           fma(e_last, kmax, c0) < (double)nbins && fma(e_last, kmin, c0) < (double)nbins;
-      double vprev = inside ? sb_eval<false>(s_c, s_m, fma(s_eb[0], k1, c0), nbins, a0, a1, a2, a3)
-                            : sb_eval<true>(s_c, s_m, fma(s_eb[0], k1, c0), nbins, a0, a1, a2, a3);
+#pragma unroll
+      for (int c = 0; c < CPL; ++c)
+        vprev[c] = sb_eval<true, ZCONST>(s_c, s_m, fma(s_eb[0], k1[c], c0), nbins, a0[c], a1[c], a2[c], a3[c]);
 #pragma unroll 1
       for (int g = 0; g < ngrp; ++g) {
         double d[32];
@@ -429,20 +453,32 @@ k_spec_bucket_run(const DevModel M, SpecBuckets B, int64_t ncell, int nnew,
         if (inside) {
 #pragma unroll
           for (int q = 0; q < 32; ++q) {
-            const double v = sb_eval<false>(s_c, s_m, fma(eb[q], k1, c0), nbins, a0, a1, a2, a3);
-            d[q] = v - vprev;
-            vprev = v;
+            const double e = eb[q];
+            double sum = 0.0;
+#pragma unroll
+            for (int c = 0; c < CPL; ++c) {
+              const double v = sb_eval<false, ZCONST>(s_c, s_m, fma(e, k1[c], c0), nbins, a0[c], a1[c], a2[c], a3[c]);
+              sum += v - vprev[c];
+              vprev[c] = v;
+            }
+            d[q] = sum;
           }
         } else {
 #pragma unroll
           for (int q = 0; q < 32; ++q) {
-            const double v = sb_eval<true>(s_c, s_m, fma(eb[q], k1, c0), nbins, a0, a1, a2, a3);
-            d[q] = v - vprev;
-            vprev = v;
+            const double e = eb[q];
+            double sum = 0.0;
+#pragma unroll
+            for (int c = 0; c < CPL; ++c) {
+              const double v = sb_eval<true, ZCONST>(s_c, s_m, fma(e, k1[c], c0), nbins, a0[c], a1[c], a2[c], a3[c]);
+              sum += v - vprev[c];
+              vprev[c] = v;
+            }
+            d[q] = sum;
           }
         }
         // transposing butterfly: after the five steps d[0] of lane L is bin (32 g + L) summed
-        // over the warp's 32 cells
+        // over the warp's cells
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
           const bool up = (lane & o) != 0;
@@ -782,10 +818,18 @@ extern "C" int pxb_thermal_spectrum(const pxb_model* model, const pxb_thermal_ce
     PXB_LAUNCH_CHECK();
     k_spec_bucket_fill<<<(unsigned)g, 256, 0, st>>>(D, *cells, B, shift);
     PXB_LAUNCH_CHECK();
-    PXB_CUDA(cudaFuncSetAttribute(k_spec_bucket_run, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bsm));
     int64_t gr = n / SB_CHUNK + B.nb;
     if (gr > pxb_sm_count()) gr = pxb_sm_count();
-    k_spec_bucket_run<<<(unsigned)gr, SB_THREADS, bsm, st>>>(D, B, n, (int)nnew, ebnew, spec_out);
+    // one metallicity for the call: the metal rows are folded into the staged rows
+    if (!cells->zmet) {
+      auto kern = k_spec_bucket_run<true, 2>;
+      PXB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bsm));
+      kern<<<(unsigned)gr, SB_THREADS, bsm, st>>>(D, B, n, cells->zmet_const, (int)nnew, ebnew, spec_out);
+    } else {
+      auto kern = k_spec_bucket_run<false, 1>;
+      PXB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bsm));
+      kern<<<(unsigned)gr, SB_THREADS, bsm, st>>>(D, B, n, 0.0, (int)nnew, ebnew, spec_out);
+    }
     PXB_LAUNCH_CHECK();
     // the cells whose clip matters (or with four rows): per-cell kernel over the list
     k_thermal_spectrum<<<(unsigned)grid, SPEC_THREADS, smem, st>>>(D, *cells, shift, (int)nnew, ebnew,

@@ -681,9 +681,11 @@ def make_events(event_prefix, data_source, redshift, area, exp_time, source_mode
     projection.  The event list is bit for bit the one ``make_photons`` + ``project_photons``
     produce with the same seeds.  Returns ``(n_photons, n_cells, n_events)`` summed over ranks.
 
-    Thermal sources with non-negative tables run fused; anything else (power-law / line sources,
-    tables with negative entries, cells extrapolating beyond the table, reference-style host
-    models) takes the two stages through an in-memory photon list."""
+    Thermal sources with non-negative tables and the common sampler (linear bins, invert_cdf,
+    no variable elements, 1-D table) run fused; anything else (power-law / line sources, tables
+    with negative entries, cells extrapolating beyond the table, reference-style host models, and
+    the option-generic sampler, for which the two stages are faster) takes the two stages through
+    an in-memory photon list."""
     require_cuda()
     event_prefix = _strip(event_prefix)
     pr = _Projection("external", normal, sky_center, absorb_model=absorb_model, nH=nH,
@@ -698,6 +700,10 @@ def make_events(event_prefix, data_source, redshift, area, exp_time, source_mode
         pr.check_list("external", G.data_type)
         dm = source_model.spectral_model.device_model(source_model.method)
         fusable = bool(_lib.load().pxb_model_nonnegative(dm.handle))
+        # with the option-generic sampler the two stages are the faster route (same events);
+        # PXB_FUSE_GENERIC=1 keeps the fused kernel on (diagnostics, parity tests)
+        if fusable and not _lib.load().pxb_model_fusion_pays(dm.handle):
+            fusable = bool(os.environ.get("PXB_FUSE_GENERIC"))
     if not fusable:
         return _make_events_two_stage(event_prefix, data_source, redshift, area, exp_time, source_model,
                                       pr, point_sources, parameters, center, dist, cosmology,

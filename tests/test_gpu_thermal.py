@@ -423,13 +423,14 @@ def test_energy_distribution_with_variable_elements(cuda, oracle):
     H.assert_distributions_agree(run, seeds=((3, 4), (13, 14)))
 
 
-def test_component_split_fractions_with_disjoint_bands(cuda, oracle):
+def test_component_split_fractions_with_disjoint_bands(cuda, oracle, monkeypatch):
     """Multinomial split of a cell's photons over its mixture components (4 rows-x-tables for a
     plain table, rows x (2 + nvar) with variable elements).  The tables here emit in DISJOINT
     energy bands, so every photon's table can be read off its energy: per table, the counts
     summed over cells must match sum_cells N_cell * q_cell,table with q from the oracle's blended
-    spectrum, both for bright cells (split mode) and for cells with a handful of photons
-    (per-photon component choice)."""
+    spectrum -- for bright cells in split mode (threshold lowered to the cells' size), for the same
+    cells and for cells with a handful of photons under the per-photon choice from the stored
+    cumulative probabilities, and under the per-photon choice that re-derives the weights."""
     nT, nbins, nvar = 12, 400, 2
     rng = np.random.RandomState(21)
     Tvals = np.logspace(np.log10(0.3), np.log10(20.0), nT)
@@ -442,7 +443,15 @@ def test_component_split_fractions_with_disjoint_bands(cuda, oracle):
             tabs[tb, r, tb * band:(tb + 1) * band] = shape * (1.0 + 0.3 * tb) * (r + 1.0) ** (0.5 * (tb + 1))
     t = dict(Tvals=Tvals, ebins=ebins, cosmic=tabs[0], metal=tabs[1], var=tabs[2:], binscale="linear")
     om = H.oracle_model(oracle, t)
-    for target, label in ((100.0, "bright"), (3.0, "dim")):
+    for target, label, sf in ((100.0, "bright", "3"), (100.0, "bright", None), (3.0, "dim", None),
+                              (3.0, "dim", "-1")):
+        if sf is None:
+            monkeypatch.delenv("PXB_SPLIT_FACTOR", raising=False)
+            monkeypatch.delenv("PXB_NO_GENERAL_SPLIT", raising=False)
+        elif sf == "-1":
+            monkeypatch.setenv("PXB_NO_GENERAL_SPLIT", "1")
+        else:
+            monkeypatch.setenv("PXB_SPLIT_FACTOR", sf)
         n = 3000
         kT = np.exp(rng.uniform(np.log(0.4), np.log(15.0), n))
         em = 1.0e60 * rng.lognormal(0, 0.3, n)
