@@ -445,6 +445,8 @@ def run_ours(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
     dev = torch.device("cuda", torch.cuda.current_device())
+    # CPUs (and with them the pinned buffers allocated from here on) next to this rank's GPU
+    W_binding = parallel.bind_host_to_gpu(dev.index)
     import logging
 
     logging.getLogger("pyxsim_b200").setLevel("WARNING")
@@ -536,8 +538,8 @@ def run_ours(args):
                 return sum(v["dram_bytes"] for k, v in kk.items() if any(p in k for p in pats))
 
             traffic = {"thermal_sample": dram("k_pipeline<0", "k_prep_sample"),
-                       "project": dram("k_pipeline<1", "k_prep_project"),
-                       "make_events": dram("k_pipeline<2", "k_prep_")}
+                       "project": dram("k_pipeline<1", "k_prep_project<1>"),
+                       "make_events": dram("k_pipeline<2", "k_prep_sample", "k_prep_project<0>")}
         except Exception:
             traffic = None
     kernel_of = {"thermal_sample": "pxb_thermal_sample: k_prep_sample + k_pipeline<MODE_SAMPLE>",
@@ -569,6 +571,12 @@ def run_ours(args):
     e2e = None
     if not args.no_e2e:
         e2e = run_e2e(args, px, torch, dist, world, dev, W, sync_all)
+        binds = _gather_bindings(dist, world, W_binding)
+        e2e["host_binding"] = {"per_rank": binds,
+                               "numa_nodes_seen": sorted({str(b.get("numa_node")) for b in binds}),
+                               "note": "each rank pinned to NVML's ideal CPUs of its GPU before any pinned "
+                                       "allocation (first touch); one NUMA node for all GPUs = the host hides "
+                                       "its topology and the binding cannot help"}
 
     # ---- CPU baseline (rank 0, N=1 only) ---------------------------------------------------------
     cpu = None
@@ -653,6 +661,15 @@ def run_e2e(args, px, torch, dist, world, dev, W, sync_all):
                                   res["photons_per_step"] / (nbytes / world / (float(tt.item()) * 1e9)), 1),
                               "note": "slowest rank's pinned D2H rate with all ranks copying at once"}
     return res
+
+
+def _gather_bindings(dist, world, mine):
+    """Host binding of every rank (NVML ideal CPU affinity, NUMA node of its GPU)."""
+    if world == 1:
+        return [mine]
+    out = [None] * world
+    dist.all_gather_object(out, mine)
+    return out
 
 
 def _e2e_leg(args, px, torch, dist, world, dev, W, sync_all, src_host, h2d, step, dtype, psutil):

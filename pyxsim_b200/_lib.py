@@ -8,7 +8,9 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libpxb.so")
+# (PXB_LIBRARY: another build of the same library, e.g. libpxb_dbg.so with the kernels' index
+# assertions compiled in -- `python -m pyxsim_b200.build --debug-checks`)
+LIB_PATH = os.environ.get("PXB_LIBRARY") or os.path.join(HERE, "libpxb.so")
 
 PXB_MAX_VAR = 64
 

@@ -30,41 +30,47 @@ def _headers_mtime():
     return max(os.path.getmtime(h) for h in hs)
 
 
-def _compile(src, verbose):
-    obj = os.path.join(OBJ, src[:-3] + ".o")
+def _compile(src, verbose, objdir=OBJ, extra=()):
+    obj = os.path.join(objdir, src[:-3] + ".o")
     spath = os.path.join(CSRC, src)
     newest = max(os.path.getmtime(spath), _headers_mtime())
     if os.path.exists(obj) and os.path.getmtime(obj) >= newest:
         return obj, ""
-    cmd = [NVCC, *ARCH, *FLAGS, "-c", spath, "-o", obj]
+    cmd = [NVCC, *ARCH, *FLAGS, *extra, "-c", spath, "-o", obj]
     p = subprocess.run(cmd, capture_output=True, text=True)
     if p.returncode != 0:
         raise RuntimeError(f"nvcc failed for {src}:\n{p.stdout}\n{p.stderr}")
     return obj, p.stderr
 
 
-def build(force=False, verbose=False):
-    os.makedirs(OBJ, exist_ok=True)
+def build(force=False, verbose=False, debug_checks=False):
+    """debug_checks: the same library with the kernels' index assertions compiled in
+    (-DPXB_DEBUG_CHECKS), as pyxsim_b200/libpxb_dbg.so; load it with PXB_LIBRARY=<path>."""
+    objdir = OBJ + "_dbg" if debug_checks else OBJ
+    lib = LIB.replace("libpxb.so", "libpxb_dbg.so") if debug_checks else LIB
+    extra = ("-DPXB_DEBUG_CHECKS",) if debug_checks else ()
+    os.makedirs(objdir, exist_ok=True)
     if force:
-        for f in os.listdir(OBJ):
-            os.remove(os.path.join(OBJ, f))
+        for f in os.listdir(objdir):
+            os.remove(os.path.join(objdir, f))
     srcs = _sources()
     with ThreadPoolExecutor(max_workers=min(8, len(srcs))) as ex:
-        results = list(ex.map(lambda s: _compile(s, verbose), srcs))
+        results = list(ex.map(lambda s: _compile(s, verbose, objdir, extra), srcs))
     objs = [r[0] for r in results]
     log = "".join(r[1] for r in results)
     if log:
-        with open(os.path.join(OBJ, "ptxas.log"), "a") as f:
+        with open(os.path.join(objdir, "ptxas.log"), "a") as f:
             f.write(log)
         if verbose:
             print(log)
-    if (not os.path.exists(LIB)) or any(os.path.getmtime(o) > os.path.getmtime(LIB) for o in objs):
-        cmd = [NVCC, *ARCH, "-shared", "-o", LIB, *objs, "-cudart", "static"]
+    if (not os.path.exists(lib)) or any(os.path.getmtime(o) > os.path.getmtime(lib) for o in objs):
+        cmd = [NVCC, *ARCH, "-shared", "-o", lib, *objs, "-cudart", "static"]
         p = subprocess.run(cmd, capture_output=True, text=True)
         if p.returncode != 0:
             raise RuntimeError(f"link failed:\n{p.stdout}\n{p.stderr}")
-    return LIB
+    return lib
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv,
+                debug_checks="--debug-checks" in sys.argv))

@@ -6,6 +6,16 @@
 #include <math.h>
 #include "../../include/pxb.h"
 
+// Index / capacity assertions of the kernels: compiled in by `python -m pyxsim_b200.build
+// --debug-checks` (libpxb_dbg.so, loaded with PXB_LIBRARY=...), nothing otherwise.  A failed
+// assertion traps the kernel and surfaces as cudaErrorAssert at the next synchronisation.
+#ifdef PXB_DEBUG_CHECKS
+#include <assert.h>
+#define PXB_DASSERT(c) assert(c)
+#else
+#define PXB_DASSERT(c) ((void)0)
+#endif
+
 #if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
 #error "libpxb is written for sm_100a (B200) only"
 #endif

@@ -68,7 +68,7 @@ struct PipeArgs {
   const int64_t* tabcum;      // general split side array
   int tab_stride;
   int use_staging;
-  int64_t n_cells, n_pairs, n_tiles;
+  int64_t n_cells, n_pairs, n_tiles, n_photons;
   unsigned int* ticket;
   double* energies;           // sample: out; project: in
   double* xsky;
@@ -541,6 +541,7 @@ k_pipeline(const DevModel M, const __grid_constant__ pxb_thermal_cells C,
       int rel;
       int64_t m;
       locate(how, relpack, s_qs, slot0, nslots, c0, c1, m00, r, srel, rel, m);
+      PXB_DASSERT(rel >= 0 && c0 + rel < A.n_cells && (!valid || m >= 0));
       const CellRec* rp = A.recs + (c0 + rel);
       const longlong2 q0 = __ldg(reinterpret_cast<const longlong2*>(rp));
       const longlong2 q1 = __ldg(reinterpret_cast<const longlong2*>(rp) + 1);
@@ -567,7 +568,9 @@ k_pipeline(const DevModel M, const __grid_constant__ pxb_thermal_cells C,
             const bool small = q1.y < 0x7fffffffll;
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
-              const long long dd = (long long)d0 + h;
+              // (a cell's last pair may lack its second photon: that lane half repeats the first
+              // one's look-ups instead of indexing past the cell's components)
+              const long long dd = (long long)d0 + ((h && hasB) ? 1 : 0);
               int comp;
               if (small) {
                 const int d32 = (int)dd;
@@ -602,6 +605,7 @@ k_pipeline(const DevModel M, const __grid_constant__ pxb_thermal_cells C,
               const unsigned dr = (unsigned)(row - tag);
               uint32_t v;
               int j;
+              PXB_DASSERT(tab >= 0 && tab < 2 + C.nvar && row >= 0 && row < tb->nrows);
               if (prim && tab < 2 && tag >= 0 && dr < 2u)   // staged row: shared-memory gather
                 j = alias_pick(s_alias + (unsigned)(tab * 2 + (int)dr) * (unsigned)T.alias_stride,
                                (unsigned)T.nbins, w0, w1, v);
@@ -636,6 +640,7 @@ k_pipeline(const DevModel M, const __grid_constant__ pxb_thermal_cells C,
       if (MODE == MODE_SAMPLE) {
         if (elig) {
           double* dst = A.energies + q1.x + (int64_t)d0;
+          PXB_DASSERT(!valid || (q1.x >= 0 && q1.x + (int64_t)d0 + (hasB ? 1 : 0) < A.n_photons));
           if (hasB && (((uintptr_t)dst) & 15) == 0) {
             asm volatile("st.global.L1::no_allocate.v2.f64 [%0], {%1, %2};" ::"l"(dst), "d"(eA), "d"(eB));
           } else {
@@ -647,6 +652,7 @@ k_pipeline(const DevModel M, const __grid_constant__ pxb_thermal_cells C,
       }
       if (MODE == MODE_PROJECT) {
         const double* src = A.energies + q1.x + (int64_t)d0;
+        PXB_DASSERT(!valid || (q1.x >= 0 && q1.x + (int64_t)d0 + (hasB ? 1 : 0) < A.n_photons));
         if (hasA) eA = ld_stream(src);
         if (hasB) eB = ld_stream(src + 1);
       }
@@ -740,6 +746,7 @@ k_pipeline(const DevModel M, const __grid_constant__ pxb_thermal_cells C,
         else
           scatter_allsky(P, RKP, g, w0, w1, w2, gid, d0 + h, xs, ys, los);
         const int o = o0 + (h && detA ? 1 : 0);
+        PXB_DASSERT(o >= 0 && base + o < A.n_photons && srel < TSLOTS);   // events never outnumber photons
         if (!A.f32) {
           st_stream(xb + o, xs);
           st_stream(yb + o, ys);
@@ -1169,6 +1176,7 @@ extern "C" int pxb_thermal_sample(const pxb_model* model, const pxb_thermal_cell
     A.use_staging = sp.use_staging;
     A.n_cells = n_active;
     A.n_pairs = n_pairs;
+    A.n_photons = n_photons;
     A.n_tiles = lay.ntiles;
     A.ticket = H.ticket;
     A.energies = energies;
@@ -1221,6 +1229,7 @@ static void fill_project_args(PipeArgs& A, char* ws, const PipeLayout& lay, cons
   A.tile_cell = (const int64_t*)(ws + lay.off_tilecell);
   A.n_cells = L->n_cells;
   A.n_pairs = L->n_pairs;
+  A.n_photons = L->n_photons;
   A.n_tiles = lay.ntiles;
   A.ticket = H.ticket;
   A.xsky = xsky;

@@ -217,7 +217,9 @@ __device__ __forceinline__ int alias_pick(const uint2* __restrict__ tab, unsigne
   const uint32_t top = alo + (uint32_t)(b >> 32);        // top 32 bits of the fraction
   const uint32_t j = (uint32_t)(a >> 32) + (top < alo);  // (carry; j stays < nb)
   v = (uint32_t)b;
+  PXB_DASSERT(j < nb);
   const uint2 t = tab[j];
+  PXB_DASSERT(t.y < nb);
   return top < t.x ? (int)j : (int)t.y;
 }
 
@@ -258,6 +260,7 @@ __device__ __forceinline__ double fast_draw(const DevModel& M, const pxb_thermal
       if (u1 >= __ldg(th + mid)) lo = mid + 1; else hi = mid;
     }
     const int r = lo / ntab;
+    PXB_DASSERT(lo >= 0 && lo < nr * ntab && u1 < __ldg(th + lo));
     uint32_t v;
     const int j = alias_pick(alias_row(t, lo - r * ntab, fast_row(t, fc.z1, nr, r)), (unsigned)t->nbins, w0, w1, v);
     return alias_energy<SPEC>(M, j, v);

@@ -359,6 +359,7 @@ __device__ __forceinline__ double sb_eval(const double2* __restrict__ s_c, const
   int lo = __double2int_rd(u);
   if (CLAMP) lo = min(lo, nbins - 1);
   const double t = u - (double)lo;
+  PXB_DASSERT(lo >= 0 && lo + 1 <= nbins);
   const double2 c0 = s_c[lo], c1 = s_c[lo + 1];
   double f0, f1;
   if (ZCONST) {

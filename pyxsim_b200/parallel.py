@@ -39,6 +39,43 @@ def init_from_env(backend=None):
     dist.init_process_group(backend=backend)
 
 
+def bind_host_to_gpu(device_index=None):
+    """Pin this process to the CPUs next to its GPU (NVML's ideal affinity), so that the pinned
+    host buffers it allocates afterwards -- first touch -- and the threads that fill them sit on
+    the GPU's NUMA node.  Best effort: returns what it found and did, never raises.  (On a
+    virtualised host that reports one NUMA node for every GPU this changes nothing.)"""
+    info = {"bound": False}
+    try:
+        import pynvml
+
+        if not torch.cuda.is_available():
+            return info
+        if device_index is None:
+            device_index = torch.cuda.current_device()
+        pynvml.nvmlInit()
+        props = torch.cuda.get_device_properties(device_index)
+        try:
+            h = pynvml.nvmlDeviceGetHandleByUUID(f"GPU-{props.uuid}".encode())
+        except Exception:
+            h = pynvml.nvmlDeviceGetHandleByIndex(device_index)
+        info["cpus_before"] = len(os.sched_getaffinity(0))
+        try:
+            info["numa_node"] = int(pynvml.nvmlDeviceGetNumaNodeId(h))
+        except Exception:
+            bdf = pynvml.nvmlDeviceGetPciInfo(h).busId
+            bdf = (bdf.decode() if isinstance(bdf, bytes) else bdf).lower()[-12:]
+            try:
+                info["numa_node"] = int(open(f"/sys/bus/pci/devices/{bdf}/numa_node").read())
+            except Exception:
+                info["numa_node"] = None
+        pynvml.nvmlDeviceSetCpuAffinity(h)
+        info["cpus_after"] = len(os.sched_getaffinity(0))
+        info["bound"] = True
+    except Exception as e:  # no NVML, no permission, ...: run unbound
+        info["error"] = f"{type(e).__name__}: {e}"[:120]
+    return info
+
+
 def _device():
     if is_initialized() and dist.get_backend() == "nccl":
         return torch.device("cuda", torch.cuda.current_device())

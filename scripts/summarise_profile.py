@@ -71,15 +71,17 @@ def launch_shares(path):
     return agg
 
 
-def source_hot_spots(report, kernel, topn):
-    rows = ncu_csv(report, "source", ["--print-source", "cuda,sass", "--kernel-name", f"regex:{kernel}"])
+def source_hot_spots(report, index, topn):
+    """Source lines of the index-th launch of the report by executed instructions."""
+    rows = ncu_csv(report, "source", ["--print-source", "cuda,sass", "--launch-skip", str(index),
+                                      "--launch-count", "1"])
     cur, hdr, si, ii = None, None, 0, 0
     agg = collections.defaultdict(lambda: [0, 0, ""])
     tot_i = tot_s = 0
     for r in rows:
         if not r:
             continue
-        if r[0] == "File Path":
+        if r[0] in ("File Path", "File Name"):
             cur = r[1].split("/")[-1]
             continue
         if r[0] == "Line No":
@@ -113,8 +115,10 @@ def main():
     ap.add_argument("--command", default="python bench.py --steps 1 --warmup 1 --no-e2e --no-cpu-baseline")
     ap.add_argument("--workload", default='{"grid": 256, "photons": 1e9, "nbins": 4000}')
     ap.add_argument("--top", type=int, default=16)
+    ap.add_argument("--outdir", default=os.path.join(ROOT, "profiles"),
+                    help="where the summaries go (gpurun_out/ when run on the GPU box)")
     args = ap.parse_args()
-    prof = os.path.join(ROOT, "profiles")
+    prof = args.outdir
     if args.launches:
         shutil.copy(args.launches, os.path.join(prof, f"{args.tag}_launches.csv"))
         agg = launch_shares(args.launches)
@@ -153,9 +157,9 @@ def main():
                 ti = hdr.index("gpu__time_duration.sum")
                 traffic["kernels"][name] = {"dram_bytes": rd + wr, "dram_read": rd, "dram_write": wr,
                                             "ms": to_ms(r[ti], units[ti])}
-            for name in names:
+            for j, name in enumerate(names):
                 f.write(f"## source-level hot spots, {name}\n")
-                f.write("\n".join(source_hot_spots(args.report, name.split("<")[0], args.top)) + "\n\n")
+                f.write("\n".join(source_hot_spots(args.report, j, args.top)) + "\n\n")
         with open(os.path.join(prof, f"{args.tag}_traffic.json"), "w") as f:
             json.dump(traffic, f, indent=1)
         print(json.dumps(traffic["kernels"], indent=1))
