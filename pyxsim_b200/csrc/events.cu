@@ -74,6 +74,7 @@ k_event_image(int64_t n, const double* __restrict__ xsky, const double* __restri
     if (!(fx >= 0.0 && fx <= top && fy >= 0.0 && fy <= top)) continue;
     const int ix = fx == top ? nx - 1 : (int)fx;
     const int iy = fy == top ? nx - 1 : (int)fy;
+    PXB_DASSERT(ix >= 0 && ix < nx && iy >= 0 && iy < nx);
     atomicAdd(image + (size_t)iy * nx + ix, 1ull);
   }
 }
@@ -103,6 +104,7 @@ k_event_spectrum(int64_t n, const double* __restrict__ eobs, int nchan,
     // the arithmetic guess can be one off: the stored edges decide (numpy does the same)
     if (e < __ldg(edges + j)) --j;
     else if (j < nchan - 1 && e >= __ldg(edges + j + 1)) ++j;
+    PXB_DASSERT(j >= 0 && j < nchan);
     if (priv) atomicAdd(s_cnt + j, 1u);
     else atomicAdd(counts + j, 1ull);
   }

@@ -194,6 +194,7 @@ __device__ __forceinline__ void rec_set_fast(CellRec& r, const FastCell& fc) {
 // every pair tile that starts inside the cell's slot range starts in this cell
 __device__ __forceinline__ void mark_tiles(int64_t* tile_cell, int64_t qa, int64_t qb, int64_t k,
                                            int tslots) {
+  PXB_DASSERT(qa >= 0 && qb >= qa);
   for (int64_t t = (qa + tslots - 1) / tslots; t * tslots < qb; ++t) tile_cell[t] = k;
 }
 

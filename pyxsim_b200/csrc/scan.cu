@@ -179,6 +179,7 @@ k_compact_cells(int64_t n, const int64_t* __restrict__ counts, const int64_t* __
   const int64_t c = ld_stream_i64(counts + i);
   if (c <= 0) return;
   const int64_t k = arank[i];
+  PXB_DASSERT(k >= 0 && k < arank[n] && offsets[i] + c <= offsets[n]);
   idx_out[k] = i;
   nph_out[k] = c;
   poff_out[k] = offsets[i];
