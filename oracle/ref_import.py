@@ -127,7 +127,9 @@ class FakeH5Group(dict):
         self[name] = g
         return g
 
-    def create_dataset(self, name, data=None, **kw):
+    def create_dataset(self, name, data=None, shape=None, dtype=None, **kw):
+        if data is None and shape is not None:       # (h5py: allocate, filled by slices later)
+            data = np.zeros(shape, dtype=dtype)
         ds = FakeH5Dataset(data)
         self[name] = ds
         return ds

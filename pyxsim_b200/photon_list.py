@@ -69,37 +69,114 @@ def _file_names(prefix):
     return [f"{prefix}.h5"]
 
 
+STREAM_CHUNK_BYTES = 64 << 20     # slab of the chunked device -> host -> file copy
+
+
+def _host_chunks(v, chunk_bytes=None):
+    """The flat array ``v`` as a sequence of contiguous host chunks (NumPy views).  A device
+    tensor is copied slab by slab through two pinned buffers on a side stream: slab k+1 crosses
+    PCIe while the caller writes slab k (the reference writes its lists tile by tile as well,
+    photon_list.py:785-799) -- no pageable host copy of the whole list is ever made."""
+    chunk_bytes = chunk_bytes or STREAM_CHUNK_BYTES
+    if not isinstance(v, torch.Tensor) or not v.is_cuda:
+        a = v.numpy() if isinstance(v, torch.Tensor) else np.ascontiguousarray(v)
+        a = a.reshape(-1)
+        per = max(1, chunk_bytes // max(a.itemsize, 1))
+        for o in range(0, a.size, per):
+            yield a[o:o + per]
+        return
+    t = v.reshape(-1)
+    n = t.numel()
+    per = max(1, chunk_bytes // t.element_size())
+    nchunk = (n + per - 1) // per
+    if nchunk == 0:
+        return
+    bufs = [torch.empty(min(per, n), dtype=t.dtype, pin_memory=True) for _ in range(min(2, nchunk))]
+    evs = [torch.cuda.Event() for _ in bufs]
+    side = torch.cuda.Stream(device=t.device)
+    side.wait_stream(torch.cuda.current_stream(t.device))
+
+    def issue(c):
+        o = c * per
+        m = min(per, n - o)
+        with torch.cuda.stream(side):
+            bufs[c % 2][:m].copy_(t[o:o + m], non_blocking=True)
+            evs[c % 2].record(side)
+        return m
+
+    m_next = issue(0)
+    for c in range(nchunk):
+        m = m_next
+        if c + 1 < nchunk:
+            m_next = issue(c + 1)      # its buffer was consumed (written out) one iteration ago
+        evs[c % 2].synchronize()
+        yield bufs[c % 2][:m].numpy()
+    t.record_stream(side)
+
+
+def _np_dtype(v):
+    if isinstance(v, torch.Tensor):
+        return np.dtype(str(v.dtype).replace("torch.", ""))
+    return np.asarray(v).dtype
+
+
+def _write_npy_member(zf, name, v):
+    """One uncompressed ``.npy`` member of an ``.npz`` archive, streamed chunk by chunk."""
+    if isinstance(v, torch.Tensor) and v.dim() != 1:
+        v = v.cpu().numpy()
+    if isinstance(v, torch.Tensor) or (isinstance(v, np.ndarray) and v.ndim == 1 and v.dtype.kind in "fiu"):
+        n = int(v.numel() if isinstance(v, torch.Tensor) else v.size)
+        hdr = {"descr": np.lib.format.dtype_to_descr(_np_dtype(v)), "fortran_order": False, "shape": (n,)}
+        with zf.open(name + ".npy", "w", force_zip64=True) as f:
+            np.lib.format.write_array_header_2_0(f, hdr)
+            for chunk in _host_chunks(v):
+                f.write(memoryview(chunk).cast("B"))
+    else:
+        with zf.open(name + ".npy", "w", force_zip64=True) as f:
+            np.lib.format.write_array(f, np.asarray(v), allow_pickle=False)
+
+
 def save_list(prefix, lst):
-    """Write a list under ``prefix`` (``mem:`` -> HBM registry, else ``.h5`` / ``.npz``)."""
+    """Write a list under ``prefix`` (``mem:`` -> HBM registry, else ``.h5`` / ``.npz``).  The
+    data arrays go from the device to the file in slabs (``_host_chunks``), the download of one
+    overlapping the write of the previous."""
     if prefix.startswith("mem:"):
         _MEMORY[_file_name(prefix)] = lst
         return _file_name(prefix)
-    host = lst.to_host()
     base = _file_name(prefix)
     if h5py is not None:
         fn = base + ".h5"
         with h5py.File(fn, "w") as f:
             g = f.create_group("info")
-            for k, v in host.info.items():
+            for k, v in lst.info.items():
                 g.attrs[k] = v
             p = f.create_group("parameters")
-            for k, v in host.parameters.items():
+            for k, v in lst.parameters.items():
                 if isinstance(v, np.ndarray) and v.dtype.kind == "U":
                     v = v.astype("S")      # h5py cannot store NumPy unicode arrays
                 p.create_dataset(k, data=v)
             d = f.create_group("data")
-            for k, v in host.data.items():
-                d.create_dataset(k, data=v)
+            for k, v in lst.data.items():
+                if (v.dim() if isinstance(v, torch.Tensor) else np.ndim(v)) != 1:
+                    d.create_dataset(k, data=v.cpu().numpy() if isinstance(v, torch.Tensor) else np.asarray(v))
+                    continue
+                n = int(v.numel() if isinstance(v, torch.Tensor) else np.asarray(v).size)
+                ds = d.create_dataset(k, shape=(n,), dtype=_np_dtype(v))
+                o = 0
+                for chunk in _host_chunks(v):
+                    ds[o:o + chunk.size] = chunk
+                    o += chunk.size
         return fn
+    import zipfile
+
     fn = base + ".npz"
-    flat = {}
-    for k, v in host.info.items():
-        flat[f"info/{k}"] = np.asarray(v)
-    for k, v in host.parameters.items():
-        flat[f"parameters/{k}"] = np.asarray(v)
-    for k, v in host.data.items():
-        flat[f"data/{k}"] = v
-    np.savez(fn, **flat)
+    with zipfile.ZipFile(fn, "w", zipfile.ZIP_STORED, allowZip64=True) as zf:
+        for k, v in lst.info.items():
+            _write_npy_member(zf, f"info/{k}", np.asarray(v))
+        for k, v in lst.parameters.items():
+            _write_npy_member(zf, f"parameters/{k}", np.asarray(v))
+        for k, v in lst.data.items():
+            _write_npy_member(zf, f"data/{k}", v)
     return fn
 
 

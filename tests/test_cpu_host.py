@@ -247,3 +247,38 @@ def test_fits_writer_roundtrip_and_merge_validation(tmp_path):
     with pytest.raises(RuntimeError):
         E.validate_parameters(p, dict(p, extra=1))
     E.validate_parameters(p, dict(p, area=2.0 + 1e-12))
+
+
+def test_save_list_streams_arrays_in_slabs(tmp_path, monkeypatch):
+    """save_list writes every data array slab by slab (``_host_chunks``) into an uncompressed
+    ``.npz`` member -- no whole-list host copy -- and np.load / load_list read it back unchanged:
+    several slabs per array, a ragged last slab, an empty array, int64 / float32 / float64, string
+    and byte-string parameters."""
+    import torch
+
+    import pyxsim_b200.photon_list as PL
+
+    monkeypatch.setattr(PL, "STREAM_CHUNK_BYTES", 1000)
+    monkeypatch.setattr(PL, "h5py", None)
+    rng = np.random.RandomState(3)
+    data = {"energy": torch.from_numpy(rng.uniform(0.1, 10.0, 1237)),
+            "num_photons": rng.randint(0, 50, 300).astype(np.int64),
+            "x": torch.from_numpy(rng.normal(size=300).astype(np.float32)),
+            "empty": torch.empty(0, dtype=torch.float64)}
+    lst = PL.DeviceList({"data_source": "test", "version": 2},
+                        {"fid_exp_time": 1.0e5, "observer": "external",
+                         "velocity_fields": np.array([["gas", "velocity_x"], ["gas", "velocity_y"]]).astype("S")},
+                        data)
+    fn = PL.save_list(str(tmp_path / "lst"), lst)
+    assert fn.endswith(".npz")
+    z = np.load(fn, allow_pickle=False)
+    for k, v in data.items():
+        want = v.numpy() if isinstance(v, torch.Tensor) else v
+        got = z[f"data/{k}"]
+        assert got.dtype == want.dtype and np.array_equal(got, want), k
+    back = PL.load_list(str(tmp_path / "lst"))
+    assert back.parameters["observer"] == "external" and float(back.parameters["fid_exp_time"]) == 1.0e5
+    assert back.parameters["velocity_fields"].shape == (2, 2) and back.info["data_source"] == "test"
+    # chunk generator: sizes and order
+    sizes = [c.size for c in PL._host_chunks(data["energy"], 1000)]
+    assert sizes == [125] * 9 + [112] and sum(sizes) == 1237

@@ -203,6 +203,41 @@ def test_h5py_roundtrip_when_available(cuda, tmp_path):
     assert n == px.load_list(str(tmp_path / "p")).numpy("energy").size
 
 
+def test_lists_stream_from_the_device_to_the_file(cuda, tmp_path, monkeypatch):
+    """File-backed lists are written slab by slab from HBM through two pinned buffers (the download
+    of one slab overlapping the write of the previous): same file contents as the in-memory list,
+    whatever the slab size; the file-backed two-stage run gives the in-memory run's events."""
+    import pyxsim_b200.photon_list as PL
+    from pyxsim_b200 import synthetic
+
+    monkeypatch.setattr(PL, "STREAM_CHUNK_BYTES", 40000)        # many slabs, ragged last one
+    kT_nodes, ebins, cosmic, metal, _ = synthetic.apec_like_tables(nT=36, nbins=300)
+    src = synthetic.beta_model_source(12, kT_range=(2.0, 8.0), device="cuda")
+    sm = px.ThermalSpectralModel(ebins, kT_nodes, cosmic, metal)
+
+    def model():
+        return px.ThermalSourceModel(sm, 0.1, 10.0, 300, 0.3, temperature_field=("gas", "kT"), prng=4)
+
+    n_mem = px.make_photons("mem:st_ph", src, 0.05, 3.0e4, 1.0e5, model())
+    n_fil = px.make_photons(str(tmp_path / "st_ph"), src, 0.05, 3.0e4, 1.0e5, model())
+    assert n_mem == n_fil and n_mem[0] > 20 * 40000 // 8
+    a, b = px.load_list("mem:st_ph"), px.load_list(str(tmp_path / "st_ph"))
+    assert set(a.data) == set(b.data)
+    for k in a.data:
+        assert np.array_equal(a.numpy(k), b.numpy(k)), k
+    e_mem = px.project_photons("mem:st_ph", "mem:st_ev", "z", [30.0, 45.0], absorb_model="wabs", nH=0.02, prng=5)
+    e_fil = px.project_photons(str(tmp_path / "st_ph"), str(tmp_path / "st_ev"), "z", [30.0, 45.0],
+                               absorb_model="wabs", nH=0.02, prng=5)
+    assert e_mem == e_fil > 0
+    a, b = px.load_list("mem:st_ev"), px.load_list(str(tmp_path / "st_ev"))
+    for k in ("xsky", "ysky", "eobs"):
+        assert np.array_equal(a.numpy(k), b.numpy(k)), k
+    # the chunk generator on a device tensor: order, sizes, values
+    t = torch.arange(100001, dtype=torch.float64, device="cuda")
+    got = np.concatenate([c.copy() for c in PL._host_chunks(t, 8 * 1000)])
+    assert np.array_equal(got, np.arange(100001.0))
+
+
 def test_region_filters(cuda):
     d, p = _events(n=60000, name="ev_flt", seed=8)
     ev = px.EventList("mem:ev_flt")
