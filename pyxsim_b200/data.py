@@ -191,7 +191,7 @@ class ArrayDataSource:
                  right_edge=None, center=None, position_fields=None, velocity_fields=None,
                  width_field="default", units=None, chunk_size=None, cosmology=None,
                  name="ArrayDataSource", ftype="gas", rank_local=False, global_offset=0,
-                 shard_block=4096, shard_of=None):
+                 shard_block=256, shard_of=None):
         self.fields = dict(fields)
         self.units = dict(units or {})
         self.data_type = data_type

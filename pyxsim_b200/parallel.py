@@ -112,9 +112,12 @@ def barrier():
         dist.barrier()
 
 
-def shard_bounds(n, block=4096, r=None, s=None):
+def shard_bounds(n, block=256, r=None, s=None):
     """Block-cyclic ownership of ``n`` cells: rank r owns blocks r, r+s, r+2s ...  Returns the
-    list of (start, stop) ranges; photon-rich core cells are spread over all ranks."""
+    list of (start, stop) ranges; photon-rich core cells are spread over all ranks.  Small
+    blocks on purpose: a block that spans many rows of a uniform grid turns into thick slabs, and
+    ``s`` slabs per period can put a cluster core on two ranks (4096-cell blocks of a 256^3 grid
+    on 4 GPUs: 37.7 ms per step instead of 26.4)."""
     r = rank() if r is None else r
     s = size() if s is None else s
     nblocks = (n + block - 1) // block
