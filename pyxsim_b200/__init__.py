@@ -19,6 +19,8 @@ from .photon_list import (
     make_photons,
     project_photons,
     project_photons_allsky,
+    set_async_writes,
+    wait_for_writes,
 )
 from .source_models import (
     CIESourceModel,

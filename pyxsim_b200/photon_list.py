@@ -10,8 +10,10 @@ written as HDF5 when h5py is importable and as ``.npz`` archives with the same k
 otherwise; a prefix that starts with ``"mem:"`` keeps the list resident in HBM, which is how
 stage 1 hands over to stage 2 without leaving the device.
 """
+import atexit
 import ctypes as C
 import os
+import threading
 
 import numpy as np
 import torch
@@ -72,7 +74,7 @@ def _file_names(prefix):
 STREAM_CHUNK_BYTES = 64 << 20     # slab of the chunked device -> host -> file copy
 
 
-def _host_chunks(v, chunk_bytes=None):
+def _host_chunks(v, chunk_bytes=None, ready=None):
     """The flat array ``v`` as a sequence of contiguous host chunks (NumPy views).  A device
     tensor is copied slab by slab through two pinned buffers on a side stream: slab k+1 crosses
     PCIe while the caller writes slab k (the reference writes its lists tile by tile as well,
@@ -94,7 +96,10 @@ def _host_chunks(v, chunk_bytes=None):
     bufs = [torch.empty(min(per, n), dtype=t.dtype, pin_memory=True) for _ in range(min(2, nchunk))]
     evs = [torch.cuda.Event() for _ in bufs]
     side = torch.cuda.Stream(device=t.device)
-    side.wait_stream(torch.cuda.current_stream(t.device))
+    if ready is not None:        # (a background writer: the event its producer recorded)
+        side.wait_event(ready)
+    else:
+        side.wait_stream(torch.cuda.current_stream(t.device))
 
     def issue(c):
         o = c * per
@@ -120,7 +125,7 @@ def _np_dtype(v):
     return np.asarray(v).dtype
 
 
-def _write_npy_member(zf, name, v):
+def _write_npy_member(zf, name, v, ready=None):
     """One uncompressed ``.npy`` member of an ``.npz`` archive, streamed chunk by chunk."""
     if isinstance(v, torch.Tensor) and v.dim() != 1:
         v = v.cpu().numpy()
@@ -129,21 +134,93 @@ def _write_npy_member(zf, name, v):
         hdr = {"descr": np.lib.format.dtype_to_descr(_np_dtype(v)), "fortran_order": False, "shape": (n,)}
         with zf.open(name + ".npy", "w", force_zip64=True) as f:
             np.lib.format.write_array_header_2_0(f, hdr)
-            for chunk in _host_chunks(v):
+            for chunk in _host_chunks(v, ready=ready):
                 f.write(memoryview(chunk).cast("B"))
     else:
         with zf.open(name + ".npy", "w", force_zip64=True) as f:
             np.lib.format.write_array(f, np.asarray(v), allow_pickle=False)
 
 
+_PENDING = {}          # file base -> _BackgroundWrite of a list still on its way to the disk
+ASYNC_WRITES = bool(os.environ.get("PXB_ASYNC_WRITES"))
+
+
+class _BackgroundWrite(threading.Thread):
+    """Writer thread of one list: streams the arrays from HBM to the file while the caller goes
+    on (the next stage reads the list from HBM, see load_list).  Errors surface in wait()."""
+
+    def __init__(self, base, lst, ready):
+        super().__init__(daemon=False, name=f"pxb-writer:{base}")
+        self.base, self.lst, self.ready, self.error, self.file = base, lst, ready, None, None
+        self.device = torch.cuda.current_device() if torch.cuda.is_available() else None
+
+    def run(self):
+        try:
+            if self.device is not None:
+                torch.cuda.set_device(self.device)      # (a new thread starts on device 0)
+            self.file = _write_file(self.base, self.lst, self.ready)
+        except BaseException as e:  # noqa: BLE001 - re-raised in wait()
+            self.error = e
+
+    def wait(self):
+        self.join()
+        if self.error is not None:
+            raise self.error
+        return self.file
+
+
+def set_async_writes(flag=True):
+    """Write file-backed lists in the background: ``make_photons`` / ``project_photons`` return
+    as soon as the list is complete in HBM, a writer thread streams it to the file, and a later
+    stage given the same prefix reads the list from HBM instead of from the file.
+    ``wait_for_writes()`` (also run at interpreter exit) joins the writers and re-raises their
+    errors.  Off by default: the reference returns with its files complete."""
+    global ASYNC_WRITES
+    ASYNC_WRITES = bool(flag)
+    if not flag:
+        wait_for_writes()
+
+
+def wait_for_writes(prefix=None):
+    """Block until the background write of ``prefix`` (default: all of them) is on the disk."""
+    keys = list(_PENDING) if prefix is None else [k for k in (_file_name(_strip(prefix)),) if k in _PENDING]
+    err = None
+    for k in keys:
+        w = _PENDING.pop(k)
+        try:
+            w.wait()
+        except BaseException as e:  # noqa: BLE001
+            err = err or e
+    if err is not None:
+        raise err
+
+
+atexit.register(wait_for_writes)
+
+
 def save_list(prefix, lst):
     """Write a list under ``prefix`` (``mem:`` -> HBM registry, else ``.h5`` / ``.npz``).  The
     data arrays go from the device to the file in slabs (``_host_chunks``), the download of one
-    overlapping the write of the previous."""
+    overlapping the write of the previous; with ``set_async_writes`` a writer thread does it
+    while the caller continues."""
     if prefix.startswith("mem:"):
         _MEMORY[_file_name(prefix)] = lst
         return _file_name(prefix)
     base = _file_name(prefix)
+    wait_for_writes(prefix)                 # (the same name written twice: in order)
+    if not ASYNC_WRITES:
+        return _write_file(base, lst, None)
+    ready = None
+    if torch.cuda.is_available() and any(isinstance(v, torch.Tensor) and v.is_cuda for v in lst.data.values()):
+        ready = torch.cuda.Event()
+        ready.record()
+    w = _BackgroundWrite(base, lst, ready)
+    _PENDING[base] = w
+    w.start()
+    return base + (".h5" if h5py is not None else ".npz")
+
+
+def _write_file(base, lst, ready):
     if h5py is not None:
         fn = base + ".h5"
         with h5py.File(fn, "w") as f:
@@ -163,7 +240,7 @@ def save_list(prefix, lst):
                 n = int(v.numel() if isinstance(v, torch.Tensor) else np.asarray(v).size)
                 ds = d.create_dataset(k, shape=(n,), dtype=_np_dtype(v))
                 o = 0
-                for chunk in _host_chunks(v):
+                for chunk in _host_chunks(v, ready=ready):
                     ds[o:o + chunk.size] = chunk
                     o += chunk.size
         return fn
@@ -176,7 +253,7 @@ def save_list(prefix, lst):
         for k, v in lst.parameters.items():
             _write_npy_member(zf, f"parameters/{k}", np.asarray(v))
         for k, v in lst.data.items():
-            _write_npy_member(zf, f"data/{k}", v)
+            _write_npy_member(zf, f"data/{k}", v, ready)
     return fn
 
 
@@ -187,6 +264,8 @@ def load_list(prefix):
             raise FileNotFoundError(f"no in-memory list named {key!r}")
         return _MEMORY[key]
     base = _file_name(prefix)
+    if base in _PENDING:                    # still being written: the list is in HBM
+        return _PENDING[base].lst
     if h5py is not None and os.path.exists(base + ".h5"):
         with h5py.File(base + ".h5", "r") as f:
             info = dict(f["info"].attrs)

@@ -282,3 +282,34 @@ def test_save_list_streams_arrays_in_slabs(tmp_path, monkeypatch):
     # chunk generator: sizes and order
     sizes = [c.size for c in PL._host_chunks(data["energy"], 1000)]
     assert sizes == [125] * 9 + [112] and sum(sizes) == 1237
+
+
+def test_background_list_writer(tmp_path, monkeypatch):
+    """set_async_writes(True): save_list returns at once, a writer thread streams the list to the
+    file, load_list of the same prefix hands back the in-memory list while the file is pending,
+    wait_for_writes() joins (and re-raises a writer's error), and the file then holds the list."""
+    import torch
+
+    import pyxsim_b200 as px
+    import pyxsim_b200.photon_list as PL
+
+    monkeypatch.setattr(PL, "h5py", None)
+    monkeypatch.setattr(PL, "STREAM_CHUNK_BYTES", 4096)
+    e = torch.arange(50000, dtype=torch.float64)
+    lst = PL.DeviceList({"k": 1}, {"fid_exp_time": 2.0}, {"energy": e, "num_photons": np.arange(10)})
+    px.set_async_writes(True)
+    try:
+        fn = PL.save_list(str(tmp_path / "bg"), lst)
+        assert fn.endswith("bg.npz")
+        assert PL.load_list(str(tmp_path / "bg")) is lst or os.path.exists(fn)   # pending -> the same object
+        px.wait_for_writes()
+        assert not PL._PENDING
+        back = PL.load_list(str(tmp_path / "bg"))
+        assert back is not lst and np.array_equal(back.data["energy"], e.numpy())
+        # an error in the writer (unwritable path) surfaces at wait_for_writes
+        PL.save_list(str(tmp_path / "no_such_dir" / "x"), lst)
+        with pytest.raises(OSError):
+            px.wait_for_writes()
+    finally:
+        px.set_async_writes(False)
+    assert not PL.ASYNC_WRITES

@@ -232,6 +232,23 @@ def test_lists_stream_from_the_device_to_the_file(cuda, tmp_path, monkeypatch):
     a, b = px.load_list("mem:st_ev"), px.load_list(str(tmp_path / "st_ev"))
     for k in ("xsky", "ysky", "eobs"):
         assert np.array_equal(a.numpy(k), b.numpy(k)), k
+    # background writer: both stages return while their files are still being written, stage 2
+    # takes the pending photon list from HBM, and the files end up identical to the synchronous ones
+    px.set_async_writes(True)
+    try:
+        n_bg = px.make_photons(str(tmp_path / "bg_ph"), src, 0.05, 3.0e4, 1.0e5, model())
+        e_bg = px.project_photons(str(tmp_path / "bg_ph"), str(tmp_path / "bg_ev"), "z", [30.0, 45.0],
+                                  absorb_model="wabs", nH=0.02, prng=5)
+        px.wait_for_writes()
+    finally:
+        px.set_async_writes(False)
+    assert n_bg == n_mem and e_bg == e_mem
+    for name, ref, keys in (("bg_ph", "st_ph", ("energy", "num_photons", "x", "cell_id")),
+                            ("bg_ev", "st_ev", ("xsky", "ysky", "eobs"))):
+        a, b = px.load_list(str(tmp_path / name)), px.load_list(str(tmp_path / ref))
+        assert isinstance(a.data[keys[0]], np.ndarray)          # read back from the file
+        for k in keys:
+            assert np.array_equal(a.numpy(k), b.numpy(k)), (name, k)
     # the chunk generator on a device tensor: order, sizes, values
     t = torch.arange(100001, dtype=torch.float64, device="cuda")
     got = np.concatenate([c.copy() for c in PL._host_chunks(t, 8 * 1000)])
