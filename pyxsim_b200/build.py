@@ -43,12 +43,16 @@ def _compile(src, verbose, objdir=OBJ, extra=()):
     return obj, p.stderr
 
 
-def build(force=False, verbose=False, debug_checks=False):
+def build(force=False, verbose=False, debug_checks=False, variant=None, defines=()):
     """debug_checks: the same library with the kernels' index assertions compiled in
-    (-DPXB_DEBUG_CHECKS), as pyxsim_b200/libpxb_dbg.so; load it with PXB_LIBRARY=<path>."""
-    objdir = OBJ + "_dbg" if debug_checks else OBJ
-    lib = LIB.replace("libpxb.so", "libpxb_dbg.so") if debug_checks else LIB
-    extra = ("-DPXB_DEBUG_CHECKS",) if debug_checks else ()
+    (-DPXB_DEBUG_CHECKS), as pyxsim_b200/libpxb_dbg.so; load it with PXB_LIBRARY=<path>.
+    variant / defines: an A/B build of the same sources with extra -D flags, as
+    pyxsim_b200/libpxb_<variant>.so (``--variant r2 -DPXB_PROJ_ROUNDS=2``)."""
+    if debug_checks:
+        variant, defines = "dbg", ("-DPXB_DEBUG_CHECKS",) + tuple(defines)
+    objdir = OBJ + "_" + variant if variant else OBJ
+    lib = LIB.replace("libpxb.so", f"libpxb_{variant}.so") if variant else LIB
+    extra = tuple(defines)
     os.makedirs(objdir, exist_ok=True)
     if force:
         for f in os.listdir(objdir):
@@ -72,5 +76,7 @@ def build(force=False, verbose=False, debug_checks=False):
 
 
 if __name__ == "__main__":
+    _variant = sys.argv[sys.argv.index("--variant") + 1] if "--variant" in sys.argv else None
     print(build(force="--force" in sys.argv, verbose="-v" in sys.argv,
-                debug_checks="--debug-checks" in sys.argv))
+                debug_checks="--debug-checks" in sys.argv, variant=_variant,
+                defines=[a for a in sys.argv if a.startswith("-D")]))

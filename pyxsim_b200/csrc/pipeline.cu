@@ -37,10 +37,16 @@ constexpr int PL_EPOCH = 16;                       // tiles per warp between two
 // between rounds and takes 128-slot tiles; the modes that project keep a tile's energies in
 // shared memory from the absorption decisions to the scatter step, DOUBLE buffered (a tile whose
 // predecessors have not all reported yet is finished after the next tile's decisions instead of
-// waiting), so their tiles are 64 slots.
+// waiting): 2 x 2 KB per warp at 128 slots.  (PXB_PROJ_ROUNDS = 2 builds the 64-slot tiles of the
+// first version: every per-tile cost -- ticket, barriers, cell starts, statistics -- is paid twice
+// as often.)
+#ifndef PXB_PROJ_ROUNDS
+#define PXB_PROJ_ROUNDS 4
+#endif
+static_assert(PXB_PROJ_ROUNDS >= 1 && PXB_PROJ_ROUNDS <= 4, "one byte per round in a 32-bit word");
 template <int MODE>
 struct Tiling {
-  static constexpr int ROUNDS = MODE == 0 ? 4 : 2;
+  static constexpr int ROUNDS = MODE == 0 ? 4 : PXB_PROJ_ROUNDS;
   static constexpr int TSLOTS = 32 * ROUNDS;       // pair slots per warp tile
   static constexpr int MAXC = TSLOTS + 4;          // cell starts staged per tile
   static constexpr int NBUF = MODE == 0 ? 1 : 2;
@@ -474,7 +480,7 @@ k_pipeline(const DevModel M, const __grid_constant__ pxb_thermal_cells C,
   // ---- a tile's decisions: energies (sampled or loaded), Doppler shift, absorption -------------
   // (writes the tile's energies and cell starts into buffer `buf`; returns its survivor count and
   // the per-lane survivor bits / cell bytes the scatter step needs)
-  auto decide = [&](int64_t tile, int buf, int& run, int& how, unsigned& bits) {
+  auto decide = [&](int64_t tile, int buf, int& run, int& how, unsigned& bits, unsigned& rels) {
     double* const s_e = reinterpret_cast<double*>(dyn + se_off + (unsigned)buf * (unsigned)(2 * TSLOTS * sizeof(double)));
     int* const s_qs = reinterpret_cast<int*>(dyn + qs_off + (unsigned)buf * (unsigned)(MAXC * sizeof(int)));
     const int64_t slot0 = tile * TSLOTS;
@@ -518,7 +524,7 @@ k_pipeline(const DevModel M, const __grid_constant__ pxb_thermal_cells C,
           cnt += (unsigned)(__popc(before) + __popc(mask & ((2u << lane) - 1u))) << (8 * r);
         }
       }
-      relpack = cnt - (ROUNDS == 4 ? 0x01010101u : 0x00000101u);   // (every byte is >= 1)
+      relpack = cnt - (0x01010101u >> (8 * (4 - ROUNDS)));   // (every byte in use is >= 1)
     } else if (how == 1) {
 #pragma unroll
       for (int r = 0; r < ROUNDS; ++r) {
@@ -552,6 +558,9 @@ k_pipeline(const DevModel M, const __grid_constant__ pxb_thermal_cells C,
       const bool hasB = valid && (int64_t)(d0 + 1) < q1.y;
       double eA = 0.0, eB = 0.0;
       bool elig = true;
+      // photon counts below 2^31 in every cell of the round (any cell in practice): 32-bit
+      // compares -- decided for the whole warp, so the 64-bit path is a branch not taken
+      const bool small = MODE != MODE_PROJECT && __all_sync(0xffffffffu, q1.y < 0x7fffffffll);
       if (MODE != MODE_PROJECT) {
         const longlong2 q2 = __ldg(reinterpret_cast<const longlong2*>(rp) + 2);
         const longlong2 q3 = __ldg(reinterpret_cast<const longlong2*>(rp) + 3);
@@ -565,8 +574,6 @@ k_pipeline(const DevModel M, const __grid_constant__ pxb_thermal_cells C,
             const bool prim = SPEC != 0 || !(meta & 8);
             const DevTable* tb = prim ? &M.prim : &M.fb;
             const bool four = SPEC != 0 || (meta & 32);
-            // counts below 2^31: 32-bit compares (any cell in practice)
-            const bool small = q1.y < 0x7fffffffll;
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
               // (a cell's last pair may lack its second photon: that lane half repeats the first
@@ -608,10 +615,10 @@ k_pipeline(const DevModel M, const __grid_constant__ pxb_thermal_cells C,
               int j;
               PXB_DASSERT(tab >= 0 && tab < 2 + C.nvar && row >= 0 && row < tb->nrows);
               if (prim && tab < 2 && tag >= 0 && dr < 2u)   // staged row: shared-memory gather
-                j = alias_pick(s_alias + (unsigned)(tab * 2 + (int)dr) * (unsigned)T.alias_stride,
+                j = alias_pick(s_alias, (unsigned)(tab * 2 + (int)dr) * (unsigned)T.alias_stride,
                                (unsigned)T.nbins, w0, w1, v);
               else
-                j = alias_pick(alias_row(tb, tab, row), (unsigned)T.nbins, w0, w1, v);
+                j = alias_pick(tb->alias, alias_row_index(tb, tab, row), (unsigned)T.nbins, w0, w1, v);
               const double e = alias_energy<(SPEC != 0) ? 1 : 0>(M, j, v);
               if (h) eB = e; else eA = e;
             }
@@ -693,12 +700,13 @@ k_pipeline(const DevModel M, const __grid_constant__ pxb_thermal_cells C,
         A.part_min[tile] = tmin;
         A.part_max[tile] = tmax;
       }
-      bits = detpack | (relpack << 8);
+      bits = detpack;
+      rels = relpack;
     }
   };
 
   // ---- a tile's scatter step: survivors -> their final, order-preserving slots ------------------
-  auto scatter = [&](int64_t ptile, int pbuf, int64_t base, int phow, unsigned pend_bits) {
+  auto scatter = [&](int64_t ptile, int pbuf, int64_t base, int phow, unsigned detpack, unsigned relpack) {
     const double* const s_e = reinterpret_cast<const double*>(dyn + se_off + (unsigned)pbuf * (unsigned)(2 * TSLOTS * sizeof(double)));
     const int* const s_qs = reinterpret_cast<const int*>(dyn + qs_off + (unsigned)pbuf * (unsigned)(MAXC * sizeof(int)));
     const int64_t slot0 = ptile * TSLOTS;
@@ -706,7 +714,6 @@ k_pipeline(const DevModel M, const __grid_constant__ pxb_thermal_cells C,
     const int64_t c0 = __ldg(A.tile_cell + ptile);
     const int64_t c1 = (ptile + 1 < A.n_tiles) ? __ldg(A.tile_cell + ptile + 1) : A.n_cells - 1;
     const int64_t m00 = slot0 - __ldg(A.qoff + c0);
-    const unsigned detpack = pend_bits & 255u, relpack = pend_bits >> 8;
     // (tile-uniform 64-bit bases, 32-bit offsets inside the tile; float events: half the bytes)
     const int64_t ob = A.f32 ? base / 2 : base;         // (float arrays: base counts 4-byte slots)
     double* const xb = A.xsky + ob;
@@ -816,8 +823,8 @@ k_pipeline(const DevModel M, const __grid_constant__ pxb_thermal_cells C,
         continue;
       }
       int run = 0, how = 0;
-      unsigned bits = 0;
-      decide(tile, 0, run, how, bits);
+      unsigned bits = 0, rels = 0;
+      decide(tile, 0, run, how, bits, rels);
     }
     return;
   }
@@ -833,7 +840,7 @@ k_pipeline(const DevModel M, const __grid_constant__ pxb_thermal_cells C,
   // otherwise let some warps starve while everybody waits for their tiles).
   int buf = 0;
   bool have_pend = false;      // this warp's tile of the previous batch still has its scatter step due
-  unsigned pend_bits = 0;
+  unsigned pend_bits = 0, pend_rels = 0;
   int pend_how = 0;
   bool lbdone = true, cta_out = false, pend_batch = false;
   for (int it = 0;; ++it) {
@@ -845,8 +852,8 @@ k_pipeline(const DevModel M, const __grid_constant__ pxb_thermal_cells C,
     const int64_t tile = batch * WARPS + wid;
     const bool have_new = !cta_out && tile < A.n_tiles;
     int run = 0, how = 0;
-    unsigned bits = 0;
-    if (have_new) decide(tile, buf, run, how, bits);
+    unsigned bits = 0, rels = 0;
+    if (have_new) decide(tile, buf, run, how, bits, rels);
     if (lane == 0) s_cnt[buf][wid] = run;
     if (wid == 0 && pend_batch && !lbdone) {
       // the pending batch's prefix, for good now: it has had a whole batch's time
@@ -888,12 +895,13 @@ k_pipeline(const DevModel M, const __grid_constant__ pxb_thermal_cells C,
       const int64_t ptile = s_batch[buf ^ 1] * WARPS + wid;
       const int64_t base = s_base[buf ^ 1] + before;
       if (ptile == A.n_tiles - 1 && lane == 0) *A.n_events = base + mine;
-      if (mine > 0) scatter(ptile, buf ^ 1, base, pend_how, pend_bits);
+      if (mine > 0) scatter(ptile, buf ^ 1, base, pend_how, pend_bits, pend_rels);
     }
     if (cta_out) break;          // nothing new was decided: the batch just scattered was the last
     have_pend = have_new;
     pend_batch = true;
     pend_bits = bits;
+    pend_rels = rels;
     pend_how = how;
     buf ^= 1;
   }

@@ -209,8 +209,9 @@ __device__ __forceinline__ FastCell fast_setup(const DevModel& M, const pxb_ther
 // ---- sampling a table row through its alias table ---------------------------------------
 // (w0, w1): 64 random bits.  Returns the bin; v receives 32 uniform bits for the position inside
 // it.  u nb = j + frac with u = (w0 2^32 + w1) / 2^64: two 32x32->64 multiplies and a carry.
-__device__ __forceinline__ int alias_pick(const uint2* __restrict__ tab, unsigned nb, uint32_t w0,
-                                          uint32_t w1, uint32_t& v) {
+// The row is entries [off, off + nb) of tab (one 32-bit index, one scaled address).
+__device__ __forceinline__ int alias_pick(const uint2* __restrict__ tab, unsigned off, unsigned nb,
+                                          uint32_t w0, uint32_t w1, uint32_t& v) {
   const unsigned long long a = (unsigned long long)w0 * nb;
   const unsigned long long b = (unsigned long long)w1 * nb;
   const uint32_t alo = (uint32_t)a;
@@ -218,7 +219,7 @@ __device__ __forceinline__ int alias_pick(const uint2* __restrict__ tab, unsigne
   const uint32_t j = (uint32_t)(a >> 32) + (top < alo);  // (carry; j stays < nb)
   v = (uint32_t)b;
   PXB_DASSERT(j < nb);
-  const uint2 t = tab[j];
+  const uint2 t = tab[off + j];
   PXB_DASSERT(t.y < nb);
   return top < t.x ? (int)j : (int)t.y;
 }
@@ -238,9 +239,14 @@ __device__ __forceinline__ double alias_energy(const DevModel& M, int j, uint32_
   return e0 + ((double)v * 2.3283064365386963e-10) * (e1 - e0);
 }
 
-// global-memory alias row of (table, row)
+// global-memory alias row of (table, row).  (32-bit element index: the whole table set has fewer
+// than 2^31 entries, checked when the model is uploaded -- one multiply-add instead of 64-bit
+// address arithmetic per photon)
+__device__ __forceinline__ unsigned alias_row_index(const DevTable* t, int tab, int row) {
+  return (unsigned)(tab * t->nrows + row) * (unsigned)t->alias_stride;
+}
 __device__ __forceinline__ const uint2* alias_row(const DevTable* t, int tab, int row) {
-  return t->alias + ((size_t)tab * t->nrows + row) * (size_t)t->alias_stride;
+  return t->alias + alias_row_index(t, tab, row);
 }
 
 // probability mode (no split): the photon picks its component with u1, then samples that row
@@ -262,7 +268,7 @@ __device__ __forceinline__ double fast_draw(const DevModel& M, const pxb_thermal
     const int r = lo / ntab;
     PXB_DASSERT(lo >= 0 && lo < nr * ntab && u1 < __ldg(th + lo));
     uint32_t v;
-    const int j = alias_pick(alias_row(t, lo - r * ntab, fast_row(t, fc.z1, nr, r)), (unsigned)t->nbins, w0, w1, v);
+    const int j = alias_pick(t->alias, alias_row_index(t, lo - r * ntab, fast_row(t, fc.z1, nr, r)), (unsigned)t->nbins, w0, w1, v);
     return alias_energy<SPEC>(M, j, v);
   }
   int r = (u1 >= fc.cum[0]) + (u1 >= fc.cum[1]) + (u1 >= fc.cum[2]);
@@ -294,6 +300,6 @@ __device__ __forceinline__ double fast_draw(const DevModel& M, const pxb_thermal
     tab = max(chosen, 0);
   }
   uint32_t v;
-  const int j = alias_pick(alias_row(t, tab, row), (unsigned)t->nbins, w0, w1, v);
+  const int j = alias_pick(t->alias, alias_row_index(t, tab, row), (unsigned)t->nbins, w0, w1, v);
   return alias_energy<SPEC>(M, j, v);
 }

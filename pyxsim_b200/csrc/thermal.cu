@@ -122,8 +122,10 @@ static int build_table(pxb_model* m, const pxb_table_desc& d, DevTable& t) {
     row_sums(d.var, (int64_t)t.nrows * d.nvar, d.nbins, rs, &t.nonneg);
     if ((rc = upload(m, rs.data(), rs.size() * sizeof(double), (const void**)&t.rs_v))) return rc;
   }
-  if (t.nonneg && d.nbins < 65536) {
-    // one alias table per (table, row) for the mixture sampler
+  // one alias table per (table, row) for the mixture sampler (entries are addressed by 32-bit
+  // element indices: sampling.cuh, alias_row_index)
+  if (t.nonneg && d.nbins < 65536 &&
+      (size_t)(2 + d.nvar) * t.nrows * (((size_t)d.nbins + 1) & ~(size_t)1) < ((size_t)1 << 31)) {
     const int ntab = 2 + d.nvar;
     const size_t nb = (size_t)d.nbins;
     const size_t as = (nb + 1) & ~(size_t)1;
