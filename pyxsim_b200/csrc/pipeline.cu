@@ -30,7 +30,15 @@
 enum { MODE_SAMPLE = 0, MODE_PROJECT = 1, MODE_FUSED = 2 };
 
 constexpr int PL_WARPS = 32;                       // warps of a persistent CTA holding staged rows
-constexpr int PL_WARPS_SMALL = 8;                  // warps of a CTA that stages nothing (4 CTAs per SM)
+#ifndef PXB_STATS_IN_SCATTER
+#define PXB_STATS_IN_SCATTER 0
+#endif
+#ifndef PXB_SMALL_WARPS
+#define PXB_SMALL_WARPS 8
+#endif
+constexpr int PL_WARPS_SMALL = PXB_SMALL_WARPS;     // warps of a CTA that stages nothing (32 warps per SM)
+constexpr int PL_SMALL_PER_SM = 32 / PL_WARPS_SMALL;
+static_assert(PL_WARPS_SMALL * PL_SMALL_PER_SM == 32 && PL_WARPS_SMALL < PL_WARPS, "small CTAs fill 32 warps per SM");
 constexpr int PL_EPOCH = 16;                       // tiles per warp between two staging decisions
 
 // Tile geometry per mode.  A warp tile is ROUNDS x 32 pair slots.  The sampler keeps nothing
@@ -50,6 +58,11 @@ struct Tiling {
   static constexpr int TSLOTS = 32 * ROUNDS;       // pair slots per warp tile
   static constexpr int MAXC = TSLOTS + 4;          // cell starts staged per tile
   static constexpr int NBUF = MODE == 0 ? 1 : 2;
+  // one tile buffer of a warp in shared memory: [energies of the tile's photons (projecting modes)
+  // | MAXC cell starts | first cell c0 of the tile], addressed as 32-bit shared-memory offsets
+  static constexpr unsigned EBYTES = MODE == 0 ? 0u : 2u * TSLOTS * (unsigned)sizeof(double);
+  static constexpr unsigned BSTRIDE = EBYTES + MAXC * 4u + 16u;
+  static_assert(BSTRIDE % 16 == 0 && (EBYTES + MAXC * 4u) % 16 == 0, "16-byte aligned tile buffers");
 };
 static inline int tslots_of(int mode) { return mode == 0 ? Tiling<0>::TSLOTS : Tiling<1>::TSLOTS; }
 
@@ -86,7 +99,7 @@ struct PipeArgs {
   double* part_sum;           // [n_tiles] per-tile partial statistics
   double* part_min;
   double* part_max;
-  int off_e, off_qs;          // byte offsets of the per-warp scratch in dynamic shared memory
+  int off_w;                  // byte offset of the per-warp tile buffers in dynamic shared memory
   int f32;                    // events are written as float (xsky / ysky minus sky0 / sky1)
   double sky0, sky1;
 };
@@ -124,6 +137,29 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         : "r"(smem_u32(bar)), "r"(parity)
         : "memory");
   }
+}
+
+// shared memory through 32-bit addresses (volatile: ordered among themselves and kept where
+// they are written; the buffers are private to a warp, __syncwarp() separates writers and readers)
+__device__ __forceinline__ int lds_s32(unsigned a) {
+  int v;
+  asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ void sts_s32(unsigned a, int v) {
+  asm volatile("st.shared.s32 [%0], %1;" ::"r"(a), "r"(v));
+}
+__device__ __forceinline__ void lds_f64x2(unsigned a, double& x, double& y) {
+  asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(x), "=d"(y) : "r"(a));
+}
+__device__ __forceinline__ void sts_f64x2(unsigned a, double x, double y) {
+  asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(a), "d"(x), "d"(y));
+}
+__device__ __forceinline__ void lds_s64x2(unsigned a, long long& x, long long& y) {
+  asm volatile("ld.shared.v2.s64 {%0, %1}, [%2];" : "=l"(x), "=l"(y) : "r"(a));
+}
+__device__ __forceinline__ void sts_s64x2(unsigned a, long long x, long long y) {
+  asm volatile("st.shared.v2.s64 [%0], {%1, %2};" ::"r"(a), "l"(x), "l"(y));
 }
 
 // ---------------------------------------------------------------------------------------
@@ -427,14 +463,16 @@ k_thermal_sample_cta(const DevModel M, const __grid_constant__ pxb_thermal_cells
 // WARPS: warps per CTA -- 32 (one persistent CTA per SM, room for the staged rows) or 8 (four CTAs
 // per SM, nothing staged: while one CTA sits at a barrier the others issue).
 template <int MODE, int SPEC, int WARPS>
-__global__ void __launch_bounds__(WARPS * 32, WARPS == PL_WARPS ? 1 : 4)
+__global__ void __launch_bounds__(WARPS * 32, WARPS == PL_WARPS ? 1 : PL_SMALL_PER_SM)
 k_pipeline(const DevModel M, const __grid_constant__ pxb_thermal_cells C,
            const __grid_constant__ pxb_project_params P, const __grid_constant__ PhiloxKeys RKE,
            const __grid_constant__ PhiloxKeys RKP, const __grid_constant__ PipeArgs A,
            const SkyConst K) {
   constexpr int ROUNDS = Tiling<MODE>::ROUNDS, TSLOTS = Tiling<MODE>::TSLOTS;
   constexpr int MAXC = Tiling<MODE>::MAXC, NBUF = Tiling<MODE>::NBUF;
-  // dynamic shared memory: [4 staged alias rows | per-warp energies | per-warp cell starts]
+  constexpr unsigned EBYTES = Tiling<MODE>::EBYTES, BSTRIDE = Tiling<MODE>::BSTRIDE;
+  constexpr unsigned HDR = EBYTES + MAXC * 4u;        // first cell of the buffer's tile (16 bytes)
+  // dynamic shared memory: [4 staged alias rows | per-warp tile buffers (Tiling<MODE>)]
   extern __shared__ __align__(128) unsigned char dyn[];
   const DevTable& T = M.prim;
   uint2* s_alias = reinterpret_cast<uint2*>(dyn);
@@ -446,26 +484,38 @@ k_pipeline(const DevModel M, const __grid_constant__ pxb_thermal_cells C,
   __shared__ long long s_lbj, s_lbprefix;              // warp 0: look-back progress of the pending batch
   __shared__ WabsFast s_wabs;
 
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  // (32-bit offsets into the dynamic shared memory: the buffers are addressed as shared memory)
-  const unsigned se_off = (unsigned)A.off_e + (unsigned)wid * (unsigned)(NBUF * 2 * TSLOTS * sizeof(double));
-  const unsigned qs_off = (unsigned)A.off_qs + (unsigned)wid * (unsigned)(NBUF * MAXC * sizeof(int));
+  // (lane and the warp's buffer address are pinned in registers: read through volatile asm, the
+  // compiler cannot re-derive them from the thread index at every use)
+  unsigned lane, wbase;
+  asm volatile("mov.u32 %0, %%laneid;" : "=r"(lane));
+  const int wid = threadIdx.x >> 5;
+  {
+    const unsigned w0 = smem_u32(dyn) + (unsigned)A.off_w + (unsigned)wid * (unsigned)(NBUF * BSTRIDE);
+    asm volatile("mov.u32 %0, %1;" : "=r"(wbase) : "r"(w0));
+  }
   if (MODE != MODE_SAMPLE && P.absorb_kind == PXB_ABS_WABS) wabs_fast_init(s_wabs);
   if (threadIdx.x == 0) mbar_init(&s_bar, 1);
   __syncthreads();
   int tag = -1;
   uint32_t parity = 0;
-  const unsigned lt = (1u << lane) - 1u;
   const bool absorb = MODE != MODE_SAMPLE && P.absorb_kind != PXB_ABS_NONE;
-  const bool staging = MODE != MODE_PROJECT && A.use_staging;
+  // rows are staged by the big CTAs only
+  const bool staging = WARPS == PL_WARPS && MODE != MODE_PROJECT && A.use_staging;
 
-  // (cell relative to c0, pair index inside the cell) of slot r*32 + lane of a tile
-  auto locate = [&](int how, unsigned relpack, const int* s_qs, int64_t slot0, int nslots, int64_t c0,
-                    int64_t c1, int64_t m00, int r, int srel, int& rel, int64_t& m) {
-    if (how != 2) {
+  // (cell relative to c0, pair index inside the cell) of slot r*32 + lane of a tile: from the
+  // packed ranks and the staged cell starts -- or, relpack == REL_SEARCH (lists with empty cells,
+  // which the ballot look-up cannot rank; a first cell that starts 2^30 slots before the tile), by
+  // bisection in the global offsets
+  constexpr unsigned REL_SEARCH = 0xffffffffu;          // (no rank byte is 255: MAXC < 255)
+  auto locate = [&](unsigned relpack, unsigned bb, int64_t tile, int64_t c0, int r, int srel,
+                    int& rel, int64_t& m) {
+    if (relpack != REL_SEARCH) {
       rel = (int)((relpack >> (8 * r)) & 255u);
-      m = rel == 0 ? m00 + srel : (int64_t)(srel - s_qs[rel]);
+      m = (int64_t)(srel - lds_s32(bb + EBYTES + 4u * (unsigned)rel));
     } else {
+      const int64_t slot0 = tile * TSLOTS;
+      const int nslots = (int)min((int64_t)TSLOTS, A.n_pairs - slot0);
+      const int64_t c1 = (tile + 1 < A.n_tiles) ? __ldg(A.tile_cell + tile + 1) : A.n_cells - 1;
       const int64_t slot = slot0 + min(srel, nslots - 1);
       int64_t lo = c0, hi = c1 + 1;   // qoff[lo] <= slot < qoff[hi]
       while (hi - lo > 1) {
@@ -478,44 +528,43 @@ k_pipeline(const DevModel M, const __grid_constant__ pxb_thermal_cells C,
   };
 
   // ---- a tile's decisions: energies (sampled or loaded), Doppler shift, absorption -------------
-  // (writes the tile's energies and cell starts into buffer `buf`; returns its survivor count and
-  // the per-lane survivor bits / cell bytes the scatter step needs)
-  auto decide = [&](int64_t tile, int buf, int& run, int& how, unsigned& bits, unsigned& rels) {
-    double* const s_e = reinterpret_cast<double*>(dyn + se_off + (unsigned)buf * (unsigned)(2 * TSLOTS * sizeof(double)));
-    int* const s_qs = reinterpret_cast<int*>(dyn + qs_off + (unsigned)buf * (unsigned)(MAXC * sizeof(int)));
+  // (writes the tile's energies, cell starts and first cell into buffer `buf`; returns its survivor
+  // count and the per-lane survivor bits / cell ranks the scatter step needs)
+  auto decide = [&](int64_t tile, int buf, int& run, unsigned& bits, unsigned& rels) {
+    const unsigned bb = wbase + (unsigned)buf * BSTRIDE;
     const int64_t slot0 = tile * TSLOTS;
     const int nslots = (int)min((int64_t)TSLOTS, A.n_pairs - slot0);
     const int64_t c0 = __ldg(A.tile_cell + tile);
-    const int64_t c1 = (tile + 1 < A.n_tiles) ? __ldg(A.tile_cell + tile + 1) : A.n_cells - 1;
-    // cell starts of the tile, relative to its first slot (the first cell's is clamped to -1:
-    // only the order matters for the look-up).
-    // how = 0: every cell of the tile is non-empty -> ballot look-up; 1: empty cells (lists
-    // from elsewhere) -> shared-memory bisection; 2: more cells than fit -> global bisection.
-    const int64_t ncl = c1 - c0 + 1;
-    const int nc = ncl <= MAXC ? (int)ncl : 0;
-    how = nc == 0 ? 2 : 0;
-    const int64_t m00 = slot0 - __ldg(A.qoff + c0);      // pair index of slot 0 inside cell c0
-    __syncwarp();
+    // cell starts of the tile, relative to its first slot (the first cell's is <= 0)
+    int nc;
     {
-      bool dup = false;
-      for (int q = lane; q < nc; q += 32) {
-        const int64_t a = __ldg(A.qoff + c0 + q) - slot0, b = __ldg(A.qoff + c0 + q + 1) - slot0;
-        s_qs[q] = (int)max(a, (int64_t)-1);
-        dup |= (a == b);
-      }
-      if (how == 0 && __any_sync(0xffffffffu, dup)) how = 1;
+      const int64_t c1 = (tile + 1 < A.n_tiles) ? __ldg(A.tile_cell + tile + 1) : A.n_cells - 1;
+      const int64_t ncl = c1 - c0 + 1;
+      nc = ncl <= MAXC ? (int)ncl : 0;
     }
     __syncwarp();
-    // Cell of every pair slot of the tile, relative to c0, for all rounds at once (one byte
-    // per round; MAXC < 256).  how = 0: the cell of a slot is the number of cells starting at
-    // or before it, minus one -- a ballot for the cells that start before the round's 32
-    // slots plus a warp-wide OR of start bits inside them.
-    unsigned relpack = 0;
-    if (how == 0) {
+    bool search = nc == 0;
+    {
+      bool bad = false;
+      for (int q = (int)lane; q < nc; q += 32) {
+        const int64_t a = __ldg(A.qoff + c0 + q) - slot0, b = __ldg(A.qoff + c0 + q + 1) - slot0;
+        sts_s32(bb + EBYTES + 4u * (unsigned)q, (int)a);
+        bad |= (a == b) || a < -(int64_t)(1 << 30);      // empty cell; start too far back for 32 bits
+      }
+      if (__any_sync(0xffffffffu, bad)) search = true;
+      if (MODE != MODE_SAMPLE && lane == 0) sts_s64x2(bb + HDR, c0, 0ll);
+    }
+    __syncwarp();
+    // Rank of the cell of every pair slot of the tile among the staged cells, for all rounds at
+    // once (one byte per round; MAXC < 255): the number of cells starting at or before the slot,
+    // minus one -- a ballot for the cells that start before the round's 32 slots plus a warp-wide
+    // OR of start bits inside them.
+    unsigned relpack = REL_SEARCH;
+    if (!search) {
       unsigned cnt = 0;
       for (int qb = 0; qb < nc; qb += 32) {
-        const int q = qb + lane;
-        const int qs = q < nc ? s_qs[q] : 0x7fffffff;
+        const int q = qb + (int)lane;
+        const int qs = q < nc ? lds_s32(bb + EBYTES + 4u * (unsigned)q) : 0x7fffffff;
 #pragma unroll
         for (int r = 0; r < ROUNDS; ++r) {
           const unsigned before = __ballot_sync(0xffffffffu, qs < r * 32);
@@ -525,29 +574,20 @@ k_pipeline(const DevModel M, const __grid_constant__ pxb_thermal_cells C,
         }
       }
       relpack = cnt - (0x01010101u >> (8 * (4 - ROUNDS)));   // (every byte in use is >= 1)
-    } else if (how == 1) {
-#pragma unroll
-      for (int r = 0; r < ROUNDS; ++r) {
-        const int srel = min(r * 32 + lane, nslots - 1);
-        int rel = 0;   // largest q with s_qs[q] <= srel
-        for (int step = 128; step > 0; step >>= 1) {
-          const int q = rel + step;
-          if (q < nc && s_qs[q] <= srel) rel = q;
-        }
-        relpack |= (unsigned)rel << (8 * r);
-      }
     }
 
     unsigned detpack = 0;
+#if !PXB_STATS_IN_SCATTER
     double tsum = 0.0, tmin = 1.0e99, tmax = -1.0e99;
+#endif
 #pragma unroll 1
     for (int r = 0; r < ROUNDS; ++r) {
       if (r * 32 >= nslots) break;
-      const int srel = r * 32 + lane;
+      const int srel = r * 32 + (int)lane;
       const bool valid = srel < nslots;
       int rel;
       int64_t m;
-      locate(how, relpack, s_qs, slot0, nslots, c0, c1, m00, r, srel, rel, m);
+      locate(relpack, bb, tile, c0, r, srel, rel, m);
       PXB_DASSERT(rel >= 0 && c0 + rel < A.n_cells && (!valid || m >= 0));
       const CellRec* rp = A.recs + (c0 + rel);
       const longlong2 q0 = __ldg(reinterpret_cast<const longlong2*>(rp));
@@ -610,11 +650,11 @@ k_pipeline(const DevModel M, const __grid_constant__ pxb_thermal_cells C,
                 row = fast_row(tb, z1, meta & 7, comp);
               }
               const uint32_t w0 = h ? E.z : E.x, w1 = h ? E.w : E.y;
-              const unsigned dr = (unsigned)(row - tag);
               uint32_t v;
               int j;
               PXB_DASSERT(tab >= 0 && tab < 2 + C.nvar && row >= 0 && row < tb->nrows);
-              if (prim && tab < 2 && tag >= 0 && dr < 2u)   // staged row: shared-memory gather
+              const unsigned dr = (unsigned)(row - tag);
+              if (WARPS == PL_WARPS && prim && tab < 2 && tag >= 0 && dr < 2u)   // staged row: shared-memory gather
                 j = alias_pick(s_alias, (unsigned)(tab * 2 + (int)dr) * (unsigned)T.alias_stride,
                                (unsigned)T.nbins, w0, w1, v);
               else
@@ -675,8 +715,8 @@ k_pipeline(const DevModel M, const __grid_constant__ pxb_thermal_cells C,
         if (detA) detA = absorb_decision<SPEC>(P, RKP, s_wabs, c0 + rel, gid, d0, Aw.x, Dw.x, eA);
         if (detB) detB = absorb_decision<SPEC>(P, RKP, s_wabs, c0 + rel, gid, d0 + 1, Aw.y, Dw.y, eB);
       }
-      s_e[2 * srel] = eA;
-      s_e[2 * srel + 1] = eB;
+      sts_f64x2(bb + 16u * (unsigned)srel, eA, eB);
+#if !PXB_STATS_IN_SCATTER
       if (detA) {
         tsum += eA;
         tmin = eA < tmin ? eA : tmin;   // (energies are never NaN: plain compares)
@@ -687,11 +727,13 @@ k_pipeline(const DevModel M, const __grid_constant__ pxb_thermal_cells C,
         tmin = eB < tmin ? eB : tmin;
         tmax = eB > tmax ? eB : tmax;
       }
+#endif
       run += __popc(__ballot_sync(0xffffffffu, detA)) + __popc(__ballot_sync(0xffffffffu, detB));
       detpack |= ((detA ? 1u : 0u) | (detB ? 2u : 0u)) << (2 * r);
     }
 
     if (MODE != MODE_SAMPLE) {
+#if !PXB_STATS_IN_SCATTER
       tsum = warp_sum(tsum);
       tmin = warp_min(tmin);
       tmax = warp_max(tmax);
@@ -700,41 +742,35 @@ k_pipeline(const DevModel M, const __grid_constant__ pxb_thermal_cells C,
         A.part_min[tile] = tmin;
         A.part_max[tile] = tmax;
       }
+#endif
       bits = detpack;
       rels = relpack;
     }
   };
 
   // ---- a tile's scatter step: survivors -> their final, order-preserving slots ------------------
-  auto scatter = [&](int64_t ptile, int pbuf, int64_t base, int phow, unsigned detpack, unsigned relpack) {
-    const double* const s_e = reinterpret_cast<const double*>(dyn + se_off + (unsigned)pbuf * (unsigned)(2 * TSLOTS * sizeof(double)));
-    const int* const s_qs = reinterpret_cast<const int*>(dyn + qs_off + (unsigned)pbuf * (unsigned)(MAXC * sizeof(int)));
-    const int64_t slot0 = ptile * TSLOTS;
-    const int nslots = (int)min((int64_t)TSLOTS, A.n_pairs - slot0);
-    const int64_t c0 = __ldg(A.tile_cell + ptile);
-    const int64_t c1 = (ptile + 1 < A.n_tiles) ? __ldg(A.tile_cell + ptile + 1) : A.n_cells - 1;
-    const int64_t m00 = slot0 - __ldg(A.qoff + c0);
-    // (tile-uniform 64-bit bases, 32-bit offsets inside the tile; float events: half the bytes)
-    const int64_t ob = A.f32 ? base / 2 : base;         // (float arrays: base counts 4-byte slots)
-    double* const xb = A.xsky + ob;
-    double* const yb = A.ysky + ob;
-    double* const eb = A.eobs + ob;
-    double* const lb = A.los ? A.los + ob : nullptr;
-    const int fo = (int)(base & 1);
+  auto scatter = [&](int64_t ptile, int pbuf, int64_t base, unsigned detpack, unsigned relpack) {
+    const unsigned bb = wbase + (unsigned)pbuf * BSTRIDE;
+    long long c0, unused;
+    lds_s64x2(bb + HDR, c0, unused);
+    // (float events: half the bytes -- the float arrays are indexed from the same pointers)
+    const unsigned lt = (1u << lane) - 1u;
     int done = 0;
+#if PXB_STATS_IN_SCATTER
+    double tsum = 0.0, tmin = 1.0e99, tmax = -1.0e99;   // the tile's survivors: flux / emin / emax partials
+#endif
 #pragma unroll 1
     for (int r = 0; r < ROUNDS; ++r) {
-      if (r * 32 >= nslots) break;
       const bool detA = (detpack >> (2 * r)) & 1u, detB = (detpack >> (2 * r + 1)) & 1u;
       const unsigned balA = __ballot_sync(0xffffffffu, detA), balB = __ballot_sync(0xffffffffu, detB);
       if (!(balA | balB)) continue;
       const int o0 = done + __popc(balA & lt) + __popc(balB & lt);
       done += __popc(balA) + __popc(balB);
       if (!(detA || detB)) continue;
-      const int srel = r * 32 + lane;
+      const int srel = r * 32 + (int)lane;
       int rel;
       int64_t m;
-      locate(phow, relpack, s_qs, slot0, nslots, c0, c1, m00, r, srel, rel, m);
+      locate(relpack, bb, ptile, c0, r, srel, rel, m);
       const uint64_t gid = (uint64_t)__ldg(&A.recs[c0 + rel].gid);
       const uint64_t d0 = 2ull * (uint64_t)m;
       const CellGeom g = ld_geom(A.geom + c0 + rel);
@@ -744,6 +780,8 @@ k_pipeline(const DevModel M, const __grid_constant__ pxb_thermal_cells C,
       Philox4 Aw{0u, 0u, 0u, 0u};
       if (SPEC == 2 || (SPEC == 0 && !(P.observer == 0 && P.data_type == 0 && P.vn_axis >= 0)))
         Aw = pxb_rand4(RKP, STREAM_PROJ_A, gid, (uint64_t)m);
+      double eA, eB;
+      lds_f64x2(bb + 16u * (unsigned)srel, eA, eB);
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
         if (!(h ? detB : detA)) continue;
@@ -753,22 +791,38 @@ k_pipeline(const DevModel M, const __grid_constant__ pxb_thermal_cells C,
           scatter_external<SPEC>(P, RKP, g, K, w0, w1, w2, gid, d0 + h, xs, ys, los);
         else
           scatter_allsky(P, RKP, g, w0, w1, w2, gid, d0 + h, xs, ys, los);
-        const int o = o0 + (h && detA ? 1 : 0);
-        PXB_DASSERT(o >= 0 && base + o < A.n_photons && srel < TSLOTS);   // events never outnumber photons
+        const int64_t o = base + o0 + (h && detA ? 1 : 0);
+        PXB_DASSERT(o >= 0 && o < A.n_photons && srel < TSLOTS);   // events never outnumber photons
+        const double ev = h ? eB : eA;
+#if PXB_STATS_IN_SCATTER
+        tsum += ev;
+        tmin = ev < tmin ? ev : tmin;   // (energies are never NaN: plain compares)
+        tmax = ev > tmax ? ev : tmax;
+#endif
         if (!A.f32) {
-          st_stream(xb + o, xs);
-          st_stream(yb + o, ys);
-          st_stream(eb + o, s_e[2 * srel + h]);
-          if (lb) st_stream(lb + o, los);
+          st_stream(A.xsky + o, xs);
+          st_stream(A.ysky + o, ys);
+          st_stream(A.eobs + o, ev);
+          if (A.los) st_stream(A.los + o, los);
         } else {
           // sky offsets from the fp64 centre and energies in single precision
-          __stcs(reinterpret_cast<float*>(xb) + fo + o, (float)(xs - A.sky0));
-          __stcs(reinterpret_cast<float*>(yb) + fo + o, (float)(ys - A.sky1));
-          __stcs(reinterpret_cast<float*>(eb) + fo + o, (float)s_e[2 * srel + h]);
-          if (lb) __stcs(reinterpret_cast<float*>(lb) + fo + o, (float)los);
+          __stcs(reinterpret_cast<float*>(A.xsky) + o, (float)(xs - A.sky0));
+          __stcs(reinterpret_cast<float*>(A.ysky) + o, (float)(ys - A.sky1));
+          __stcs(reinterpret_cast<float*>(A.eobs) + o, (float)ev);
+          if (A.los) __stcs(reinterpret_cast<float*>(A.los) + o, (float)los);
         }
       }
     }
+#if PXB_STATS_IN_SCATTER
+    tsum = warp_sum(tsum);
+    tmin = warp_min(tmin);
+    tmax = warp_max(tmax);
+    if (lane == 0) {
+      A.part_sum[ptile] = tsum;
+      A.part_min[ptile] = tmin;
+      A.part_max[ptile] = tmax;
+    }
+#endif
   };
 
   // the rows of the temperature bin the grid is working in are (re)staged; every thread of the CTA
@@ -822,9 +876,9 @@ k_pipeline(const DevModel M, const __grid_constant__ pxb_thermal_cells C,
         if (!staging) break;
         continue;
       }
-      int run = 0, how = 0;
+      int run = 0;
       unsigned bits = 0, rels = 0;
-      decide(tile, 0, run, how, bits, rels);
+      decide(tile, 0, run, bits, rels);
     }
     return;
   }
@@ -841,7 +895,6 @@ k_pipeline(const DevModel M, const __grid_constant__ pxb_thermal_cells C,
   int buf = 0;
   bool have_pend = false;      // this warp's tile of the previous batch still has its scatter step due
   unsigned pend_bits = 0, pend_rels = 0;
-  int pend_how = 0;
   bool lbdone = true, cta_out = false, pend_batch = false;
   for (int it = 0;; ++it) {
     if (threadIdx.x == 0) s_batch[buf] = cta_out ? -1ll : (long long)atomicAdd(A.ticket, 1u);
@@ -851,9 +904,9 @@ k_pipeline(const DevModel M, const __grid_constant__ pxb_thermal_cells C,
     if (staging && !cta_out && (it & (PL_EPOCH - 1)) == 0) restage(batch * WARPS);
     const int64_t tile = batch * WARPS + wid;
     const bool have_new = !cta_out && tile < A.n_tiles;
-    int run = 0, how = 0;
+    int run = 0;
     unsigned bits = 0, rels = 0;
-    if (have_new) decide(tile, buf, run, how, bits, rels);
+    if (have_new) decide(tile, buf, run, bits, rels);
     if (lane == 0) s_cnt[buf][wid] = run;
     if (wid == 0 && pend_batch && !lbdone) {
       // the pending batch's prefix, for good now: it has had a whole batch's time
@@ -895,14 +948,20 @@ k_pipeline(const DevModel M, const __grid_constant__ pxb_thermal_cells C,
       const int64_t ptile = s_batch[buf ^ 1] * WARPS + wid;
       const int64_t base = s_base[buf ^ 1] + before;
       if (ptile == A.n_tiles - 1 && lane == 0) *A.n_events = base + mine;
-      if (mine > 0) scatter(ptile, buf ^ 1, base, pend_how, pend_bits, pend_rels);
+      if (mine > 0) scatter(ptile, buf ^ 1, base, pend_bits, pend_rels);
+#if PXB_STATS_IN_SCATTER
+      else if (lane == 0) {
+        A.part_sum[ptile] = 0.0;
+        A.part_min[ptile] = 1.0e99;
+        A.part_max[ptile] = -1.0e99;
+      }
+#endif
     }
     if (cta_out) break;          // nothing new was decided: the batch just scattered was the last
     have_pend = have_new;
     pend_batch = true;
     pend_bits = bits;
     pend_rels = rels;
-    pend_how = how;
     buf ^= 1;
   }
 }
@@ -995,7 +1054,7 @@ static PipeHeader pipe_header(char* ws, const PipeLayout& l) {
 
 // shared-memory plan of a k_pipeline launch
 struct SmemPlan {
-  int use_staging, off_e, off_qs, warps;
+  int use_staging, off_w, warps;
   size_t total;
 };
 // mode project stages nothing and runs small CTAs; sampling and the fused mode run one big CTA per
@@ -1004,22 +1063,20 @@ struct SmemPlan {
 static SmemPlan smem_plan(const DevModel* D, int mode, bool small_fused = false) {
   SmemPlan s;
   s.warps = (mode == MODE_PROJECT || (mode == MODE_FUSED && small_fused)) ? PL_WARPS_SMALL : PL_WARPS;
-  const size_t e_bytes = mode == MODE_SAMPLE ? 0
-                         : (size_t)s.warps * Tiling<1>::NBUF * 2 * Tiling<1>::TSLOTS * sizeof(double);
-  const size_t qs_bytes = mode == MODE_SAMPLE ? (size_t)s.warps * Tiling<0>::MAXC * sizeof(int)
-                                              : (size_t)s.warps * Tiling<1>::NBUF * Tiling<1>::MAXC * sizeof(int);
+  const size_t w_bytes = mode == MODE_SAMPLE
+                             ? (size_t)s.warps * Tiling<0>::NBUF * Tiling<0>::BSTRIDE
+                             : (size_t)s.warps * Tiling<1>::NBUF * Tiling<1>::BSTRIDE;
   size_t rows = 0;
   s.use_staging = 0;
   if (s.warps == PL_WARPS && mode != MODE_PROJECT && D && !D->density_dependent && !D->has_fb) {
     rows = 4 * (size_t)D->prim.alias_stride * sizeof(uint2);
     // rows are staged when the four of them fit beside the per-warp scratch
-    if (rows + e_bytes + qs_bytes + 2048 <= 227 * 1024) s.use_staging = 1;
+    if (rows + w_bytes + 2048 <= 227 * 1024) s.use_staging = 1;
     else rows = 0;
   }
   rows = (rows + 127) & ~(size_t)127;
-  s.off_e = (int)rows;
-  s.off_qs = (int)(rows + e_bytes);
-  s.total = rows + e_bytes + qs_bytes;
+  s.off_w = (int)rows;
+  s.total = rows + w_bytes;
   return s;
 }
 
@@ -1043,7 +1100,7 @@ static int launch_pipeline_w(const DevModel& D, const pxb_thermal_cells& C, cons
     attr_set = sp.total + 1;
   }
   // persistent CTAs: one per SM (big CTAs) or four per SM (small ones)
-  int64_t grid = (int64_t)pxb_sm_count() * (WARPS == PL_WARPS ? 1 : 4);
+  int64_t grid = (int64_t)pxb_sm_count() * (WARPS == PL_WARPS ? 1 : PL_SMALL_PER_SM);
   const int64_t enough = (A.n_tiles + WARPS - 1) / WARPS;
   if (grid > enough) grid = enough;
   const SkyConst K = make_sky_const(&P);
@@ -1189,8 +1246,7 @@ extern "C" int pxb_thermal_sample(const pxb_model* model, const pxb_thermal_cell
     A.n_tiles = lay.ntiles;
     A.ticket = H.ticket;
     A.energies = energies;
-    A.off_e = sp.off_e;
-    A.off_qs = sp.off_qs;
+    A.off_w = sp.off_w;
     pxb_project_params P0{};
     if (sample_is_common(D, cells)) rc = launch_pipeline<MODE_SAMPLE, 1>(D, *cells, P0, A, sp, st);
     else rc = launch_pipeline<MODE_SAMPLE, 0>(D, *cells, P0, A, sp, st);
@@ -1298,8 +1354,7 @@ extern "C" int pxb_project(const pxb_photon_list* L, const pxb_project_params* P
   PipeArgs A{};
   fill_project_args(A, ws, lay, H, L, P, xsky, ysky, eobs, los, n_events_out);
   A.energies = const_cast<double*>(L->energy);
-  A.off_e = sp.off_e;
-  A.off_qs = sp.off_qs;
+  A.off_w = sp.off_w;
   static const DevModel D0{};
   static const pxb_thermal_cells C0{};
   const int spec = project_spec(P);
@@ -1363,8 +1418,7 @@ extern "C" int pxb_make_events(const pxb_model* model, const pxb_thermal_cells* 
   A.tabcum = tabcum;
   A.tab_stride = tab_stride;
   A.use_staging = sp.use_staging;
-  A.off_e = sp.off_e;
-  A.off_qs = sp.off_qs;
+  A.off_w = sp.off_w;
   const int pspec = project_spec(P);
   const bool scommon = sample_is_common(D, cells);
   if (scommon && pspec == 1) rc = launch_pipeline<MODE_FUSED, 1>(D, *cells, *P, A, sp, st);
