@@ -598,9 +598,6 @@ k_pipeline(const DevModel M, const __grid_constant__ pxb_thermal_cells C,
       const bool hasB = valid && (int64_t)(d0 + 1) < q1.y;
       double eA = 0.0, eB = 0.0;
       bool elig = true;
-      // photon counts below 2^31 in every cell of the round (any cell in practice): 32-bit
-      // compares -- decided for the whole warp, so the 64-bit path is a branch not taken
-      const bool small = MODE != MODE_PROJECT && __all_sync(0xffffffffu, q1.y < 0x7fffffffll);
       if (MODE != MODE_PROJECT) {
         const longlong2 q2 = __ldg(reinterpret_cast<const longlong2*>(rp) + 2);
         const longlong2 q3 = __ldg(reinterpret_cast<const longlong2*>(rp) + 3);
@@ -618,14 +615,9 @@ k_pipeline(const DevModel M, const __grid_constant__ pxb_thermal_cells C,
             for (int h = 0; h < 2; ++h) {
               // (a cell's last pair may lack its second photon: that lane half repeats the first
               // one's look-ups instead of indexing past the cell's components)
-              const long long dd = (long long)d0 + ((h && hasB) ? 1 : 0);
-              int comp;
-              if (small) {
-                const int d32 = (int)dd;
-                comp = (d32 >= (int)cn0) + (d32 >= (int)cn1) + (d32 >= (int)cn2);
-              } else {
-                comp = (dd >= cn0) + (dd >= cn1) + (dd >= cn2);
-              }
+              // (eligible cells have fewer than 2^31 photons, fast_setup: 32-bit compares)
+              const int dd = (int)d0 + ((h && hasB) ? 1 : 0);
+              const int comp = (dd >= (int)cn0) + (dd >= (int)cn1) + (dd >= (int)cn2);
               int tab, row;
               if (four) {
                 // four components: (row0,cosmic), (row0,metal), (row1,cosmic), (row1,metal)
@@ -633,7 +625,7 @@ k_pipeline(const DevModel M, const __grid_constant__ pxb_thermal_cells C,
                 row = z1 + (comp >> 1);
               } else {
                 // general split: comp is the ROW, the table comes from the side array
-                const long long din = dd - (comp == 0 ? 0 : (comp == 1 ? cn0 : (comp == 2 ? cn1 : cn2)));
+                const long long din = dd - (comp == 0 ? 0 : (comp == 1 ? (int)cn0 : (comp == 2 ? (int)cn1 : (int)cn2)));
                 const int ntab = 2 + C.nvar;
                 const int64_t* tc = A.tabcum + (c0 + rel) * A.tab_stride + comp * ntab;
                 tab = 0;

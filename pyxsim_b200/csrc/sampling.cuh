@@ -50,7 +50,9 @@ __device__ __forceinline__ FastCell fast_setup(const DevModel& M, const pxb_ther
   const double xh = cell_xh(C, i);
   const double Z = cell_metal(C, i, xh);
   const DevTable* t = mx.t;
-  bool ok = mx.interior && (Z >= 0.0);
+  // (a cell with 2^31 photons or more goes to the general kernel: the photon kernels compare a
+  // photon's index inside its cell with the component counts in 32 bits)
+  bool ok = mx.interior && (Z >= 0.0) && N < 0x7fffffffll;
   // (explicit multiply-adds: the threshold mode below re-accumulates the same sums and relies on
   // reaching exactly these totals)
   double s[4] = {0.0, 0.0, 0.0, 0.0}, sraw[4] = {0.0, 0.0, 0.0, 0.0};
